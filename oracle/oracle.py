@@ -1,0 +1,517 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+CPU oracle for the Consenrich state-space hot path: ctypes wrappers around
+``oracle/ssm_oracle.c`` (a sequential C restatement of the loops in
+``/root/reference/src/consenrich/cconsenrich.pyx``) exposing the six native entry points
+with the reference's keyword signatures and return tuples:
+
+* ``cforwardPass``            <- cconsenrich.pyx:6393-6632
+* ``cbackwardPass``           <- cconsenrich.pyx:6635-6850
+* ``cforwardPassLevel``       <- cconsenrich.pyx:6853-7049
+* ``cbackwardPassLevel``      <- cconsenrich.pyx:7052-7150
+* ``cfixedBackgroundECMLevel``<- cconsenrich.pyx:7153-7657
+* ``cfixedBackgroundECM``     <- cconsenrich.pyx:7660-8442
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
+this module.  The product (``consenrich_b200``) never does.
+
+Parity pinning: ``tests/test_oracle_pinning.py`` checks this restatement (a) bit-for-bit
+against the reference itself (``oracle/_ref``, built by ``oracle/build_ref.sh`` from the
+unmodified ``cconsenrich.pyx``) whenever that build is present, (b) against golden vectors
+generated from that build (``tests/golden/``), and (c) against independent float64
+known-answer recursions of the kind the reference's own tests use
+(``tests/test_core.py:522-592``, tolerance 2e-6).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "libssm_oracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement (gcc, reference flags).  Returns the library path."""
+    src = os.path.join(_HERE, "ssm_oracle.c")
+    if force or (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
+    return _LIB_PATH
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("state_init", C.c_double),
+        ("cov_init", C.c_double),
+        ("pad", C.c_double),
+        ("F", C.c_double * 4),
+        ("Q0", C.c_double * 4),
+        ("lam_min", C.c_double),
+        ("lam_max", C.c_double),
+        ("kap_min", C.c_double),
+        ("kap_max", C.c_double),
+        ("apn_min_q", C.c_double),
+        ("apn_max_q", C.c_double),
+        ("apn_thresh", C.c_double),
+        ("apn_scale", C.c_double),
+        ("apn_pc", C.c_double),
+        ("use_lambda", C.c_int32),
+        ("use_kappa", C.c_int32),
+        ("use_qscale", C.c_int32),
+        ("use_apn", C.c_int32),
+        ("return_nll", C.c_int32),
+        ("store_nll_in_d", C.c_int32),
+        ("do_store", C.c_int32),
+        ("pad_", C.c_int32),
+    ]
+
+
+_lib = None
+
+
+def _L():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        fp, ip, dp, vp = (C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p)
+        for name in ("oracle_forward2", "oracle_forward1"):
+            f = getattr(_lib, name)
+            f.restype = C.c_int64
+            f.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, vp,
+                          C.POINTER(_Params), vp, vp, vp, vp, dp, dp]
+        _lib.oracle_backward2.restype = None
+        _lib.oracle_backward2.argtypes = [vp, C.c_int64, C.c_int64, dp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+        _lib.oracle_backward1.restype = None
+        _lib.oracle_backward1.argtypes = [vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+        _lib.oracle_update_lambda.restype = None
+        _lib.oracle_update_lambda.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp, C.c_int,
+                                              C.c_double, C.c_double, C.c_double, C.c_double, vp]
+        _lib.oracle_update_kappa2.restype = None
+        _lib.oracle_update_kappa2.argtypes = [C.c_int64, vp, C.c_int64, vp, vp, vp, dp, dp, vp,
+                                              C.c_double, C.c_double, C.c_double, vp]
+        _lib.oracle_update_kappa1.restype = None
+        _lib.oracle_update_kappa1.argtypes = [C.c_int64, vp, C.c_int64, vp, vp, vp, C.c_double, vp,
+                                              C.c_double, C.c_double, C.c_double, vp]
+        del fp, ip
+    return _lib
+
+
+def _f32(x):
+    """Round a Python scalar to C float and widen back, as Cython does for ``float`` args."""
+    return float(np.float32(x))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c32(a, name, ndim):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == ndim and a.flags.c_contiguous):
+        raise ValueError(f"{name}: Buffer dtype mismatch / not C-contiguous float32 ndim={ndim}")
+    return a
+
+
+def _coerce_qscale(q, n):
+    """cconsenrich.pyx:101-131 (_coerceProcessQScale)."""
+    arr = np.ascontiguousarray(q, dtype=np.float32).reshape(-1)
+    if arr.shape[0] != n:
+        raise ValueError("processQScale length must match intervalCount")
+    if n > 0:
+        a64 = arr.astype(np.float64)
+        if (~np.isfinite(a64) | (a64 <= 0.0)).any():
+            raise ValueError("processQScale must contain only positive finite values")
+        if abs(float(a64[0]) - 1.0) > 1.0e-6:
+            raise ValueError("processQScale[0] must be 1.0")
+    return arr
+
+
+def _check_bounds(lo, hi, is_obs):
+    """cconsenrich.pyx:143-151."""
+    if lo <= 0.0 or hi <= 0.0 or hi < lo:
+        if is_obs:
+            raise ValueError("observation precision multiplier bounds must satisfy 0 < min <= max")
+        raise ValueError("process precision multiplier bounds must satisfy 0 < min <= max")
+
+
+def _forward(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+             stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
+             returnNLL, storeNLLInD, lambdaExp, processPrecExp, useObs, useProc, useAPN,
+             lamMin, lamMax, kapMin, kapMax, apnMinQ, apnMaxQ, apnThresh, apnScale, apnPC, processQScale):
+    data = _c32(matrixData, "matrixData", 2)
+    munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
+    m, n = data.shape
+    do_store = stateForward is not None
+    use_lambda = bool(useObs and (lambdaExp is not None))
+    use_qscale = processQScale is not None
+    use_kappa = bool(useProc and (processPrecExp is not None) and ((not useAPN) or use_qscale))
+    qs = _coerce_qscale(processQScale, n) if use_qscale else None
+    if n <= 0 or m <= 0:
+        d = np.empty(n, dtype=np.float32) if vectorD is None else vectorD
+        return (np.float32(0.0), 0, d, 0.0) if returnNLL else (np.float32(0.0), 0, d)
+    if blockCount <= 0:
+        raise ValueError("blockCount must be positive")
+    if munc.shape[0] != m or munc.shape[1] != n:
+        raise ValueError("matrixPluginMuncInit shape must match matrixData shape")
+    Q0 = np.asarray(matrixQ0)
+    if dim == 2:
+        Fm = np.asarray(matrixF)
+        if Fm.shape[0] < 2 or Fm.shape[1] < 2:
+            raise ValueError("matrixF must have at least shape (2, 2)")
+        if Q0.shape[0] < 2 or Q0.shape[1] < 2:
+            raise ValueError("matrixQ0 must have at least shape (2, 2)")
+    else:
+        if Q0.shape[0] < 1 or Q0.shape[1] < 1:
+            raise ValueError("matrixQ0 must have at least shape (1, 1)")
+        if float(Q0[0, 0]) <= 0.0:
+            raise ValueError("matrixQ0[0, 0] must be positive")
+    lamMin, lamMax, kapMin, kapMax = map(_f32, (lamMin, lamMax, kapMin, kapMax))
+    _check_bounds(lamMin, lamMax, True)
+    _check_bounds(kapMin, kapMax, False)
+    bm = intervalToBlockMap
+    if bm.shape[0] < n:
+        raise ValueError("intervalToBlockMap length must match intervalCount")
+    if use_lambda and lambdaExp.shape[0] != n:
+        raise ValueError("lambdaExp length must match intervalCount")
+    if use_kappa and processPrecExp.shape[0] != n:
+        raise ValueError("processPrecExp length must match intervalCount")
+    if vectorD is None:
+        d = np.empty(n, dtype=np.float32)
+        vectorD = d
+    else:
+        d = vectorD
+        if d.shape[0] < n:
+            raise ValueError("vectorD length must match intervalCount")
+    p = _Params()
+    p.state_init, p.cov_init, p.pad = _f32(stateInit), _f32(stateCovarInit), _f32(pad)
+    if dim == 2:
+        p.F[0], p.F[1], p.F[2], p.F[3] = (float(Fm[0, 0]), float(Fm[0, 1]), float(Fm[1, 0]), float(Fm[1, 1]))
+        p.Q0[0], p.Q0[1], p.Q0[2], p.Q0[3] = (float(Q0[0, 0]), float(Q0[0, 1]), float(Q0[1, 0]), float(Q0[1, 1]))
+    else:
+        p.Q0[0] = float(Q0[0, 0])
+    p.lam_min, p.lam_max, p.kap_min, p.kap_max = lamMin, lamMax, kapMin, kapMax
+    p.apn_min_q, p.apn_max_q, p.apn_thresh, p.apn_scale, p.apn_pc = map(
+        _f32, (apnMinQ, apnMaxQ, apnThresh, apnScale, apnPC))
+    p.use_lambda, p.use_kappa, p.use_qscale, p.use_apn = int(use_lambda), int(use_kappa), int(use_qscale), int(bool(useAPN))
+    p.return_nll, p.store_nll_in_d, p.do_store = int(bool(returnNLL)), int(bool(storeNLLInD)), int(do_store)
+    sum_d, sum_nll = C.c_double(0.0), C.c_double(0.0)
+    fn = _L().oracle_forward2 if dim == 2 else _L().oracle_forward1
+    bad = fn(_ptr(data), _ptr(munc), m, n, _ptr(bm), int(blockCount),
+             _ptr(lambdaExp) if use_lambda else None, _ptr(processPrecExp) if use_kappa else None,
+             _ptr(qs), C.byref(p), _ptr(d),
+             _ptr(stateForward) if do_store else None, _ptr(stateCovarForward) if do_store else None,
+             _ptr(pNoiseForward) if do_store else None, C.byref(sum_d), C.byref(sum_nll))
+    if bad >= 0:
+        raise ValueError("intervalToBlockMap has out-of-range block id")
+    phi = np.float32(sum_d.value / float(n))
+    phi = float(phi)
+    if returnNLL:
+        return (phi, 0, vectorD, sum_nll.value)
+    return (phi, 0, vectorD)
+
+
+def cforwardPass(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                 stateInit, stateCovarInit, pad=1.0e-4, projectStateDuringFiltering=False,
+                 stateLowerBound=0.0, stateUpperBound=0.0, chunkSize=1000000, stateForward=None,
+                 stateCovarForward=None, pNoiseForward=None, vectorD=None, returnNLL=False,
+                 storeNLLInD=False, lambdaExp=None, processPrecExp=None,
+                 ECM_useObsPrecisionReweighting=True, ECM_useProcessPrecisionReweighting=True,
+                 ECM_useAPN=False, obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0,
+                 procPrecisionMultiplierMin=0.25, procPrecisionMultiplierMax=4.0, APN_minQ=1.0e-4,
+                 APN_maxQ=1000.0, APN_dStatThresh=5.0, APN_dStatScale=10.0, APN_dStatPC=2.0,
+                 processQScale=None):
+    return _forward(2, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                    stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
+                    returnNLL, storeNLLInD, lambdaExp, processPrecExp, ECM_useObsPrecisionReweighting,
+                    ECM_useProcessPrecisionReweighting, ECM_useAPN, obsPrecisionMultiplierMin,
+                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax,
+                    APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC, processQScale)
+
+
+def cforwardPassLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBlockMap, blockCount,
+                      stateInit, stateCovarInit, pad=1.0e-4, chunkSize=1000000, stateForward=None,
+                      stateCovarForward=None, pNoiseForward=None, vectorD=None, returnNLL=False,
+                      storeNLLInD=False, lambdaExp=None, processPrecExp=None,
+                      ECM_useObsPrecisionReweighting=True, ECM_useProcessPrecisionReweighting=True,
+                      ECM_useAPN=False, obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0,
+                      procPrecisionMultiplierMin=0.25, procPrecisionMultiplierMax=4.0, APN_minQ=1.0e-4,
+                      APN_maxQ=1000.0, APN_dStatThresh=5.0, APN_dStatScale=10.0, APN_dStatPC=2.0,
+                      processQScale=None):
+    return _forward(1, matrixData, matrixPluginMuncInit, None, matrixQ0, intervalToBlockMap, blockCount,
+                    stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
+                    returnNLL, storeNLLInD, lambdaExp, processPrecExp, ECM_useObsPrecisionReweighting,
+                    ECM_useProcessPrecisionReweighting, ECM_useAPN, obsPrecisionMultiplierMin,
+                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax,
+                    APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC, processQScale)
+
+
+def _backward(dim, matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward,
+              stateSmoothed, stateCovarSmoothed, lagCovSmoothed, postFitResiduals):
+    data = _c32(matrixData, "matrixData", 2)
+    m, n = data.shape
+    xs = stateSmoothed if stateSmoothed is not None else np.empty((n, dim), dtype=np.float32)
+    Ps = stateCovarSmoothed if stateCovarSmoothed is not None else np.empty((n, dim, dim), dtype=np.float32)
+    lag = lagCovSmoothed if lagCovSmoothed is not None else np.empty((max(n - 1, 1), dim, dim), dtype=np.float32)
+    res = postFitResiduals if postFitResiduals is not None else np.empty((n, m), dtype=np.float32)
+    if n <= 0:
+        return (xs, Ps, lag, res)
+    if dim == 2:
+        Fm = np.asarray(matrixF)
+        F = (C.c_double * 4)(float(Fm[0, 0]), float(Fm[0, 1]), float(Fm[1, 0]), float(Fm[1, 1]))
+        _L().oracle_backward2(_ptr(data), m, n, F, _ptr(stateForward), _ptr(stateCovarForward),
+                              _ptr(pNoiseForward), _ptr(xs), _ptr(Ps), _ptr(lag), int(lag.shape[0]), _ptr(res))
+    else:
+        _L().oracle_backward1(_ptr(data), m, n, _ptr(stateForward), _ptr(stateCovarForward),
+                              _ptr(pNoiseForward), _ptr(xs), _ptr(Ps), _ptr(lag), int(lag.shape[0]), _ptr(res))
+    return (xs, Ps, lag, res)
+
+
+def cbackwardPass(matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward, chunkSize=1000000,
+                  stateSmoothed=None, stateCovarSmoothed=None, lagCovSmoothed=None, postFitResiduals=None):
+    return _backward(2, matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward,
+                     stateSmoothed, stateCovarSmoothed, lagCovSmoothed, postFitResiduals)
+
+
+def cbackwardPassLevel(matrixData, stateForward, stateCovarForward, pNoiseForward, chunkSize=1000000,
+                       stateSmoothed=None, stateCovarSmoothed=None, lagCovSmoothed=None,
+                       postFitResiduals=None):
+    return _backward(1, matrixData, None, stateForward, stateCovarForward, pNoiseForward,
+                     stateSmoothed, stateCovarSmoothed, lagCovSmoothed, postFitResiduals)
+
+
+def _init_multiplier(init, n, lo, hi, what):
+    """Warm-start copy + clip, cconsenrich.pyx:7899-7923."""
+    if init is None:
+        return np.ones(n, dtype=np.float32)
+    arr = np.array(init, dtype=np.float32, copy=True, order="C").reshape(-1)
+    if arr.shape[0] != n:
+        raise ValueError(f"{what} length must match intervalCount")
+    if not np.all(np.isfinite(arr)):
+        raise ValueError(f"{what} must contain only finite values")
+    np.clip(arr, lo, hi, out=arr)
+    return arr
+
+
+def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+         stateInit, stateCovarInit, iters, rtol, pad, nu, lamMin, lamMax, kapMin, kapMax, useObs, useProc,
+         useAPN, apnMinQ, apnMaxQ, apnThresh, apnScale, apnPC, t_innerIters, returnIntermediates,
+         returnDiagnostics, lambdaExpInit, processPrecExpInit, trackOptimizationPath, processQScale):
+    """ECM driver, cconsenrich.pyx:7877-8442 (2-state) / 7188-7657 (level)."""
+    data = _c32(matrixData, "matrixData", 2)
+    munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
+    m, n = data.shape
+    use_qscale = processQScale is not None
+    lam = kap = None
+    if useObs:
+        lam = _init_multiplier(lambdaExpInit, n, lamMin, lamMax, "lambdaExpInit")
+    if useProc and ((not useAPN) or use_qscale):
+        kap = _init_multiplier(processPrecExpInit, n, kapMin, kapMax, "processPrecExpInit")
+    qs = _coerce_qscale(processQScale, n) if use_qscale else None
+    xf = np.empty((n, dim), np.float32)
+    Pf = np.empty((n, dim, dim), np.float32)
+    Qf = np.empty((n, dim, dim), np.float32)
+    xs = np.empty((n, dim), np.float32)
+    Ps = np.empty((n, dim, dim), np.float32)
+    lag = np.empty((max(n - 1, 1), dim, dim), np.float32)
+    res = np.empty((n, m), np.float32)
+    Q0 = np.asarray(matrixQ0)
+    rtol_d, pad_d, nu_d = _f32(rtol), _f32(pad), _f32(nu)
+    lamMin_d, lamMax_d, kapMin_d, kapMax_d = map(_f32, (lamMin, lamMax, kapMin, kapMax))
+    patience = 2
+    path = [] if trackOptimizationPath else None
+
+    fkw = dict(matrixData=data, matrixPluginMuncInit=munc, matrixQ0=matrixQ0,
+               intervalToBlockMap=intervalToBlockMap, blockCount=blockCount, stateInit=stateInit,
+               stateCovarInit=stateCovarInit, pad=pad, chunkSize=0, lambdaExp=lam, processPrecExp=kap,
+               ECM_useObsPrecisionReweighting=useObs, ECM_useProcessPrecisionReweighting=useProc,
+               ECM_useAPN=useAPN, obsPrecisionMultiplierMin=lamMin, obsPrecisionMultiplierMax=lamMax,
+               procPrecisionMultiplierMin=kapMin, procPrecisionMultiplierMax=kapMax, APN_minQ=apnMinQ,
+               APN_maxQ=apnMaxQ, APN_dStatThresh=apnThresh, APN_dStatScale=apnScale, APN_dStatPC=apnPC,
+               processQScale=qs)
+    if dim == 2:
+        fkw["matrixF"] = matrixF
+        fwd, bwd = cforwardPass, cbackwardPass
+        bkw = dict(matrixData=data, matrixF=matrixF)
+    else:
+        fwd, bwd = cforwardPassLevel, cbackwardPassLevel
+        bkw = dict(matrixData=data)
+
+    def sweep():
+        nonlocal xs, Ps, lag, res
+        fwd(**fkw, stateForward=xf, stateCovarForward=Pf, pNoiseForward=Qf, vectorD=None,
+            returnNLL=False, storeNLLInD=False)
+        xs, Ps, lag, res = bwd(**bkw, stateForward=xf, stateCovarForward=Pf, pNoiseForward=Qf, chunkSize=0,
+                               stateSmoothed=xs, stateCovarSmoothed=Ps, lagCovSmoothed=lag,
+                               postFitResiduals=res)
+
+    def nll_only():
+        return float(fwd(**fkw, stateForward=None, stateCovarForward=None, pNoiseForward=None,
+                         vectorD=None, returnNLL=True, storeNLLInD=False)[3])
+
+    def validate():
+        if blockCount <= 0:
+            raise ValueError("blockCount must be positive")
+        if dim == 1:
+            if munc.shape[0] != m or munc.shape[1] != n:
+                raise ValueError("matrixPluginMuncInit shape must match matrixData shape")
+            if float(Q0[0, 0]) <= 0.0:
+                raise ValueError("matrixQ0[0, 0] must be positive")
+        _check_bounds(lamMin_d, lamMax_d, True)
+        _check_bounds(kapMin_d, kapMax_d, False)
+        if intervalToBlockMap.shape[0] < n:
+            raise ValueError("intervalToBlockMap length must match intervalCount")
+        if dim == 2:
+            if munc.shape[0] != m or munc.shape[1] != n:
+                raise ValueError("matrixPluginMuncInit shape must match matrixData shape")
+            det = float(Q0[0, 0]) * float(Q0[1, 1]) - float(Q0[0, 1]) * float(Q0[1, 0])
+            if det == 0.0:
+                raise ValueError("matrixQ0 is singular")
+
+    def pack(iters_done, nll, diag):
+        if returnIntermediates:
+            out = (iters_done, float(nll), xs, Ps, lag, res, lam, kap)
+            return out + (diag,) if returnDiagnostics else out
+        return (iters_done, float(nll), diag) if returnDiagnostics else (iters_done, float(nll))
+
+    if n <= 5:  # pyx:7998-8129: filter + smoother only
+        cur = 0.0
+        if n > 0 and m > 0:
+            validate()
+            sweep()
+            cur = nll_only()
+        diag = {
+            "iters_done": 0, "max_iters": int(iters), "converged": False, "skipped": True,
+            "skip_reason": "too_few_intervals" if n > 0 else "empty_input",
+            "fallback": "filter_smoother_only", "stable_iters": 0, "patience_target": patience,
+            "initial_nll": float(cur), "final_nll": float(cur), "final_abs_rel_change": None,
+            "final_rel_improvement": None, "nll_increase_count": 0,
+        }
+        if trackOptimizationPath:
+            diag["optimization_path"] = path
+        return pack(0, cur, diag)
+
+    validate()
+    Fd = None
+    if dim == 2:
+        Fm = np.asarray(matrixF)
+        Fd = (C.c_double * 4)(float(Fm[0, 0]), float(Fm[0, 1]), float(Fm[1, 0]), float(Fm[1, 1]))
+        Qd = (C.c_double * 4)(float(Q0[0, 0]), float(Q0[0, 1]), float(Q0[1, 0]), float(Q0[1, 1]))
+    prev, cur, init_nll = 1.0e16, 0.0, 0.0
+    has_init = False
+    iters_done = stable = inc = 0
+    converged = False
+    rel_impr = abs_rel = 0.0
+    L = _L()
+    for i in range(int(iters)):
+        iters_done = i + 1
+        for _ in range(int(t_innerIters)):
+            sweep()
+            if useObs:
+                L.oracle_update_lambda(_ptr(data), _ptr(munc), m, n, _ptr(intervalToBlockMap), int(blockCount),
+                                       _ptr(xs), _ptr(Ps), dim, pad_d, nu_d, lamMin_d, lamMax_d, _ptr(lam))
+            if kap is not None:
+                if dim == 2:
+                    L.oracle_update_kappa2(n, _ptr(intervalToBlockMap), int(blockCount), _ptr(xs), _ptr(Ps),
+                                           _ptr(lag), Fd, Qd, _ptr(qs), nu_d, kapMin_d, kapMax_d, _ptr(kap))
+                else:
+                    L.oracle_update_kappa1(n, _ptr(intervalToBlockMap), int(blockCount), _ptr(xs), _ptr(Ps),
+                                           _ptr(lag), float(Q0[0, 0]), _ptr(qs), nu_d, kapMin_d, kapMax_d,
+                                           _ptr(kap))
+        cur = nll_only()
+        has_prev = has_init
+        if not has_prev:
+            init_nll, has_init = cur, True
+        elif cur > prev + (1.0e-12 * max(abs(prev), 1.0)):
+            inc += 1
+        if has_prev:
+            delta, scale = abs(cur - prev), abs(prev)
+        else:
+            delta, scale = 0.0, abs(cur)
+        scale = max(scale, abs(cur))
+        scale = max(scale, 1.0)
+        if has_prev:
+            rel_impr, abs_rel = (prev - cur) / scale, delta / scale
+        else:
+            rel_impr = abs_rel = 0.0
+        tol = rtol_d * scale
+        prev = cur
+        stable = stable + 1 if (has_prev and delta <= tol) else 0
+        it_conv = stable >= patience
+        if trackOptimizationPath:
+            path.append({
+                "iter": iters_done, "objective_name": "nll", "objective_value": float(cur),
+                "change": float(delta) if has_prev else None,
+                "relative_improvement": float(rel_impr) if has_prev else None,
+                "abs_relative_change": float(abs_rel) if has_prev else None,
+                "threshold": float(tol) if has_prev else None, "stable_iters": int(stable),
+                "patience_target": patience, "reset_iteration": bool(not has_prev),
+                "converged": bool(it_conv),
+            })
+        if it_conv:
+            converged = True
+            break
+    diag = {
+        "iters_done": int(iters_done), "max_iters": int(iters), "converged": bool(converged),
+        "skipped": False, "skip_reason": None, "fallback": None, "stable_iters": int(stable),
+        "patience_target": patience, "initial_nll": float(init_nll) if has_init else None,
+        "final_nll": float(prev), "final_abs_rel_change": float(abs_rel) if has_init else None,
+        "final_rel_improvement": float(rel_impr) if has_init else None, "nll_increase_count": int(inc),
+    }
+    if trackOptimizationPath:
+        diag["optimization_path"] = path
+    return pack(iters_done, prev, diag)
+
+
+def cfixedBackgroundECM(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                        stateInit, stateCovarInit, ECM_fixedBackgroundIters=50, ECM_fixedBackgroundRtol=1.0e-4,
+                        pad=1.0e-4, ECM_robustTNu=8.0, obsPrecisionMultiplierMin=0.25,
+                        obsPrecisionMultiplierMax=4.0, procPrecisionMultiplierMin=0.25,
+                        procPrecisionMultiplierMax=4.0, ECM_useObsPrecisionReweighting=True,
+                        ECM_useProcessPrecisionReweighting=True, ECM_useAPN=False, APN_minQ=1.0e-4,
+                        APN_maxQ=1000.0, APN_dStatThresh=5.0, APN_dStatScale=10.0, APN_dStatPC=2.0,
+                        t_innerIters=5, returnIntermediates=False, returnDiagnostics=False,
+                        lambdaExpInit=None, processPrecExpInit=None, trackOptimizationPath=False,
+                        logIterations=True, processQScale=None):
+    return _ecm(2, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                stateInit, stateCovarInit, ECM_fixedBackgroundIters, ECM_fixedBackgroundRtol, pad,
+                ECM_robustTNu, obsPrecisionMultiplierMin, obsPrecisionMultiplierMax,
+                procPrecisionMultiplierMin, procPrecisionMultiplierMax, ECM_useObsPrecisionReweighting,
+                ECM_useProcessPrecisionReweighting, ECM_useAPN, APN_minQ, APN_maxQ, APN_dStatThresh,
+                APN_dStatScale, APN_dStatPC, t_innerIters, returnIntermediates, returnDiagnostics,
+                lambdaExpInit, processPrecExpInit, trackOptimizationPath, processQScale)
+
+
+def cfixedBackgroundECMLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBlockMap, blockCount,
+                             stateInit, stateCovarInit, ECM_fixedBackgroundIters=50,
+                             ECM_fixedBackgroundRtol=1.0e-4, pad=1.0e-4, ECM_robustTNu=8.0,
+                             obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0,
+                             procPrecisionMultiplierMin=0.25, procPrecisionMultiplierMax=4.0,
+                             ECM_useObsPrecisionReweighting=True, ECM_useProcessPrecisionReweighting=True,
+                             ECM_useAPN=False, APN_minQ=1.0e-4, APN_maxQ=1000.0, APN_dStatThresh=5.0,
+                             APN_dStatScale=10.0, APN_dStatPC=2.0, t_innerIters=5, returnIntermediates=False,
+                             returnDiagnostics=False, lambdaExpInit=None, processPrecExpInit=None,
+                             trackOptimizationPath=False, logIterations=True, processQScale=None):
+    return _ecm(1, matrixData, matrixPluginMuncInit, None, matrixQ0, intervalToBlockMap, blockCount,
+                stateInit, stateCovarInit, ECM_fixedBackgroundIters, ECM_fixedBackgroundRtol, pad,
+                ECM_robustTNu, obsPrecisionMultiplierMin, obsPrecisionMultiplierMax,
+                procPrecisionMultiplierMin, procPrecisionMultiplierMax, ECM_useObsPrecisionReweighting,
+                ECM_useProcessPrecisionReweighting, ECM_useAPN, APN_minQ, APN_maxQ, APN_dStatThresh,
+                APN_dStatScale, APN_dStatPC, t_innerIters, returnIntermediates, returnDiagnostics,
+                lambdaExpInit, processPrecExpInit, trackOptimizationPath, processQScale)
+
+
+def load_reference():
+    """Return the reference-built ``cconsenrich`` module from oracle/_ref, or None if absent."""
+    ref_dir = os.path.join(_HERE, "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "consenrich_ref")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import consenrich_ref.cconsenrich as ref  # type: ignore
+    except Exception:
+        return None
+    return ref
