@@ -1,0 +1,46 @@
+"""Stated parity tolerance for floating-point tracks (CPU-emulation and GPU parity tests).
+
+The reference computes in float64 but rounds its carried state/covariance to float32 at every
+bin (cconsenrich.pyx:405-406, 427-430, 478-479, 492-495) and stores float32; the scan path
+re-associates the float64 arithmetic, so the two cannot agree bit-for-bit.  The rounding noise
+the reference injects is not damped on the weakly observed trend component: measured here
+against an un-rounded float64 recursion, the reference itself is off by up to 3e-5 absolute
+on a state of scale 6 (5e-6 of scale on the level, 1e-4 of the trend's own scale).  The
+stated tolerance sits just above that floor:
+
+    |got - want| <= RTOL * |want| + ATOL_REL * scale,      RTOL = 1e-4, ATOL_REL = 1e-5
+
+``scale`` is max|want| over the whole array for state vectors, residuals and per-bin
+statistics (level and trend share units through F), and per trailing-axis component for
+covariance-like arrays (P00, P01, P11 differ by orders of magnitude).  For comparison the
+reference's own tests use rtol = atol = 2e-6 against a float64 recursion on n <= 64 bins
+(tests/test_core.py:3344-3351).  Integer outputs, Q tracks, and everything in the level
+(1-state) forward pass, where the reference does not round, are compared much tighter in
+the tests that use them.
+"""
+import numpy as np
+
+RTOL = 1.0e-4
+ATOL_REL = 1.0e-5
+
+
+def max_violation(got, want, scale="array", rtol=RTOL, atol_rel=ATOL_REL):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    if got.size == 0:
+        return 0.0
+    g2 = got.reshape(got.shape[0], -1)
+    w2 = want.reshape(want.shape[0], -1)
+    if scale == "component":
+        sc = np.max(np.abs(w2), axis=0, keepdims=True)
+    else:
+        sc = np.max(np.abs(w2))
+    tol = rtol * np.abs(w2) + atol_rel * sc + 1e-300
+    return float(np.max(np.abs(g2 - w2) / tol))
+
+
+def assert_tracks_close(got, want, name="", scale="array", rtol=RTOL, atol_rel=ATOL_REL):
+    assert np.all(np.isfinite(np.asarray(got, np.float64))), f"{name}: non-finite values"
+    v = max_violation(got, want, scale, rtol, atol_rel)
+    assert v <= 1.0, f"{name}: max |err|/tol = {v:.3g} (rtol={rtol}, atol_rel={atol_rel}, scale={scale})"

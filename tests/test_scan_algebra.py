@@ -1,0 +1,142 @@
+"""CPU check of the scan algebra the sm_100a kernels use (consenrich_b200/csrc/ssm_math.cuh).
+
+tests/emul/scan_emul.cpp replays the kernels' tiling (thread chunks, Kogge-Stone tile scan,
+look-back over tile aggregates with randomised windows, reference-ordered replay) on the CPU
+from the same header; here it is compared with the oracle.  Tolerances are the ones the GPU
+parity tests use (tests/test_gpu_parity.py): the scan re-associates float64 arithmetic and
+the reference rounds its carried state to float32 every bin, so agreement is to float32
+resolution of each track's own scale, not bit-exact.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, synth_tracks
+from parity_util import assert_tracks_close
+
+F = np.array([[1.0, 1.0], [0.0, 1.0]], np.float32)
+_EMUL_SRC = os.path.join(ROOT, "tests", "emul", "scan_emul.cpp")
+_EMUL_SO = os.path.join(ROOT, "tests", "emul", "_build", "libscan_emul.so")
+
+
+class _P(C.Structure):
+    _fields_ = [("F", C.c_double * 4), ("Q0", C.c_double * 4), ("state_init", C.c_double),
+                ("cov_init", C.c_double), ("lam_min", C.c_double), ("lam_max", C.c_double),
+                ("kap_min", C.c_double), ("kap_max", C.c_double), ("use_lambda", C.c_int32),
+                ("use_kappa", C.c_int32), ("use_qscale", C.c_int32), ("return_nll", C.c_int32),
+                ("store_nll_in_d", C.c_int32), ("do_store", C.c_int32), ("chunk", C.c_int32),
+                ("tile_chunks", C.c_int32), ("seed", C.c_uint64)]
+
+
+@pytest.fixture(scope="module")
+def emul():
+    hdr = os.path.join(ROOT, "consenrich_b200", "csrc", "ssm_math.cuh")
+    if (not os.path.exists(_EMUL_SO)) or os.path.getmtime(_EMUL_SO) < max(os.path.getmtime(_EMUL_SRC),
+                                                                           os.path.getmtime(hdr)):
+        os.makedirs(os.path.dirname(_EMUL_SO), exist_ok=True)
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-fPIC", "-shared", "-ffp-contract=off",
+                               _EMUL_SRC, "-o", _EMUL_SO])
+    return C.CDLL(_EMUL_SO)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _fold(emul, data, munc, pad):
+    m, n = data.shape
+    S = [np.empty(n, np.float64) for _ in range(4)]
+    emul.emul_fold(_ptr(data), _ptr(munc), C.c_int64(m), C.c_int64(n), C.c_int64(n),
+                   C.c_double(float(np.float32(pad))), *map(_ptr, S))
+    return S
+
+
+def _params(Q0, state_init, chunk, tile_chunks, seed, lam, kap, qs, bounds, return_nll, nll_in_d):
+    p = _P()
+    p.F[:] = [1.0, 1.0, 0.0, 1.0]
+    p.Q0[:] = [float(Q0[0, 0]), float(Q0[0, 1]), float(Q0[1, 0]), float(Q0[1, 1])]
+    p.state_init, p.cov_init = float(np.float32(state_init)), 1000.0
+    p.lam_min, p.lam_max, p.kap_min, p.kap_max = [float(np.float32(b)) for b in bounds]
+    p.use_lambda, p.use_kappa, p.use_qscale = int(lam is not None), int(kap is not None), int(qs is not None)
+    p.return_nll, p.store_nll_in_d, p.do_store = int(return_nll), int(nll_in_d), 1
+    p.chunk, p.tile_chunks, p.seed = chunk, tile_chunks, seed
+    return p
+
+
+CASES = [
+    # m, n, masked, weights, chunk, tile_chunks
+    (3, 257, 0.0, False, 4, 8),
+    (10, 5000, 0.05, True, 8, 32),
+    (5, 1, 0.0, False, 8, 32),
+    (5, 2, 0.0, True, 8, 32),
+    (25, 3001, 0.3, True, 16, 4),
+    (2, 20000, 0.0, True, 8, 128),
+]
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+@pytest.mark.parametrize("case", CASES)
+def test_emulated_scan_matches_oracle(oracle, emul, dim, case):
+    m, n, masked, weights, chunk, tile_chunks = case
+    data, munc = synth_tracks(1000 + n, m, n, masked_frac=masked)
+    rng = np.random.default_rng(n)
+    Q0 = np.array([[2e-3, 0.0], [0.0, 1e-4]], np.float32)
+    lam = kap = qs = None
+    bounds = (0.25, 4.0, 5e-3, 5e3)
+    if weights:
+        lam = (0.1 + 5 * rng.random(n)).astype(np.float32)
+        kap = np.exp(rng.normal(0, 2, n)).astype(np.float32)
+        qs = (0.5 + rng.random(n)).astype(np.float32)
+        qs[0] = 1.0
+    bm = np.zeros(n, np.int32)
+    kw = dict(matrixData=data, matrixPluginMuncInit=munc, matrixQ0=Q0, intervalToBlockMap=bm, blockCount=1,
+              stateInit=0.25, stateCovarInit=1000.0, pad=1e-4, returnNLL=True, storeNLLInD=False,
+              lambdaExp=lam, processPrecExp=kap, processQScale=qs, obsPrecisionMultiplierMin=bounds[0],
+              obsPrecisionMultiplierMax=bounds[1], procPrecisionMultiplierMin=bounds[2],
+              procPrecisionMultiplierMax=bounds[3])
+    want = dict(xf=np.empty((n, dim), np.float32), Pf=np.empty((n, dim, dim), np.float32),
+                Qf=np.zeros((n, dim, dim), np.float32), D=np.empty(n, np.float32))
+    st = dict(stateForward=want["xf"], stateCovarForward=want["Pf"], pNoiseForward=want["Qf"], vectorD=want["D"])
+    if dim == 2:
+        r = oracle.cforwardPass(matrixF=F, **kw, **st)
+        b = oracle.cbackwardPass(matrixData=data, matrixF=F, stateForward=want["xf"], stateCovarForward=want["Pf"],
+                                 pNoiseForward=want["Qf"])
+    else:
+        r = oracle.cforwardPassLevel(**kw, **st)
+        b = oracle.cbackwardPassLevel(matrixData=data, stateForward=want["xf"], stateCovarForward=want["Pf"],
+                                      pNoiseForward=want["Qf"])
+    S = _fold(emul, data, munc, 1e-4)
+    p = _params(Q0, 0.25, chunk, tile_chunks, 12345 + n, lam, kap, qs, bounds, True, False)
+    got = dict(xf=np.empty((n, dim), np.float32), Pf=np.empty((n, dim, dim), np.float32),
+               Qf=np.zeros((n, dim, dim), np.float32), D=np.empty(n, np.float32))
+    sd, snll = C.c_double(), C.c_double()
+    fwd = emul.emul_forward2 if dim == 2 else emul.emul_forward1
+    fwd(*map(_ptr, S), C.c_int64(m), C.c_int64(n), _ptr(lam), _ptr(kap), _ptr(qs), C.byref(p),
+        _ptr(got["D"]), _ptr(got["xf"]), _ptr(got["Pf"]), _ptr(got["Qf"]), C.byref(sd), C.byref(snll))
+    assert_tracks_close(got["xf"], want["xf"], "stateForward")
+    assert_tracks_close(got["Pf"], want["Pf"], "stateCovarForward", scale="component")
+    np.testing.assert_array_equal(got["Qf"][: n - 1], want["Qf"][: n - 1])
+    assert_tracks_close(got["D"], want["D"], "vectorD")
+    assert abs(snll.value - r[3]) <= 1e-7 * max(abs(r[3]), 1.0)
+    if dim == 1:  # the level filter carries float64 in the reference too: float32 outputs identical
+        np.testing.assert_array_equal(got["xf"], want["xf"])
+        np.testing.assert_array_equal(got["Pf"], want["Pf"])
+    assert abs(np.float32(sd.value / n) - np.float32(r[0])) <= 1e-5 * max(abs(r[0]), 1e-3)
+
+    # smoother: feed BOTH the oracle's forward outputs (isolates the reverse scan)
+    xs, Ps = np.empty((n, dim), np.float32), np.empty((n, dim, dim), np.float32)
+    lag = np.zeros((max(n - 1, 1), dim, dim), np.float32)
+    if dim == 2:
+        Fd = (C.c_double * 4)(1.0, 1.0, 0.0, 1.0)
+        emul.emul_backward2(C.c_int64(n), Fd, _ptr(want["xf"]), _ptr(want["Pf"]), _ptr(want["Qf"]), C.byref(p),
+                            _ptr(xs), _ptr(Ps), _ptr(lag), C.c_int64(lag.shape[0]))
+    else:
+        emul.emul_backward1(C.c_int64(n), _ptr(want["xf"]), _ptr(want["Pf"]), _ptr(want["Qf"]), C.byref(p),
+                            _ptr(xs), _ptr(Ps), _ptr(lag), C.c_int64(lag.shape[0]))
+    assert_tracks_close(xs, b[0], "stateSmoothed")
+    assert_tracks_close(Ps, b[1], "stateCovarSmoothed", scale="component")
+    if n > 1:
+        assert_tracks_close(lag, b[2], "lagCovSmoothed", scale="component")
