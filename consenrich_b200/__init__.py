@@ -1,0 +1,18 @@
+"""consenrich_b200 -- B200 (sm_100a) implementation of Consenrich's state-space hot path.
+
+Only what the path needs lives here:
+
+* ``csrc/``      hand-written CUDA kernels + the C ABI (``include/consenrich_b200.h``)
+* ``_lib``       ctypes binding of ``lib/libconsenrich_b200.so``
+* ``native``     drop-in replacements for the six hot-path functions of ``consenrich.cconsenrich``
+* ``device``     device-resident sweeps on torch tensors (torch is only a tensor carrier)
+* ``sharding``   chromosome / bin-range sharding across ranks (torch.distributed plumbing)
+
+There is no CPU implementation: importing works anywhere, calling requires the built library
+and a CUDA device, and fails loudly otherwise.
+"""
+from . import _lib  # noqa: F401
+from .native import (cbackwardPass, cbackwardPassLevel, cfixedBackgroundECM,  # noqa: F401
+                     cfixedBackgroundECMLevel, cforwardPass, cforwardPassLevel, install, sweep, uninstall)
+
+__version__ = "0.1.0"

@@ -1,0 +1,199 @@
+"""ctypes binding of libconsenrich_b200.so (include/consenrich_b200.h).
+
+Loading fails loudly when the library has not been built: there is no CPU implementation to
+fall back to.  Creating a context fails loudly when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libconsenrich_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
+ABI_VERSION = 1
+
+FAM_FOLD, FAM_FORWARD, FAM_BACKWARD, FAM_RESIDUALS, FAM_PRECISION = range(5)
+FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates")
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+class Model(C.Structure):
+    """cb200_model"""
+    _fields_ = [
+        ("state_dim", C.c_int32), ("use_lambda", C.c_int32), ("use_kappa", C.c_int32), ("use_qscale", C.c_int32),
+        ("return_nll", C.c_int32), ("store_nll_in_d", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("F", C.c_double * 4), ("Q0", C.c_double * 4),
+        ("state_init", C.c_double), ("cov_init", C.c_double), ("pad", C.c_double),
+        ("lam_min", C.c_double), ("lam_max", C.c_double), ("kap_min", C.c_double), ("kap_max", C.c_double),
+    ]
+
+
+class EcmOpts(C.Structure):
+    """cb200_ecm_opts"""
+    _fields_ = [
+        ("max_iters", C.c_int32), ("inner_iters", C.c_int32), ("update_lambda", C.c_int32),
+        ("update_kappa", C.c_int32), ("want_outputs", C.c_int32), ("reserved0", C.c_int32),
+        ("rtol", C.c_double), ("nu", C.c_double),
+    ]
+
+
+class EcmResult(C.Structure):
+    """cb200_ecm_result"""
+    _fields_ = [
+        ("iters_done", C.c_int32), ("converged", C.c_int32), ("skipped", C.c_int32), ("stable_iters", C.c_int32),
+        ("nll_increase_count", C.c_int32), ("has_initial", C.c_int32),
+        ("initial_nll", C.c_double), ("final_nll", C.c_double), ("final_abs_rel_change", C.c_double),
+        ("final_rel_improvement", C.c_double),
+    ]
+
+
+_vp, _i64, _i32, _dbl, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t
+_pm, _po, _pr = C.POINTER(Model), C.POINTER(EcmOpts), C.POINTER(EcmResult)
+
+# name -> (restype, argtypes); one entry per declaration in include/consenrich_b200.h
+SIGNATURES = {
+    "cb200_abi_version": (C.c_int, []),
+    "cb200_ctx_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "cb200_ctx_destroy": (None, [_vp]),
+    "cb200_ctx_set_stream": (C.c_int, [_vp, _vp]),
+    "cb200_ctx_sync": (C.c_int, [_vp]),
+    "cb200_last_error": (C.c_char_p, []),
+    "cb200_ctx_launch_count": (_i64, [_vp]),
+    "cb200_ctx_enable_timing": (C.c_int, [_vp, C.c_int]),
+    "cb200_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(_dbl), C.POINTER(_i64)]),
+    "cb200_ctx_reset_timing": (C.c_int, [_vp]),
+    "cb200_device_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
+    "cb200_device_free": (C.c_int, [_vp, _vp]),
+    "cb200_pinned_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
+    "cb200_pinned_free": (C.c_int, [_vp]),
+    "cb200_copy_h2d": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
+    "cb200_copy_d2h": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
+    "cb200_fold_tracks": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dbl, _vp, _i64]),
+    "cb200_forward_scan": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cb200_forward_shard_aggregate": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "cb200_forward_shard_prefix": (C.c_int, [_vp, _pm, _vp, _i32, _vp]),
+    "cb200_backward_scan": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "cb200_backward_shard_aggregate": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "cb200_backward_shard_prefix": (C.c_int, [_vp, _pm, _vp, _i32, _i32, _vp]),
+    "cb200_residuals": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp]),
+    "cb200_update_lambda": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _i64, _vp, _vp, _dbl, _vp]),
+    "cb200_update_kappa": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _vp, _dbl, _vp]),
+    "cb200_ecm_device": (C.c_int, [_vp, _pm, _po, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   _pr, _vp]),
+    "cb200_host_forward_pass": (C.c_int, [_vp, _pm, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                          _vp, C.POINTER(_dbl), C.POINTER(_dbl)]),
+    "cb200_host_backward_pass": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "cb200_host_sweep": (C.c_int, [_vp, _pm, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                   C.POINTER(_dbl), C.POINTER(_dbl), _vp, _vp, _vp, _i64, _vp]),
+    "cb200_host_ecm": (C.c_int, [_vp, _pm, _po, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                 _pr, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def load() -> C.CDLL:
+    """Load libconsenrich_b200.so; raises NativeLibraryMissing if it has not been built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} is missing. Build it with `python -m consenrich_b200.build` (needs nvcc); "
+                "consenrich_b200 has no CPU implementation to fall back to.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError here = header / library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if lib.cb200_abi_version() != ABI_VERSION:
+            raise NativeLibraryMissing(f"{LIB_PATH} has ABI {lib.cb200_abi_version()}, expected {ABI_VERSION}; rebuild")
+        _lib = lib
+        return lib
+
+
+def last_error() -> str:
+    msg = load().cb200_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    """Map a C status to the reference's exception types (ValueError for argument errors)."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise CudaError(msg)
+
+
+class Context:
+    """One cb200_ctx: a device, a stream, the device arena and launch accounting."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        self._lib = load()
+        h = _vp()
+        check(self._lib.cb200_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h)))
+        self.handle = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self._lib.cb200_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, stream: int | None):
+        check(self._lib.cb200_ctx_set_stream(self.handle, _vp(stream) if stream else None))
+
+    def sync(self):
+        check(self._lib.cb200_ctx_sync(self.handle))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.cb200_ctx_launch_count(self.handle))
+
+    def enable_timing(self, on: bool = True):
+        check(self._lib.cb200_ctx_enable_timing(self.handle, int(on)))
+
+    def reset_timing(self):
+        check(self._lib.cb200_ctx_reset_timing(self.handle))
+
+    def kernel_ms(self) -> dict:
+        out = {}
+        for fam, name in enumerate(FAMILY_NAMES):
+            ms, cnt = _dbl(), _i64()
+            check(self._lib.cb200_ctx_kernel_ms(self.handle, fam, C.byref(ms), C.byref(cnt)))
+            out[name] = (ms.value, cnt.value)
+        return out
+
+
+_default_ctx: dict = {}
+
+
+def default_context(device: int = 0) -> Context:
+    """Process-wide context per device, used by the drop-in functions."""
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = Context(device)
+        _default_ctx[device] = ctx
+    return ctx

@@ -1,0 +1,870 @@
+// consenrich_b200/csrc/cabi.cu -- C ABI of libconsenrich_b200.so (include/consenrich_b200.h).
+//
+// Host-side runtime around the sm_100a kernels: context (stream, device arena, launch
+// accounting, optional per-kernel CUDA-event timing), the device-resident entry points, the
+// ECM driver (reference cconsenrich.pyx:7877-8442 / 7188-7657) and the reference-facing
+// host-buffer entry points.  There is no CPU implementation behind any of them.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/consenrich_b200.h"
+#include "ssm_kernels.cuh"
+
+using namespace cb200;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(CB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                      \
+    } while (0)
+
+#define CB_TRY(expr)                \
+    do {                            \
+        int _rc = (expr);           \
+        if (_rc != CB200_OK) return _rc; \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_COUNT = 5 };
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int fam;
+};
+
+}  // namespace
+
+struct cb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t launches = 0;
+    // arena (device)
+    DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, D, xs, Ps, lag, resid, lam, kap, qs, shard;
+    double *sums_host = nullptr;  // pinned double[2]
+    // timing
+    bool timing = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> pool;
+    double fam_ms[FAM_COUNT] = {0, 0, 0, 0, 0};
+    int64_t fam_n[FAM_COUNT] = {0, 0, 0, 0, 0};
+};
+
+namespace {
+
+int ensure(cb200_ctx *c, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap && b.p) return CB200_OK;
+    if (b.p) {
+        // buffers may still be in flight on the stream
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        CU_TRY(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    size_t want = bytes < 256 ? 256 : bytes;
+    CU_TRY(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return CB200_OK;
+}
+
+struct Span {
+    cb200_ctx *c;
+    TimedSpan s{};
+    bool on = false;
+    Span(cb200_ctx *ctx, int fam) : c(ctx) {
+        if (!c->timing) return;
+        auto get = [&](cudaEvent_t &e) {
+            if (!c->pool.empty()) {
+                e = c->pool.back();
+                c->pool.pop_back();
+                return true;
+            }
+            return cudaEventCreate(&e) == cudaSuccess;
+        };
+        if (!get(s.a)) return;
+        if (!get(s.b)) {
+            c->pool.push_back(s.a);
+            return;
+        }
+        s.fam = fam;
+        on = true;
+        cudaEventRecord(s.a, c->stream);
+    }
+    ~Span() {
+        if (!on) return;
+        cudaEventRecord(s.b, c->stream);
+        c->spans.push_back(s);
+    }
+};
+
+int resolve_spans(cb200_ctx *c) {
+    if (c->spans.empty()) return CB200_OK;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    for (auto &s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            c->fam_ms[s.fam] += (double)ms;
+            c->fam_n[s.fam] += 1;
+        }
+        c->pool.push_back(s.a);
+        c->pool.push_back(s.b);
+    }
+    c->spans.clear();
+    return CB200_OK;
+}
+
+int check_model(const cb200_model *mo) {
+    if (!mo) return fail(CB200_ERR_INVALID, "model is NULL");
+    if (mo->state_dim != 1 && mo->state_dim != 2) return fail(CB200_ERR_INVALID, "state_dim must be 1 or 2");
+    if (mo->lam_min <= 0.0 || mo->lam_max <= 0.0 || mo->lam_max < mo->lam_min)
+        return fail(CB200_ERR_INVALID, "observation precision multiplier bounds must satisfy 0 < min <= max");
+    if (mo->kap_min <= 0.0 || mo->kap_max <= 0.0 || mo->kap_max < mo->kap_min)
+        return fail(CB200_ERR_INVALID, "process precision multiplier bounds must satisfy 0 < min <= max");
+    if (mo->state_dim == 1) {
+        if (!(mo->Q0[0] > 0.0)) return fail(CB200_ERR_INVALID, "matrixQ0[0, 0] must be positive");
+    } else {
+        const double asym = fabs(mo->Q0[1] - mo->Q0[2]);
+        const double scale = fabs(mo->Q0[0]) + fabs(mo->Q0[3]) + fabs(mo->Q0[1]) + 1e-300;
+        if (asym > 1e-12 * scale)
+            return fail(CB200_ERR_UNSUPPORTED,
+                        "matrixQ0 must be symmetric: the filtering scan carries symmetric covariances");
+    }
+    return CB200_OK;
+}
+
+Model2 to_model2(const cb200_model *mo) {
+    Model2 M;
+    if (mo->state_dim == 2) {
+        M.F00 = mo->F[0]; M.F01 = mo->F[1]; M.F10 = mo->F[2]; M.F11 = mo->F[3];
+        M.q00 = mo->Q0[0]; M.q01 = mo->Q0[1]; M.q10 = mo->Q0[2]; M.q11 = mo->Q0[3];
+    } else {
+        M.F00 = 1.0; M.F01 = 0.0; M.F10 = 0.0; M.F11 = 1.0;
+        M.q00 = mo->Q0[0]; M.q01 = M.q10 = M.q11 = 0.0;
+    }
+    return M;
+}
+
+bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// ---- device-level building blocks ------------------------------------------------------
+int do_fold(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
+            double *stats, int64_t stride) {
+    Span sp(c, FAM_FOLD);
+    CU_TRY(launch_fold(data, munc, m, n, ld, pad, stats, stats + stride, stats + 2 * stride, stats + 3 * stride,
+                       c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stride, int64_t m, int64_t n,
+               const float *lam, const float *kap, const float *qs, const double *init_state, float *xf, float *Pf,
+               float *Qf, float *D, double *sums, double *agg_out, bool aggregate_only) {
+    const int d = mo->state_dim;
+    const bool store = (xf != nullptr);
+    if (store && (!Pf || !Qf)) return fail(CB200_ERR_INVALID, "xf, Pf and Qf must be given together");
+    if (store && d == 2 && (!aligned(xf, 8) || !aligned(Pf, 16) || !aligned(Qf, 16)))
+        return fail(CB200_ERR_INVALID, "forward outputs must be 8/16-byte aligned device pointers");
+    if (mo->use_lambda && !lam) return fail(CB200_ERR_INVALID, "lambdaExp is required when use_lambda is set");
+    if (mo->use_kappa && !kap) return fail(CB200_ERR_INVALID, "processPrecExp is required when use_kappa is set");
+    if (mo->use_qscale && !qs) return fail(CB200_ERR_INVALID, "processQScale is required when use_qscale is set");
+    CB_TRY(ensure(c, c->scan_ws, scan_workspace_bytes(n)));
+    FwdArgs a{};
+    a.S0 = stats; a.S1 = stats + stride; a.S2 = stats + 2 * stride; a.SL = stats + 3 * stride;
+    a.lam = lam; a.kap = kap; a.qs = qs;
+    a.init_state = init_state;
+    a.xf = xf; a.Pf = Pf; a.Qf = Qf; a.D = D;
+    a.sums = sums;
+    a.agg_out = agg_out;
+    a.n = n;
+    a.m = (double)m;
+    a.mlog2pi = (double)m * log(6.2831853071795864769);
+    a.M = to_model2(mo);
+    a.state_init = mo->state_init;
+    a.cov_init = mo->cov_init;
+    a.lam_min = mo->lam_min; a.lam_max = mo->lam_max;
+    a.kap_min = mo->kap_min; a.kap_max = mo->kap_max;
+    a.use_lambda = mo->use_lambda; a.use_kappa = mo->use_kappa; a.use_qscale = mo->use_qscale;
+    a.want_nll = mo->return_nll; a.nll_in_d = mo->store_nll_in_d;
+    a.do_store = store ? 1 : 0;
+    ScanWorkspace ws = scan_workspace_carve(c->scan_ws.p, n);
+    int launches = 0;
+    {
+        Span sp(c, FAM_FWD);
+        CU_TRY(launch_forward(d, a, ws, aggregate_only, c->stream, &launches));
+    }
+    c->launches += launches;
+    return CB200_OK;
+}
+
+int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf, const float *Qf,
+                const double *tail_state, int is_last, float *xs, float *Ps, float *lag, int64_t lag_rows,
+                double *agg_out, bool aggregate_only) {
+    const int d = mo->state_dim;
+    if (d == 2 && (!aligned(xf, 8) || !aligned(Pf, 16) || !aligned(Qf, 16) ||
+                   (!aggregate_only && (!aligned(xs, 8) || !aligned(Ps, 16) || !aligned(lag, 16)))))
+        return fail(CB200_ERR_INVALID, "smoother tracks must be 8/16-byte aligned device pointers");
+    CB_TRY(ensure(c, c->scan_ws, scan_workspace_bytes(n)));
+    BwdArgs a{};
+    a.xf = xf; a.Pf = Pf; a.Qf = Qf;
+    a.tail_state = tail_state;
+    a.xs = xs; a.Ps = Ps; a.lag = lag;
+    a.agg_out = agg_out;
+    a.n = n;
+    a.lag_rows = lag_rows;
+    a.M = to_model2(mo);
+    a.is_last_shard = is_last;
+    ScanWorkspace ws = scan_workspace_carve(c->scan_ws.p, n);
+    int launches = 0;
+    {
+        Span sp(c, FAM_BWD);
+        CU_TRY(launch_backward(d, a, ws, aggregate_only, c->stream, &launches));
+    }
+    c->launches += launches;
+    return CB200_OK;
+}
+
+int do_residuals(cb200_ctx *c, const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
+                 float *resid) {
+    Span sp(c, FAM_RESID);
+    CU_TRY(launch_residuals(data, m, n, ld, xs, dim, resid, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int check_block_map(const int32_t *bm, int64_t n, int64_t block_count) {
+    if (block_count <= 0) return fail(CB200_ERR_INVALID, "blockCount must be positive");
+    if (!bm) return fail(CB200_ERR_INVALID, "intervalToBlockMap length must match intervalCount");
+    int32_t lo = 0, hi = 0;
+    if (n > 0) lo = hi = bm[0];
+    for (int64_t k = 1; k < n; ++k) {
+        const int32_t b = bm[k];
+        lo = b < lo ? b : lo;
+        hi = b > hi ? b : hi;
+    }
+    if (n > 0 && (lo < 0 || (int64_t)hi >= block_count))
+        return fail(CB200_ERR_INVALID, "intervalToBlockMap has out-of-range block id");
+    return CB200_OK;
+}
+
+int h2d(cb200_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return CB200_OK;
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    return CB200_OK;
+}
+int d2h(cb200_ctx *c, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return CB200_OK;
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    return CB200_OK;
+}
+
+// upload [m x n] host tracks into a pitched device buffer; returns ld
+int upload_tracks(cb200_ctx *c, DevBuf &buf, const float *host, int64_t m, int64_t n, int64_t *ld_out) {
+    const int64_t ld = round_up(n, 32);
+    CB_TRY(ensure(c, buf, (size_t)m * (size_t)ld * sizeof(float)));
+    CU_TRY(cudaMemcpy2DAsync(buf.p, (size_t)ld * 4, host, (size_t)n * 4, (size_t)n * 4, (size_t)m,
+                             cudaMemcpyHostToDevice, c->stream));
+    *ld_out = ld;
+    return CB200_OK;
+}
+
+int upload_vec(cb200_ctx *c, DevBuf &buf, const float *host, int64_t n, bool live, const float **dev_out) {
+    *dev_out = nullptr;
+    if (!live) return CB200_OK;
+    if (!host) return fail(CB200_ERR_INVALID, "a per-interval vector flagged live in the model is NULL");
+    CB_TRY(ensure(c, buf, (size_t)n * 4));
+    CB_TRY(h2d(c, buf.p, host, (size_t)n * 4));
+    *dev_out = static_cast<const float *>(buf.p);
+    return CB200_OK;
+}
+
+int read_sums(cb200_ctx *c, double *out2) {
+    CB_TRY(d2h(c, c->sums_host, c->sums.p, 16));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    out2[0] = c->sums_host[0];
+    out2[1] = c->sums_host[1];
+    return CB200_OK;
+}
+
+}  // namespace
+
+// =====================================================================================
+// context
+// =====================================================================================
+extern "C" {
+
+int cb200_abi_version(void) { return CB200_ABI_VERSION; }
+
+const char *cb200_last_error(void) { return g_err.c_str(); }
+
+int cb200_ctx_create(int device, void *stream, cb200_ctx **out) {
+    if (!out) return fail(CB200_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(CB200_ERR_CUDA, "no CUDA device available (%s); libconsenrich_b200 has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(CB200_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(CB200_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+                    prop.minor);
+    cb200_ctx *c = new cb200_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+            delete c;
+            return fail(CB200_ERR_CUDA, "cudaStreamCreate failed");
+        }
+        c->own_stream = true;
+    }
+    if (configure_kernels() != cudaSuccess || cudaMalloc(&c->sums.p, 256) != cudaSuccess ||
+        cudaMallocHost(reinterpret_cast<void **>(&c->sums_host), 64) != cudaSuccess) {
+        cudaError_t le = cudaGetLastError();
+        cb200_ctx_destroy(c);
+        return fail(CB200_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(le));
+    }
+    c->sums.cap = 256;
+    *out = c;
+    return CB200_OK;
+}
+
+void cb200_ctx_destroy(cb200_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->D,
+                      &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard};
+    for (DevBuf *b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->sums_host) cudaFreeHost(c->sums_host);
+    for (auto &s : c->spans) {
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    for (auto &e : c->pool) cudaEventDestroy(e);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int cb200_ctx_set_stream(cb200_ctx *c, void *stream) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) {
+        cudaStreamDestroy(c->stream);
+        c->own_stream = false;
+    }
+    if (stream) {
+        c->stream = static_cast<cudaStream_t>(stream);
+    } else {
+        CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    return CB200_OK;
+}
+
+int cb200_ctx_sync(cb200_ctx *c) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
+int64_t cb200_ctx_launch_count(const cb200_ctx *c) { return c ? c->launches : 0; }
+
+int cb200_ctx_enable_timing(cb200_ctx *c, int on) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    CB_TRY(resolve_spans(c));
+    c->timing = on != 0;
+    return CB200_OK;
+}
+
+int cb200_ctx_kernel_ms(cb200_ctx *c, int family, double *ms, int64_t *launches) {
+    if (!c || family < 0 || family >= FAM_COUNT) return fail(CB200_ERR_INVALID, "bad kernel family");
+    CB_TRY(resolve_spans(c));
+    if (ms) *ms = c->fam_ms[family];
+    if (launches) *launches = c->fam_n[family];
+    return CB200_OK;
+}
+
+int cb200_ctx_reset_timing(cb200_ctx *c) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    CB_TRY(resolve_spans(c));
+    for (int i = 0; i < FAM_COUNT; ++i) {
+        c->fam_ms[i] = 0.0;
+        c->fam_n[i] = 0;
+    }
+    return CB200_OK;
+}
+
+// =====================================================================================
+// memory helpers
+// =====================================================================================
+int cb200_device_alloc(cb200_ctx *c, size_t bytes, void **dptr) {
+    if (!c || !dptr) return fail(CB200_ERR_INVALID, "ctx/dptr is NULL");
+    CU_TRY(cudaSetDevice(c->device));
+    CU_TRY(cudaMalloc(dptr, bytes < 256 ? 256 : bytes));
+    return CB200_OK;
+}
+
+int cb200_device_free(cb200_ctx *c, void *dptr) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (!dptr) return CB200_OK;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(cudaFree(dptr));
+    return CB200_OK;
+}
+
+int cb200_pinned_alloc(size_t bytes, void **hptr) {
+    if (!hptr) return fail(CB200_ERR_INVALID, "hptr is NULL");
+    CU_TRY(cudaMallocHost(hptr, bytes < 64 ? 64 : bytes));
+    return CB200_OK;
+}
+
+int cb200_pinned_free(void *hptr) {
+    if (!hptr) return CB200_OK;
+    CU_TRY(cudaFreeHost(hptr));
+    return CB200_OK;
+}
+
+int cb200_copy_h2d(cb200_ctx *c, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
+                   size_t rows) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (rows == 0 || row_bytes == 0) return CB200_OK;
+    CU_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, c->stream));
+    return CB200_OK;
+}
+
+int cb200_copy_d2h(cb200_ctx *c, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
+                   size_t rows) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (rows == 0 || row_bytes == 0) return CB200_OK;
+    CU_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, c->stream));
+    return CB200_OK;
+}
+
+// =====================================================================================
+// device-resident path
+// =====================================================================================
+int cb200_fold_tracks(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n, int64_t ld,
+                      double pad, double *stats, int64_t stat_stride) {
+    if (!c || !data || !munc || !stats) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (m <= 0 || n <= 0) return CB200_OK;
+    if (ld < n) return fail(CB200_ERR_INVALID, "row stride ld must be >= n");
+    if (stat_stride < n || (stat_stride & 1)) return fail(CB200_ERR_INVALID, "stat_stride must be even and >= n");
+    if (!aligned(stats, 16)) return fail(CB200_ERR_INVALID, "stats must be 16-byte aligned");
+    return do_fold(c, data, munc, m, n, ld, pad, stats, stat_stride);
+}
+
+int cb200_forward_scan(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride, int64_t m,
+                       int64_t n, const float *lam, const float *kap, const float *qscale, const double *init_state,
+                       float *xf, float *Pf, float *Qf, float *D, double *sums) {
+    if (!c || !stats) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return CB200_OK;
+    return do_forward(c, mo, stats, stat_stride, m, n, lam, kap, qscale, init_state, xf, Pf, Qf, D, sums, nullptr,
+                      false);
+}
+
+int cb200_forward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride,
+                                  int64_t n, const float *lam, const float *kap, const float *qscale, double *agg) {
+    if (!c || !stats || !agg) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return fail(CB200_ERR_INVALID, "a shard must hold at least one interval");
+    return do_forward(c, mo, stats, stat_stride, 1, n, lam, kap, qscale, nullptr, nullptr, nullptr, nullptr, nullptr,
+                      nullptr, agg, true);
+}
+
+int cb200_forward_shard_prefix(cb200_ctx *c, const cb200_model *mo, const double *aggs, int32_t rank,
+                               double *init_state) {
+    if (!c || !aggs || !init_state) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    CU_TRY(launch_forward_shard_prefix(mo->state_dim, aggs, rank, mo->state_init, mo->cov_init, init_state,
+                                       c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_backward_scan(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf,
+                        const float *Qf, const double *tail_state, float *xs, float *Ps, float *lag,
+                        int64_t lag_rows) {
+    if (!c || !xf || !Pf || !Qf || !xs || !Ps || !lag) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return CB200_OK;
+    return do_backward(c, mo, n, xf, Pf, Qf, tail_state, tail_state == nullptr, xs, Ps, lag, lag_rows, nullptr, false);
+}
+
+int cb200_backward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf,
+                                   const float *Qf, int32_t is_last_shard, double *agg) {
+    if (!c || !xf || !Pf || !Qf || !agg) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return fail(CB200_ERR_INVALID, "a shard must hold at least one interval");
+    return do_backward(c, mo, n, xf, Pf, Qf, nullptr, is_last_shard, nullptr, nullptr, nullptr, 0, agg, true);
+}
+
+int cb200_backward_shard_prefix(cb200_ctx *c, const cb200_model *mo, const double *aggs, int32_t rank,
+                                int32_t n_shards, double *tail_state) {
+    if (!c || !aggs || !tail_state) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    CU_TRY(launch_backward_shard_prefix(mo->state_dim, aggs, rank, n_shards, tail_state, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_residuals(cb200_ctx *c, const float *data, int64_t m, int64_t n, int64_t ld, const float *xs,
+                    int32_t state_dim, float *resid) {
+    if (!c || !data || !xs || !resid) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (state_dim != 1 && state_dim != 2) return fail(CB200_ERR_INVALID, "state_dim must be 1 or 2");
+    if (m <= 0 || n <= 0) return CB200_OK;
+    return do_residuals(c, data, m, n, ld, xs, state_dim, resid);
+}
+
+int cb200_update_lambda(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride, int64_t m,
+                        int64_t n, const float *xs, const float *Ps, double nu, float *lam) {
+    if (!c || !stats || !xs || !Ps || !lam) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    Span sp(c, FAM_PREC);
+    CU_TRY(launch_update_lambda(stats, stats + stat_stride, stats + 2 * stat_stride, n, (double)m, xs, Ps,
+                                mo->state_dim, nu, mo->lam_min, mo->lam_max, lam, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_update_kappa(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xs, const float *Ps,
+                       const float *lag, const float *qscale, double nu, float *kap) {
+    if (!c || !xs || !Ps || !lag || !kap) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (mo->state_dim == 2) {
+        const double det = mo->Q0[0] * mo->Q0[3] - mo->Q0[1] * mo->Q0[2];
+        if (det == 0.0) return fail(CB200_ERR_INVALID, "matrixQ0 is singular");
+    }
+    Span sp(c, FAM_PREC);
+    CU_TRY(launch_update_kappa(mo->state_dim, to_model2(mo), n, xs, Ps, lag, qscale, nu, mo->kap_min, mo->kap_max,
+                               kap, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+// =====================================================================================
+// ECM (cconsenrich.pyx:7877-8442, 7188-7657)
+// =====================================================================================
+int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opts *op, const float *data,
+                     const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *lam, float *kap,
+                     float *xs, float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
+    if (!c || !op || !res || !data || !munc || !xs || !Ps || !lag) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo_in));
+    memset(res, 0, sizeof(*res));
+    if (n <= 0 || m <= 0) {
+        res->skipped = 1;
+        return CB200_OK;
+    }
+    cb200_model mo = *mo_in;
+    const int d = mo.state_dim;
+    if (d == 2) {
+        const double det = mo.Q0[0] * mo.Q0[3] - mo.Q0[1] * mo.Q0[2];
+        if (det == 0.0) return fail(CB200_ERR_INVALID, "matrixQ0 is singular");
+    }
+    mo.use_lambda = lam != nullptr;
+    mo.use_kappa = kap != nullptr;
+    mo.use_qscale = qscale != nullptr;
+    mo.store_nll_in_d = 0;
+    const int64_t stride = round_up(n, 32);
+    CB_TRY(ensure(c, c->stats, (size_t)stride * 4 * 8));
+    CB_TRY(ensure(c, c->xf, (size_t)n * d * 4));
+    CB_TRY(ensure(c, c->Pf, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->Qf, (size_t)n * d * d * 4));
+    double *stats = static_cast<double *>(c->stats.p);
+    float *xf = static_cast<float *>(c->xf.p), *Pf = static_cast<float *>(c->Pf.p), *Qf = static_cast<float *>(c->Qf.p);
+    double *sums = static_cast<double *>(c->sums.p);
+    CB_TRY(do_fold(c, data, munc, m, n, ld, mo.pad, stats, stride));
+
+    auto sweep = [&]() -> int {
+        cb200_model f = mo;
+        f.return_nll = 0;
+        CB_TRY(do_forward(c, &f, stats, stride, m, n, lam, kap, qscale, nullptr, xf, Pf, Qf, nullptr, nullptr, nullptr,
+                          false));
+        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false));
+        return CB200_OK;
+    };
+    auto nll_only = [&](double *out) -> int {
+        cb200_model f = mo;
+        f.return_nll = 1;
+        CB_TRY(do_forward(c, &f, stats, stride, m, n, lam, kap, qscale, nullptr, nullptr, nullptr, nullptr, nullptr,
+                          sums, nullptr, false));
+        double s[2];
+        CB_TRY(read_sums(c, s));
+        *out = s[1];
+        return CB200_OK;
+    };
+
+    const int patience = 2;
+    if (n <= 5) {  // pyx:7998-8129: filter + smoother only
+        double cur = 0.0;
+        CB_TRY(sweep());
+        CB_TRY(nll_only(&cur));
+        res->skipped = 1;
+        res->initial_nll = res->final_nll = cur;
+        if (resid) CB_TRY(do_residuals(c, data, m, n, ld, xs, d, resid));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        return CB200_OK;
+    }
+
+    double prev = 1.0e16, cur = 0.0, init_nll = 0.0, rel_impr = 0.0, abs_rel = 0.0;
+    bool has_init = false, converged = false;
+    int iters_done = 0, stable = 0, inc = 0;
+    for (int i = 0; i < op->max_iters; ++i) {
+        iters_done = i + 1;
+        for (int t = 0; t < op->inner_iters; ++t) {
+            CB_TRY(sweep());
+            if (lam) {
+                Span sp(c, FAM_PREC);
+                CU_TRY(launch_update_lambda(stats, stats + stride, stats + 2 * stride, n, (double)m, xs, Ps, d, op->nu,
+                                            mo.lam_min, mo.lam_max, lam, c->stream));
+                c->launches += 1;
+            }
+            if (kap) {
+                Span sp(c, FAM_PREC);
+                CU_TRY(launch_update_kappa(d, to_model2(&mo), n, xs, Ps, lag, qscale, op->nu, mo.kap_min, mo.kap_max,
+                                           kap, c->stream));
+                c->launches += 1;
+            }
+        }
+        CB_TRY(nll_only(&cur));
+        if (nll_path) nll_path[i] = cur;
+        const bool has_prev = has_init;
+        if (!has_prev) {
+            init_nll = cur;
+            has_init = true;
+        } else if (cur > prev + (1.0e-12 * fmax(fabs(prev), 1.0))) {
+            inc += 1;
+        }
+        double delta, scale;
+        if (has_prev) {
+            delta = fabs(cur - prev);
+            scale = fabs(prev);
+        } else {
+            delta = 0.0;
+            scale = fabs(cur);
+        }
+        scale = fmax(scale, fabs(cur));
+        scale = fmax(scale, 1.0);
+        if (has_prev) {
+            rel_impr = (prev - cur) / scale;
+            abs_rel = delta / scale;
+        } else {
+            rel_impr = abs_rel = 0.0;
+        }
+        const double tol = op->rtol * scale;
+        prev = cur;
+        stable = (has_prev && delta <= tol) ? stable + 1 : 0;
+        if (stable >= patience) {
+            converged = true;
+            break;
+        }
+    }
+    if (resid) CB_TRY(do_residuals(c, data, m, n, ld, xs, d, resid));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    res->iters_done = iters_done;
+    res->converged = converged ? 1 : 0;
+    res->skipped = 0;
+    res->stable_iters = stable;
+    res->nll_increase_count = inc;
+    res->has_initial = has_init ? 1 : 0;
+    res->initial_nll = init_nll;
+    res->final_nll = prev;
+    res->final_abs_rel_change = abs_rel;
+    res->final_rel_improvement = rel_impr;
+    return CB200_OK;
+}
+
+// =====================================================================================
+// reference-facing path (host buffers)
+// =====================================================================================
+int cb200_host_sweep(cb200_ctx *c, const cb200_model *mo, const float *data, const float *munc, int64_t m, int64_t n,
+                     const float *lam, const float *kap, const float *qscale, float *xf, float *Pf, float *Qf, float *D,
+                     double *sum_d, double *sum_nll, float *xs, float *Ps, float *lag, int64_t lag_rows, float *resid) {
+    if (!c || !data || !munc) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (sum_d) *sum_d = 0.0;
+    if (sum_nll) *sum_nll = 0.0;
+    if (n <= 0 || m <= 0) return CB200_OK;
+    const int d = mo->state_dim;
+    const bool want_bwd = xs || Ps || lag || resid;
+    const bool store = xf || Pf || Qf || want_bwd;
+    int64_t ld = 0, ld2 = 0;
+    CB_TRY(upload_tracks(c, c->data, data, m, n, &ld));
+    CB_TRY(upload_tracks(c, c->munc, munc, m, n, &ld2));
+    const float *dlam, *dkap, *dqs;
+    CB_TRY(upload_vec(c, c->lam, lam, n, mo->use_lambda != 0, &dlam));
+    CB_TRY(upload_vec(c, c->kap, kap, n, mo->use_kappa != 0, &dkap));
+    CB_TRY(upload_vec(c, c->qs, qscale, n, mo->use_qscale != 0, &dqs));
+    const int64_t stride = round_up(n, 32);
+    CB_TRY(ensure(c, c->stats, (size_t)stride * 4 * 8));
+    double *stats = static_cast<double *>(c->stats.p);
+    CB_TRY(do_fold(c, static_cast<const float *>(c->data.p), static_cast<const float *>(c->munc.p), m, n, ld, mo->pad,
+                   stats, stride));
+    float *dxf = nullptr, *dPf = nullptr, *dQf = nullptr;
+    if (store) {
+        CB_TRY(ensure(c, c->xf, (size_t)n * d * 4));
+        CB_TRY(ensure(c, c->Pf, (size_t)n * d * d * 4));
+        CB_TRY(ensure(c, c->Qf, (size_t)n * d * d * 4));
+        dxf = static_cast<float *>(c->xf.p);
+        dPf = static_cast<float *>(c->Pf.p);
+        dQf = static_cast<float *>(c->Qf.p);
+    }
+    CB_TRY(ensure(c, c->D, (size_t)n * 4));
+    CB_TRY(do_forward(c, mo, stats, stride, m, n, dlam, dkap, dqs, nullptr, dxf, dPf, dQf, static_cast<float *>(c->D.p),
+                      static_cast<double *>(c->sums.p), nullptr, false));
+    if (xf) CB_TRY(d2h(c, xf, dxf, (size_t)n * d * 4));
+    if (Pf) CB_TRY(d2h(c, Pf, dPf, (size_t)n * d * d * 4));
+    if (Qf && n > 1) CB_TRY(d2h(c, Qf, dQf, (size_t)(n - 1) * d * d * 4));
+    if (D) CB_TRY(d2h(c, D, c->D.p, (size_t)n * 4));
+    if (want_bwd) {
+        CB_TRY(ensure(c, c->xs, (size_t)n * d * 4));
+        CB_TRY(ensure(c, c->Ps, (size_t)n * d * d * 4));
+        CB_TRY(ensure(c, c->lag, (size_t)n * d * d * 4));
+        const int64_t rows = n > 1 ? n - 1 : 1;
+        CB_TRY(do_backward(c, mo, n, dxf, dPf, dQf, nullptr, 1, static_cast<float *>(c->xs.p),
+                           static_cast<float *>(c->Ps.p), static_cast<float *>(c->lag.p), rows, nullptr, false));
+        if (xs) CB_TRY(d2h(c, xs, c->xs.p, (size_t)n * d * 4));
+        if (Ps) CB_TRY(d2h(c, Ps, c->Ps.p, (size_t)n * d * d * 4));
+        if (lag && n > 1) {
+            const int64_t r = lag_rows < n - 1 ? lag_rows : n - 1;
+            CB_TRY(d2h(c, lag, c->lag.p, (size_t)r * d * d * 4));
+        }
+        if (resid) {
+            CB_TRY(ensure(c, c->resid, (size_t)n * m * 4));
+            CB_TRY(do_residuals(c, static_cast<const float *>(c->data.p), m, n, ld, static_cast<float *>(c->xs.p), d,
+                                static_cast<float *>(c->resid.p)));
+            CB_TRY(d2h(c, resid, c->resid.p, (size_t)n * m * 4));
+        }
+    }
+    double s[2];
+    CB_TRY(read_sums(c, s));
+    if (sum_d) *sum_d = s[0];
+    if (sum_nll) *sum_nll = s[1];
+    return CB200_OK;
+}
+
+int cb200_host_forward_pass(cb200_ctx *c, const cb200_model *mo, const float *data, const float *munc, int64_t m,
+                            int64_t n, const int32_t *block_map, int64_t block_count, const float *lam,
+                            const float *kap, const float *qscale, float *xf, float *Pf, float *Qf, float *D,
+                            double *sum_d, double *sum_nll) {
+    if (n > 0 && m > 0) CB_TRY(check_block_map(block_map, n, block_count));
+    return cb200_host_sweep(c, mo, data, munc, m, n, lam, kap, qscale, xf, Pf, Qf, D, sum_d, sum_nll, nullptr, nullptr,
+                            nullptr, 0, nullptr);
+}
+
+int cb200_host_backward_pass(cb200_ctx *c, const cb200_model *mo, const float *data, int64_t m, int64_t n,
+                             const float *xf, const float *Pf, const float *Qf, float *xs, float *Ps, float *lag,
+                             int64_t lag_rows, float *resid) {
+    if (!c || !xf || !Pf || !Qf || !xs || !Ps || !lag) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return CB200_OK;
+    const int d = mo->state_dim;
+    CB_TRY(ensure(c, c->xf, (size_t)n * d * 4));
+    CB_TRY(ensure(c, c->Pf, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->Qf, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->xs, (size_t)n * d * 4));
+    CB_TRY(ensure(c, c->Ps, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->lag, (size_t)n * d * d * 4));
+    CB_TRY(h2d(c, c->xf.p, xf, (size_t)n * d * 4));
+    CB_TRY(h2d(c, c->Pf.p, Pf, (size_t)n * d * d * 4));
+    if (n > 1) CB_TRY(h2d(c, c->Qf.p, Qf, (size_t)(n - 1) * d * d * 4));
+    const int64_t rows = n > 1 ? n - 1 : 1;
+    CB_TRY(do_backward(c, mo, n, static_cast<float *>(c->xf.p), static_cast<float *>(c->Pf.p),
+                       static_cast<float *>(c->Qf.p), nullptr, 1, static_cast<float *>(c->xs.p),
+                       static_cast<float *>(c->Ps.p), static_cast<float *>(c->lag.p), rows, nullptr, false));
+    CB_TRY(d2h(c, xs, c->xs.p, (size_t)n * d * 4));
+    CB_TRY(d2h(c, Ps, c->Ps.p, (size_t)n * d * d * 4));
+    if (n > 1) {
+        const int64_t r = lag_rows < n - 1 ? lag_rows : n - 1;
+        CB_TRY(d2h(c, lag, c->lag.p, (size_t)r * d * d * 4));
+    }
+    if (resid && m > 0) {
+        if (!data) return fail(CB200_ERR_INVALID, "matrixData is required for residuals");
+        int64_t ld = 0;
+        CB_TRY(upload_tracks(c, c->data, data, m, n, &ld));
+        CB_TRY(ensure(c, c->resid, (size_t)n * m * 4));
+        CB_TRY(do_residuals(c, static_cast<const float *>(c->data.p), m, n, ld, static_cast<float *>(c->xs.p), d,
+                            static_cast<float *>(c->resid.p)));
+        CB_TRY(d2h(c, resid, c->resid.p, (size_t)n * m * 4));
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
+int cb200_host_ecm(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op, const float *data,
+                   const float *munc, int64_t m, int64_t n, const int32_t *block_map, int64_t block_count,
+                   const float *qscale, float *lam, float *kap, float *xs, float *Ps, float *lag, float *resid,
+                   cb200_ecm_result *res, double *nll_path) {
+    if (!c || !op || !res || !data || !munc) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    memset(res, 0, sizeof(*res));
+    if (n <= 0 || m <= 0) {
+        res->skipped = 1;
+        return CB200_OK;
+    }
+    CB_TRY(check_block_map(block_map, n, block_count));
+    const int d = mo->state_dim;
+    int64_t ld = 0, ld2 = 0;
+    CB_TRY(upload_tracks(c, c->data, data, m, n, &ld));
+    CB_TRY(upload_tracks(c, c->munc, munc, m, n, &ld2));
+    const float *dqs, *dlam_c, *dkap_c;
+    CB_TRY(upload_vec(c, c->qs, qscale, n, qscale != nullptr, &dqs));
+    CB_TRY(upload_vec(c, c->lam, lam, n, lam != nullptr, &dlam_c));
+    CB_TRY(upload_vec(c, c->kap, kap, n, kap != nullptr, &dkap_c));
+    CB_TRY(ensure(c, c->xs, (size_t)n * d * 4));
+    CB_TRY(ensure(c, c->Ps, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->lag, (size_t)n * d * d * 4));
+    float *dres = nullptr;
+    if (resid) {
+        CB_TRY(ensure(c, c->resid, (size_t)n * m * 4));
+        dres = static_cast<float *>(c->resid.p);
+    }
+    CB_TRY(cb200_ecm_device(c, mo, op, static_cast<const float *>(c->data.p), static_cast<const float *>(c->munc.p), m,
+                            n, ld, dqs, const_cast<float *>(dlam_c), const_cast<float *>(dkap_c),
+                            static_cast<float *>(c->xs.p), static_cast<float *>(c->Ps.p),
+                            static_cast<float *>(c->lag.p), dres, res, nll_path));
+    if (xs) CB_TRY(d2h(c, xs, c->xs.p, (size_t)n * d * 4));
+    if (Ps) CB_TRY(d2h(c, Ps, c->Ps.p, (size_t)n * d * d * 4));
+    if (lag && n > 1) CB_TRY(d2h(c, lag, c->lag.p, (size_t)(n - 1) * d * d * 4));
+    if (resid) CB_TRY(d2h(c, resid, dres, (size_t)n * m * 4));
+    if (lam) CB_TRY(d2h(c, lam, c->lam.p, (size_t)n * 4));
+    if (kap) CB_TRY(d2h(c, kap, c->kap.p, (size_t)n * 4));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1072 @@
+// consenrich_b200/csrc/ssm_kernels.cu -- sm_100a kernels of the Consenrich state-space hot path.
+//
+//   fold_kernel        one coalesced pass over data/munc [m x n] -> per-bin information-form
+//                      statistics (replaces _accumulateObservationValue, cconsenrich.pyx:259-283)
+//   scan_kernel<Fwd*>  forward Kalman filter as a single-pass decoupled look-back scan of
+//                      filtering elements (replaces the loops at cconsenrich.pyx:291-529, 538-707)
+//   scan_kernel<Bwd*>  RTS smoother as the reverse scan of smoothing elements
+//                      (replaces cconsenrich.pyx:6740-6848, 7116-7148)
+//   residual_kernel    postFitResiduals [n x m] = data^T - level   (cconsenrich.pyx:6846-6848)
+//   lambda/kappa       Student-t precision multipliers (cconsenrich.pyx:8210-8298, 7474-7521)
+//
+// The path is HBM-bound byte/double work: no tensor cores.  Global traffic is coalesced
+// (bins are the contiguous axis), per-thread bin chunks are transposed through padded shared
+// memory records, and the only inter-CTA dependency is the look-back on published tile
+// aggregates.
+#include <cuda_runtime.h>
+
+#include "ssm_kernels.cuh"
+
+namespace cb200 {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NWARPS = SCAN_THREADS / 32;
+
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class E>
+__device__ __forceinline__ E shfl_up_elem(const E &e, int d) {
+    E r;
+    const double *s = reinterpret_cast<const double *>(&e);
+    double *t = reinterpret_cast<double *>(&r);
+#pragma unroll
+    for (int i = 0; i < E::N; ++i) t[i] = __shfl_up_sync(FULL, s[i], d);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ E shfl_down_elem(const E &e, int d) {
+    E r;
+    const double *s = reinterpret_cast<const double *>(&e);
+    double *t = reinterpret_cast<double *>(&r);
+#pragma unroll
+    for (int i = 0; i < E::N; ++i) t[i] = __shfl_down_sync(FULL, s[i], d);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ E shfl_bcast_elem(const E &e, int src) {
+    E r;
+    const double *s = reinterpret_cast<const double *>(&e);
+    double *t = reinterpret_cast<double *>(&r);
+#pragma unroll
+    for (int i = 0; i < E::N; ++i) t[i] = __shfl_sync(FULL, s[i], src);
+    return r;
+}
+template <class E>
+__device__ __forceinline__ void store_elem(double *dst, const E &e) {
+    const double *s = reinterpret_cast<const double *>(&e);
+#pragma unroll
+    for (int i = 0; i < E::N; ++i) dst[i] = s[i];
+}
+template <class E>
+__device__ __forceinline__ E load_elem(const double *src) {
+    E r;
+    double *t = reinterpret_cast<double *>(&r);
+#pragma unroll
+    for (int i = 0; i < E::N; ++i) t[i] = src[i];
+    return r;
+}
+template <class E>
+__device__ __forceinline__ E load_elem_cg(const double *src) {
+    E r;
+    double *t = reinterpret_cast<double *>(&r);
+#pragma unroll
+    for (int i = 0; i < E::N; ++i) t[i] = __ldcg(src + i);
+    return r;
+}
+
+// =====================================================================================
+// fold kernel
+// =====================================================================================
+struct FoldAcc {
+    double s0, s1, s2, prod;
+    int esum;
+};
+
+__device__ __forceinline__ void fold_cell(FoldAcc &a, float zf, float vf, double pad) {
+    const double z = (double)zf;
+    double r = (double)vf + pad;
+    if (r < 1.0e-12) r = 1.0e-12;
+    const double w = 1.0 / r;
+    const double wz = w * z;
+    a.s0 += w;
+    a.s1 += wz;
+    a.s2 = fma(wz, z, a.s2);
+    // sum of logs as the log of a product: split r = mant * 2^e, mant in [1, 2)
+    const long long bits = __double_as_longlong(r);
+    a.esum += (int)((bits >> 52) & 0x7ff) - 1023;
+    a.prod *= __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+}
+
+__device__ __forceinline__ void fold_renorm(FoldAcc &a) {
+    const long long bits = __double_as_longlong(a.prod);
+    a.esum += (int)((bits >> 52) & 0x7ff) - 1023;
+    a.prod = __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+}
+
+__device__ __forceinline__ double fold_logsum(const FoldAcc &a) {
+    return log(a.prod) + (double)a.esum * 0.693147180559945309417232121458;
+}
+
+constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_UNROLL = 4;
+
+// VEC = 4: each thread owns 4 consecutive bins and streams float4 (needs 16-byte aligned rows);
+// VEC = 1: scalar loads, any alignment.
+template <int VEC>
+__global__ void __launch_bounds__(FOLD_THREADS)
+fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int64_t m, int64_t n, int64_t ld,
+            double pad, double *__restrict__ S0, double *__restrict__ S1, double *__restrict__ S2,
+            double *__restrict__ SL) {
+    const int64_t k0 = ((int64_t)blockIdx.x * FOLD_THREADS + threadIdx.x) * VEC;
+    if (k0 >= n) return;
+    FoldAcc acc[VEC];
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        acc[c].s0 = acc[c].s1 = acc[c].s2 = 0.0;
+        acc[c].prod = 1.0;
+        acc[c].esum = 0;
+    }
+    const float *dp = data + k0;
+    const float *vp = munc + k0;
+    int64_t j = 0;
+    int since = 0;
+    if (VEC == 4) {
+        for (; j + FOLD_UNROLL <= m; j += FOLD_UNROLL) {
+            float4 z[FOLD_UNROLL], v[FOLD_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FOLD_UNROLL; ++u) {
+                z[u] = __ldcs(reinterpret_cast<const float4 *>(dp + (j + u) * ld));
+                v[u] = __ldcs(reinterpret_cast<const float4 *>(vp + (j + u) * ld));
+            }
+#pragma unroll
+            for (int u = 0; u < FOLD_UNROLL; ++u) {
+                fold_cell(acc[0], z[u].x, v[u].x, pad);
+                fold_cell(acc[1 % VEC], z[u].y, v[u].y, pad);
+                fold_cell(acc[2 % VEC], z[u].z, v[u].z, pad);
+                fold_cell(acc[3 % VEC], z[u].w, v[u].w, pad);
+            }
+            since += FOLD_UNROLL;
+            if (since >= 512) {
+#pragma unroll
+                for (int c = 0; c < VEC; ++c) fold_renorm(acc[c]);
+                since = 0;
+            }
+        }
+        for (; j < m; ++j) {
+            const float4 z = __ldcs(reinterpret_cast<const float4 *>(dp + j * ld));
+            const float4 v = __ldcs(reinterpret_cast<const float4 *>(vp + j * ld));
+            fold_cell(acc[0], z.x, v.x, pad);
+            fold_cell(acc[1 % VEC], z.y, v.y, pad);
+            fold_cell(acc[2 % VEC], z.z, v.z, pad);
+            fold_cell(acc[3 % VEC], z.w, v.w, pad);
+        }
+    } else {
+        for (; j + FOLD_UNROLL <= m; j += FOLD_UNROLL) {
+            float z[FOLD_UNROLL], v[FOLD_UNROLL];
+#pragma unroll
+            for (int u = 0; u < FOLD_UNROLL; ++u) {
+                z[u] = __ldcs(dp + (j + u) * ld);
+                v[u] = __ldcs(vp + (j + u) * ld);
+            }
+#pragma unroll
+            for (int u = 0; u < FOLD_UNROLL; ++u) fold_cell(acc[0], z[u], v[u], pad);
+            since += FOLD_UNROLL;
+            if (since >= 512) {
+                fold_renorm(acc[0]);
+                since = 0;
+            }
+        }
+        for (; j < m; ++j) fold_cell(acc[0], __ldcs(dp + j * ld), __ldcs(vp + j * ld), pad);
+    }
+#pragma unroll
+    for (int c = 0; c < VEC; ++c) {
+        const int64_t k = k0 + c;
+        if (k < n) {
+            S0[k] = acc[c].s0;
+            S1[k] = acc[c].s1;
+            S2[k] = acc[c].s2;
+            SL[k] = fold_logsum(acc[c]);
+        }
+    }
+}
+
+// =====================================================================================
+// scan traits
+// =====================================================================================
+// Shared-memory record of one thread: CHUNK bins of BIN_BYTES plus 16 bytes of padding so that
+// 16-byte accesses of a quarter warp fall in distinct banks (record stride = 4 mod 8 words).
+template <int BIN_BYTES>
+struct RecGeom {
+    static constexpr int REC_BYTES = CHUNK * BIN_BYTES + 16;
+    __device__ static __forceinline__ unsigned char *slot(unsigned char *recs, int g) {
+        return recs + (g / CHUNK) * REC_BYTES + (g % CHUNK) * BIN_BYTES;
+    }
+};
+
+// ---- forward, 2-state ------------------------------------------------------------------
+// record per bin, in : [S0 S1][S2 SL][qk(f64) lam(f32) pad]        (48 bytes)
+//                 out: [Pf 4xf32][Qf 4xf32][xf 2xf32, D f32, pad]
+struct Fwd2 {
+    using Elem = Filt2;
+    using State = State2;
+    using Args = FwdArgs;
+    using G = RecGeom<48>;
+    static constexpr bool HAS_SUMS = true;
+    __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
+
+    __device__ static __forceinline__ Elem identity() { return filt2_identity(); }
+    __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt2_combine(a, b); }
+    __device__ static __forceinline__ State apply(const Elem &e, const State &s) { return filt2_apply(e, s); }
+    __device__ static __forceinline__ Elem from_state(const State &s) { return filt2_from_state(s); }
+    __device__ static __forceinline__ State elem_state(const Elem &e) {
+        return State2{e.b0, e.b1, e.C00, e.C01, e.C11};
+    }
+    __device__ static __forceinline__ State initial(const Args &a) {
+        if (a.init_state) return load_elem_cg<State2>(a.init_state);
+        return State2{a.state_init, 0.0, a.cov_init, 0.0, a.cov_init};
+    }
+
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+        double s0[CHUNK], s1[CHUNK], s2[CHUNK], sl[CHUNK];
+        float lm[CHUNK], kp[CHUNK], qs[CHUNK];
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int64_t k = p0 + tid + r * SCAN_THREADS;
+            const bool ok = k < a.n;
+            s0[r] = ok ? __ldg(a.S0 + k) : 0.0;
+            s1[r] = ok ? __ldg(a.S1 + k) : 0.0;
+            s2[r] = ok ? __ldg(a.S2 + k) : 0.0;
+            sl[r] = (ok && a.want_nll) ? __ldg(a.SL + k) : 0.0;
+            lm[r] = (ok && a.use_lambda) ? __ldg(a.lam + k) : 1.0f;
+            kp[r] = (ok && a.use_kappa) ? __ldg(a.kap + k) : 1.0f;
+            qs[r] = (ok && a.use_qscale) ? __ldg(a.qs + k) : 1.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            unsigned char *s = G::slot(recs, tid + r * SCAN_THREADS);
+            const double kappa = a.use_kappa ? clampd((double)kp[r], a.kap_min, a.kap_max) : 1.0;
+            const double lam = a.use_lambda ? clampd((double)lm[r], a.lam_min, a.lam_max) : 1.0;
+            const double qk = (double)qs[r] / kappa;
+            *reinterpret_cast<double2 *>(s) = make_double2(s0[r], s1[r]);
+            *reinterpret_cast<double2 *>(s + 16) = make_double2(s2[r], sl[r]);
+            *reinterpret_cast<double2 *>(s + 32) = make_double2(qk, __longlong_as_double((long long)__float_as_uint((float)lam)));
+        }
+    }
+
+    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t) {
+        Elem g = filt2_identity();
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
+                const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
+                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
+                const double qk = ql.x;
+                filt2_step(g, a.M, qk * a.M.q00, qk * a.M.q01, qk * a.M.q11, lam * s01.x, lam * s01.y);
+            }
+        }
+        return g;
+    }
+
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t,
+                                                 const State &st, double &acc_d, double &acc_nll) {
+        Kf2 s{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                unsigned char *b = rec + i * 48;
+                const double2 s01 = *reinterpret_cast<const double2 *>(b);
+                const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
+                const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
+                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
+                BinOut o;
+                kf2_step(s, a.M, ql.x, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.mlog2pi, a.want_nll != 0,
+                         a.nll_in_d != 0, o);
+                const float d = (float)o.stat;
+                acc_d += (double)d;
+                acc_nll += o.nll;
+                *reinterpret_cast<float4 *>(b) = make_float4((float)s.P00, (float)s.P01, (float)s.P10, (float)s.P11);
+                *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.Q00, (float)o.Q01, (float)o.Q10, (float)o.Q11);
+                *reinterpret_cast<float4 *>(b + 32) = make_float4((float)s.x0, (float)s.x1, d, 0.0f);
+            }
+        }
+    }
+
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int g = tid + r * SCAN_THREADS;
+            const int64_t k = p0 + g;
+            if (k < a.n) {
+                const unsigned char *s = G::slot(recs, g);
+                const float4 xd = *reinterpret_cast<const float4 *>(s + 32);
+                if (a.do_store) {
+                    reinterpret_cast<float4 *>(a.Pf)[k] = *reinterpret_cast<const float4 *>(s);
+                    if (k > 0) reinterpret_cast<float4 *>(a.Qf)[k - 1] = *reinterpret_cast<const float4 *>(s + 16);
+                    reinterpret_cast<float2 *>(a.xf)[k] = make_float2(xd.x, xd.y);
+                }
+                if (a.D) a.D[k] = xd.z;
+            }
+        }
+    }
+};
+
+// ---- forward, level --------------------------------------------------------------------
+// same input record; out: [xf Pf Qf D] in the first 16 bytes
+struct Fwd1 {
+    using Elem = Filt1;
+    using State = State1;
+    using Args = FwdArgs;
+    using G = RecGeom<48>;
+    static constexpr bool HAS_SUMS = true;
+    __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
+
+    __device__ static __forceinline__ Elem identity() { return filt1_identity(); }
+    __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt1_combine(a, b); }
+    __device__ static __forceinline__ State apply(const Elem &e, const State &s) { return filt1_apply(e, s); }
+    __device__ static __forceinline__ Elem from_state(const State &s) { return filt1_from_state(s); }
+    __device__ static __forceinline__ State elem_state(const Elem &e) { return State1{e.b, e.C}; }
+    __device__ static __forceinline__ State initial(const Args &a) {
+        if (a.init_state) return load_elem_cg<State1>(a.init_state);
+        return State1{a.state_init, a.cov_init};
+    }
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+        Fwd2::stage_in(a, recs, p0, tid);
+    }
+    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t) {
+        Elem g = filt1_identity();
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
+                const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
+                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
+                filt1_step(g, ql.x * a.M.q00, lam * s01.x, lam * s01.y);
+            }
+        }
+        return g;
+    }
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t,
+                                                 const State &st, double &acc_d, double &acc_nll) {
+        State1 s = st;
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                unsigned char *b = rec + i * 48;
+                const double2 s01 = *reinterpret_cast<const double2 *>(b);
+                const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
+                const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
+                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
+                BinOut o;
+                kf1_step(s, ql.x * a.M.q00, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.mlog2pi, a.want_nll != 0,
+                         a.nll_in_d != 0, o);
+                const float d = (float)o.stat;
+                acc_d += (double)d;
+                acc_nll += o.nll;
+                *reinterpret_cast<float4 *>(b) = make_float4((float)s.x, (float)s.P, (float)o.Q00, d);
+            }
+        }
+    }
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int g = tid + r * SCAN_THREADS;
+            const int64_t k = p0 + g;
+            if (k < a.n) {
+                const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
+                if (a.do_store) {
+                    a.xf[k] = o.x;
+                    a.Pf[k] = o.y;
+                    if (k > 0) a.Qf[k - 1] = o.z;
+                }
+                if (a.D) a.D[k] = o.w;
+            }
+        }
+    }
+};
+
+// ---- backward, 2-state -----------------------------------------------------------------
+// position q = n-1-k runs forward.  record per bin, in: [Pf][Qf row k][xf, pad]; out: [Ps][lag][xs]
+struct Bwd2 {
+    using Elem = Smo2;
+    using State = State2;
+    using Args = BwdArgs;
+    using G = RecGeom<48>;
+    static constexpr bool HAS_SUMS = false;
+    __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
+
+    __device__ static __forceinline__ Elem identity() { return smo2_identity(); }
+    __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo2_combine(a, b); }
+    __device__ static __forceinline__ State apply(const Elem &e, const State &s) { return smo2_apply(e, s); }
+    __device__ static __forceinline__ Elem from_state(const State &s) { return smo2_from_state(s); }
+    __device__ static __forceinline__ State elem_state(const Elem &e) {
+        return State2{e.g0, e.g1, e.L00, e.L01, e.L11};
+    }
+    __device__ static __forceinline__ State initial(const Args &a) {
+        if (a.tail_state) return load_elem_cg<State2>(a.tail_state);
+        return State2{0.0, 0.0, 0.0, 0.0, 0.0};
+    }
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+        float4 P[CHUNK], Q[CHUNK];
+        float2 x[CHUNK];
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int64_t k = a.n - 1 - (p0 + tid + r * SCAN_THREADS);
+            const bool ok = k >= 0;
+            P[r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.Pf) + k) : make_float4(0, 0, 0, 0);
+            // row n-1 of Qf holds nothing unless a following shard supplied it
+            Q[r] = (ok && (k < a.n - 1 || !a.is_last_shard)) ? __ldg(reinterpret_cast<const float4 *>(a.Qf) + k)
+                                                             : make_float4(0, 0, 0, 0);
+            x[r] = ok ? __ldg(reinterpret_cast<const float2 *>(a.xf) + k) : make_float2(0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            unsigned char *s = G::slot(recs, tid + r * SCAN_THREADS);
+            *reinterpret_cast<float4 *>(s) = P[r];
+            *reinterpret_cast<float4 *>(s + 16) = Q[r];
+            *reinterpret_cast<float4 *>(s + 32) = make_float4(x[r].x, x[r].y, 0.0f, 0.0f);
+        }
+    }
+    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t q0) {
+        Elem g = smo2_identity();
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                const float4 P = *reinterpret_cast<const float4 *>(rec + i * 48);
+                const float4 Q = *reinterpret_cast<const float4 *>(rec + i * 48 + 16);
+                const float4 x = *reinterpret_cast<const float4 *>(rec + i * 48 + 32);
+                Elem e;
+                if (q0 + i == 0 && a.is_last_shard) {
+                    e = smo2_from_state(State2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.w});
+                } else {
+                    const Rts2 r = rts2_gain(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
+                    e = smo2_from_rts(r, x.x, x.y, P.x, P.y, P.w);
+                }
+                g = smo2_combine(g, e);
+            }
+        }
+        return g;
+    }
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t q0,
+                                                 const State &st, double &, double &) {
+        Rs2 c{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                unsigned char *b = rec + i * 48;
+                const float4 P = *reinterpret_cast<const float4 *>(b);
+                const float4 Q = *reinterpret_cast<const float4 *>(b + 16);
+                const float4 x = *reinterpret_cast<const float4 *>(b + 32);
+                if (q0 + i == 0 && a.is_last_shard) {
+                    c = Rs2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.z, (double)P.w};
+                    // xs = xf, Ps = Pf already in place; lag row n-1 does not exist
+                } else {
+                    const Rts2 r = rts2_gain(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
+                    Smo2Out o;
+                    rts2_step(c, r, x.x, x.y, P.x, P.y, P.w, o);
+                    *reinterpret_cast<float4 *>(b) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
+                    *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
+                    *reinterpret_cast<float4 *>(b + 32) = make_float4((float)o.xs0, (float)o.xs1, 0.0f, 0.0f);
+                }
+            }
+        }
+    }
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int g = tid + r * SCAN_THREADS;
+            const int64_t k = a.n - 1 - (p0 + g);
+            if (k >= 0) {
+                const unsigned char *s = G::slot(recs, g);
+                reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(s);
+                if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
+                    reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(s + 16);
+                const float4 x = *reinterpret_cast<const float4 *>(s + 32);
+                reinterpret_cast<float2 *>(a.xs)[k] = make_float2(x.x, x.y);
+            }
+        }
+    }
+};
+
+// ---- backward, level -------------------------------------------------------------------
+// record per bin (16 bytes), in: [xf Pf Qf pad]; out: [xs Ps lag pad]
+struct Bwd1 {
+    using Elem = Smo1;
+    using State = State1;
+    using Args = BwdArgs;
+    using G = RecGeom<16>;
+    static constexpr bool HAS_SUMS = false;
+    __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
+
+    __device__ static __forceinline__ Elem identity() { return smo1_identity(); }
+    __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo1_combine(a, b); }
+    __device__ static __forceinline__ State apply(const Elem &e, const State &s) { return smo1_apply(e, s); }
+    __device__ static __forceinline__ Elem from_state(const State &s) { return smo1_from_state(s); }
+    __device__ static __forceinline__ State elem_state(const Elem &e) { return State1{e.g, e.L}; }
+    __device__ static __forceinline__ State initial(const Args &a) {
+        if (a.tail_state) return load_elem_cg<State1>(a.tail_state);
+        return State1{0.0, 0.0};
+    }
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+        float x[CHUNK], P[CHUNK], Q[CHUNK];
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int64_t k = a.n - 1 - (p0 + tid + r * SCAN_THREADS);
+            const bool ok = k >= 0;
+            x[r] = ok ? __ldg(a.xf + k) : 0.0f;
+            P[r] = ok ? __ldg(a.Pf + k) : 0.0f;
+            Q[r] = (ok && (k < a.n - 1 || !a.is_last_shard)) ? __ldg(a.Qf + k) : 0.0f;
+        }
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r)
+            *reinterpret_cast<float4 *>(G::slot(recs, tid + r * SCAN_THREADS)) = make_float4(x[r], P[r], Q[r], 0.0f);
+    }
+    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t q0) {
+        Elem g = smo1_identity();
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                const float4 v = *reinterpret_cast<const float4 *>(rec + i * 16);
+                Elem e;
+                if (q0 + i == 0 && a.is_last_shard) {
+                    e = smo1_from_state(State1{(double)v.x, (double)v.y});
+                } else {
+                    double pp, J;
+                    rts1_gain((double)v.y, (double)v.z, pp, J);
+                    e = smo1_from_rts((double)v.x, (double)v.y, pp, J);
+                }
+                g = smo1_combine(g, e);
+            }
+        }
+        return g;
+    }
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t q0,
+                                                 const State &st, double &, double &) {
+        double cx = r32(st.x), cP = r32(st.P);
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) {
+            if (i < cnt) {
+                unsigned char *b = rec + i * 16;
+                const float4 v = *reinterpret_cast<const float4 *>(b);
+                if (q0 + i == 0 && a.is_last_shard) {
+                    cx = (double)v.x;
+                    cP = (double)v.y;
+                } else {
+                    const double xf = (double)v.x, pf = (double)v.y;
+                    double pp, J;
+                    rts1_gain(pf, (double)v.z, pp, J);
+                    const double xsv = xf + J * (cx - xf);
+                    const double dP = cP - pp;
+                    double ps = pf + (J * J * dP);
+                    if (ps < 0.0) ps = 0.0;
+                    const float xs32 = (float)xsv, ps32 = (float)ps;
+                    *reinterpret_cast<float4 *>(b) = make_float4(xs32, ps32, (float)(pf + (J * dP)), 0.0f);
+                    cx = (double)xs32;
+                    cP = (double)ps32;
+                }
+            }
+        }
+    }
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+#pragma unroll
+        for (int r = 0; r < CHUNK; ++r) {
+            const int g = tid + r * SCAN_THREADS;
+            const int64_t k = a.n - 1 - (p0 + g);
+            if (k >= 0) {
+                const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
+                a.xs[k] = o.x;
+                a.Ps[k] = o.y;
+                if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard)) a.lag[k] = o.z;
+            }
+        }
+    }
+};
+
+// =====================================================================================
+// decoupled look-back (warp 0 of the CTA)
+// =====================================================================================
+template <class Tr>
+__device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWorkspace &ws, int tile, int lane) {
+    using Elem = typename Tr::Elem;
+    using State = typename Tr::State;
+    Elem running = Tr::identity();
+    bool have = false;
+    int base = tile - 1;
+    while (true) {
+        const int idx = base - lane;
+        int f;
+        while (true) {
+            f = (idx >= 0) ? ld_acquire(ws.flags + idx) : 2;
+            if (!__any_sync(FULL, f == 0)) break;
+        }
+        const unsigned pm = __ballot_sync(FULL, f == 2);
+        const int first = pm ? (__ffs(pm) - 1) : 32;
+        Elem e;
+        if (lane > first) {
+            e = Tr::identity();
+        } else if (f == 2) {
+            State s = (idx >= 0) ? load_elem_cg<State>(ws.tile_pref + (int64_t)idx * PREF_PITCH) : Tr::initial(a);
+            e = Tr::from_state(s);
+        } else {
+            e = load_elem_cg<Elem>(ws.tile_agg + (int64_t)idx * AGG_PITCH);
+        }
+        // ordered tree reduction: lane i holds tile base-i, lane i+d an earlier tile
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Elem o = shfl_down_elem(e, d);
+            if (lane + d < 32) e = Tr::combine(o, e);
+        }
+        running = have ? Tr::combine(e, running) : e;
+        have = true;
+        if (first < 32) break;
+        base -= 32;
+    }
+    const Elem r0 = shfl_bcast_elem(running, 0);
+    return Tr::elem_state(r0);
+}
+
+// =====================================================================================
+// scan kernel
+// =====================================================================================
+template <class Tr>
+struct ScanSmem {
+    static constexpr int N = Tr::Elem::N;
+    static constexpr int SN = Tr::State::N;
+    static constexpr int REC_TOTAL = SCAN_THREADS * Tr::G::REC_BYTES;
+    // doubles after the records
+    static constexpr int OFF_WAGG = 0;                     // [NWARPS][N]
+    static constexpr int OFF_WEXCL = OFF_WAGG + NWARPS * N;  // [NWARPS][N]
+    static constexpr int OFF_TAGG = OFF_WEXCL + NWARPS * N;  // [N]
+    static constexpr int OFF_TSTATE = OFF_TAGG + N;          // [SN] exclusive prefix state of the tile
+    static constexpr int OFF_TINCL = OFF_TSTATE + SN;        // [SN]
+    static constexpr int OFF_RED = OFF_TINCL + SN;           // [NWARPS][2]
+    static constexpr int OFF_END = OFF_RED + NWARPS * 2;
+    static constexpr int BYTES = REC_TOTAL + OFF_END * 8 + 16;
+};
+
+template <class Tr, bool AGG_ONLY>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles) {
+    using Elem = typename Tr::Elem;
+    using State = typename Tr::State;
+    using SM = ScanSmem<Tr>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    unsigned char *recs = smem;
+    double *sd = reinterpret_cast<double *>(smem + SM::REC_TOTAL);
+    int *s_tile = reinterpret_cast<int *>(sd + SM::OFF_END);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile[0] = AGG_ONLY ? (int)blockIdx.x : atomicAdd(ws.counters, 1);
+    __syncthreads();
+    const int tile = s_tile[0];
+    const int64_t p0 = (int64_t)tile * TILE_BINS;
+    const int64_t q0 = p0 + (int64_t)tid * CHUNK;
+
+    Tr::stage_in(a, recs, p0, tid);
+    __syncthreads();
+
+    int64_t rem = a.n - q0;
+    const int cnt = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
+    unsigned char *myrec = recs + tid * Tr::G::REC_BYTES;
+    const Elem mine = Tr::pass1(a, myrec, cnt, q0);
+
+    // inclusive Kogge-Stone scan across the warp
+    Elem inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Elem o = shfl_up_elem(inc, d);
+        if (lane >= d) inc = Tr::combine(o, inc);
+    }
+    if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
+    __syncthreads();
+
+    if (warp == 0) {
+        // exclusive prefixes across warps and the tile aggregate (all lanes redundantly)
+        Elem run = load_elem<Elem>(sd + SM::OFF_WAGG);
+        if (lane == 0) store_elem(sd + SM::OFF_WEXCL, Tr::identity());
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) {
+            if (lane == 0) store_elem(sd + SM::OFF_WEXCL + w * SM::N, run);
+            run = Tr::combine(run, load_elem<Elem>(sd + SM::OFF_WAGG + w * SM::N));
+        }
+        if (lane == 0) store_elem(sd + SM::OFF_TAGG, run);
+        __syncwarp();
+        if (AGG_ONLY) {
+            if (lane < SM::N) ws.tile_agg[(int64_t)tile * AGG_PITCH + lane] = sd[SM::OFF_TAGG + lane];
+        } else {
+            State pref;
+            if (tile == 0) {
+                pref = Tr::initial(a);
+            } else {
+                if (lane < SM::N) {
+                    ws.tile_agg[(int64_t)tile * AGG_PITCH + lane] = sd[SM::OFF_TAGG + lane];
+                    __threadfence();
+                }
+                __syncwarp();
+                if (lane == 0) st_release(ws.flags + tile, 1);
+                pref = lookback<Tr>(a, ws, tile, lane);
+            }
+            const State incl = Tr::apply(run, pref);
+            if (lane == 0) {
+                store_elem(sd + SM::OFF_TSTATE, pref);
+                store_elem(sd + SM::OFF_TINCL, incl);
+            }
+            __syncwarp();
+            if (lane < SM::SN) {
+                ws.tile_pref[(int64_t)tile * PREF_PITCH + lane] = sd[SM::OFF_TINCL + lane];
+                __threadfence();
+            }
+            __syncwarp();
+            if (lane == 0) st_release(ws.flags + tile, 2);
+        }
+    }
+    if (AGG_ONLY) return;
+    __syncthreads();
+
+    const State tpref = load_elem<State>(sd + SM::OFF_TSTATE);
+    State wst = tpref;
+    if (warp > 0) wst = Tr::apply(load_elem<Elem>(sd + SM::OFF_WEXCL + warp * SM::N), tpref);
+    const Elem lex = shfl_up_elem(inc, 1);
+    State start = wst;
+    if (lane > 0) start = Tr::apply(lex, wst);
+
+    double acc0 = 0.0, acc1 = 0.0;
+    Tr::pass2(a, myrec, cnt, q0, start, acc0, acc1);
+
+    if (Tr::HAS_SUMS) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            acc0 += __shfl_xor_sync(FULL, acc0, d);
+            acc1 += __shfl_xor_sync(FULL, acc1, d);
+        }
+        if (lane == 0) {
+            sd[SM::OFF_RED + warp * 2] = acc0;
+            sd[SM::OFF_RED + warp * 2 + 1] = acc1;
+        }
+    }
+    __syncthreads();
+    Tr::stage_out(a, recs, p0, tid);
+
+    if (Tr::HAS_SUMS) {
+        if (tid == 0) {
+            double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARPS; ++w) {
+                t0 += sd[SM::OFF_RED + w * 2];
+                t1 += sd[SM::OFF_RED + w * 2 + 1];
+            }
+            ws.partials[(int64_t)tile * 2] = t0;
+            ws.partials[(int64_t)tile * 2 + 1] = t1;
+            __threadfence();
+            const int done = atomicAdd(ws.counters + 1, 1);
+            __threadfence();
+            s_tile[1] = (done == ntiles - 1) ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_tile[1] && warp == 0) {
+            // the last CTA to finish adds the per-tile partial sums in tile order
+            double t0 = 0.0, t1 = 0.0;
+            for (int t = lane; t < ntiles; t += 32) {
+                t0 += __ldcg(ws.partials + (int64_t)t * 2);
+                t1 += __ldcg(ws.partials + (int64_t)t * 2 + 1);
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                t0 += __shfl_xor_sync(FULL, t0, d);
+                t1 += __shfl_xor_sync(FULL, t1, d);
+            }
+            double *sums = Tr::sums(a);
+            if (lane == 0 && sums != nullptr) {
+                sums[0] = t0;
+                sums[1] = t1;
+            }
+        }
+    }
+}
+
+// Ordered reduction of the per-tile aggregates of a shard into one element (aggregate-only mode).
+template <class Tr>
+__global__ void __launch_bounds__(256) reduce_tile_aggs_kernel(const double *tile_agg, int ntiles, double *out) {
+    using Elem = typename Tr::Elem;
+    __shared__ double sh[256 * Tr::Elem::N];
+    const int tid = threadIdx.x;
+    const int per = (ntiles + 255) / 256;
+    Elem e = Tr::identity();
+    for (int i = 0; i < per; ++i) {
+        const int t = tid * per + i;
+        if (t < ntiles) e = Tr::combine(e, load_elem<Elem>(tile_agg + (int64_t)t * AGG_PITCH));
+    }
+    store_elem(sh + tid * Tr::Elem::N, e);
+    __syncthreads();
+    for (int s = 1; s < 256; s <<= 1) {
+        if ((tid % (2 * s)) == 0 && tid + s < 256) {
+            const Elem a = load_elem<Elem>(sh + tid * Tr::Elem::N);
+            const Elem b = load_elem<Elem>(sh + (tid + s) * Tr::Elem::N);
+            store_elem(sh + tid * Tr::Elem::N, Tr::combine(a, b));
+        }
+        __syncthreads();
+    }
+    if (tid < Tr::Elem::N) out[tid] = sh[tid];
+}
+
+template <class Tr>
+__global__ void forward_shard_prefix_kernel(const double *aggs, int rank, double state_init, double cov_init,
+                                            double *init_state) {
+    using Elem = typename Tr::Elem;
+    using State = typename Tr::State;
+    FwdArgs a{};
+    a.init_state = nullptr;
+    a.state_init = state_init;
+    a.cov_init = cov_init;
+    State s = Tr::initial(a);
+    for (int r = 0; r < rank; ++r) s = Tr::apply(load_elem<Elem>(aggs + (int64_t)r * AGG_PITCH), s);
+    store_elem(init_state, s);
+}
+
+template <class Tr>
+__global__ void backward_shard_prefix_kernel(const double *aggs, int rank, int n_shards, double *tail_state) {
+    using Elem = typename Tr::Elem;
+    using State = typename Tr::State;
+    BwdArgs a{};
+    a.tail_state = nullptr;
+    State s = Tr::initial(a);
+    for (int r = n_shards - 1; r > rank; --r) s = Tr::apply(load_elem<Elem>(aggs + (int64_t)r * AGG_PITCH), s);
+    store_elem(tail_state, s);
+}
+
+// =====================================================================================
+// residuals: resid[k][j] = data[j][k] - level[k]
+// =====================================================================================
+constexpr int RES_BINS = 128;
+constexpr int RES_TRACKS = 32;
+constexpr int RES_THREADS = 256;
+
+__global__ void __launch_bounds__(RES_THREADS)
+residual_kernel(const float *__restrict__ data, int64_t m, int64_t n, int64_t ld, const float *__restrict__ xs,
+                int dim, float *__restrict__ resid) {
+    __shared__ float tile[RES_TRACKS][RES_BINS + 1];
+    __shared__ double lvl[RES_BINS];
+    const int64_t k0 = (int64_t)blockIdx.x * RES_BINS;
+    const int64_t j0 = (int64_t)blockIdx.y * RES_TRACKS;
+    const int nb = (int)min((int64_t)RES_BINS, n - k0);
+    const int nt = (int)min((int64_t)RES_TRACKS, m - j0);
+    const int tid = threadIdx.x;
+    if (tid < nb) lvl[tid] = (double)__ldg(xs + (k0 + tid) * dim);
+    for (int idx = tid; idx < nt * RES_BINS; idx += RES_THREADS) {
+        const int jj = idx / RES_BINS, kk = idx % RES_BINS;
+        if (kk < nb) tile[jj][kk] = __ldcs(data + (j0 + jj) * ld + k0 + kk);
+    }
+    __syncthreads();
+    const int total = nb * nt;
+    for (int idx = tid; idx < total; idx += RES_THREADS) {
+        const int kk = idx / nt, jj = idx - kk * nt;
+        const float r = (float)((double)tile[jj][kk] - lvl[kk]);
+        __stcs(resid + (k0 + kk) * m + j0 + jj, r);
+    }
+}
+
+// =====================================================================================
+// Student-t precision multipliers
+// =====================================================================================
+__global__ void lambda_kernel(const double *__restrict__ S0, const double *__restrict__ S1,
+                              const double *__restrict__ S2, int64_t n, double m, const float *__restrict__ xs,
+                              const float *__restrict__ Ps, int dim, double nu, double lo, double hi,
+                              float *__restrict__ lam) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double lvl = (double)xs[k * dim];
+    const double p00 = (double)Ps[k * dim * dim];
+    lam[k] = (float)lambda_update(S0[k], S1[k], S2[k], lvl, p00, m, nu, lo, hi);
+}
+
+__global__ void kappa2_kernel(Model2 M, double qi00, double qi01, double qi10, double qi11, int64_t n,
+                              const float *__restrict__ xs, const float *__restrict__ Ps,
+                              const float *__restrict__ lag, const float *__restrict__ qs, double nu, double lo,
+                              double hi, float *__restrict__ kap) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) kap[0] = 1.0f;
+    if (k >= n - 1) return;
+    const float2 x = reinterpret_cast<const float2 *>(xs)[k], y = reinterpret_cast<const float2 *>(xs)[k + 1];
+    const float4 P = reinterpret_cast<const float4 *>(Ps)[k], Py = reinterpret_cast<const float4 *>(Ps)[k + 1];
+    const float4 C = reinterpret_cast<const float4 *>(lag)[k];
+    const double q = qs ? (double)qs[k + 1] : 1.0;
+    kap[k + 1] = (float)kappa2_update(M, qi00, qi01, qi10, qi11, x.x, x.y, P.x, P.y, P.z, P.w, y.x, y.y, Py.x, Py.y,
+                                      Py.z, Py.w, C.x, C.y, C.z, C.w, q, qs != nullptr, nu, lo, hi);
+}
+
+__global__ void kappa1_kernel(double q0inv, int64_t n, const float *__restrict__ xs, const float *__restrict__ Ps,
+                              const float *__restrict__ lag, const float *__restrict__ qs, double nu, double lo,
+                              double hi, float *__restrict__ kap) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) kap[0] = 1.0f;
+    if (k >= n - 1) return;
+    const double q = qs ? (double)qs[k + 1] : 1.0;
+    kap[k + 1] = (float)kappa1_update(q0inv, (double)xs[k], (double)Ps[k], (double)xs[k + 1], (double)Ps[k + 1],
+                                      (double)lag[k], q, qs != nullptr, nu, lo, hi);
+}
+
+template <class Tr, bool AGG_ONLY>
+cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int64_t n, cudaStream_t st,
+                        int *launches) {
+    const int ntiles = (int)scan_num_tiles(n);
+    if (ntiles <= 0) return cudaSuccess;
+    if (!AGG_ONLY) {
+        // flags [ntiles] and counters [2] are contiguous
+        cudaError_t e = cudaMemsetAsync(ws.flags, 0, sizeof(int32_t) * ((size_t)ntiles + 2), st);
+        if (e != cudaSuccess) return e;
+    }
+    scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles);
+    if (launches) *launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    if (AGG_ONLY) {
+        reduce_tile_aggs_kernel<Tr><<<1, 256, 0, st>>>(ws.tile_agg, ntiles, a.agg_out);
+        if (launches) *launches += 1;
+        e = cudaGetLastError();
+    }
+    return e;
+}
+
+template <class Tr>
+cudaError_t set_smem_attr() {
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel<Tr, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         ScanSmem<Tr>::BYTES);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(scan_kernel<Tr, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                ScanSmem<Tr>::BYTES);
+}
+
+}  // namespace
+
+// =====================================================================================
+// host-side launchers
+// =====================================================================================
+int64_t scan_num_tiles(int64_t n) { return (n + TILE_BINS - 1) / TILE_BINS; }
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+size_t scan_workspace_bytes(int64_t n) {
+    const size_t t = (size_t)scan_num_tiles(n) + 1;
+    return align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
+           align_up((t + 2) * 4, 256);
+}
+
+ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
+    const size_t t = (size_t)scan_num_tiles(n) + 1;
+    unsigned char *p = static_cast<unsigned char *>(base);
+    ScanWorkspace ws;
+    ws.tile_agg = reinterpret_cast<double *>(p);
+    p += align_up(t * AGG_PITCH * 8, 256);
+    ws.tile_pref = reinterpret_cast<double *>(p);
+    p += align_up(t * PREF_PITCH * 8, 256);
+    ws.partials = reinterpret_cast<double *>(p);
+    p += align_up(t * 2 * 8, 256);
+    ws.flags = reinterpret_cast<int32_t *>(p);
+    ws.counters = ws.flags + scan_num_tiles(n);  // contiguous with flags: one memset clears both
+    return ws;
+}
+
+cudaError_t configure_kernels() {
+    cudaError_t e;
+    if ((e = set_smem_attr<Fwd2>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Fwd1>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Bwd2>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Bwd1>()) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
+                        double *S0, double *S1, double *S2, double *SL, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(munc) & 15) == 0);
+    if (vec) {
+        const int64_t threads = (n + 3) / 4;
+        const unsigned grid = (unsigned)((threads + FOLD_THREADS - 1) / FOLD_THREADS);
+        fold_kernel<4><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, S0, S1, S2, SL);
+    } else {
+        const unsigned grid = (unsigned)((n + FOLD_THREADS - 1) / FOLD_THREADS);
+        fold_kernel<1><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, S0, S1, S2, SL);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forward(int dim, const FwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
+                           cudaStream_t st, int *launches) {
+    if (dim == 2)
+        return aggregate_only ? launch_scan<Fwd2, true>(a, ws, a.n, st, launches)
+                              : launch_scan<Fwd2, false>(a, ws, a.n, st, launches);
+    return aggregate_only ? launch_scan<Fwd1, true>(a, ws, a.n, st, launches)
+                          : launch_scan<Fwd1, false>(a, ws, a.n, st, launches);
+}
+
+cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
+                            cudaStream_t st, int *launches) {
+    if (dim == 2)
+        return aggregate_only ? launch_scan<Bwd2, true>(a, ws, a.n, st, launches)
+                              : launch_scan<Bwd2, false>(a, ws, a.n, st, launches);
+    return aggregate_only ? launch_scan<Bwd1, true>(a, ws, a.n, st, launches)
+                          : launch_scan<Bwd1, false>(a, ws, a.n, st, launches);
+}
+
+cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
+                             float *resid, cudaStream_t st) {
+    if (n <= 0 || m <= 0) return cudaSuccess;
+    const int64_t gy = (m + RES_TRACKS - 1) / RES_TRACKS;
+    if (gy > 65535) return cudaErrorInvalidValue;
+    dim3 grid((unsigned)((n + RES_BINS - 1) / RES_BINS), (unsigned)gy);
+    residual_kernel<<<grid, RES_THREADS, 0, st>>>(data, m, n, ld, xs, dim, resid);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_lambda(const double *S0, const double *S1, const double *S2, int64_t n, double m,
+                                 const float *xs, const float *Ps, int dim, double nu, double lo, double hi,
+                                 float *lam, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    lambda_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S0, S1, S2, n, m, xs, Ps, dim, nu, lo, hi, lam);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_kappa(int dim, const Model2 &M, int64_t n, const float *xs, const float *Ps,
+                                const float *lag, const float *qs, double nu, double lo, double hi, float *kap,
+                                cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (dim == 2) {
+        const double det = M.q00 * M.q11 - M.q01 * M.q10;
+        kappa2_kernel<<<grid, 256, 0, st>>>(M, M.q11 / det, -M.q01 / det, -M.q10 / det, M.q00 / det, n, xs, Ps, lag,
+                                            qs, nu, lo, hi, kap);
+    } else {
+        kappa1_kernel<<<grid, 256, 0, st>>>(1.0 / M.q00, n, xs, Ps, lag, qs, nu, lo, hi, kap);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_forward_shard_prefix(int dim, const double *aggs, int rank, double state_init,
+                                        double cov_init, double *init_state, cudaStream_t st) {
+    if (dim == 2)
+        forward_shard_prefix_kernel<Fwd2><<<1, 1, 0, st>>>(aggs, rank, state_init, cov_init, init_state);
+    else
+        forward_shard_prefix_kernel<Fwd1><<<1, 1, 0, st>>>(aggs, rank, state_init, cov_init, init_state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_backward_shard_prefix(int dim, const double *aggs, int rank, int n_shards,
+                                         double *tail_state, cudaStream_t st) {
+    if (dim == 2)
+        backward_shard_prefix_kernel<Bwd2><<<1, 1, 0, st>>>(aggs, rank, n_shards, tail_state);
+    else
+        backward_shard_prefix_kernel<Bwd1><<<1, 1, 0, st>>>(aggs, rank, n_shards, tail_state);
+    return cudaGetLastError();
+}
+
+}  // namespace cb200

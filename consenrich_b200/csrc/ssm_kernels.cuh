@@ -1,0 +1,77 @@
+// consenrich_b200/csrc/ssm_kernels.cuh -- launch interface between the C ABI (cabi.cu) and the
+// sm_100a kernels (ssm_kernels.cu).  Device pointers only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ssm_math.cuh"
+
+namespace cb200 {
+
+// Geometry of the look-back scans: every thread owns CHUNK consecutive bins, a tile is
+// SCAN_THREADS * CHUNK bins.
+constexpr int SCAN_THREADS = 128;
+constexpr int CHUNK = 8;
+constexpr int TILE_BINS = SCAN_THREADS * CHUNK;
+constexpr int AGG_PITCH = 16;   // doubles per published tile aggregate (14 used)
+constexpr int PREF_PITCH = 8;   // doubles per published tile prefix state (5 used)
+
+struct ScanWorkspace {    // sized by scan_workspace_bytes(n); zeroed flags/counters per launch
+    double *tile_agg;     // [ntiles][AGG_PITCH]
+    double *tile_pref;    // [ntiles][PREF_PITCH]
+    double *partials;     // [ntiles][2]
+    int32_t *flags;       // [ntiles]  0 = nothing, 1 = aggregate published, 2 = prefix published
+    int32_t *counters;    // [0] dynamic tile ticket, [1] tiles finished
+};
+
+struct FwdArgs {
+    const double *S0, *S1, *S2, *SL;
+    const float *lam, *kap, *qs;
+    const double *init_state;  // device, or nullptr -> model prior
+    float *xf, *Pf, *Qf, *D;
+    double *sums;              // device double[2] or nullptr
+    double *agg_out;           // aggregate-only mode: shard aggregate destination
+    int64_t n;
+    double m, mlog2pi;
+    Model2 M;
+    double state_init, cov_init;
+    double lam_min, lam_max, kap_min, kap_max;
+    int32_t use_lambda, use_kappa, use_qscale, want_nll, nll_in_d, do_store;
+};
+
+struct BwdArgs {
+    const float *xf, *Pf, *Qf;
+    const double *tail_state;  // device, or nullptr -> this shard ends the chromosome
+    float *xs, *Ps, *lag;
+    double *agg_out;
+    int64_t n, lag_rows;
+    Model2 M;
+    int32_t is_last_shard;
+};
+
+size_t scan_workspace_bytes(int64_t n);
+ScanWorkspace scan_workspace_carve(void *base, int64_t n);
+int64_t scan_num_tiles(int64_t n);
+
+// every launcher returns the cudaError_t of the launch (cudaGetLastError)
+cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
+                        double *S0, double *S1, double *S2, double *SL, cudaStream_t st);
+cudaError_t launch_forward(int dim, const FwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
+                           cudaStream_t st, int *launches);
+cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
+                            cudaStream_t st, int *launches);
+cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
+                             float *resid, cudaStream_t st);
+cudaError_t launch_update_lambda(const double *S0, const double *S1, const double *S2, int64_t n, double m,
+                                 const float *xs, const float *Ps, int dim, double nu, double lo, double hi,
+                                 float *lam, cudaStream_t st);
+cudaError_t launch_update_kappa(int dim, const Model2 &M, int64_t n, const float *xs, const float *Ps,
+                                const float *lag, const float *qs, double nu, double lo, double hi, float *kap,
+                                cudaStream_t st);
+cudaError_t launch_forward_shard_prefix(int dim, const double *aggs, int rank, double state_init,
+                                        double cov_init, double *init_state, cudaStream_t st);
+cudaError_t launch_backward_shard_prefix(int dim, const double *aggs, int rank, int n_shards,
+                                         double *tail_state, cudaStream_t st);
+cudaError_t configure_kernels();
+
+}  // namespace cb200

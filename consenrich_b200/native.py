@@ -1,0 +1,492 @@
+"""Host-side mirror of the six native entry points of ``consenrich.cconsenrich`` that sit on the
+state-space hot path, backed by libconsenrich_b200.so (sm_100a).
+
+Same names, keyword arguments, return tuples and ValueError texts as the reference
+(``/root/reference/src/consenrich/cconsenrich.pyx``):
+
+* ``cforwardPass``             pyx:6393-6632      * ``cbackwardPass``            pyx:6635-6850
+* ``cforwardPassLevel``        pyx:6853-7049      * ``cbackwardPassLevel``       pyx:7052-7150
+* ``cfixedBackgroundECM``      pyx:7660-8442      * ``cfixedBackgroundECMLevel`` pyx:7153-7657
+
+``install()`` replaces those attributes on the reference's module (the seam the reference's own
+tests patch, tests/test_core.py:1317), so ``consenrich.core.runConsenrich`` runs on the GPU
+unchanged.  Arguments the reference accepts but never forwards to its loops (``chunkSize``,
+``projectStateDuringFiltering``, ``stateLowerBound``/``stateUpperBound``; pyx:6403-6406) are
+accepted and ignored here too.  Adaptive process noise (``ECM_useAPN`` without a
+``processQScale``; pyx:510-527) is a per-bin nonlinear feedback that no associative scan can
+express: it raises NotImplementedError instead of silently running something else.
+
+There is no CPU fallback: without the built library or without a CUDA device every function
+raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__all__ = ["cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPassLevel",
+           "cfixedBackgroundECM", "cfixedBackgroundECMLevel", "sweep", "install", "uninstall"]
+
+_HOT_PATH = ("cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPassLevel",
+             "cfixedBackgroundECM", "cfixedBackgroundECMLevel")
+
+
+def _f32(x) -> float:
+    """Round a Python scalar to C float and widen back (Cython ``float`` arguments)."""
+    return float(np.float32(x))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _c32(a, name, ndim):
+    if not (isinstance(a, np.ndarray) and a.dtype == np.float32 and a.ndim == ndim and a.flags.c_contiguous):
+        raise ValueError(f"{name}: Buffer dtype mismatch / not C-contiguous float32 ndim={ndim}")
+    return a
+
+
+def _vec32(a, name, n):
+    if a is None:
+        return None
+    a = _c32(a, name, 1)
+    if a.shape[0] != n:
+        raise ValueError(f"{name} length must match intervalCount")
+    return a
+
+
+def _coerce_qscale(q, n):
+    """cconsenrich.pyx:101-131 (_coerceProcessQScale)."""
+    arr = np.ascontiguousarray(q, dtype=np.float32).reshape(-1)
+    if arr.shape[0] != n:
+        raise ValueError("processQScale length must match intervalCount")
+    if n > 0:
+        a64 = arr.astype(np.float64)
+        if (~np.isfinite(a64) | (a64 <= 0.0)).any():
+            raise ValueError("processQScale must contain only positive finite values")
+        if abs(float(a64[0]) - 1.0) > 1.0e-6:
+            raise ValueError("processQScale[0] must be 1.0")
+    return arr
+
+
+def _check_bounds(lo, hi, is_obs):
+    """cconsenrich.pyx:143-151."""
+    if lo <= 0.0 or hi <= 0.0 or hi < lo:
+        raise ValueError(("observation" if is_obs else "process")
+                         + " precision multiplier bounds must satisfy 0 < min <= max")
+
+
+def _apn_live(useAPN, use_qscale, Q0, dim) -> bool:
+    """True when the reference would run the adaptive-process-noise feedback (pyx:6574-6576, 510)."""
+    if not useAPN or use_qscale:
+        return False
+    q_diag = 0.5 * (float(Q0[0, 0]) + float(Q0[1, 1])) if dim == 2 else float(Q0[0, 0])
+    return q_diag > 1.0e-12
+
+
+_APN_MSG = ("ECM_useAPN without processQScale is a sequential nonlinear feedback (cconsenrich.pyx:510-527) that the "
+            "parallel-in-time scan cannot express; consenrich_b200 has no CPU fallback. Pass processQScale or "
+            "disable APN.")
+
+
+def _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kapMin, kapMax, use_lambda, use_kappa,
+           use_qscale, returnNLL, storeNLLInD):
+    mo = _lib.Model()
+    mo.state_dim = dim
+    mo.use_lambda, mo.use_kappa, mo.use_qscale = int(use_lambda), int(use_kappa), int(use_qscale)
+    mo.return_nll, mo.store_nll_in_d = int(bool(returnNLL)), int(bool(storeNLLInD))
+    if dim == 2:
+        Fm = np.asarray(matrixF)
+        mo.F[:] = [float(Fm[0, 0]), float(Fm[0, 1]), float(Fm[1, 0]), float(Fm[1, 1])]
+        mo.Q0[:] = [float(Q0[0, 0]), float(Q0[0, 1]), float(Q0[1, 0]), float(Q0[1, 1])]
+    else:
+        mo.F[:] = [1.0, 0.0, 0.0, 1.0]
+        mo.Q0[:] = [float(Q0[0, 0]), 0.0, 0.0, 0.0]
+    mo.state_init, mo.cov_init, mo.pad = _f32(stateInit), _f32(stateCovarInit), _f32(pad)
+    mo.lam_min, mo.lam_max, mo.kap_min, mo.kap_max = lamMin, lamMax, kapMin, kapMax
+    return mo
+
+
+def _ctx(device=None):
+    return _lib.default_context(0 if device is None else int(device))
+
+
+def _forward(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount, stateInit,
+             stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD, returnNLL, storeNLLInD,
+             lambdaExp, processPrecExp, useObs, useProc, useAPN, lamMin, lamMax, kapMin, kapMax, processQScale):
+    data = _c32(matrixData, "matrixData", 2)
+    munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
+    m, n = data.shape
+    do_store = stateForward is not None
+    use_lambda = bool(useObs and (lambdaExp is not None))
+    use_qscale = processQScale is not None
+    use_kappa = bool(useProc and (processPrecExp is not None) and ((not useAPN) or use_qscale))
+    qs = _coerce_qscale(processQScale, n) if use_qscale else None
+    if n <= 0 or m <= 0:  # pyx:6494-6501
+        d = np.empty(n, dtype=np.float32) if vectorD is None else vectorD
+        return (np.float32(0.0), 0, d, 0.0) if returnNLL else (np.float32(0.0), 0, d)
+    if blockCount <= 0:
+        raise ValueError("blockCount must be positive")
+    if munc.shape[0] != m or munc.shape[1] != n:
+        raise ValueError("matrixPluginMuncInit shape must match matrixData shape")
+    Q0 = np.asarray(matrixQ0)
+    if dim == 2:
+        Fm = np.asarray(matrixF)
+        if Fm.shape[0] < 2 or Fm.shape[1] < 2:
+            raise ValueError("matrixF must have at least shape (2, 2)")
+        if Q0.shape[0] < 2 or Q0.shape[1] < 2:
+            raise ValueError("matrixQ0 must have at least shape (2, 2)")
+    else:
+        if Q0.shape[0] < 1 or Q0.shape[1] < 1:
+            raise ValueError("matrixQ0 must have at least shape (1, 1)")
+        if float(Q0[0, 0]) <= 0.0:
+            raise ValueError("matrixQ0[0, 0] must be positive")
+    lamMin, lamMax, kapMin, kapMax = map(_f32, (lamMin, lamMax, kapMin, kapMax))
+    _check_bounds(lamMin, lamMax, True)
+    _check_bounds(kapMin, kapMax, False)
+    bm = np.ascontiguousarray(intervalToBlockMap, dtype=np.int32)
+    if bm.shape[0] < n:
+        raise ValueError("intervalToBlockMap length must match intervalCount")
+    lam = _vec32(lambdaExp, "lambdaExp", n) if use_lambda else None
+    kap = _vec32(processPrecExp, "processPrecExp", n) if use_kappa else None
+    if vectorD is None:
+        vectorD = np.empty(n, dtype=np.float32)
+    elif vectorD.shape[0] < n:
+        raise ValueError("vectorD length must match intervalCount")
+    if _apn_live(useAPN, use_qscale, Q0, dim):
+        raise NotImplementedError(_APN_MSG)
+    if do_store:
+        _c32(stateForward, "stateForward", 2)
+        _c32(stateCovarForward, "stateCovarForward", 3)
+        _c32(pNoiseForward, "pNoiseForward", 3)
+    mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kapMin, kapMax, use_lambda,
+                use_kappa, use_qscale, returnNLL, storeNLLInD)
+    sum_d, sum_nll = C.c_double(0.0), C.c_double(0.0)
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_forward_pass(
+        ctx.handle, C.byref(mo), _ptr(data), _ptr(munc), m, n, _ptr(bm), int(blockCount), _ptr(lam), _ptr(kap),
+        _ptr(qs), _ptr(stateForward) if do_store else None, _ptr(stateCovarForward) if do_store else None,
+        _ptr(pNoiseForward) if do_store else None, _ptr(vectorD), C.byref(sum_d), C.byref(sum_nll)))
+    phi = float(np.float32(sum_d.value / float(n)))
+    if returnNLL:
+        return (phi, 0, vectorD, sum_nll.value)
+    return (phi, 0, vectorD)
+
+
+def cforwardPass(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                 stateInit, stateCovarInit, pad=1.0e-4, projectStateDuringFiltering=False,
+                 stateLowerBound=0.0, stateUpperBound=0.0, chunkSize=1000000, stateForward=None,
+                 stateCovarForward=None, pNoiseForward=None, vectorD=None, returnNLL=False,
+                 storeNLLInD=False, lambdaExp=None, processPrecExp=None,
+                 ECM_useObsPrecisionReweighting=True, ECM_useProcessPrecisionReweighting=True,
+                 ECM_useAPN=False, obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0,
+                 procPrecisionMultiplierMin=0.25, procPrecisionMultiplierMax=4.0, APN_minQ=1.0e-4,
+                 APN_maxQ=1000.0, APN_dStatThresh=5.0, APN_dStatScale=10.0, APN_dStatPC=2.0,
+                 processQScale=None):
+    """2-state forward filter; signature and returns of cconsenrich.pyx:6393-6632."""
+    return _forward(2, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                    stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
+                    returnNLL, storeNLLInD, lambdaExp, processPrecExp, ECM_useObsPrecisionReweighting,
+                    ECM_useProcessPrecisionReweighting, ECM_useAPN, obsPrecisionMultiplierMin,
+                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax, processQScale)
+
+
+def cforwardPassLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBlockMap, blockCount,
+                      stateInit, stateCovarInit, pad=1.0e-4, chunkSize=1000000, stateForward=None,
+                      stateCovarForward=None, pNoiseForward=None, vectorD=None, returnNLL=False,
+                      storeNLLInD=False, lambdaExp=None, processPrecExp=None,
+                      ECM_useObsPrecisionReweighting=True, ECM_useProcessPrecisionReweighting=True,
+                      ECM_useAPN=False, obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0,
+                      procPrecisionMultiplierMin=0.25, procPrecisionMultiplierMax=4.0, APN_minQ=1.0e-4,
+                      APN_maxQ=1000.0, APN_dStatThresh=5.0, APN_dStatScale=10.0, APN_dStatPC=2.0,
+                      processQScale=None):
+    """Level-only forward filter; signature and returns of cconsenrich.pyx:6853-7049."""
+    return _forward(1, matrixData, matrixPluginMuncInit, None, matrixQ0, intervalToBlockMap, blockCount,
+                    stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
+                    returnNLL, storeNLLInD, lambdaExp, processPrecExp, ECM_useObsPrecisionReweighting,
+                    ECM_useProcessPrecisionReweighting, ECM_useAPN, obsPrecisionMultiplierMin,
+                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax, processQScale)
+
+
+def _backward(dim, matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward, stateSmoothed,
+              stateCovarSmoothed, lagCovSmoothed, postFitResiduals):
+    data = _c32(matrixData, "matrixData", 2)
+    m, n = data.shape
+    xs = stateSmoothed if stateSmoothed is not None else np.empty((n, dim), dtype=np.float32)
+    Ps = stateCovarSmoothed if stateCovarSmoothed is not None else np.empty((n, dim, dim), dtype=np.float32)
+    lag = lagCovSmoothed if lagCovSmoothed is not None else np.empty((max(n - 1, 1), dim, dim), dtype=np.float32)
+    res = postFitResiduals if postFitResiduals is not None else np.empty((n, m), dtype=np.float32)
+    if n <= 0:
+        return (xs, Ps, lag, res)
+    xf = _c32(stateForward, "stateForward", 2)
+    Pf = _c32(stateCovarForward, "stateCovarForward", 3)
+    Qf = _c32(pNoiseForward, "pNoiseForward", 3)
+    mo = _model(dim, matrixF, np.eye(2), 0.0, 1.0, 0.0, 1.0, 1.0, 1.0, 1.0, False, False, False, False, False)
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_backward_pass(
+        ctx.handle, C.byref(mo), _ptr(data), m, n, _ptr(xf), _ptr(Pf), _ptr(Qf), _ptr(xs), _ptr(Ps), _ptr(lag),
+        int(lag.shape[0]), _ptr(res)))
+    return (xs, Ps, lag, res)
+
+
+def cbackwardPass(matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward, chunkSize=1000000,
+                  stateSmoothed=None, stateCovarSmoothed=None, lagCovSmoothed=None, postFitResiduals=None):
+    """2-state RTS smoother + lag-one covariance + residuals; cconsenrich.pyx:6635-6850."""
+    return _backward(2, matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward, stateSmoothed,
+                     stateCovarSmoothed, lagCovSmoothed, postFitResiduals)
+
+
+def cbackwardPassLevel(matrixData, stateForward, stateCovarForward, pNoiseForward, chunkSize=1000000,
+                       stateSmoothed=None, stateCovarSmoothed=None, lagCovSmoothed=None, postFitResiduals=None):
+    """Level-only RTS smoother; cconsenrich.pyx:7052-7150."""
+    return _backward(1, matrixData, None, stateForward, stateCovarForward, pNoiseForward, stateSmoothed,
+                     stateCovarSmoothed, lagCovSmoothed, postFitResiduals)
+
+
+def sweep(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, stateInit, stateCovarInit, pad=1.0e-4, stateModel=2,
+          lambdaExp=None, processPrecExp=None, processQScale=None, returnNLL=True, storeNLLInD=False,
+          obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0, procPrecisionMultiplierMin=0.25,
+          procPrecisionMultiplierMax=4.0, wantResiduals=True, out=None):
+    """One forward + backward sweep on a single upload (what core._runForwardBackward, core.py:4207,
+    obtains from cforwardPass followed by cbackwardPass).  Returns a dict of the reference's arrays.
+    ``out`` may hold preallocated (e.g. pinned) arrays under the same keys."""
+    dim = int(stateModel)
+    data = _c32(matrixData, "matrixData", 2)
+    munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
+    m, n = data.shape
+    if munc.shape != data.shape:
+        raise ValueError("matrixPluginMuncInit shape must match matrixData shape")
+    Q0 = np.asarray(matrixQ0)
+    lamMin, lamMax, kapMin, kapMax = map(_f32, (obsPrecisionMultiplierMin, obsPrecisionMultiplierMax,
+                                                 procPrecisionMultiplierMin, procPrecisionMultiplierMax))
+    _check_bounds(lamMin, lamMax, True)
+    _check_bounds(kapMin, kapMax, False)
+    qs = _coerce_qscale(processQScale, n) if processQScale is not None else None
+    lam = _vec32(lambdaExp, "lambdaExp", n)
+    kap = _vec32(processPrecExp, "processPrecExp", n)
+    mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kapMin, kapMax, lam is not None,
+                kap is not None, qs is not None, returnNLL, storeNLLInD)
+    out = {} if out is None else out
+
+    def buf(key, shape):
+        a = out.get(key)
+        if a is None:
+            a = out[key] = np.empty(shape, np.float32)
+        return a
+
+    xf, Pf, Qf = buf("stateForward", (n, dim)), buf("stateCovarForward", (n, dim, dim)), buf("pNoiseForward", (n, dim, dim))
+    D = buf("vectorD", (n,))
+    xs, Ps = buf("stateSmoothed", (n, dim)), buf("stateCovarSmoothed", (n, dim, dim))
+    lag = buf("lagCovSmoothed", (max(n - 1, 1), dim, dim))
+    res = buf("postFitResiduals", (n, m)) if wantResiduals else None
+    sum_d, sum_nll = C.c_double(0.0), C.c_double(0.0)
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_sweep(
+        ctx.handle, C.byref(mo), _ptr(data), _ptr(munc), m, n, _ptr(lam), _ptr(kap), _ptr(qs), _ptr(xf), _ptr(Pf),
+        _ptr(Qf), _ptr(D), C.byref(sum_d), C.byref(sum_nll), _ptr(xs), _ptr(Ps), _ptr(lag), int(lag.shape[0]),
+        _ptr(res)))
+    out["phiHat"] = float(np.float32(sum_d.value / float(max(n, 1))))
+    out["sumNLL"] = sum_nll.value
+    return out
+
+
+def _init_multiplier(init, n, lo, hi, what):
+    """Warm-start copy + clip, cconsenrich.pyx:7899-7923."""
+    if init is None:
+        return np.ones(n, dtype=np.float32)
+    arr = np.array(init, dtype=np.float32, copy=True, order="C").reshape(-1)
+    if arr.shape[0] != n:
+        raise ValueError(f"{what} length must match intervalCount")
+    if not np.all(np.isfinite(arr)):
+        raise ValueError(f"{what} must contain only finite values")
+    np.clip(arr, lo, hi, out=arr)
+    return arr
+
+
+def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount, stateInit,
+         stateCovarInit, iters, rtol, pad, nu, lamMin, lamMax, kapMin, kapMax, useObs, useProc, useAPN,
+         t_innerIters, returnIntermediates, returnDiagnostics, lambdaExpInit, processPrecExpInit,
+         trackOptimizationPath, processQScale):
+    """ECM driver with the packing rules of cconsenrich.pyx:8409-8442."""
+    data = _c32(matrixData, "matrixData", 2)
+    munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
+    m, n = data.shape
+    use_qscale = processQScale is not None
+    lam = kap = None
+    if useObs:
+        lam = _init_multiplier(lambdaExpInit, n, lamMin, lamMax, "lambdaExpInit")
+    if useProc and ((not useAPN) or use_qscale):
+        kap = _init_multiplier(processPrecExpInit, n, kapMin, kapMax, "processPrecExpInit")
+    qs = _coerce_qscale(processQScale, n) if use_qscale else None
+    xs = np.empty((n, dim), np.float32)
+    Ps = np.empty((n, dim, dim), np.float32)
+    lag = np.empty((max(n - 1, 1), dim, dim), np.float32)
+    res = np.empty((n, m), np.float32)
+    Q0 = np.asarray(matrixQ0)
+    patience = 2
+    path = [] if trackOptimizationPath else None
+
+    def pack(iters_done, nll, diag):
+        if returnIntermediates:
+            out = (iters_done, float(nll), xs, Ps, lag, res, lam, kap)
+            return out + (diag,) if returnDiagnostics else out
+        return (iters_done, float(nll), diag) if returnDiagnostics else (iters_done, float(nll))
+
+    if n <= 0 or m <= 0:
+        diag = {"iters_done": 0, "max_iters": int(iters), "converged": False, "skipped": True,
+                "skip_reason": "too_few_intervals" if n > 0 else "empty_input", "fallback": "filter_smoother_only",
+                "stable_iters": 0, "patience_target": patience, "initial_nll": 0.0, "final_nll": 0.0,
+                "final_abs_rel_change": None, "final_rel_improvement": None, "nll_increase_count": 0}
+        if trackOptimizationPath:
+            diag["optimization_path"] = path
+        return pack(0, 0.0, diag)
+
+    # validation order of pyx:8131-8140 / 7396-7404
+    if blockCount <= 0:
+        raise ValueError("blockCount must be positive")
+    if munc.shape[0] != m or munc.shape[1] != n:
+        raise ValueError("matrixPluginMuncInit shape must match matrixData shape")
+    if dim == 1 and float(Q0[0, 0]) <= 0.0:
+        raise ValueError("matrixQ0[0, 0] must be positive")
+    lamMin_d, lamMax_d, kapMin_d, kapMax_d = map(_f32, (lamMin, lamMax, kapMin, kapMax))
+    _check_bounds(lamMin_d, lamMax_d, True)
+    _check_bounds(kapMin_d, kapMax_d, False)
+    bm = np.ascontiguousarray(intervalToBlockMap, dtype=np.int32)
+    if bm.shape[0] < n:
+        raise ValueError("intervalToBlockMap length must match intervalCount")
+    if dim == 2:
+        det = float(Q0[0, 0]) * float(Q0[1, 1]) - float(Q0[0, 1]) * float(Q0[1, 0])
+        if det == 0.0:
+            raise ValueError("matrixQ0 is singular")
+    if _apn_live(useAPN, use_qscale, Q0, dim):
+        raise NotImplementedError(_APN_MSG)
+
+    mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin_d, lamMax_d, kapMin_d, kapMax_d,
+                lam is not None, kap is not None, use_qscale, True, False)
+    op = _lib.EcmOpts()
+    op.max_iters, op.inner_iters = int(iters), int(t_innerIters)
+    op.update_lambda, op.update_kappa = int(lam is not None), int(kap is not None)
+    op.want_outputs = int(bool(returnIntermediates))
+    op.rtol, op.nu = _f32(rtol), _f32(nu)
+    result = _lib.EcmResult()
+    nll_path = np.zeros(max(int(iters), 1), np.float64)
+    ctx = _ctx()
+    want = bool(returnIntermediates)
+    _lib.check(ctx._lib.cb200_host_ecm(
+        ctx.handle, C.byref(mo), C.byref(op), _ptr(data), _ptr(munc), m, n, _ptr(bm), int(blockCount), _ptr(qs),
+        _ptr(lam), _ptr(kap), _ptr(xs) if want else None, _ptr(Ps) if want else None, _ptr(lag) if want else None,
+        _ptr(res) if want else None, C.byref(result), _ptr(nll_path)))
+
+    if result.skipped:  # n <= 5 (pyx:7998-8129)
+        diag = {"iters_done": 0, "max_iters": int(iters), "converged": False, "skipped": True,
+                "skip_reason": "too_few_intervals", "fallback": "filter_smoother_only", "stable_iters": 0,
+                "patience_target": patience, "initial_nll": float(result.final_nll),
+                "final_nll": float(result.final_nll), "final_abs_rel_change": None, "final_rel_improvement": None,
+                "nll_increase_count": 0}
+        if trackOptimizationPath:
+            diag["optimization_path"] = path
+        return pack(0, result.final_nll, diag)
+
+    if trackOptimizationPath:  # rebuilt from the per-iteration NLL values (pyx:8364-8392)
+        prev, stable, rtol_d = None, 0, _f32(rtol)
+        for i in range(result.iters_done):
+            cur = float(nll_path[i])
+            if prev is None:
+                delta, scale = 0.0, max(abs(cur), 1.0)
+            else:
+                delta, scale = abs(cur - prev), max(abs(prev), abs(cur), 1.0)
+            tol = rtol_d * scale
+            stable = stable + 1 if (prev is not None and delta <= tol) else 0
+            path.append({
+                "iter": i + 1, "objective_name": "nll", "objective_value": cur,
+                "change": float(delta) if prev is not None else None,
+                "relative_improvement": float((prev - cur) / scale) if prev is not None else None,
+                "abs_relative_change": float(delta / scale) if prev is not None else None,
+                "threshold": float(tol) if prev is not None else None, "stable_iters": int(stable),
+                "patience_target": patience, "reset_iteration": bool(prev is None),
+                "converged": bool(stable >= patience),
+            })
+            prev = cur
+    has_init = bool(result.has_initial)
+    diag = {
+        "iters_done": int(result.iters_done), "max_iters": int(iters), "converged": bool(result.converged),
+        "skipped": False, "skip_reason": None, "fallback": None, "stable_iters": int(result.stable_iters),
+        "patience_target": patience, "initial_nll": float(result.initial_nll) if has_init else None,
+        "final_nll": float(result.final_nll),
+        "final_abs_rel_change": float(result.final_abs_rel_change) if has_init else None,
+        "final_rel_improvement": float(result.final_rel_improvement) if has_init else None,
+        "nll_increase_count": int(result.nll_increase_count),
+    }
+    if trackOptimizationPath:
+        diag["optimization_path"] = path
+    return pack(int(result.iters_done), result.final_nll, diag)
+
+
+def cfixedBackgroundECM(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                        stateInit, stateCovarInit, ECM_fixedBackgroundIters=50, ECM_fixedBackgroundRtol=1.0e-4,
+                        pad=1.0e-4, ECM_robustTNu=8.0, obsPrecisionMultiplierMin=0.25,
+                        obsPrecisionMultiplierMax=4.0, procPrecisionMultiplierMin=0.25,
+                        procPrecisionMultiplierMax=4.0, ECM_useObsPrecisionReweighting=True,
+                        ECM_useProcessPrecisionReweighting=True, ECM_useAPN=False, APN_minQ=1.0e-4,
+                        APN_maxQ=1000.0, APN_dStatThresh=5.0, APN_dStatScale=10.0, APN_dStatPC=2.0,
+                        t_innerIters=5, returnIntermediates=False, returnDiagnostics=False,
+                        lambdaExpInit=None, processPrecExpInit=None, trackOptimizationPath=False,
+                        logIterations=True, processQScale=None):
+    """2-state fixed-background ECM; signature and returns of cconsenrich.pyx:7660-8442."""
+    return _ecm(2, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount,
+                stateInit, stateCovarInit, ECM_fixedBackgroundIters, ECM_fixedBackgroundRtol, pad, ECM_robustTNu,
+                obsPrecisionMultiplierMin, obsPrecisionMultiplierMax, procPrecisionMultiplierMin,
+                procPrecisionMultiplierMax, ECM_useObsPrecisionReweighting, ECM_useProcessPrecisionReweighting,
+                ECM_useAPN, t_innerIters, returnIntermediates, returnDiagnostics, lambdaExpInit,
+                processPrecExpInit, trackOptimizationPath, processQScale)
+
+
+def cfixedBackgroundECMLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBlockMap, blockCount,
+                             stateInit, stateCovarInit, ECM_fixedBackgroundIters=50,
+                             ECM_fixedBackgroundRtol=1.0e-4, pad=1.0e-4, ECM_robustTNu=8.0,
+                             obsPrecisionMultiplierMin=0.25, obsPrecisionMultiplierMax=4.0,
+                             procPrecisionMultiplierMin=0.25, procPrecisionMultiplierMax=4.0,
+                             ECM_useObsPrecisionReweighting=True, ECM_useProcessPrecisionReweighting=True,
+                             ECM_useAPN=False, APN_minQ=1.0e-4, APN_maxQ=1000.0, APN_dStatThresh=5.0,
+                             APN_dStatScale=10.0, APN_dStatPC=2.0, t_innerIters=5, returnIntermediates=False,
+                             returnDiagnostics=False, lambdaExpInit=None, processPrecExpInit=None,
+                             trackOptimizationPath=False, logIterations=True, processQScale=None):
+    """Level-only fixed-background ECM; signature and returns of cconsenrich.pyx:7153-7657."""
+    return _ecm(1, matrixData, matrixPluginMuncInit, None, matrixQ0, intervalToBlockMap, blockCount,
+                stateInit, stateCovarInit, ECM_fixedBackgroundIters, ECM_fixedBackgroundRtol, pad, ECM_robustTNu,
+                obsPrecisionMultiplierMin, obsPrecisionMultiplierMax, procPrecisionMultiplierMin,
+                procPrecisionMultiplierMax, ECM_useObsPrecisionReweighting, ECM_useProcessPrecisionReweighting,
+                ECM_useAPN, t_innerIters, returnIntermediates, returnDiagnostics, lambdaExpInit,
+                processPrecExpInit, trackOptimizationPath, processQScale)
+
+
+_saved: dict = {}
+
+
+def install(module=None):
+    """Replace the six hot-path attributes of ``consenrich.cconsenrich`` (or ``module``) with the
+    B200 implementations.  ``core.py`` looks them up by attribute at call time (core.py:4274,
+    4309, 3286), so ``runConsenrich`` picks them up without modification."""
+    if module is None:
+        import importlib
+        module = importlib.import_module("consenrich.cconsenrich")
+    _lib.load()  # fail now, loudly, if the native library is missing
+    saved = _saved.setdefault(id(module), {})
+    for name in _HOT_PATH:
+        if name not in saved:
+            saved[name] = getattr(module, name, None)
+        setattr(module, name, globals()[name])
+    return module
+
+
+def uninstall(module=None):
+    if module is None:
+        import importlib
+        module = importlib.import_module("consenrich.cconsenrich")
+    for name, fn in _saved.pop(id(module), {}).items():
+        if fn is not None:
+            setattr(module, name, fn)
+    return module

@@ -1,0 +1,217 @@
+/*
+ * consenrich_b200.h -- C ABI of libconsenrich_b200.so
+ *
+ * B200 (sm_100a) implementation of Consenrich's state-space hot path: the multi-sample
+ * Kalman forward filter, the RTS smoother and the fixed-background ECM (Student-t precision
+ * re-weighting) loop.  These entry points are what a binding for the six native functions
+ * of the reference's `consenrich.cconsenrich` module would call:
+ *
+ *   reference (src/consenrich/cconsenrich.pyx)          this library
+ *   -------------------------------------------------   ---------------------------------
+ *   cforwardPass               :6393-6632  (loop 291)   cb200_host_forward_pass (state_dim 2)
+ *   cforwardPassLevel          :6853-7049  (loop 538)   cb200_host_forward_pass (state_dim 1)
+ *   cbackwardPass              :6635-6850               cb200_host_backward_pass (state_dim 2)
+ *   cbackwardPassLevel         :7052-7150               cb200_host_backward_pass (state_dim 1)
+ *   cfixedBackgroundECM        :7660-8442               cb200_host_ecm (state_dim 2)
+ *   cfixedBackgroundECMLevel   :7153-7657               cb200_host_ecm (state_dim 1)
+ *   _accumulateObservationValue :259-283                cb200_fold_tracks (device fold kernel)
+ *
+ * Conventions
+ *   - plain C: pointers, sizes, POD structs; no torch / numpy types.
+ *   - "tracks" = the m samples (rows), "intervals" = the n genomic bins (columns); matrices are
+ *     row-major float32 [m x n] with a row stride `ld` (elements) >= n.
+ *   - every function returns CB200_OK or an error code; cb200_last_error() gives the message
+ *     (for CB200_ERR_INVALID the text is the reference's ValueError text, so a binding can
+ *     re-raise it verbatim).
+ *   - cb200_host_* take HOST pointers and run H2D copies, kernels and D2H copies on the
+ *     context's stream, returning after the results are in the caller's buffers.
+ *   - all other entry points take DEVICE pointers, enqueue work on the context's stream and
+ *     return without synchronising (inputs already resident in HBM).
+ *   - there is no CPU implementation behind any entry point: without a CUDA device
+ *     cb200_ctx_create fails with CB200_ERR_CUDA.
+ */
+#ifndef CONSENRICH_B200_H
+#define CONSENRICH_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_OK 0
+#define CB200_ERR_INVALID 1     /* bad argument: maps to the reference's ValueError */
+#define CB200_ERR_CUDA 2        /* CUDA runtime / driver failure */
+#define CB200_ERR_UNSUPPORTED 3 /* valid in the reference, not expressible as a scan (APN) */
+
+#define CB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CB200_API __attribute__((visibility("default")))
+#else
+#define CB200_API
+#endif
+
+typedef struct cb200_ctx cb200_ctx;
+
+/* State-space model and per-call switches.  Scalars that the reference receives as C `float`
+ * (stateInit, stateCovarInit, pad, the multiplier bounds; cconsenrich.pyx:6400-6426) must be
+ * rounded to float by the caller before being widened into these doubles. */
+typedef struct cb200_model {
+    int32_t state_dim;      /* 2 = level + trend (cforwardPass), 1 = level (cforwardPassLevel) */
+    int32_t use_lambda;     /* per-interval observation precision multipliers are live */
+    int32_t use_kappa;      /* per-interval process precision multipliers are live */
+    int32_t use_qscale;     /* per-interval processQScale is live */
+    int32_t return_nll;     /* accumulate the Gaussian negative log-likelihood */
+    int32_t store_nll_in_d; /* vectorD holds the per-interval NLL instead of NIS */
+    int32_t reserved0, reserved1;
+    double F[4];            /* row-major transition matrix (ignored when state_dim == 1) */
+    double Q0[4];           /* row-major base process noise; state_dim 1 uses Q0[0] */
+    double state_init, cov_init, pad;
+    double lam_min, lam_max; /* observation precision multiplier clamp */
+    double kap_min, kap_max; /* process precision multiplier clamp */
+} cb200_model;
+
+/* ECM controls (cconsenrich.pyx:7660-7693). */
+typedef struct cb200_ecm_opts {
+    int32_t max_iters;       /* ECM_fixedBackgroundIters */
+    int32_t inner_iters;     /* t_innerIters */
+    int32_t update_lambda;   /* ECM_useObsPrecisionReweighting */
+    int32_t update_kappa;    /* ECM_useProcessPrecisionReweighting (and not disabled by APN) */
+    int32_t want_outputs;    /* returnIntermediates: smoothed tracks + residuals are produced */
+    int32_t reserved0;
+    double rtol;             /* ECM_fixedBackgroundRtol (rounded to float by the caller) */
+    double nu;               /* ECM_robustTNu (rounded to float by the caller) */
+} cb200_ecm_opts;
+
+/* ECM outcome; mirrors the diagnostics dict of cconsenrich.pyx:8409-8425. */
+typedef struct cb200_ecm_result {
+    int32_t iters_done;
+    int32_t converged;
+    int32_t skipped;          /* n <= 5: filter + smoother only (pyx:7998-8129) */
+    int32_t stable_iters;
+    int32_t nll_increase_count;
+    int32_t has_initial;
+    double initial_nll, final_nll, final_abs_rel_change, final_rel_improvement;
+} cb200_ecm_result;
+
+/* ---- context ------------------------------------------------------------------------ */
+CB200_API int cb200_abi_version(void);
+/* stream: a cudaStream_t to enqueue on, or NULL for a stream owned by the context. */
+CB200_API int cb200_ctx_create(int device, void *stream, cb200_ctx **out);
+CB200_API void cb200_ctx_destroy(cb200_ctx *ctx);
+CB200_API int cb200_ctx_set_stream(cb200_ctx *ctx, void *stream);
+CB200_API int cb200_ctx_sync(cb200_ctx *ctx);
+CB200_API const char *cb200_last_error(void); /* thread-local; valid until the next failing call */
+/* number of kernel launches this context has enqueued (bench.py's gpu_launches). */
+CB200_API int64_t cb200_ctx_launch_count(const cb200_ctx *ctx);
+/* cumulative device time (ms) of the named kernel family since the last reset, measured
+ * with CUDA events on the context's stream when timing is enabled: 0 fold, 1 forward scan,
+ * 2 backward scan, 3 residuals, 4 precision updates. */
+CB200_API int cb200_ctx_enable_timing(cb200_ctx *ctx, int on);
+CB200_API int cb200_ctx_kernel_ms(cb200_ctx *ctx, int family, double *ms, int64_t *launches);
+CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
+
+/* ---- memory helpers (so that hosts without torch can stage tracks) -------------------- */
+CB200_API int cb200_device_alloc(cb200_ctx *ctx, size_t bytes, void **dptr);
+CB200_API int cb200_device_free(cb200_ctx *ctx, void *dptr);
+CB200_API int cb200_pinned_alloc(size_t bytes, void **hptr);
+CB200_API int cb200_pinned_free(void *hptr);
+/* rows x row_bytes, pitched on either side; asynchronous on the context's stream. */
+CB200_API int cb200_copy_h2d(cb200_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                   size_t row_bytes, size_t rows);
+CB200_API int cb200_copy_d2h(cb200_ctx *ctx, void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                   size_t row_bytes, size_t rows);
+
+/* ---- device-resident path ------------------------------------------------------------- */
+/* Fold the m observations of every interval into information form, one coalesced pass over
+ * data and munc (replaces the per-(interval, sample) calls of _accumulateObservationValue,
+ * cconsenrich.pyx:259-283).  stats = 4 arrays of `stat_stride` doubles laid end to end:
+ * S0 = sum 1/r, S1 = sum z/r, S2 = sum z^2/r, SL = sum log r, r = max(munc + pad, 1e-12). */
+CB200_API int cb200_fold_tracks(cb200_ctx *ctx, const float *data, const float *munc, int64_t m, int64_t n,
+                      int64_t ld, double pad, double *stats, int64_t stat_stride);
+
+/* Forward filter as a single-pass decoupled look-back scan (replaces the loops at
+ * cconsenrich.pyx:291-529 and 538-707).  lam/kap/qscale: float32 [n] or NULL according to the
+ * model flags.  xf [n][d], Pf [n][d][d], Qf [n][d][d] (Q_k stored at k-1) may all be NULL (no
+ * store).  D float32 [n] may be NULL.  sums: device double[2] = {sum of float-rounded D, sum
+ * NLL}, or NULL.  init_state: device double[5] {x0, x1, P00, P01, P11} (d = 1: {x, P}) that
+ * overrides the model's prior -- the carry of the preceding contiguous shard -- or NULL. */
+CB200_API int cb200_forward_scan(cb200_ctx *ctx, const cb200_model *model, const double *stats,
+                       int64_t stat_stride, int64_t m, int64_t n, const float *lam, const float *kap,
+                       const float *qscale, const double *init_state, float *xf, float *Pf, float *Qf,
+                       float *D, double *sums);
+
+/* Aggregate filtering element of a whole shard (14 doubles for d = 2: A, b, C, eta, J; 5 for
+ * d = 1), the only thing ranks exchange when a chromosome is split into contiguous ranges. */
+CB200_API int cb200_forward_shard_aggregate(cb200_ctx *ctx, const cb200_model *model, const double *stats,
+                                  int64_t stat_stride, int64_t n, const float *lam, const float *kap,
+                                  const float *qscale, double *agg);
+/* Combine the prior with the gathered aggregates of shards 0..rank-1 (aggs: [n_shards][16]
+ * doubles, 16-double pitch) into the init_state of shard `rank`. */
+CB200_API int cb200_forward_shard_prefix(cb200_ctx *ctx, const cb200_model *model, const double *aggs,
+                               int32_t rank, double *init_state);
+
+/* RTS smoother as a reverse decoupled look-back scan (replaces cconsenrich.pyx:6740-6848 and
+ * 7116-7148, residuals excluded).  lag has lag_rows rows.  tail_state: device double[5]
+ * smoothed {x, P} of the first interval of the FOLLOWING shard, or NULL when this shard ends
+ * the chromosome. */
+CB200_API int cb200_backward_scan(cb200_ctx *ctx, const cb200_model *model, int64_t n, const float *xf,
+                        const float *Pf, const float *Qf, const double *tail_state, float *xs,
+                        float *Ps, float *lag, int64_t lag_rows);
+CB200_API int cb200_backward_shard_aggregate(cb200_ctx *ctx, const cb200_model *model, int64_t n, const float *xf,
+                                   const float *Pf, const float *Qf, int32_t is_last_shard,
+                                   double *agg);
+CB200_API int cb200_backward_shard_prefix(cb200_ctx *ctx, const cb200_model *model, const double *aggs,
+                                int32_t rank, int32_t n_shards, double *tail_state);
+
+/* postFitResiduals[k][j] = data[j][k] - xs[k][0], float32 [n][m] (transposed with respect to
+ * data; cconsenrich.pyx:6846-6848). */
+CB200_API int cb200_residuals(cb200_ctx *ctx, const float *data, int64_t m, int64_t n, int64_t ld,
+                    const float *xs, int32_t state_dim, float *resid);
+
+/* Student-t precision multipliers (cconsenrich.pyx:8210-8298, 7474-7521). */
+CB200_API int cb200_update_lambda(cb200_ctx *ctx, const cb200_model *model, const double *stats,
+                        int64_t stat_stride, int64_t m, int64_t n, const float *xs, const float *Ps,
+                        double nu, float *lam);
+CB200_API int cb200_update_kappa(cb200_ctx *ctx, const cb200_model *model, int64_t n, const float *xs,
+                       const float *Ps, const float *lag, const float *qscale, double nu, float *kap);
+
+/* Whole ECM loop on device-resident tracks.  lam / kap are in-out float32 [n] (warm start,
+ * already clipped) or NULL when the corresponding update is off.  xs, Ps, lag are required
+ * work/output tracks; resid may be NULL.  Blocks until the loop has finished (the stopping
+ * rule reads one double per iteration). */
+CB200_API int cb200_ecm_device(cb200_ctx *ctx, const cb200_model *model, const cb200_ecm_opts *opts,
+                     const float *data, const float *munc, int64_t m, int64_t n, int64_t ld,
+                     const float *qscale, float *lam, float *kap, float *xs, float *Ps, float *lag,
+                     float *resid, cb200_ecm_result *result, double *nll_path /* [max_iters] or NULL */);
+
+/* ---- reference-facing path (host buffers) ---------------------------------------------- */
+/* cforwardPass / cforwardPassLevel.  block_map is range-checked only (pyx:389-392). */
+CB200_API int cb200_host_forward_pass(cb200_ctx *ctx, const cb200_model *model, const float *data,
+                            const float *munc, int64_t m, int64_t n, const int32_t *block_map,
+                            int64_t block_count, const float *lam, const float *kap,
+                            const float *qscale, float *xf, float *Pf, float *Qf, float *D,
+                            double *sum_d, double *sum_nll);
+/* cbackwardPass / cbackwardPassLevel. */
+CB200_API int cb200_host_backward_pass(cb200_ctx *ctx, const cb200_model *model, const float *data, int64_t m,
+                             int64_t n, const float *xf, const float *Pf, const float *Qf, float *xs,
+                             float *Ps, float *lag, int64_t lag_rows, float *resid);
+/* Fused forward + backward sweep on one upload of the tracks (what core._runForwardBackward,
+ * core.py:4207, does with two native calls).  Any output pointer may be NULL. */
+CB200_API int cb200_host_sweep(cb200_ctx *ctx, const cb200_model *model, const float *data, const float *munc,
+                     int64_t m, int64_t n, const float *lam, const float *kap, const float *qscale,
+                     float *xf, float *Pf, float *Qf, float *D, double *sum_d, double *sum_nll,
+                     float *xs, float *Ps, float *lag, int64_t lag_rows, float *resid);
+/* cfixedBackgroundECM / cfixedBackgroundECMLevel. */
+CB200_API int cb200_host_ecm(cb200_ctx *ctx, const cb200_model *model, const cb200_ecm_opts *opts,
+                   const float *data, const float *munc, int64_t m, int64_t n,
+                   const int32_t *block_map, int64_t block_count, const float *qscale, float *lam,
+                   float *kap, float *xs, float *Ps, float *lag, float *resid,
+                   cb200_ecm_result *result, double *nll_path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONSENRICH_B200_H */

@@ -1,0 +1,321 @@
+"""GPU parity tests: the sm_100a path, called through the C ABI (ctypes -> libconsenrich_b200.so),
+against the CPU oracle on the same seeded inputs, against the committed golden fixtures produced
+by the reference build, and through size-independent properties at the benchmark size.
+
+Floating-point tolerance: tests/parity_util.py (rtol 1e-4 + 1e-5 of the track's scale); integer
+outputs, Q tracks and residual identities are compared exactly.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_DIR, synth_tracks
+from parity_util import assert_tracks_close
+
+pytestmark = pytest.mark.gpu
+
+F = np.array([[1.0, 1.0], [0.0, 1.0]], np.float32)
+Q0 = np.array([[2e-3, 0.0], [0.0, 1e-4]], np.float32)
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import consenrich_b200 as cb
+    cb._lib.default_context(0)  # fails loudly without the library or a device
+    return cb
+
+
+def _weights(rng, n):
+    lam = (0.1 + 5 * rng.random(n)).astype(np.float32)
+    kap = np.exp(rng.normal(0, 2, n)).astype(np.float32)
+    qs = (0.5 + rng.random(n)).astype(np.float32)
+    qs[0] = 1.0
+    return lam, kap, qs
+
+
+def _sweep(mod, dim, data, munc, lam=None, kap=None, qs=None, nll_in_d=False, bounds=(0.25, 4.0, 5e-3, 5e3),
+           state_init=0.25):
+    m, n = data.shape
+    kw = dict(matrixData=data, matrixPluginMuncInit=munc, matrixQ0=Q0, intervalToBlockMap=np.zeros(n, np.int32),
+              blockCount=1, stateInit=state_init, stateCovarInit=1000.0, pad=1e-4, returnNLL=True,
+              storeNLLInD=nll_in_d, lambdaExp=lam, processPrecExp=kap, processQScale=qs,
+              obsPrecisionMultiplierMin=bounds[0], obsPrecisionMultiplierMax=bounds[1],
+              procPrecisionMultiplierMin=bounds[2], procPrecisionMultiplierMax=bounds[3])
+    o = dict(xf=np.empty((n, dim), np.float32), Pf=np.empty((n, dim, dim), np.float32),
+             Qf=np.zeros((n, dim, dim), np.float32), D=np.empty(n, np.float32))
+    st = dict(stateForward=o["xf"], stateCovarForward=o["Pf"], pNoiseForward=o["Qf"], vectorD=o["D"])
+    if dim == 2:
+        r = mod.cforwardPass(matrixF=F, **kw, **st)
+        b = mod.cbackwardPass(matrixData=data, matrixF=F, stateForward=o["xf"], stateCovarForward=o["Pf"],
+                              pNoiseForward=o["Qf"])
+    else:
+        r = mod.cforwardPassLevel(**kw, **st)
+        b = mod.cbackwardPassLevel(matrixData=data, stateForward=o["xf"], stateCovarForward=o["Pf"],
+                                   pNoiseForward=o["Qf"])
+    assert r[2] is o["D"]  # the supplied vectorD object is returned (tests/test_core.py:3427)
+    o.update(phi=r[0], nll=r[3], xs=b[0], Ps=b[1], lag=b[2], res=b[3])
+    return o
+
+
+def _compare_sweeps(got, want, n, dim, label):
+    assert_tracks_close(got["xf"], want["xf"], f"{label} stateForward")
+    assert_tracks_close(got["Pf"], want["Pf"], f"{label} stateCovarForward", scale="component")
+    np.testing.assert_array_equal(got["Qf"][: n - 1], want["Qf"][: n - 1], err_msg=f"{label} pNoiseForward")
+    assert_tracks_close(got["D"], want["D"], f"{label} vectorD")
+    assert abs(got["nll"] - want["nll"]) <= 1e-7 * max(abs(want["nll"]), 1.0), label
+    assert abs(got["phi"] - want["phi"]) <= 1e-4 * max(abs(want["phi"]), 1e-3), label
+    assert_tracks_close(got["xs"], want["xs"], f"{label} stateSmoothed")
+    assert_tracks_close(got["Ps"], want["Ps"], f"{label} stateCovarSmoothed", scale="component")
+    if n > 1:
+        assert_tracks_close(got["lag"], want["lag"], f"{label} lagCovSmoothed", scale="component")
+    assert_tracks_close(got["res"], want["res"], f"{label} postFitResiduals")
+    if dim == 1:  # the level filter carries float64 in the reference as well
+        assert_tracks_close(got["xf"], want["xf"], f"{label} level stateForward", rtol=1e-6, atol_rel=1e-7)
+
+
+SWEEP_CASES = [
+    # m, n, masked_frac, weights
+    (2, 1, 0.0, False), (2, 2, 0.0, True), (3, 3, 0.0, False), (4, 7, 0.0, True), (3, 257, 0.0, False),
+    (10, 1023, 0.05, True), (10, 1024, 0.0, False), (7, 1025, 0.0, True), (5, 2048, 0.3, True),
+    (33, 4097, 0.0, True), (1, 5000, 0.0, False), (130, 3000, 0.1, True),
+    (10, 300001, 0.02, True), (3, 1200003, 0.0, False),
+]
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+@pytest.mark.parametrize("case", SWEEP_CASES)
+def test_sweep_matches_oracle(cb, oracle, dim, case):
+    m, n, masked, weights = case
+    data, munc = synth_tracks(5000 + n + m, m, n, masked_frac=masked)
+    lam = kap = qs = None
+    if weights:
+        lam, kap, qs = _weights(np.random.default_rng(n), n)
+    want = _sweep(oracle, dim, data, munc, lam, kap, qs)
+    got = _sweep(cb, dim, data, munc, lam, kap, qs)
+    _compare_sweeps(got, want, n, dim, f"{m}x{n} d{dim}")
+    # exact identities of the residual track
+    lvl = got["xs"][:, 0].astype(np.float64)
+    np.testing.assert_array_equal(got["res"], (data.T.astype(np.float64) - lvl[:, None]).astype(np.float32))
+    np.testing.assert_array_equal(got["xs"][-1], got["xf"][-1])
+    np.testing.assert_array_equal(got["Ps"][-1], got["Pf"][-1])
+
+
+def test_sweep_nll_in_d_and_cli_bounds(cb, oracle):
+    m, n = 6, 5000
+    data, munc = synth_tracks(77, m, n)
+    lam, kap, qs = _weights(np.random.default_rng(3), n)
+    for dim in (2, 1):
+        want = _sweep(oracle, dim, data, munc, lam, kap, qs, nll_in_d=True, bounds=(0.5, 2.0, 5e-3, 5e3))
+        got = _sweep(cb, dim, data, munc, lam, kap, qs, nll_in_d=True, bounds=(0.5, 2.0, 5e-3, 5e3))
+        _compare_sweeps(got, want, n, dim, f"nll_in_d d{dim}")
+
+
+def _golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name), allow_pickle=False)
+    cases = {}
+    for key in z.files:
+        case, rest = key.split("/", 1)
+        cases.setdefault(case, {})[rest] = z[key]
+    return cases
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+def test_sweep_matches_reference_golden_vectors(cb, dim):
+    """Fixtures generated by the unmodified reference build (tests/golden/make_golden.py)."""
+    for name, case in _golden("sweep_golden.npz").items():
+        data, munc, Q, bm = case["data"], case["munc"], case["Q0"], case["blockMap"]
+        n = data.shape[1]
+        extra = {k[6:]: (v if v.ndim else v.item()) for k, v in case.items() if k.startswith("extra/")}
+        kw = dict(matrixData=data, matrixPluginMuncInit=munc, matrixQ0=Q, intervalToBlockMap=bm,
+                  blockCount=int(bm.max()) + 1, stateInit=float(case["stateInit"]), stateCovarInit=1000.0,
+                  pad=1.0e-4, returnNLL=True, **extra)
+        st = dict(stateForward=np.empty((n, dim), np.float32), stateCovarForward=np.empty((n, dim, dim), np.float32),
+                  pNoiseForward=np.zeros((n, dim, dim), np.float32), vectorD=np.empty(n, np.float32))
+        if extra.get("ECM_useAPN"):
+            with pytest.raises(NotImplementedError):
+                (cb.cforwardPass(matrixF=F, **kw, **st) if dim == 2 else cb.cforwardPassLevel(**kw, **st))
+            continue
+        if dim == 2:
+            r = cb.cforwardPass(matrixF=F, **kw, **st)
+            b = cb.cbackwardPass(matrixData=data, matrixF=F, stateForward=st["stateForward"],
+                                 stateCovarForward=st["stateCovarForward"], pNoiseForward=st["pNoiseForward"])
+        else:
+            r = cb.cforwardPassLevel(**kw, **st)
+            b = cb.cbackwardPassLevel(matrixData=data, stateForward=st["stateForward"],
+                                      stateCovarForward=st["stateCovarForward"], pNoiseForward=st["pNoiseForward"])
+        pre = f"d{dim}/"
+        assert_tracks_close(st["stateForward"], case[pre + "stateForward"], name)
+        assert_tracks_close(st["stateCovarForward"], case[pre + "stateCovarForward"], name, scale="component")
+        np.testing.assert_array_equal(st["pNoiseForward"][: n - 1], case[pre + "pNoiseForward"][: n - 1])
+        assert_tracks_close(st["vectorD"], case[pre + "vectorD"], name)
+        assert abs(r[3] - float(case[pre + "sumNLL"])) <= 1e-7 * max(abs(float(case[pre + "sumNLL"])), 1.0)
+        assert_tracks_close(b[0], case[pre + "stateSmoothed"], name)
+        assert_tracks_close(b[1], case[pre + "stateCovarSmoothed"], name, scale="component")
+        if n > 1:
+            assert_tracks_close(b[2], case[pre + "lagCovSmoothed"], name, scale="component")
+        assert_tracks_close(b[3], case[pre + "postFitResiduals"], name)
+
+
+def _ecm(mod, dim, data, munc, **opts):
+    n = data.shape[1]
+    kw = dict(matrixData=data, matrixPluginMuncInit=munc, matrixQ0=Q0, intervalToBlockMap=np.zeros(n, np.int32),
+              blockCount=1, stateInit=0.0, stateCovarInit=1000.0, returnIntermediates=True, returnDiagnostics=True,
+              logIterations=False, **opts)
+    return mod.cfixedBackgroundECM(matrixF=F, **kw) if dim == 2 else mod.cfixedBackgroundECMLevel(**kw)
+
+
+def _compare_ecm(a, b, label, exact_iters=True):
+    if exact_iters:
+        assert a[0] == b[0], label
+    assert abs(a[1] - b[1]) <= 1e-6 * max(abs(b[1]), 1.0), f"{label}: nll {a[1]} vs {b[1]}"
+    assert_tracks_close(a[2], b[2], f"{label} stateSmoothed", rtol=2e-4, atol_rel=1e-4)
+    assert_tracks_close(a[3], b[3], f"{label} stateCovarSmoothed", scale="component", rtol=2e-3, atol_rel=1e-4)
+    assert_tracks_close(a[5], b[5], f"{label} residuals", rtol=2e-4, atol_rel=1e-4)
+    for x, y, nm in ((a[6], b[6], "lambda"), (a[7], b[7], "kappa")):
+        assert (x is None) == (y is None), f"{label} {nm}"
+        if x is not None:
+            assert_tracks_close(x, y, f"{label} {nm}", rtol=2e-3, atol_rel=1e-4)
+    da, db = a[8], b[8]
+    assert set(da) == set(db)
+    for key in ("max_iters", "skipped", "skip_reason", "fallback", "patience_target"):
+        assert da[key] == db[key], (label, key)
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+@pytest.mark.parametrize("opts", [
+    dict(ECM_fixedBackgroundIters=3, ECM_fixedBackgroundRtol=0.0, t_innerIters=2),
+    dict(ECM_fixedBackgroundIters=2, ECM_fixedBackgroundRtol=0.0, t_innerIters=3,
+         ECM_useObsPrecisionReweighting=False, procPrecisionMultiplierMin=5e-3, procPrecisionMultiplierMax=5e3),
+    dict(ECM_fixedBackgroundIters=2, ECM_fixedBackgroundRtol=0.0, ECM_useProcessPrecisionReweighting=False),
+    dict(ECM_fixedBackgroundIters=4, ECM_fixedBackgroundRtol=0.0, t_innerIters=1, ECM_robustTNu=4.0,
+         trackOptimizationPath=True),
+])
+def test_ecm_fixed_budget_matches_oracle(cb, oracle, dim, opts):
+    """Deterministic iteration budget (rtol = 0): the multipliers go through an identical number of
+    updates on both sides, so the tracks are comparable without the stopping rule's discreteness."""
+    data, munc = synth_tracks(909, 8, 6000, masked_frac=0.02)
+    a, b = _ecm(cb, dim, data, munc, **opts), _ecm(oracle, dim, data, munc, **opts)
+    _compare_ecm(a, b, f"ecm d{dim} {sorted(opts)}")
+    if opts.get("trackOptimizationPath"):
+        pa, pb = a[8]["optimization_path"], b[8]["optimization_path"]
+        assert len(pa) == len(pb)
+        for ea, eb in zip(pa, pb):
+            assert set(ea) == set(eb) and ea["iter"] == eb["iter"] and ea["reset_iteration"] == eb["reset_iteration"]
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+def test_ecm_free_running_and_qscale_and_warm_start(cb, oracle, dim):
+    data, munc = synth_tracks(31, 5, 3000)
+    rng = np.random.default_rng(5)
+    qs = (0.5 + rng.random(3000)).astype(np.float32)
+    qs[0] = 1.0
+    opts = dict(ECM_fixedBackgroundIters=25, ECM_fixedBackgroundRtol=1e-4, processQScale=qs,
+                lambdaExpInit=(0.2 + 6 * rng.random(3000)).astype(np.float32),
+                processPrecExpInit=np.exp(rng.normal(0, 1, 3000)).astype(np.float32))
+    a, b = _ecm(cb, dim, data, munc, **opts), _ecm(oracle, dim, data, munc, **opts)
+    _compare_ecm(a, b, f"ecm free d{dim}")
+    assert a[8]["converged"] == b[8]["converged"]
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+def test_ecm_tiny_track_uses_filter_smoother_fallback(cb, oracle, dim):
+    """n <= 5 (cconsenrich.pyx:7998-8129; reference case _caseCFixedBackgroundECMTinyTrackUsesFiniteFallback)."""
+    data, munc = synth_tracks(3, 3, 4)
+    a, b = _ecm(cb, dim, data, munc), _ecm(oracle, dim, data, munc)
+    assert a[0] == b[0] == 0
+    _compare_ecm(a, b, f"tiny d{dim}")
+    assert a[8]["skipped"] and a[8]["fallback"] == "filter_smoother_only"
+    np.testing.assert_array_equal(a[6], b[6])
+    np.testing.assert_array_equal(a[7], b[7])
+    short = (cb.cfixedBackgroundECM(matrixData=data, matrixPluginMuncInit=munc, matrixF=F, matrixQ0=Q0,
+                                    intervalToBlockMap=np.zeros(4, np.int32), blockCount=1, stateInit=0.0,
+                                    stateCovarInit=1000.0))
+    assert len(short) == 2 and short[0] == 0
+
+
+def test_disabled_multipliers_are_returned_as_none(cb):
+    data, munc = synth_tracks(8, 3, 200)
+    out = _ecm(cb, 2, data, munc, ECM_fixedBackgroundIters=1, ECM_useObsPrecisionReweighting=False,
+               ECM_useProcessPrecisionReweighting=False)
+    assert out[6] is None and out[7] is None  # tests/test_core.py:3078-3079
+
+
+def test_error_behaviour_matches_reference(cb, oracle):
+    data, munc = synth_tracks(1, 3, 50)
+    base = dict(matrixData=data, matrixPluginMuncInit=munc, matrixF=F, matrixQ0=Q0, blockCount=1, stateInit=0.0,
+                stateCovarInit=1000.0)
+    bad_bm = np.zeros(50, np.int32)
+    bad_bm[17] = 3
+    bad_qs = np.ones(50, np.float32)
+    bad_qs[0] = 2.0
+    for extra in (dict(intervalToBlockMap=bad_bm), dict(intervalToBlockMap=np.zeros(50, np.int32), blockCount=0),
+                  dict(intervalToBlockMap=np.zeros(50, np.int32), processQScale=bad_qs),
+                  dict(intervalToBlockMap=np.zeros(50, np.int32), obsPrecisionMultiplierMin=0.0),
+                  dict(intervalToBlockMap=np.zeros(10, np.int32)),
+                  dict(intervalToBlockMap=np.zeros(50, np.int32), matrixPluginMuncInit=munc[:, :40].copy())):
+        kw = {**base, **extra}
+        with pytest.raises(ValueError) as want:
+            oracle.cforwardPass(**kw)
+        with pytest.raises(ValueError) as got:
+            cb.cforwardPass(**kw)
+        assert str(got.value) == str(want.value)
+    with pytest.raises(ValueError, match="matrixQ0 is singular"):
+        cb.cfixedBackgroundECM(**{**base, "intervalToBlockMap": np.zeros(50, np.int32),
+                                  "matrixQ0": np.ones((2, 2), np.float32)})
+    with pytest.raises(NotImplementedError):
+        cb.cforwardPass(**base, intervalToBlockMap=np.zeros(50, np.int32), ECM_useAPN=True)
+    # empty input returns zeros without touching the device (pyx:6494-6501)
+    e = np.empty((3, 0), np.float32)
+    r = cb.cforwardPass(**{**base, "matrixData": e, "matrixPluginMuncInit": e}, intervalToBlockMap=np.zeros(0, np.int32),
+                        returnNLL=True)
+    assert r[0] == 0.0 and r[1] == 0 and r[2].shape == (0,) and r[3] == 0.0
+
+
+def test_install_routes_the_reference_seam(cb):
+    """install() swaps the six attributes on a module object, as the reference's tests do with
+    monkeypatch.setattr(cconsenrich, ...) (tests/test_core.py:1300-1317)."""
+    import types
+    fake = types.ModuleType("cconsenrich")
+    fake.cforwardPass = lambda *a, **k: "reference"
+    cb.install(fake)
+    assert fake.cforwardPass is cb.cforwardPass and fake.cfixedBackgroundECMLevel is cb.cfixedBackgroundECMLevel
+    cb.uninstall(fake)
+    assert fake.cforwardPass() == "reference"
+
+
+# ---------------------------------------------------------------------------------------------
+# benchmark-size checks (BASELINE.json configs[1]: m = 10, hg38 chr19 at 25 bp = 2 344 705 bins)
+# ---------------------------------------------------------------------------------------------
+CHR19_BINS_25BP = 2344705
+
+
+def test_chr19_sized_sweep_matches_oracle_and_properties(cb, oracle):
+    m, n = 10, CHR19_BINS_25BP
+    rng = np.random.default_rng(1729)
+    k = np.arange(n, dtype=np.float64)
+    x = 0.5 * np.sin(2 * np.pi * k / 5.0e4)
+    centers = rng.integers(0, n, size=3000)
+    for c, w, h in zip(centers, rng.uniform(8, 80, 3000), rng.uniform(0.5, 4.0, 3000)):
+        lo, hi = max(0, int(c - 5 * w)), min(n, int(c + 5 * w))
+        x[lo:hi] += h * np.exp(-0.5 * ((k[lo:hi] - c) / w) ** 2)
+    v0 = rng.uniform(0.05, 0.3, size=(m, 1))
+    munc = (v0 * (1.0 + np.abs(x))[None, :] * rng.uniform(0.5, 1.5, size=(m, n))).astype(np.float32)
+    data = (x[None, :] + rng.normal(0, 0.05, size=(m, 1)) + rng.normal(size=(m, n)) * np.sqrt(munc)).astype(np.float32)
+    want = _sweep(oracle, 2, data, munc)
+    got = _sweep(cb, 2, data, munc)
+    _compare_sweeps(got, want, n, 2, "chr19")
+    # size-independent properties
+    lvl = got["xs"][:, 0].astype(np.float64)
+    np.testing.assert_array_equal(got["res"], (data.T.astype(np.float64) - lvl[:, None]).astype(np.float32))
+    assert np.all(got["Ps"][:, 0, 0] <= got["Pf"][:, 0, 0] * (1 + 1e-5) + 1e-12)  # smoothing never adds variance
+    assert np.all(got["Pf"][:, 0, 0] > 0) and np.all(got["Ps"][:, 1, 1] >= 0)
+    np.testing.assert_array_equal(got["Ps"][:, 0, 1], got["Ps"][:, 1, 0])
+    again = _sweep(cb, 2, data, munc)  # look-back windows differ run to run; results may not
+    assert_tracks_close(again["xs"], got["xs"], "rerun", rtol=1e-6, atol_rel=1e-6)
+    # the filter is linear in (data, stateInit): scaling both by 2 scales the states by 2 exactly
+    # in exact arithmetic (powers of two commute with rounding)
+    twice = _sweep(cb, 2, 2.0 * data, munc, state_init=0.5)
+    assert_tracks_close(twice["xs"], 2.0 * got["xs"], "linearity", rtol=1e-5, atol_rel=1e-6)
+    assert_tracks_close(twice["Ps"], got["Ps"], "covariance is data-independent", scale="component",
+                        rtol=1e-6, atol_rel=1e-7)
