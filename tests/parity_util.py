@@ -17,11 +17,26 @@ reference's own tests use rtol = atol = 2e-6 against a float64 recursion on n <=
 (tests/test_core.py:3344-3351).  Integer outputs, Q tracks, and everything in the level
 (1-state) forward pass, where the reference does not round, are compared much tighter in
 the tests that use them.
+
+Diffuse-prior transient.  For the first TRANSIENT_BINS bins of a chromosome the prior
+(stateCovarInit = 1000, constants.py:141) still dominates: the reference rounds P^- ~ 1000 to
+float32 (ulp 6e-5) while the posterior cross terms are ~1e-3, so its own early-bin values
+carry rounding noise of relative size ~1e-4 (measured against the float64 recursion), and the
+smoother then subtracts ~500 from ~500 there.  Those rows are compared with both terms of the
+tolerance widened by TRANSIENT_FACTOR; every later row uses the stated tolerance.
 """
 import numpy as np
 
 RTOL = 1.0e-4
 ATOL_REL = 1.0e-5
+TRANSIENT_BINS = 64
+TRANSIENT_FACTOR = 10.0
+
+
+def _scale(w2, scale):
+    if isinstance(scale, str):
+        return np.max(np.abs(w2), axis=0, keepdims=True) if scale == "component" else np.max(np.abs(w2))
+    return scale  # precomputed (array scale or per-component row vector)
 
 
 def max_violation(got, want, scale="array", rtol=RTOL, atol_rel=ATOL_REL):
@@ -32,15 +47,34 @@ def max_violation(got, want, scale="array", rtol=RTOL, atol_rel=ATOL_REL):
         return 0.0
     g2 = got.reshape(got.shape[0], -1)
     w2 = want.reshape(want.shape[0], -1)
-    if scale == "component":
-        sc = np.max(np.abs(w2), axis=0, keepdims=True)
-    else:
-        sc = np.max(np.abs(w2))
-    tol = rtol * np.abs(w2) + atol_rel * sc + 1e-300
+    tol = rtol * np.abs(w2) + atol_rel * _scale(w2, scale) + 1e-300
     return float(np.max(np.abs(g2 - w2) / tol))
+
+
+def worst(got, want, scale="array", rtol=RTOL, atol_rel=ATOL_REL):
+    """(row, flat component, got, want) at the largest |err|/tol -- for failure messages."""
+    g2 = np.asarray(got, np.float64).reshape(len(got), -1)
+    w2 = np.asarray(want, np.float64).reshape(len(want), -1)
+    v = np.abs(g2 - w2) / (rtol * np.abs(w2) + atol_rel * _scale(w2, scale) + 1e-300)
+    r, c = np.unravel_index(int(np.argmax(v)), v.shape)
+    return int(r), int(c), float(g2[r, c]), float(w2[r, c])
 
 
 def assert_tracks_close(got, want, name="", scale="array", rtol=RTOL, atol_rel=ATOL_REL):
     assert np.all(np.isfinite(np.asarray(got, np.float64))), f"{name}: non-finite values"
     v = max_violation(got, want, scale, rtol, atol_rel)
-    assert v <= 1.0, f"{name}: max |err|/tol = {v:.3g} (rtol={rtol}, atol_rel={atol_rel}, scale={scale})"
+    assert v <= 1.0, (f"{name}: max |err|/tol = {v:.3g} (rtol={rtol}, atol_rel={atol_rel}); "
+                      f"worst (row, comp, got, want) = {worst(got, want, scale, rtol, atol_rel)}")
+
+
+def assert_sweep_tracks_close(got, want, name="", scale="array", rtol=RTOL, atol_rel=ATOL_REL):
+    """assert_tracks_close with the diffuse-prior transient rows at TRANSIENT_FACTOR x tolerance.
+    The scale is the steady rows' (rows past the transient) when there are any, else all rows'."""
+    got, want = np.asarray(got), np.asarray(want)
+    t = min(TRANSIENT_BINS, len(want))
+    w2 = np.asarray(want, np.float64).reshape(len(want), -1)
+    sc = _scale(w2[t:] if len(want) > t else w2, scale)
+    if len(want) > t:
+        assert_tracks_close(got[t:], want[t:], name, sc, rtol, atol_rel)
+    assert_tracks_close(got[:t], want[:t], name + " (transient rows)", sc, rtol * TRANSIENT_FACTOR,
+                        atol_rel * TRANSIENT_FACTOR)

