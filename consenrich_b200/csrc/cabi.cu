@@ -205,6 +205,7 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     a.agg_out = agg_out;
     a.n = n;
     a.m = (double)m;
+    a.inv_m = 1.0 / (double)m;
     a.mlog2pi = (double)m * log(6.2831853071795864769);
     a.M = to_model2(mo);
     a.state_init = mo->state_init;

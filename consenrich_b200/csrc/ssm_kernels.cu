@@ -95,7 +95,7 @@ __device__ __forceinline__ void fold_cell(FoldAcc &a, float zf, float vf, double
     const double z = (double)zf;
     double r = (double)vf + pad;
     if (r < 1.0e-12) r = 1.0e-12;
-    const double w = 1.0 / r;
+    const double w = cb_rcp(r);
     const double wz = w * z;
     a.s0 += w;
     a.s1 += wz;
@@ -262,11 +262,12 @@ struct Fwd2 {
         }
     }
 
+    template <bool FULL>
     __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t) {
         Elem g = filt2_identity();
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
                 const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
@@ -277,20 +278,24 @@ struct Fwd2 {
         return g;
     }
 
+    template <bool FULL>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t,
                                                  const State &st, double &acc_d, double &acc_nll) {
         Kf2 s{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+        NllAcc acc;
+        nll_acc_init(acc);
+        const bool per_bin = a.nll_in_d != 0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 unsigned char *b = rec + i * 48;
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
                 const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
                 BinOut o;
-                kf2_step(s, a.M, ql.x, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.mlog2pi, a.want_nll != 0,
-                         a.nll_in_d != 0, o);
+                kf2_step(s, a.M, ql.x, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi, a.want_nll != 0,
+                         per_bin, o, acc);
                 const float d = (float)o.stat;
                 acc_d += (double)d;
                 acc_nll += o.nll;
@@ -299,6 +304,7 @@ struct Fwd2 {
                 *reinterpret_cast<float4 *>(b + 32) = make_float4((float)s.x0, (float)s.x1, d, 0.0f);
             }
         }
+        if (a.want_nll && !per_bin) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
     }
 
     __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
@@ -342,11 +348,12 @@ struct Fwd1 {
     __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
         Fwd2::stage_in(a, recs, p0, tid);
     }
+    template <bool FULL>
     __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t) {
         Elem g = filt1_identity();
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
                 const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
@@ -355,26 +362,31 @@ struct Fwd1 {
         }
         return g;
     }
+    template <bool FULL>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t,
                                                  const State &st, double &acc_d, double &acc_nll) {
         State1 s = st;
+        NllAcc acc;
+        nll_acc_init(acc);
+        const bool per_bin = a.nll_in_d != 0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 unsigned char *b = rec + i * 48;
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
                 const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
                 BinOut o;
-                kf1_step(s, ql.x * a.M.q00, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.mlog2pi, a.want_nll != 0,
-                         a.nll_in_d != 0, o);
+                kf1_step(s, ql.x * a.M.q00, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
+                         a.want_nll != 0, per_bin, o, acc);
                 const float d = (float)o.stat;
                 acc_d += (double)d;
                 acc_nll += o.nll;
                 *reinterpret_cast<float4 *>(b) = make_float4((float)s.x, (float)s.P, (float)o.Q00, d);
             }
         }
+        if (a.want_nll && !per_bin) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
     }
     __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
 #pragma unroll
@@ -436,11 +448,12 @@ struct Bwd2 {
             *reinterpret_cast<float4 *>(s + 32) = make_float4(x[r].x, x[r].y, 0.0f, 0.0f);
         }
     }
+    template <bool FULL>
     __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t q0) {
         Elem g = smo2_identity();
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 const float4 P = *reinterpret_cast<const float4 *>(rec + i * 48);
                 const float4 Q = *reinterpret_cast<const float4 *>(rec + i * 48 + 16);
                 const float4 x = *reinterpret_cast<const float4 *>(rec + i * 48 + 32);
@@ -456,12 +469,13 @@ struct Bwd2 {
         }
         return g;
     }
+    template <bool FULL>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t q0,
                                                  const State &st, double &, double &) {
         Rs2 c{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 unsigned char *b = rec + i * 48;
                 const float4 P = *reinterpret_cast<const float4 *>(b);
                 const float4 Q = *reinterpret_cast<const float4 *>(b + 16);
@@ -530,11 +544,12 @@ struct Bwd1 {
         for (int r = 0; r < CHUNK; ++r)
             *reinterpret_cast<float4 *>(G::slot(recs, tid + r * SCAN_THREADS)) = make_float4(x[r], P[r], Q[r], 0.0f);
     }
+    template <bool FULL>
     __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t q0) {
         Elem g = smo1_identity();
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 const float4 v = *reinterpret_cast<const float4 *>(rec + i * 16);
                 Elem e;
                 if (q0 + i == 0 && a.is_last_shard) {
@@ -549,12 +564,13 @@ struct Bwd1 {
         }
         return g;
     }
+    template <bool FULL>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t q0,
                                                  const State &st, double &, double &) {
         double cx = r32(st.x), cP = r32(st.P);
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (i < cnt) {
+            if (FULL || i < cnt) {
                 unsigned char *b = rec + i * 16;
                 const float4 v = *reinterpret_cast<const float4 *>(b);
                 if (q0 + i == 0 && a.is_last_shard) {
@@ -606,7 +622,12 @@ __device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWor
         int f;
         while (true) {
             f = (idx >= 0) ? ld_acquire(ws.flags + idx) : 2;
-            if (!__any_sync(FULL, f == 0)) break;
+            // the window is usable as soon as every tile up to the nearest published prefix has
+            // at least its aggregate out; tiles beyond that prefix do not matter
+            const unsigned pm = __ballot_sync(FULL, f == 2);
+            const unsigned zm = __ballot_sync(FULL, f == 0);
+            const unsigned upto = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : FULL;  // lanes 0..first
+            if ((zm & upto) == 0) break;
         }
         const unsigned pm = __ballot_sync(FULL, f == 2);
         const int first = pm ? (__ffs(pm) - 1) : 32;
@@ -619,9 +640,10 @@ __device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWor
         } else {
             e = load_elem_cg<Elem>(ws.tile_agg + (int64_t)idx * AGG_PITCH);
         }
-        // ordered tree reduction: lane i holds tile base-i, lane i+d an earlier tile
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        // ordered tree reduction over lanes 0..first: lane i holds tile base-i, lane i+d an earlier
+        // tile; only as many levels as the window needs
+        const int span = first < 32 ? first + 1 : 32;
+        for (int d = 1; d < span; d <<= 1) {
             const Elem o = shfl_down_elem(e, d);
             if (lane + d < 32) e = Tr::combine(o, e);
         }
@@ -677,7 +699,8 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
     int64_t rem = a.n - q0;
     const int cnt = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
     unsigned char *myrec = recs + tid * Tr::G::REC_BYTES;
-    const Elem mine = Tr::pass1(a, myrec, cnt, q0);
+    const Elem mine = (cnt == CHUNK) ? Tr::template pass1<true>(a, myrec, cnt, q0)
+                                     : Tr::template pass1<false>(a, myrec, cnt, q0);
 
     // inclusive Kogge-Stone scan across the warp
     Elem inc = mine;
@@ -740,7 +763,10 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
     if (lane > 0) start = Tr::apply(lex, wst);
 
     double acc0 = 0.0, acc1 = 0.0;
-    Tr::pass2(a, myrec, cnt, q0, start, acc0, acc1);
+    if (cnt == CHUNK)
+        Tr::template pass2<true>(a, myrec, cnt, q0, start, acc0, acc1);
+    else
+        Tr::template pass2<false>(a, myrec, cnt, q0, start, acc0, acc1);
 
     if (Tr::HAS_SUMS) {
 #pragma unroll

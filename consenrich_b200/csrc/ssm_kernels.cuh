@@ -32,7 +32,7 @@ struct FwdArgs {
     double *sums;              // device double[2] or nullptr
     double *agg_out;           // aggregate-only mode: shard aggregate destination
     int64_t n;
-    double m, mlog2pi;
+    double m, inv_m, mlog2pi;
     Model2 M;
     double state_init, cov_init;
     double lam_min, lam_max, kap_min, kap_max;

@@ -120,10 +120,12 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
             s.x0 = r32(s.x0); s.x1 = r32(s.x1);
             s.P00 = r32(s.P00); s.P01 = r32(s.P01); s.P10 = s.P01; s.P11 = r32(s.P11);
         }
+        NllAcc acc;
+        nll_acc_init(acc);
         for (int64_t k = c * L; k < n && k < (c + 1) * L; ++k) {
             BinOut o;
-            kf2_step(s, M, qk_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, mlog2pi,
-                     p->return_nll != 0, p->store_nll_in_d != 0, o);
+            kf2_step(s, M, qk_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, 1.0 / (double)m, mlog2pi,
+                     p->return_nll != 0, p->store_nll_in_d != 0, o, acc);
             D[k] = (float)o.stat;
             *sum_d += (double)D[k];
             *sum_nll += o.nll;
@@ -137,6 +139,7 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
                 }
             }
         }
+        if (p->return_nll && !p->store_nll_in_d) *sum_nll += nll_acc_finish(acc, (double)m, mlog2pi);
     }
 }
 
@@ -191,10 +194,12 @@ void emul_forward1(const double *S0, const double *S1, const double *S2, const d
         int64_t t = c / T, i = c % T;
         State1 s = tile_prefix[t];
         if (i > 0) s = filt1_apply(incl[t][i - 1], s);
+        NllAcc acc;
+        nll_acc_init(acc);
         for (int64_t k = c * L; k < n && k < (c + 1) * L; ++k) {
             BinOut o;
-            kf1_step(s, q_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, mlog2pi,
-                     p->return_nll != 0, p->store_nll_in_d != 0, o);
+            kf1_step(s, q_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, 1.0 / (double)m, mlog2pi,
+                     p->return_nll != 0, p->store_nll_in_d != 0, o, acc);
             D[k] = (float)o.stat;
             *sum_d += (double)D[k];
             *sum_nll += o.nll;
@@ -204,6 +209,7 @@ void emul_forward1(const double *S0, const double *S1, const double *S2, const d
                 if (k > 0) Qf[k - 1] = (float)o.Q00;
             }
         }
+        if (p->return_nll && !p->store_nll_in_d) *sum_nll += nll_acc_finish(acc, (double)m, mlog2pi);
     }
 }
 
