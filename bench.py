@@ -248,13 +248,17 @@ def run_b200_arm(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
+    # one explicit stream carries everything: the library's kernels, the CUDA events that time them
+    # and torch's own work
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
     m, n = M_TRACKS, N_BINS
     ld = (n + 31) // 32 * 32
     reps = [synth_device(torch, dev, 1729 + 97 * rank + r, m, n, ld) for r in range(N_REPLICAS)]
     model = make_model(2, F_MAT, Q0_MAT, 0.0, 1000.0, 1e-4, kap_bounds=KAP_BOUNDS, return_nll=True, use_kappa=True)
-    stream = torch.cuda.current_stream(dev)
     ts = TrackSweep(m, n, 2, local, residuals=True)
     ctx = ts.ctx
+    assert ctx.stream_handle == int(stream.cuda_stream) != 0, "library and timing events must share one stream"
 
     def step(i):
         d, v, kap = reps[i % N_REPLICAS]
@@ -286,6 +290,14 @@ def run_b200_arm(args):
     kern = ctx.kernel_ms()
     ctx.enable_timing(False)
     nll = float(ts.sums[1].item())  # the step's scalar result
+    # diagnostic: the same K steps without the per-kernel event pairs (how much the bracketing costs)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    e1.record(stream)
+    barrier()
+    ms_plain = e0.elapsed_time(e1)
 
     # ---- e2e through the reference-facing host API, pinned host buffers ----
     host = {}
@@ -374,7 +386,8 @@ def run_b200_arm(args):
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "gpu_launches": int(e2e_launches),
                     "api": "consenrich_b200.sweep -> cb200_host_sweep (pinned host arrays)"},
             "roofline": roofline, "cpu_baseline": cpu,
-            "check": {"sum_nll_device": nll, "sum_nll_e2e": nll_e2e},
+            "check": {"sum_nll_device": nll, "sum_nll_e2e": nll_e2e,
+                      "ms_per_step_without_kernel_events": ms_plain / args.steps},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -72,6 +72,7 @@ SIGNATURES = {
     "cb200_ctx_enable_timing": (C.c_int, [_vp, C.c_int]),
     "cb200_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cb200_ctx_reset_timing": (C.c_int, [_vp]),
+    "cb200_set_scan_substeps": (C.c_int, [C.c_int]),
     "cb200_device_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "cb200_device_free": (C.c_int, [_vp, _vp]),
     "cb200_pinned_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),
@@ -150,6 +151,7 @@ class Context:
         check(self._lib.cb200_ctx_create(int(device), _vp(stream) if stream else None, C.byref(h)))
         self.handle = h
         self.device = int(device)
+        self.stream_handle = int(stream) if stream else 0  # 0: a stream owned by the context
 
     def close(self):
         if getattr(self, "handle", None):
@@ -164,6 +166,7 @@ class Context:
 
     def set_stream(self, stream: int | None):
         check(self._lib.cb200_ctx_set_stream(self.handle, _vp(stream) if stream else None))
+        self.stream_handle = int(stream) if stream else 0
 
     def sync(self):
         check(self._lib.cb200_ctx_sync(self.handle))

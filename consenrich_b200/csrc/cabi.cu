@@ -65,6 +65,8 @@ struct cb200_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int64_t launches = 0;
+    int32_t scan_epoch = 0;  // bumped per look-back scan launch (tags the workspace flags)
+    int64_t scan_ws_n = 0;   // track length the scan workspace is laid out for
     // arena (device)
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     double *sums_host = nullptr;  // pinned double[2]
@@ -90,6 +92,28 @@ int ensure(cb200_ctx *c, DevBuf &b, size_t bytes) {
     size_t want = bytes < 256 ? 256 : bytes;
     CU_TRY(cudaMalloc(&b.p, want));
     b.cap = want;
+    return CB200_OK;
+}
+
+// workspace view for the next look-back scan launch
+int next_scan_ws(cb200_ctx *c, int64_t n, ScanWorkspace *ws) {
+    // The layout (where flags and counters live) is fixed per allocation: the flags carry launch
+    // epochs and the counters are left at zero by each launch, so they must not move between
+    // launches of different lengths.
+    bool fresh = false;
+    if (n > c->scan_ws_n || !c->scan_ws.p) {
+        const int64_t n_alloc = n + n / 4 + 4096;
+        CB_TRY(ensure(c, c->scan_ws, scan_workspace_bytes(n_alloc)));
+        c->scan_ws_n = n_alloc;
+        fresh = true;
+    }
+    if (fresh || c->scan_epoch >= (1 << 28)) {
+        CU_TRY(cudaMemsetAsync(c->scan_ws.p, 0, c->scan_ws.cap, c->stream));
+        c->scan_epoch = 0;
+    }
+    c->scan_epoch += 1;
+    *ws = scan_workspace_carve(c->scan_ws.p, c->scan_ws_n);
+    ws->epoch4 = c->scan_epoch * 4;
     return CB200_OK;
 }
 
@@ -195,7 +219,8 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     if (mo->use_lambda && !lam) return fail(CB200_ERR_INVALID, "lambdaExp is required when use_lambda is set");
     if (mo->use_kappa && !kap) return fail(CB200_ERR_INVALID, "processPrecExp is required when use_kappa is set");
     if (mo->use_qscale && !qs) return fail(CB200_ERR_INVALID, "processQScale is required when use_qscale is set");
-    CB_TRY(ensure(c, c->scan_ws, scan_workspace_bytes(n)));
+    ScanWorkspace ws;
+    CB_TRY(next_scan_ws(c, n, &ws));
     FwdArgs a{};
     a.S0 = stats; a.S1 = stats + stride; a.S2 = stats + 2 * stride; a.SL = stats + 3 * stride;
     a.lam = lam; a.kap = kap; a.qs = qs;
@@ -215,7 +240,6 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     a.use_lambda = mo->use_lambda; a.use_kappa = mo->use_kappa; a.use_qscale = mo->use_qscale;
     a.want_nll = mo->return_nll; a.nll_in_d = mo->store_nll_in_d;
     a.do_store = store ? 1 : 0;
-    ScanWorkspace ws = scan_workspace_carve(c->scan_ws.p, n);
     int launches = 0;
     {
         Span sp(c, FAM_FWD);
@@ -232,7 +256,8 @@ int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf,
     if (d == 2 && (!aligned(xf, 8) || !aligned(Pf, 16) || !aligned(Qf, 16) ||
                    (!aggregate_only && (!aligned(xs, 8) || !aligned(Ps, 16) || !aligned(lag, 16)))))
         return fail(CB200_ERR_INVALID, "smoother tracks must be 8/16-byte aligned device pointers");
-    CB_TRY(ensure(c, c->scan_ws, scan_workspace_bytes(n)));
+    ScanWorkspace ws;
+    CB_TRY(next_scan_ws(c, n, &ws));
     BwdArgs a{};
     a.xf = xf; a.Pf = Pf; a.Qf = Qf;
     a.tail_state = tail_state;
@@ -242,7 +267,6 @@ int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf,
     a.lag_rows = lag_rows;
     a.M = to_model2(mo);
     a.is_last_shard = is_last;
-    ScanWorkspace ws = scan_workspace_carve(c->scan_ws.p, n);
     int launches = 0;
     {
         Span sp(c, FAM_BWD);
@@ -416,6 +440,12 @@ int cb200_ctx_kernel_ms(cb200_ctx *c, int family, double *ms, int64_t *launches)
     CB_TRY(resolve_spans(c));
     if (ms) *ms = c->fam_ms[family];
     if (launches) *launches = c->fam_n[family];
+    return CB200_OK;
+}
+
+int cb200_set_scan_substeps(int nsub) {
+    if (nsub < 0 || nsub > MAX_NSUB) return fail(CB200_ERR_INVALID, "scan sub-steps must be in [0, %d]", MAX_NSUB);
+    scan_set_nsub_override(nsub);
     return CB200_OK;
 }
 

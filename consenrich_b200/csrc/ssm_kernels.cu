@@ -15,6 +15,8 @@
 // aggregates.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "ssm_kernels.cuh"
 
 namespace cb200 {
@@ -202,6 +204,12 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
 // =====================================================================================
 // scan traits
 // =====================================================================================
+// Geometry.  A tile is SCAN_THREADS runs of L = CHUNK * nsub consecutive scan positions, one
+// run per thread.  A run is processed in nsub sub-steps of CHUNK positions; for each sub-step
+// the CTA stages the 128 x CHUNK records of all its threads through shared memory so that
+// global traffic stays coalesced (groups of CHUNK consecutive bins = whole 32-byte sectors).
+// Long runs amortise the warp scan, the cross-warp prefix and the look-back over L positions.
+//
 // Shared-memory record of one thread: CHUNK bins of BIN_BYTES plus 16 bytes of padding so that
 // 16-byte accesses of a quarter warp fall in distinct banks (record stride = 4 mod 8 words).
 template <int BIN_BYTES>
@@ -212,16 +220,25 @@ struct RecGeom {
     }
 };
 
+// scan position of staged record g (thread g / CHUNK, slot g % CHUNK) in sub-step s
+__device__ __forceinline__ int64_t stage_pos(int64_t p0, int L, int s, int g) {
+    return p0 + (int64_t)(g / CHUNK) * L + s * CHUNK + (g % CHUNK);
+}
+
 // ---- forward, 2-state ------------------------------------------------------------------
 // record per bin, in : [S0 S1][S2 SL][qk(f64) lam(f32) pad]        (48 bytes)
 //                 out: [Pf 4xf32][Qf 4xf32][xf 2xf32, D f32, pad]
+// scan position = bin index k.
+template <bool CANON>
 struct Fwd2 {
     using Elem = Filt2;
     using State = State2;
     using Args = FwdArgs;
     using G = RecGeom<48>;
+    using Carry = Kf2;
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
+    __device__ static __forceinline__ int64_t positions(const Args &a) { return a.n; }
 
     __device__ static __forceinline__ Elem identity() { return filt2_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt2_combine(a, b); }
@@ -234,68 +251,79 @@ struct Fwd2 {
         if (a.init_state) return load_elem_cg<State2>(a.init_state);
         return State2{a.state_init, 0.0, a.cov_init, 0.0, a.cov_init};
     }
+    // valid slots [lo, hi) of the CHUNK positions starting at q0
+    __device__ static __forceinline__ void bounds(const Args &a, int64_t q0, int &lo, int &hi) {
+        const int64_t rem = a.n - q0;
+        lo = 0;
+        hi = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
+    }
 
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    // ALL = false: only what pass 1 reads (S0, S1, qk, lam)
+    template <bool ALL>
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                    int tid) {
         double s0[CHUNK], s1[CHUNK], s2[CHUNK], sl[CHUNK];
         float lm[CHUNK], kp[CHUNK], qs[CHUNK];
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int64_t k = p0 + tid + r * SCAN_THREADS;
+            const int64_t k = stage_pos(p0, L, s, tid + r * SCAN_THREADS);
             const bool ok = k < a.n;
             s0[r] = ok ? __ldg(a.S0 + k) : 0.0;
             s1[r] = ok ? __ldg(a.S1 + k) : 0.0;
-            s2[r] = ok ? __ldg(a.S2 + k) : 0.0;
-            sl[r] = (ok && a.want_nll) ? __ldg(a.SL + k) : 0.0;
+            s2[r] = (ALL && ok) ? __ldg(a.S2 + k) : 0.0;
+            sl[r] = (ALL && ok && a.want_nll) ? __ldg(a.SL + k) : 0.0;
             lm[r] = (ok && a.use_lambda) ? __ldg(a.lam + k) : 1.0f;
             kp[r] = (ok && a.use_kappa) ? __ldg(a.kap + k) : 1.0f;
             qs[r] = (ok && a.use_qscale) ? __ldg(a.qs + k) : 1.0f;
         }
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            unsigned char *s = G::slot(recs, tid + r * SCAN_THREADS);
+            unsigned char *d = G::slot(recs, tid + r * SCAN_THREADS);
             const double kappa = a.use_kappa ? clampd((double)kp[r], a.kap_min, a.kap_max) : 1.0;
             const double lam = a.use_lambda ? clampd((double)lm[r], a.lam_min, a.lam_max) : 1.0;
-            const double qk = (double)qs[r] / kappa;
-            *reinterpret_cast<double2 *>(s) = make_double2(s0[r], s1[r]);
-            *reinterpret_cast<double2 *>(s + 16) = make_double2(s2[r], sl[r]);
-            *reinterpret_cast<double2 *>(s + 32) = make_double2(qk, __longlong_as_double((long long)__float_as_uint((float)lam)));
+            const double qk = a.use_kappa ? cb_div((double)qs[r], kappa) : (double)qs[r];
+            *reinterpret_cast<double2 *>(d) = make_double2(s0[r], s1[r]);
+            if (ALL) *reinterpret_cast<double2 *>(d + 16) = make_double2(s2[r], sl[r]);
+            *reinterpret_cast<double2 *>(d + 32) = make_double2(qk, __longlong_as_double((long long)__float_as_uint((float)lam)));
         }
     }
 
-    template <bool FULL>
-    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t) {
-        Elem g = filt2_identity();
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t,
+                                                 Elem &g) {
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
                 const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
                 const double qk = ql.x;
-                filt2_step(g, a.M, qk * a.M.q00, qk * a.M.q01, qk * a.M.q11, lam * s01.x, lam * s01.y);
+                filt2_step<CANON>(g, a.M, qk * a.M.q00, qk * a.M.q01, qk * a.M.q11, lam * s01.x, lam * s01.y);
             }
         }
-        return g;
     }
 
-    template <bool FULL>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t,
-                                                 const State &st, double &acc_d, double &acc_nll) {
-        Kf2 s{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+    __device__ static __forceinline__ Carry begin2(const Args &, const State &st) {
+        return Kf2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+    }
+
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t,
+                                                 Carry &s, double &acc_d, double &acc_nll) {
         NllAcc acc;
         nll_acc_init(acc);
         const bool per_bin = a.nll_in_d != 0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 unsigned char *b = rec + i * 48;
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
                 const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
                 BinOut o;
-                kf2_step(s, a.M, ql.x, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi, a.want_nll != 0,
-                         per_bin, o, acc);
+                kf2_step<CANON>(s, a.M, ql.x, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
+                                a.want_nll != 0, per_bin, o, acc);
                 const float d = (float)o.stat;
                 acc_d += (double)d;
                 acc_nll += o.nll;
@@ -307,19 +335,22 @@ struct Fwd2 {
         if (a.want_nll && !per_bin) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
     }
 
-    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                     int tid) {
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
             const int g = tid + r * SCAN_THREADS;
-            const int64_t k = p0 + g;
+            const int64_t k = stage_pos(p0, L, s, g);
             if (k < a.n) {
-                const unsigned char *s = G::slot(recs, g);
-                const float4 xd = *reinterpret_cast<const float4 *>(s + 32);
+                const unsigned char *d = G::slot(recs, g);
+                const float4 xd = *reinterpret_cast<const float4 *>(d + 32);
                 if (a.do_store) {
-                    reinterpret_cast<float4 *>(a.Pf)[k] = *reinterpret_cast<const float4 *>(s);
-                    if (k > 0) reinterpret_cast<float4 *>(a.Qf)[k - 1] = *reinterpret_cast<const float4 *>(s + 16);
+                    reinterpret_cast<float4 *>(a.Pf)[k] = *reinterpret_cast<const float4 *>(d);
+                    if (k > 0) reinterpret_cast<float4 *>(a.Qf)[k - 1] = *reinterpret_cast<const float4 *>(d + 16);
                     reinterpret_cast<float2 *>(a.xf)[k] = make_float2(xd.x, xd.y);
                 }
+                // Q of the shard's first bin belongs to row n-1 of the preceding shard
+                if (k == 0 && a.q_head) *reinterpret_cast<float4 *>(a.q_head) = *reinterpret_cast<const float4 *>(d + 16);
                 if (a.D) a.D[k] = xd.z;
             }
         }
@@ -333,8 +364,10 @@ struct Fwd1 {
     using State = State1;
     using Args = FwdArgs;
     using G = RecGeom<48>;
+    using Carry = State1;
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
+    __device__ static __forceinline__ int64_t positions(const Args &a) { return a.n; }
 
     __device__ static __forceinline__ Elem identity() { return filt1_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt1_combine(a, b); }
@@ -345,33 +378,37 @@ struct Fwd1 {
         if (a.init_state) return load_elem_cg<State1>(a.init_state);
         return State1{a.state_init, a.cov_init};
     }
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
-        Fwd2::stage_in(a, recs, p0, tid);
+    __device__ static __forceinline__ void bounds(const Args &a, int64_t q0, int &lo, int &hi) {
+        Fwd2<false>::bounds(a, q0, lo, hi);
     }
-    template <bool FULL>
-    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t) {
-        Elem g = filt1_identity();
+    template <bool ALL>
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                    int tid) {
+        Fwd2<false>::stage_in<ALL>(a, recs, p0, L, s, tid);
+    }
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t,
+                                                 Elem &g) {
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
                 const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
                 const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
                 filt1_step(g, ql.x * a.M.q00, lam * s01.x, lam * s01.y);
             }
         }
-        return g;
     }
-    template <bool FULL>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t,
-                                                 const State &st, double &acc_d, double &acc_nll) {
-        State1 s = st;
+    __device__ static __forceinline__ Carry begin2(const Args &, const State &st) { return st; }
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t,
+                                                 Carry &s, double &acc_d, double &acc_nll) {
         NllAcc acc;
         nll_acc_init(acc);
         const bool per_bin = a.nll_in_d != 0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 unsigned char *b = rec + i * 48;
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
@@ -388,11 +425,12 @@ struct Fwd1 {
         }
         if (a.want_nll && !per_bin) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
     }
-    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                     int tid) {
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
             const int g = tid + r * SCAN_THREADS;
-            const int64_t k = p0 + g;
+            const int64_t k = stage_pos(p0, L, s, g);
             if (k < a.n) {
                 const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
                 if (a.do_store) {
@@ -400,6 +438,7 @@ struct Fwd1 {
                     a.Pf[k] = o.y;
                     if (k > 0) a.Qf[k - 1] = o.z;
                 }
+                if (k == 0 && a.q_head) a.q_head[0] = o.z;
                 if (a.D) a.D[k] = o.w;
             }
         }
@@ -407,14 +446,21 @@ struct Fwd1 {
 };
 
 // ---- backward, 2-state -----------------------------------------------------------------
-// position q = n-1-k runs forward.  record per bin, in: [Pf][Qf row k][xf, pad]; out: [Ps][lag][xs]
+// scan position q runs against the bins: k = npad - 1 - q with npad = n rounded up to CHUNK, so
+// that every staged group of CHUNK positions is a CHUNK-aligned block of bins (whole sectors);
+// the first npad - n positions are empty.  record per bin, in: [Pf][Qf row k][xf, pad];
+// out: [Ps][lag][xs]
+template <bool CANON>
 struct Bwd2 {
     using Elem = Smo2;
     using State = State2;
     using Args = BwdArgs;
     using G = RecGeom<48>;
+    using Carry = Rs2;
     static constexpr bool HAS_SUMS = false;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
+    __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
+    __device__ static __forceinline__ int64_t positions(const Args &a) { return npad(a); }
 
     __device__ static __forceinline__ Elem identity() { return smo2_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo2_combine(a, b); }
@@ -427,13 +473,23 @@ struct Bwd2 {
         if (a.tail_state) return load_elem_cg<State2>(a.tail_state);
         return State2{0.0, 0.0, 0.0, 0.0, 0.0};
     }
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    __device__ static __forceinline__ void bounds(const Args &a, int64_t q0, int &lo, int &hi) {
+        const int64_t np = npad(a);
+        const int64_t first = (np - a.n) - q0;  // positions below npad - n hold no bin
+        const int64_t rem = np - q0;
+        lo = first <= 0 ? 0 : (first >= CHUNK ? CHUNK : (int)first);
+        hi = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
+    }
+    template <bool ALL>
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                    int tid) {
         float4 P[CHUNK], Q[CHUNK];
         float2 x[CHUNK];
+        const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int64_t k = a.n - 1 - (p0 + tid + r * SCAN_THREADS);
-            const bool ok = k >= 0;
+            const int64_t k = np - 1 - stage_pos(p0, L, s, tid + r * SCAN_THREADS);
+            const bool ok = k >= 0 && k < a.n;
             P[r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.Pf) + k) : make_float4(0, 0, 0, 0);
             // row n-1 of Qf holds nothing unless a following shard supplied it
             Q[r] = (ok && (k < a.n - 1 || !a.is_last_shard)) ? __ldg(reinterpret_cast<const float4 *>(a.Qf) + k)
@@ -442,49 +498,52 @@ struct Bwd2 {
         }
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            unsigned char *s = G::slot(recs, tid + r * SCAN_THREADS);
-            *reinterpret_cast<float4 *>(s) = P[r];
-            *reinterpret_cast<float4 *>(s + 16) = Q[r];
-            *reinterpret_cast<float4 *>(s + 32) = make_float4(x[r].x, x[r].y, 0.0f, 0.0f);
+            unsigned char *d = G::slot(recs, tid + r * SCAN_THREADS);
+            *reinterpret_cast<float4 *>(d) = P[r];
+            *reinterpret_cast<float4 *>(d + 16) = Q[r];
+            *reinterpret_cast<float4 *>(d + 32) = make_float4(x[r].x, x[r].y, 0.0f, 0.0f);
         }
     }
-    template <bool FULL>
-    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t q0) {
-        Elem g = smo2_identity();
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t q0,
+                                                 Elem &g) {
+        const int64_t klast = npad(a) - 1 - q0;  // bin of slot 0
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 const float4 P = *reinterpret_cast<const float4 *>(rec + i * 48);
                 const float4 Q = *reinterpret_cast<const float4 *>(rec + i * 48 + 16);
                 const float4 x = *reinterpret_cast<const float4 *>(rec + i * 48 + 32);
                 Elem e;
-                if (q0 + i == 0 && a.is_last_shard) {
+                if (klast - i == a.n - 1 && a.is_last_shard) {
                     e = smo2_from_state(State2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.w});
                 } else {
-                    const Rts2 r = rts2_gain(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
+                    const Rts2 r = rts2_gain<CANON>(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
                     e = smo2_from_rts(r, x.x, x.y, P.x, P.y, P.w);
                 }
                 g = smo2_combine(g, e);
             }
         }
-        return g;
     }
-    template <bool FULL>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t q0,
-                                                 const State &st, double &, double &) {
-        Rs2 c{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+    __device__ static __forceinline__ Carry begin2(const Args &, const State &st) {
+        return Rs2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+    }
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
+                                                 Carry &c, double &, double &) {
+        const int64_t klast = npad(a) - 1 - q0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 unsigned char *b = rec + i * 48;
                 const float4 P = *reinterpret_cast<const float4 *>(b);
                 const float4 Q = *reinterpret_cast<const float4 *>(b + 16);
                 const float4 x = *reinterpret_cast<const float4 *>(b + 32);
-                if (q0 + i == 0 && a.is_last_shard) {
+                if (klast - i == a.n - 1 && a.is_last_shard) {
                     c = Rs2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.z, (double)P.w};
                     // xs = xf, Ps = Pf already in place; lag row n-1 does not exist
                 } else {
-                    const Rts2 r = rts2_gain(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
+                    const Rts2 r = rts2_gain<CANON>(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
                     Smo2Out o;
                     rts2_step(c, r, x.x, x.y, P.x, P.y, P.w, o);
                     *reinterpret_cast<float4 *>(b) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
@@ -494,17 +553,19 @@ struct Bwd2 {
             }
         }
     }
-    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                     int tid) {
+        const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
             const int g = tid + r * SCAN_THREADS;
-            const int64_t k = a.n - 1 - (p0 + g);
-            if (k >= 0) {
-                const unsigned char *s = G::slot(recs, g);
-                reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(s);
+            const int64_t k = np - 1 - stage_pos(p0, L, s, g);
+            if (k >= 0 && k < a.n) {
+                const unsigned char *d = G::slot(recs, g);
+                reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(d);
                 if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
-                    reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(s + 16);
-                const float4 x = *reinterpret_cast<const float4 *>(s + 32);
+                    reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(d + 16);
+                const float4 x = *reinterpret_cast<const float4 *>(d + 32);
                 reinterpret_cast<float2 *>(a.xs)[k] = make_float2(x.x, x.y);
             }
         }
@@ -518,8 +579,13 @@ struct Bwd1 {
     using State = State1;
     using Args = BwdArgs;
     using G = RecGeom<16>;
+    struct Carry {
+        double x, P;
+    };
     static constexpr bool HAS_SUMS = false;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
+    __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
+    __device__ static __forceinline__ int64_t positions(const Args &a) { return npad(a); }
 
     __device__ static __forceinline__ Elem identity() { return smo1_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo1_combine(a, b); }
@@ -530,12 +596,22 @@ struct Bwd1 {
         if (a.tail_state) return load_elem_cg<State1>(a.tail_state);
         return State1{0.0, 0.0};
     }
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    __device__ static __forceinline__ void bounds(const Args &a, int64_t q0, int &lo, int &hi) {
+        const int64_t np = npad(a);
+        const int64_t first = (np - a.n) - q0;
+        const int64_t rem = np - q0;
+        lo = first <= 0 ? 0 : (first >= CHUNK ? CHUNK : (int)first);
+        hi = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
+    }
+    template <bool ALL>
+    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                    int tid) {
         float x[CHUNK], P[CHUNK], Q[CHUNK];
+        const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int64_t k = a.n - 1 - (p0 + tid + r * SCAN_THREADS);
-            const bool ok = k >= 0;
+            const int64_t k = np - 1 - stage_pos(p0, L, s, tid + r * SCAN_THREADS);
+            const bool ok = k >= 0 && k < a.n;
             x[r] = ok ? __ldg(a.xf + k) : 0.0f;
             P[r] = ok ? __ldg(a.Pf + k) : 0.0f;
             Q[r] = (ok && (k < a.n - 1 || !a.is_last_shard)) ? __ldg(a.Qf + k) : 0.0f;
@@ -544,15 +620,16 @@ struct Bwd1 {
         for (int r = 0; r < CHUNK; ++r)
             *reinterpret_cast<float4 *>(G::slot(recs, tid + r * SCAN_THREADS)) = make_float4(x[r], P[r], Q[r], 0.0f);
     }
-    template <bool FULL>
-    __device__ static __forceinline__ Elem pass1(const Args &a, const unsigned char *rec, int cnt, int64_t q0) {
-        Elem g = smo1_identity();
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t q0,
+                                                 Elem &g) {
+        const int64_t klast = npad(a) - 1 - q0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 const float4 v = *reinterpret_cast<const float4 *>(rec + i * 16);
                 Elem e;
-                if (q0 + i == 0 && a.is_last_shard) {
+                if (klast - i == a.n - 1 && a.is_last_shard) {
                     e = smo1_from_state(State1{(double)v.x, (double)v.y});
                 } else {
                     double pp, J;
@@ -562,42 +639,44 @@ struct Bwd1 {
                 g = smo1_combine(g, e);
             }
         }
-        return g;
     }
-    template <bool FULL>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int cnt, int64_t q0,
-                                                 const State &st, double &, double &) {
-        double cx = r32(st.x), cP = r32(st.P);
+    __device__ static __forceinline__ Carry begin2(const Args &, const State &st) { return Carry{r32(st.x), r32(st.P)}; }
+    template <bool FULLC>
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
+                                                 Carry &c, double &, double &) {
+        const int64_t klast = npad(a) - 1 - q0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
-            if (FULL || i < cnt) {
+            if (FULLC || (i >= lo && i < hi)) {
                 unsigned char *b = rec + i * 16;
                 const float4 v = *reinterpret_cast<const float4 *>(b);
-                if (q0 + i == 0 && a.is_last_shard) {
-                    cx = (double)v.x;
-                    cP = (double)v.y;
+                if (klast - i == a.n - 1 && a.is_last_shard) {
+                    c.x = (double)v.x;
+                    c.P = (double)v.y;
                 } else {
                     const double xf = (double)v.x, pf = (double)v.y;
                     double pp, J;
                     rts1_gain(pf, (double)v.z, pp, J);
-                    const double xsv = xf + J * (cx - xf);
-                    const double dP = cP - pp;
+                    const double xsv = xf + J * (c.x - xf);
+                    const double dP = c.P - pp;
                     double ps = pf + (J * J * dP);
                     if (ps < 0.0) ps = 0.0;
                     const float xs32 = (float)xsv, ps32 = (float)ps;
                     *reinterpret_cast<float4 *>(b) = make_float4(xs32, ps32, (float)(pf + (J * dP)), 0.0f);
-                    cx = (double)xs32;
-                    cP = (double)ps32;
+                    c.x = (double)xs32;
+                    c.P = (double)ps32;
                 }
             }
         }
     }
-    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int tid) {
+    __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
+                                                     int tid) {
+        const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
             const int g = tid + r * SCAN_THREADS;
-            const int64_t k = a.n - 1 - (p0 + g);
-            if (k >= 0) {
+            const int64_t k = np - 1 - stage_pos(p0, L, s, g);
+            if (k >= 0 && k < a.n) {
                 const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
                 a.xs[k] = o.x;
                 a.Ps[k] = o.y;
@@ -608,7 +687,7 @@ struct Bwd1 {
 };
 
 // =====================================================================================
-// decoupled look-back (warp 0 of the CTA)
+// decoupled look-back (one warp of the CTA)
 // =====================================================================================
 template <class Tr>
 __device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWorkspace &ws, int tile, int lane) {
@@ -621,7 +700,12 @@ __device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWor
         const int idx = base - lane;
         int f;
         while (true) {
-            f = (idx >= 0) ? ld_acquire(ws.flags + idx) : 2;
+            f = 2;
+            if (idx >= 0) {
+                // flags carry the launch epoch: values left by earlier launches read as "nothing"
+                const int v = ld_acquire(ws.flags + idx) - ws.epoch4;
+                f = (v == 1 || v == 2) ? v : 0;
+            }
             // the window is usable as soon as every tile up to the nearest published prefix has
             // at least its aggregate out; tiles beyond that prefix do not matter
             const unsigned pm = __ballot_sync(FULL, f == 2);
@@ -677,7 +761,7 @@ struct ScanSmem {
 
 template <class Tr, bool AGG_ONLY>
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles) {
+scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles, const int nsub) {
     using Elem = typename Tr::Elem;
     using State = typename Tr::State;
     using SM = ScanSmem<Tr>;
@@ -690,17 +774,29 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
     if (tid == 0) s_tile[0] = AGG_ONLY ? (int)blockIdx.x : atomicAdd(ws.counters, 1);
     __syncthreads();
     const int tile = s_tile[0];
-    const int64_t p0 = (int64_t)tile * TILE_BINS;
-    const int64_t q0 = p0 + (int64_t)tid * CHUNK;
-
-    Tr::stage_in(a, recs, p0, tid);
-    __syncthreads();
-
-    int64_t rem = a.n - q0;
-    const int cnt = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
+    const int L = CHUNK * nsub;
+    const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
+    const int64_t run0 = p0 + (int64_t)tid * L;
     unsigned char *myrec = recs + tid * Tr::G::REC_BYTES;
-    const Elem mine = (cnt == CHUNK) ? Tr::template pass1<true>(a, myrec, cnt, q0)
-                                     : Tr::template pass1<false>(a, myrec, cnt, q0);
+    const bool single = nsub == 1;  // the records staged for pass 1 are kept for pass 2
+
+    // ---- pass 1: every thread composes the element of its run ----
+    Elem mine = Tr::identity();
+    for (int s = 0; s < nsub; ++s) {
+        if (s) __syncthreads();  // the previous sub-step's records are still being read
+        if (single)
+            Tr::template stage_in<true>(a, recs, p0, L, s, tid);
+        else
+            Tr::template stage_in<false>(a, recs, p0, L, s, tid);
+        __syncthreads();
+        const int64_t q0 = run0 + s * CHUNK;
+        int lo, hi;
+        Tr::bounds(a, q0, lo, hi);
+        if (lo == 0 && hi == CHUNK)
+            Tr::template pass1<true>(a, myrec, lo, hi, q0, mine);
+        else if (hi > lo)
+            Tr::template pass1<false>(a, myrec, lo, hi, q0, mine);
+    }
 
     // inclusive Kogge-Stone scan across the warp
     Elem inc = mine;
@@ -712,7 +808,9 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
     if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
     __syncthreads();
 
-    if (warp == 0) {
+    // the serial section (cross-warp prefix, look-back, publication) rotates over the warps so
+    // that it does not always land on the same SM sub-partition
+    if (warp == (tile & (NWARPS - 1))) {
         // exclusive prefixes across warps and the tile aggregate (all lanes redundantly)
         Elem run = load_elem<Elem>(sd + SM::OFF_WAGG);
         if (lane == 0) store_elem(sd + SM::OFF_WEXCL, Tr::identity());
@@ -735,7 +833,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
                     __threadfence();
                 }
                 __syncwarp();
-                if (lane == 0) st_release(ws.flags + tile, 1);
+                if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 1);
                 pref = lookback<Tr>(a, ws, tile, lane);
             }
             const State incl = Tr::apply(run, pref);
@@ -749,7 +847,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
                 __threadfence();
             }
             __syncwarp();
-            if (lane == 0) st_release(ws.flags + tile, 2);
+            if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 2);
         }
     }
     if (AGG_ONLY) return;
@@ -762,11 +860,25 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
     State start = wst;
     if (lane > 0) start = Tr::apply(lex, wst);
 
+    // ---- pass 2: replay the reference's recursion over the run from its exact start state ----
+    typename Tr::Carry carry = Tr::begin2(a, start);
     double acc0 = 0.0, acc1 = 0.0;
-    if (cnt == CHUNK)
-        Tr::template pass2<true>(a, myrec, cnt, q0, start, acc0, acc1);
-    else
-        Tr::template pass2<false>(a, myrec, cnt, q0, start, acc0, acc1);
+    for (int s = 0; s < nsub; ++s) {
+        if (!single) {
+            if (s) __syncthreads();  // the previous sub-step's outputs are still being stored
+            Tr::template stage_in<true>(a, recs, p0, L, s, tid);
+            __syncthreads();
+        }
+        const int64_t q0 = run0 + s * CHUNK;
+        int lo, hi;
+        Tr::bounds(a, q0, lo, hi);
+        if (lo == 0 && hi == CHUNK)
+            Tr::template pass2<true>(a, myrec, lo, hi, q0, carry, acc0, acc1);
+        else if (hi > lo)
+            Tr::template pass2<false>(a, myrec, lo, hi, q0, carry, acc0, acc1);
+        __syncthreads();
+        Tr::stage_out(a, recs, p0, L, s, tid);
+    }
 
     if (Tr::HAS_SUMS) {
 #pragma unroll
@@ -778,12 +890,10 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
             sd[SM::OFF_RED + warp * 2] = acc0;
             sd[SM::OFF_RED + warp * 2 + 1] = acc1;
         }
+        __syncthreads();
     }
-    __syncthreads();
-    Tr::stage_out(a, recs, p0, tid);
-
-    if (Tr::HAS_SUMS) {
-        if (tid == 0) {
+    if (tid == 0) {
+        if (Tr::HAS_SUMS) {
             double t0 = 0.0, t1 = 0.0;
 #pragma unroll
             for (int w = 0; w < NWARPS; ++w) {
@@ -793,10 +903,18 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles)
             ws.partials[(int64_t)tile * 2] = t0;
             ws.partials[(int64_t)tile * 2 + 1] = t1;
             __threadfence();
-            const int done = atomicAdd(ws.counters + 1, 1);
-            __threadfence();
-            s_tile[1] = (done == ntiles - 1) ? 1 : 0;
         }
+        const int done = atomicAdd(ws.counters + 1, 1);
+        const int last = (done == ntiles - 1) ? 1 : 0;
+        if (last) {
+            // every tile has taken its ticket and finished: leave the counters ready for the next launch
+            ws.counters[0] = 0;
+            ws.counters[1] = 0;
+            __threadfence();
+        }
+        s_tile[1] = last;
+    }
+    if (Tr::HAS_SUMS) {
         __syncthreads();
         if (s_tile[1] && warp == 0) {
             // the last CTA to finish adds the per-tile partial sums in tile order
@@ -941,16 +1059,11 @@ __global__ void kappa1_kernel(double q0inv, int64_t n, const float *__restrict__
 }
 
 template <class Tr, bool AGG_ONLY>
-cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int64_t n, cudaStream_t st,
-                        int *launches) {
-    const int ntiles = (int)scan_num_tiles(n);
+cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int64_t positions, int nsub,
+                        cudaStream_t st, int *launches) {
+    const int ntiles = (int)scan_num_tiles(positions, nsub);
     if (ntiles <= 0) return cudaSuccess;
-    if (!AGG_ONLY) {
-        // flags [ntiles] and counters [2] are contiguous
-        cudaError_t e = cudaMemsetAsync(ws.flags, 0, sizeof(int32_t) * ((size_t)ntiles + 2), st);
-        if (e != cudaSuccess) return e;
-    }
-    scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles);
+    scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -971,23 +1084,43 @@ cudaError_t set_smem_attr() {
                                 ScanSmem<Tr>::BYTES);
 }
 
+// resident CTAs of the scan kernels on the current device (tiles in flight)
+template <class Tr>
+int scan_slots() {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_kernel<Tr, false>, SCAN_THREADS,
+                                                      ScanSmem<Tr>::BYTES) != cudaSuccess)
+        return 0;
+    return per_sm * sms;
+}
+
+bool canonical_F(const Model2 &M) { return M.F00 == 1.0 && M.F10 == 0.0 && M.F11 == 1.0; }
+
 }  // namespace
 
 // =====================================================================================
 // host-side launchers
 // =====================================================================================
-int64_t scan_num_tiles(int64_t n) { return (n + TILE_BINS - 1) / TILE_BINS; }
+int64_t scan_num_tiles(int64_t positions, int nsub) {
+    const int64_t tb = (int64_t)TILE_BINS * nsub;
+    return (positions + tb - 1) / tb;
+}
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// workspace for the finest tiling (nsub = 1) of n + CHUNK positions (the reverse scans pad n)
+static size_t ws_tiles(int64_t n) { return (size_t)scan_num_tiles(n + CHUNK, 1) + 1; }
+
 size_t scan_workspace_bytes(int64_t n) {
-    const size_t t = (size_t)scan_num_tiles(n) + 1;
+    const size_t t = ws_tiles(n);
     return align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
            align_up((t + 2) * 4, 256);
 }
 
 ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
-    const size_t t = (size_t)scan_num_tiles(n) + 1;
+    const size_t t = ws_tiles(n);
     unsigned char *p = static_cast<unsigned char *>(base);
     ScanWorkspace ws;
     ws.tile_agg = reinterpret_cast<double *>(p);
@@ -997,17 +1130,51 @@ ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
     ws.partials = reinterpret_cast<double *>(p);
     p += align_up(t * 2 * 8, 256);
     ws.flags = reinterpret_cast<int32_t *>(p);
-    ws.counters = ws.flags + scan_num_tiles(n);  // contiguous with flags: one memset clears both
+    ws.counters = ws.flags + t;  // contiguous with flags: one memset clears both
     return ws;
 }
 
+static int g_slots[4] = {0, 0, 0, 0};  // Fwd2, Fwd1, Bwd2, Bwd1 tiles in flight
+static int g_nsub_override = 0;
+
 cudaError_t configure_kernels() {
     cudaError_t e;
-    if ((e = set_smem_attr<Fwd2>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Fwd2<true>>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Fwd2<false>>()) != cudaSuccess) return e;
     if ((e = set_smem_attr<Fwd1>()) != cudaSuccess) return e;
-    if ((e = set_smem_attr<Bwd2>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Bwd2<true>>()) != cudaSuccess) return e;
+    if ((e = set_smem_attr<Bwd2<false>>()) != cudaSuccess) return e;
     if ((e = set_smem_attr<Bwd1>()) != cudaSuccess) return e;
+    g_slots[0] = scan_slots<Fwd2<true>>();
+    g_slots[1] = scan_slots<Fwd1>();
+    g_slots[2] = scan_slots<Bwd2<true>>();
+    g_slots[3] = scan_slots<Bwd1>();
+    const char *ov = getenv("CB200_SCAN_NSUB");
+    if (ov) g_nsub_override = atoi(ov);
     return cudaSuccess;
+}
+
+void scan_set_nsub_override(int nsub) { g_nsub_override = nsub < 0 ? 0 : nsub; }
+
+// Sub-steps per run.  Longer runs amortise the warp scan and the look-back; the choice also
+// has to keep the last wave of tiles reasonably full.  which: 0 Fwd2, 1 Fwd1, 2 Bwd2, 3 Bwd1.
+int scan_pick_nsub(int64_t positions, int which) {
+    if (g_nsub_override > 0) return g_nsub_override > MAX_NSUB ? MAX_NSUB : g_nsub_override;
+    const int slots = g_slots[which] > 0 ? g_slots[which] : 444;
+    int best = 1;
+    double best_score = -1.0;
+    for (int ns = 1; ns <= MAX_NSUB; ++ns) {
+        const int64_t tiles = scan_num_tiles(positions, ns);
+        const int64_t waves = (tiles + slots - 1) / slots;
+        const double fill = (double)tiles / (double)(waves * slots);  // occupancy of the tile slots
+        // per-position overhead of the scan stages shrinks as 1 / ns
+        const double score = fill / (1.0 + 0.9 / ns);
+        if (score > best_score + 1e-9) {
+            best_score = score;
+            best = ns;
+        }
+    }
+    return best;
 }
 
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
@@ -1028,20 +1195,33 @@ cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t
 
 cudaError_t launch_forward(int dim, const FwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
                            cudaStream_t st, int *launches) {
-    if (dim == 2)
-        return aggregate_only ? launch_scan<Fwd2, true>(a, ws, a.n, st, launches)
-                              : launch_scan<Fwd2, false>(a, ws, a.n, st, launches);
-    return aggregate_only ? launch_scan<Fwd1, true>(a, ws, a.n, st, launches)
-                          : launch_scan<Fwd1, false>(a, ws, a.n, st, launches);
+    if (dim == 2) {
+        const int ns = scan_pick_nsub(a.n, 0);
+        if (canonical_F(a.M))
+            return aggregate_only ? launch_scan<Fwd2<true>, true>(a, ws, a.n, ns, st, launches)
+                                  : launch_scan<Fwd2<true>, false>(a, ws, a.n, ns, st, launches);
+        return aggregate_only ? launch_scan<Fwd2<false>, true>(a, ws, a.n, ns, st, launches)
+                              : launch_scan<Fwd2<false>, false>(a, ws, a.n, ns, st, launches);
+    }
+    const int ns = scan_pick_nsub(a.n, 1);
+    return aggregate_only ? launch_scan<Fwd1, true>(a, ws, a.n, ns, st, launches)
+                          : launch_scan<Fwd1, false>(a, ws, a.n, ns, st, launches);
 }
 
 cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
                             cudaStream_t st, int *launches) {
-    if (dim == 2)
-        return aggregate_only ? launch_scan<Bwd2, true>(a, ws, a.n, st, launches)
-                              : launch_scan<Bwd2, false>(a, ws, a.n, st, launches);
-    return aggregate_only ? launch_scan<Bwd1, true>(a, ws, a.n, st, launches)
-                          : launch_scan<Bwd1, false>(a, ws, a.n, st, launches);
+    const int64_t positions = (a.n + CHUNK - 1) / CHUNK * CHUNK;
+    if (dim == 2) {
+        const int ns = scan_pick_nsub(positions, 2);
+        if (canonical_F(a.M))
+            return aggregate_only ? launch_scan<Bwd2<true>, true>(a, ws, positions, ns, st, launches)
+                                  : launch_scan<Bwd2<true>, false>(a, ws, positions, ns, st, launches);
+        return aggregate_only ? launch_scan<Bwd2<false>, true>(a, ws, positions, ns, st, launches)
+                              : launch_scan<Bwd2<false>, false>(a, ws, positions, ns, st, launches);
+    }
+    const int ns = scan_pick_nsub(positions, 3);
+    return aggregate_only ? launch_scan<Bwd1, true>(a, ws, positions, ns, st, launches)
+                          : launch_scan<Bwd1, false>(a, ws, positions, ns, st, launches);
 }
 
 cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
@@ -1080,7 +1260,7 @@ cudaError_t launch_update_kappa(int dim, const Model2 &M, int64_t n, const float
 cudaError_t launch_forward_shard_prefix(int dim, const double *aggs, int rank, double state_init,
                                         double cov_init, double *init_state, cudaStream_t st) {
     if (dim == 2)
-        forward_shard_prefix_kernel<Fwd2><<<1, 1, 0, st>>>(aggs, rank, state_init, cov_init, init_state);
+        forward_shard_prefix_kernel<Fwd2<false>><<<1, 1, 0, st>>>(aggs, rank, state_init, cov_init, init_state);
     else
         forward_shard_prefix_kernel<Fwd1><<<1, 1, 0, st>>>(aggs, rank, state_init, cov_init, init_state);
     return cudaGetLastError();
@@ -1089,7 +1269,7 @@ cudaError_t launch_forward_shard_prefix(int dim, const double *aggs, int rank, d
 cudaError_t launch_backward_shard_prefix(int dim, const double *aggs, int rank, int n_shards,
                                          double *tail_state, cudaStream_t st) {
     if (dim == 2)
-        backward_shard_prefix_kernel<Bwd2><<<1, 1, 0, st>>>(aggs, rank, n_shards, tail_state);
+        backward_shard_prefix_kernel<Bwd2<false>><<<1, 1, 0, st>>>(aggs, rank, n_shards, tail_state);
     else
         backward_shard_prefix_kernel<Bwd1><<<1, 1, 0, st>>>(aggs, rank, n_shards, tail_state);
     return cudaGetLastError();

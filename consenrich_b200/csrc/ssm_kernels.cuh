@@ -8,20 +8,22 @@
 
 namespace cb200 {
 
-// Geometry of the look-back scans: every thread owns CHUNK consecutive bins, a tile is
-// SCAN_THREADS * CHUNK bins.
+// Geometry of the look-back scans: every thread owns a run of CHUNK * nsub consecutive scan
+// positions, processed in nsub sub-steps of CHUNK; a tile is SCAN_THREADS runs.
 constexpr int SCAN_THREADS = 128;
 constexpr int CHUNK = 8;
-constexpr int TILE_BINS = SCAN_THREADS * CHUNK;
+constexpr int TILE_BINS = SCAN_THREADS * CHUNK;  // positions per tile per sub-step
+constexpr int MAX_NSUB = 8;
 constexpr int AGG_PITCH = 16;   // doubles per published tile aggregate (14 used)
 constexpr int PREF_PITCH = 8;   // doubles per published tile prefix state (5 used)
 
-struct ScanWorkspace {    // sized by scan_workspace_bytes(n); zeroed flags/counters per launch
+struct ScanWorkspace {    // sized by scan_workspace_bytes(n); zeroed once when allocated
     double *tile_agg;     // [ntiles][AGG_PITCH]
     double *tile_pref;    // [ntiles][PREF_PITCH]
     double *partials;     // [ntiles][2]
-    int32_t *flags;       // [ntiles]  0 = nothing, 1 = aggregate published, 2 = prefix published
-    int32_t *counters;    // [0] dynamic tile ticket, [1] tiles finished
+    int32_t *flags;       // [ntiles]  epoch4 + 1 = aggregate published, epoch4 + 2 = prefix published
+    int32_t *counters;    // [0] dynamic tile ticket, [1] tiles finished (reset by the last tile)
+    int32_t epoch4;       // 4 * launch epoch: flags of earlier launches read as "nothing"
 };
 
 struct FwdArgs {
@@ -29,6 +31,8 @@ struct FwdArgs {
     const float *lam, *kap, *qs;
     const double *init_state;  // device, or nullptr -> model prior
     float *xf, *Pf, *Qf, *D;
+    float *q_head;             // device float[d*d] or nullptr: Q of this shard's first bin (row n-1 of
+                               // the preceding shard's pNoiseForward)
     double *sums;              // device double[2] or nullptr
     double *agg_out;           // aggregate-only mode: shard aggregate destination
     int64_t n;
@@ -51,7 +55,9 @@ struct BwdArgs {
 
 size_t scan_workspace_bytes(int64_t n);
 ScanWorkspace scan_workspace_carve(void *base, int64_t n);
-int64_t scan_num_tiles(int64_t n);
+int64_t scan_num_tiles(int64_t positions, int nsub);
+int scan_pick_nsub(int64_t positions, int which);
+void scan_set_nsub_override(int nsub);
 
 // every launcher returns the cudaError_t of the launch (cudaGetLastError)
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,

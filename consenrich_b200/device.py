@@ -50,7 +50,9 @@ class TrackSweep:
             raise _lib.CudaError("TrackSweep needs a CUDA device; consenrich_b200 has no CPU path")
         self.m, self.n, self.d = int(m), int(n), int(state_dim)
         self.dev = torch.device("cuda", device)
-        self.ctx = ctx or _lib.Context(device, torch.cuda.current_stream(self.dev).cuda_stream)
+        # kernels are enqueued on torch's CURRENT stream; the legacy default stream has handle 0, which
+        # the C ABI reads as "make your own stream", so it is passed as the per-thread alias instead
+        self.ctx = ctx or _lib.Context(device, self._stream_handle(torch.cuda.current_stream(self.dev)))
         self.stride = (self.n + 31) // 32 * 32
         f32, f64 = torch.float32, torch.float64
         n, d = self.n, self.d
@@ -65,8 +67,13 @@ class TrackSweep:
         self.resid = torch.empty((n, self.m), dtype=f32, device=self.dev) if residuals else None
         self.sums = torch.zeros(2, dtype=f64, device=self.dev)
 
+    @staticmethod
+    def _stream_handle(stream) -> int:
+        h = int(stream.cuda_stream)
+        return h if h != 0 else 1  # cudaStreamLegacy == (cudaStream_t)0x1
+
     def bind_current_stream(self):
-        self.ctx.set_stream(_torch().cuda.current_stream(self.dev).cuda_stream)
+        self.ctx.set_stream(self._stream_handle(_torch().cuda.current_stream(self.dev)))
 
     # individual stages (all asynchronous on the context's stream)
     def fold(self, data, munc, ld, pad):

@@ -112,6 +112,10 @@ CB200_API int64_t cb200_ctx_launch_count(const cb200_ctx *ctx);
 CB200_API int cb200_ctx_enable_timing(cb200_ctx *ctx, int on);
 CB200_API int cb200_ctx_kernel_ms(cb200_ctx *ctx, int family, double *ms, int64_t *launches);
 CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
+/* Tuning knob (process-wide): sub-steps of 8 bins each thread of the scan kernels runs through
+ * (1..8), 0 = choose per launch from the track length and the resident tile slots.  Results do not
+ * depend on it beyond float64 re-association.  Also settable with CB200_SCAN_NSUB. */
+CB200_API int cb200_set_scan_substeps(int nsub);
 
 /* ---- memory helpers (so that hosts without torch can stage tracks) -------------------- */
 CB200_API int cb200_device_alloc(cb200_ctx *ctx, size_t bytes, void **dptr);

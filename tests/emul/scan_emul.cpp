@@ -53,6 +53,7 @@ struct emul_params {
     double lam_min, lam_max, kap_min, kap_max;
     int32_t use_lambda, use_kappa, use_qscale, return_nll, store_nll_in_d, do_store;
     int32_t chunk, tile_chunks;  // bins per thread, threads per tile
+    int32_t canon, pad_;         // use the F = [[1, f], [0, 1]] specialisations
     uint64_t seed;               // randomises the look-back window lengths
 };
 
@@ -80,7 +81,10 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
         Filt2 g = filt2_identity();
         for (int64_t k = c * L; k < n && k < (c + 1) * L; ++k) {
             double qk = qk_of(k), l = lam_of(k);
-            filt2_step(g, M, qk * M.q00, qk * M.q01, qk * M.q11, l * S0[k], l * S1[k]);
+            if (p->canon)
+                filt2_step<true>(g, M, qk * M.q00, qk * M.q01, qk * M.q11, l * S0[k], l * S1[k]);
+            else
+                filt2_step<false>(g, M, qk * M.q00, qk * M.q01, qk * M.q11, l * S0[k], l * S1[k]);
         }
         agg[c] = g;
     }
@@ -124,8 +128,12 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
         nll_acc_init(acc);
         for (int64_t k = c * L; k < n && k < (c + 1) * L; ++k) {
             BinOut o;
-            kf2_step(s, M, qk_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, 1.0 / (double)m, mlog2pi,
-                     p->return_nll != 0, p->store_nll_in_d != 0, o, acc);
+            if (p->canon)
+                kf2_step<true>(s, M, qk_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, 1.0 / (double)m,
+                               mlog2pi, p->return_nll != 0, p->store_nll_in_d != 0, o, acc);
+            else
+                kf2_step<false>(s, M, qk_of(k), lam_of(k), S0[k], S1[k], S2[k], SL[k], (double)m, 1.0 / (double)m,
+                                mlog2pi, p->return_nll != 0, p->store_nll_in_d != 0, o, acc);
             D[k] = (float)o.stat;
             *sum_d += (double)D[k];
             *sum_nll += o.nll;
@@ -222,8 +230,10 @@ void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf
     const int64_t nchunks = (n + L - 1) / L, ntiles = (nchunks + T - 1) / T;
     auto elem_of = [&](int64_t k) {
         if (k == n - 1) return smo2_from_state(State2{xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3]});
-        Rts2 r = rts2_gain(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2], Pf[k * 4 + 3],
-                           Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3]);
+        Rts2 r = p->canon ? rts2_gain<true>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
+                                            Pf[k * 4 + 3], Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3])
+                          : rts2_gain<false>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
+                                             Pf[k * 4 + 3], Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3]);
         return smo2_from_rts(r, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3]);
     };
     std::vector<Smo2> agg(nchunks);
@@ -265,8 +275,10 @@ void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf
                 cy = Rs2{xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2], Pf[k * 4 + 3]};
                 continue;
             }
-            Rts2 r = rts2_gain(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2], Pf[k * 4 + 3],
-                               Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3]);
+            Rts2 r = p->canon ? rts2_gain<true>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
+                                                Pf[k * 4 + 3], Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3])
+                              : rts2_gain<false>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
+                                                 Pf[k * 4 + 3], Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3]);
             Smo2Out o;
             rts2_step(cy, r, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3], o);
             xs[k * 2] = (float)o.xs0; xs[k * 2 + 1] = (float)o.xs1;

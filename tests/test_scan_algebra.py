@@ -28,7 +28,7 @@ class _P(C.Structure):
                 ("kap_min", C.c_double), ("kap_max", C.c_double), ("use_lambda", C.c_int32),
                 ("use_kappa", C.c_int32), ("use_qscale", C.c_int32), ("return_nll", C.c_int32),
                 ("store_nll_in_d", C.c_int32), ("do_store", C.c_int32), ("chunk", C.c_int32),
-                ("tile_chunks", C.c_int32), ("seed", C.c_uint64)]
+                ("tile_chunks", C.c_int32), ("canon", C.c_int32), ("pad_", C.c_int32), ("seed", C.c_uint64)]
 
 
 @pytest.fixture(scope="module")
@@ -54,7 +54,7 @@ def _fold(emul, data, munc, pad):
     return S
 
 
-def _params(Q0, state_init, chunk, tile_chunks, seed, lam, kap, qs, bounds, return_nll, nll_in_d):
+def _params(Q0, state_init, chunk, tile_chunks, seed, lam, kap, qs, bounds, return_nll, nll_in_d, canon=0):
     p = _P()
     p.F[:] = [1.0, 1.0, 0.0, 1.0]
     p.Q0[:] = [float(Q0[0, 0]), float(Q0[0, 1]), float(Q0[1, 0]), float(Q0[1, 1])]
@@ -63,24 +63,27 @@ def _params(Q0, state_init, chunk, tile_chunks, seed, lam, kap, qs, bounds, retu
     p.use_lambda, p.use_kappa, p.use_qscale = int(lam is not None), int(kap is not None), int(qs is not None)
     p.return_nll, p.store_nll_in_d, p.do_store = int(return_nll), int(nll_in_d), 1
     p.chunk, p.tile_chunks, p.seed = chunk, tile_chunks, seed
+    p.canon = int(canon)
     return p
 
 
 CASES = [
-    # m, n, masked, weights, chunk, tile_chunks
-    (3, 257, 0.0, False, 4, 8),
-    (10, 5000, 0.05, True, 8, 32),
-    (5, 1, 0.0, False, 8, 32),
-    (5, 2, 0.0, True, 8, 32),
-    (25, 3001, 0.3, True, 16, 4),
-    (2, 20000, 0.0, True, 8, 128),
+    # m, n, masked, weights, chunk (bins per thread run), tile_chunks (runs per tile), canonical-F code path
+    (3, 257, 0.0, False, 4, 8, 0),
+    (10, 5000, 0.05, True, 8, 32, 1),
+    (5, 1, 0.0, False, 8, 32, 1),
+    (5, 2, 0.0, True, 8, 32, 0),
+    (25, 3001, 0.3, True, 16, 4, 1),
+    (2, 20000, 0.0, True, 8, 128, 0),
+    (10, 40000, 0.02, True, 32, 128, 1),   # long runs: 4 sub-steps of 8 per thread
+    (4, 70000, 0.0, True, 64, 128, 1),     # 8 sub-steps
 ]
 
 
 @pytest.mark.parametrize("dim", [2, 1])
 @pytest.mark.parametrize("case", CASES)
 def test_emulated_scan_matches_oracle(oracle, emul, dim, case):
-    m, n, masked, weights, chunk, tile_chunks = case
+    m, n, masked, weights, chunk, tile_chunks, canon = case
     data, munc = synth_tracks(1000 + n, m, n, masked_frac=masked)
     rng = np.random.default_rng(n)
     Q0 = np.array([[2e-3, 0.0], [0.0, 1e-4]], np.float32)
@@ -109,7 +112,7 @@ def test_emulated_scan_matches_oracle(oracle, emul, dim, case):
         b = oracle.cbackwardPassLevel(matrixData=data, stateForward=want["xf"], stateCovarForward=want["Pf"],
                                       pNoiseForward=want["Qf"])
     S = _fold(emul, data, munc, 1e-4)
-    p = _params(Q0, 0.25, chunk, tile_chunks, 12345 + n, lam, kap, qs, bounds, True, False)
+    p = _params(Q0, 0.25, chunk, tile_chunks, 12345 + n, lam, kap, qs, bounds, True, False, canon)
     got = dict(xf=np.empty((n, dim), np.float32), Pf=np.empty((n, dim, dim), np.float32),
                Qf=np.zeros((n, dim, dim), np.float32), D=np.empty(n, np.float32))
     sd, snll = C.c_double(), C.c_double()
