@@ -202,8 +202,8 @@ int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 int do_fold(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
             double *stats, int64_t stride) {
     Span sp(c, FAM_FOLD);
-    CU_TRY(launch_fold(data, munc, m, n, ld, pad, stats, stats + stride, stats + 2 * stride, stats + 3 * stride,
-                       c->stream));
+    CU_TRY(launch_fold(data, munc, m, n, ld, pad, reinterpret_cast<double2 *>(stats),
+                       reinterpret_cast<double2 *>(stats + 2 * stride), c->stream));
     c->launches += 1;
     return CB200_OK;
 }
@@ -222,7 +222,8 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     ScanWorkspace ws;
     CB_TRY(next_scan_ws(c, n, &ws));
     FwdArgs a{};
-    a.S0 = stats; a.S1 = stats + stride; a.S2 = stats + 2 * stride; a.SL = stats + 3 * stride;
+    a.SA = reinterpret_cast<const double2 *>(stats);
+    a.SB = reinterpret_cast<const double2 *>(stats + 2 * stride);
     a.lam = lam; a.kap = kap; a.qs = qs;
     a.init_state = init_state;
     a.xf = xf; a.Pf = Pf; a.Qf = Qf; a.D = D;
@@ -586,7 +587,8 @@ int cb200_update_lambda(cb200_ctx *c, const cb200_model *mo, const double *stats
     if (!c || !stats || !xs || !Ps || !lam) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     Span sp(c, FAM_PREC);
-    CU_TRY(launch_update_lambda(stats, stats + stat_stride, stats + 2 * stat_stride, n, (double)m, xs, Ps,
+    CU_TRY(launch_update_lambda(reinterpret_cast<const double2 *>(stats),
+                                reinterpret_cast<const double2 *>(stats + 2 * stat_stride), n, (double)m, xs, Ps,
                                 mo->state_dim, nu, mo->lam_min, mo->lam_max, lam, c->stream));
     c->launches += 1;
     return CB200_OK;
@@ -680,8 +682,9 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
             CB_TRY(sweep());
             if (lam) {
                 Span sp(c, FAM_PREC);
-                CU_TRY(launch_update_lambda(stats, stats + stride, stats + 2 * stride, n, (double)m, xs, Ps, d, op->nu,
-                                            mo.lam_min, mo.lam_max, lam, c->stream));
+                CU_TRY(launch_update_lambda(reinterpret_cast<const double2 *>(stats),
+                                            reinterpret_cast<const double2 *>(stats + 2 * stride), n, (double)m, xs, Ps,
+                                            d, op->nu, mo.lam_min, mo.lam_max, lam, c->stream));
                 c->launches += 1;
             }
             if (kap) {

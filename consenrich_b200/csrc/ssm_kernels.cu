@@ -126,8 +126,7 @@ constexpr int FOLD_UNROLL = 4;
 template <int VEC>
 __global__ void __launch_bounds__(FOLD_THREADS)
 fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int64_t m, int64_t n, int64_t ld,
-            double pad, double *__restrict__ S0, double *__restrict__ S1, double *__restrict__ S2,
-            double *__restrict__ SL) {
+            double pad, double2 *__restrict__ SA, double2 *__restrict__ SB) {
     const int64_t k0 = ((int64_t)blockIdx.x * FOLD_THREADS + threadIdx.x) * VEC;
     if (k0 >= n) return;
     FoldAcc acc[VEC];
@@ -193,10 +192,8 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
     for (int c = 0; c < VEC; ++c) {
         const int64_t k = k0 + c;
         if (k < n) {
-            S0[k] = acc[c].s0;
-            S1[k] = acc[c].s1;
-            S2[k] = acc[c].s2;
-            SL[k] = fold_logsum(acc[c]);
+            SA[k] = make_double2(acc[c].s0, acc[c].s1);
+            SB[k] = make_double2(acc[c].s2, fold_logsum(acc[c]));
         }
     }
 }
@@ -205,16 +202,18 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
 // scan traits
 // =====================================================================================
 // Geometry.  A tile is SCAN_THREADS runs of L = CHUNK * nsub consecutive scan positions, one
-// run per thread.  A run is processed in nsub sub-steps of CHUNK positions; for each sub-step
-// the CTA stages the 128 x CHUNK records of all its threads through shared memory so that
-// global traffic stays coalesced (groups of CHUNK consecutive bins = whole 32-byte sectors).
-// Long runs amortise the warp scan, the cross-warp prefix and the look-back over L positions.
+// run per thread.  A run is processed in nsub sub-steps of CHUNK positions.  For each sub-step
+// the CTA stages the SCAN_THREADS x CHUNK records of all its threads in shared memory with
+// cp.async (LDGSTS: no registers, groups of CHUNK consecutive bins = whole sectors), double
+// buffered so that the copies of sub-step s+1 fly while sub-step s is computed.  Long runs
+// amortise the warp scan, the cross-warp prefix and the look-back over L positions.
 //
 // Shared-memory record of one thread: CHUNK bins of BIN_BYTES plus 16 bytes of padding so that
-// 16-byte accesses of a quarter warp fall in distinct banks (record stride = 4 mod 8 words).
+// 16-byte accesses of a quarter warp fall in distinct banks.
 template <int BIN_BYTES>
 struct RecGeom {
     static constexpr int REC_BYTES = CHUNK * BIN_BYTES + 16;
+    static constexpr int BUF_BYTES = SCAN_THREADS * REC_BYTES;
     __device__ static __forceinline__ unsigned char *slot(unsigned char *recs, int g) {
         return recs + (g / CHUNK) * REC_BYTES + (g % CHUNK) * BIN_BYTES;
     }
@@ -222,13 +221,60 @@ struct RecGeom {
 
 // scan position of staged record g (thread g / CHUNK, slot g % CHUNK) in sub-step s
 __device__ __forceinline__ int64_t stage_pos(int64_t p0, int L, int s, int g) {
-    return p0 + (int64_t)(g / CHUNK) * L + s * CHUNK + (g % CHUNK);
+    return p0 + (int64_t)((g / CHUNK) * L + s * CHUNK + (g % CHUNK));
 }
 
+// cp.async of BYTES (4, 8 or 16) bytes; !ok zero-fills the destination without touching src
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *dst_smem, const void *src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    const int sz = ok ? BYTES : 0;
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+    else if (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // ---- forward, 2-state ------------------------------------------------------------------
-// record per bin, in : [S0 S1][S2 SL][qk(f64) lam(f32) pad]        (48 bytes)
+// record per bin, in : [S0 S1][S2 SL][kappa qscale lambda (f32) pad]      (48 bytes, raw copies)
 //                 out: [Pf 4xf32][Qf 4xf32][xf 2xf32, D f32, pad]
 // scan position = bin index k.
+struct FwdRaw {
+    double qk, lam;
+};
+
+// qk = qScale / clamp(kappa), lam = clamp(lambda) from the raw float triple of a record
+__device__ __forceinline__ FwdRaw fwd_raw(const FwdArgs &a, const unsigned char *bin) {
+    const float4 w = *reinterpret_cast<const float4 *>(bin + 32);
+    FwdRaw r;
+    const double qs = a.use_qscale ? (double)w.y : 1.0;
+    r.qk = a.use_kappa ? cb_div(qs, clampd((double)w.x, a.kap_min, a.kap_max)) : qs;
+    // the reference clamps in double and uses the double value (pyx:432-435)
+    r.lam = a.use_lambda ? clampd((double)w.z, a.lam_min, a.lam_max) : 1.0;
+    return r;
+}
+
+template <bool ALL>
+__device__ __forceinline__ void fwd_issue(const FwdArgs &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
+#pragma unroll
+    for (int r = 0; r < CHUNK; ++r) {
+        const int g = tid + r * SCAN_THREADS;
+        const int64_t k = stage_pos(p0, L, s, g);
+        const bool ok = k < a.n;
+        const int64_t kk = ok ? k : 0;
+        unsigned char *d = RecGeom<48>::slot(buf, g);
+        cp_async<16>(d, a.SA + kk, ok);
+        if (ALL) cp_async<16>(d + 16, a.SB + kk, ok);
+        if (a.use_kappa) cp_async<4>(d + 32, a.kap + kk, ok);
+        if (a.use_qscale) cp_async<4>(d + 36, a.qs + kk, ok);
+        if (a.use_lambda) cp_async<4>(d + 40, a.lam + kk, ok);
+    }
+}
+
 template <bool CANON>
 struct Fwd2 {
     using Elem = Filt2;
@@ -238,7 +284,6 @@ struct Fwd2 {
     using Carry = Kf2;
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
-    __device__ static __forceinline__ int64_t positions(const Args &a) { return a.n; }
 
     __device__ static __forceinline__ Elem identity() { return filt2_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt2_combine(a, b); }
@@ -257,35 +302,10 @@ struct Fwd2 {
         lo = 0;
         hi = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
     }
-
-    // ALL = false: only what pass 1 reads (S0, S1, qk, lam)
+    // ALL = false: only what pass 1 reads (S0, S1 and the raw multipliers)
     template <bool ALL>
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
-                                                    int tid) {
-        double s0[CHUNK], s1[CHUNK], s2[CHUNK], sl[CHUNK];
-        float lm[CHUNK], kp[CHUNK], qs[CHUNK];
-#pragma unroll
-        for (int r = 0; r < CHUNK; ++r) {
-            const int64_t k = stage_pos(p0, L, s, tid + r * SCAN_THREADS);
-            const bool ok = k < a.n;
-            s0[r] = ok ? __ldg(a.S0 + k) : 0.0;
-            s1[r] = ok ? __ldg(a.S1 + k) : 0.0;
-            s2[r] = (ALL && ok) ? __ldg(a.S2 + k) : 0.0;
-            sl[r] = (ALL && ok && a.want_nll) ? __ldg(a.SL + k) : 0.0;
-            lm[r] = (ok && a.use_lambda) ? __ldg(a.lam + k) : 1.0f;
-            kp[r] = (ok && a.use_kappa) ? __ldg(a.kap + k) : 1.0f;
-            qs[r] = (ok && a.use_qscale) ? __ldg(a.qs + k) : 1.0f;
-        }
-#pragma unroll
-        for (int r = 0; r < CHUNK; ++r) {
-            unsigned char *d = G::slot(recs, tid + r * SCAN_THREADS);
-            const double kappa = a.use_kappa ? clampd((double)kp[r], a.kap_min, a.kap_max) : 1.0;
-            const double lam = a.use_lambda ? clampd((double)lm[r], a.lam_min, a.lam_max) : 1.0;
-            const double qk = a.use_kappa ? cb_div((double)qs[r], kappa) : (double)qs[r];
-            *reinterpret_cast<double2 *>(d) = make_double2(s0[r], s1[r]);
-            if (ALL) *reinterpret_cast<double2 *>(d + 16) = make_double2(s2[r], sl[r]);
-            *reinterpret_cast<double2 *>(d + 32) = make_double2(qk, __longlong_as_double((long long)__float_as_uint((float)lam)));
-        }
+    __device__ static __forceinline__ void issue(const Args &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
+        fwd_issue<ALL>(a, buf, p0, L, s, tid);
     }
 
     template <bool FULLC>
@@ -295,10 +315,9 @@ struct Fwd2 {
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
-                const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
-                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
-                const double qk = ql.x;
-                filt2_step<CANON>(g, a.M, qk * a.M.q00, qk * a.M.q01, qk * a.M.q11, lam * s01.x, lam * s01.y);
+                const FwdRaw w = fwd_raw(a, rec + i * 48);
+                filt2_step<CANON>(g, a.M, w.qk * a.M.q00, w.qk * a.M.q01, w.qk * a.M.q11, w.lam * s01.x,
+                                  w.lam * s01.y);
             }
         }
     }
@@ -319,10 +338,9 @@ struct Fwd2 {
                 unsigned char *b = rec + i * 48;
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
-                const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
-                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
+                const FwdRaw w = fwd_raw(a, b);
                 BinOut o;
-                kf2_step<CANON>(s, a.M, ql.x, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
+                kf2_step<CANON>(s, a.M, w.qk, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
                                 a.want_nll != 0, per_bin, o, acc);
                 const float d = (float)o.stat;
                 acc_d += (double)d;
@@ -341,7 +359,9 @@ struct Fwd2 {
         for (int r = 0; r < CHUNK; ++r) {
             const int g = tid + r * SCAN_THREADS;
             const int64_t k = stage_pos(p0, L, s, g);
-            if (k < a.n) {
+            // bins [L, HEAD_BINS) of an unsharded chromosome are written by the head replay instead
+            const bool head = a.init_state == nullptr && k >= L && k < HEAD_BINS;
+            if (k < a.n && !head) {
                 const unsigned char *d = G::slot(recs, g);
                 const float4 xd = *reinterpret_cast<const float4 *>(d + 32);
                 if (a.do_store) {
@@ -353,6 +373,30 @@ struct Fwd2 {
                 if (k == 0 && a.q_head) *reinterpret_cast<float4 *>(a.q_head) = *reinterpret_cast<const float4 *>(d + 16);
                 if (a.D) a.D[k] = xd.z;
             }
+        }
+    }
+
+    // Head replay (see HEAD_BINS): the first thread of the first tile carries its replay on through
+    // bins [L, HEAD_BINS), reading the inputs straight from global memory.
+    __device__ static __forceinline__ void epilogue(const Args &a, int tile, int tid, int L, Carry &s) {
+        if (tile != 0 || tid != 0 || L >= HEAD_BINS || a.init_state != nullptr) return;
+        const int64_t end = a.n < HEAD_BINS ? a.n : HEAD_BINS;
+        NllAcc acc;
+        nll_acc_init(acc);
+        for (int64_t k = L; k < end; ++k) {
+            const double2 s01 = a.SA[k], s2l = a.SB[k];
+            const double qs = a.use_qscale ? (double)a.qs[k] : 1.0;
+            const double qk = a.use_kappa ? cb_div(qs, clampd((double)a.kap[k], a.kap_min, a.kap_max)) : qs;
+            const double lam = a.use_lambda ? clampd((double)a.lam[k], a.lam_min, a.lam_max) : 1.0;
+            BinOut o;
+            kf2_step<CANON>(s, a.M, qk, lam, s01.x, s01.y, s2l.x, a.want_nll ? s2l.y : 0.0, a.m, a.inv_m, a.mlog2pi,
+                            a.want_nll != 0, a.nll_in_d != 0, o, acc);
+            if (a.do_store) {
+                reinterpret_cast<float4 *>(a.Pf)[k] = make_float4((float)s.P00, (float)s.P01, (float)s.P10, (float)s.P11);
+                reinterpret_cast<float4 *>(a.Qf)[k - 1] = make_float4((float)o.Q00, (float)o.Q01, (float)o.Q10, (float)o.Q11);
+                reinterpret_cast<float2 *>(a.xf)[k] = make_float2((float)s.x0, (float)s.x1);
+            }
+            if (a.D) a.D[k] = (float)o.stat;
         }
     }
 };
@@ -367,7 +411,6 @@ struct Fwd1 {
     using Carry = State1;
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
-    __device__ static __forceinline__ int64_t positions(const Args &a) { return a.n; }
 
     __device__ static __forceinline__ Elem identity() { return filt1_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt1_combine(a, b); }
@@ -382,9 +425,8 @@ struct Fwd1 {
         Fwd2<false>::bounds(a, q0, lo, hi);
     }
     template <bool ALL>
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
-                                                    int tid) {
-        Fwd2<false>::stage_in<ALL>(a, recs, p0, L, s, tid);
+    __device__ static __forceinline__ void issue(const Args &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
+        fwd_issue<ALL>(a, buf, p0, L, s, tid);
     }
     template <bool FULLC>
     __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t,
@@ -393,13 +435,13 @@ struct Fwd1 {
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
-                const double2 ql = *reinterpret_cast<const double2 *>(rec + i * 48 + 32);
-                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
-                filt1_step(g, ql.x * a.M.q00, lam * s01.x, lam * s01.y);
+                const FwdRaw w = fwd_raw(a, rec + i * 48);
+                filt1_step(g, w.qk * a.M.q00, w.lam * s01.x, w.lam * s01.y);
             }
         }
     }
     __device__ static __forceinline__ Carry begin2(const Args &, const State &st) { return st; }
+    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t,
                                                  Carry &s, double &acc_d, double &acc_nll) {
@@ -412,10 +454,9 @@ struct Fwd1 {
                 unsigned char *b = rec + i * 48;
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
-                const double2 ql = *reinterpret_cast<const double2 *>(b + 32);
-                const double lam = (double)__uint_as_float((unsigned)__double_as_longlong(ql.y));
+                const FwdRaw w = fwd_raw(a, b);
                 BinOut o;
-                kf1_step(s, ql.x * a.M.q00, lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
+                kf1_step(s, w.qk * a.M.q00, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
                          a.want_nll != 0, per_bin, o, acc);
                 const float d = (float)o.stat;
                 acc_d += (double)d;
@@ -460,7 +501,6 @@ struct Bwd2 {
     static constexpr bool HAS_SUMS = false;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
     __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
-    __device__ static __forceinline__ int64_t positions(const Args &a) { return npad(a); }
 
     __device__ static __forceinline__ Elem identity() { return smo2_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo2_combine(a, b); }
@@ -481,27 +521,19 @@ struct Bwd2 {
         hi = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
     }
     template <bool ALL>
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
-                                                    int tid) {
-        float4 P[CHUNK], Q[CHUNK];
-        float2 x[CHUNK];
+    __device__ static __forceinline__ void issue(const Args &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
         const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int64_t k = np - 1 - stage_pos(p0, L, s, tid + r * SCAN_THREADS);
+            const int g = tid + r * SCAN_THREADS;
+            const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             const bool ok = k >= 0 && k < a.n;
-            P[r] = ok ? __ldg(reinterpret_cast<const float4 *>(a.Pf) + k) : make_float4(0, 0, 0, 0);
+            const int64_t kk = ok ? k : 0;
+            unsigned char *d = G::slot(buf, g);
+            cp_async<16>(d, reinterpret_cast<const float4 *>(a.Pf) + kk, ok);
             // row n-1 of Qf holds nothing unless a following shard supplied it
-            Q[r] = (ok && (k < a.n - 1 || !a.is_last_shard)) ? __ldg(reinterpret_cast<const float4 *>(a.Qf) + k)
-                                                             : make_float4(0, 0, 0, 0);
-            x[r] = ok ? __ldg(reinterpret_cast<const float2 *>(a.xf) + k) : make_float2(0, 0);
-        }
-#pragma unroll
-        for (int r = 0; r < CHUNK; ++r) {
-            unsigned char *d = G::slot(recs, tid + r * SCAN_THREADS);
-            *reinterpret_cast<float4 *>(d) = P[r];
-            *reinterpret_cast<float4 *>(d + 16) = Q[r];
-            *reinterpret_cast<float4 *>(d + 32) = make_float4(x[r].x, x[r].y, 0.0f, 0.0f);
+            cp_async<16>(d + 16, reinterpret_cast<const float4 *>(a.Qf) + kk, ok && (k < a.n - 1 || !a.is_last_shard));
+            cp_async<8>(d + 32, reinterpret_cast<const float2 *>(a.xf) + kk, ok);
         }
     }
     template <bool FULLC>
@@ -513,7 +545,7 @@ struct Bwd2 {
             if (FULLC || (i >= lo && i < hi)) {
                 const float4 P = *reinterpret_cast<const float4 *>(rec + i * 48);
                 const float4 Q = *reinterpret_cast<const float4 *>(rec + i * 48 + 16);
-                const float4 x = *reinterpret_cast<const float4 *>(rec + i * 48 + 32);
+                const float2 x = *reinterpret_cast<const float2 *>(rec + i * 48 + 32);
                 Elem e;
                 if (klast - i == a.n - 1 && a.is_last_shard) {
                     e = smo2_from_state(State2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.w});
@@ -528,6 +560,7 @@ struct Bwd2 {
     __device__ static __forceinline__ Carry begin2(const Args &, const State &st) {
         return Rs2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
     }
+    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
@@ -538,7 +571,7 @@ struct Bwd2 {
                 unsigned char *b = rec + i * 48;
                 const float4 P = *reinterpret_cast<const float4 *>(b);
                 const float4 Q = *reinterpret_cast<const float4 *>(b + 16);
-                const float4 x = *reinterpret_cast<const float4 *>(b + 32);
+                const float2 x = *reinterpret_cast<const float2 *>(b + 32);
                 if (klast - i == a.n - 1 && a.is_last_shard) {
                     c = Rs2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.z, (double)P.w};
                     // xs = xf, Ps = Pf already in place; lag row n-1 does not exist
@@ -548,7 +581,7 @@ struct Bwd2 {
                     rts2_step(c, r, x.x, x.y, P.x, P.y, P.w, o);
                     *reinterpret_cast<float4 *>(b) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
                     *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
-                    *reinterpret_cast<float4 *>(b + 32) = make_float4((float)o.xs0, (float)o.xs1, 0.0f, 0.0f);
+                    *reinterpret_cast<float2 *>(b + 32) = make_float2((float)o.xs0, (float)o.xs1);
                 }
             }
         }
@@ -565,8 +598,7 @@ struct Bwd2 {
                 reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(d);
                 if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
                     reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(d + 16);
-                const float4 x = *reinterpret_cast<const float4 *>(d + 32);
-                reinterpret_cast<float2 *>(a.xs)[k] = make_float2(x.x, x.y);
+                reinterpret_cast<float2 *>(a.xs)[k] = *reinterpret_cast<const float2 *>(d + 32);
             }
         }
     }
@@ -585,7 +617,6 @@ struct Bwd1 {
     static constexpr bool HAS_SUMS = false;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
     __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
-    __device__ static __forceinline__ int64_t positions(const Args &a) { return npad(a); }
 
     __device__ static __forceinline__ Elem identity() { return smo1_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo1_combine(a, b); }
@@ -604,21 +635,19 @@ struct Bwd1 {
         hi = rem <= 0 ? 0 : (rem >= CHUNK ? CHUNK : (int)rem);
     }
     template <bool ALL>
-    __device__ static __forceinline__ void stage_in(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
-                                                    int tid) {
-        float x[CHUNK], P[CHUNK], Q[CHUNK];
+    __device__ static __forceinline__ void issue(const Args &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
         const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int64_t k = np - 1 - stage_pos(p0, L, s, tid + r * SCAN_THREADS);
+            const int g = tid + r * SCAN_THREADS;
+            const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             const bool ok = k >= 0 && k < a.n;
-            x[r] = ok ? __ldg(a.xf + k) : 0.0f;
-            P[r] = ok ? __ldg(a.Pf + k) : 0.0f;
-            Q[r] = (ok && (k < a.n - 1 || !a.is_last_shard)) ? __ldg(a.Qf + k) : 0.0f;
+            const int64_t kk = ok ? k : 0;
+            unsigned char *d = G::slot(buf, g);
+            cp_async<4>(d, a.xf + kk, ok);
+            cp_async<4>(d + 4, a.Pf + kk, ok);
+            cp_async<4>(d + 8, a.Qf + kk, ok && (k < a.n - 1 || !a.is_last_shard));
         }
-#pragma unroll
-        for (int r = 0; r < CHUNK; ++r)
-            *reinterpret_cast<float4 *>(G::slot(recs, tid + r * SCAN_THREADS)) = make_float4(x[r], P[r], Q[r], 0.0f);
     }
     template <bool FULLC>
     __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t q0,
@@ -641,6 +670,7 @@ struct Bwd1 {
         }
     }
     __device__ static __forceinline__ Carry begin2(const Args &, const State &st) { return Carry{r32(st.x), r32(st.P)}; }
+    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
@@ -747,7 +777,7 @@ template <class Tr>
 struct ScanSmem {
     static constexpr int N = Tr::Elem::N;
     static constexpr int SN = Tr::State::N;
-    static constexpr int REC_TOTAL = SCAN_THREADS * Tr::G::REC_BYTES;
+    static constexpr int REC_TOTAL = 2 * Tr::G::BUF_BYTES;  // double-buffered records
     // doubles after the records
     static constexpr int OFF_WAGG = 0;                     // [NWARPS][N]
     static constexpr int OFF_WEXCL = OFF_WAGG + NWARPS * N;  // [NWARPS][N]
@@ -766,7 +796,6 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     using State = typename Tr::State;
     using SM = ScanSmem<Tr>;
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char *recs = smem;
     double *sd = reinterpret_cast<double *>(smem + SM::REC_TOTAL);
     int *s_tile = reinterpret_cast<int *>(sd + SM::OFF_END);
 
@@ -777,25 +806,28 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     const int L = CHUNK * nsub;
     const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
     const int64_t run0 = p0 + (int64_t)tid * L;
-    unsigned char *myrec = recs + tid * Tr::G::REC_BYTES;
-    const bool single = nsub == 1;  // the records staged for pass 1 are kept for pass 2
+    const int myoff = tid * Tr::G::REC_BYTES;
+    auto buf = [&](int s) -> unsigned char * { return smem + (s & 1) * Tr::G::BUF_BYTES; };
 
-    // ---- pass 1: every thread composes the element of its run ----
+    // ---- pass 1: every thread composes the element of its run; the copies of sub-step s+1 are
+    // in flight while sub-step s is computed ----
+    Tr::template issue<false>(a, buf(0), p0, L, 0, tid);
+    cp_async_commit();
     Elem mine = Tr::identity();
     for (int s = 0; s < nsub; ++s) {
-        if (s) __syncthreads();  // the previous sub-step's records are still being read
-        if (single)
-            Tr::template stage_in<true>(a, recs, p0, L, s, tid);
-        else
-            Tr::template stage_in<false>(a, recs, p0, L, s, tid);
-        __syncthreads();
+        cp_async_wait_all();
+        __syncthreads();  // sub-step s has landed for every thread; buffer (s+1)&1 is no longer read
+        if (s + 1 < nsub) {
+            Tr::template issue<false>(a, buf(s + 1), p0, L, s + 1, tid);
+            cp_async_commit();
+        }
         const int64_t q0 = run0 + s * CHUNK;
         int lo, hi;
         Tr::bounds(a, q0, lo, hi);
         if (lo == 0 && hi == CHUNK)
-            Tr::template pass1<true>(a, myrec, lo, hi, q0, mine);
+            Tr::template pass1<true>(a, buf(s) + myoff, lo, hi, q0, mine);
         else if (hi > lo)
-            Tr::template pass1<false>(a, myrec, lo, hi, q0, mine);
+            Tr::template pass1<false>(a, buf(s) + myoff, lo, hi, q0, mine);
     }
 
     // inclusive Kogge-Stone scan across the warp
@@ -807,6 +839,11 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     }
     if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
     __syncthreads();
+    if (!AGG_ONLY) {
+        // pass 2's first sub-step is fetched underneath the serial section below
+        Tr::template issue<true>(a, buf(0), p0, L, 0, tid);
+        cp_async_commit();
+    }
 
     // the serial section (cross-warp prefix, look-back, publication) rotates over the warps so
     // that it does not always land on the same SM sub-partition
@@ -851,6 +888,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         }
     }
     if (AGG_ONLY) return;
+    cp_async_wait_all();
     __syncthreads();
 
     const State tpref = load_elem<State>(sd + SM::OFF_TSTATE);
@@ -864,21 +902,25 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     typename Tr::Carry carry = Tr::begin2(a, start);
     double acc0 = 0.0, acc1 = 0.0;
     for (int s = 0; s < nsub; ++s) {
-        if (!single) {
-            if (s) __syncthreads();  // the previous sub-step's outputs are still being stored
-            Tr::template stage_in<true>(a, recs, p0, L, s, tid);
-            __syncthreads();
+        if (s) {
+            cp_async_wait_all();
+            __syncthreads();  // sub-step s has landed; the stores of sub-step s-1 have read their buffer
+        }
+        if (s + 1 < nsub) {
+            Tr::template issue<true>(a, buf(s + 1), p0, L, s + 1, tid);
+            cp_async_commit();
         }
         const int64_t q0 = run0 + s * CHUNK;
         int lo, hi;
         Tr::bounds(a, q0, lo, hi);
         if (lo == 0 && hi == CHUNK)
-            Tr::template pass2<true>(a, myrec, lo, hi, q0, carry, acc0, acc1);
+            Tr::template pass2<true>(a, buf(s) + myoff, lo, hi, q0, carry, acc0, acc1);
         else if (hi > lo)
-            Tr::template pass2<false>(a, myrec, lo, hi, q0, carry, acc0, acc1);
+            Tr::template pass2<false>(a, buf(s) + myoff, lo, hi, q0, carry, acc0, acc1);
         __syncthreads();
-        Tr::stage_out(a, recs, p0, L, s, tid);
+        Tr::stage_out(a, buf(s), p0, L, s, tid);
     }
+    Tr::epilogue(a, tile, tid, L, carry);
 
     if (Tr::HAS_SUMS) {
 #pragma unroll
@@ -1021,15 +1063,16 @@ residual_kernel(const float *__restrict__ data, int64_t m, int64_t n, int64_t ld
 // =====================================================================================
 // Student-t precision multipliers
 // =====================================================================================
-__global__ void lambda_kernel(const double *__restrict__ S0, const double *__restrict__ S1,
-                              const double *__restrict__ S2, int64_t n, double m, const float *__restrict__ xs,
+__global__ void lambda_kernel(const double2 *__restrict__ SA, const double2 *__restrict__ SB, int64_t n, double m,
+                              const float *__restrict__ xs,
                               const float *__restrict__ Ps, int dim, double nu, double lo, double hi,
                               float *__restrict__ lam) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const double lvl = (double)xs[k * dim];
     const double p00 = (double)Ps[k * dim * dim];
-    lam[k] = (float)lambda_update(S0[k], S1[k], S2[k], lvl, p00, m, nu, lo, hi);
+    const double2 s01 = SA[k];
+    lam[k] = (float)lambda_update(s01.x, s01.y, SB[k].x, lvl, p00, m, nu, lo, hi);
 }
 
 __global__ void kappa2_kernel(Model2 M, double qi00, double qi01, double qi10, double qi11, int64_t n,
@@ -1168,7 +1211,7 @@ int scan_pick_nsub(int64_t positions, int which) {
         const int64_t waves = (tiles + slots - 1) / slots;
         const double fill = (double)tiles / (double)(waves * slots);  // occupancy of the tile slots
         // per-position overhead of the scan stages shrinks as 1 / ns
-        const double score = fill / (1.0 + 0.9 / ns);
+        const double score = fill / (1.0 + 1.8 / ns);
         if (score > best_score + 1e-9) {
             best_score = score;
             best = ns;
@@ -1178,17 +1221,17 @@ int scan_pick_nsub(int64_t positions, int which) {
 }
 
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
-                        double *S0, double *S1, double *S2, double *SL, cudaStream_t st) {
+                        double2 *SA, double2 *SB, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(munc) & 15) == 0);
     if (vec) {
         const int64_t threads = (n + 3) / 4;
         const unsigned grid = (unsigned)((threads + FOLD_THREADS - 1) / FOLD_THREADS);
-        fold_kernel<4><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, S0, S1, S2, SL);
+        fold_kernel<4><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, SA, SB);
     } else {
         const unsigned grid = (unsigned)((n + FOLD_THREADS - 1) / FOLD_THREADS);
-        fold_kernel<1><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, S0, S1, S2, SL);
+        fold_kernel<1><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, SA, SB);
     }
     return cudaGetLastError();
 }
@@ -1234,11 +1277,11 @@ cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld
     return cudaGetLastError();
 }
 
-cudaError_t launch_update_lambda(const double *S0, const double *S1, const double *S2, int64_t n, double m,
+cudaError_t launch_update_lambda(const double2 *SA, const double2 *SB, int64_t n, double m,
                                  const float *xs, const float *Ps, int dim, double nu, double lo, double hi,
                                  float *lam, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
-    lambda_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(S0, S1, S2, n, m, xs, Ps, dim, nu, lo, hi, lam);
+    lambda_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(SA, SB, n, m, xs, Ps, dim, nu, lo, hi, lam);
     return cudaGetLastError();
 }
 

@@ -11,9 +11,15 @@ namespace cb200 {
 // Geometry of the look-back scans: every thread owns a run of CHUNK * nsub consecutive scan
 // positions, processed in nsub sub-steps of CHUNK; a tile is SCAN_THREADS runs.
 constexpr int SCAN_THREADS = 128;
-constexpr int CHUNK = 8;
+constexpr int CHUNK = 4;
 constexpr int TILE_BINS = SCAN_THREADS * CHUNK;  // positions per tile per sub-step
-constexpr int MAX_NSUB = 8;
+constexpr int MAX_NSUB = 16;
+// The 2-state forward filter replays the first HEAD_BINS bins of a chromosome as ONE sequential
+// run (the first thread of the first tile continues past its own run if that is shorter): under
+// the diffuse prior (stateCovarInit = 1000 carried in float32) the reference's own cross
+// covariances are rounding-noise dominated for about ten bins, and only an uninterrupted replay
+// of its rounding sequence reproduces them.
+constexpr int HEAD_BINS = 16;
 constexpr int AGG_PITCH = 16;   // doubles per published tile aggregate (14 used)
 constexpr int PREF_PITCH = 8;   // doubles per published tile prefix state (5 used)
 
@@ -27,7 +33,7 @@ struct ScanWorkspace {    // sized by scan_workspace_bytes(n); zeroed once when 
 };
 
 struct FwdArgs {
-    const double *S0, *S1, *S2, *SL;
+    const double2 *SA, *SB;    // fold statistics per bin: SA = {S0, S1}, SB = {S2, SL}
     const float *lam, *kap, *qs;
     const double *init_state;  // device, or nullptr -> model prior
     float *xf, *Pf, *Qf, *D;
@@ -61,14 +67,14 @@ void scan_set_nsub_override(int nsub);
 
 // every launcher returns the cudaError_t of the launch (cudaGetLastError)
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
-                        double *S0, double *S1, double *S2, double *SL, cudaStream_t st);
+                        double2 *SA, double2 *SB, cudaStream_t st);
 cudaError_t launch_forward(int dim, const FwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
                            cudaStream_t st, int *launches);
 cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
                             cudaStream_t st, int *launches);
 cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
                              float *resid, cudaStream_t st);
-cudaError_t launch_update_lambda(const double *S0, const double *S1, const double *S2, int64_t n, double m,
+cudaError_t launch_update_lambda(const double2 *SA, const double2 *SB, int64_t n, double m,
                                  const float *xs, const float *Ps, int dim, double nu, double lo, double hi,
                                  float *lam, cudaStream_t st);
 cudaError_t launch_update_kappa(int dim, const Model2 &M, int64_t n, const float *xs, const float *Ps,

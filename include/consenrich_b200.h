@@ -131,8 +131,9 @@ CB200_API int cb200_copy_d2h(cb200_ctx *ctx, void *dst, size_t dst_pitch, const 
 /* ---- device-resident path ------------------------------------------------------------- */
 /* Fold the m observations of every interval into information form, one coalesced pass over
  * data and munc (replaces the per-(interval, sample) calls of _accumulateObservationValue,
- * cconsenrich.pyx:259-283).  stats = 4 arrays of `stat_stride` doubles laid end to end:
- * S0 = sum 1/r, S1 = sum z/r, S2 = sum z^2/r, SL = sum log r, r = max(munc + pad, 1e-12). */
+ * cconsenrich.pyx:259-283).  stats = 4 * stat_stride doubles: first stat_stride pairs {S0, S1}, then
+ * stat_stride pairs {S2, SL}; S0 = sum 1/r, S1 = sum z/r, S2 = sum z^2/r, SL = sum log r,
+ * r = max(munc + pad, 1e-12).  Opaque to callers: produced here, consumed by the scans. */
 CB200_API int cb200_fold_tracks(cb200_ctx *ctx, const float *data, const float *munc, int64_t m, int64_t n,
                       int64_t ld, double pad, double *stats, int64_t stat_stride);
 

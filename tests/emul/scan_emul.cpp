@@ -115,6 +115,7 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
     const double mlog2pi = (double)m * log(6.2831853071795864769);
     *sum_d = 0.0;
     *sum_nll = 0.0;
+    Kf2 head_carry{};
     for (int64_t c = 0; c < nchunks; ++c) {
         int64_t t = c / T, i = c % T;
         State2 s0 = tile_prefix[t];
@@ -124,6 +125,8 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
             s.x0 = r32(s.x0); s.x1 = r32(s.x1);
             s.P00 = r32(s.P00); s.P01 = r32(s.P01); s.P10 = s.P01; s.P11 = r32(s.P11);
         }
+        // head replay: runs that start inside the first 16 bins continue the first run's replay
+        if (c > 0 && c * L < 16) s = head_carry;
         NllAcc acc;
         nll_acc_init(acc);
         for (int64_t k = c * L; k < n && k < (c + 1) * L; ++k) {
@@ -148,6 +151,7 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
             }
         }
         if (p->return_nll && !p->store_nll_in_d) *sum_nll += nll_acc_finish(acc, (double)m, mlog2pi);
+        head_carry = s;
     }
 }
 

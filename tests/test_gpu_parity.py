@@ -103,16 +103,16 @@ def test_sweep_matches_oracle(cb, oracle, dim, case):
 
 
 @pytest.mark.parametrize("dim", [2, 1])
-@pytest.mark.parametrize("nsub", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("nsub", [1, 2, 3, 5, 8, 16])
 def test_sweep_is_independent_of_the_run_length(cb, oracle, dim, nsub):
-    """Every thread of the scan kernels runs through nsub sub-steps of 8 bins; the launch heuristic
+    """Every thread of the scan kernels runs through nsub sub-steps of 4 bins; the launch heuristic
     picks nsub from the track length.  Force each value: ragged tails, runs that straddle the end,
     several tiles per value."""
     from consenrich_b200 import _lib
     L = _lib.load()
     try:
         _lib.check(L.cb200_set_scan_substeps(nsub))
-        for m, n in ((4, 8 * 128 * nsub * 3 + 13), (6, 8 * 128 * nsub - 1), (3, 8 * nsub + 1), (9, 70001)):
+        for m, n in ((4, 4 * 128 * nsub * 3 + 13), (6, 4 * 128 * nsub - 1), (3, 4 * nsub + 1), (9, 70001)):
             data, munc = synth_tracks(900 + n + nsub, m, n, masked_frac=0.03)
             lam, kap, qs = _weights(np.random.default_rng(n), n)
             want = _sweep(oracle, dim, data, munc, lam, kap, qs)
