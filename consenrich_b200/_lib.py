@@ -73,6 +73,7 @@ SIGNATURES = {
     "cb200_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cb200_ctx_reset_timing": (C.c_int, [_vp]),
     "cb200_set_scan_substeps": (C.c_int, [C.c_int]),
+    "cb200_debug_scan_times": (C.c_int, [_vp, _i64, _vp]),
     "cb200_device_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "cb200_device_free": (C.c_int, [_vp, _vp]),
     "cb200_pinned_alloc": (C.c_int, [_sz, C.POINTER(_vp)]),

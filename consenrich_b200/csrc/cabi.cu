@@ -67,6 +67,8 @@ struct cb200_ctx {
     int64_t launches = 0;
     int32_t scan_epoch = 0;  // bumped per look-back scan launch (tags the workspace flags)
     int64_t scan_ws_n = 0;   // track length the scan workspace is laid out for
+    long long *scan_dbg = nullptr;  // diagnostics buffer (cb200_debug_scan_times)
+    int64_t scan_dbg_tiles = 0;
     // arena (device)
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     double *sums_host = nullptr;  // pinned double[2]
@@ -114,6 +116,7 @@ int next_scan_ws(cb200_ctx *c, int64_t n, ScanWorkspace *ws) {
     c->scan_epoch += 1;
     *ws = scan_workspace_carve(c->scan_ws.p, c->scan_ws_n);
     ws->epoch4 = c->scan_epoch * 4;
+    ws->dbg = c->scan_dbg;
     return CB200_OK;
 }
 
@@ -441,6 +444,26 @@ int cb200_ctx_kernel_ms(cb200_ctx *c, int family, double *ms, int64_t *launches)
     CB_TRY(resolve_spans(c));
     if (ms) *ms = c->fam_ms[family];
     if (launches) *launches = c->fam_n[family];
+    return CB200_OK;
+}
+
+int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (host_out && c->scan_dbg) {
+        const int64_t t = tiles < c->scan_dbg_tiles ? tiles : c->scan_dbg_tiles;
+        CU_TRY(cudaMemcpy(host_out, c->scan_dbg, (size_t)t * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    if (c->scan_dbg) {
+        CU_TRY(cudaFree(c->scan_dbg));
+        c->scan_dbg = nullptr;
+        c->scan_dbg_tiles = 0;
+    }
+    if (tiles > 0 && !host_out) {  // arm: the next scan launches stamp their phases
+        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&c->scan_dbg), (size_t)tiles * 4 * sizeof(long long)));
+        CU_TRY(cudaMemset(c->scan_dbg, 0, (size_t)tiles * 4 * sizeof(long long)));
+        c->scan_dbg_tiles = tiles;
+    }
     return CB200_OK;
 }
 

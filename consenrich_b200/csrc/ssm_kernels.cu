@@ -25,11 +25,19 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NWARPS = SCAN_THREADS / 32;
+#ifndef SCAN_MIN_CTAS
+#define SCAN_MIN_CTAS 4
+#endif
 
 __device__ __forceinline__ int ld_acquire(const int *p) {
     int v;
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ long long gtimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -719,55 +727,104 @@ struct Bwd1 {
 // =====================================================================================
 // decoupled look-back (one warp of the CTA)
 // =====================================================================================
+// Two-level look-back.  When every tile of a wave finishes composing its run elements at about
+// the same time, no tile has a prefix yet and a plain look-back walks back 32 aggregates per
+// round, all the way to the start (hundreds of tiles = tens of microseconds, every tile doing the
+// same work).  Here a tile that finds no prefix in its first window publishes the aggregate of
+// that window plus itself (a level-1 aggregate spanning SPAN1 = 33 tiles); further rounds then
+// read level-1 aggregates at a stride of 33 tiles, covering 1056 tiles per round.  Dependencies
+// still point only at earlier tiles, so there is nothing to deadlock on.
+//   flag - epoch4:  1 = aggregate published, 2 = level-1 aggregate published, 3 = prefix published
+constexpr int SPAN1 = 33;
+
 template <class Tr>
-__device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWorkspace &ws, int tile, int lane) {
+__device__ __forceinline__ int flag_state(const ScanWorkspace &ws, int idx) {
+    const int v = ld_acquire(ws.flags + idx) - ws.epoch4;
+    return (v >= 1 && v <= 3) ? v : 0;
+}
+
+// ordered tree reduction over lanes 0..first of a window (lane i holds the later tiles)
+template <class Tr>
+__device__ __forceinline__ typename Tr::Elem window_reduce(typename Tr::Elem e, int first, int lane) {
+    const int span = first < 32 ? first + 1 : 32;
+    for (int d = 1; d < span; d <<= 1) {
+        const typename Tr::Elem o = shfl_down_elem(e, d);
+        if (lane + d < 32) e = Tr::combine(o, e);
+    }
+    return e;
+}
+
+template <class Tr>
+__device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWorkspace &ws, int tile, int lane,
+                                       const typename Tr::Elem &own_agg) {
     using Elem = typename Tr::Elem;
     using State = typename Tr::State;
-    Elem running = Tr::identity();
-    bool have = false;
-    int base = tile - 1;
-    while (true) {
-        const int idx = base - lane;
+    // ---- round A: plain aggregates of tiles tile-1 .. tile-32 ----
+    Elem running;
+    {
+        const int idx = tile - 1 - lane;
         int f;
         while (true) {
-            f = 2;
-            if (idx >= 0) {
-                // flags carry the launch epoch: values left by earlier launches read as "nothing"
-                const int v = ld_acquire(ws.flags + idx) - ws.epoch4;
-                f = (v == 1 || v == 2) ? v : 0;
-            }
-            // the window is usable as soon as every tile up to the nearest published prefix has
-            // at least its aggregate out; tiles beyond that prefix do not matter
-            const unsigned pm = __ballot_sync(FULL, f == 2);
+            f = idx >= 0 ? flag_state<Tr>(ws, idx) : 3;
+            // usable as soon as every tile up to the nearest published prefix has its aggregate out
+            const unsigned pm = __ballot_sync(FULL, f == 3);
             const unsigned zm = __ballot_sync(FULL, f == 0);
             const unsigned upto = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : FULL;  // lanes 0..first
             if ((zm & upto) == 0) break;
         }
-        const unsigned pm = __ballot_sync(FULL, f == 2);
+        const unsigned pm = __ballot_sync(FULL, f == 3);
         const int first = pm ? (__ffs(pm) - 1) : 32;
         Elem e;
         if (lane > first) {
             e = Tr::identity();
-        } else if (f == 2) {
+        } else if (f == 3) {
             State s = (idx >= 0) ? load_elem_cg<State>(ws.tile_pref + (int64_t)idx * PREF_PITCH) : Tr::initial(a);
             e = Tr::from_state(s);
         } else {
             e = load_elem_cg<Elem>(ws.tile_agg + (int64_t)idx * AGG_PITCH);
         }
-        // ordered tree reduction over lanes 0..first: lane i holds tile base-i, lane i+d an earlier
-        // tile; only as many levels as the window needs
-        const int span = first < 32 ? first + 1 : 32;
-        for (int d = 1; d < span; d <<= 1) {
-            const Elem o = shfl_down_elem(e, d);
-            if (lane + d < 32) e = Tr::combine(o, e);
-        }
-        running = have ? Tr::combine(e, running) : e;
-        have = true;
-        if (first < 32) break;
-        base -= 32;
+        running = window_reduce<Tr>(e, first, lane);
+        if (first < 32) return Tr::elem_state(shfl_bcast_elem(running, 0));
     }
-    const Elem r0 = shfl_bcast_elem(running, 0);
-    return Tr::elem_state(r0);
+    // no prefix within 32 tiles: publish the level-1 aggregate of tiles tile-32 .. tile
+    {
+        const Elem l1 = Tr::combine(shfl_bcast_elem(running, 0), own_agg);
+        if (lane == 0) {
+            store_elem(ws.tile_agg1 + (int64_t)tile * AGG_PITCH, l1);
+            __threadfence();
+            st_release(ws.flags + tile, ws.epoch4 + 2);
+        }
+        __syncwarp();
+    }
+    // ---- further rounds: level-1 aggregates at a stride of SPAN1 tiles ----
+    int pos = tile - SPAN1;  // latest tile not yet covered
+    while (true) {
+        const int idx = pos - SPAN1 * lane;
+        int f;
+        while (true) {
+            f = idx >= 0 ? flag_state<Tr>(ws, idx) : 3;
+            const unsigned pm = __ballot_sync(FULL, f == 3);
+            const unsigned zm = __ballot_sync(FULL, f < 2);
+            const unsigned upto = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : FULL;
+            if ((zm & upto) == 0) break;
+        }
+        const unsigned pm = __ballot_sync(FULL, f == 3);
+        const int first = pm ? (__ffs(pm) - 1) : 32;
+        Elem e;
+        if (lane > first) {
+            e = Tr::identity();
+        } else if (f == 3) {
+            State s = (idx >= 0) ? load_elem_cg<State>(ws.tile_pref + (int64_t)idx * PREF_PITCH) : Tr::initial(a);
+            e = Tr::from_state(s);
+        } else {
+            e = load_elem_cg<Elem>(ws.tile_agg1 + (int64_t)idx * AGG_PITCH);
+        }
+        e = window_reduce<Tr>(e, first, lane);
+        running = Tr::combine(e, running);
+        if (first < 32) break;
+        pos -= 32 * SPAN1;
+    }
+    return Tr::elem_state(shfl_bcast_elem(running, 0));
 }
 
 // =====================================================================================
@@ -790,7 +847,7 @@ struct ScanSmem {
 };
 
 template <class Tr, bool AGG_ONLY>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS)
 scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles, const int nsub) {
     using Elem = typename Tr::Elem;
     using State = typename Tr::State;
@@ -803,6 +860,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     if (tid == 0) s_tile[0] = AGG_ONLY ? (int)blockIdx.x : atomicAdd(ws.counters, 1);
     __syncthreads();
     const int tile = s_tile[0];
+    if (ws.dbg && tid == 0) ws.dbg[tile * 4] = gtimer();
     const int L = CHUNK * nsub;
     const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
     const int64_t run0 = p0 + (int64_t)tid * L;
@@ -839,6 +897,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     }
     if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
     __syncthreads();
+    if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 1] = gtimer();
     if (!AGG_ONLY) {
         // pass 2's first sub-step is fetched underneath the serial section below
         Tr::template issue<true>(a, buf(0), p0, L, 0, tid);
@@ -871,7 +930,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
                 }
                 __syncwarp();
                 if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 1);
-                pref = lookback<Tr>(a, ws, tile, lane);
+                pref = lookback<Tr>(a, ws, tile, lane, run);
             }
             const State incl = Tr::apply(run, pref);
             if (lane == 0) {
@@ -884,12 +943,13 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
                 __threadfence();
             }
             __syncwarp();
-            if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 2);
+            if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 3);
         }
     }
     if (AGG_ONLY) return;
     cp_async_wait_all();
     __syncthreads();
+    if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 2] = gtimer();
 
     const State tpref = load_elem<State>(sd + SM::OFF_TSTATE);
     State wst = tpref;
@@ -921,6 +981,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         Tr::stage_out(a, buf(s), p0, L, s, tid);
     }
     Tr::epilogue(a, tile, tid, L, carry);
+    if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 3] = gtimer();
 
     if (Tr::HAS_SUMS) {
 #pragma unroll
@@ -1158,15 +1219,17 @@ static size_t ws_tiles(int64_t n) { return (size_t)scan_num_tiles(n + CHUNK, 1) 
 
 size_t scan_workspace_bytes(int64_t n) {
     const size_t t = ws_tiles(n);
-    return align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
+    return 2 * align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
            align_up((t + 2) * 4, 256);
 }
 
 ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
     const size_t t = ws_tiles(n);
     unsigned char *p = static_cast<unsigned char *>(base);
-    ScanWorkspace ws;
+    ScanWorkspace ws{};
     ws.tile_agg = reinterpret_cast<double *>(p);
+    p += align_up(t * AGG_PITCH * 8, 256);
+    ws.tile_agg1 = reinterpret_cast<double *>(p);
     p += align_up(t * AGG_PITCH * 8, 256);
     ws.tile_pref = reinterpret_cast<double *>(p);
     p += align_up(t * PREF_PITCH * 8, 256);

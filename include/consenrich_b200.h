@@ -116,6 +116,10 @@ CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
  * (1..8), 0 = choose per launch from the track length and the resident tile slots.  Results do not
  * depend on it beyond float64 re-association.  Also settable with CB200_SCAN_NSUB. */
 CB200_API int cb200_set_scan_substeps(int nsub);
+/* Diagnostics.  (tiles > 0, host_out NULL) arms phase stamping: every tile of the following scan
+ * launches writes four %globaltimer values (start, run elements composed, prefix known, end).
+ * (host_out non-NULL) copies the stamps of the last launch out ([tiles][4] int64 ns) and disarms. */
+CB200_API int cb200_debug_scan_times(cb200_ctx *ctx, int64_t tiles, long long *host_out);
 
 /* ---- memory helpers (so that hosts without torch can stage tracks) -------------------- */
 CB200_API int cb200_device_alloc(cb200_ctx *ctx, size_t bytes, void **dptr);

@@ -112,7 +112,10 @@ def test_sweep_is_independent_of_the_run_length(cb, oracle, dim, nsub):
     L = _lib.load()
     try:
         _lib.check(L.cb200_set_scan_substeps(nsub))
-        for m, n in ((4, 4 * 128 * nsub * 3 + 13), (6, 4 * 128 * nsub - 1), (3, 4 * nsub + 1), (9, 70001)):
+        sizes = [(4, 4 * 128 * nsub * 3 + 13), (6, 4 * 128 * nsub - 1), (3, 4 * nsub + 1), (9, 70001)]
+        if nsub == 1:
+            sizes.append((2, 1_300_003))  # 2540 tiles: the look-back goes through several level-1 rounds
+        for m, n in sizes:
             data, munc = synth_tracks(900 + n + nsub, m, n, masked_frac=0.03)
             lam, kap, qs = _weights(np.random.default_rng(n), n)
             want = _sweep(oracle, dim, data, munc, lam, kap, qs)
