@@ -127,12 +127,15 @@ __device__ __forceinline__ double fold_logsum(const FoldAcc &a) {
 }
 
 constexpr int FOLD_THREADS = 256;
+#ifndef FOLD_MIN_CTAS
+#define FOLD_MIN_CTAS 4
+#endif
 constexpr int FOLD_UNROLL = 4;
 
 // VEC = 4: each thread owns 4 consecutive bins and streams float4 (needs 16-byte aligned rows);
 // VEC = 1: scalar loads, any alignment.
 template <int VEC>
-__global__ void __launch_bounds__(FOLD_THREADS)
+__global__ void __launch_bounds__(FOLD_THREADS, FOLD_MIN_CTAS)
 fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int64_t m, int64_t n, int64_t ld,
             double pad, double2 *__restrict__ SA, double2 *__restrict__ SB) {
     const int64_t k0 = ((int64_t)blockIdx.x * FOLD_THREADS + threadIdx.x) * VEC;
@@ -227,6 +230,12 @@ struct RecGeom {
     }
 };
 
+// Staging is warp-private: the 32 threads of a warp copy in and store out the records of their
+// own 32 runs (element r of lane l is record l + 32 r of the warp's 32 * CHUNK), so the sub-step
+// loops need only __syncwarp() and the warps of a CTA drift freely between the two CTA-wide
+// barriers around the scan section.
+__device__ __forceinline__ int stage_elem(int tid, int r) { return (tid & ~31) * CHUNK + (tid & 31) + 32 * r; }
+
 // scan position of staged record g (thread g / CHUNK, slot g % CHUNK) in sub-step s
 __device__ __forceinline__ int64_t stage_pos(int64_t p0, int L, int s, int g) {
     return p0 + (int64_t)((g / CHUNK) * L + s * CHUNK + (g % CHUNK));
@@ -270,7 +279,7 @@ template <bool ALL>
 __device__ __forceinline__ void fwd_issue(const FwdArgs &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
 #pragma unroll
     for (int r = 0; r < CHUNK; ++r) {
-        const int g = tid + r * SCAN_THREADS;
+        const int g = stage_elem(tid, r);
         const int64_t k = stage_pos(p0, L, s, g);
         const bool ok = k < a.n;
         const int64_t kk = ok ? k : 0;
@@ -289,7 +298,10 @@ struct Fwd2 {
     using State = State2;
     using Args = FwdArgs;
     using G = RecGeom<48>;
-    using Carry = Kf2;
+    struct Carry {
+        Kf2 s;
+        NllAcc acc;
+    };
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
 
@@ -331,15 +343,24 @@ struct Fwd2 {
     }
 
     __device__ static __forceinline__ Carry begin2(const Args &, const State &st) {
-        return Kf2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+        Carry c;
+        c.s = Kf2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
+        nll_acc_init(c.acc);
+        return c;
+    }
+    // sum of the run's NLL pieces (one pair of logs per run)
+    __device__ static __forceinline__ double finish2(const Args &a, const Carry &c) {
+        return (a.want_nll && !a.nll_in_d) ? nll_acc_finish(c.acc, a.m, a.mlog2pi) : 0.0;
     }
 
     template <bool FULLC>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t,
-                                                 Carry &s, double &acc_d, double &acc_nll) {
-        NllAcc acc;
-        nll_acc_init(acc);
+    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
+                                                 Carry &c, double &acc_d, double &acc_nll) {
+        Kf2 &s = c.s;
+        NllAcc &acc = c.acc;
         const bool per_bin = a.nll_in_d != 0;
+        // bins [head_from, HEAD_BINS) are written and summed by the head replay (epilogue)
+        const bool near_head = q0 < HEAD_BINS && q0 + CHUNK > a.head_from;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
@@ -347,28 +368,29 @@ struct Fwd2 {
                 const double2 s01 = *reinterpret_cast<const double2 *>(b);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
                 const FwdRaw w = fwd_raw(a, b);
+                const bool counted = !(near_head && q0 + i >= a.head_from && q0 + i < HEAD_BINS);
                 BinOut o;
                 kf2_step<CANON>(s, a.M, w.qk, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
-                                a.want_nll != 0, per_bin, o, acc);
+                                a.want_nll != 0 && counted, per_bin, o, acc);
                 const float d = (float)o.stat;
-                acc_d += (double)d;
+                if (counted) acc_d += (double)d;
                 acc_nll += o.nll;
                 *reinterpret_cast<float4 *>(b) = make_float4((float)s.P00, (float)s.P01, (float)s.P10, (float)s.P11);
                 *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.Q00, (float)o.Q01, (float)o.Q10, (float)o.Q11);
                 *reinterpret_cast<float4 *>(b + 32) = make_float4((float)s.x0, (float)s.x1, d, 0.0f);
             }
         }
-        if (a.want_nll && !per_bin) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
+        if (a.want_nll && !per_bin) nll_acc_renorm(acc, a.use_lambda != 0);
     }
 
     __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
                                                      int tid) {
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = tid + r * SCAN_THREADS;
+            const int g = stage_elem(tid, r);
             const int64_t k = stage_pos(p0, L, s, g);
             // bins [L, HEAD_BINS) of an unsharded chromosome are written by the head replay instead
-            const bool head = a.init_state == nullptr && k >= L && k < HEAD_BINS;
+            const bool head = k >= a.head_from && k < HEAD_BINS;
             if (k < a.n && !head) {
                 const unsigned char *d = G::slot(recs, g);
                 const float4 xd = *reinterpret_cast<const float4 *>(d + 32);
@@ -386,9 +408,11 @@ struct Fwd2 {
 
     // Head replay (see HEAD_BINS): the first thread of the first tile carries its replay on through
     // bins [L, HEAD_BINS), reading the inputs straight from global memory.
-    __device__ static __forceinline__ void epilogue(const Args &a, int tile, int tid, int L, Carry &s) {
-        if (tile != 0 || tid != 0 || L >= HEAD_BINS || a.init_state != nullptr) return;
+    __device__ static __forceinline__ void epilogue(const Args &a, int tile, int tid, int L, Carry &c, double &acc_d,
+                                                    double &acc_nll) {
+        if (tile != 0 || tid != 0 || a.head_from >= HEAD_BINS) return;
         const int64_t end = a.n < HEAD_BINS ? a.n : HEAD_BINS;
+        Kf2 &s = c.s;
         NllAcc acc;
         nll_acc_init(acc);
         for (int64_t k = L; k < end; ++k) {
@@ -399,13 +423,17 @@ struct Fwd2 {
             BinOut o;
             kf2_step<CANON>(s, a.M, qk, lam, s01.x, s01.y, s2l.x, a.want_nll ? s2l.y : 0.0, a.m, a.inv_m, a.mlog2pi,
                             a.want_nll != 0, a.nll_in_d != 0, o, acc);
+            const float d = (float)o.stat;
+            acc_d += (double)d;
+            acc_nll += o.nll;
             if (a.do_store) {
                 reinterpret_cast<float4 *>(a.Pf)[k] = make_float4((float)s.P00, (float)s.P01, (float)s.P10, (float)s.P11);
                 reinterpret_cast<float4 *>(a.Qf)[k - 1] = make_float4((float)o.Q00, (float)o.Q01, (float)o.Q10, (float)o.Q11);
                 reinterpret_cast<float2 *>(a.xf)[k] = make_float2((float)s.x0, (float)s.x1);
             }
-            if (a.D) a.D[k] = (float)o.stat;
+            if (a.D) a.D[k] = d;
         }
+        if (a.want_nll && !a.nll_in_d) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
     }
 };
 
@@ -416,7 +444,10 @@ struct Fwd1 {
     using State = State1;
     using Args = FwdArgs;
     using G = RecGeom<48>;
-    using Carry = State1;
+    struct Carry {
+        State1 s;
+        NllAcc acc;
+    };
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
 
@@ -448,13 +479,21 @@ struct Fwd1 {
             }
         }
     }
-    __device__ static __forceinline__ Carry begin2(const Args &, const State &st) { return st; }
-    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &) {}
+    __device__ static __forceinline__ Carry begin2(const Args &, const State &st) {
+        Carry c;
+        c.s = st;
+        nll_acc_init(c.acc);
+        return c;
+    }
+    __device__ static __forceinline__ double finish2(const Args &a, const Carry &c) {
+        return (a.want_nll && !a.nll_in_d) ? nll_acc_finish(c.acc, a.m, a.mlog2pi) : 0.0;
+    }
+    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t,
-                                                 Carry &s, double &acc_d, double &acc_nll) {
-        NllAcc acc;
-        nll_acc_init(acc);
+                                                 Carry &c, double &acc_d, double &acc_nll) {
+        State1 &s = c.s;
+        NllAcc &acc = c.acc;
         const bool per_bin = a.nll_in_d != 0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
@@ -472,13 +511,13 @@ struct Fwd1 {
                 *reinterpret_cast<float4 *>(b) = make_float4((float)s.x, (float)s.P, (float)o.Q00, d);
             }
         }
-        if (a.want_nll && !per_bin) acc_nll += nll_acc_finish(acc, a.m, a.mlog2pi);
+        if (a.want_nll && !per_bin) nll_acc_renorm(acc, a.use_lambda != 0);
     }
     __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
                                                      int tid) {
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = tid + r * SCAN_THREADS;
+            const int g = stage_elem(tid, r);
             const int64_t k = stage_pos(p0, L, s, g);
             if (k < a.n) {
                 const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
@@ -533,7 +572,7 @@ struct Bwd2 {
         const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = tid + r * SCAN_THREADS;
+            const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             const bool ok = k >= 0 && k < a.n;
             const int64_t kk = ok ? k : 0;
@@ -568,7 +607,8 @@ struct Bwd2 {
     __device__ static __forceinline__ Carry begin2(const Args &, const State &st) {
         return Rs2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
     }
-    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &) {}
+    __device__ static __forceinline__ double finish2(const Args &, const Carry &) { return 0.0; }
+    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
@@ -599,7 +639,7 @@ struct Bwd2 {
         const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = tid + r * SCAN_THREADS;
+            const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             if (k >= 0 && k < a.n) {
                 const unsigned char *d = G::slot(recs, g);
@@ -647,7 +687,7 @@ struct Bwd1 {
         const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = tid + r * SCAN_THREADS;
+            const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             const bool ok = k >= 0 && k < a.n;
             const int64_t kk = ok ? k : 0;
@@ -678,7 +718,8 @@ struct Bwd1 {
         }
     }
     __device__ static __forceinline__ Carry begin2(const Args &, const State &st) { return Carry{r32(st.x), r32(st.P)}; }
-    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &) {}
+    __device__ static __forceinline__ double finish2(const Args &, const Carry &) { return 0.0; }
+    __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
@@ -712,7 +753,7 @@ struct Bwd1 {
         const int64_t np = npad(a);
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = tid + r * SCAN_THREADS;
+            const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             if (k >= 0 && k < a.n) {
                 const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
@@ -874,7 +915,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     Elem mine = Tr::identity();
     for (int s = 0; s < nsub; ++s) {
         cp_async_wait_all();
-        __syncthreads();  // sub-step s has landed for every thread; buffer (s+1)&1 is no longer read
+        __syncwarp();  // sub-step s has landed for the whole warp; its buffer (s+1)&1 is no longer read
         if (s + 1 < nsub) {
             Tr::template issue<false>(a, buf(s + 1), p0, L, s + 1, tid);
             cp_async_commit();
@@ -906,9 +947,11 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
 
     // the serial section (cross-warp prefix, look-back, publication) rotates over the warps so
     // that it does not always land on the same SM sub-partition
-    if (warp == (tile & (NWARPS - 1))) {
+    const bool leader = warp == (tile & (NWARPS - 1));
+    Elem run = Tr::identity();
+    if (leader) {
         // exclusive prefixes across warps and the tile aggregate (all lanes redundantly)
-        Elem run = load_elem<Elem>(sd + SM::OFF_WAGG);
+        run = load_elem<Elem>(sd + SM::OFF_WAGG);
         if (lane == 0) store_elem(sd + SM::OFF_WEXCL, Tr::identity());
 #pragma unroll
         for (int w = 1; w < NWARPS; ++w) {
@@ -917,36 +960,29 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         }
         if (lane == 0) store_elem(sd + SM::OFF_TAGG, run);
         __syncwarp();
-        if (AGG_ONLY) {
-            if (lane < SM::N) ws.tile_agg[(int64_t)tile * AGG_PITCH + lane] = sd[SM::OFF_TAGG + lane];
-        } else {
-            State pref;
-            if (tile == 0) {
-                pref = Tr::initial(a);
-            } else {
-                if (lane < SM::N) {
-                    ws.tile_agg[(int64_t)tile * AGG_PITCH + lane] = sd[SM::OFF_TAGG + lane];
-                    __threadfence();
-                }
-                __syncwarp();
-                if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 1);
-                pref = lookback<Tr>(a, ws, tile, lane, run);
-            }
-            const State incl = Tr::apply(run, pref);
-            if (lane == 0) {
-                store_elem(sd + SM::OFF_TSTATE, pref);
-                store_elem(sd + SM::OFF_TINCL, incl);
-            }
+        if (lane < SM::N) ws.tile_agg[(int64_t)tile * AGG_PITCH + lane] = sd[SM::OFF_TAGG + lane];
+        if (!AGG_ONLY) {
+            if (lane < SM::N) __threadfence();
             __syncwarp();
-            if (lane < SM::SN) {
-                ws.tile_pref[(int64_t)tile * PREF_PITCH + lane] = sd[SM::OFF_TINCL + lane];
-                __threadfence();
-            }
-            __syncwarp();
-            if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 3);
+            if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 1);
         }
     }
     if (AGG_ONLY) return;
+    if (leader) {
+        const State pref = tile == 0 ? Tr::initial(a) : lookback<Tr>(a, ws, tile, lane, run);
+        const State incl = Tr::apply(run, pref);
+        if (lane == 0) {
+            store_elem(sd + SM::OFF_TSTATE, pref);
+            store_elem(sd + SM::OFF_TINCL, incl);
+        }
+        __syncwarp();
+        if (lane < SM::SN) {
+            ws.tile_pref[(int64_t)tile * PREF_PITCH + lane] = sd[SM::OFF_TINCL + lane];
+            __threadfence();
+        }
+        __syncwarp();
+        if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 3);
+    }
     cp_async_wait_all();
     __syncthreads();
     if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 2] = gtimer();
@@ -964,7 +1000,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     for (int s = 0; s < nsub; ++s) {
         if (s) {
             cp_async_wait_all();
-            __syncthreads();  // sub-step s has landed; the stores of sub-step s-1 have read their buffer
+            __syncwarp();  // sub-step s has landed; the warp's stores of sub-step s-1 have read their buffer
         }
         if (s + 1 < nsub) {
             Tr::template issue<true>(a, buf(s + 1), p0, L, s + 1, tid);
@@ -977,10 +1013,11 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
             Tr::template pass2<true>(a, buf(s) + myoff, lo, hi, q0, carry, acc0, acc1);
         else if (hi > lo)
             Tr::template pass2<false>(a, buf(s) + myoff, lo, hi, q0, carry, acc0, acc1);
-        __syncthreads();
+        __syncwarp();
         Tr::stage_out(a, buf(s), p0, L, s, tid);
     }
-    Tr::epilogue(a, tile, tid, L, carry);
+    acc1 += Tr::finish2(a, carry);
+    Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);
     if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 3] = gtimer();
 
     if (Tr::HAS_SUMS) {
@@ -1091,33 +1128,72 @@ __global__ void backward_shard_prefix_kernel(const double *aggs, int rank, int n
 }
 
 // =====================================================================================
-// residuals: resid[k][j] = data[j][k] - level[k]
+// residuals: resid[k][j] = data[j][k] - level[k]      (float32 [n][m], transposed w.r.t. data)
 // =====================================================================================
+// The reference evaluates (float)((double)z - (double)x_s) (pyx:6846-6848).  The double
+// difference of two floats is exact, so rounding it to float is the correctly rounded float
+// difference: a single FSUB gives the same bits.
+//
+// A CTA transposes RES_BINS bins x up to RES_TRACKS tracks per step through shared memory:
+// float4 loads along the bins (coalesced rows of data), scalar stores along the tracks (the
+// [bins x tracks] block of the output is contiguous when the tile spans all m tracks, and rows
+// of >= 32 floats otherwise).  Output indices advance incrementally: no per-element division.
 constexpr int RES_BINS = 128;
 constexpr int RES_TRACKS = 32;
 constexpr int RES_THREADS = 256;
+constexpr int RES_PITCH = RES_BINS + 4;  // floats; keeps float4 rows 16-byte aligned, row stride = 4 banks
 
 __global__ void __launch_bounds__(RES_THREADS)
 residual_kernel(const float *__restrict__ data, int64_t m, int64_t n, int64_t ld, const float *__restrict__ xs,
-                int dim, float *__restrict__ resid) {
-    __shared__ float tile[RES_TRACKS][RES_BINS + 1];
-    __shared__ double lvl[RES_BINS];
-    const int64_t k0 = (int64_t)blockIdx.x * RES_BINS;
-    const int64_t j0 = (int64_t)blockIdx.y * RES_TRACKS;
-    const int nb = (int)min((int64_t)RES_BINS, n - k0);
-    const int nt = (int)min((int64_t)RES_TRACKS, m - j0);
+                int dim, float *__restrict__ resid, int steps_per_cta, int vec_ok) {
+    __shared__ __align__(16) float tile[RES_TRACKS * RES_PITCH];
     const int tid = threadIdx.x;
-    if (tid < nb) lvl[tid] = (double)__ldg(xs + (k0 + tid) * dim);
-    for (int idx = tid; idx < nt * RES_BINS; idx += RES_THREADS) {
-        const int jj = idx / RES_BINS, kk = idx % RES_BINS;
-        if (kk < nb) tile[jj][kk] = __ldcs(data + (j0 + jj) * ld + k0 + kk);
-    }
-    __syncthreads();
-    const int total = nb * nt;
-    for (int idx = tid; idx < total; idx += RES_THREADS) {
-        const int kk = idx / nt, jj = idx - kk * nt;
-        const float r = (float)((double)tile[jj][kk] - lvl[kk]);
-        __stcs(resid + (k0 + kk) * m + j0 + jj, r);
+    const int64_t j0 = (int64_t)blockIdx.y * RES_TRACKS;
+    const int nt = (int)min((int64_t)RES_TRACKS, m - j0);
+    const int c = tid & 31, r0 = tid >> 5;  // column group (4 bins) and first row of this thread
+    // (dkk, djj) = RES_THREADS divmod nt: how the output position moves per store iteration
+    const int dkk = RES_THREADS / nt, djj = RES_THREADS - dkk * nt;
+    const int kk0 = tid / nt, jj0 = tid - kk0 * nt;
+    for (int st = 0; st < steps_per_cta; ++st) {
+        const int64_t k0 = ((int64_t)blockIdx.x * steps_per_cta + st) * RES_BINS;
+        if (k0 >= n) break;
+        const int nb = (int)min((int64_t)RES_BINS, n - k0);
+        // ---- load: rows of data, minus the level of each bin ----
+        float lv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int64_t k = k0 + 4 * c + i;
+            lv[i] = k < n ? __ldg(xs + k * dim) : 0.0f;
+        }
+        if (vec_ok && nb == RES_BINS) {
+            for (int jj = r0; jj < nt; jj += RES_THREADS / 32) {
+                const float4 z = __ldcs(reinterpret_cast<const float4 *>(data + (j0 + jj) * ld + k0) + c);
+                *reinterpret_cast<float4 *>(tile + jj * RES_PITCH + 4 * c) =
+                    make_float4(z.x - lv[0], z.y - lv[1], z.z - lv[2], z.w - lv[3]);
+            }
+        } else {
+            for (int jj = r0; jj < nt; jj += RES_THREADS / 32) {
+                const float *row = data + (j0 + jj) * ld + k0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * c + i < nb) tile[jj * RES_PITCH + 4 * c + i] = __ldcs(row + 4 * c + i) - lv[i];
+            }
+        }
+        __syncthreads();
+        // ---- store: walk the [nb][nt] output block in memory order ----
+        const int total = nb * nt;
+        int kk = kk0, jj = jj0;
+        float *out = resid + k0 * m + j0;
+        for (int idx = tid; idx < total; idx += RES_THREADS) {
+            __stcs(out + (int64_t)kk * m + jj, tile[jj * RES_PITCH + kk]);
+            kk += dkk;
+            jj += djj;
+            if (jj >= nt) {
+                jj -= nt;
+                kk += 1;
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -1162,11 +1238,14 @@ __global__ void kappa1_kernel(double q0inv, int64_t n, const float *__restrict__
                                       (double)lag[k], q, qs != nullptr, nu, lo, hi);
 }
 
+static int g_slots[4] = {0, 0, 0, 0};  // Fwd2, Fwd1, Bwd2, Bwd1 tiles in flight
+
 template <class Tr, bool AGG_ONLY>
 cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int64_t positions, int nsub,
-                        cudaStream_t st, int *launches) {
+                        int slots, cudaStream_t st, int *launches) {
     const int ntiles = (int)scan_num_tiles(positions, nsub);
     if (ntiles <= 0) return cudaSuccess;
+    (void)slots;
     scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
@@ -1220,7 +1299,7 @@ static size_t ws_tiles(int64_t n) { return (size_t)scan_num_tiles(n + CHUNK, 1) 
 size_t scan_workspace_bytes(int64_t n) {
     const size_t t = ws_tiles(n);
     return 2 * align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
-           align_up((t + 2) * 4, 256);
+           align_up((t + 4) * 4, 256);
 }
 
 ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
@@ -1240,7 +1319,7 @@ ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
     return ws;
 }
 
-static int g_slots[4] = {0, 0, 0, 0};  // Fwd2, Fwd1, Bwd2, Bwd1 tiles in flight
+
 static int g_nsub_override = 0;
 
 cudaError_t configure_kernels() {
@@ -1262,25 +1341,18 @@ cudaError_t configure_kernels() {
 
 void scan_set_nsub_override(int nsub) { g_nsub_override = nsub < 0 ? 0 : nsub; }
 
-// Sub-steps per run.  Longer runs amortise the warp scan and the look-back; the choice also
-// has to keep the last wave of tiles reasonably full.  which: 0 Fwd2, 1 Fwd1, 2 Bwd2, 3 Bwd1.
+// Sub-steps per run.  Longer runs amortise the warp scan and the look-back (fewer, longer tiles
+// also shorten the walk back to a published prefix), but the tiles must still cover the machine:
+// measured on B200 (chr19 @ 25 bp, 592 resident tiles) the scans run fastest with the longest
+// runs that leave about half of the tile slots filled.  which: 0 Fwd2, 1 Fwd1, 2 Bwd2, 3 Bwd1.
 int scan_pick_nsub(int64_t positions, int which) {
     if (g_nsub_override > 0) return g_nsub_override > MAX_NSUB ? MAX_NSUB : g_nsub_override;
-    const int slots = g_slots[which] > 0 ? g_slots[which] : 444;
-    int best = 1;
-    double best_score = -1.0;
-    for (int ns = 1; ns <= MAX_NSUB; ++ns) {
-        const int64_t tiles = scan_num_tiles(positions, ns);
-        const int64_t waves = (tiles + slots - 1) / slots;
-        const double fill = (double)tiles / (double)(waves * slots);  // occupancy of the tile slots
-        // per-position overhead of the scan stages shrinks as 1 / ns
-        const double score = fill / (1.0 + 1.8 / ns);
-        if (score > best_score + 1e-9) {
-            best_score = score;
-            best = ns;
-        }
-    }
-    return best;
+    const int slots = g_slots[which] > 0 ? g_slots[which] : 592;
+    const int64_t want_tiles = (int64_t)(0.45 * slots) + 1;
+    int64_t ns = positions / (TILE_BINS * want_tiles);
+    if (ns < 1) ns = 1;
+    if (ns > MAX_NSUB) ns = MAX_NSUB;
+    return (int)ns;
 }
 
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
@@ -1299,19 +1371,23 @@ cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t
     return cudaGetLastError();
 }
 
-cudaError_t launch_forward(int dim, const FwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
+cudaError_t launch_forward(int dim, const FwdArgs &a_in, const ScanWorkspace &ws, bool aggregate_only,
                            cudaStream_t st, int *launches) {
     if (dim == 2) {
-        const int ns = scan_pick_nsub(a.n, 0);
+        const int ns = scan_pick_nsub(a_in.n, 0);
+        FwdArgs a = a_in;
+        a.head_from = (a.init_state == nullptr && !aggregate_only) ? CHUNK * ns : HEAD_BINS;
         if (canonical_F(a.M))
-            return aggregate_only ? launch_scan<Fwd2<true>, true>(a, ws, a.n, ns, st, launches)
-                                  : launch_scan<Fwd2<true>, false>(a, ws, a.n, ns, st, launches);
-        return aggregate_only ? launch_scan<Fwd2<false>, true>(a, ws, a.n, ns, st, launches)
-                              : launch_scan<Fwd2<false>, false>(a, ws, a.n, ns, st, launches);
+            return aggregate_only ? launch_scan<Fwd2<true>, true>(a, ws, a.n, ns, g_slots[0], st, launches)
+                                  : launch_scan<Fwd2<true>, false>(a, ws, a.n, ns, g_slots[0], st, launches);
+        return aggregate_only ? launch_scan<Fwd2<false>, true>(a, ws, a.n, ns, g_slots[0], st, launches)
+                              : launch_scan<Fwd2<false>, false>(a, ws, a.n, ns, g_slots[0], st, launches);
     }
+    FwdArgs a = a_in;
+    a.head_from = HEAD_BINS;
     const int ns = scan_pick_nsub(a.n, 1);
-    return aggregate_only ? launch_scan<Fwd1, true>(a, ws, a.n, ns, st, launches)
-                          : launch_scan<Fwd1, false>(a, ws, a.n, ns, st, launches);
+    return aggregate_only ? launch_scan<Fwd1, true>(a, ws, a.n, ns, g_slots[1], st, launches)
+                          : launch_scan<Fwd1, false>(a, ws, a.n, ns, g_slots[1], st, launches);
 }
 
 cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
@@ -1320,14 +1396,14 @@ cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, 
     if (dim == 2) {
         const int ns = scan_pick_nsub(positions, 2);
         if (canonical_F(a.M))
-            return aggregate_only ? launch_scan<Bwd2<true>, true>(a, ws, positions, ns, st, launches)
-                                  : launch_scan<Bwd2<true>, false>(a, ws, positions, ns, st, launches);
-        return aggregate_only ? launch_scan<Bwd2<false>, true>(a, ws, positions, ns, st, launches)
-                              : launch_scan<Bwd2<false>, false>(a, ws, positions, ns, st, launches);
+            return aggregate_only ? launch_scan<Bwd2<true>, true>(a, ws, positions, ns, g_slots[2], st, launches)
+                                  : launch_scan<Bwd2<true>, false>(a, ws, positions, ns, g_slots[2], st, launches);
+        return aggregate_only ? launch_scan<Bwd2<false>, true>(a, ws, positions, ns, g_slots[2], st, launches)
+                              : launch_scan<Bwd2<false>, false>(a, ws, positions, ns, g_slots[2], st, launches);
     }
     const int ns = scan_pick_nsub(positions, 3);
-    return aggregate_only ? launch_scan<Bwd1, true>(a, ws, positions, ns, st, launches)
-                          : launch_scan<Bwd1, false>(a, ws, positions, ns, st, launches);
+    return aggregate_only ? launch_scan<Bwd1, true>(a, ws, positions, ns, g_slots[3], st, launches)
+                          : launch_scan<Bwd1, false>(a, ws, positions, ns, g_slots[3], st, launches);
 }
 
 cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
@@ -1335,8 +1411,12 @@ cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld
     if (n <= 0 || m <= 0) return cudaSuccess;
     const int64_t gy = (m + RES_TRACKS - 1) / RES_TRACKS;
     if (gy > 65535) return cudaErrorInvalidValue;
-    dim3 grid((unsigned)((n + RES_BINS - 1) / RES_BINS), (unsigned)gy);
-    residual_kernel<<<grid, RES_THREADS, 0, st>>>(data, m, n, ld, xs, dim, resid);
+    // few tracks: a CTA walks several bin blocks so that it has enough work per launch slot
+    const int steps = m <= 8 ? 8 : (m <= 16 ? 4 : (m <= 32 ? 2 : 1));
+    const int64_t blocks = (n + RES_BINS - 1) / RES_BINS;
+    const int vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
+    dim3 grid((unsigned)((blocks + steps - 1) / steps), (unsigned)gy);
+    residual_kernel<<<grid, RES_THREADS, 0, st>>>(data, m, n, ld, xs, dim, resid, steps, vec_ok);
     return cudaGetLastError();
 }
 

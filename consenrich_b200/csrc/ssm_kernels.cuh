@@ -49,6 +49,7 @@ struct FwdArgs {
     double state_init, cov_init;
     double lam_min, lam_max, kap_min, kap_max;
     int32_t use_lambda, use_kappa, use_qscale, want_nll, nll_in_d, do_store;
+    int32_t head_from;         // 2-state: bins [head_from, HEAD_BINS) belong to the head replay (set at launch)
 };
 
 struct BwdArgs {
