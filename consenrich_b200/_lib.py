@@ -82,6 +82,8 @@ SIGNATURES = {
     "cb200_copy_d2h": (C.c_int, [_vp, _vp, _sz, _vp, _sz, _sz, _sz]),
     "cb200_fold_tracks": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _dbl, _vp, _i64]),
     "cb200_forward_scan": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "cb200_forward_scan_shard": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                           _vp]),
     "cb200_forward_shard_aggregate": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cb200_forward_shard_prefix": (C.c_int, [_vp, _pm, _vp, _i32, _vp]),
     "cb200_backward_scan": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),

@@ -213,7 +213,7 @@ int do_fold(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64
 
 int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stride, int64_t m, int64_t n,
                const float *lam, const float *kap, const float *qs, const double *init_state, float *xf, float *Pf,
-               float *Qf, float *D, double *sums, double *agg_out, bool aggregate_only) {
+               float *Qf, float *D, double *sums, double *agg_out, bool aggregate_only, float *q_head = nullptr) {
     const int d = mo->state_dim;
     const bool store = (xf != nullptr);
     if (store && (!Pf || !Qf)) return fail(CB200_ERR_INVALID, "xf, Pf and Qf must be given together");
@@ -230,6 +230,7 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     a.lam = lam; a.kap = kap; a.qs = qs;
     a.init_state = init_state;
     a.xf = xf; a.Pf = Pf; a.Qf = Qf; a.D = D;
+    a.q_head = q_head;
     a.sums = sums;
     a.agg_out = agg_out;
     a.n = n;
@@ -550,6 +551,17 @@ int cb200_forward_scan(cb200_ctx *c, const cb200_model *mo, const double *stats,
     if (n <= 0) return CB200_OK;
     return do_forward(c, mo, stats, stat_stride, m, n, lam, kap, qscale, init_state, xf, Pf, Qf, D, sums, nullptr,
                       false);
+}
+
+int cb200_forward_scan_shard(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride, int64_t m,
+                             int64_t n, const float *lam, const float *kap, const float *qscale,
+                             const double *init_state, float *xf, float *Pf, float *Qf, float *D, double *sums,
+                             float *q_head) {
+    if (!c || !stats) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return fail(CB200_ERR_INVALID, "a shard must hold at least one interval");
+    return do_forward(c, mo, stats, stat_stride, m, n, lam, kap, qscale, init_state, xf, Pf, Qf, D, sums, nullptr,
+                      false, q_head);
 }
 
 int cb200_forward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride,

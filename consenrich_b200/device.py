@@ -63,7 +63,7 @@ class TrackSweep:
         self.D = torch.empty(n, dtype=f32, device=self.dev)
         self.xs = torch.empty((n, d), dtype=f32, device=self.dev)
         self.Ps = torch.empty((n, d, d), dtype=f32, device=self.dev)
-        self.lag = torch.empty((max(n - 1, 1), d, d), dtype=f32, device=self.dev)
+        self.lag = torch.empty((n, d, d), dtype=f32, device=self.dev)  # row n-1 is used by a non-final shard only
         self.resid = torch.empty((n, self.m), dtype=f32, device=self.dev) if residuals else None
         self.sums = torch.zeros(2, dtype=f64, device=self.dev)
 

@@ -152,6 +152,14 @@ CB200_API int cb200_forward_scan(cb200_ctx *ctx, const cb200_model *model, const
                        const float *qscale, const double *init_state, float *xf, float *Pf, float *Qf,
                        float *D, double *sums);
 
+/* Same as cb200_forward_scan for a shard of a split chromosome: q_head (device float[d*d], or NULL)
+ * receives Q of the shard's FIRST interval, which the reference stores in row n-1 of the PRECEDING
+ * shard's pNoiseForward (Q_k lives at row k-1) and which that shard's smoother needs. */
+CB200_API int cb200_forward_scan_shard(cb200_ctx *ctx, const cb200_model *model, const double *stats,
+                             int64_t stat_stride, int64_t m, int64_t n, const float *lam, const float *kap,
+                             const float *qscale, const double *init_state, float *xf, float *Pf,
+                             float *Qf, float *D, double *sums, float *q_head);
+
 /* Aggregate filtering element of a whole shard (14 doubles for d = 2: A, b, C, eta, J; 5 for
  * d = 1), the only thing ranks exchange when a chromosome is split into contiguous ranges. */
 CB200_API int cb200_forward_shard_aggregate(cb200_ctx *ctx, const cb200_model *model, const double *stats,

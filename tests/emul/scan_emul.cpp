@@ -57,13 +57,15 @@ struct emul_params {
     uint64_t seed;               // randomises the look-back window lengths
 };
 
-extern "C" {
+namespace {
 
 // 2-state forward filter from fold statistics.  Outputs as the reference (Qf[k-1] = Q_k).
-void emul_forward2(const double *S0, const double *S1, const double *S2, const double *SL, int64_t m,
+// init5 (x0, x1, P00, P01, P11) replaces the model prior for a shard that continues a chromosome;
+// q_head receives Q of the first bin in that case.
+void forward2_impl(const double *S0, const double *S1, const double *S2, const double *SL, int64_t m,
                    int64_t n, const float *lam, const float *kap, const float *qscale,
                    const emul_params *p, float *D, float *xf, float *Pf, float *Qf, double *sum_d,
-                   double *sum_nll) {
+                   double *sum_nll, const double *init5, float *q_head) {
     Model2 M{p->F[0], p->F[1], p->F[2], p->F[3], p->Q0[0], p->Q0[1], p->Q0[2], p->Q0[3]};
     const int64_t L = p->chunk, T = p->tile_chunks;
     const int64_t nchunks = (n + L - 1) / L, ntiles = (nchunks + T - 1) / T;
@@ -99,7 +101,8 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
     }
     // look-back: tile prefix states
     std::vector<State2> tile_prefix(ntiles + 1);
-    tile_prefix[0] = State2{p->state_init, 0.0, p->cov_init, 0.0, p->cov_init};
+    tile_prefix[0] = init5 ? State2{init5[0], init5[1], init5[2], init5[3], init5[4]}
+                           : State2{p->state_init, 0.0, p->cov_init, 0.0, p->cov_init};
     Lcg rng{p->seed | 1};
     for (int64_t t = 1; t <= ntiles; ++t) {
         // exclusive prefix of tile t = prefix(t - w) (x) agg[t-w .. t-1], random window w
@@ -121,12 +124,12 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
         State2 s0 = tile_prefix[t];
         if (i > 0) s0 = filt2_apply(incl[t][i - 1], s0);
         Kf2 s{s0.x0, s0.x1, s0.P00, s0.P01, s0.P01, s0.P11};
-        if (c > 0) {  // the reference carries float32-rounded values between bins
+        if (c > 0 || init5) {  // the reference carries float32-rounded values between bins
             s.x0 = r32(s.x0); s.x1 = r32(s.x1);
             s.P00 = r32(s.P00); s.P01 = r32(s.P01); s.P10 = s.P01; s.P11 = r32(s.P11);
         }
         // head replay: runs that start inside the first 16 bins continue the first run's replay
-        if (c > 0 && c * L < 16) s = head_carry;
+        if (c > 0 && c * L < 16 && !init5) s = head_carry;
         NllAcc acc;
         nll_acc_init(acc);
         for (int64_t k = c * L; k < n && k < (c + 1) * L; ++k) {
@@ -147,12 +150,61 @@ void emul_forward2(const double *S0, const double *S1, const double *S2, const d
                 if (k > 0) {
                     Qf[(k - 1) * 4] = (float)o.Q00; Qf[(k - 1) * 4 + 1] = (float)o.Q01;
                     Qf[(k - 1) * 4 + 2] = (float)o.Q10; Qf[(k - 1) * 4 + 3] = (float)o.Q11;
+                } else if (q_head) {
+                    q_head[0] = (float)o.Q00; q_head[1] = (float)o.Q01;
+                    q_head[2] = (float)o.Q10; q_head[3] = (float)o.Q11;
                 }
             }
         }
         if (p->return_nll && !p->store_nll_in_d) *sum_nll += nll_acc_finish(acc, (double)m, mlog2pi);
         head_carry = s;
     }
+}
+
+}  // namespace
+
+extern "C" {
+
+void emul_forward2(const double *S0, const double *S1, const double *S2, const double *SL, int64_t m,
+                   int64_t n, const float *lam, const float *kap, const float *qscale,
+                   const emul_params *p, float *D, float *xf, float *Pf, float *Qf, double *sum_d,
+                   double *sum_nll) {
+    forward2_impl(S0, S1, S2, SL, m, n, lam, kap, qscale, p, D, xf, Pf, Qf, sum_d, sum_nll, nullptr, nullptr);
+}
+
+// ---- shards of a split chromosome (what the cb200_*_shard_* entry points compute) -------------
+void emul_forward2_shard(const double *S0, const double *S1, const double *S2, const double *SL, int64_t m,
+                         int64_t n, const float *lam, const float *kap, const float *qscale,
+                         const emul_params *p, float *D, float *xf, float *Pf, float *Qf, double *sum_d,
+                         double *sum_nll, const double *init5, float *q_head) {
+    forward2_impl(S0, S1, S2, SL, m, n, lam, kap, qscale, p, D, xf, Pf, Qf, sum_d, sum_nll, init5, q_head);
+}
+
+// filtering element of a whole range: 14 doubles in the field order of Filt2
+void emul_forward2_aggregate(const double *S0, const double *S1, int64_t n, const float *lam, const float *kap,
+                             const float *qscale, const emul_params *p, double *agg) {
+    Model2 M{p->F[0], p->F[1], p->F[2], p->F[3], p->Q0[0], p->Q0[1], p->Q0[2], p->Q0[3]};
+    Filt2 g = filt2_identity();
+    for (int64_t k = 0; k < n; ++k) {
+        const double kappa = p->use_kappa ? clampd((double)kap[k], p->kap_min, p->kap_max) : 1.0;
+        const double qk = (p->use_qscale ? (double)qscale[k] : 1.0) / kappa;
+        const double l = p->use_lambda ? clampd((double)lam[k], p->lam_min, p->lam_max) : 1.0;
+        filt2_step<true>(g, M, qk * M.q00, qk * M.q01, qk * M.q11, l * S0[k], l * S1[k]);
+    }
+    const double *src = reinterpret_cast<const double *>(&g);
+    for (int i = 0; i < 14; ++i) agg[i] = src[i];
+}
+
+// prior pushed through the aggregates of shards 0..rank-1 (16-double pitch) -> init5
+void emul_forward2_prefix(const double *aggs, int rank, const emul_params *p, double *init5) {
+    State2 s{p->state_init, 0.0, p->cov_init, 0.0, p->cov_init};
+    for (int r = 0; r < rank; ++r) {
+        Filt2 g;
+        double *dst = reinterpret_cast<double *>(&g);
+        for (int i = 0; i < 14; ++i) dst[i] = aggs[r * 16 + i];
+        s = filt2_apply(g, s);
+    }
+    init5[0] = s.x0; init5[1] = s.x1; init5[2] = s.P00; init5[3] = s.P01; init5[4] = s.P11;
 }
 
 void emul_forward1(const double *S0, const double *S1, const double *S2, const double *SL, int64_t m,
@@ -225,15 +277,23 @@ void emul_forward1(const double *S0, const double *S1, const double *S2, const d
     }
 }
 
-// 2-state RTS smoother as a reverse scan.  Position p = n-1-k runs forward.
-void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf, const float *Qf,
-                    const emul_params *p, float *xs, float *Ps, float *lagC, int64_t lag_rows) {
+}  // extern "C"
+
+namespace {
+
+// 2-state RTS smoother as a reverse scan.  Position p = n-1-k runs forward.  tail5 = smoothed
+// (x, P) of the first bin of the FOLLOWING shard (then row n-1 of Qf is live), or null.
+void backward2_impl(int64_t n, const double *F, const float *xf, const float *Pf, const float *Qf,
+                    const emul_params *p, float *xs, float *Ps, float *lagC, int64_t lag_rows,
+                    const double *tail5) {
     if (n <= 0) return;
+    const bool last = tail5 == nullptr;
     Model2 M{F[0], F[1], F[2], F[3], 0, 0, 0, 0};
     const int64_t L = p->chunk, T = p->tile_chunks;
     const int64_t nchunks = (n + L - 1) / L, ntiles = (nchunks + T - 1) / T;
     auto elem_of = [&](int64_t k) {
-        if (k == n - 1) return smo2_from_state(State2{xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3]});
+        if (k == n - 1 && last)
+            return smo2_from_state(State2{xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3]});
         Rts2 r = p->canon ? rts2_gain<true>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
                                             Pf[k * 4 + 3], Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3])
                           : rts2_gain<false>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
@@ -255,7 +315,8 @@ void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf
         tile_agg[t] = incl[t].back();
     }
     std::vector<State2> tile_prefix(ntiles + 1);
-    tile_prefix[0] = State2{0, 0, 0, 0, 0};  // irrelevant: bin n-1's element ignores it
+    tile_prefix[0] = last ? State2{0, 0, 0, 0, 0}  // irrelevant: bin n-1's element ignores it
+                          : State2{tail5[0], tail5[1], tail5[2], tail5[3], tail5[4]};
     Lcg rng{p->seed | 1};
     for (int64_t t = 1; t <= ntiles; ++t) {
         int64_t w = 1 + (int64_t)(rng.next() % 40);
@@ -273,7 +334,7 @@ void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf
         Rs2 cy{r32(s0.x0), r32(s0.x1), r32(s0.P00), r32(s0.P01), r32(s0.P01), r32(s0.P11)};
         for (int64_t q = c * L; q < n && q < (c + 1) * L; ++q) {
             int64_t k = n - 1 - q;
-            if (k == n - 1) {
+            if (k == n - 1 && last) {
                 for (int e = 0; e < 2; ++e) xs[k * 2 + e] = xf[k * 2 + e];
                 for (int e = 0; e < 4; ++e) Ps[k * 4 + e] = Pf[k * 4 + e];
                 cy = Rs2{xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2], Pf[k * 4 + 3]};
@@ -294,6 +355,53 @@ void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf
             }
         }
     }
+}
+
+}  // namespace
+
+extern "C" {
+
+void emul_backward2(int64_t n, const double *F, const float *xf, const float *Pf, const float *Qf,
+                    const emul_params *p, float *xs, float *Ps, float *lagC, int64_t lag_rows) {
+    backward2_impl(n, F, xf, Pf, Qf, p, xs, Ps, lagC, lag_rows, nullptr);
+}
+
+void emul_backward2_shard(int64_t n, const double *F, const float *xf, const float *Pf, const float *Qf,
+                          const emul_params *p, float *xs, float *Ps, float *lagC, int64_t lag_rows,
+                          const double *tail5) {
+    backward2_impl(n, F, xf, Pf, Qf, p, xs, Ps, lagC, lag_rows, tail5);
+}
+
+// smoothing element of a whole range: 9 doubles in the field order of Smo2
+void emul_backward2_aggregate(int64_t n, const double *F, const float *xf, const float *Pf, const float *Qf,
+                              int is_last, double *agg) {
+    Model2 M{F[0], F[1], F[2], F[3], 0, 0, 0, 0};
+    Smo2 g = smo2_identity();
+    for (int64_t k = n - 1; k >= 0; --k) {
+        Smo2 e;
+        if (k == n - 1 && is_last) {
+            e = smo2_from_state(State2{xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3]});
+        } else {
+            Rts2 r = rts2_gain<true>(M, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 2],
+                                     Pf[k * 4 + 3], Qf[k * 4], Qf[k * 4 + 1], Qf[k * 4 + 2], Qf[k * 4 + 3]);
+            e = smo2_from_rts(r, xf[k * 2], xf[k * 2 + 1], Pf[k * 4], Pf[k * 4 + 1], Pf[k * 4 + 3]);
+        }
+        g = smo2_combine(g, e);
+    }
+    const double *src = reinterpret_cast<const double *>(&g);
+    for (int i = 0; i < 9; ++i) agg[i] = src[i];
+}
+
+// tail state of shard `rank`: the aggregates of the shards after it, applied from the end
+void emul_backward2_prefix(const double *aggs, int rank, int n_shards, double *tail5) {
+    State2 s{0, 0, 0, 0, 0};
+    for (int r = n_shards - 1; r > rank; --r) {
+        Smo2 g;
+        double *dst = reinterpret_cast<double *>(&g);
+        for (int i = 0; i < 9; ++i) dst[i] = aggs[r * 16 + i];
+        s = smo2_apply(g, s);
+    }
+    tail5[0] = s.x0; tail5[1] = s.x1; tail5[2] = s.P00; tail5[3] = s.P01; tail5[4] = s.P11;
 }
 
 void emul_backward1(int64_t n, const float *xf, const float *Pf, const float *Qf, const emul_params *p,

@@ -1,0 +1,62 @@
+"""A chromosome split into contiguous bin ranges: the shard entry points of the C ABI
+(aggregate -> gathered prefix -> scan with a carried state, and the mirror image for the smoother)
+must reproduce the unsharded sweep.  All shards run on ONE GPU, one after the other
+(consenrich_b200.sharding.run_split_local); the multi-process plumbing is covered on the CPU by
+tests/test_sharding_host.py."""
+import numpy as np
+import pytest
+
+from conftest import synth_tracks
+from parity_util import assert_sweep_tracks_close
+from test_gpu_parity import Q0, F, _sweep, _weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+@pytest.mark.parametrize("shards,n", [(2, 40_000), (3, 100_003), (5, 7_777)])
+def test_split_chromosome_matches_unsharded_oracle(oracle, dim, shards, n):
+    import torch
+
+    from consenrich_b200 import sharding
+    from consenrich_b200.device import TrackSweep, make_model
+
+    m = 6
+    data, munc = synth_tracks(77 + n, m, n, masked_frac=0.02)
+    lam, kap, qs = _weights(np.random.default_rng(n), n)
+    want = _sweep(oracle, dim, data, munc, lam, kap, qs)
+
+    dev = torch.device("cuda", 0)
+    model = make_model(dim, F, Q0, 0.25, 1000.0, 1e-4, lam_bounds=(0.25, 4.0), kap_bounds=(5e-3, 5e3),
+                       return_nll=True, use_lambda=True, use_kappa=True, use_qscale=True)
+    ranges = sharding.split_ranges(n, shards, align=512)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n and all(a < b for a, b in ranges)
+    backends = []
+    for a, b in ranges:
+        nb = b - a
+        ld = (nb + 31) // 32 * 32
+        d_dev = torch.zeros((m, ld), dtype=torch.float32, device=dev)
+        v_dev = torch.ones((m, ld), dtype=torch.float32, device=dev)
+        d_dev[:, :nb] = torch.from_numpy(data[:, a:b]).to(dev)
+        v_dev[:, :nb] = torch.from_numpy(munc[:, a:b]).to(dev)
+        vec = lambda x: torch.from_numpy(np.ascontiguousarray(x[a:b])).to(dev)
+        ts = TrackSweep(m, nb, dim, 0, residuals=True)
+        backends.append(sharding.DeviceShard(ts, model, d_dev, v_dev, ld, vec(lam), vec(kap), vec(qs)))
+    sums = sharding.run_split_local(backends).cpu().numpy()
+    torch.cuda.synchronize()
+
+    cat = lambda name: np.concatenate([getattr(b.ts, name).cpu().numpy() for b in backends])
+    got = dict(xf=cat("xf"), Pf=cat("Pf"), D=cat("D"), xs=cat("xs"), Ps=cat("Ps"), res=cat("resid"))
+    Qf = cat("Qf")
+    lag = cat("lag")  # every shard holds n_local rows; row n-1 of the last one does not exist
+    close = assert_sweep_tracks_close
+    close(got["xf"], want["xf"], "stateForward")
+    close(got["Pf"], want["Pf"], "stateCovarForward", scale="component")
+    np.testing.assert_array_equal(Qf[: n - 1], want["Qf"][: n - 1])
+    close(got["D"], want["D"], "vectorD")
+    close(got["xs"], want["xs"], "stateSmoothed")
+    close(got["Ps"], want["Ps"], "stateCovarSmoothed", scale="component")
+    close(lag[: n - 1], want["lag"], "lagCovSmoothed", scale="component")
+    close(got["res"], want["res"], "postFitResiduals")
+    assert abs(sums[1] - want["nll"]) <= 2e-6 * abs(want["nll"])
+    assert abs(np.float32(sums[0] / n) - want["phi"]) <= 1e-4 * max(abs(want["phi"]), 1e-3)
