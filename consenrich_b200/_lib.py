@@ -193,6 +193,60 @@ class Context:
         return out
 
 
+# ------------------------------------------------------------------------------------------
+# pinned result arrays
+# ------------------------------------------------------------------------------------------
+# The arrays the drop-in functions hand back are allocated in page-locked host memory, so that the
+# device -> host copy lands in them directly at full PCIe rate (a pageable destination is staged
+# through a bounce buffer by the driver at a fraction of that).  Blocks are recycled through a
+# small pool when the numpy array that wraps them is garbage collected: cudaHostAlloc is far too
+# slow to call per result.
+_pin_pool: dict = {}
+_pin_lock = threading.Lock()
+_PIN_MIN = 1 << 16        # smaller results stay ordinary numpy arrays
+_PIN_POOL_CAP = 8 << 30   # bytes kept for reuse
+
+
+class _PinnedBlock:
+    __slots__ = ("ptr", "nbytes", "__weakref__")
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def __del__(self):
+        try:
+            with _pin_lock:
+                held = sum(k * len(v) for k, v in _pin_pool.items())
+                if held + self.nbytes <= _PIN_POOL_CAP:
+                    _pin_pool.setdefault(self.nbytes, []).append(self.ptr)
+                    return
+            load().cb200_pinned_free(_vp(self.ptr))
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype):
+    """numpy array in page-locked memory (falls back to numpy.empty for small results)."""
+    import numpy as np
+    dt = np.dtype(dtype)
+    count = int(np.prod(shape)) if len(shape) else 1
+    nbytes = count * dt.itemsize
+    if nbytes < _PIN_MIN:
+        return np.empty(shape, dt)
+    size = 1 << (nbytes - 1).bit_length() if nbytes < (1 << 24) else (nbytes + (1 << 22) - 1) >> 22 << 22
+    with _pin_lock:
+        free = _pin_pool.get(size)
+        ptr = free.pop() if free else None
+    if ptr is None:
+        p = _vp()
+        check(load().cb200_pinned_alloc(size, C.byref(p)))
+        ptr = p.value
+    block = _PinnedBlock(ptr, size)
+    buf = (C.c_char * nbytes).from_address(ptr)
+    buf._cb200_block = block  # the block lives exactly as long as the buffer numpy keeps as its base
+    return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
+
+
 _default_ctx: dict = {}
 
 

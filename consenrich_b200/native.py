@@ -215,10 +215,11 @@ def _backward(dim, matrixData, matrixF, stateForward, stateCovarForward, pNoiseF
               stateCovarSmoothed, lagCovSmoothed, postFitResiduals):
     data = _c32(matrixData, "matrixData", 2)
     m, n = data.shape
-    xs = stateSmoothed if stateSmoothed is not None else np.empty((n, dim), dtype=np.float32)
-    Ps = stateCovarSmoothed if stateCovarSmoothed is not None else np.empty((n, dim, dim), dtype=np.float32)
-    lag = lagCovSmoothed if lagCovSmoothed is not None else np.empty((max(n - 1, 1), dim, dim), dtype=np.float32)
-    res = postFitResiduals if postFitResiduals is not None else np.empty((n, m), dtype=np.float32)
+    alloc = _lib.pinned_empty if n > 0 else np.empty
+    xs = stateSmoothed if stateSmoothed is not None else alloc((n, dim), np.float32)
+    Ps = stateCovarSmoothed if stateCovarSmoothed is not None else alloc((n, dim, dim), np.float32)
+    lag = lagCovSmoothed if lagCovSmoothed is not None else alloc((max(n - 1, 1), dim, dim), np.float32)
+    res = postFitResiduals if postFitResiduals is not None else alloc((n, m), np.float32)
     if n <= 0:
         return (xs, Ps, lag, res)
     xf = _c32(stateForward, "stateForward", 2)
@@ -321,10 +322,8 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     if useProc and ((not useAPN) or use_qscale):
         kap = _init_multiplier(processPrecExpInit, n, kapMin, kapMax, "processPrecExpInit")
     qs = _coerce_qscale(processQScale, n) if use_qscale else None
-    xs = np.empty((n, dim), np.float32)
-    Ps = np.empty((n, dim, dim), np.float32)
-    lag = np.empty((max(n - 1, 1), dim, dim), np.float32)
-    res = np.empty((n, m), np.float32)
+    want = bool(returnIntermediates) and n > 0 and m > 0
+    xs = Ps = lag = res = None  # allocated after validation (page-locked: the copy engine writes them)
     Q0 = np.asarray(matrixQ0)
     patience = 2
     path = [] if trackOptimizationPath else None
@@ -336,6 +335,8 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
         return (iters_done, float(nll), diag) if returnDiagnostics else (iters_done, float(nll))
 
     if n <= 0 or m <= 0:
+        xs, Ps = np.empty((n, dim), np.float32), np.empty((n, dim, dim), np.float32)
+        lag, res = np.empty((max(n - 1, 1), dim, dim), np.float32), np.empty((n, m), np.float32)
         diag = {"iters_done": 0, "max_iters": int(iters), "converged": False, "skipped": True,
                 "skip_reason": "too_few_intervals" if n > 0 else "empty_input", "fallback": "filter_smoother_only",
                 "stable_iters": 0, "patience_target": patience, "initial_nll": 0.0, "final_nll": 0.0,
@@ -364,6 +365,9 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     if _apn_live(useAPN, use_qscale, Q0, dim):
         raise NotImplementedError(_APN_MSG)
 
+    alloc = _lib.pinned_empty if want else np.empty
+    xs, Ps = alloc((n, dim), np.float32), alloc((n, dim, dim), np.float32)
+    lag, res = alloc((max(n - 1, 1), dim, dim), np.float32), alloc((n, m), np.float32)
     mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin_d, lamMax_d, kapMin_d, kapMax_d,
                 lam is not None, kap is not None, use_qscale, True, False)
     op = _lib.EcmOpts()
@@ -374,7 +378,6 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     result = _lib.EcmResult()
     nll_path = np.zeros(max(int(iters), 1), np.float64)
     ctx = _ctx()
-    want = bool(returnIntermediates)
     _lib.check(ctx._lib.cb200_host_ecm(
         ctx.handle, C.byref(mo), C.byref(op), _ptr(data), _ptr(munc), m, n, _ptr(bm), int(blockCount), _ptr(qs),
         _ptr(lam), _ptr(kap), _ptr(xs) if want else None, _ptr(Ps) if want else None, _ptr(lag) if want else None,
