@@ -373,8 +373,8 @@ def run_b200_arm(args):
         return cb.cfixedBackgroundECM(**kw)
 
     e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    for _ in range(3):  # keeps two generations of page-locked result arrays alive, as the timed loop does
+        r = e2e_step()
     hctx = _lib.default_context(local)
     hl0 = hctx.launch_count
     barrier()

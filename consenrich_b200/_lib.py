@@ -63,6 +63,7 @@ _pm, _po, _pr = C.POINTER(Model), C.POINTER(EcmOpts), C.POINTER(EcmResult)
 # name -> (restype, argtypes); one entry per declaration in include/consenrich_b200.h
 SIGNATURES = {
     "cb200_abi_version": (C.c_int, []),
+    "cb200_current_device": (C.c_int, [C.POINTER(C.c_int)]),
     "cb200_ctx_create": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
     "cb200_ctx_destroy": (None, [_vp]),
     "cb200_ctx_set_stream": (C.c_int, [_vp, _vp]),
@@ -250,8 +251,17 @@ def pinned_empty(shape, dtype):
 _default_ctx: dict = {}
 
 
-def default_context(device: int = 0) -> Context:
-    """Process-wide context per device, used by the drop-in functions."""
+def current_device() -> int:
+    d = C.c_int(0)
+    check(load().cb200_current_device(C.byref(d)))
+    return int(d.value)
+
+
+def default_context(device: int | None = None) -> Context:
+    """Process-wide context per device, used by the drop-in functions; the device defaults to the one
+    the calling thread has selected (cudaGetDevice), i.e. the rank's GPU under torchrun."""
+    if device is None:
+        device = current_device()
     ctx = _default_ctx.get(device)
     if ctx is None:
         ctx = Context(device)

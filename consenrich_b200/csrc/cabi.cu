@@ -46,6 +46,20 @@ int fail(int code, const char *fmt, ...) {
         if (_rc != CB200_OK) return _rc; \
     } while (0)
 
+// Entry points run on the context's device whatever device the calling thread had selected
+// (one process per GPU under torchrun: rank r's thread sits on device r), and hand the
+// thread's selection back on return.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+};
+
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -352,6 +366,12 @@ extern "C" {
 
 int cb200_abi_version(void) { return CB200_ABI_VERSION; }
 
+int cb200_current_device(int *device) {
+    if (!device) return fail(CB200_ERR_INVALID, "device is NULL");
+    CU_TRY(cudaGetDevice(device));
+    return CB200_OK;
+}
+
 const char *cb200_last_error(void) { return g_err.c_str(); }
 
 int cb200_ctx_create(int device, void *stream, cb200_ctx **out) {
@@ -363,7 +383,7 @@ int cb200_ctx_create(int device, void *stream, cb200_ctx **out) {
         return fail(CB200_ERR_CUDA, "no CUDA device available (%s); libconsenrich_b200 has no CPU path",
                     e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(CB200_ERR_INVALID, "device %d out of range [0, %d)", device, count);
-    CU_TRY(cudaSetDevice(device));
+    DeviceGuard _dg(device);
     cudaDeviceProp prop;
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
@@ -392,8 +412,8 @@ int cb200_ctx_create(int device, void *stream, cb200_ctx **out) {
 }
 
 void cb200_ctx_destroy(cb200_ctx *c) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return;
-    cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->D,
                       &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard};
@@ -410,6 +430,7 @@ void cb200_ctx_destroy(cb200_ctx *c) {
 }
 
 int cb200_ctx_set_stream(cb200_ctx *c, void *stream) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (c->own_stream) {
@@ -426,14 +447,17 @@ int cb200_ctx_set_stream(cb200_ctx *c, void *stream) {
 }
 
 int cb200_ctx_sync(cb200_ctx *c) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     CU_TRY(cudaStreamSynchronize(c->stream));
     return CB200_OK;
 }
 
-int64_t cb200_ctx_launch_count(const cb200_ctx *c) { return c ? c->launches : 0; }
+int64_t cb200_ctx_launch_count(const cb200_ctx *c) {
+    DeviceGuard _dg(c ? c->device : 0); return c ? c->launches : 0; }
 
 int cb200_ctx_enable_timing(cb200_ctx *c, int on) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     CB_TRY(resolve_spans(c));
     c->timing = on != 0;
@@ -441,6 +465,7 @@ int cb200_ctx_enable_timing(cb200_ctx *c, int on) {
 }
 
 int cb200_ctx_kernel_ms(cb200_ctx *c, int family, double *ms, int64_t *launches) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || family < 0 || family >= FAM_COUNT) return fail(CB200_ERR_INVALID, "bad kernel family");
     CB_TRY(resolve_spans(c));
     if (ms) *ms = c->fam_ms[family];
@@ -449,6 +474,7 @@ int cb200_ctx_kernel_ms(cb200_ctx *c, int family, double *ms, int64_t *launches)
 }
 
 int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (host_out && c->scan_dbg) {
@@ -475,6 +501,7 @@ int cb200_set_scan_substeps(int nsub) {
 }
 
 int cb200_ctx_reset_timing(cb200_ctx *c) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     CB_TRY(resolve_spans(c));
     for (int i = 0; i < FAM_COUNT; ++i) {
@@ -488,6 +515,7 @@ int cb200_ctx_reset_timing(cb200_ctx *c) {
 // memory helpers
 // =====================================================================================
 int cb200_device_alloc(cb200_ctx *c, size_t bytes, void **dptr) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !dptr) return fail(CB200_ERR_INVALID, "ctx/dptr is NULL");
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaMalloc(dptr, bytes < 256 ? 256 : bytes));
@@ -495,6 +523,7 @@ int cb200_device_alloc(cb200_ctx *c, size_t bytes, void **dptr) {
 }
 
 int cb200_device_free(cb200_ctx *c, void *dptr) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     if (!dptr) return CB200_OK;
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -516,6 +545,7 @@ int cb200_pinned_free(void *hptr) {
 
 int cb200_copy_h2d(cb200_ctx *c, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
                    size_t rows) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     if (rows == 0 || row_bytes == 0) return CB200_OK;
     CU_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, c->stream));
@@ -524,6 +554,7 @@ int cb200_copy_h2d(cb200_ctx *c, void *dst, size_t dst_pitch, const void *src, s
 
 int cb200_copy_d2h(cb200_ctx *c, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
                    size_t rows) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
     if (rows == 0 || row_bytes == 0) return CB200_OK;
     CU_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, row_bytes, rows, cudaMemcpyDeviceToHost, c->stream));
@@ -535,6 +566,7 @@ int cb200_copy_d2h(cb200_ctx *c, void *dst, size_t dst_pitch, const void *src, s
 // =====================================================================================
 int cb200_fold_tracks(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n, int64_t ld,
                       double pad, double *stats, int64_t stat_stride) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !data || !munc || !stats) return fail(CB200_ERR_INVALID, "NULL argument");
     if (m <= 0 || n <= 0) return CB200_OK;
     if (ld < n) return fail(CB200_ERR_INVALID, "row stride ld must be >= n");
@@ -546,6 +578,7 @@ int cb200_fold_tracks(cb200_ctx *c, const float *data, const float *munc, int64_
 int cb200_forward_scan(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride, int64_t m,
                        int64_t n, const float *lam, const float *kap, const float *qscale, const double *init_state,
                        float *xf, float *Pf, float *Qf, float *D, double *sums) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !stats) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (n <= 0) return CB200_OK;
@@ -557,6 +590,7 @@ int cb200_forward_scan_shard(cb200_ctx *c, const cb200_model *mo, const double *
                              int64_t n, const float *lam, const float *kap, const float *qscale,
                              const double *init_state, float *xf, float *Pf, float *Qf, float *D, double *sums,
                              float *q_head) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !stats) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (n <= 0) return fail(CB200_ERR_INVALID, "a shard must hold at least one interval");
@@ -566,6 +600,7 @@ int cb200_forward_scan_shard(cb200_ctx *c, const cb200_model *mo, const double *
 
 int cb200_forward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride,
                                   int64_t n, const float *lam, const float *kap, const float *qscale, double *agg) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !stats || !agg) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (n <= 0) return fail(CB200_ERR_INVALID, "a shard must hold at least one interval");
@@ -575,6 +610,7 @@ int cb200_forward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, const dou
 
 int cb200_forward_shard_prefix(cb200_ctx *c, const cb200_model *mo, const double *aggs, int32_t rank,
                                double *init_state) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !aggs || !init_state) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     CU_TRY(launch_forward_shard_prefix(mo->state_dim, aggs, rank, mo->state_init, mo->cov_init, init_state,
@@ -586,6 +622,7 @@ int cb200_forward_shard_prefix(cb200_ctx *c, const cb200_model *mo, const double
 int cb200_backward_scan(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf,
                         const float *Qf, const double *tail_state, float *xs, float *Ps, float *lag,
                         int64_t lag_rows) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !xf || !Pf || !Qf || !xs || !Ps || !lag) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (n <= 0) return CB200_OK;
@@ -594,6 +631,7 @@ int cb200_backward_scan(cb200_ctx *c, const cb200_model *mo, int64_t n, const fl
 
 int cb200_backward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf,
                                    const float *Qf, int32_t is_last_shard, double *agg) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !xf || !Pf || !Qf || !agg) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (n <= 0) return fail(CB200_ERR_INVALID, "a shard must hold at least one interval");
@@ -602,6 +640,7 @@ int cb200_backward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, int64_t 
 
 int cb200_backward_shard_prefix(cb200_ctx *c, const cb200_model *mo, const double *aggs, int32_t rank,
                                 int32_t n_shards, double *tail_state) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !aggs || !tail_state) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     CU_TRY(launch_backward_shard_prefix(mo->state_dim, aggs, rank, n_shards, tail_state, c->stream));
@@ -611,6 +650,7 @@ int cb200_backward_shard_prefix(cb200_ctx *c, const cb200_model *mo, const doubl
 
 int cb200_residuals(cb200_ctx *c, const float *data, int64_t m, int64_t n, int64_t ld, const float *xs,
                     int32_t state_dim, float *resid) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !data || !xs || !resid) return fail(CB200_ERR_INVALID, "NULL argument");
     if (state_dim != 1 && state_dim != 2) return fail(CB200_ERR_INVALID, "state_dim must be 1 or 2");
     if (m <= 0 || n <= 0) return CB200_OK;
@@ -619,6 +659,7 @@ int cb200_residuals(cb200_ctx *c, const float *data, int64_t m, int64_t n, int64
 
 int cb200_update_lambda(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stat_stride, int64_t m,
                         int64_t n, const float *xs, const float *Ps, double nu, float *lam) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !stats || !xs || !Ps || !lam) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     Span sp(c, FAM_PREC);
@@ -631,6 +672,7 @@ int cb200_update_lambda(cb200_ctx *c, const cb200_model *mo, const double *stats
 
 int cb200_update_kappa(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xs, const float *Ps,
                        const float *lag, const float *qscale, double nu, float *kap) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !xs || !Ps || !lag || !kap) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (mo->state_dim == 2) {
@@ -650,6 +692,7 @@ int cb200_update_kappa(cb200_ctx *c, const cb200_model *mo, int64_t n, const flo
 int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opts *op, const float *data,
                      const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *lam, float *kap,
                      float *xs, float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !op || !res || !data || !munc || !xs || !Ps || !lag) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo_in));
     memset(res, 0, sizeof(*res));
@@ -783,6 +826,7 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
 int cb200_host_sweep(cb200_ctx *c, const cb200_model *mo, const float *data, const float *munc, int64_t m, int64_t n,
                      const float *lam, const float *kap, const float *qscale, float *xf, float *Pf, float *Qf, float *D,
                      double *sum_d, double *sum_nll, float *xs, float *Ps, float *lag, int64_t lag_rows, float *resid) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !data || !munc) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (sum_d) *sum_d = 0.0;
@@ -850,6 +894,7 @@ int cb200_host_forward_pass(cb200_ctx *c, const cb200_model *mo, const float *da
                             int64_t n, const int32_t *block_map, int64_t block_count, const float *lam,
                             const float *kap, const float *qscale, float *xf, float *Pf, float *Qf, float *D,
                             double *sum_d, double *sum_nll) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (n > 0 && m > 0) CB_TRY(check_block_map(block_map, n, block_count));
     return cb200_host_sweep(c, mo, data, munc, m, n, lam, kap, qscale, xf, Pf, Qf, D, sum_d, sum_nll, nullptr, nullptr,
                             nullptr, 0, nullptr);
@@ -858,6 +903,7 @@ int cb200_host_forward_pass(cb200_ctx *c, const cb200_model *mo, const float *da
 int cb200_host_backward_pass(cb200_ctx *c, const cb200_model *mo, const float *data, int64_t m, int64_t n,
                              const float *xf, const float *Pf, const float *Qf, float *xs, float *Ps, float *lag,
                              int64_t lag_rows, float *resid) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !xf || !Pf || !Qf || !xs || !Ps || !lag) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     if (n <= 0) return CB200_OK;
@@ -898,6 +944,7 @@ int cb200_host_ecm(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op
                    const float *munc, int64_t m, int64_t n, const int32_t *block_map, int64_t block_count,
                    const float *qscale, float *lam, float *kap, float *xs, float *Ps, float *lag, float *resid,
                    cb200_ecm_result *res, double *nll_path) {
+    DeviceGuard _dg(c ? c->device : 0);
     if (!c || !op || !res || !data || !munc) return fail(CB200_ERR_INVALID, "NULL argument");
     CB_TRY(check_model(mo));
     memset(res, 0, sizeof(*res));

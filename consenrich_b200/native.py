@@ -111,7 +111,7 @@ def _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kap
 
 
 def _ctx(device=None):
-    return _lib.default_context(0 if device is None else int(device))
+    return _lib.default_context(None if device is None else int(device))
 
 
 def _forward(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount, stateInit,

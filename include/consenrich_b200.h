@@ -98,6 +98,9 @@ typedef struct cb200_ecm_result {
 
 /* ---- context ------------------------------------------------------------------------ */
 CB200_API int cb200_abi_version(void);
+/* The CUDA device the calling thread has selected (cudaGetDevice): the drop-in functions create
+ * their context there, so that one process per GPU (torchrun) needs no extra argument. */
+CB200_API int cb200_current_device(int *device);
 /* stream: a cudaStream_t to enqueue on, or NULL for a stream owned by the context. */
 CB200_API int cb200_ctx_create(int device, void *stream, cb200_ctx **out);
 CB200_API void cb200_ctx_destroy(cb200_ctx *ctx);
