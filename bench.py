@@ -432,8 +432,17 @@ def run_b200_arm(args):
         step_ms = ms_total / args.steps
         # reference-equivalent traffic of the step: the reference re-reads data + munc in every pass
         ref_equiv = SWEEPS_PER_STEP * (cells * 8.0 + n * 84.0) + ECM_ITERS * cells * 8.0 + cells * 4.0
+        # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch)
+        traffic, traffic_src = None, None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1g_ncu_full_summary.json")))
+            traffic = float(prof["kernels"][dom]["dram_bytes_per_launch"])
+            traffic_src = "profiles/r1g_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom],
                     "kernel_ms_per_launch": {k_: per[k_] for k_ in per if kern[k_][1] > 0},
                     "kernel_launches_per_step": {k_: kern[k_][1] / args.steps for k_ in per if kern[k_][1] > 0},
