@@ -88,6 +88,7 @@ SIGNATURES = {
     "cb200_forward_shard_aggregate": (C.c_int, [_vp, _pm, _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "cb200_forward_shard_prefix": (C.c_int, [_vp, _pm, _vp, _i32, _vp]),
     "cb200_backward_scan": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
+    "cb200_backward_scan_kappa": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _dbl, _vp]),
     "cb200_backward_shard_aggregate": (C.c_int, [_vp, _pm, _i64, _vp, _vp, _vp, _i32, _vp]),
     "cb200_backward_shard_prefix": (C.c_int, [_vp, _pm, _vp, _i32, _i32, _vp]),
     "cb200_residuals": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _i32, _vp]),

@@ -268,9 +268,15 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     return CB200_OK;
 }
 
+struct KappaFuse {  // Student-t process precision update carried out inside the backward replay
+    float *kap_out = nullptr;
+    const float *qs = nullptr;
+    double nu = 0.0;
+};
+
 int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf, const float *Qf,
                 const double *tail_state, int is_last, float *xs, float *Ps, float *lag, int64_t lag_rows,
-                double *agg_out, bool aggregate_only) {
+                double *agg_out, bool aggregate_only, const KappaFuse *kf = nullptr) {
     const int d = mo->state_dim;
     if (d == 2 && (!aligned(xf, 8) || !aligned(Pf, 16) || !aligned(Qf, 16) ||
                    (!aggregate_only && (!aligned(xs, 8) || !aligned(Ps, 16) || !aligned(lag, 16)))))
@@ -286,6 +292,20 @@ int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf,
     a.lag_rows = lag_rows;
     a.M = to_model2(mo);
     a.is_last_shard = is_last;
+    if (kf && kf->kap_out && !aggregate_only) {
+        a.kap_out = kf->kap_out;
+        a.qs = kf->qs;
+        a.nu = kf->nu;
+        a.kap_lo = mo->kap_min;
+        a.kap_hi = mo->kap_max;
+        if (d == 2) {
+            const double det = mo->Q0[0] * mo->Q0[3] - mo->Q0[1] * mo->Q0[2];
+            if (det == 0.0) return fail(CB200_ERR_INVALID, "matrixQ0 is singular");
+            a.qi00 = mo->Q0[3] / det; a.qi01 = -mo->Q0[1] / det; a.qi10 = -mo->Q0[2] / det; a.qi11 = mo->Q0[0] / det;
+        } else {
+            a.qi00 = 1.0 / mo->Q0[0];
+        }
+    }
     int launches = 0;
     {
         Span sp(c, FAM_BWD);
@@ -629,6 +649,20 @@ int cb200_backward_scan(cb200_ctx *c, const cb200_model *mo, int64_t n, const fl
     return do_backward(c, mo, n, xf, Pf, Qf, tail_state, tail_state == nullptr, xs, Ps, lag, lag_rows, nullptr, false);
 }
 
+int cb200_backward_scan_kappa(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf,
+                              const float *Qf, float *xs, float *Ps, float *lag, int64_t lag_rows, const float *qscale,
+                              double nu, float *kap) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !xf || !Pf || !Qf || !xs || !Ps || !lag || !kap) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo));
+    if (n <= 0) return CB200_OK;
+    KappaFuse kf;
+    kf.kap_out = kap;
+    kf.qs = qscale;
+    kf.nu = nu;
+    return do_backward(c, mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, lag_rows, nullptr, false, &kf);
+}
+
 int cb200_backward_shard_aggregate(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf,
                                    const float *Qf, int32_t is_last_shard, double *agg) {
     DeviceGuard _dg(c ? c->device : 0);
@@ -720,12 +754,19 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     double *sums = static_cast<double *>(c->sums.p);
     CB_TRY(do_fold(c, data, munc, m, n, ld, mo.pad, stats, stride));
 
-    auto sweep = [&]() -> int {
+    // with_kappa: the kappa update of this inner iteration rides on the backward replay
+    auto sweep = [&](bool with_kappa) -> int {
         cb200_model f = mo;
         f.return_nll = 0;
         CB_TRY(do_forward(c, &f, stats, stride, m, n, lam, kap, qscale, nullptr, xf, Pf, Qf, nullptr, nullptr, nullptr,
                           false));
-        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false));
+        KappaFuse kf;
+        if (with_kappa) {
+            kf.kap_out = kap;
+            kf.qs = qscale;
+            kf.nu = op->nu;
+        }
+        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, &kf));
         return CB200_OK;
     };
     auto nll_only = [&](double *out) -> int {
@@ -742,7 +783,7 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     const int patience = 2;
     if (n <= 5) {  // pyx:7998-8129: filter + smoother only
         double cur = 0.0;
-        CB_TRY(sweep());
+        CB_TRY(sweep(false));
         CB_TRY(nll_only(&cur));
         res->skipped = 1;
         res->initial_nll = res->final_nll = cur;
@@ -757,18 +798,14 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     for (int i = 0; i < op->max_iters; ++i) {
         iters_done = i + 1;
         for (int t = 0; t < op->inner_iters; ++t) {
-            CB_TRY(sweep());
+            // kappa is read by the forward pass only, so the backward pass may overwrite it in place; the
+            // lambda update (separate kernel) reads the smoothed tracks, not kappa
+            CB_TRY(sweep(kap != nullptr));
             if (lam) {
                 Span sp(c, FAM_PREC);
                 CU_TRY(launch_update_lambda(reinterpret_cast<const double2 *>(stats),
                                             reinterpret_cast<const double2 *>(stats + 2 * stride), n, (double)m, xs, Ps,
                                             d, op->nu, mo.lam_min, mo.lam_max, lam, c->stream));
-                c->launches += 1;
-            }
-            if (kap) {
-                Span sp(c, FAM_PREC);
-                CU_TRY(launch_update_kappa(d, to_model2(&mo), n, xs, Ps, lag, qscale, op->nu, mo.kap_min, mo.kap_max,
-                                           kap, c->stream));
                 c->launches += 1;
             }
         }

@@ -581,6 +581,7 @@ struct Bwd2 {
             // row n-1 of Qf holds nothing unless a following shard supplied it
             cp_async<16>(d + 16, reinterpret_cast<const float4 *>(a.Qf) + kk, ok && (k < a.n - 1 || !a.is_last_shard));
             cp_async<8>(d + 32, reinterpret_cast<const float2 *>(a.xf) + kk, ok);
+            if (ALL && a.kap_out && a.qs) cp_async<4>(d + 44, a.qs + (kk + 1 < a.n ? kk + 1 : kk), ok);
         }
     }
     template <bool FULLC>
@@ -625,11 +626,21 @@ struct Bwd2 {
                     // xs = xf, Ps = Pf already in place; lag row n-1 does not exist
                 } else {
                     const Rts2 r = rts2_gain<CANON>(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
+                    const Rs2 nxt = c;  // smoothed bin k+1 as the reference stores it (float32 values)
+                    const float qs_next = *reinterpret_cast<const float *>(b + 44);
                     Smo2Out o;
                     rts2_step(c, r, x.x, x.y, P.x, P.y, P.w, o);
                     *reinterpret_cast<float4 *>(b) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
                     *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
-                    *reinterpret_cast<float2 *>(b + 32) = make_float2((float)o.xs0, (float)o.xs1);
+                    float kv = 1.0f;
+                    if (a.kap_out) {
+                        // the reference reads its float32 tracks back: c now holds bin k rounded that way
+                        kv = (float)kappa2_update(a.M, a.qi00, a.qi01, a.qi10, a.qi11, c.x0, c.x1, c.P00, c.P01, c.P10,
+                                                  c.P11, nxt.x0, nxt.x1, nxt.P00, nxt.P01, nxt.P10, nxt.P11, r32(o.C00),
+                                                  r32(o.C01), r32(o.C10), r32(o.C11), (double)qs_next, a.qs != nullptr,
+                                                  a.nu, a.kap_lo, a.kap_hi);
+                    }
+                    *reinterpret_cast<float4 *>(b + 32) = make_float4((float)o.xs0, (float)o.xs1, kv, 0.0f);
                 }
             }
         }
@@ -646,7 +657,12 @@ struct Bwd2 {
                 reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(d);
                 if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
                     reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(d + 16);
-                reinterpret_cast<float2 *>(a.xs)[k] = *reinterpret_cast<const float2 *>(d + 32);
+                const float4 xk = *reinterpret_cast<const float4 *>(d + 32);
+                reinterpret_cast<float2 *>(a.xs)[k] = make_float2(xk.x, xk.y);
+                if (a.kap_out) {
+                    if (k + 1 < a.n) a.kap_out[k + 1] = xk.z;  // multiplier of the transition k -> k+1
+                    if (k == 0) a.kap_out[0] = 1.0f;
+                }
             }
         }
     }
@@ -695,6 +711,7 @@ struct Bwd1 {
             cp_async<4>(d, a.xf + kk, ok);
             cp_async<4>(d + 4, a.Pf + kk, ok);
             cp_async<4>(d + 8, a.Qf + kk, ok && (k < a.n - 1 || !a.is_last_shard));
+            if (ALL && a.kap_out && a.qs) cp_async<4>(d + 12, a.qs + (kk + 1 < a.n ? kk + 1 : kk), ok);
         }
     }
     template <bool FULLC>
@@ -740,8 +757,12 @@ struct Bwd1 {
                     const double dP = c.P - pp;
                     double ps = pf + (J * J * dP);
                     if (ps < 0.0) ps = 0.0;
-                    const float xs32 = (float)xsv, ps32 = (float)ps;
-                    *reinterpret_cast<float4 *>(b) = make_float4(xs32, ps32, (float)(pf + (J * dP)), 0.0f);
+                    const float xs32 = (float)xsv, ps32 = (float)ps, lag32 = (float)(pf + (J * dP));
+                    float kv = 1.0f;
+                    if (a.kap_out)
+                        kv = (float)kappa1_update(a.qi00, (double)xs32, (double)ps32, c.x, c.P, (double)lag32, (double)v.w,
+                                                  a.qs != nullptr, a.nu, a.kap_lo, a.kap_hi);
+                    *reinterpret_cast<float4 *>(b) = make_float4(xs32, ps32, lag32, kv);
                     c.x = (double)xs32;
                     c.P = (double)ps32;
                 }
@@ -760,6 +781,10 @@ struct Bwd1 {
                 a.xs[k] = o.x;
                 a.Ps[k] = o.y;
                 if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard)) a.lag[k] = o.z;
+                if (a.kap_out) {
+                    if (k + 1 < a.n) a.kap_out[k + 1] = o.w;
+                    if (k == 0) a.kap_out[0] = 1.0f;
+                }
             }
         }
     }

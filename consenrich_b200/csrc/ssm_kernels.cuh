@@ -60,6 +60,13 @@ struct BwdArgs {
     int64_t n, lag_rows;
     Model2 M;
     int32_t is_last_shard;
+    // Student-t process precision update fused into the replay (cconsenrich.pyx:8252-8298, 7499-7521):
+    // kap_out[k+1] from the smoothed bins k, k+1 and their lag-one covariance, as soon as the replay
+    // has them in registers.  kap_out == nullptr: off.
+    float *kap_out;
+    const float *qs;           // processQScale or nullptr
+    double nu, kap_lo, kap_hi;
+    double qi00, qi01, qi10, qi11;  // Q0^-1 (state_dim 1: qi00 = 1 / Q0[0])
 };
 
 size_t scan_workspace_bytes(int64_t n);

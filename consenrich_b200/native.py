@@ -275,7 +275,7 @@ def sweep(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, stateInit, stateC
     def buf(key, shape):
         a = out.get(key)
         if a is None:
-            a = out[key] = np.empty(shape, np.float32)
+            a = out[key] = _lib.pinned_empty(shape, np.float32)  # page-locked: full-rate D2H
         return a
 
     xf, Pf, Qf = buf("stateForward", (n, dim)), buf("stateCovarForward", (n, dim, dim)), buf("pNoiseForward", (n, dim, dim))
@@ -294,16 +294,26 @@ def sweep(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, stateInit, stateC
     return out
 
 
-def _init_multiplier(init, n, lo, hi, what):
-    """Warm-start copy + clip, cconsenrich.pyx:7899-7923."""
+def _check_multiplier(init, n, what):
+    """Validation half of the warm-start handling (cconsenrich.pyx:7899-7923)."""
     if init is None:
-        return np.ones(n, dtype=np.float32)
-    arr = np.array(init, dtype=np.float32, copy=True, order="C").reshape(-1)
-    if arr.shape[0] != n:
+        return None
+    src = np.asarray(init, dtype=np.float32).reshape(-1)
+    if src.shape[0] != n:
         raise ValueError(f"{what} length must match intervalCount")
-    if not np.all(np.isfinite(arr)):
+    if not np.all(np.isfinite(src)):
         raise ValueError(f"{what} must contain only finite values")
-    np.clip(arr, lo, hi, out=arr)
+    return src
+
+
+def _init_multiplier(src, n, lo, hi, pinned):
+    """Warm-start copy + clip (pyx:7899-7923).  The array travels to the device and back, so it is
+    page-locked when the call is going to run on the device (``pinned``)."""
+    arr = (_lib.pinned_empty if pinned else np.empty)((n,), np.float32)
+    if src is None:
+        arr.fill(1.0)
+    else:
+        np.clip(src, lo, hi, out=arr)
     return arr
 
 
@@ -317,10 +327,10 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     m, n = data.shape
     use_qscale = processQScale is not None
     lam = kap = None
-    if useObs:
-        lam = _init_multiplier(lambdaExpInit, n, lamMin, lamMax, "lambdaExpInit")
-    if useProc and ((not useAPN) or use_qscale):
-        kap = _init_multiplier(processPrecExpInit, n, kapMin, kapMax, "processPrecExpInit")
+    use_lam = bool(useObs)
+    use_kap = bool(useProc and ((not useAPN) or use_qscale))
+    lam_src = _check_multiplier(lambdaExpInit, n, "lambdaExpInit") if use_lam else None
+    kap_src = _check_multiplier(processPrecExpInit, n, "processPrecExpInit") if use_kap else None
     qs = _coerce_qscale(processQScale, n) if use_qscale else None
     want = bool(returnIntermediates) and n > 0 and m > 0
     xs = Ps = lag = res = None  # allocated after validation (page-locked: the copy engine writes them)
@@ -335,6 +345,8 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
         return (iters_done, float(nll), diag) if returnDiagnostics else (iters_done, float(nll))
 
     if n <= 0 or m <= 0:
+        lam = _init_multiplier(lam_src, n, lamMin, lamMax, False) if use_lam else None
+        kap = _init_multiplier(kap_src, n, kapMin, kapMax, False) if use_kap else None
         xs, Ps = np.empty((n, dim), np.float32), np.empty((n, dim, dim), np.float32)
         lag, res = np.empty((max(n - 1, 1), dim, dim), np.float32), np.empty((n, m), np.float32)
         diag = {"iters_done": 0, "max_iters": int(iters), "converged": False, "skipped": True,
@@ -365,6 +377,8 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     if _apn_live(useAPN, use_qscale, Q0, dim):
         raise NotImplementedError(_APN_MSG)
 
+    lam = _init_multiplier(lam_src, n, lamMin, lamMax, True) if use_lam else None
+    kap = _init_multiplier(kap_src, n, kapMin, kapMax, True) if use_kap else None
     alloc = _lib.pinned_empty if want else np.empty
     xs, Ps = alloc((n, dim), np.float32), alloc((n, dim, dim), np.float32)
     lag, res = alloc((max(n - 1, 1), dim, dim), np.float32), alloc((n, m), np.float32)

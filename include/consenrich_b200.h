@@ -180,6 +180,13 @@ CB200_API int cb200_forward_shard_prefix(cb200_ctx *ctx, const cb200_model *mode
 CB200_API int cb200_backward_scan(cb200_ctx *ctx, const cb200_model *model, int64_t n, const float *xf,
                         const float *Pf, const float *Qf, const double *tail_state, float *xs,
                         float *Ps, float *lag, int64_t lag_rows);
+/* cb200_backward_scan of a whole chromosome with the Student-t process precision update
+ * (cb200_update_kappa) carried out inside the replay: kap[k+1] is written as soon as the smoothed
+ * intervals k and k+1 and their lag-one covariance are in registers; kap[0] = 1.  kap may be the
+ * array the preceding forward scan read. */
+CB200_API int cb200_backward_scan_kappa(cb200_ctx *ctx, const cb200_model *model, int64_t n, const float *xf,
+                              const float *Pf, const float *Qf, float *xs, float *Ps, float *lag,
+                              int64_t lag_rows, const float *qscale, double nu, float *kap);
 CB200_API int cb200_backward_shard_aggregate(cb200_ctx *ctx, const cb200_model *model, int64_t n, const float *xf,
                                    const float *Pf, const float *Qf, int32_t is_last_shard,
                                    double *agg);
