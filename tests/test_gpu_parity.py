@@ -364,3 +364,32 @@ def test_chr19_sized_sweep_matches_oracle_and_properties(cb, oracle):
     assert_tracks_close(twice["xs"], 2.0 * got["xs"], "linearity", rtol=1e-5, atol_rel=1e-6)
     assert_tracks_close(twice["Ps"], got["Ps"], "covariance is data-independent", scale="component",
                         rtol=1e-6, atol_rel=1e-7)
+
+
+def test_longest_chromosome_at_10bp_and_widest_cohort(cb, oracle):
+    """Maximum sizes of BASELINE.json's configs: chr1 at 10 bp (24 895 643 bins, cfg4's longest track:
+    ~3040 tiles, several waves, multi-round look-back, 64-bit offsets) with few tracks, and a
+    1000-track cohort (cfg5's width: 32 track tiles in the residual transpose, long fold loops with
+    mantissa renormalisation)."""
+    # ---- longest chromosome ----
+    m, n = 2, 24_895_643
+    rng = np.random.default_rng(5)
+    k = np.arange(n, dtype=np.float32)
+    x = (0.5 * np.sin(k / 9000.0) + 1.5 * (np.sin(k / 411.0) > 0.97)).astype(np.float32)
+    munc = (0.15 * (1.0 + np.abs(x))[None, :] * rng.uniform(0.5, 1.5, size=(m, n)).astype(np.float32)).astype(np.float32)
+    data = (x[None, :] + rng.standard_normal((m, n), dtype=np.float32) * np.sqrt(munc)).astype(np.float32)
+    want = _sweep(oracle, 2, data, munc)
+    got = _sweep(cb, 2, data, munc)
+    _compare_sweeps(got, want, n, 2, "chr1@10bp")
+    np.testing.assert_array_equal(got["xs"][-1], got["xf"][-1])
+    del want, got
+    # ---- widest cohort ----
+    m, n = 1000, 6_001
+    data, munc = synth_tracks(31337, m, n, masked_frac=0.05)
+    lam, kap, qs = _weights(np.random.default_rng(3), n)
+    for dim in (2, 1):
+        want = _sweep(oracle, dim, data, munc, lam, kap, qs)
+        got = _sweep(cb, dim, data, munc, lam, kap, qs)
+        _compare_sweeps(got, want, n, dim, f"1000 tracks d{dim}")
+        lvl = got["xs"][:, 0].astype(np.float64)
+        np.testing.assert_array_equal(got["res"], (data.T.astype(np.float64) - lvl[:, None]).astype(np.float32))
