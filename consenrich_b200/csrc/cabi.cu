@@ -499,7 +499,7 @@ int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
     CU_TRY(cudaStreamSynchronize(c->stream));
     if (host_out && c->scan_dbg) {
         const int64_t t = tiles < c->scan_dbg_tiles ? tiles : c->scan_dbg_tiles;
-        CU_TRY(cudaMemcpy(host_out, c->scan_dbg, (size_t)t * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(host_out, c->scan_dbg, (size_t)t * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
     }
     if (c->scan_dbg) {
         CU_TRY(cudaFree(c->scan_dbg));
@@ -507,8 +507,8 @@ int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
         c->scan_dbg_tiles = 0;
     }
     if (tiles > 0 && !host_out) {  // arm: the next scan launches stamp their phases
-        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&c->scan_dbg), (size_t)tiles * 4 * sizeof(long long)));
-        CU_TRY(cudaMemset(c->scan_dbg, 0, (size_t)tiles * 4 * sizeof(long long)));
+        CU_TRY(cudaMalloc(reinterpret_cast<void **>(&c->scan_dbg), (size_t)tiles * 8 * sizeof(long long)));
+        CU_TRY(cudaMemset(c->scan_dbg, 0, (size_t)tiles * 8 * sizeof(long long)));
         c->scan_dbg_tiles = tiles;
     }
     return CB200_OK;

@@ -793,104 +793,113 @@ struct Bwd1 {
 // =====================================================================================
 // decoupled look-back (one warp of the CTA)
 // =====================================================================================
-// Two-level look-back.  When every tile of a wave finishes composing its run elements at about
-// the same time, no tile has a prefix yet and a plain look-back walks back 32 aggregates per
-// round, all the way to the start (hundreds of tiles = tens of microseconds, every tile doing the
-// same work).  Here a tile that finds no prefix in its first window publishes the aggregate of
-// that window plus itself (a level-1 aggregate spanning SPAN1 = 33 tiles); further rounds then
-// read level-1 aggregates at a stride of 33 tiles, covering 1056 tiles per round.  Dependencies
-// still point only at earlier tiles, so there is nothing to deadlock on.
-//   flag - epoch4:  1 = aggregate published, 2 = level-1 aggregate published, 3 = prefix published
-constexpr int SPAN1 = 33;
-
+// Cooperative look-back.  When every tile of a wave finishes composing its run elements at about
+// the same time, no tile has a published prefix yet.  A single warp walking back 32 aggregates
+// per round then needs one round per 32 tiles, and waiting for intermediate results of other
+// tiles costs several L2 round trips per generation.  Here the WHOLE CTA (its other warps would
+// only wait at a barrier anyway) reduces a window of SCAN_THREADS * c preceding tiles at once:
+// thread j takes the c tiles base - j c ... base - j c - (c - 1), composes them in order, the
+// warps reduce by an ordered shuffle tree and the four warp results are combined through shared
+// memory.  Nothing but plain aggregates (flag 1) and final prefixes (flag 2) is ever published, a
+// tile depends on earlier tiles only, and one window of c = 4 spans 512 tiles.
+//   flag - epoch4:  1 = aggregate published, 2 = inclusive prefix published
 template <class Tr>
 __device__ __forceinline__ int flag_state(const ScanWorkspace &ws, int idx) {
     const int v = ld_acquire(ws.flags + idx) - ws.epoch4;
-    return (v >= 1 && v <= 3) ? v : 0;
+    return (v == 1 || v == 2) ? v : 0;
 }
 
-// ordered tree reduction over lanes 0..first of a window (lane i holds the later tiles)
-template <class Tr>
-__device__ __forceinline__ typename Tr::Elem window_reduce(typename Tr::Elem e, int first, int lane) {
-    const int span = first < 32 ? first + 1 : 32;
-    for (int d = 1; d < span; d <<= 1) {
-        const typename Tr::Elem o = shfl_down_elem(e, d);
-        if (lane + d < 32) e = Tr::combine(o, e);
-    }
-    return e;
-}
+constexpr int LB_MAX_PER_THREAD = 4;
 
+// Exclusive prefix state of `tile` (> 0); every thread of the CTA calls it and gets the result.
+// sd_red: NWARPS * N doubles of shared scratch, sd_int: NWARPS ints.
 template <class Tr>
-__device__ typename Tr::State lookback(const typename Tr::Args &a, const ScanWorkspace &ws, int tile, int lane,
-                                       const typename Tr::Elem &own_agg) {
+__device__ typename Tr::State cooperative_lookback(const typename Tr::Args &a, const ScanWorkspace &ws, int tile,
+                                                    int first_wave, int tid, double *sd_red, int *sd_int) {
     using Elem = typename Tr::Elem;
     using State = typename Tr::State;
-    // ---- round A: plain aggregates of tiles tile-1 .. tile-32 ----
-    Elem running;
-    {
-        const int idx = tile - 1 - lane;
-        int f;
-        while (true) {
-            f = idx >= 0 ? flag_state<Tr>(ws, idx) : 3;
-            // usable as soon as every tile up to the nearest published prefix has its aggregate out
-            const unsigned pm = __ballot_sync(FULL, f == 3);
-            const unsigned zm = __ballot_sync(FULL, f == 0);
-            const unsigned upto = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : FULL;  // lanes 0..first
-            if ((zm & upto) == 0) break;
-        }
-        const unsigned pm = __ballot_sync(FULL, f == 3);
-        const int first = pm ? (__ffs(pm) - 1) : 32;
-        Elem e;
-        if (lane > first) {
-            e = Tr::identity();
-        } else if (f == 3) {
-            State s = (idx >= 0) ? load_elem_cg<State>(ws.tile_pref + (int64_t)idx * PREF_PITCH) : Tr::initial(a);
-            e = Tr::from_state(s);
-        } else {
-            e = load_elem_cg<Elem>(ws.tile_agg + (int64_t)idx * AGG_PITCH);
-        }
-        running = window_reduce<Tr>(e, first, lane);
-        if (first < 32) return Tr::elem_state(shfl_bcast_elem(running, 0));
+    constexpr int N = Elem::N;
+    const int lane = tid & 31, warp = tid >> 5;
+    Elem running = Tr::identity();
+    bool have = false;
+    int base = tile - 1;  // latest tile not yet covered
+    // tiles per thread in this window.  A tile of the first wave has no published prefix near it (its
+    // neighbours started together with it): take everything back to tile 0 in one window if it fits.
+    // Later tiles find a prefix a few tiles back: one tile per thread keeps the loads minimal.
+    int c = 1;
+    if (tile < first_wave) {
+        c = (tile + 1 + SCAN_THREADS - 1) / SCAN_THREADS;
+        if (c > LB_MAX_PER_THREAD) c = LB_MAX_PER_THREAD;
     }
-    // no prefix within 32 tiles: publish the level-1 aggregate of tiles tile-32 .. tile
-    {
-        const Elem l1 = Tr::combine(shfl_bcast_elem(running, 0), own_agg);
-        if (lane == 0) {
-            store_elem(ws.tile_agg1 + (int64_t)tile * AGG_PITCH, l1);
-            __threadfence();
-            st_release(ws.flags + tile, ws.epoch4 + 2);
-        }
-        __syncwarp();
-    }
-    // ---- further rounds: level-1 aggregates at a stride of SPAN1 tiles ----
-    int pos = tile - SPAN1;  // latest tile not yet covered
     while (true) {
-        const int idx = pos - SPAN1 * lane;
-        int f;
+        // ---- wait until every tile of the window has at least its aggregate out ----
+        int f[LB_MAX_PER_THREAD];
         while (true) {
-            f = idx >= 0 ? flag_state<Tr>(ws, idx) : 3;
-            const unsigned pm = __ballot_sync(FULL, f == 3);
-            const unsigned zm = __ballot_sync(FULL, f < 2);
-            const unsigned upto = pm ? ((2u << (__ffs(pm) - 1)) - 1u) : FULL;
-            if ((zm & upto) == 0) break;
+            bool zero = false;
+#pragma unroll
+            for (int u = 0; u < LB_MAX_PER_THREAD; ++u) {
+                if (u < c) {
+                    const int idx = base - (tid * c + u);
+                    f[u] = idx >= 0 ? flag_state<Tr>(ws, idx) : 2;  // before tile 0: the model prior, a "prefix"
+                    zero |= f[u] == 0;
+                }
+            }
+            // a tile publishes its prefix only after all earlier tiles have published aggregates, so
+            // zeros can only sit nearer than the nearest prefix: all of them are needed
+            if (!__syncthreads_or(zero)) break;
         }
-        const unsigned pm = __ballot_sync(FULL, f == 3);
-        const int first = pm ? (__ffs(pm) - 1) : 32;
-        Elem e;
-        if (lane > first) {
-            e = Tr::identity();
-        } else if (f == 3) {
-            State s = (idx >= 0) ? load_elem_cg<State>(ws.tile_pref + (int64_t)idx * PREF_PITCH) : Tr::initial(a);
-            e = Tr::from_state(s);
-        } else {
-            e = load_elem_cg<Elem>(ws.tile_agg1 + (int64_t)idx * AGG_PITCH);
+        if (ws.dbg && tid == 0 && !have) ws.dbg[tile * 8 + 4] = gtimer();
+        // ---- nearest published prefix of the window (position = distance from base) ----
+        int mypos = 1 << 30;
+#pragma unroll
+        for (int u = LB_MAX_PER_THREAD - 1; u >= 0; --u)
+            if (u < c && f[u] == 2) mypos = tid * c + u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mypos = min(mypos, __shfl_xor_sync(FULL, mypos, d));
+        if (lane == 0) sd_int[warp] = mypos;
+        __syncthreads();
+        int first = sd_int[0];
+#pragma unroll
+        for (int w = 1; w < NWARPS; ++w) first = min(first, sd_int[w]);
+        // ---- this thread's tiles, earliest first ----
+        Elem e = Tr::identity();
+#pragma unroll
+        for (int u = LB_MAX_PER_THREAD - 1; u >= 0; --u) {
+            if (u < c) {
+                const int pos = tid * c + u;
+                const int idx = base - pos;
+                if (pos < first) {
+                    e = Tr::combine(e, load_elem_cg<Elem>(ws.tile_agg + (int64_t)idx * AGG_PITCH));
+                } else if (pos == first) {
+                    const State s = idx >= 0 ? load_elem_cg<State>(ws.tile_pref + (int64_t)idx * PREF_PITCH)
+                                             : Tr::initial(a);
+                    e = Tr::from_state(s);  // everything before it is inside the prefix
+                }
+            }
         }
-        e = window_reduce<Tr>(e, first, lane);
-        running = Tr::combine(e, running);
-        if (first < 32) break;
-        pos -= 32 * SPAN1;
+        if (ws.dbg && tid == 0 && !have) ws.dbg[tile * 8 + 5] = gtimer();
+        // ---- ordered reduction: lane i holds later tiles than lane i + d, warp w later than w + 1 ----
+        // only as many levels / warps as the window up to the nearest prefix needs
+        const int last_thread = first < (1 << 30) ? first / c : SCAN_THREADS - 1;  // thread holding that prefix
+        const int last_warp = last_thread >> 5;
+        const int span = warp < last_warp ? 32 : (warp == last_warp ? (last_thread & 31) + 1 : 0);
+        for (int d = 1; d < span; d <<= 1) {
+            const Elem o = shfl_down_elem(e, d);
+            if (lane + d < 32) e = Tr::combine(o, e);
+        }
+        if (lane == 0) store_elem(sd_red + warp * N, e);
+        __syncthreads();
+        Elem win = load_elem<Elem>(sd_red + last_warp * N);
+        for (int w = last_warp - 1; w >= 0; --w) win = Tr::combine(win, load_elem<Elem>(sd_red + w * N));
+        running = have ? Tr::combine(win, running) : win;
+        if (ws.dbg && tid == 0 && !have) ws.dbg[tile * 8 + 6] = gtimer();
+        have = true;
+        if (first < (1 << 30)) break;
+        base -= SCAN_THREADS * c;
+        c = LB_MAX_PER_THREAD;
+        __syncthreads();  // sd_red / sd_int are rewritten by the next window
     }
-    return Tr::elem_state(shfl_bcast_elem(running, 0));
+    return Tr::elem_state(running);
 }
 
 // =====================================================================================
@@ -908,13 +917,14 @@ struct ScanSmem {
     static constexpr int OFF_TSTATE = OFF_TAGG + N;          // [SN] exclusive prefix state of the tile
     static constexpr int OFF_TINCL = OFF_TSTATE + SN;        // [SN]
     static constexpr int OFF_RED = OFF_TINCL + SN;           // [NWARPS][2]
-    static constexpr int OFF_END = OFF_RED + NWARPS * 2;
-    static constexpr int BYTES = REC_TOTAL + OFF_END * 8 + 16;
+    static constexpr int OFF_LB = OFF_RED + NWARPS * 2;      // [NWARPS][N] look-back: per-warp window results
+    static constexpr int OFF_END = OFF_LB + NWARPS * N;
+    static constexpr int BYTES = REC_TOTAL + OFF_END * 8 + 48;  // + s_tile[4], look-back ints[NWARPS]
 };
 
 template <class Tr, bool AGG_ONLY>
 __global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS)
-scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles, const int nsub) {
+scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles, const int nsub, const int first_wave) {
     using Elem = typename Tr::Elem;
     using State = typename Tr::State;
     using SM = ScanSmem<Tr>;
@@ -926,7 +936,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     if (tid == 0) s_tile[0] = AGG_ONLY ? (int)blockIdx.x : atomicAdd(ws.counters, 1);
     __syncthreads();
     const int tile = s_tile[0];
-    if (ws.dbg && tid == 0) ws.dbg[tile * 4] = gtimer();
+    if (ws.dbg && tid == 0) ws.dbg[tile * 8] = gtimer();
     const int L = CHUNK * nsub;
     const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
     const int64_t run0 = p0 + (int64_t)tid * L;
@@ -963,7 +973,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     }
     if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
     __syncthreads();
-    if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 1] = gtimer();
+    if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 1] = gtimer();
     if (!AGG_ONLY) {
         // pass 2's first sub-step is fetched underneath the serial section below
         Tr::template issue<true>(a, buf(0), p0, L, 0, tid);
@@ -972,49 +982,40 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
 
     // the serial section (cross-warp prefix, look-back, publication) rotates over the warps so
     // that it does not always land on the same SM sub-partition
-    const bool leader = warp == (tile & (NWARPS - 1));
-    Elem run = Tr::identity();
-    if (leader) {
-        // exclusive prefixes across warps and the tile aggregate (all lanes redundantly)
-        run = load_elem<Elem>(sd + SM::OFF_WAGG);
-        if (lane == 0) store_elem(sd + SM::OFF_WEXCL, Tr::identity());
-#pragma unroll
-        for (int w = 1; w < NWARPS; ++w) {
-            if (lane == 0) store_elem(sd + SM::OFF_WEXCL + w * SM::N, run);
-            run = Tr::combine(run, load_elem<Elem>(sd + SM::OFF_WAGG + w * SM::N));
-        }
-        if (lane == 0) store_elem(sd + SM::OFF_TAGG, run);
-        __syncwarp();
-        if (lane < SM::N) ws.tile_agg[(int64_t)tile * AGG_PITCH + lane] = sd[SM::OFF_TAGG + lane];
-        if (!AGG_ONLY) {
-            if (lane < SM::N) __threadfence();
-            __syncwarp();
-            if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 1);
+    // ---- scan section: cross-warp prefix, publication of the tile aggregate, look-back ----
+    // every warp forms its own exclusive prefix over the warps before it (lane-redundant); the last
+    // warp also forms and publishes the tile aggregate
+    Elem wex = warp > 0 ? load_elem<Elem>(sd + SM::OFF_WAGG) : Tr::identity();
+    for (int w = 1; w < warp; ++w) wex = Tr::combine(wex, load_elem<Elem>(sd + SM::OFF_WAGG + w * SM::N));
+    if (warp == NWARPS - 1) {
+        const Elem tagg = Tr::combine(wex, load_elem<Elem>(sd + SM::OFF_WAGG + warp * SM::N));
+        if (lane == 0) {
+            store_elem(sd + SM::OFF_TAGG, tagg);
+            store_elem(ws.tile_agg + (int64_t)tile * AGG_PITCH, tagg);
+            if (!AGG_ONLY) {
+                __threadfence();
+                st_release(ws.flags + tile, ws.epoch4 + 1);
+                if (ws.dbg) ws.dbg[tile * 8 + 7] = gtimer();
+            }
         }
     }
     if (AGG_ONLY) return;
-    if (leader) {
-        const State pref = tile == 0 ? Tr::initial(a) : lookback<Tr>(a, ws, tile, lane, run);
-        const State incl = Tr::apply(run, pref);
-        if (lane == 0) {
-            store_elem(sd + SM::OFF_TSTATE, pref);
-            store_elem(sd + SM::OFF_TINCL, incl);
-        }
-        __syncwarp();
-        if (lane < SM::SN) {
-            ws.tile_pref[(int64_t)tile * PREF_PITCH + lane] = sd[SM::OFF_TINCL + lane];
-            __threadfence();
-        }
-        __syncwarp();
-        if (lane == 0) st_release(ws.flags + tile, ws.epoch4 + 3);
-    }
+    int *s_lb = s_tile + 4;
+    const State tpref = tile == 0 ? Tr::initial(a)
+                                  : cooperative_lookback<Tr>(a, ws, tile, first_wave, tid, sd + SM::OFF_LB, s_lb);
     cp_async_wait_all();
-    __syncthreads();
-    if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 2] = gtimer();
+    __syncthreads();  // OFF_TAGG is visible; pass 2's first records have landed
+    if (warp == NWARPS - 1 && lane == 0) {
+        // inclusive prefix of the tile for the tiles behind it (off this tile's critical path)
+        const State incl = Tr::apply(load_elem<Elem>(sd + SM::OFF_TAGG), tpref);
+        store_elem(ws.tile_pref + (int64_t)tile * PREF_PITCH, incl);
+        __threadfence();
+        st_release(ws.flags + tile, ws.epoch4 + 2);
+    }
+    if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 2] = gtimer();
 
-    const State tpref = load_elem<State>(sd + SM::OFF_TSTATE);
     State wst = tpref;
-    if (warp > 0) wst = Tr::apply(load_elem<Elem>(sd + SM::OFF_WEXCL + warp * SM::N), tpref);
+    if (warp > 0) wst = Tr::apply(wex, tpref);
     const Elem lex = shfl_up_elem(inc, 1);
     State start = wst;
     if (lane > 0) start = Tr::apply(lex, wst);
@@ -1043,7 +1044,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     }
     acc1 += Tr::finish2(a, carry);
     Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);
-    if (ws.dbg && tid == 0) ws.dbg[tile * 4 + 3] = gtimer();
+    if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 3] = gtimer();
 
     if (Tr::HAS_SUMS) {
 #pragma unroll
@@ -1270,8 +1271,7 @@ cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int
                         int slots, cudaStream_t st, int *launches) {
     const int ntiles = (int)scan_num_tiles(positions, nsub);
     if (ntiles <= 0) return cudaSuccess;
-    (void)slots;
-    scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub);
+    scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub, slots);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -1323,7 +1323,7 @@ static size_t ws_tiles(int64_t n) { return (size_t)scan_num_tiles(n + CHUNK, 1) 
 
 size_t scan_workspace_bytes(int64_t n) {
     const size_t t = ws_tiles(n);
-    return 2 * align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
+    return align_up(t * AGG_PITCH * 8, 256) + align_up(t * PREF_PITCH * 8, 256) + align_up(t * 2 * 8, 256) +
            align_up((t + 4) * 4, 256);
 }
 
@@ -1332,8 +1332,6 @@ ScanWorkspace scan_workspace_carve(void *base, int64_t n) {
     unsigned char *p = static_cast<unsigned char *>(base);
     ScanWorkspace ws{};
     ws.tile_agg = reinterpret_cast<double *>(p);
-    p += align_up(t * AGG_PITCH * 8, 256);
-    ws.tile_agg1 = reinterpret_cast<double *>(p);
     p += align_up(t * AGG_PITCH * 8, 256);
     ws.tile_pref = reinterpret_cast<double *>(p);
     p += align_up(t * PREF_PITCH * 8, 256);

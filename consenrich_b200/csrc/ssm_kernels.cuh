@@ -25,10 +25,9 @@ constexpr int PREF_PITCH = 8;   // doubles per published tile prefix state (5 us
 
 struct ScanWorkspace {    // sized by scan_workspace_bytes(n); zeroed once when allocated
     double *tile_agg;     // [ntiles][AGG_PITCH]
-    double *tile_agg1;    // [ntiles][AGG_PITCH] level-1 aggregates (a tile and the 32 before it)
     double *tile_pref;    // [ntiles][PREF_PITCH]
     double *partials;     // [ntiles][2]
-    int32_t *flags;       // [ntiles]  epoch4 + 1 = aggregate, + 2 = level-1 aggregate, + 3 = prefix published
+    int32_t *flags;       // [ntiles]  epoch4 + 1 = aggregate published, epoch4 + 2 = inclusive prefix published
     int32_t *counters;    // [0] dynamic tile ticket, [1] tiles finished (reset by the last tile)
     int32_t epoch4;       // 4 * launch epoch: flags of earlier launches read as "nothing"
     long long *dbg;       // diagnostics: [ntiles][4] globaltimer stamps (start, pass 1 done, prefix known, end) or nullptr

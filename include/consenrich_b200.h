@@ -120,8 +120,9 @@ CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
  * depend on it beyond float64 re-association.  Also settable with CB200_SCAN_NSUB. */
 CB200_API int cb200_set_scan_substeps(int nsub);
 /* Diagnostics.  (tiles > 0, host_out NULL) arms phase stamping: every tile of the following scan
- * launches writes four %globaltimer values (start, run elements composed, prefix known, end).
- * (host_out non-NULL) copies the stamps of the last launch out ([tiles][4] int64 ns) and disarms. */
+ * launches writes eight %globaltimer values (0 start, 1 run elements composed, 2 prefix known, 3 end,
+ * 4 look-back flags ready, 5 window loaded, 6 window reduced, 7 aggregate published).
+ * (host_out non-NULL) copies the stamps of the last launch out ([tiles][8] int64 ns) and disarms. */
 CB200_API int cb200_debug_scan_times(cb200_ctx *ctx, int64_t tiles, long long *host_out);
 
 /* ---- memory helpers (so that hosts without torch can stage tracks) -------------------- */

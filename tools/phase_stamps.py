@@ -23,7 +23,7 @@ for ns in [int(x) for x in (sys.argv[1:] or ["0"])]:
         T = 6000
         _lib.check(L.cb200_debug_scan_times(ts.ctx.handle, T, None))
         fn()
-        buf = np.zeros((T, 4), np.int64)
+        buf = np.zeros((T, 8), np.int64)
         _lib.check(L.cb200_debug_scan_times(ts.ctx.handle, T, buf.ctypes.data_as(C.c_void_p)))
         buf = buf[buf[:, 0] > 0]
         t0 = buf[:, 0].min()
@@ -35,9 +35,9 @@ for ns in [int(x) for x in (sys.argv[1:] or ["0"])]:
         # per-tile series of the last configuration (forward then backward were run; re-run forward)
         _lib.check(L.cb200_debug_scan_times(ts.ctx.handle, 6000, None))
         ts.forward(model, kap=kap)
-        buf = np.zeros((6000, 4), np.int64)
+        buf = np.zeros((6000, 8), np.int64)
         _lib.check(L.cb200_debug_scan_times(ts.ctx.handle, 6000, buf.ctypes.data_as(C.c_void_p)))
         k = int((buf[:, 0] > 0).sum())
         b = (buf[:k] - buf[:k, 0].min()) / 1e3
         for t in list(range(0, 70, 3)) + list(range(70, k, 24)):
-            print(f"tile {t:4d} start {b[t,0]:6.1f} p1end {b[t,1]:6.1f} prefix {b[t,2]:6.1f} end {b[t,3]:6.1f}")
+            print(f"tile {t:4d} start {b[t,0]:6.1f} p1end {b[t,1]:6.1f} aggpub {b[t,7]:6.1f} flagsready {b[t,4]:6.1f} loaded {b[t,5]:6.1f} reduced {b[t,6]:6.1f} prefix {b[t,2]:6.1f} end {b[t,3]:6.1f}")

@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N scratch/split_nccl.py : one chromosome split over N GPUs (NCCL), checked
+"""torchrun --nproc-per-node N tools/split_nccl.py : one chromosome split over N GPUs (NCCL), checked
 against the same sweep done unsharded on rank 0's GPU."""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
