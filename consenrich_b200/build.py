@@ -43,7 +43,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS, *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB_PATH]
+    extra = os.environ.get("CB200_EXTRA_NVCC", "").split()  # e.g. -DSCAN_MIN_CTAS=3 for experiments
+    cmd = [_nvcc(), *NVCC_FLAGS, *extra, *[os.path.join(CSRC, s) for s in SOURCES], "-o", LIB_PATH]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd), file=sys.stderr)

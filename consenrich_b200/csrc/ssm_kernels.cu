@@ -219,14 +219,33 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
 // buffered so that the copies of sub-step s+1 fly while sub-step s is computed.  Long runs
 // amortise the warp scan, the cross-warp prefix and the look-back over L positions.
 //
-// Shared-memory record of one thread: CHUNK bins of BIN_BYTES plus 16 bytes of padding so that
-// 16-byte accesses of a quarter warp fall in distinct banks.
+// Shared-memory layout of a sub-step buffer: BIN_BYTES / 16 planes of 16-byte cells, one cell per
+// (thread, slot).  Two access patterns have to be free of bank conflicts: a thread walking its own
+// CHUNK slots (lanes t, t+1, ... read the same slot index: stride of one thread) and the staging
+// copies (lanes 4o .. 4o+3 touch the CHUNK slots of owner o: stride of one slot).  With 16-byte
+// cells a quarter warp covers all 32 banks exactly once in both patterns when slot i of thread t
+// sits at cell  t * CHUNK + ((i + (t >> 1)) mod CHUNK):  the rotation by t >> 1 spreads equal slot
+// indices of neighbouring threads over the four bank groups that 4 t leaves open.
+struct Cells {  // the cells of one thread
+    unsigned char *base;  // plane 0 of the buffer
+    int t4, rot;
+    __device__ __forceinline__ unsigned char *at(int i, int plane, int plane_bytes) const {
+        return base + plane * plane_bytes + ((t4 + ((i + rot) & (CHUNK - 1))) << 4);
+    }
+};
+
 template <int BIN_BYTES>
 struct RecGeom {
-    static constexpr int REC_BYTES = CHUNK * BIN_BYTES + 16;
-    static constexpr int BUF_BYTES = SCAN_THREADS * REC_BYTES;
-    __device__ static __forceinline__ unsigned char *slot(unsigned char *recs, int g) {
-        return recs + (g / CHUNK) * REC_BYTES + (g % CHUNK) * BIN_BYTES;
+    static_assert(BIN_BYTES % 16 == 0, "records are made of 16-byte cells");
+    static constexpr int PLANES = BIN_BYTES / 16;
+    static constexpr int PLANE_BYTES = SCAN_THREADS * CHUNK * 16;
+    static constexpr int BUF_BYTES = PLANES * PLANE_BYTES;
+    __device__ static __forceinline__ Cells cells(unsigned char *buf, int thread) {
+        return Cells{buf, thread * CHUNK, (thread >> 1) & (CHUNK - 1)};
+    }
+    // 16-byte cell `plane` of staged record g (thread g / CHUNK, slot g % CHUNK)
+    __device__ static __forceinline__ unsigned char *cell(unsigned char *buf, int g, int plane) {
+        return cells(buf, g / CHUNK).at(g % CHUNK, plane, PLANE_BYTES);
     }
 };
 
@@ -265,8 +284,8 @@ struct FwdRaw {
 };
 
 // qk = qScale / clamp(kappa), lam = clamp(lambda) from the raw float triple of a record
-__device__ __forceinline__ FwdRaw fwd_raw(const FwdArgs &a, const unsigned char *bin) {
-    const float4 w = *reinterpret_cast<const float4 *>(bin + 32);
+__device__ __forceinline__ FwdRaw fwd_raw(const FwdArgs &a, const unsigned char *cell2) {
+    const float4 w = *reinterpret_cast<const float4 *>(cell2);
     FwdRaw r;
     const double qs = a.use_qscale ? (double)w.y : 1.0;
     r.qk = a.use_kappa ? cb_div(qs, clampd((double)w.x, a.kap_min, a.kap_max)) : qs;
@@ -283,12 +302,13 @@ __device__ __forceinline__ void fwd_issue(const FwdArgs &a, unsigned char *buf, 
         const int64_t k = stage_pos(p0, L, s, g);
         const bool ok = k < a.n;
         const int64_t kk = ok ? k : 0;
-        unsigned char *d = RecGeom<48>::slot(buf, g);
-        cp_async<16>(d, a.SA + kk, ok);
-        if (ALL) cp_async<16>(d + 16, a.SB + kk, ok);
-        if (a.use_kappa) cp_async<4>(d + 32, a.kap + kk, ok);
-        if (a.use_qscale) cp_async<4>(d + 36, a.qs + kk, ok);
-        if (a.use_lambda) cp_async<4>(d + 40, a.lam + kk, ok);
+        using G = RecGeom<48>;
+        cp_async<16>(G::cell(buf, g, 0), a.SA + kk, ok);
+        if (ALL) cp_async<16>(G::cell(buf, g, 1), a.SB + kk, ok);
+        unsigned char *d2 = G::cell(buf, g, 2);
+        if (a.use_kappa) cp_async<4>(d2, a.kap + kk, ok);
+        if (a.use_qscale) cp_async<4>(d2 + 4, a.qs + kk, ok);
+        if (a.use_lambda) cp_async<4>(d2 + 8, a.lam + kk, ok);
     }
 }
 
@@ -329,13 +349,13 @@ struct Fwd2 {
     }
 
     template <bool FULLC>
-    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t,
+    __device__ static __forceinline__ void pass1(const Args &a, const Cells &rec, int lo, int hi, int64_t,
                                                  Elem &g) {
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
-                const FwdRaw w = fwd_raw(a, rec + i * 48);
+                const double2 s01 = *reinterpret_cast<const double2 *>(rec.at(i, 0, G::PLANE_BYTES));
+                const FwdRaw w = fwd_raw(a, rec.at(i, 2, G::PLANE_BYTES));
                 filt2_step<CANON>(g, a.M, w.qk * a.M.q00, w.qk * a.M.q01, w.qk * a.M.q11, w.lam * s01.x,
                                   w.lam * s01.y);
             }
@@ -354,7 +374,7 @@ struct Fwd2 {
     }
 
     template <bool FULLC>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
+    __device__ static __forceinline__ void pass2(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &acc_d, double &acc_nll) {
         Kf2 &s = c.s;
         NllAcc &acc = c.acc;
@@ -364,20 +384,25 @@ struct Fwd2 {
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                unsigned char *b = rec + i * 48;
-                const double2 s01 = *reinterpret_cast<const double2 *>(b);
-                const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
-                const FwdRaw w = fwd_raw(a, b);
+                unsigned char *b0 = rec.at(i, 0, G::PLANE_BYTES), *b1 = rec.at(i, 1, G::PLANE_BYTES), *b2 = rec.at(i, 2, G::PLANE_BYTES);
+                const double2 s01 = *reinterpret_cast<const double2 *>(b0);
+                const double2 s2l = *reinterpret_cast<const double2 *>(b1);
+                const FwdRaw w = fwd_raw(a, b2);
                 const bool counted = !(near_head && q0 + i >= a.head_from && q0 + i < HEAD_BINS);
                 BinOut o;
+#if defined(CB_EXP_NOSTEP)
+                o.Q00 = w.qk; o.Q01 = o.Q10 = 0; o.Q11 = w.lam; o.stat = s01.x + s2l.x; o.nll = 0;
+                s.x0 += s01.y * 1e-30;
+#else
                 kf2_step<CANON>(s, a.M, w.qk, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
                                 a.want_nll != 0 && counted, per_bin, o, acc);
+#endif
                 const float d = (float)o.stat;
                 if (counted) acc_d += (double)d;
                 acc_nll += o.nll;
-                *reinterpret_cast<float4 *>(b) = make_float4((float)s.P00, (float)s.P01, (float)s.P10, (float)s.P11);
-                *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.Q00, (float)o.Q01, (float)o.Q10, (float)o.Q11);
-                *reinterpret_cast<float4 *>(b + 32) = make_float4((float)s.x0, (float)s.x1, d, 0.0f);
+                *reinterpret_cast<float4 *>(b0) = make_float4((float)s.P00, (float)s.P01, (float)s.P10, (float)s.P11);
+                *reinterpret_cast<float4 *>(b1) = make_float4((float)o.Q00, (float)o.Q01, (float)o.Q10, (float)o.Q11);
+                *reinterpret_cast<float4 *>(b2) = make_float4((float)s.x0, (float)s.x1, d, 0.0f);
             }
         }
         if (a.want_nll && !per_bin) nll_acc_renorm(acc, a.use_lambda != 0);
@@ -392,15 +417,14 @@ struct Fwd2 {
             // bins [L, HEAD_BINS) of an unsharded chromosome are written by the head replay instead
             const bool head = k >= a.head_from && k < HEAD_BINS;
             if (k < a.n && !head) {
-                const unsigned char *d = G::slot(recs, g);
-                const float4 xd = *reinterpret_cast<const float4 *>(d + 32);
+                const float4 xd = *reinterpret_cast<const float4 *>(G::cell(recs, g, 2));
                 if (a.do_store) {
-                    reinterpret_cast<float4 *>(a.Pf)[k] = *reinterpret_cast<const float4 *>(d);
-                    if (k > 0) reinterpret_cast<float4 *>(a.Qf)[k - 1] = *reinterpret_cast<const float4 *>(d + 16);
+                    reinterpret_cast<float4 *>(a.Pf)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
+                    if (k > 0) reinterpret_cast<float4 *>(a.Qf)[k - 1] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 1));
                     reinterpret_cast<float2 *>(a.xf)[k] = make_float2(xd.x, xd.y);
                 }
                 // Q of the shard's first bin belongs to row n-1 of the preceding shard
-                if (k == 0 && a.q_head) *reinterpret_cast<float4 *>(a.q_head) = *reinterpret_cast<const float4 *>(d + 16);
+                if (k == 0 && a.q_head) *reinterpret_cast<float4 *>(a.q_head) = *reinterpret_cast<const float4 *>(G::cell(recs, g, 1));
                 if (a.D) a.D[k] = xd.z;
             }
         }
@@ -468,13 +492,13 @@ struct Fwd1 {
         fwd_issue<ALL>(a, buf, p0, L, s, tid);
     }
     template <bool FULLC>
-    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t,
+    __device__ static __forceinline__ void pass1(const Args &a, const Cells &rec, int lo, int hi, int64_t,
                                                  Elem &g) {
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                const double2 s01 = *reinterpret_cast<const double2 *>(rec + i * 48);
-                const FwdRaw w = fwd_raw(a, rec + i * 48);
+                const double2 s01 = *reinterpret_cast<const double2 *>(rec.at(i, 0, G::PLANE_BYTES));
+                const FwdRaw w = fwd_raw(a, rec.at(i, 2, G::PLANE_BYTES));
                 filt1_step(g, w.qk * a.M.q00, w.lam * s01.x, w.lam * s01.y);
             }
         }
@@ -490,7 +514,7 @@ struct Fwd1 {
     }
     __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t,
+    __device__ static __forceinline__ void pass2(const Args &a, const Cells &rec, int lo, int hi, int64_t,
                                                  Carry &c, double &acc_d, double &acc_nll) {
         State1 &s = c.s;
         NllAcc &acc = c.acc;
@@ -498,17 +522,17 @@ struct Fwd1 {
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                unsigned char *b = rec + i * 48;
-                const double2 s01 = *reinterpret_cast<const double2 *>(b);
-                const double2 s2l = *reinterpret_cast<const double2 *>(b + 16);
-                const FwdRaw w = fwd_raw(a, b);
+                unsigned char *b0 = rec.at(i, 0, G::PLANE_BYTES), *b1 = rec.at(i, 1, G::PLANE_BYTES), *b2 = rec.at(i, 2, G::PLANE_BYTES);
+                const double2 s01 = *reinterpret_cast<const double2 *>(b0);
+                const double2 s2l = *reinterpret_cast<const double2 *>(b1);
+                const FwdRaw w = fwd_raw(a, b2);
                 BinOut o;
                 kf1_step(s, w.qk * a.M.q00, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
                          a.want_nll != 0, per_bin, o, acc);
                 const float d = (float)o.stat;
                 acc_d += (double)d;
                 acc_nll += o.nll;
-                *reinterpret_cast<float4 *>(b) = make_float4((float)s.x, (float)s.P, (float)o.Q00, d);
+                *reinterpret_cast<float4 *>(b0) = make_float4((float)s.x, (float)s.P, (float)o.Q00, d);
             }
         }
         if (a.want_nll && !per_bin) nll_acc_renorm(acc, a.use_lambda != 0);
@@ -520,7 +544,7 @@ struct Fwd1 {
             const int g = stage_elem(tid, r);
             const int64_t k = stage_pos(p0, L, s, g);
             if (k < a.n) {
-                const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
+                const float4 o = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
                 if (a.do_store) {
                     a.xf[k] = o.x;
                     a.Pf[k] = o.y;
@@ -576,24 +600,25 @@ struct Bwd2 {
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             const bool ok = k >= 0 && k < a.n;
             const int64_t kk = ok ? k : 0;
-            unsigned char *d = G::slot(buf, g);
-            cp_async<16>(d, reinterpret_cast<const float4 *>(a.Pf) + kk, ok);
+            unsigned char *d2 = G::cell(buf, g, 2);
+            cp_async<16>(G::cell(buf, g, 0), reinterpret_cast<const float4 *>(a.Pf) + kk, ok);
             // row n-1 of Qf holds nothing unless a following shard supplied it
-            cp_async<16>(d + 16, reinterpret_cast<const float4 *>(a.Qf) + kk, ok && (k < a.n - 1 || !a.is_last_shard));
-            cp_async<8>(d + 32, reinterpret_cast<const float2 *>(a.xf) + kk, ok);
-            if (ALL && a.kap_out && a.qs) cp_async<4>(d + 44, a.qs + (kk + 1 < a.n ? kk + 1 : kk), ok);
+            cp_async<16>(G::cell(buf, g, 1), reinterpret_cast<const float4 *>(a.Qf) + kk,
+                         ok && (k < a.n - 1 || !a.is_last_shard));
+            cp_async<8>(d2, reinterpret_cast<const float2 *>(a.xf) + kk, ok);
+            if (ALL && a.kap_out && a.qs) cp_async<4>(d2 + 12, a.qs + (kk + 1 < a.n ? kk + 1 : kk), ok);
         }
     }
     template <bool FULLC>
-    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t q0,
+    __device__ static __forceinline__ void pass1(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Elem &g) {
         const int64_t klast = npad(a) - 1 - q0;  // bin of slot 0
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                const float4 P = *reinterpret_cast<const float4 *>(rec + i * 48);
-                const float4 Q = *reinterpret_cast<const float4 *>(rec + i * 48 + 16);
-                const float2 x = *reinterpret_cast<const float2 *>(rec + i * 48 + 32);
+                const float4 P = *reinterpret_cast<const float4 *>(rec.at(i, 0, G::PLANE_BYTES));
+                const float4 Q = *reinterpret_cast<const float4 *>(rec.at(i, 1, G::PLANE_BYTES));
+                const float2 x = *reinterpret_cast<const float2 *>(rec.at(i, 2, G::PLANE_BYTES));
                 Elem e;
                 if (klast - i == a.n - 1 && a.is_last_shard) {
                     e = smo2_from_state(State2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.w});
@@ -611,27 +636,27 @@ struct Bwd2 {
     __device__ static __forceinline__ double finish2(const Args &, const Carry &) { return 0.0; }
     __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
+    __device__ static __forceinline__ void pass2(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
         const int64_t klast = npad(a) - 1 - q0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                unsigned char *b = rec + i * 48;
-                const float4 P = *reinterpret_cast<const float4 *>(b);
-                const float4 Q = *reinterpret_cast<const float4 *>(b + 16);
-                const float2 x = *reinterpret_cast<const float2 *>(b + 32);
+                unsigned char *b0 = rec.at(i, 0, G::PLANE_BYTES), *b1 = rec.at(i, 1, G::PLANE_BYTES), *b2 = rec.at(i, 2, G::PLANE_BYTES);
+                const float4 P = *reinterpret_cast<const float4 *>(b0);
+                const float4 Q = *reinterpret_cast<const float4 *>(b1);
+                const float2 x = *reinterpret_cast<const float2 *>(b2);
                 if (klast - i == a.n - 1 && a.is_last_shard) {
                     c = Rs2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.z, (double)P.w};
                     // xs = xf, Ps = Pf already in place; lag row n-1 does not exist
                 } else {
                     const Rts2 r = rts2_gain<CANON>(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
                     const Rs2 nxt = c;  // smoothed bin k+1 as the reference stores it (float32 values)
-                    const float qs_next = *reinterpret_cast<const float *>(b + 44);
+                    const float qs_next = *reinterpret_cast<const float *>(b2 + 12);
                     Smo2Out o;
                     rts2_step(c, r, x.x, x.y, P.x, P.y, P.w, o);
-                    *reinterpret_cast<float4 *>(b) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
-                    *reinterpret_cast<float4 *>(b + 16) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
+                    *reinterpret_cast<float4 *>(b0) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
+                    *reinterpret_cast<float4 *>(b1) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
                     float kv = 1.0f;
                     if (a.kap_out) {
                         // the reference reads its float32 tracks back: c now holds bin k rounded that way
@@ -640,7 +665,7 @@ struct Bwd2 {
                                                   r32(o.C01), r32(o.C10), r32(o.C11), (double)qs_next, a.qs != nullptr,
                                                   a.nu, a.kap_lo, a.kap_hi);
                     }
-                    *reinterpret_cast<float4 *>(b + 32) = make_float4((float)o.xs0, (float)o.xs1, kv, 0.0f);
+                    *reinterpret_cast<float4 *>(b2) = make_float4((float)o.xs0, (float)o.xs1, kv, 0.0f);
                 }
             }
         }
@@ -653,11 +678,10 @@ struct Bwd2 {
             const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             if (k >= 0 && k < a.n) {
-                const unsigned char *d = G::slot(recs, g);
-                reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(d);
+                reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
                 if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
-                    reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(d + 16);
-                const float4 xk = *reinterpret_cast<const float4 *>(d + 32);
+                    reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 1));
+                const float4 xk = *reinterpret_cast<const float4 *>(G::cell(recs, g, 2));
                 reinterpret_cast<float2 *>(a.xs)[k] = make_float2(xk.x, xk.y);
                 if (a.kap_out) {
                     if (k + 1 < a.n) a.kap_out[k + 1] = xk.z;  // multiplier of the transition k -> k+1
@@ -707,7 +731,7 @@ struct Bwd1 {
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             const bool ok = k >= 0 && k < a.n;
             const int64_t kk = ok ? k : 0;
-            unsigned char *d = G::slot(buf, g);
+            unsigned char *d = G::cell(buf, g, 0);
             cp_async<4>(d, a.xf + kk, ok);
             cp_async<4>(d + 4, a.Pf + kk, ok);
             cp_async<4>(d + 8, a.Qf + kk, ok && (k < a.n - 1 || !a.is_last_shard));
@@ -715,13 +739,13 @@ struct Bwd1 {
         }
     }
     template <bool FULLC>
-    __device__ static __forceinline__ void pass1(const Args &a, const unsigned char *rec, int lo, int hi, int64_t q0,
+    __device__ static __forceinline__ void pass1(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Elem &g) {
         const int64_t klast = npad(a) - 1 - q0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                const float4 v = *reinterpret_cast<const float4 *>(rec + i * 16);
+                const float4 v = *reinterpret_cast<const float4 *>(rec.at(i, 0, G::PLANE_BYTES));
                 Elem e;
                 if (klast - i == a.n - 1 && a.is_last_shard) {
                     e = smo1_from_state(State1{(double)v.x, (double)v.y});
@@ -738,13 +762,13 @@ struct Bwd1 {
     __device__ static __forceinline__ double finish2(const Args &, const Carry &) { return 0.0; }
     __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
-    __device__ static __forceinline__ void pass2(const Args &a, unsigned char *rec, int lo, int hi, int64_t q0,
+    __device__ static __forceinline__ void pass2(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
         const int64_t klast = npad(a) - 1 - q0;
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
-                unsigned char *b = rec + i * 16;
+                unsigned char *b = rec.at(i, 0, G::PLANE_BYTES);
                 const float4 v = *reinterpret_cast<const float4 *>(b);
                 if (klast - i == a.n - 1 && a.is_last_shard) {
                     c.x = (double)v.x;
@@ -777,7 +801,7 @@ struct Bwd1 {
             const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             if (k >= 0 && k < a.n) {
-                const float4 o = *reinterpret_cast<const float4 *>(G::slot(recs, g));
+                const float4 o = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
                 a.xs[k] = o.x;
                 a.Ps[k] = o.y;
                 if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard)) a.lag[k] = o.z;
@@ -940,7 +964,6 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     const int L = CHUNK * nsub;
     const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
     const int64_t run0 = p0 + (int64_t)tid * L;
-    const int myoff = tid * Tr::G::REC_BYTES;
     auto buf = [&](int s) -> unsigned char * { return smem + (s & 1) * Tr::G::BUF_BYTES; };
 
     // ---- pass 1: every thread composes the element of its run; the copies of sub-step s+1 are
@@ -959,9 +982,9 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         int lo, hi;
         Tr::bounds(a, q0, lo, hi);
         if (lo == 0 && hi == CHUNK)
-            Tr::template pass1<true>(a, buf(s) + myoff, lo, hi, q0, mine);
+            Tr::template pass1<true>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, mine);
         else if (hi > lo)
-            Tr::template pass1<false>(a, buf(s) + myoff, lo, hi, q0, mine);
+            Tr::template pass1<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, mine);
     }
 
     // inclusive Kogge-Stone scan across the warp
@@ -1036,9 +1059,9 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         int lo, hi;
         Tr::bounds(a, q0, lo, hi);
         if (lo == 0 && hi == CHUNK)
-            Tr::template pass2<true>(a, buf(s) + myoff, lo, hi, q0, carry, acc0, acc1);
+            Tr::template pass2<true>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
         else if (hi > lo)
-            Tr::template pass2<false>(a, buf(s) + myoff, lo, hi, q0, carry, acc0, acc1);
+            Tr::template pass2<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
         __syncwarp();
         Tr::stage_out(a, buf(s), p0, L, s, tid);
     }
