@@ -270,6 +270,7 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
 
 struct KappaFuse {  // Student-t process precision update carried out inside the backward replay
     float *kap_out = nullptr;
+    bool no_store = false;  // do not write the smoothed tracks: only kappa is wanted
     const float *qs = nullptr;
     double nu = 0.0;
 };
@@ -294,6 +295,7 @@ int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf,
     a.is_last_shard = is_last;
     if (kf && kf->kap_out && !aggregate_only) {
         a.kap_out = kf->kap_out;
+        a.no_store = kf->no_store ? 1 : 0;
         a.qs = kf->qs;
         a.nu = kf->nu;
         a.kap_lo = mo->kap_min;
@@ -754,6 +756,11 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     double *sums = static_cast<double *>(c->sums.p);
     CB_TRY(do_fold(c, data, munc, m, n, ld, mo.pad, stats, stride));
 
+    // The smoothed tracks of an inner sweep are read by the multiplier updates only.  When kappa is
+    // the only one (the CLI default) and rides on the backward replay, the replay does not store them
+    // at all; one plain backward pass after the loop writes the tracks the call returns (it reads the
+    // forward tracks of the last sweep, which the kappa update does not touch).
+    const bool lean = kap != nullptr && lam == nullptr;
     // with_kappa: the kappa update of this inner iteration rides on the backward replay
     auto sweep = [&](bool with_kappa) -> int {
         cb200_model f = mo;
@@ -765,6 +772,7 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
             kf.kap_out = kap;
             kf.qs = qscale;
             kf.nu = op->nu;
+            kf.no_store = lean;
         }
         CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, &kf));
         return CB200_OK;
@@ -842,6 +850,8 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
             break;
         }
     }
+    if (lean && iters_done > 0 && op->inner_iters > 0)
+        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false));
     if (resid) CB_TRY(do_residuals(c, data, m, n, ld, xs, d, resid));
     CU_TRY(cudaStreamSynchronize(c->stream));
     res->iters_done = iters_done;

@@ -655,8 +655,10 @@ struct Bwd2 {
                     const float qs_next = *reinterpret_cast<const float *>(b2 + 12);
                     Smo2Out o;
                     rts2_step(c, r, x.x, x.y, P.x, P.y, P.w, o);
-                    *reinterpret_cast<float4 *>(b0) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
-                    *reinterpret_cast<float4 *>(b1) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
+                    if (!a.no_store) {
+                        *reinterpret_cast<float4 *>(b0) = make_float4((float)o.S00, (float)o.S01, (float)o.S01, (float)o.S11);
+                        *reinterpret_cast<float4 *>(b1) = make_float4((float)o.C00, (float)o.C01, (float)o.C10, (float)o.C11);
+                    }
                     float kv = 1.0f;
                     if (a.kap_out) {
                         // the reference reads its float32 tracks back: c now holds bin k rounded that way
@@ -678,11 +680,13 @@ struct Bwd2 {
             const int g = stage_elem(tid, r);
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             if (k >= 0 && k < a.n) {
-                reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
-                if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
-                    reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 1));
                 const float4 xk = *reinterpret_cast<const float4 *>(G::cell(recs, g, 2));
-                reinterpret_cast<float2 *>(a.xs)[k] = make_float2(xk.x, xk.y);
+                if (!a.no_store) {
+                    reinterpret_cast<float4 *>(a.Ps)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
+                    if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard))
+                        reinterpret_cast<float4 *>(a.lag)[k] = *reinterpret_cast<const float4 *>(G::cell(recs, g, 1));
+                    reinterpret_cast<float2 *>(a.xs)[k] = make_float2(xk.x, xk.y);
+                }
                 if (a.kap_out) {
                     if (k + 1 < a.n) a.kap_out[k + 1] = xk.z;  // multiplier of the transition k -> k+1
                     if (k == 0) a.kap_out[0] = 1.0f;
@@ -802,9 +806,11 @@ struct Bwd1 {
             const int64_t k = np - 1 - stage_pos(p0, L, s, g);
             if (k >= 0 && k < a.n) {
                 const float4 o = *reinterpret_cast<const float4 *>(G::cell(recs, g, 0));
-                a.xs[k] = o.x;
-                a.Ps[k] = o.y;
-                if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard)) a.lag[k] = o.z;
+                if (!a.no_store) {
+                    a.xs[k] = o.x;
+                    a.Ps[k] = o.y;
+                    if (k < a.lag_rows && (k < a.n - 1 || !a.is_last_shard)) a.lag[k] = o.z;
+                }
                 if (a.kap_out) {
                     if (k + 1 < a.n) a.kap_out[k + 1] = o.w;
                     if (k == 0) a.kap_out[0] = 1.0f;
@@ -1051,10 +1057,12 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
             cp_async_wait_all();
             __syncwarp();  // sub-step s has landed; the warp's stores of sub-step s-1 have read their buffer
         }
+#if !defined(CB_EXP_NOLOAD2)
         if (s + 1 < nsub) {
             Tr::template issue<true>(a, buf(s + 1), p0, L, s + 1, tid);
             cp_async_commit();
         }
+#endif
         const int64_t q0 = run0 + s * CHUNK;
         int lo, hi;
         Tr::bounds(a, q0, lo, hi);
@@ -1063,7 +1071,9 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         else if (hi > lo)
             Tr::template pass2<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
         __syncwarp();
+#if !defined(CB_EXP_NOSTORE)
         Tr::stage_out(a, buf(s), p0, L, s, tid);
+#endif
     }
     acc1 += Tr::finish2(a, carry);
     Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);

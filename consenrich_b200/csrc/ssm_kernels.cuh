@@ -63,6 +63,7 @@ struct BwdArgs {
     // kap_out[k+1] from the smoothed bins k, k+1 and their lag-one covariance, as soon as the replay
     // has them in registers.  kap_out == nullptr: off.
     float *kap_out;
+    int32_t no_store;          // with kap_out: do not write xs / Ps / lag (the ECM's inner sweeps need only kappa)
     const float *qs;           // processQScale or nullptr
     double nu, kap_lo, kap_hi;
     double qi00, qi01, qi10, qi11;  // Q0^-1 (state_dim 1: qi00 = 1 / Q0[0])
