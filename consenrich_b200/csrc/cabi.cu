@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -84,7 +85,7 @@ struct cb200_ctx {
     long long *scan_dbg = nullptr;  // diagnostics buffer (cb200_debug_scan_times)
     int64_t scan_dbg_tiles = 0;
     // arena (device)
-    DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, D, xs, Ps, lag, resid, lam, kap, qs, shard;
+    DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     double *sums_host = nullptr;  // pinned double[2]
     // timing
     bool timing = false;
@@ -437,7 +438,8 @@ void cb200_ctx_destroy(cb200_ctx *c) {
     DeviceGuard _dg(c ? c->device : 0);
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->D,
+    DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->xf2, &c->Pf2,
+                      &c->Qf2, &c->D,
                       &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -751,8 +753,15 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     CB_TRY(ensure(c, c->xf, (size_t)n * d * 4));
     CB_TRY(ensure(c, c->Pf, (size_t)n * d * d * 4));
     CB_TRY(ensure(c, c->Qf, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->xf2, (size_t)n * d * 4));
+    CB_TRY(ensure(c, c->Pf2, (size_t)n * d * d * 4));
+    CB_TRY(ensure(c, c->Qf2, (size_t)n * d * d * 4));
     double *stats = static_cast<double *>(c->stats.p);
+    // two sets of forward tracks: the NLL pass that closes an iteration is, when another iteration
+    // follows, the storing forward pass that iteration would open with (same multipliers, same
+    // arithmetic), run ahead of time into the spare set
     float *xf = static_cast<float *>(c->xf.p), *Pf = static_cast<float *>(c->Pf.p), *Qf = static_cast<float *>(c->Qf.p);
+    float *xf2 = static_cast<float *>(c->xf2.p), *Pf2 = static_cast<float *>(c->Pf2.p), *Qf2 = static_cast<float *>(c->Qf2.p);
     double *sums = static_cast<double *>(c->sums.p);
     CB_TRY(do_fold(c, data, munc, m, n, ld, mo.pad, stats, stride));
 
@@ -761,12 +770,14 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     // at all; one plain backward pass after the loop writes the tracks the call returns (it reads the
     // forward tracks of the last sweep, which the kappa update does not touch).
     const bool lean = kap != nullptr && lam == nullptr;
-    // with_kappa: the kappa update of this inner iteration rides on the backward replay
-    auto sweep = [&](bool with_kappa) -> int {
+    auto forward_store = [&](float *oxf, float *oPf, float *oQf, bool with_nll) -> int {
         cb200_model f = mo;
-        f.return_nll = 0;
-        CB_TRY(do_forward(c, &f, stats, stride, m, n, lam, kap, qscale, nullptr, xf, Pf, Qf, nullptr, nullptr, nullptr,
-                          false));
+        f.return_nll = with_nll ? 1 : 0;
+        return do_forward(c, &f, stats, stride, m, n, lam, kap, qscale, nullptr, oxf, oPf, oQf, nullptr,
+                          with_nll ? sums : nullptr, nullptr, false);
+    };
+    // with_kappa: the kappa update of this inner iteration rides on the backward replay
+    auto backward = [&](bool with_kappa) -> int {
         KappaFuse kf;
         if (with_kappa) {
             kf.kap_out = kap;
@@ -774,8 +785,11 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
             kf.nu = op->nu;
             kf.no_store = lean;
         }
-        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, &kf));
-        return CB200_OK;
+        return do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, &kf);
+    };
+    auto sweep = [&](bool with_kappa) -> int {
+        CB_TRY(forward_store(xf, Pf, Qf, false));
+        return backward(with_kappa);
     };
     auto nll_only = [&](double *out) -> int {
         cb200_model f = mo;
@@ -803,12 +817,18 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     double prev = 1.0e16, cur = 0.0, init_nll = 0.0, rel_impr = 0.0, abs_rel = 0.0;
     bool has_init = false, converged = false;
     int iters_done = 0, stable = 0, inc = 0;
+    bool opened = false;  // the forward pass of the next sweep has already run (into xf, Pf, Qf)
     for (int i = 0; i < op->max_iters; ++i) {
         iters_done = i + 1;
         for (int t = 0; t < op->inner_iters; ++t) {
             // kappa is read by the forward pass only, so the backward pass may overwrite it in place; the
             // lambda update (separate kernel) reads the smoothed tracks, not kappa
-            CB_TRY(sweep(kap != nullptr));
+            if (opened) {
+                CB_TRY(backward(kap != nullptr));
+                opened = false;
+            } else {
+                CB_TRY(sweep(kap != nullptr));
+            }
             if (lam) {
                 Span sp(c, FAM_PREC);
                 CU_TRY(launch_update_lambda(reinterpret_cast<const double2 *>(stats),
@@ -817,7 +837,15 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
                 c->launches += 1;
             }
         }
-        CB_TRY(nll_only(&cur));
+        const bool ahead = i + 1 < op->max_iters && op->inner_iters > 0;
+        if (ahead) {  // NLL of this iteration = by-product of the next iteration's opening forward pass
+            CB_TRY(forward_store(xf2, Pf2, Qf2, true));
+            double s2[2];
+            CB_TRY(read_sums(c, s2));
+            cur = s2[1];
+        } else {
+            CB_TRY(nll_only(&cur));
+        }
         if (nll_path) nll_path[i] = cur;
         const bool has_prev = has_init;
         if (!has_prev) {
@@ -847,7 +875,13 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
         stable = (has_prev && delta <= tol) ? stable + 1 : 0;
         if (stable >= patience) {
             converged = true;
-            break;
+            break;  // the tracks run ahead into the spare set are dropped
+        }
+        if (ahead) {  // the next iteration continues from the tracks just written
+            std::swap(xf, xf2);
+            std::swap(Pf, Pf2);
+            std::swap(Qf, Qf2);
+            opened = true;
         }
     }
     if (lean && iters_done > 0 && op->inner_iters > 0)
