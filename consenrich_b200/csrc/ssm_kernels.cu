@@ -390,13 +390,8 @@ struct Fwd2 {
                 const FwdRaw w = fwd_raw(a, b2);
                 const bool counted = !(near_head && q0 + i >= a.head_from && q0 + i < HEAD_BINS);
                 BinOut o;
-#if defined(CB_EXP_NOSTEP)
-                o.Q00 = w.qk; o.Q01 = o.Q10 = 0; o.Q11 = w.lam; o.stat = s01.x + s2l.x; o.nll = 0;
-                s.x0 += s01.y * 1e-30;
-#else
                 kf2_step<CANON>(s, a.M, w.qk, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
                                 a.want_nll != 0 && counted, per_bin, o, acc);
-#endif
                 const float d = (float)o.stat;
                 if (counted) acc_d += (double)d;
                 acc_nll += o.nll;
@@ -1057,12 +1052,10 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
             cp_async_wait_all();
             __syncwarp();  // sub-step s has landed; the warp's stores of sub-step s-1 have read their buffer
         }
-#if !defined(CB_EXP_NOLOAD2)
         if (s + 1 < nsub) {
             Tr::template issue<true>(a, buf(s + 1), p0, L, s + 1, tid);
             cp_async_commit();
         }
-#endif
         const int64_t q0 = run0 + s * CHUNK;
         int lo, hi;
         Tr::bounds(a, q0, lo, hi);
@@ -1071,9 +1064,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         else if (hi > lo)
             Tr::template pass2<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
         __syncwarp();
-#if !defined(CB_EXP_NOSTORE)
         Tr::stage_out(a, buf(s), p0, L, s, tid);
-#endif
     }
     acc1 += Tr::finish2(a, carry);
     Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);
