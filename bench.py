@@ -418,12 +418,18 @@ def run_b200_arm(args):
             pass
         peak, peak_src = (float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)") if "hbm_gbs" in peaks \
             else (6650.0, "fallback (B200_PROFILING.md)")
-        # Algorithmic bytes per launch (SURVEY 8d / DESIGN.md 4): the per-bin tracks each kernel has to
-        # read and write for the reference's sweep -- forward: statistics 32 + kappa 4 in, xf 8 + Pf 16
-        # + Q 16 out (no D: the ECM's storing passes do not emit it); backward: 40 in, 40 out; kappa
-        # update: xs 8 + Ps 16 (x2 neighbours, counted once) + lag 16 in, 4 out; fold and residuals per
-        # bin*sample.
-        alg = {"fold": cells * 8.0 + n * 32.0, "forward_scan": n * 76.0, "backward_scan": n * 80.0,
+        # Algorithmic bytes per launch (SURVEY 8d / DESIGN.md 4): the per-bin tracks each kernel HAS to read
+        # and write, averaged over the launches of one step.
+        #   forward : fold statistics 32 + kappa 4 in; a storing pass writes xf 8 + Pf 16 + Q 16 (the ECM's
+        #             storing passes do not emit D).  Per step: SWEEPS_PER_STEP storing passes (the NLL pass
+        #             that closes an iteration is the next iteration's opening pass) + 1 NLL-only pass.
+        #   backward: xf, Pf, Q 40 in.  The inner sweeps write only kappa (4): their smoothed tracks feed
+        #             nothing but the kappa update, which rides on the replay.  One plain pass per step
+        #             writes xs 8 + Ps 16 + lag 16.
+        n_fwd, n_bwd = SWEEPS_PER_STEP + 1, SWEEPS_PER_STEP + 1
+        fwd_bytes = (SWEEPS_PER_STEP * 76.0 + 36.0) / n_fwd
+        bwd_bytes = (SWEEPS_PER_STEP * 44.0 + 80.0) / n_bwd
+        alg = {"fold": cells * 8.0 + n * 32.0, "forward_scan": n * fwd_bytes, "backward_scan": n * bwd_bytes,
                "residuals": cells * 8.0 + n * 8.0, "precision_updates": n * 44.0}
         per = {k_: (v[0] / max(v[1], 1)) for k_, v in kern.items()}          # ms per launch
         tot = {k_: v[0] for k_, v in kern.items()}                           # ms inside the timed region
@@ -435,15 +441,16 @@ def run_b200_arm(args):
         # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch)
         traffic, traffic_src = None, None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1g_ncu_full_summary.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1h_ncu_full_summary.json")))
             traffic = float(prof["kernels"][dom]["dram_bytes_per_launch"])
-            traffic_src = "profiles/r1g_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+            traffic_src = "profiles/r1h_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": alg[dom],
+                    "frac_by_kernel": {k_: alg[k_] / (per[k_] * 1e-3) / 1e9 / peak for k_ in per if kern[k_][1] > 0},
                     "kernel_ms_per_launch": {k_: per[k_] for k_ in per if kern[k_][1] > 0},
                     "kernel_launches_per_step": {k_: kern[k_][1] / args.steps for k_ in per if kern[k_][1] > 0},
                     "kernel_share_of_step": {k_: tot[k_] / ms_total for k_ in per if kern[k_][1] > 0},
