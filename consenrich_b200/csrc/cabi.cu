@@ -85,7 +85,7 @@ struct cb200_ctx {
     long long *scan_dbg = nullptr;  // diagnostics buffer (cb200_debug_scan_times)
     int64_t scan_dbg_tiles = 0;
     // arena (device)
-    DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
+    DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, smo, smo2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     double *sums_host = nullptr;  // pinned double[2]
     // timing
     bool timing = false;
@@ -217,6 +217,13 @@ bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) %
 int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // ---- device-level building blocks ------------------------------------------------------
+struct SmoFuse {  // smoothing run elements composed by the forward replay for the backward scan
+    double *run = nullptr;  // 9 arrays of `pitch` doubles
+    int64_t pitch = 0;
+    int nsub = 0;           // sub-steps per run both scans use
+    int64_t npad = 0;       // forward tiles x tile length: where the backward scan counts positions from
+};
+
 int do_fold(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
             double *stats, int64_t stride) {
     Span sp(c, FAM_FOLD);
@@ -228,7 +235,8 @@ int do_fold(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64
 
 int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stride, int64_t m, int64_t n,
                const float *lam, const float *kap, const float *qs, const double *init_state, float *xf, float *Pf,
-               float *Qf, float *D, double *sums, double *agg_out, bool aggregate_only, float *q_head = nullptr) {
+               float *Qf, float *D, double *sums, double *agg_out, bool aggregate_only, float *q_head = nullptr,
+               const SmoFuse *sf = nullptr) {
     const int d = mo->state_dim;
     const bool store = (xf != nullptr);
     if (store && (!Pf || !Qf)) return fail(CB200_ERR_INVALID, "xf, Pf and Qf must be given together");
@@ -246,6 +254,11 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     a.init_state = init_state;
     a.xf = xf; a.Pf = Pf; a.Qf = Qf; a.D = D;
     a.q_head = q_head;
+    if (sf && sf->run && d == 2 && !aggregate_only && !init_state) {
+        a.smo_run = sf->run;
+        a.smo_pitch = sf->pitch;
+        a.nsub = sf->nsub;
+    }
     a.sums = sums;
     a.agg_out = agg_out;
     a.n = n;
@@ -278,7 +291,7 @@ struct KappaFuse {  // Student-t process precision update carried out inside the
 
 int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf, const float *Pf, const float *Qf,
                 const double *tail_state, int is_last, float *xs, float *Ps, float *lag, int64_t lag_rows,
-                double *agg_out, bool aggregate_only, const KappaFuse *kf = nullptr) {
+                double *agg_out, bool aggregate_only, const KappaFuse *kf = nullptr, const SmoFuse *sf = nullptr) {
     const int d = mo->state_dim;
     if (d == 2 && (!aligned(xf, 8) || !aligned(Pf, 16) || !aligned(Qf, 16) ||
                    (!aggregate_only && (!aligned(xs, 8) || !aligned(Ps, 16) || !aligned(lag, 16)))))
@@ -294,6 +307,12 @@ int do_backward(cb200_ctx *c, const cb200_model *mo, int64_t n, const float *xf,
     a.lag_rows = lag_rows;
     a.M = to_model2(mo);
     a.is_last_shard = is_last;
+    if (sf && sf->run && d == 2 && !aggregate_only && is_last && !tail_state) {
+        a.smo_run = sf->run;
+        a.smo_pitch = sf->pitch;
+        a.npad_fixed = sf->npad;
+        a.nsub = sf->nsub;
+    }
     if (kf && kf->kap_out && !aggregate_only) {
         a.kap_out = kf->kap_out;
         a.no_store = kf->no_store ? 1 : 0;
@@ -439,7 +458,7 @@ void cb200_ctx_destroy(cb200_ctx *c) {
     if (!c) return;
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->xf2, &c->Pf2,
-                      &c->Qf2, &c->D,
+                      &c->Qf2, &c->smo, &c->smo2, &c->D,
                       &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
@@ -765,6 +784,26 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     double *sums = static_cast<double *>(c->sums.p);
     CB_TRY(do_fold(c, data, munc, m, n, ld, mo.pad, stats, stride));
 
+    // 2-state model: the forward replay composes the smoother's run elements, so the backward scan
+    // needs no first pass.  Both scans then share one partition into runs.  Not when the runs are
+    // shorter than the head replay (tiny tracks): the head rewrites bins other threads composed from.
+    SmoFuse sfa, sfb;  // current / spare set, like the forward tracks
+    {
+        const int ns = scan_pick_nsub(n, 0);
+        if (d == 2 && CHUNK * ns >= HEAD_BINS) {
+            const int64_t tiles = scan_num_tiles(n, ns);
+            const int64_t runs = tiles * SCAN_THREADS;
+            const int64_t pitch = round_up(runs, 32);
+            CB_TRY(ensure(c, c->smo, (size_t)pitch * 9 * 8));
+            CB_TRY(ensure(c, c->smo2, (size_t)pitch * 9 * 8));
+            sfa.run = static_cast<double *>(c->smo.p);
+            sfb.run = static_cast<double *>(c->smo2.p);
+            sfa.pitch = sfb.pitch = pitch;
+            sfa.nsub = sfb.nsub = ns;
+            sfa.npad = sfb.npad = tiles * TILE_BINS * ns;
+        }
+    }
+
     // The smoothed tracks of an inner sweep are read by the multiplier updates only.  When kappa is
     // the only one (the CLI default) and rides on the backward replay, the replay does not store them
     // at all; one plain backward pass after the loop writes the tracks the call returns (it reads the
@@ -774,7 +813,7 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
         cb200_model f = mo;
         f.return_nll = with_nll ? 1 : 0;
         return do_forward(c, &f, stats, stride, m, n, lam, kap, qscale, nullptr, oxf, oPf, oQf, nullptr,
-                          with_nll ? sums : nullptr, nullptr, false);
+                          with_nll ? sums : nullptr, nullptr, false, nullptr, oxf == xf ? &sfa : &sfb);
     };
     // with_kappa: the kappa update of this inner iteration rides on the backward replay
     auto backward = [&](bool with_kappa) -> int {
@@ -785,7 +824,7 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
             kf.nu = op->nu;
             kf.no_store = lean;
         }
-        return do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, &kf);
+        return do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, &kf, &sfa);
     };
     auto sweep = [&](bool with_kappa) -> int {
         CB_TRY(forward_store(xf, Pf, Qf, false));
@@ -881,11 +920,12 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
             std::swap(xf, xf2);
             std::swap(Pf, Pf2);
             std::swap(Qf, Qf2);
+            std::swap(sfa, sfb);
             opened = true;
         }
     }
     if (lean && iters_done > 0 && op->inner_iters > 0)
-        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false));
+        CB_TRY(do_backward(c, &mo, n, xf, Pf, Qf, nullptr, 1, xs, Ps, lag, n > 1 ? n - 1 : 1, nullptr, false, nullptr, &sfa));
     if (resid) CB_TRY(do_residuals(c, data, m, n, ld, xs, d, resid));
     CU_TRY(cudaStreamSynchronize(c->stream));
     res->iters_done = iters_done;

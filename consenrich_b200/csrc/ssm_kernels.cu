@@ -321,9 +321,13 @@ struct Fwd2 {
     struct Carry {
         Kf2 s;
         NllAcc acc;
+        Smo2 brun;  // smoothing element of the bins replayed so far (FwdArgs::smo_run)
+        int nb;     // bins replayed so far
     };
     static constexpr bool HAS_SUMS = true;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
+    __device__ static __forceinline__ bool prebuilt(const Args &) { return false; }
+    __device__ static __forceinline__ Elem load_prebuilt(const Args &, int64_t) { return filt2_identity(); }
 
     __device__ static __forceinline__ Elem identity() { return filt2_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return filt2_combine(a, b); }
@@ -366,7 +370,36 @@ struct Fwd2 {
         Carry c;
         c.s = Kf2{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
         nll_acc_init(c.acc);
+        c.brun = smo2_identity();
+        c.nb = 0;
         return c;
+    }
+    // smoothing element of a bin from its filtered state (float32 values, as stored) and the float32
+    // process noise of the NEXT bin, composed onto the run element (later bins first: they are the
+    // ones the reverse scan meets first)
+    __device__ static __forceinline__ void compose_smo(const Args &a, Smo2 &brun, const Kf2 &f, double Q00, double Q01,
+                                                       double Q10, double Q11) {
+        const Rts2 r = rts2_gain<CANON>(a.M, f.x0, f.x1, f.P00, f.P01, f.P10, f.P11, r32(Q00), r32(Q01), r32(Q10), r32(Q11));
+        brun = smo2_combine(smo2_from_rts(r, f.x0, f.x1, f.P00, f.P01, f.P11), brun);
+    }
+    // After the replay of a run: its last bin's element (needs the NEXT run's first process noise, or
+    // is the terminal element of the chromosome), then the run element goes to global memory.
+    __device__ static __forceinline__ void finish_run(const Args &a, int64_t run, int64_t run0, int L, Carry &c) {
+        if (!a.smo_run) return;
+        const int64_t next = run0 + L;  // first bin of the next run
+        if (c.nb > 0) {
+            if (next >= a.n) {
+                // the run holds the last bin of the chromosome: x_s = x_f, P_s = P_f there
+                c.brun = smo2_combine(smo2_from_state(State2{c.s.x0, c.s.x1, c.s.P00, c.s.P01, c.s.P11}), c.brun);
+            } else {
+                const double qs = a.use_qscale ? (double)a.qs[next] : 1.0;
+                const double qk = a.use_kappa ? cb_div(qs, clampd((double)a.kap[next], a.kap_min, a.kap_max)) : qs;
+                compose_smo(a, c.brun, c.s, qk * a.M.q00, qk * a.M.q01, qk * a.M.q10, qk * a.M.q11);
+            }
+        }
+        const double *e = reinterpret_cast<const double *>(&c.brun);
+#pragma unroll
+        for (int i = 0; i < Smo2::N; ++i) a.smo_run[i * a.smo_pitch + run] = e[i];
     }
     // sum of the run's NLL pieces (one pair of logs per run)
     __device__ static __forceinline__ double finish2(const Args &a, const Carry &c) {
@@ -389,9 +422,14 @@ struct Fwd2 {
                 const double2 s2l = *reinterpret_cast<const double2 *>(b1);
                 const FwdRaw w = fwd_raw(a, b2);
                 const bool counted = !(near_head && q0 + i >= a.head_from && q0 + i < HEAD_BINS);
+                const Kf2 prev = s;  // filtered state of the previous bin, float32 values
                 BinOut o;
                 kf2_step<CANON>(s, a.M, w.qk, w.lam, s01.x, s01.y, s2l.x, s2l.y, a.m, a.inv_m, a.mlog2pi,
                                 a.want_nll != 0 && counted, per_bin, o, acc);
+                if (a.smo_run) {
+                    if (c.nb > 0) compose_smo(a, c.brun, prev, o.Q00, o.Q01, o.Q10, o.Q11);
+                    c.nb += 1;
+                }
                 const float d = (float)o.stat;
                 if (counted) acc_d += (double)d;
                 acc_nll += o.nll;
@@ -507,6 +545,9 @@ struct Fwd1 {
     __device__ static __forceinline__ double finish2(const Args &a, const Carry &c) {
         return (a.want_nll && !a.nll_in_d) ? nll_acc_finish(c.acc, a.m, a.mlog2pi) : 0.0;
     }
+    __device__ static __forceinline__ void finish_run(const Args &, int64_t, int64_t, int, Carry &) {}
+    __device__ static __forceinline__ bool prebuilt(const Args &) { return false; }
+    __device__ static __forceinline__ Elem load_prebuilt(const Args &, int64_t) { return filt1_identity(); }
     __device__ static __forceinline__ void epilogue(const Args &, int, int, int, Carry &, double &, double &) {}
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, const Cells &rec, int lo, int hi, int64_t,
@@ -566,7 +607,19 @@ struct Bwd2 {
     using Carry = Rs2;
     static constexpr bool HAS_SUMS = false;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
-    __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
+    __device__ static __forceinline__ int64_t npad(const Args &a) {
+        return a.npad_fixed > 0 ? a.npad_fixed : (a.n + CHUNK - 1) / CHUNK * CHUNK;
+    }
+    __device__ static __forceinline__ bool prebuilt(const Args &a) { return a.smo_run != nullptr; }
+    // run element composed by the forward scan: backward run `run` is forward run (runs - 1 - run)
+    __device__ static __forceinline__ Elem load_prebuilt(const Args &a, int64_t fwd_run) {
+        Elem e;
+        double *d = reinterpret_cast<double *>(&e);
+#pragma unroll
+        for (int i = 0; i < Elem::N; ++i) d[i] = __ldcg(a.smo_run + i * a.smo_pitch + fwd_run);
+        return e;
+    }
+    __device__ static __forceinline__ void finish_run(const Args &, int64_t, int64_t, int, Carry &) {}
 
     __device__ static __forceinline__ Elem identity() { return smo2_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo2_combine(a, b); }
@@ -704,6 +757,9 @@ struct Bwd1 {
     static constexpr bool HAS_SUMS = false;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
     __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
+    __device__ static __forceinline__ bool prebuilt(const Args &) { return false; }
+    __device__ static __forceinline__ Elem load_prebuilt(const Args &, int64_t) { return smo1_identity(); }
+    __device__ static __forceinline__ void finish_run(const Args &, int64_t, int64_t, int, Carry &) {}
 
     __device__ static __forceinline__ Elem identity() { return smo1_identity(); }
     __device__ static __forceinline__ Elem combine(const Elem &a, const Elem &b) { return smo1_combine(a, b); }
@@ -969,10 +1025,16 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
 
     // ---- pass 1: every thread composes the element of its run; the copies of sub-step s+1 are
     // in flight while sub-step s is computed ----
-    Tr::template issue<false>(a, buf(0), p0, L, 0, tid);
-    cp_async_commit();
     Elem mine = Tr::identity();
-    for (int s = 0; s < nsub; ++s) {
+    const bool prebuilt = !AGG_ONLY && Tr::prebuilt(a);
+    if (prebuilt) {
+        // the forward scan composed this run's element during its replay
+        mine = Tr::load_prebuilt(a, (int64_t)ntiles * SCAN_THREADS - 1 - ((int64_t)tile * SCAN_THREADS + tid));
+    } else {
+        Tr::template issue<false>(a, buf(0), p0, L, 0, tid);
+        cp_async_commit();
+    }
+    for (int s = 0; s < (prebuilt ? 0 : nsub); ++s) {
         cp_async_wait_all();
         __syncwarp();  // sub-step s has landed for the whole warp; its buffer (s+1)&1 is no longer read
         if (s + 1 < nsub) {
@@ -1067,6 +1129,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
         Tr::stage_out(a, buf(s), p0, L, s, tid);
     }
     acc1 += Tr::finish2(a, carry);
+    Tr::finish_run(a, (int64_t)tile * SCAN_THREADS + tid, run0, L, carry);
     Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);
     if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 3] = gtimer();
 
@@ -1421,7 +1484,7 @@ cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t
 cudaError_t launch_forward(int dim, const FwdArgs &a_in, const ScanWorkspace &ws, bool aggregate_only,
                            cudaStream_t st, int *launches) {
     if (dim == 2) {
-        const int ns = scan_pick_nsub(a_in.n, 0);
+        const int ns = a_in.nsub > 0 ? a_in.nsub : scan_pick_nsub(a_in.n, 0);
         FwdArgs a = a_in;
         a.head_from = (a.init_state == nullptr && !aggregate_only) ? CHUNK * ns : HEAD_BINS;
         if (canonical_F(a.M))
@@ -1439,9 +1502,9 @@ cudaError_t launch_forward(int dim, const FwdArgs &a_in, const ScanWorkspace &ws
 
 cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
                             cudaStream_t st, int *launches) {
-    const int64_t positions = (a.n + CHUNK - 1) / CHUNK * CHUNK;
+    const int64_t positions = (dim == 2 && a.npad_fixed > 0) ? a.npad_fixed : (a.n + CHUNK - 1) / CHUNK * CHUNK;
     if (dim == 2) {
-        const int ns = scan_pick_nsub(positions, 2);
+        const int ns = a.nsub > 0 ? a.nsub : scan_pick_nsub(positions, 2);
         if (canonical_F(a.M))
             return aggregate_only ? launch_scan<Bwd2<true>, true>(a, ws, positions, ns, g_slots[2], st, launches)
                                   : launch_scan<Bwd2<true>, false>(a, ws, positions, ns, g_slots[2], st, launches);

@@ -38,6 +38,13 @@ struct FwdArgs {
     const float *lam, *kap, *qs;
     const double *init_state;  // device, or nullptr -> model prior
     float *xf, *Pf, *Qf, *D;
+    // 2-state, whole chromosome, device pipelines: the replay also composes, run by run, the smoothing
+    // elements the backward scan would otherwise build in a pass of its own (it has every filtered
+    // state and process noise in registers at that moment).  smo_run: 9 arrays of smo_pitch doubles
+    // (structure of arrays over the forward runs), or nullptr.
+    double *smo_run;
+    int64_t smo_pitch;
+    int32_t nsub;              // sub-steps per run, fixed by the caller (0 = chosen per launch)
     float *q_head;             // device float[d*d] or nullptr: Q of this shard's first bin (row n-1 of
                                // the preceding shard's pNoiseForward)
     double *sums;              // device double[2] or nullptr
@@ -59,6 +66,12 @@ struct BwdArgs {
     int64_t n, lag_rows;
     Model2 M;
     int32_t is_last_shard;
+    // run elements composed by the forward scan (FwdArgs::smo_run): the backward scan then uses the
+    // forward scan's partition into runs (positions counted from npad_fixed = forward tiles x tile
+    // length, same nsub) and skips its own first pass.  nullptr: off.
+    const double *smo_run;
+    int64_t smo_pitch, npad_fixed;
+    int32_t nsub;
     // Student-t process precision update fused into the replay (cconsenrich.pyx:8252-8298, 7499-7521):
     // kap_out[k+1] from the smoothed bins k, k+1 and their lag-one covariance, as soon as the replay
     // has them in registers.  kap_out == nullptr: off.

@@ -393,3 +393,33 @@ def test_longest_chromosome_at_10bp_and_widest_cohort(cb, oracle):
         _compare_sweeps(got, want, n, dim, f"1000 tracks d{dim}")
         lvl = got["xs"][:, 0].astype(np.float64)
         np.testing.assert_array_equal(got["res"], (data.T.astype(np.float64) - lvl[:, None]).astype(np.float32))
+
+
+@pytest.mark.parametrize("nsub", [4, 7, 16])
+@pytest.mark.parametrize("opts", [
+    # the CLI configuration: kappa only -> lean inner sweeps, fused kappa update, run-ahead NLL pass
+    dict(ECM_fixedBackgroundIters=3, ECM_fixedBackgroundRtol=0.0, t_innerIters=2,
+         ECM_useObsPrecisionReweighting=False, procPrecisionMultiplierMin=5e-3, procPrecisionMultiplierMax=5e3),
+    # lambda and kappa, free-running with a tolerance (stops early: the run-ahead pass is dropped)
+    dict(ECM_fixedBackgroundIters=12, ECM_fixedBackgroundRtol=1e-3, t_innerIters=2),
+])
+def test_ecm_with_run_elements_composed_by_the_forward_replay(cb, oracle, nsub, opts):
+    """With runs of at least 16 bins the 2-state ECM lets the forward replay compose the smoother's run
+    elements and the backward scan skips its first pass.  The launch heuristic only picks such runs for
+    tracks of ~5e5 bins and more; force them on a track the oracle finishes quickly (several tiles, a
+    ragged last run, masked cells) and on one long enough for the heuristic itself."""
+    from consenrich_b200 import _lib
+    L = _lib.load()
+    try:
+        _lib.check(L.cb200_set_scan_substeps(nsub))
+        for m, n in ((7, 40_003), (3, 4 * nsub * 128 * 2 + 1)):
+            data, munc = synth_tracks(4000 + n, m, n, masked_frac=0.03)
+            a, b = _ecm(cb, 2, data, munc, **opts), _ecm(oracle, 2, data, munc, **opts)
+            _compare_ecm(a, b, f"fused nsub{nsub} {m}x{n}", exact_iters="ECM_fixedBackgroundRtol" in opts and opts["ECM_fixedBackgroundRtol"] == 0.0)
+    finally:
+        _lib.check(L.cb200_set_scan_substeps(0))
+    if nsub == 16:  # the heuristic's own choice on a long track
+        data, munc = synth_tracks(77, 2, 900_001)
+        o = dict(ECM_fixedBackgroundIters=2, ECM_fixedBackgroundRtol=0.0, t_innerIters=2,
+                 ECM_useObsPrecisionReweighting=False)
+        _compare_ecm(_ecm(cb, 2, data, munc, **o), _ecm(oracle, 2, data, munc, **o), "fused long track")
