@@ -325,6 +325,7 @@ struct Fwd2 {
         int nb;     // bins replayed so far
     };
     static constexpr bool HAS_SUMS = true;
+    static constexpr int MIN_CTAS = 3;  // 168 registers: the replay also carries the smoother's run element
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
     __device__ static __forceinline__ bool prebuilt(const Args &) { return false; }
     __device__ static __forceinline__ Elem load_prebuilt(const Args &, int64_t) { return filt2_identity(); }
@@ -506,6 +507,7 @@ struct Fwd1 {
         NllAcc acc;
     };
     static constexpr bool HAS_SUMS = true;
+    static constexpr int MIN_CTAS = SCAN_MIN_CTAS;
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
 
     __device__ static __forceinline__ Elem identity() { return filt1_identity(); }
@@ -606,6 +608,7 @@ struct Bwd2 {
     using G = RecGeom<48>;
     using Carry = Rs2;
     static constexpr bool HAS_SUMS = false;
+    static constexpr int MIN_CTAS = SCAN_MIN_CTAS;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
     __device__ static __forceinline__ int64_t npad(const Args &a) {
         return a.npad_fixed > 0 ? a.npad_fixed : (a.n + CHUNK - 1) / CHUNK * CHUNK;
@@ -755,6 +758,7 @@ struct Bwd1 {
         double x, P;
     };
     static constexpr bool HAS_SUMS = false;
+    static constexpr int MIN_CTAS = SCAN_MIN_CTAS;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
     __device__ static __forceinline__ int64_t npad(const Args &a) { return (a.n + CHUNK - 1) / CHUNK * CHUNK; }
     __device__ static __forceinline__ bool prebuilt(const Args &) { return false; }
@@ -1004,7 +1008,7 @@ struct ScanSmem {
 };
 
 template <class Tr, bool AGG_ONLY>
-__global__ void __launch_bounds__(SCAN_THREADS, SCAN_MIN_CTAS)
+__global__ void __launch_bounds__(SCAN_THREADS, Tr::MIN_CTAS)
 scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles, const int nsub, const int first_wave) {
     using Elem = typename Tr::Elem;
     using State = typename Tr::State;
@@ -1451,15 +1455,16 @@ cudaError_t configure_kernels() {
 
 void scan_set_nsub_override(int nsub) { g_nsub_override = nsub < 0 ? 0 : nsub; }
 
-// Sub-steps per run.  Longer runs amortise the warp scan and the look-back (fewer, longer tiles
-// also shorten the walk back to a published prefix), but the tiles must still cover the machine:
-// measured on B200 (chr19 @ 25 bp, 592 resident tiles) the scans run fastest with the longest
-// runs that leave about half of the tile slots filled.  which: 0 Fwd2, 1 Fwd1, 2 Bwd2, 3 Bwd1.
+// Sub-steps per run.  Longer runs amortise the warp scan and the look-back, but the tiles must still
+// cover the machine, and a launch that spills into a second wave of tiles pays for it: measured on
+// B200 (chr19 @ 25 bp) both scans run fastest with the longest runs that keep one wave about 94 %
+// full (417 tiles: 444 slots for the forward scan at 3 CTAs/SM, 592 for the others at 4).
+// which: 0 Fwd2, 1 Fwd1, 2 Bwd2, 3 Bwd1.
 int scan_pick_nsub(int64_t positions, int which) {
     if (g_nsub_override > 0) return g_nsub_override > MAX_NSUB ? MAX_NSUB : g_nsub_override;
-    const int slots = g_slots[which] > 0 ? g_slots[which] : 592;
-    const int64_t want_tiles = (int64_t)(0.45 * slots) + 1;
-    int64_t ns = positions / (TILE_BINS * want_tiles);
+    const int slots = g_slots[which] > 0 ? g_slots[which] : 444;
+    const int64_t want_tiles = (int64_t)((slots > 444 ? 0.705 : 0.94) * slots);
+    int64_t ns = (positions + TILE_BINS * want_tiles - 1) / (TILE_BINS * want_tiles);  // tiles <= want_tiles
     if (ns < 1) ns = 1;
     if (ns > MAX_NSUB) ns = MAX_NSUB;
     return (int)ns;
