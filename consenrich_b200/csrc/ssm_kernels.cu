@@ -996,12 +996,9 @@ struct ScanSmem {
     static constexpr int SN = Tr::State::N;
     static constexpr int REC_TOTAL = 2 * Tr::G::BUF_BYTES;  // double-buffered records
     // doubles after the records
-    static constexpr int OFF_WAGG = 0;                     // [NWARPS][N]
-    static constexpr int OFF_WEXCL = OFF_WAGG + NWARPS * N;  // [NWARPS][N]
-    static constexpr int OFF_TAGG = OFF_WEXCL + NWARPS * N;  // [N]
-    static constexpr int OFF_TSTATE = OFF_TAGG + N;          // [SN] exclusive prefix state of the tile
-    static constexpr int OFF_TINCL = OFF_TSTATE + SN;        // [SN]
-    static constexpr int OFF_RED = OFF_TINCL + SN;           // [NWARPS][2]
+    static constexpr int OFF_WAGG = 0;                   // [NWARPS][N] warp aggregates
+    static constexpr int OFF_TAGG = OFF_WAGG + NWARPS * N;  // [N] tile aggregate
+    static constexpr int OFF_RED = OFF_TAGG + N;            // [NWARPS][2] partial sums
     static constexpr int OFF_LB = OFF_RED + NWARPS * 2;      // [NWARPS][N] look-back: per-warp window results
     static constexpr int OFF_END = OFF_LB + NWARPS * N;
     static constexpr int BYTES = REC_TOTAL + OFF_END * 8 + 48;  // + s_tile[4], look-back ints[NWARPS]
