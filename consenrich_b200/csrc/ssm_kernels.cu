@@ -993,7 +993,6 @@ __device__ typename Tr::State cooperative_lookback(const typename Tr::Args &a, c
 template <class Tr>
 struct ScanSmem {
     static constexpr int N = Tr::Elem::N;
-    static constexpr int SN = Tr::State::N;
     static constexpr int REC_TOTAL = 2 * Tr::G::BUF_BYTES;  // double-buffered records
     // doubles after the records
     static constexpr int OFF_WAGG = 0;                   // [NWARPS][N] warp aggregates
