@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <utility>
 #include <string>
@@ -84,6 +85,8 @@ struct cb200_ctx {
     int64_t scan_ws_n = 0;   // track length the scan workspace is laid out for
     long long *scan_dbg = nullptr;  // diagnostics buffer (cb200_debug_scan_times)
     int64_t scan_dbg_tiles = 0;
+    int scan_dbg_pick = -1;  // CB200_DEBUG_STAMP_LAUNCH: only this scan launch after arming stamps (-1: all)
+    int scan_dbg_seen = 0;
     // arena (device)
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, smo, smo2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     double *sums_host = nullptr;  // pinned double[2]
@@ -131,7 +134,9 @@ int next_scan_ws(cb200_ctx *c, int64_t n, ScanWorkspace *ws) {
     c->scan_epoch += 1;
     *ws = scan_workspace_carve(c->scan_ws.p, c->scan_ws_n);
     ws->epoch4 = c->scan_epoch * 4;
-    ws->dbg = c->scan_dbg;
+    ws->dbg = nullptr;
+    if (c->scan_dbg && (c->scan_dbg_pick < 0 || c->scan_dbg_seen == c->scan_dbg_pick)) ws->dbg = c->scan_dbg;
+    if (c->scan_dbg) c->scan_dbg_seen += 1;
     return CB200_OK;
 }
 
@@ -533,6 +538,9 @@ int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
         CU_TRY(cudaMalloc(reinterpret_cast<void **>(&c->scan_dbg), (size_t)tiles * 8 * sizeof(long long)));
         CU_TRY(cudaMemset(c->scan_dbg, 0, (size_t)tiles * 8 * sizeof(long long)));
         c->scan_dbg_tiles = tiles;
+        const char *pick = getenv("CB200_DEBUG_STAMP_LAUNCH");
+        c->scan_dbg_pick = pick && *pick ? atoi(pick) : -1;
+        c->scan_dbg_seen = 0;
     }
     return CB200_OK;
 }

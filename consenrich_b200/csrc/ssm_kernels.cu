@@ -25,6 +25,12 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NWARPS = SCAN_THREADS / 32;
+#ifndef FWD2_MIN_CTAS
+#define FWD2_MIN_CTAS 3
+#endif
+#ifndef BWD2_MIN_CTAS
+#define BWD2_MIN_CTAS 4
+#endif
 #ifndef SCAN_MIN_CTAS
 #define SCAN_MIN_CTAS 4
 #endif
@@ -272,6 +278,17 @@ __device__ __forceinline__ void cp_async(void *dst_smem, const void *src, bool o
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
+// same, source known to be valid (no src-size operand)
+template <int BYTES>
+__device__ __forceinline__ void cp_async_full(void *dst_smem, const void *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    if (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+    else if (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -284,25 +301,35 @@ struct FwdRaw {
 };
 
 // qk = qScale / clamp(kappa), lam = clamp(lambda) from the raw float triple of a record
+// qk = qScale / clamp(kappa) from the raw float32 multipliers
+__device__ __forceinline__ double fwd_qk(const FwdArgs &a, float kap, float qscale) {
+    const double qs = a.use_qscale ? (double)qscale : 1.0;
+    return a.use_kappa ? cb_div(qs, clampd((double)kap, a.kap_min, a.kap_max)) : qs;
+}
+
 __device__ __forceinline__ FwdRaw fwd_raw(const FwdArgs &a, const unsigned char *cell2) {
     const float4 w = *reinterpret_cast<const float4 *>(cell2);
     FwdRaw r;
-    const double qs = a.use_qscale ? (double)w.y : 1.0;
-    r.qk = a.use_kappa ? cb_div(qs, clampd((double)w.x, a.kap_min, a.kap_max)) : qs;
+    r.qk = fwd_qk(a, w.x, w.y);
     // the reference clamps in double and uses the double value (pyx:432-435)
     r.lam = a.use_lambda ? clampd((double)w.z, a.lam_min, a.lam_max) : 1.0;
     return r;
 }
 
+// process-noise scale of bin k read straight from global memory (run boundaries, head replay)
+__device__ __forceinline__ double fwd_qk_global(const FwdArgs &a, int64_t k) {
+    return fwd_qk(a, a.use_kappa ? a.kap[k] : 1.0f, a.use_qscale ? a.qs[k] : 1.0f);
+}
+
 template <bool ALL>
 __device__ __forceinline__ void fwd_issue(const FwdArgs &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
+    using G = RecGeom<48>;
 #pragma unroll
     for (int r = 0; r < CHUNK; ++r) {
         const int g = stage_elem(tid, r);
         const int64_t k = stage_pos(p0, L, s, g);
         const bool ok = k < a.n;
         const int64_t kk = ok ? k : 0;
-        using G = RecGeom<48>;
         cp_async<16>(G::cell(buf, g, 0), a.SA + kk, ok);
         if (ALL) cp_async<16>(G::cell(buf, g, 1), a.SB + kk, ok);
         unsigned char *d2 = G::cell(buf, g, 2);
@@ -325,7 +352,7 @@ struct Fwd2 {
         int nb;     // bins replayed so far
     };
     static constexpr bool HAS_SUMS = true;
-    static constexpr int MIN_CTAS = 3;  // 168 registers: the replay also carries the smoother's run element
+    static constexpr int MIN_CTAS = FWD2_MIN_CTAS;  // 3: 168 registers: the replay also carries the smoother's run element
     __device__ static __forceinline__ double *sums(const Args &a) { return a.sums; }
     __device__ static __forceinline__ bool prebuilt(const Args &) { return false; }
     __device__ static __forceinline__ Elem load_prebuilt(const Args &, int64_t) { return filt2_identity(); }
@@ -393,8 +420,7 @@ struct Fwd2 {
                 // the run holds the last bin of the chromosome: x_s = x_f, P_s = P_f there
                 c.brun = smo2_combine(smo2_from_state(State2{c.s.x0, c.s.x1, c.s.P00, c.s.P01, c.s.P11}), c.brun);
             } else {
-                const double qs = a.use_qscale ? (double)a.qs[next] : 1.0;
-                const double qk = a.use_kappa ? cb_div(qs, clampd((double)a.kap[next], a.kap_min, a.kap_max)) : qs;
+                const double qk = fwd_qk_global(a, next);
                 compose_smo(a, c.brun, c.s, qk * a.M.q00, qk * a.M.q01, qk * a.M.q10, qk * a.M.q11);
             }
         }
@@ -475,8 +501,7 @@ struct Fwd2 {
         nll_acc_init(acc);
         for (int64_t k = L; k < end; ++k) {
             const double2 s01 = a.SA[k], s2l = a.SB[k];
-            const double qs = a.use_qscale ? (double)a.qs[k] : 1.0;
-            const double qk = a.use_kappa ? cb_div(qs, clampd((double)a.kap[k], a.kap_min, a.kap_max)) : qs;
+            const double qk = fwd_qk_global(a, k);
             const double lam = a.use_lambda ? clampd((double)a.lam[k], a.lam_min, a.lam_max) : 1.0;
             BinOut o;
             kf2_step<CANON>(s, a.M, qk, lam, s01.x, s01.y, s2l.x, a.want_nll ? s2l.y : 0.0, a.m, a.inv_m, a.mlog2pi,
@@ -608,7 +633,7 @@ struct Bwd2 {
     using G = RecGeom<48>;
     using Carry = Rs2;
     static constexpr bool HAS_SUMS = false;
-    static constexpr int MIN_CTAS = SCAN_MIN_CTAS;
+    static constexpr int MIN_CTAS = BWD2_MIN_CTAS;
     __device__ static __forceinline__ double *sums(const Args &) { return nullptr; }
     __device__ static __forceinline__ int64_t npad(const Args &a) {
         return a.npad_fixed > 0 ? a.npad_fixed : (a.n + CHUNK - 1) / CHUNK * CHUNK;
@@ -645,10 +670,28 @@ struct Bwd2 {
     template <bool ALL>
     __device__ static __forceinline__ void issue(const Args &a, unsigned char *buf, int64_t p0, int L, int s, int tid) {
         const int64_t np = npad(a);
+        // the thread's CHUNK records are 8 runs apart: bins k0 - 8 L r
+        const int g0 = stage_elem(tid, 0);
+        const int64_t k0 = np - 1 - stage_pos(p0, L, s, g0);
+        const int64_t dk = (int64_t)(32 / CHUNK) * L;
+        const bool want_qs = ALL && a.kap_out && a.qs;
+        if (k0 - (CHUNK - 1) * dk >= 0 && k0 < a.n - 1) {  // all inside the track, none the last bin
+#pragma unroll
+            for (int r = 0; r < CHUNK; ++r) {
+                const int g = g0 + 32 * r;
+                const int64_t k = k0 - r * dk;
+                unsigned char *d2 = G::cell(buf, g, 2);
+                cp_async_full<16>(G::cell(buf, g, 0), reinterpret_cast<const float4 *>(a.Pf) + k);
+                cp_async_full<16>(G::cell(buf, g, 1), reinterpret_cast<const float4 *>(a.Qf) + k);
+                cp_async_full<8>(d2, reinterpret_cast<const float2 *>(a.xf) + k);
+                if (want_qs) cp_async_full<4>(d2 + 12, a.qs + k + 1);
+            }
+            return;
+        }
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = stage_elem(tid, r);
-            const int64_t k = np - 1 - stage_pos(p0, L, s, g);
+            const int g = g0 + 32 * r;
+            const int64_t k = k0 - r * dk;
             const bool ok = k >= 0 && k < a.n;
             const int64_t kk = ok ? k : 0;
             unsigned char *d2 = G::cell(buf, g, 2);
@@ -657,13 +700,19 @@ struct Bwd2 {
             cp_async<16>(G::cell(buf, g, 1), reinterpret_cast<const float4 *>(a.Qf) + kk,
                          ok && (k < a.n - 1 || !a.is_last_shard));
             cp_async<8>(d2, reinterpret_cast<const float2 *>(a.xf) + kk, ok);
-            if (ALL && a.kap_out && a.qs) cp_async<4>(d2 + 12, a.qs + (kk + 1 < a.n ? kk + 1 : kk), ok);
+            if (want_qs) cp_async<4>(d2 + 12, a.qs + (kk + 1 < a.n ? kk + 1 : kk), ok);
         }
+    }
+    // slot (0..CHUNK-1) of the sub-step starting at position q0 that holds the chromosome's last bin
+    // (x_s = x_f there), or -1
+    __device__ static __forceinline__ int last_bin_slot(const Args &a, int64_t q0) {
+        const int64_t di = (npad(a) - 1 - q0) - (a.n - 1);
+        return (a.is_last_shard && di >= 0 && di < CHUNK) ? (int)di : -1;
     }
     template <bool FULLC>
     __device__ static __forceinline__ void pass1(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Elem &g) {
-        const int64_t klast = npad(a) - 1 - q0;  // bin of slot 0
+        const int i_end = last_bin_slot(a, q0);
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
@@ -671,7 +720,7 @@ struct Bwd2 {
                 const float4 Q = *reinterpret_cast<const float4 *>(rec.at(i, 1, G::PLANE_BYTES));
                 const float2 x = *reinterpret_cast<const float2 *>(rec.at(i, 2, G::PLANE_BYTES));
                 Elem e;
-                if (klast - i == a.n - 1 && a.is_last_shard) {
+                if (i == i_end) {
                     e = smo2_from_state(State2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.w});
                 } else {
                     const Rts2 r = rts2_gain<CANON>(a.M, x.x, x.y, P.x, P.y, P.z, P.w, Q.x, Q.y, Q.z, Q.w);
@@ -689,7 +738,7 @@ struct Bwd2 {
     template <bool FULLC>
     __device__ static __forceinline__ void pass2(const Args &a, const Cells &rec, int lo, int hi, int64_t q0,
                                                  Carry &c, double &, double &) {
-        const int64_t klast = npad(a) - 1 - q0;
+        const int i_end = last_bin_slot(a, q0);
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
@@ -697,7 +746,7 @@ struct Bwd2 {
                 const float4 P = *reinterpret_cast<const float4 *>(b0);
                 const float4 Q = *reinterpret_cast<const float4 *>(b1);
                 const float2 x = *reinterpret_cast<const float2 *>(b2);
-                if (klast - i == a.n - 1 && a.is_last_shard) {
+                if (i == i_end) {
                     c = Rs2{(double)x.x, (double)x.y, (double)P.x, (double)P.y, (double)P.z, (double)P.w};
                     // xs = xf, Ps = Pf already in place; lag row n-1 does not exist
                 } else {
@@ -713,10 +762,10 @@ struct Bwd2 {
                     float kv = 1.0f;
                     if (a.kap_out) {
                         // the reference reads its float32 tracks back: c now holds bin k rounded that way
-                        kv = (float)kappa2_update(a.M, a.qi00, a.qi01, a.qi10, a.qi11, c.x0, c.x1, c.P00, c.P01, c.P10,
-                                                  c.P11, nxt.x0, nxt.x1, nxt.P00, nxt.P01, nxt.P10, nxt.P11, r32(o.C00),
-                                                  r32(o.C01), r32(o.C10), r32(o.C11), (double)qs_next, a.qs != nullptr,
-                                                  a.nu, a.kap_lo, a.kap_hi);
+                        kv = (float)kappa2_update<CANON>(a.M, a.qi00, a.qi01, a.qi10, a.qi11, c.x0, c.x1, c.P00, c.P01, c.P10,
+                                                         c.P11, nxt.x0, nxt.x1, nxt.P00, nxt.P01, nxt.P10, nxt.P11, r32(o.C00),
+                                                         r32(o.C01), r32(o.C10), r32(o.C11), (double)qs_next, a.qs != nullptr,
+                                                         a.nu, a.kap_lo, a.kap_hi);
                     }
                     *reinterpret_cast<float4 *>(b2) = make_float4((float)o.xs0, (float)o.xs1, kv, 0.0f);
                 }
@@ -726,10 +775,13 @@ struct Bwd2 {
     __device__ static __forceinline__ void stage_out(const Args &a, unsigned char *recs, int64_t p0, int L, int s,
                                                      int tid) {
         const int64_t np = npad(a);
+        const int g0 = stage_elem(tid, 0);
+        const int64_t k0 = np - 1 - stage_pos(p0, L, s, g0);
+        const int64_t dk = (int64_t)(32 / CHUNK) * L;
 #pragma unroll
         for (int r = 0; r < CHUNK; ++r) {
-            const int g = stage_elem(tid, r);
-            const int64_t k = np - 1 - stage_pos(p0, L, s, g);
+            const int g = g0 + 32 * r;
+            const int64_t k = k0 - r * dk;
             if (k >= 0 && k < a.n) {
                 const float4 xk = *reinterpret_cast<const float4 *>(G::cell(recs, g, 2));
                 if (!a.no_store) {
@@ -977,7 +1029,6 @@ __device__ typename Tr::State cooperative_lookback(const typename Tr::Args &a, c
         Elem win = load_elem<Elem>(sd_red + last_warp * N);
         for (int w = last_warp - 1; w >= 0; --w) win = Tr::combine(win, load_elem<Elem>(sd_red + w * N));
         running = have ? Tr::combine(win, running) : win;
-        if (ws.dbg && tid == 0 && !have) ws.dbg[tile * 8 + 6] = gtimer();
         have = true;
         if (first < (1 << 30)) break;
         base -= SCAN_THREADS * c;
@@ -990,16 +1041,25 @@ __device__ typename Tr::State cooperative_lookback(const typename Tr::Args &a, c
 // =====================================================================================
 // scan kernel
 // =====================================================================================
+// A CTA works through tiles it claims from a counter, software-pipelined over two tiles: it
+// composes the run elements of the NEXT tile and publishes that tile's aggregate (stage 1) before
+// it looks back and replays the tile it claimed before (stage 2).  By the time a tile's look-back
+// starts, the aggregates of the tiles in front of it have had a whole stage 1 to arrive, so the
+// wait that a single-pass scan otherwise spends between its two passes is filled with the next
+// tile's first pass.  A claimed tile's stage 1 follows its claim without any wait in between, so
+// every aggregate a look-back waits for is being produced by a running CTA: no deadlock whatever
+// the number of resident CTAs.
 template <class Tr>
 struct ScanSmem {
     static constexpr int N = Tr::Elem::N;
     static constexpr int REC_TOTAL = 2 * Tr::G::BUF_BYTES;  // double-buffered records
     // doubles after the records
-    static constexpr int OFF_WAGG = 0;                   // [NWARPS][N] warp aggregates
-    static constexpr int OFF_TAGG = OFF_WAGG + NWARPS * N;  // [N] tile aggregate
-    static constexpr int OFF_RED = OFF_TAGG + N;            // [NWARPS][2] partial sums
+    static constexpr int OFF_WAGG = 0;                       // [NWARPS][N] warp aggregates
+    static constexpr int OFF_TAGG = OFF_WAGG + NWARPS * N;   // [2][N] tile aggregates (pending tile, next tile)
+    static constexpr int OFF_RED = OFF_TAGG + 2 * N;         // [NWARPS][2] partial sums
     static constexpr int OFF_LB = OFF_RED + NWARPS * 2;      // [NWARPS][N] look-back: per-warp window results
-    static constexpr int OFF_END = OFF_LB + NWARPS * N;
+    static constexpr int OFF_EX = OFF_LB + NWARPS * N;       // [N][SCAN_THREADS] exclusive elements of the pending tile
+    static constexpr int OFF_END = OFF_EX + N * SCAN_THREADS;
     static constexpr int BYTES = REC_TOTAL + OFF_END * 8 + 48;  // + s_tile[4], look-back ints[NWARPS]
 };
 
@@ -1012,155 +1072,187 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     extern __shared__ __align__(16) unsigned char smem[];
     double *sd = reinterpret_cast<double *>(smem + SM::REC_TOTAL);
     int *s_tile = reinterpret_cast<int *>(sd + SM::OFF_END);
+    int *s_lb = s_tile + 4;
+    double *sd_ex = sd + SM::OFF_EX + threadIdx.x;  // this thread's column
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) s_tile[0] = AGG_ONLY ? (int)blockIdx.x : atomicAdd(ws.counters, 1);
-    __syncthreads();
-    const int tile = s_tile[0];
-    if (ws.dbg && tid == 0) ws.dbg[tile * 8] = gtimer();
     const int L = CHUNK * nsub;
-    const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
-    const int64_t run0 = p0 + (int64_t)tid * L;
     auto buf = [&](int s) -> unsigned char * { return smem + (s & 1) * Tr::G::BUF_BYTES; };
 
-    // ---- pass 1: every thread composes the element of its run; the copies of sub-step s+1 are
-    // in flight while sub-step s is computed ----
-    Elem mine = Tr::identity();
-    const bool prebuilt = !AGG_ONLY && Tr::prebuilt(a);
-    if (prebuilt) {
-        // the forward scan composed this run's element during its replay
-        mine = Tr::load_prebuilt(a, (int64_t)ntiles * SCAN_THREADS - 1 - ((int64_t)tile * SCAN_THREADS + tid));
-    } else {
-        Tr::template issue<false>(a, buf(0), p0, L, 0, tid);
-        cp_async_commit();
-    }
-    for (int s = 0; s < (prebuilt ? 0 : nsub); ++s) {
-        cp_async_wait_all();
-        __syncwarp();  // sub-step s has landed for the whole warp; its buffer (s+1)&1 is no longer read
-        if (s + 1 < nsub) {
-            Tr::template issue<false>(a, buf(s + 1), p0, L, s + 1, tid);
-            cp_async_commit();
-        }
-        const int64_t q0 = run0 + s * CHUNK;
-        int lo, hi;
-        Tr::bounds(a, q0, lo, hi);
-        if (lo == 0 && hi == CHUNK)
-            Tr::template pass1<true>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, mine);
-        else if (hi > lo)
-            Tr::template pass1<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, mine);
-    }
-
-    // inclusive Kogge-Stone scan across the warp
-    Elem inc = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const Elem o = shfl_up_elem(inc, d);
-        if (lane >= d) inc = Tr::combine(o, inc);
-    }
-    if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
-    __syncthreads();
-    if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 1] = gtimer();
-    if (!AGG_ONLY) {
-        // pass 2's first sub-step is fetched underneath the serial section below
-        Tr::template issue<true>(a, buf(0), p0, L, 0, tid);
-        cp_async_commit();
-    }
-
-    // the serial section (cross-warp prefix, look-back, publication) rotates over the warps so
-    // that it does not always land on the same SM sub-partition
-    // ---- scan section: cross-warp prefix, publication of the tile aggregate, look-back ----
-    // every warp forms its own exclusive prefix over the warps before it (lane-redundant); the last
-    // warp also forms and publishes the tile aggregate
-    Elem wex = warp > 0 ? load_elem<Elem>(sd + SM::OFF_WAGG) : Tr::identity();
-    for (int w = 1; w < warp; ++w) wex = Tr::combine(wex, load_elem<Elem>(sd + SM::OFF_WAGG + w * SM::N));
-    if (warp == NWARPS - 1) {
-        const Elem tagg = Tr::combine(wex, load_elem<Elem>(sd + SM::OFF_WAGG + warp * SM::N));
-        if (lane == 0) {
-            store_elem(sd + SM::OFF_TAGG, tagg);
-            store_elem(ws.tile_agg + (int64_t)tile * AGG_PITCH, tagg);
-            if (!AGG_ONLY) {
-                __threadfence();
-                st_release(ws.flags + tile, ws.epoch4 + 1);
-                if (ws.dbg) ws.dbg[tile * 8 + 7] = gtimer();
-            }
-        }
-    }
-    if (AGG_ONLY) return;
-    int *s_lb = s_tile + 4;
-    const State tpref = tile == 0 ? Tr::initial(a)
-                                  : cooperative_lookback<Tr>(a, ws, tile, first_wave, tid, sd + SM::OFF_LB, s_lb);
-    cp_async_wait_all();
-    __syncthreads();  // OFF_TAGG is visible; pass 2's first records have landed
-    if (warp == NWARPS - 1 && lane == 0) {
-        // inclusive prefix of the tile for the tiles behind it (off this tile's critical path)
-        const State incl = Tr::apply(load_elem<Elem>(sd + SM::OFF_TAGG), tpref);
-        store_elem(ws.tile_pref + (int64_t)tile * PREF_PITCH, incl);
-        __threadfence();
-        st_release(ws.flags + tile, ws.epoch4 + 2);
-    }
-    if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 2] = gtimer();
-
-    State wst = tpref;
-    if (warp > 0) wst = Tr::apply(wex, tpref);
-    const Elem lex = shfl_up_elem(inc, 1);
-    State start = wst;
-    if (lane > 0) start = Tr::apply(lex, wst);
-
-    // ---- pass 2: replay the reference's recursion over the run from its exact start state ----
-    typename Tr::Carry carry = Tr::begin2(a, start);
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int s = 0; s < nsub; ++s) {
-        if (s) {
-            cp_async_wait_all();
-            __syncwarp();  // sub-step s has landed; the warp's stores of sub-step s-1 have read their buffer
-        }
-        if (s + 1 < nsub) {
-            Tr::template issue<true>(a, buf(s + 1), p0, L, s + 1, tid);
-            cp_async_commit();
-        }
-        const int64_t q0 = run0 + s * CHUNK;
-        int lo, hi;
-        Tr::bounds(a, q0, lo, hi);
-        if (lo == 0 && hi == CHUNK)
-            Tr::template pass2<true>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
-        else if (hi > lo)
-            Tr::template pass2<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
-        __syncwarp();
-        Tr::stage_out(a, buf(s), p0, L, s, tid);
-    }
-    acc1 += Tr::finish2(a, carry);
-    Tr::finish_run(a, (int64_t)tile * SCAN_THREADS + tid, run0, L, carry);
-    Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);
-    if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 3] = gtimer();
-
-    if (Tr::HAS_SUMS) {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            acc0 += __shfl_xor_sync(FULL, acc0, d);
-            acc1 += __shfl_xor_sync(FULL, acc1, d);
-        }
-        if (lane == 0) {
-            sd[SM::OFF_RED + warp * 2] = acc0;
-            sd[SM::OFF_RED + warp * 2 + 1] = acc1;
-        }
+    int cur = -1;  // tile whose run elements are composed and whose replay is pending
+    for (int it = 0;; ++it) {
+        // ---- claim the next tile ----
+        if (tid == 0) s_tile[0] = AGG_ONLY ? (int)blockIdx.x : atomicAdd(ws.counters, 1);
         __syncthreads();
-    }
-    if (tid == 0) {
-        if (Tr::HAS_SUMS) {
-            double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-            for (int w = 0; w < NWARPS; ++w) {
-                t0 += sd[SM::OFF_RED + w * 2];
-                t1 += sd[SM::OFF_RED + w * 2 + 1];
+        const int nxt = s_tile[0];
+        const bool have_next = nxt < ntiles;
+
+        // ================= stage 1 of tile nxt: run elements, warp scan, aggregate =================
+        Elem ex_next = Tr::identity();  // composition of the runs of this tile in front of this thread's
+        if (have_next) {
+            const int tile = nxt;
+            if (ws.dbg && tid == 0) ws.dbg[tile * 8] = gtimer();
+            const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
+            const int64_t run0 = p0 + (int64_t)tid * L;
+            Elem mine = Tr::identity();
+            const bool prebuilt = !AGG_ONLY && Tr::prebuilt(a);
+            if (prebuilt) {
+                // the forward scan composed this run's element during its replay
+                mine = Tr::load_prebuilt(a, (int64_t)ntiles * SCAN_THREADS - 1 - ((int64_t)tile * SCAN_THREADS + tid));
+            } else {
+                __syncwarp();  // the warp's stores of the preceding replay have read their records
+                Tr::template issue<false>(a, buf(0), p0, L, 0, tid);
+                cp_async_commit();
             }
-            ws.partials[(int64_t)tile * 2] = t0;
-            ws.partials[(int64_t)tile * 2 + 1] = t1;
-            __threadfence();
+            // the copies of sub-step s+1 are in flight while sub-step s is computed
+            for (int s = 0; s < (prebuilt ? 0 : nsub); ++s) {
+                cp_async_wait_all();
+                __syncwarp();  // sub-step s has landed for the whole warp; its buffer (s+1)&1 is no longer read
+                if (s + 1 < nsub) {
+                    Tr::template issue<false>(a, buf(s + 1), p0, L, s + 1, tid);
+                    cp_async_commit();
+                }
+                const int64_t q0 = run0 + s * CHUNK;
+                int lo, hi;
+                Tr::bounds(a, q0, lo, hi);
+                if (lo == 0 && hi == CHUNK)
+                    Tr::template pass1<true>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, mine);
+                else if (hi > lo)
+                    Tr::template pass1<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, mine);
+            }
+            // inclusive Kogge-Stone scan across the warp
+            Elem inc = mine;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const Elem o = shfl_up_elem(inc, d);
+                if (lane >= d) inc = Tr::combine(o, inc);
+            }
+            if (lane == 31) store_elem(sd + SM::OFF_WAGG + warp * SM::N, inc);
+            __syncthreads();
+            if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 1] = gtimer();
+            // every warp forms its own exclusive prefix over the warps before it (lane-redundant); the
+            // last warp also forms and publishes the tile aggregate
+            Elem wex = warp > 0 ? load_elem<Elem>(sd + SM::OFF_WAGG) : Tr::identity();
+            for (int w = 1; w < warp; ++w) wex = Tr::combine(wex, load_elem<Elem>(sd + SM::OFF_WAGG + w * SM::N));
+            if (warp == NWARPS - 1) {
+                const Elem tagg = Tr::combine(wex, load_elem<Elem>(sd + SM::OFF_WAGG + warp * SM::N));
+                if (lane == 0) {
+                    store_elem(sd + SM::OFF_TAGG + (it & 1) * SM::N, tagg);
+                    store_elem(ws.tile_agg + (int64_t)tile * AGG_PITCH, tagg);
+                    if (!AGG_ONLY) {
+                        __threadfence();
+                        st_release(ws.flags + tile, ws.epoch4 + 1);
+                        if (ws.dbg) ws.dbg[tile * 8 + 7] = gtimer();
+                    }
+                }
+            }
+            if (!AGG_ONLY) {
+                const Elem lex = shfl_up_elem(inc, 1);
+                ex_next = lane > 0 ? (warp > 0 ? Tr::combine(wex, lex) : lex) : wex;
+            }
         }
+        if (AGG_ONLY) return;
+
+        // hand over: the pending tile's exclusive element comes out of this thread's column of
+        // shared memory, the next tile's goes in (thread-private, no barrier)
+        Elem ex_cur = Tr::identity();
+        if (cur >= 0) {
+            double *d = reinterpret_cast<double *>(&ex_cur);
+#pragma unroll
+            for (int i = 0; i < SM::N; ++i) d[i] = sd_ex[i * SCAN_THREADS];
+        }
+        if (have_next) {
+            const double *d = reinterpret_cast<const double *>(&ex_next);
+#pragma unroll
+            for (int i = 0; i < SM::N; ++i) sd_ex[i * SCAN_THREADS] = d[i];
+        }
+
+        // ================= stage 2 of tile cur: look-back, prefix, replay =================
+        if (cur >= 0) {
+            const int tile = cur;
+            const int64_t p0 = (int64_t)tile * TILE_BINS * nsub;
+            const int64_t run0 = p0 + (int64_t)tid * L;
+            // the replay's first sub-step is fetched underneath the look-back
+            __syncwarp();
+            Tr::template issue<true>(a, buf(0), p0, L, 0, tid);
+            cp_async_commit();
+            if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 6] = gtimer();
+            const State tpref = tile == 0 ? Tr::initial(a)
+                                          : cooperative_lookback<Tr>(a, ws, tile, first_wave, tid, sd + SM::OFF_LB, s_lb);
+            cp_async_wait_all();
+            __syncthreads();  // the replay's first records have landed
+            if (warp == NWARPS - 1 && lane == 0) {
+                // inclusive prefix of the tile for the tiles behind it (off this tile's critical path)
+                const State incl = Tr::apply(load_elem<Elem>(sd + SM::OFF_TAGG + ((it + 1) & 1) * SM::N), tpref);
+                store_elem(ws.tile_pref + (int64_t)tile * PREF_PITCH, incl);
+                __threadfence();
+                st_release(ws.flags + tile, ws.epoch4 + 2);
+            }
+            if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 2] = gtimer();
+            const State start = tid == 0 ? tpref : Tr::apply(ex_cur, tpref);
+
+            // replay the reference's recursion over the run from its exact start state
+            typename Tr::Carry carry = Tr::begin2(a, start);
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int s = 0; s < nsub; ++s) {
+                if (s) {
+                    cp_async_wait_all();
+                    __syncwarp();  // sub-step s has landed; the warp's stores of sub-step s-1 have read their buffer
+                }
+                if (s + 1 < nsub) {
+                    Tr::template issue<true>(a, buf(s + 1), p0, L, s + 1, tid);
+                    cp_async_commit();
+                }
+                const int64_t q0 = run0 + s * CHUNK;
+                int lo, hi;
+                Tr::bounds(a, q0, lo, hi);
+                if (lo == 0 && hi == CHUNK)
+                    Tr::template pass2<true>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
+                else if (hi > lo)
+                    Tr::template pass2<false>(a, Tr::G::cells(buf(s), tid), lo, hi, q0, carry, acc0, acc1);
+                __syncwarp();
+                Tr::stage_out(a, buf(s), p0, L, s, tid);
+            }
+            acc1 += Tr::finish2(a, carry);
+            Tr::finish_run(a, (int64_t)tile * SCAN_THREADS + tid, run0, L, carry);
+            Tr::epilogue(a, tile, tid, L, carry, acc0, acc1);
+            if (ws.dbg && tid == 0) ws.dbg[tile * 8 + 3] = gtimer();
+
+            if (Tr::HAS_SUMS) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) {
+                    acc0 += __shfl_xor_sync(FULL, acc0, d);
+                    acc1 += __shfl_xor_sync(FULL, acc1, d);
+                }
+                if (lane == 0) {
+                    sd[SM::OFF_RED + warp * 2] = acc0;
+                    sd[SM::OFF_RED + warp * 2 + 1] = acc1;
+                }
+                __syncthreads();
+                if (tid == 0) {
+                    double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NWARPS; ++w) {
+                        t0 += sd[SM::OFF_RED + w * 2];
+                        t1 += sd[SM::OFF_RED + w * 2 + 1];
+                    }
+                    ws.partials[(int64_t)tile * 2] = t0;
+                    ws.partials[(int64_t)tile * 2 + 1] = t1;
+                }
+            }
+        }
+        if (!have_next) break;
+        cur = nxt;
+        __syncthreads();  // s_tile[0] and the scratch of this iteration are rewritten by the next
+    }
+
+    // ---- this CTA is done: the last one to leave resets the counters and adds up the partial sums ----
+    if (tid == 0) {
+        __threadfence();
         const int done = atomicAdd(ws.counters + 1, 1);
-        const int last = (done == ntiles - 1) ? 1 : 0;
+        const int last = (done == (int)gridDim.x - 1) ? 1 : 0;
         if (last) {
-            // every tile has taken its ticket and finished: leave the counters ready for the next launch
+            // every CTA has made its last (failing) claim: leave the counters ready for the next launch
             ws.counters[0] = 0;
             ws.counters[1] = 0;
             __threadfence();
@@ -1170,7 +1262,7 @@ scan_kernel(const typename Tr::Args a, const ScanWorkspace ws, const int ntiles,
     if (Tr::HAS_SUMS) {
         __syncthreads();
         if (s_tile[1] && warp == 0) {
-            // the last CTA to finish adds the per-tile partial sums in tile order
+            // per-tile partial sums in tile order
             double t0 = 0.0, t1 = 0.0;
             for (int t = lane; t < ntiles; t += 32) {
                 t0 += __ldcg(ws.partials + (int64_t)t * 2);
@@ -1358,7 +1450,10 @@ cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int
                         int slots, cudaStream_t st, int *launches) {
     const int ntiles = (int)scan_num_tiles(positions, nsub);
     if (ntiles <= 0) return cudaSuccess;
-    scan_kernel<Tr, AGG_ONLY><<<ntiles, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub, slots);
+    // aggregate-only: one CTA per tile; full scan: as many CTAs as are resident, each working through
+    // the tiles it claims
+    const int grid = AGG_ONLY ? ntiles : (slots > 0 && slots < ntiles ? slots : ntiles);
+    scan_kernel<Tr, AGG_ONLY><<<grid, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub, ntiles);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

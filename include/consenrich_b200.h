@@ -115,14 +115,16 @@ CB200_API int64_t cb200_ctx_launch_count(const cb200_ctx *ctx);
 CB200_API int cb200_ctx_enable_timing(cb200_ctx *ctx, int on);
 CB200_API int cb200_ctx_kernel_ms(cb200_ctx *ctx, int family, double *ms, int64_t *launches);
 CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
-/* Tuning knob (process-wide): sub-steps of 8 bins each thread of the scan kernels runs through
- * (1..8), 0 = choose per launch from the track length and the resident tile slots.  Results do not
+/* Tuning knob (process-wide): sub-steps of 4 bins each thread of the scan kernels runs through
+ * (1..16), 0 = choose per launch from the track length and the resident tile slots.  Results do not
  * depend on it beyond float64 re-association.  Also settable with CB200_SCAN_NSUB. */
 CB200_API int cb200_set_scan_substeps(int nsub);
 /* Diagnostics.  (tiles > 0, host_out NULL) arms phase stamping: every tile of the following scan
  * launches writes eight %globaltimer values (0 start, 1 run elements composed, 2 prefix known, 3 end,
- * 4 look-back flags ready, 5 window loaded, 6 window reduced, 7 aggregate published).
- * (host_out non-NULL) copies the stamps of the last launch out ([tiles][8] int64 ns) and disarms. */
+ * 4 look-back flags ready, 5 window loaded, 6 look-back entered, 7 aggregate published).
+ * (host_out non-NULL) copies the stamps of the last launch out ([tiles][8] int64 ns) and disarms.
+ * With CB200_DEBUG_STAMP_LAUNCH=k in the environment when arming, only the k-th (0-based) scan
+ * launch after arming stamps, so that one launch inside cb200_ecm_device can be looked at. */
 CB200_API int cb200_debug_scan_times(cb200_ctx *ctx, int64_t tiles, long long *host_out);
 
 /* ---- memory helpers (so that hosts without torch can stage tracks) -------------------- */
