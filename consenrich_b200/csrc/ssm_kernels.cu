@@ -303,8 +303,10 @@ struct FwdRaw {
 // qk = qScale / clamp(kappa), lam = clamp(lambda) from the raw float triple of a record
 // qk = qScale / clamp(kappa) from the raw float32 multipliers
 __device__ __forceinline__ double fwd_qk(const FwdArgs &a, float kap, float qscale) {
+    // branch-free (selects): the replay loops hoist these ahead of the serial per-bin chain
     const double qs = a.use_qscale ? (double)qscale : 1.0;
-    return a.use_kappa ? cb_div(qs, clampd((double)kap, a.kap_min, a.kap_max)) : qs;
+    const double kc = a.use_kappa ? clampd((double)kap, a.kap_min, a.kap_max) : 1.0;
+    return cb_div(qs, kc);
 }
 
 __device__ __forceinline__ FwdRaw fwd_raw(const FwdArgs &a, const unsigned char *cell2) {
@@ -383,11 +385,15 @@ struct Fwd2 {
     template <bool FULLC>
     __device__ static __forceinline__ void pass1(const Args &a, const Cells &rec, int lo, int hi, int64_t,
                                                  Elem &g) {
+        // the multipliers of the CHUNK bins first: independent of one another and of the chain below
+        FwdRaw wr[CHUNK];
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) wr[i] = fwd_raw(a, rec.at(i, 2, G::PLANE_BYTES));
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
                 const double2 s01 = *reinterpret_cast<const double2 *>(rec.at(i, 0, G::PLANE_BYTES));
-                const FwdRaw w = fwd_raw(a, rec.at(i, 2, G::PLANE_BYTES));
+                const FwdRaw w = wr[i];
                 filt2_step<CANON>(g, a.M, w.qk * a.M.q00, w.qk * a.M.q01, w.qk * a.M.q11, w.lam * s01.x,
                                   w.lam * s01.y);
             }
@@ -441,13 +447,16 @@ struct Fwd2 {
         const bool per_bin = a.nll_in_d != 0;
         // bins [head_from, HEAD_BINS) are written and summed by the head replay (epilogue)
         const bool near_head = q0 < HEAD_BINS && q0 + CHUNK > a.head_from;
+        FwdRaw wr[CHUNK];
+#pragma unroll
+        for (int i = 0; i < CHUNK; ++i) wr[i] = fwd_raw(a, rec.at(i, 2, G::PLANE_BYTES));
 #pragma unroll
         for (int i = 0; i < CHUNK; ++i) {
             if (FULLC || (i >= lo && i < hi)) {
                 unsigned char *b0 = rec.at(i, 0, G::PLANE_BYTES), *b1 = rec.at(i, 1, G::PLANE_BYTES), *b2 = rec.at(i, 2, G::PLANE_BYTES);
                 const double2 s01 = *reinterpret_cast<const double2 *>(b0);
                 const double2 s2l = *reinterpret_cast<const double2 *>(b1);
-                const FwdRaw w = fwd_raw(a, b2);
+                const FwdRaw w = wr[i];
                 const bool counted = !(near_head && q0 + i >= a.head_from && q0 + i < HEAD_BINS);
                 const Kf2 prev = s;  // filtered state of the previous bin, float32 values
                 BinOut o;
