@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libconsenrich_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 FAM_FOLD, FAM_FORWARD, FAM_BACKWARD, FAM_RESIDUALS, FAM_PRECISION = range(5)
 FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates")
@@ -42,7 +42,7 @@ class EcmOpts(C.Structure):
     """cb200_ecm_opts"""
     _fields_ = [
         ("max_iters", C.c_int32), ("inner_iters", C.c_int32), ("update_lambda", C.c_int32),
-        ("update_kappa", C.c_int32), ("want_outputs", C.c_int32), ("reserved0", C.c_int32),
+        ("update_kappa", C.c_int32), ("want_outputs", C.c_int32), ("init_ones", C.c_int32),
         ("rtol", C.c_double), ("nu", C.c_double),
     ]
 

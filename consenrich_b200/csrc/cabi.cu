@@ -396,6 +396,15 @@ int upload_vec(cb200_ctx *c, DevBuf &buf, const float *host, int64_t n, bool liv
     return CB200_OK;
 }
 
+// a multiplier vector that starts at 1: filled on the device, nothing crosses the bus
+int ones_vec(cb200_ctx *c, DevBuf &buf, int64_t n, const float **dev_out) {
+    CB_TRY(ensure(c, buf, (size_t)n * 4));
+    CU_TRY(launch_fill(static_cast<float *>(buf.p), n, 1.0f, c->stream));
+    c->launches += 1;
+    *dev_out = static_cast<const float *>(buf.p);
+    return CB200_OK;
+}
+
 int read_sums(cb200_ctx *c, double *out2) {
     CB_TRY(d2h(c, c->sums_host, c->sums.p, 16));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -1088,8 +1097,10 @@ int cb200_host_ecm(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op
     CB_TRY(upload_tracks(c, c->munc, munc, m, n, &ld2));
     const float *dqs, *dlam_c, *dkap_c;
     CB_TRY(upload_vec(c, c->qs, qscale, n, qscale != nullptr, &dqs));
-    CB_TRY(upload_vec(c, c->lam, lam, n, lam != nullptr, &dlam_c));
-    CB_TRY(upload_vec(c, c->kap, kap, n, kap != nullptr, &dkap_c));
+    if (lam && (op->init_ones & 1)) CB_TRY(ones_vec(c, c->lam, n, &dlam_c));
+    else CB_TRY(upload_vec(c, c->lam, lam, n, lam != nullptr, &dlam_c));
+    if (kap && (op->init_ones & 2)) CB_TRY(ones_vec(c, c->kap, n, &dkap_c));
+    else CB_TRY(upload_vec(c, c->kap, kap, n, kap != nullptr, &dkap_c));
     CB_TRY(ensure(c, c->xs, (size_t)n * d * 4));
     CB_TRY(ensure(c, c->Ps, (size_t)n * d * d * 4));
     CB_TRY(ensure(c, c->lag, (size_t)n * d * d * 4));

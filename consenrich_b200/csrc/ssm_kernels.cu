@@ -1452,6 +1452,11 @@ __global__ void kappa1_kernel(double q0inv, int64_t n, const float *__restrict__
                                       (double)lag[k], q, qs != nullptr, nu, lo, hi);
 }
 
+__global__ void fill_kernel(float *v, int64_t n, float value) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = value;
+}
+
 static int g_slots[4] = {0, 0, 0, 0};  // Fwd2, Fwd1, Bwd2, Bwd1 tiles in flight
 
 template <class Tr, bool AGG_ONLY>
@@ -1568,6 +1573,12 @@ int scan_pick_nsub(int64_t positions, int which) {
     if (ns < 1) ns = 1;
     if (ns > MAX_NSUB) ns = MAX_NSUB;
     return (int)ns;
+}
+
+cudaError_t launch_fill(float *v, int64_t n, float value, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, n, value);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,

@@ -97,6 +97,8 @@ cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, 
                             cudaStream_t st, int *launches);
 cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
                              float *resid, cudaStream_t st);
+// v[0..n) = value (multipliers that start at 1 without a warm start)
+cudaError_t launch_fill(float *v, int64_t n, float value, cudaStream_t st);
 cudaError_t launch_update_lambda(const double2 *SA, const double2 *SB, int64_t n, double m,
                                  const float *xs, const float *Ps, int dim, double nu, double lo, double hi,
                                  float *lam, cudaStream_t st);

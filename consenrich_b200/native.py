@@ -306,12 +306,14 @@ def _check_multiplier(init, n, what):
     return src
 
 
-def _init_multiplier(src, n, lo, hi, pinned):
+def _init_multiplier(src, n, lo, hi, pinned, fill=True):
     """Warm-start copy + clip (pyx:7899-7923).  The array travels to the device and back, so it is
-    page-locked when the call is going to run on the device (``pinned``)."""
+    page-locked when the call is going to run on the device (``pinned``).  ``fill=False``: without a
+    warm start the device sets the ones itself (cb200_ecm_opts.init_ones) and the array is output only."""
     arr = (_lib.pinned_empty if pinned else np.empty)((n,), np.float32)
     if src is None:
-        arr.fill(1.0)
+        if fill:
+            arr.fill(1.0)
     else:
         np.clip(src, lo, hi, out=arr)
     return arr
@@ -377,8 +379,8 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     if _apn_live(useAPN, use_qscale, Q0, dim):
         raise NotImplementedError(_APN_MSG)
 
-    lam = _init_multiplier(lam_src, n, lamMin, lamMax, True) if use_lam else None
-    kap = _init_multiplier(kap_src, n, kapMin, kapMax, True) if use_kap else None
+    lam = _init_multiplier(lam_src, n, lamMin, lamMax, True, fill=False) if use_lam else None
+    kap = _init_multiplier(kap_src, n, kapMin, kapMax, True, fill=False) if use_kap else None
     alloc = _lib.pinned_empty if want else np.empty
     xs, Ps = alloc((n, dim), np.float32), alloc((n, dim, dim), np.float32)
     lag, res = alloc((max(n - 1, 1), dim, dim), np.float32), alloc((n, m), np.float32)
@@ -388,6 +390,7 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
     op.max_iters, op.inner_iters = int(iters), int(t_innerIters)
     op.update_lambda, op.update_kappa = int(lam is not None), int(kap is not None)
     op.want_outputs = int(bool(returnIntermediates))
+    op.init_ones = (1 if (lam is not None and lam_src is None) else 0) | (2 if (kap is not None and kap_src is None) else 0)
     op.rtol, op.nu = _f32(rtol), _f32(nu)
     result = _lib.EcmResult()
     nll_path = np.zeros(max(int(iters), 1), np.float64)

@@ -45,7 +45,7 @@ extern "C" {
 #define CB200_ERR_CUDA 2        /* CUDA runtime / driver failure */
 #define CB200_ERR_UNSUPPORTED 3 /* valid in the reference, not expressible as a scan (APN) */
 
-#define CB200_ABI_VERSION 1
+#define CB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CB200_API __attribute__((visibility("default")))
@@ -80,7 +80,8 @@ typedef struct cb200_ecm_opts {
     int32_t update_lambda;   /* ECM_useObsPrecisionReweighting */
     int32_t update_kappa;    /* ECM_useProcessPrecisionReweighting (and not disabled by APN) */
     int32_t want_outputs;    /* returnIntermediates: smoothed tracks + residuals are produced */
-    int32_t reserved0;
+    int32_t init_ones;       /* cb200_host_ecm: bit 0 lambda, bit 1 kappa start at 1 (no warm start): the host
+                              * array is an output only and is not read */
     double rtol;             /* ECM_fixedBackgroundRtol (rounded to float by the caller) */
     double nu;               /* ECM_robustTNu (rounded to float by the caller) */
 } cb200_ecm_opts;

@@ -21,7 +21,7 @@ model = make_model(2, bench.F_MAT, bench.Q0_MAT, 0.0, 1000.0, 1e-4, kap_bounds=b
 ts = TrackSweep(m, n, 2, 0, residuals=True)
 L = ts.ctx._lib
 opts = _lib.EcmOpts(max_iters=bench.ECM_ITERS, inner_iters=bench.T_INNER, update_lambda=0, update_kappa=1,
-                    want_outputs=1, reserved0=0, rtol=0.0, nu=bench.ROBUST_NU)
+                    want_outputs=1, init_ones=0, rtol=0.0, nu=bench.ROBUST_NU)
 result = _lib.EcmResult()
 kap = torch.ones(n, dtype=torch.float32, device=dev)
 
