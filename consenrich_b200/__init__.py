@@ -4,7 +4,8 @@ Only what the path needs lives here:
 
 * ``csrc/``      hand-written CUDA kernels + the C ABI (``include/consenrich_b200.h``)
 * ``_lib``       ctypes binding of ``lib/libconsenrich_b200.so``
-* ``native``     drop-in replacements for the six hot-path functions of ``consenrich.cconsenrich``
+* ``native``     drop-in replacements for the six hot-path functions of ``consenrich.cconsenrich`` (and the
+                 three background-track functions that call them from the other side)
 * ``device``     device-resident sweeps on torch tensors (torch is only a tensor carrier)
 * ``sharding``   chromosome / bin-range sharding across ranks (torch.distributed plumbing)
 
@@ -12,7 +13,8 @@ There is no CPU implementation: importing works anywhere, calling requires the b
 and a CUDA device, and fails loudly otherwise.
 """
 from . import _lib  # noqa: F401
-from .native import (cbackwardPass, cbackwardPassLevel, cfixedBackgroundECM,  # noqa: F401
-                     cfixedBackgroundECMLevel, cforwardPass, cforwardPassLevel, install, sweep, uninstall)
+from .native import (cbackgroundWeightedStats, cbackgroundWeightedStatsWithSupport,  # noqa: F401
+                     cbackwardPass, cbackwardPassLevel, cfixedBackgroundECM, cfixedBackgroundECMLevel,
+                     cforwardPass, cforwardPassLevel, csolveZeroCenteredBackground, install, sweep, uninstall)
 
 __version__ = "0.1.0"

@@ -16,7 +16,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 ABI_VERSION = 2
 
 FAM_FOLD, FAM_FORWARD, FAM_BACKWARD, FAM_RESIDUALS, FAM_PRECISION = range(5)
-FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates")
+FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates", "background")
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -103,6 +103,11 @@ SIGNATURES = {
                                    C.POINTER(_dbl), C.POINTER(_dbl), _vp, _vp, _vp, _i64, _vp]),
     "cb200_host_ecm": (C.c_int, [_vp, _pm, _po, _vp, _vp, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                  _pr, _vp]),
+    "cb200_background_stats": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "cb200_background_solve": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _i32, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
+    "cb200_host_background_stats": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, C.POINTER(_i64)]),
+    "cb200_host_background_solve": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _i32, _vp, C.POINTER(_i64),
+                                              C.POINTER(_dbl)]),
 }
 
 _lib = None

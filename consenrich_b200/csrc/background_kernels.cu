@@ -1,0 +1,440 @@
+// Background-track kernels: the per-interval weighted statistics of the
+// residual matrix and the roughness-penalised solve
+//     (diag(w) + lamFirst D1'D1 + lam D2'D2) x = rhs        [, sum(x) = 0 by a Lagrange multiplier]
+// that the reference runs once per outer pass and per IRLS pass of its background update
+// (cconsenrich.pyx:9675-9724, 944-1096; core.py:8085-8378).
+//
+// The reference factorises the pentadiagonal matrix sequentially (LDL').  Here the n unknowns are
+// paired into 2x2 blocks, which turns the system into a symmetric block-TRIdiagonal one, and that is
+// solved by block cyclic reduction: each level eliminates every other block row in parallel (Schur
+// complements of a symmetric positive definite matrix stay symmetric positive definite, so no
+// pivoting is needed), log2(n/2) levels down, the same number back up.  Two right-hand sides ride
+// along: rhs and the vector of ones the zero-sum constraint needs.
+//
+// A block row is 12 doubles: D (symmetric: d00 d01 d11), U (coupling to the NEXT row; the coupling to
+// the previous row is the previous row's U transposed), B (2 unknowns x 2 right-hand sides), pad.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "background_kernels.cuh"
+
+namespace cb200 {
+namespace {
+
+constexpr int ROW = 12;  // doubles per block row
+constexpr double MIN_PIVOT = 1.0e-12;  // cconsenrich.pyx:968
+
+struct Row {
+    double d00, d01, d11;
+    double u00, u01, u10, u11;
+    double b00, b01, b10, b11;  // b[r][c]: unknown r of the block, right-hand side c
+};
+
+__device__ __forceinline__ Row load_row(const double *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5];
+    return Row{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x};
+}
+__device__ __forceinline__ void store_row(double *p, const Row &r) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(r.d00, r.d01);
+    q[1] = make_double2(r.d11, r.u00);
+    q[2] = make_double2(r.u01, r.u10);
+    q[3] = make_double2(r.u11, r.b00);
+    q[4] = make_double2(r.b01, r.b10);
+    q[5] = make_double2(r.b11, 0.0);
+}
+
+// inverse of the symmetric 2x2 block; reports a pivot below the floor (row index) through *bad
+struct Inv2 {
+    double i00, i01, i11;
+};
+__device__ __forceinline__ Inv2 inv_spd2(const Row &r, int64_t unknown0, BackgroundStatus *st) {
+    // LDL' pivots of the block: d00 and d11 - d01^2 / d00
+    const double p0 = r.d00;
+    const double p1 = r.d11 - (r.d01 * r.d01) / r.d00;
+    if (!(p0 >= MIN_PIVOT) || !(p1 >= MIN_PIVOT)) {
+        const long long idx = unknown0 + ((p0 >= MIN_PIVOT) ? 1 : 0);
+        const long long old = atomicMin(reinterpret_cast<long long *>(&st->bad_index), idx);
+        if (idx < old) st->bad_value = (p0 >= MIN_PIVOT) ? p1 : p0;  // advisory (racy only between bad pivots)
+    }
+    const double rdet = 1.0 / (r.d00 * r.d11 - r.d01 * r.d01);
+    return Inv2{r.d11 * rdet, -r.d01 * rdet, r.d00 * rdet};
+}
+
+// ---- penalty coefficients (cconsenrich.pyx:905-943) ----
+__device__ __forceinline__ double second_diag(int64_t n, int64_t i, double lam) {
+    if (n < 3 || lam <= 0.0) return 0.0;
+    if (n == 3) return i == 1 ? 4.0 * lam : lam;
+    if (i == 0 || i == n - 1) return lam;
+    if (i == 1 || i == n - 2) return 5.0 * lam;
+    return 6.0 * lam;
+}
+__device__ __forceinline__ double second_off1(int64_t n, int64_t i, double lam) {
+    if (n < 3 || lam <= 0.0) return 0.0;
+    if (n == 3) return -2.0 * lam;
+    if (i == 0 || i == n - 2) return -2.0 * lam;
+    return -4.0 * lam;
+}
+__device__ __forceinline__ double first_diag(int64_t n, int64_t i, double lam) {
+    if (n < 2 || lam <= 0.0) return 0.0;
+    return (i == 0 || i == n - 1) ? lam : 2.0 * lam;
+}
+__device__ __forceinline__ double first_off1(int64_t n, double lam) { return (n < 2 || lam <= 0.0) ? 0.0 : -lam; }
+
+// entries of the pentadiagonal matrix; unknowns >= n (the pad of an odd n) are decoupled identities
+__device__ __forceinline__ double mat_diag(const double *w, int64_t n, int64_t k, double lam, double lam1,
+                                           BackgroundStatus *st) {
+    if (k >= n) return 1.0;
+    double v = w[k] + first_diag(n, k, lam1) + second_diag(n, k, lam);
+    if (v < MIN_PIVOT) {  // the reference floors the entry and fails the solve (pyx:1024-1031)
+        const long long old = atomicMin(reinterpret_cast<long long *>(&st->bad_index), (long long)k);
+        if ((long long)k < old) st->bad_value = v;
+        v = MIN_PIVOT;
+    }
+    return v;
+}
+__device__ __forceinline__ double mat_off1(int64_t n, int64_t k, double lam, double lam1) {  // (k, k+1)
+    return (k + 1 < n) ? first_off1(n, lam1) + second_off1(n, k, lam) : 0.0;
+}
+__device__ __forceinline__ double mat_off2(int64_t n, int64_t k, double lam) {  // (k, k+2)
+    return (k + 2 < n) ? lam : 0.0;
+}
+
+__global__ void build_rows_kernel(const double *__restrict__ w, const double *__restrict__ rhs, int64_t n, double lam,
+                                  double lam1, int64_t rows, double *__restrict__ out, BackgroundStatus *st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const int64_t k = 2 * i;
+    Row r;
+    r.d00 = mat_diag(w, n, k, lam, lam1, st);
+    r.d11 = mat_diag(w, n, k + 1, lam, lam1, st);
+    r.d01 = mat_off1(n, k, lam, lam1);
+    // U: [x_k, x_{k+1}] against [x_{k+2}, x_{k+3}]
+    r.u00 = mat_off2(n, k, lam);
+    r.u01 = 0.0;
+    r.u10 = mat_off1(n, k + 1, lam, lam1);
+    r.u11 = mat_off2(n, k + 1, lam);
+    r.b00 = rhs[k];
+    r.b01 = 1.0;
+    r.b10 = (k + 1 < n) ? rhs[k + 1] : 0.0;
+    r.b11 = (k + 1 < n) ? 1.0 : 0.0;
+    store_row(out + i * ROW, r);
+}
+
+// new row j of the next level from rows 2j-1, 2j, 2j+1 of this one
+__device__ __forceinline__ void reduce_row(const double *__restrict__ in, int64_t rows_in, int64_t j, int64_t stride_unknowns,
+                                           double *__restrict__ out, BackgroundStatus *st) {
+    const int64_t i = 2 * j;
+    Row c = load_row(in + i * ROW);
+    Row o = c;
+    o.u00 = o.u01 = o.u10 = o.u11 = 0.0;
+    if (i - 1 >= 0) {
+        const Row p = load_row(in + (i - 1) * ROW);
+        const Inv2 v = inv_spd2(p, (i - 1) * stride_unknowns, st);
+        // L_i = U_p'.  alpha = L_i inv(D_p) = U_p' V
+        const double a00 = p.u00 * v.i00 + p.u10 * v.i01, a01 = p.u00 * v.i01 + p.u10 * v.i11;
+        const double a10 = p.u01 * v.i00 + p.u11 * v.i01, a11 = p.u01 * v.i01 + p.u11 * v.i11;
+        // D -= alpha U_p
+        o.d00 -= a00 * p.u00 + a01 * p.u10;
+        o.d01 -= a00 * p.u01 + a01 * p.u11;
+        o.d11 -= a10 * p.u01 + a11 * p.u11;
+        o.b00 -= a00 * p.b00 + a01 * p.b10;
+        o.b01 -= a00 * p.b01 + a01 * p.b11;
+        o.b10 -= a10 * p.b00 + a11 * p.b10;
+        o.b11 -= a10 * p.b01 + a11 * p.b11;
+        // (the new coupling to the previous kept row is that row's new U transposed)
+    }
+    if (i + 1 < rows_in) {
+        const Row q = load_row(in + (i + 1) * ROW);
+        const Inv2 v = inv_spd2(q, (i + 1) * stride_unknowns, st);
+        // gamma = U_i inv(D_q)
+        const double g00 = c.u00 * v.i00 + c.u01 * v.i01, g01 = c.u00 * v.i01 + c.u01 * v.i11;
+        const double g10 = c.u10 * v.i00 + c.u11 * v.i01, g11 = c.u10 * v.i01 + c.u11 * v.i11;
+        // D -= gamma L_q = gamma U_i'
+        o.d00 -= g00 * c.u00 + g01 * c.u01;
+        o.d01 -= g00 * c.u10 + g01 * c.u11;
+        o.d11 -= g10 * c.u10 + g11 * c.u11;
+        o.b00 -= g00 * q.b00 + g01 * q.b10;
+        o.b01 -= g00 * q.b01 + g01 * q.b11;
+        o.b10 -= g10 * q.b00 + g11 * q.b10;
+        o.b11 -= g10 * q.b01 + g11 * q.b11;
+        // U' = -gamma U_q
+        o.u00 = -(g00 * q.u00 + g01 * q.u10);
+        o.u01 = -(g00 * q.u01 + g01 * q.u11);
+        o.u10 = -(g10 * q.u00 + g11 * q.u10);
+        o.u11 = -(g10 * q.u01 + g11 * q.u11);
+    }
+    store_row(out + j * ROW, o);
+}
+
+// X: [rows][4] doubles = x[r][c] of each block row.  Odd rows of this level from their even neighbours
+// (already solved: they are the rows of the next level), even rows copied from the next level.
+__device__ __forceinline__ void backsub_row(const double *__restrict__ lvl, int64_t rows, const double *__restrict__ x_next,
+                                            int64_t i, double *__restrict__ x_out, BackgroundStatus *st,
+                                            int64_t stride_unknowns) {
+    double2 *o = reinterpret_cast<double2 *>(x_out + i * 4);
+    if ((i & 1) == 0) {
+        const double2 *s = reinterpret_cast<const double2 *>(x_next + (i >> 1) * 4);
+        o[0] = s[0];
+        o[1] = s[1];
+        return;
+    }
+    const Row r = load_row(lvl + i * ROW);
+    const Row p = load_row(lvl + (i - 1) * ROW);  // for L_i = U_p'
+    const double2 *xp = reinterpret_cast<const double2 *>(x_next + ((i - 1) >> 1) * 4);
+    const double2 xp0 = xp[0], xp1 = xp[1];  // x[0][0], x[0][1]; x[1][0], x[1][1]
+    double t00 = r.b00 - (p.u00 * xp0.x + p.u10 * xp1.x);
+    double t01 = r.b01 - (p.u00 * xp0.y + p.u10 * xp1.y);
+    double t10 = r.b10 - (p.u01 * xp0.x + p.u11 * xp1.x);
+    double t11 = r.b11 - (p.u01 * xp0.y + p.u11 * xp1.y);
+    if (i + 1 < rows) {
+        const double2 *xq = reinterpret_cast<const double2 *>(x_next + ((i + 1) >> 1) * 4);
+        const double2 xq0 = xq[0], xq1 = xq[1];
+        t00 -= r.u00 * xq0.x + r.u01 * xq1.x;
+        t01 -= r.u00 * xq0.y + r.u01 * xq1.y;
+        t10 -= r.u10 * xq0.x + r.u11 * xq1.x;
+        t11 -= r.u10 * xq0.y + r.u11 * xq1.y;
+    }
+    (void)st;
+    (void)stride_unknowns;
+    const double rdet = 1.0 / (r.d00 * r.d11 - r.d01 * r.d01);
+    const double i00 = r.d11 * rdet, i01 = -r.d01 * rdet, i11 = r.d00 * rdet;
+    o[0] = make_double2(i00 * t00 + i01 * t10, i00 * t01 + i01 * t11);
+    o[1] = make_double2(i01 * t00 + i11 * t10, i01 * t01 + i11 * t11);
+}
+
+__global__ void reduce_kernel(const double *__restrict__ in, int64_t rows_in, int64_t rows_out, int64_t stride_unknowns,
+                              double *__restrict__ out, BackgroundStatus *st) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < rows_out) reduce_row(in, rows_in, j, stride_unknowns, out, st);
+}
+
+__global__ void backsub_kernel(const double *__restrict__ lvl, int64_t rows, const double *__restrict__ x_next,
+                               double *__restrict__ x_out, BackgroundStatus *st, int64_t stride_unknowns) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows) backsub_row(lvl, rows, x_next, i, x_out, st, stride_unknowns);
+}
+
+// The small end of the recursion in one CTA: levels first..last-1 reduced, the single remaining row
+// solved, and the levels substituted back, with CTA barriers between levels.
+struct SmallArgs {
+    const double *lvl[BG_MAX_LEVELS];
+    double *lvl_out[BG_MAX_LEVELS];
+    double *x[BG_MAX_LEVELS];
+    int64_t rows[BG_MAX_LEVELS];
+    int64_t stride[BG_MAX_LEVELS];
+    int first, last;  // levels [first, last]; rows[last] == 1
+};
+
+__global__ void __launch_bounds__(1024) small_system_kernel(const SmallArgs a, BackgroundStatus *st) {
+    for (int l = a.first; l < a.last; ++l) {
+        for (int64_t j = threadIdx.x; j < a.rows[l + 1]; j += blockDim.x)
+            reduce_row(a.lvl[l], a.rows[l], j, a.stride[l], a.lvl_out[l + 1], st);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const Row r = load_row(a.lvl[a.last]);
+        const Inv2 v = inv_spd2(r, 0, st);
+        double *x = a.x[a.last];
+        x[0] = v.i00 * r.b00 + v.i01 * r.b10;
+        x[1] = v.i00 * r.b01 + v.i01 * r.b11;
+        x[2] = v.i01 * r.b00 + v.i11 * r.b10;
+        x[3] = v.i01 * r.b01 + v.i11 * r.b11;
+    }
+    __syncthreads();
+    for (int l = a.last - 1; l >= a.first; --l) {
+        for (int64_t i = threadIdx.x; i < a.rows[l]; i += blockDim.x)
+            backsub_row(a.lvl[l], a.rows[l], a.x[l + 1], i, a.x[l], st, a.stride[l]);
+        __syncthreads();
+    }
+}
+
+// ---- zero-sum constraint: column sums of X, then out = x0 - mu x1 ----
+constexpr int SUM_THREADS = 256;
+
+__global__ void __launch_bounds__(SUM_THREADS) column_sums_kernel(const double *__restrict__ x, int64_t n,
+                                                                  double *__restrict__ partial) {
+    // unknown k lives at x[(k / 2) * 4 + (k % 2) * 2 + c]
+    __shared__ double s0[SUM_THREADS], s1[SUM_THREADS];
+    double a0 = 0.0, a1 = 0.0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const double2 v = *reinterpret_cast<const double2 *>(x + (k >> 1) * 4 + (k & 1) * 2);
+        a0 += v.x;
+        a1 += v.y;
+    }
+    s0[threadIdx.x] = a0;
+    s1[threadIdx.x] = a1;
+    __syncthreads();
+    for (int d = SUM_THREADS / 2; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            s0[threadIdx.x] += s0[threadIdx.x + d];
+            s1[threadIdx.x] += s1[threadIdx.x + d];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        partial[2 * blockIdx.x] = s0[0];
+        partial[2 * blockIdx.x + 1] = s1[0];
+    }
+}
+
+// mu of the zero-sum constraint from the per-block partial sums (one warp, fixed order)
+__global__ void mu_kernel(const double *__restrict__ partial, int nparts, int64_t n, double *__restrict__ mu) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int p = threadIdx.x; p < nparts; p += 32) {
+        t0 += partial[2 * p];
+        t1 += partial[2 * p + 1];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        t0 += __shfl_xor_sync(0xffffffffu, t0, d);
+        t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+    }
+    if (threadIdx.x == 0) *mu = (fabs(t1) > MIN_PIVOT) ? t0 / t1 : t0 / (double)n;  // pyx:1078-1081
+}
+
+__global__ void finish_kernel(const double *__restrict__ x, int64_t n, const double *__restrict__ mu_ptr,
+                              double *__restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double2 v = *reinterpret_cast<const double2 *>(x + (k >> 1) * 4 + (k & 1) * 2);
+    out[k] = mu_ptr ? v.x - (*mu_ptr) * v.y : v.x;
+}
+
+// ---- weighted statistics of the residual matrix (cconsenrich.pyx:9675-9724) ----
+// weight[i] = sum_j inv[j][i], rhs[i] = sum_j inv[j][i] * resid[j][i], accumulated over j in order in
+// float64 with separately rounded products -- the reference's arithmetic, bit for bit.
+constexpr int STAT_THREADS = 256;
+
+__global__ void __launch_bounds__(STAT_THREADS) weighted_stats_kernel(const float *__restrict__ resid,
+                                                                      const float *__restrict__ inv, int64_t m,
+                                                                      int64_t n, int64_t ld, double *__restrict__ weight,
+                                                                      double *__restrict__ rhs,
+                                                                      unsigned long long *__restrict__ support) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int pos = 0;
+    if (i < n) {
+        double ws = 0.0, rs = 0.0;
+        for (int64_t j = 0; j < m; ++j) {
+            const double w = (double)__ldcs(inv + j * ld + i);
+            const double r = (double)__ldcs(resid + j * ld + i);
+            ws = __dadd_rn(ws, w);
+            rs = __dadd_rn(rs, __dmul_rn(w, r));
+        }
+        weight[i] = ws;
+        rhs[i] = rs;
+        pos = ws > 0.0;
+    }
+    if (support) {
+        const unsigned b = __ballot_sync(0xffffffffu, pos);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(support, (unsigned long long)__popc(b));
+    }
+}
+
+}  // namespace
+
+// =====================================================================================
+// host side
+// =====================================================================================
+int64_t background_rows(int64_t n) { return (n + 1) / 2; }
+
+size_t background_workspace_bytes(int64_t n) {
+    // rows of all levels (<= 2 x level 0) + solutions of all levels + partial sums
+    int64_t rows = background_rows(n), total = 0;
+    while (true) {
+        total += rows;
+        if (rows <= 1) break;
+        rows = (rows + 1) / 2;
+    }
+    return (size_t)total * (ROW + 4) * 8 + (size_t)(BG_SUM_BLOCKS * 2 + 2) * 8 + 256;
+}
+
+cudaError_t launch_background_stats(const float *resid, const float *inv, int64_t m, int64_t n, int64_t ld,
+                                    double *weight, double *rhs, unsigned long long *support, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (support) {
+        cudaError_t e = cudaMemsetAsync(support, 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+    }
+    weighted_stats_kernel<<<(unsigned)((n + STAT_THREADS - 1) / STAT_THREADS), STAT_THREADS, 0, st>>>(
+        resid, inv, m, n, ld, weight, rhs, support);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t n, double lam, double lam_first,
+                                    int zero_center, double *out, void *workspace, BackgroundStatus *status,
+                                    cudaStream_t st, int *launches) {
+    if (n <= 0) return cudaSuccess;
+    // carve the workspace
+    int64_t rows[BG_MAX_LEVELS], stride[BG_MAX_LEVELS];
+    double *lvl[BG_MAX_LEVELS], *x[BG_MAX_LEVELS];
+    int nl = 0;
+    {
+        int64_t r = background_rows(n), s = 2;
+        while (true) {
+            rows[nl] = r;
+            stride[nl] = s;
+            ++nl;
+            if (r <= 1) break;
+            r = (r + 1) / 2;
+            s *= 2;
+        }
+    }
+    double *p = static_cast<double *>(workspace);
+    for (int l = 0; l < nl; ++l) {
+        lvl[l] = p;
+        p += rows[l] * ROW;
+    }
+    for (int l = 0; l < nl; ++l) {
+        x[l] = p;
+        p += rows[l] * 4;
+    }
+    double *partial = p;
+    const BackgroundStatus init{INT64_MAX, 0.0};
+    cudaError_t e = cudaMemcpyAsync(status, &init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return e;
+    int count = 0;
+    const int T = 256;
+    build_rows_kernel<<<(unsigned)((rows[0] + T - 1) / T), T, 0, st>>>(w, rhs, n, lam, lam_first, rows[0], lvl[0], status);
+    ++count;
+    // large levels: one launch each; from the first level with <= BG_SMALL_ROWS rows on, one CTA does the rest
+    int first_small = 0;
+    while (first_small < nl - 1 && rows[first_small] > BG_SMALL_ROWS) ++first_small;
+    for (int l = 0; l < first_small; ++l) {
+        reduce_kernel<<<(unsigned)((rows[l + 1] + T - 1) / T), T, 0, st>>>(lvl[l], rows[l], rows[l + 1], stride[l], lvl[l + 1],
+                                                                         status);
+        ++count;
+    }
+    SmallArgs sa{};
+    for (int l = 0; l < nl; ++l) {
+        sa.lvl[l] = lvl[l];
+        sa.lvl_out[l] = lvl[l];
+        sa.x[l] = x[l];
+        sa.rows[l] = rows[l];
+        sa.stride[l] = stride[l];
+    }
+    sa.first = first_small;
+    sa.last = nl - 1;
+    small_system_kernel<<<1, 1024, 0, st>>>(sa, status);
+    ++count;
+    for (int l = first_small - 1; l >= 0; --l) {
+        backsub_kernel<<<(unsigned)((rows[l] + T - 1) / T), T, 0, st>>>(lvl[l], rows[l], x[l + 1], x[l], status, stride[l]);
+        ++count;
+    }
+    double *mu = nullptr;
+    if (zero_center) {
+        int nparts = (int)((n + SUM_THREADS - 1) / SUM_THREADS);
+        if (nparts > BG_SUM_BLOCKS) nparts = BG_SUM_BLOCKS;
+        mu = partial + 2 * BG_SUM_BLOCKS;
+        column_sums_kernel<<<nparts, SUM_THREADS, 0, st>>>(x[0], n, partial);
+        mu_kernel<<<1, 32, 0, st>>>(partial, nparts, n, mu);
+        count += 2;
+    }
+    finish_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x[0], n, mu, out);
+    ++count;
+    if (launches) *launches += count;
+    return cudaGetLastError();
+}
+
+}  // namespace cb200

@@ -1,0 +1,33 @@
+// Background-track kernels: launch interface (see background_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace cb200 {
+
+constexpr int BG_MAX_LEVELS = 32;
+constexpr int BG_SMALL_ROWS = 2048;  // from this many block rows on, one CTA finishes the recursion
+constexpr int BG_SUM_BLOCKS = 1024;
+
+// outcome of a solve: first unknown whose pivot fell below the reference's floor (1e-12), or
+// INT64_MAX; the reference fails such a solve (cconsenrich.pyx:1090-1095)
+struct BackgroundStatus {
+    int64_t bad_index;
+    double bad_value;
+};
+
+size_t background_workspace_bytes(int64_t n);
+
+// weight[i] = sum_j inv[j][i]; rhs[i] = sum_j inv[j][i] * resid[j][i]  (float32 [m][ld] in, float64 out);
+// support (or nullptr): number of intervals with weight > 0
+cudaError_t launch_background_stats(const float *resid, const float *inv, int64_t m, int64_t n, int64_t ld,
+                                    double *weight, double *rhs, unsigned long long *support, cudaStream_t st);
+
+// (diag(w) + lam_first D1'D1 + lam D2'D2) x = rhs, optionally with sum(x) = 0; n >= 2.
+// workspace: background_workspace_bytes(n) bytes of device memory; status: device BackgroundStatus.
+cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t n, double lam, double lam_first,
+                                    int zero_center, double *out, void *workspace, BackgroundStatus *status,
+                                    cudaStream_t st, int *launches);
+
+}  // namespace cb200

@@ -17,6 +17,7 @@
 
 #include "../../include/consenrich_b200.h"
 #include "ssm_kernels.cuh"
+#include "background_kernels.cuh"
 
 using namespace cb200;
 
@@ -67,7 +68,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_COUNT = 5 };
+enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_BG = 5, FAM_COUNT = 6 };
 
 struct TimedSpan {
     cudaEvent_t a, b;
@@ -89,13 +90,14 @@ struct cb200_ctx {
     int scan_dbg_seen = 0;
     // arena (device)
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, smo, smo2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
+    DevBuf bg_ws, bg_w, bg_rhs, bg_out, bg_status;  // background solve: workspace, operands, outcome
     double *sums_host = nullptr;  // pinned double[2]
     // timing
     bool timing = false;
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> pool;
-    double fam_ms[FAM_COUNT] = {0, 0, 0, 0, 0};
-    int64_t fam_n[FAM_COUNT] = {0, 0, 0, 0, 0};
+    double fam_ms[FAM_COUNT] = {0, 0, 0, 0, 0, 0};
+    int64_t fam_n[FAM_COUNT] = {0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -473,7 +475,8 @@ void cb200_ctx_destroy(cb200_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->xf2, &c->Pf2,
                       &c->Qf2, &c->smo, &c->smo2, &c->D,
-                      &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard};
+                      &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard,
+                      &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->sums_host) cudaFreeHost(c->sums_host);
@@ -1119,6 +1122,125 @@ int cb200_host_ecm(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op
     if (resid) CB_TRY(d2h(c, resid, dres, (size_t)n * m * 4));
     if (lam) CB_TRY(d2h(c, lam, c->lam.p, (size_t)n * 4));
     if (kap) CB_TRY(d2h(c, kap, c->kap.p, (size_t)n * 4));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
+// ---- background track ----------------------------------------------------------------
+int cb200_background_stats(cb200_ctx *c, const float *resid, const float *inv, int64_t m, int64_t n, int64_t ld,
+                           double *weight, double *rhs, unsigned long long *support) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !resid || !inv || !weight || !rhs) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (m < 0 || n < 0 || ld < n) return fail(CB200_ERR_INVALID, "bad matrix shape");
+    if (n == 0) return CB200_OK;
+    Span sp(c, FAM_BG);
+    CU_TRY(launch_background_stats(resid, inv, m, n, ld, weight, rhs, support, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+static int check_background_args(int64_t n, double lam, double lam_first) {
+    // messages of cconsenrich.pyx:985-990
+    if (!std::isfinite(lam_first) || lam_first < 0.0) return fail(CB200_ERR_INVALID, "lamFirst must be finite and nonnegative");
+    if (!std::isfinite(lam) || lam < 0.0) return fail(CB200_ERR_INVALID, "lam must be finite and nonnegative");
+    if (n < 0) return fail(CB200_ERR_INVALID, "n must be nonnegative");
+    return CB200_OK;
+}
+
+int cb200_background_solve(cb200_ctx *c, const double *weight, const double *rhs, int64_t n, double lam,
+                           double lam_first, int32_t zero_center, double *out, int64_t *bad_index, double *bad_value) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !weight || !rhs || !out) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_background_args(n, lam, lam_first));
+    if (bad_index) *bad_index = -1;
+    if (bad_value) *bad_value = 0.0;
+    if (n == 0) return CB200_OK;
+    if (n == 1) return fail(CB200_ERR_INVALID, "a single interval is solved by the host entry point");
+    CB_TRY(ensure(c, c->bg_ws, background_workspace_bytes(n)));
+    CB_TRY(ensure(c, c->bg_status, sizeof(BackgroundStatus)));
+    int launches = 0;
+    {
+        Span sp(c, FAM_BG);
+        CU_TRY(launch_background_solve(weight, rhs, n, lam, lam_first, zero_center, out, c->bg_ws.p,
+                                       static_cast<BackgroundStatus *>(c->bg_status.p), c->stream, &launches));
+    }
+    c->launches += launches;
+    if (bad_index || bad_value) {
+        BackgroundStatus st;
+        CU_TRY(cudaMemcpyAsync(&st, c->bg_status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (st.bad_index != INT64_MAX) {
+            if (bad_index) *bad_index = st.bad_index;
+            if (bad_value) *bad_value = st.bad_value;
+        }
+    }
+    return CB200_OK;
+}
+
+int cb200_host_background_stats(cb200_ctx *c, const float *resid, const float *inv, int64_t m, int64_t n,
+                                double *weight, double *rhs, int64_t *support) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !weight || !rhs) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (support) *support = 0;
+    if (n <= 0) return CB200_OK;
+    if (m <= 0) {  // empty sums
+        memset(weight, 0, (size_t)n * 8);
+        memset(rhs, 0, (size_t)n * 8);
+        return CB200_OK;
+    }
+    if (!resid || !inv) return fail(CB200_ERR_INVALID, "NULL argument");
+    int64_t ld = 0, ld2 = 0;
+    CB_TRY(upload_tracks(c, c->data, resid, m, n, &ld));
+    CB_TRY(upload_tracks(c, c->munc, inv, m, n, &ld2));
+    CB_TRY(ensure(c, c->bg_w, (size_t)n * 8));
+    CB_TRY(ensure(c, c->bg_rhs, (size_t)n * 8));
+    CB_TRY(ensure(c, c->bg_status, sizeof(BackgroundStatus)));
+    unsigned long long *dsup = support ? reinterpret_cast<unsigned long long *>(c->bg_status.p) : nullptr;
+    CB_TRY(cb200_background_stats(c, static_cast<const float *>(c->data.p), static_cast<const float *>(c->munc.p), m, n, ld,
+                                  static_cast<double *>(c->bg_w.p), static_cast<double *>(c->bg_rhs.p), dsup));
+    CB_TRY(d2h(c, weight, c->bg_w.p, (size_t)n * 8));
+    CB_TRY(d2h(c, rhs, c->bg_rhs.p, (size_t)n * 8));
+    unsigned long long sup = 0;
+    if (support) CB_TRY(d2h(c, &sup, dsup, sizeof(sup)));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    if (support) *support = (int64_t)sup;
+    return CB200_OK;
+}
+
+int cb200_host_background_solve(cb200_ctx *c, const double *weight, const double *rhs, int64_t n, double lam,
+                                double lam_first, int32_t zero_center, double *out, int64_t *bad_index,
+                                double *bad_value) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    CB_TRY(check_background_args(n, lam, lam_first));
+    if (bad_index) *bad_index = -1;
+    if (bad_value) *bad_value = 0.0;
+    if (n == 0) return CB200_OK;
+    if (!weight || !rhs || !out) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (n == 1) {  // cconsenrich.pyx:995-1006
+        out[0] = 0.0;
+        if (!zero_center) {
+            if (weight[0] < 1.0e-12) {
+                if (bad_index) *bad_index = 0;
+                if (bad_value) *bad_value = weight[0];
+            } else {
+                out[0] = rhs[0] / weight[0];
+            }
+        }
+        return CB200_OK;
+    }
+    CB_TRY(ensure(c, c->bg_w, (size_t)n * 8));
+    CB_TRY(ensure(c, c->bg_rhs, (size_t)n * 8));
+    CB_TRY(ensure(c, c->bg_out, (size_t)n * 8));
+    CB_TRY(h2d(c, c->bg_w.p, weight, (size_t)n * 8));
+    CB_TRY(h2d(c, c->bg_rhs.p, rhs, (size_t)n * 8));
+    int64_t bi = -1;
+    double bv = 0.0;
+    CB_TRY(cb200_background_solve(c, static_cast<const double *>(c->bg_w.p), static_cast<const double *>(c->bg_rhs.p), n,
+                                  lam, lam_first, zero_center, static_cast<double *>(c->bg_out.p), &bi, &bv));
+    if (bad_index) *bad_index = bi;
+    if (bad_value) *bad_value = bv;
+    CB_TRY(d2h(c, out, c->bg_out.p, (size_t)n * 8));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return CB200_OK;
 }

@@ -32,6 +32,8 @@ __all__ = ["cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPassL
 
 _HOT_PATH = ("cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPassLevel",
              "cfixedBackgroundECM", "cfixedBackgroundECMLevel")
+# the callers on the other side of the ECM inside an outer pass
+_BACKGROUND = ("cbackgroundWeightedStats", "cbackgroundWeightedStatsWithSupport", "csolveZeroCenteredBackground")
 
 
 def _f32(x) -> float:
@@ -483,19 +485,74 @@ def cfixedBackgroundECMLevel(matrixData, matrixPluginMuncInit, matrixQ0, interva
                 processPrecExpInit, trackOptimizationPath, processQScale)
 
 
+# ------------------------------------------------------------------------------------------
+# background track: weighted statistics + roughness-penalised solve (core.py:8085-8378)
+# ------------------------------------------------------------------------------------------
+def _background_stats(residualMatrix, invVarMatrix, want_support):
+    res = np.ascontiguousarray(residualMatrix, dtype=np.float32)
+    inv = np.ascontiguousarray(invVarMatrix, dtype=np.float32)
+    if res.ndim != 2 or inv.ndim != 2 or inv.shape[0] != res.shape[0] or inv.shape[1] != res.shape[1]:
+        raise ValueError("residualMatrix and invVarMatrix must have identical 2D shapes")
+    m, n = res.shape
+    weight, rhs = np.empty(n, np.float64), np.empty(n, np.float64)
+    support = C.c_int64(0)
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_background_stats(ctx.handle, _ptr(res), _ptr(inv), m, n, _ptr(weight), _ptr(rhs),
+                                                    C.byref(support) if want_support else None))
+    return weight, rhs, int(support.value)
+
+
+def cbackgroundWeightedStats(residualMatrix, invVarMatrix):
+    """Column-wise background sufficient statistics; signature and returns of cconsenrich.pyx:9675-9697."""
+    weight, rhs, _ = _background_stats(residualMatrix, invVarMatrix, False)
+    return weight, rhs
+
+
+def cbackgroundWeightedStatsWithSupport(residualMatrix, invVarMatrix):
+    """As above plus the number of intervals with positive weight (cconsenrich.pyx:9700-9724)."""
+    return _background_stats(residualMatrix, invVarMatrix, True)
+
+
+def csolveZeroCenteredBackground(weightTrack, rhsTrack, lam, zeroCenter=True, lamFirst=0.0):
+    """Roughness-penalised background update, ``(diag(w) + lamFirst D1'D1 + lam D2'D2) x = rhs`` with an
+    optional zero-sum constraint; signature, checks and error texts of cconsenrich.pyx:944-1096."""
+    w = np.ascontiguousarray(weightTrack, dtype=np.float64).reshape(-1)
+    rhs = np.ascontiguousarray(rhsTrack, dtype=np.float64).reshape(-1)
+    n = w.shape[0]
+    lam, lamFirst = float(lam), float(lamFirst)
+    if rhs.shape[0] != n:
+        raise ValueError("weightTrack and rhsTrack must have the same length")
+    if not np.isfinite(lamFirst) or lamFirst < 0.0:
+        raise ValueError("lamFirst must be finite and nonnegative")
+    if not np.isfinite(lam) or lam < 0.0:
+        raise ValueError("lam must be finite and nonnegative")
+    out = np.zeros(n, np.float64)
+    if n <= 0:
+        return out
+    bad, val = C.c_int64(-1), C.c_double(0.0)
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_background_solve(ctx.handle, _ptr(w), _ptr(rhs), n, lam, lamFirst,
+                                                    int(bool(zeroCenter)), _ptr(out), C.byref(bad), C.byref(val)))
+    if bad.value >= 0:
+        raise RuntimeError("roughness-penalized LDL factorization required pivot "
+                           f"modification at index {bad.value} (pivot={val.value:.6g}, floor={1.0e-12:.6g}).")
+    return out
+
+
 _saved: dict = {}
 
 
-def install(module=None):
+def install(module=None, background=True):
     """Replace the six hot-path attributes of ``consenrich.cconsenrich`` (or ``module``) with the
     B200 implementations.  ``core.py`` looks them up by attribute at call time (core.py:4274,
-    4309, 3286), so ``runConsenrich`` picks them up without modification."""
+    4309, 3286), so ``runConsenrich`` picks them up without modification.  ``background``: also the
+    three background-track functions (core.py:7543, 8145)."""
     if module is None:
         import importlib
         module = importlib.import_module("consenrich.cconsenrich")
     _lib.load()  # fail now, loudly, if the native library is missing
     saved = _saved.setdefault(id(module), {})
-    for name in _HOT_PATH:
+    for name in _HOT_PATH + (_BACKGROUND if background else ()):
         if name not in saved:
             saved[name] = getattr(module, name, None)
         setattr(module, name, globals()[name])

@@ -15,6 +15,8 @@
  *   cfixedBackgroundECM        :7660-8442               cb200_host_ecm (state_dim 2)
  *   cfixedBackgroundECMLevel   :7153-7657               cb200_host_ecm (state_dim 1)
  *   _accumulateObservationValue :259-283                cb200_fold_tracks (device fold kernel)
+ *   cbackgroundWeightedStats[WithSupport] :9675-9724    cb200_host_background_stats
+ *   csolveZeroCenteredBackground :944-1096              cb200_host_background_solve
  *
  * Conventions
  *   - plain C: pointers, sizes, POD structs; no torch / numpy types.
@@ -241,6 +243,29 @@ CB200_API int cb200_host_ecm(cb200_ctx *ctx, const cb200_model *model, const cb2
                    const int32_t *block_map, int64_t block_count, const float *qscale, float *lam,
                    float *kap, float *xs, float *Ps, float *lag, float *resid,
                    cb200_ecm_result *result, double *nll_path);
+
+/* ---- background track (the caller on the other side of the ECM: core.py:8085-8378) ------ */
+/* cbackgroundWeightedStats[WithSupport] (cconsenrich.pyx:9675-9724): weight[i] = sum_j inv[j][i],
+ * rhs[i] = sum_j inv[j][i] * resid[j][i], float64, accumulated over j in order (bit-identical to the
+ * reference).  resid, inv: float32 [m][ld] on the device.  support: device counter of the intervals
+ * with weight > 0, or NULL. */
+CB200_API int cb200_background_stats(cb200_ctx *ctx, const float *resid, const float *inv, int64_t m, int64_t n,
+                           int64_t ld, double *weight, double *rhs, unsigned long long *support);
+/* csolveZeroCenteredBackground (cconsenrich.pyx:944-1096): solves
+ * (diag(weight) + lam_first D1'D1 + lam D2'D2) x = rhs, with sum(x) = 0 imposed by a Lagrange
+ * multiplier when zero_center is set, by block cyclic reduction (float64; agrees with the reference's
+ * sequential LDL' to rounding times the conditioning of the system).  weight, rhs, out: device
+ * float64 [n].  *bad_index (host) receives the first unknown whose pivot fell below the reference's
+ * 1e-12 floor, or -1, and *bad_value that pivot: the reference raises RuntimeError for such a system. */
+CB200_API int cb200_background_solve(cb200_ctx *ctx, const double *weight, const double *rhs, int64_t n, double lam,
+                           double lam_first, int32_t zero_center, double *out, int64_t *bad_index,
+                           double *bad_value);
+/* The same two with HOST arrays (uploads, kernels, downloads; return when the results are in place). */
+CB200_API int cb200_host_background_stats(cb200_ctx *ctx, const float *resid, const float *inv, int64_t m, int64_t n,
+                                double *weight, double *rhs, int64_t *support);
+CB200_API int cb200_host_background_solve(cb200_ctx *ctx, const double *weight, const double *rhs, int64_t n,
+                                double lam, double lam_first, int32_t zero_center, double *out,
+                                int64_t *bad_index, double *bad_value);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,11 @@ with the reference's keyword signatures and return tuples:
 * ``cfixedBackgroundECMLevel``<- cconsenrich.pyx:7153-7657
 * ``cfixedBackgroundECM``     <- cconsenrich.pyx:7660-8442
 
+and (``oracle/background_oracle.c``) the background-track functions on the other side of the ECM:
+
+* ``cbackgroundWeightedStats[WithSupport]`` <- cconsenrich.pyx:9675-9724
+* ``csolveZeroCenteredBackground``          <- cconsenrich.pyx:944-1096
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this module.  The product (``consenrich_b200``) never does.
 
@@ -37,8 +42,8 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libssm_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the C restatement (gcc, reference flags).  Returns the library path."""
-    src = os.path.join(_HERE, "ssm_oracle.c")
-    if force or (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("ssm_oracle.c", "background_oracle.c")]
+    if force or (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
     return _LIB_PATH
 
@@ -515,3 +520,70 @@ def load_reference():
     except Exception:
         return None
     return ref
+
+
+# ------------------------------------------------------------------------------------------
+# background track (oracle/background_oracle.c)
+# ------------------------------------------------------------------------------------------
+def _bg_lib():
+    lib = _L()
+    if not getattr(lib, "_bg_ready", False):
+        lib.bg_weighted_stats.restype = C.c_int64
+        lib.bg_weighted_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]
+        lib.bg_solve.restype = C.c_int64
+        lib.bg_solve.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double)]
+        lib._bg_ready = True
+    return lib
+
+
+def cbackgroundWeightedStatsWithSupport(residualMatrix, invVarMatrix):
+    """cconsenrich.pyx:9700-9724."""
+    res = np.ascontiguousarray(residualMatrix, dtype=np.float32)
+    inv = np.ascontiguousarray(invVarMatrix, dtype=np.float32)
+    if res.ndim != 2 or inv.ndim != 2 or inv.shape != res.shape:
+        raise ValueError("residualMatrix and invVarMatrix must have identical 2D shapes")
+    m, n = res.shape
+    weight, rhs = np.empty(n, np.float64), np.empty(n, np.float64)
+    support = _bg_lib().bg_weighted_stats(res.ctypes.data, inv.ctypes.data, m, n, weight.ctypes.data, rhs.ctypes.data)
+    return weight, rhs, int(support)
+
+
+def cbackgroundWeightedStats(residualMatrix, invVarMatrix):
+    """cconsenrich.pyx:9675-9697."""
+    return cbackgroundWeightedStatsWithSupport(residualMatrix, invVarMatrix)[:2]
+
+
+def csolveZeroCenteredBackground(weightTrack, rhsTrack, lam, zeroCenter=True, lamFirst=0.0):
+    """cconsenrich.pyx:944-1096 (checks and error texts included)."""
+    w = np.ascontiguousarray(weightTrack, dtype=np.float64).reshape(-1)
+    r = np.ascontiguousarray(rhsTrack, dtype=np.float64).reshape(-1)
+    n = w.shape[0]
+    lam, lamFirst = float(lam), float(lamFirst)
+    min_pivot = 1.0e-12
+    if r.shape[0] != n:
+        raise ValueError("weightTrack and rhsTrack must have the same length")
+    if not np.isfinite(lamFirst) or lamFirst < 0.0:
+        raise ValueError("lamFirst must be finite and nonnegative")
+    if not np.isfinite(lam) or lam < 0.0:
+        raise ValueError("lam must be finite and nonnegative")
+    out = np.zeros(n, np.float64)
+    if n <= 0:
+        return out
+    bad, val = -1, 0.0
+    if n == 1:
+        if not zeroCenter:
+            if w[0] < min_pivot:
+                bad, val = 0, float(w[0])
+            else:
+                out[0] = r[0] / w[0]
+    else:
+        diag, rhs = w.copy(), r.copy()
+        cons, lower = np.empty(n, np.float64), np.empty(n, np.float64)
+        v = C.c_double(0.0)
+        bad = int(_bg_lib().bg_solve(diag.ctypes.data, rhs.ctypes.data, cons.ctypes.data, lower.ctypes.data,
+                                     out.ctypes.data, n, lam, lamFirst, int(bool(zeroCenter)), C.byref(v)))
+        val = v.value
+    if bad >= 0:
+        raise RuntimeError("roughness-penalized LDL factorization required pivot "
+                           f"modification at index {bad} (pivot={val:.6g}, floor={min_pivot:.6g}).")
+    return out

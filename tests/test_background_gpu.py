@@ -1,0 +1,156 @@
+"""GPU parity of the background-track functions through the C ABI:
+``cbackgroundWeightedStats[WithSupport]`` bit-exact, ``csolveZeroCenteredBackground`` (block cyclic
+reduction against the reference's sequential LDL') within a stated float64 tolerance, against the
+golden vectors of the reference build, the oracle on fresh seeds, and -- at genome-scale lengths --
+through the residual of the linear system itself."""
+import numpy as np
+import pytest
+
+from test_background_oracle import golden_cases
+
+pytestmark = pytest.mark.gpu
+
+# Both factorisations are backward stable; their solutions differ by rounding times the conditioning
+# of the system.  For the golden / seeded systems here (weights 5..200, lam <= 1e4, masked stretches of
+# 20 intervals) that stays below 1e-9 of the largest solution entry.
+SOLVE_ATOL_REL = 1.0e-9
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import consenrich_b200 as cb
+    return cb
+
+
+def penalised_matvec(w, lam, lam1, x):
+    """(diag(w) + lam1 D1'D1 + lam D2'D2) x without forming the matrix."""
+    y = w * x
+    if x.shape[0] >= 2 and lam1 > 0:
+        d = np.diff(x)
+        y[:-1] -= lam1 * d
+        y[1:] += lam1 * d
+    if x.shape[0] >= 3 and lam > 0:
+        d2 = x[:-2] - 2.0 * x[1:-1] + x[2:]
+        y[:-2] += lam * d2
+        y[1:-1] -= 2.0 * lam * d2
+        y[2:] += lam * d2
+    return y
+
+
+def test_weighted_stats_match_golden_and_oracle_bitwise(cb, oracle):
+    for name, c in golden_cases("stats").items():
+        w, r, sup = cb.cbackgroundWeightedStatsWithSupport(c["resid"], c["inv"])
+        np.testing.assert_array_equal(w, c["weight"], err_msg=name)
+        np.testing.assert_array_equal(r, c["rhs"], err_msg=name)
+        assert sup == int(c["support"])
+    rng = np.random.default_rng(11)
+    for m, n in ((1, 1), (3, 31), (10, 70001), (130, 5000), (2, 1_000_003)):
+        res = rng.normal(size=(m, n)).astype(np.float32)
+        inv = (1.0 / rng.uniform(1e-3, 3.0, (m, n))).astype(np.float32)
+        inv[:, rng.random(n) < 0.07] = 0.0
+        want = oracle.cbackgroundWeightedStatsWithSupport(res, inv)
+        got = cb.cbackgroundWeightedStatsWithSupport(res, inv)
+        np.testing.assert_array_equal(got[0], want[0])
+        np.testing.assert_array_equal(got[1], want[1])
+        assert got[2] == want[2]
+        got2 = cb.cbackgroundWeightedStats(res, inv)
+        np.testing.assert_array_equal(got2[0], want[0])
+        np.testing.assert_array_equal(got2[1], want[1])
+    w0, r0 = cb.cbackgroundWeightedStats(np.zeros((0, 5), np.float32), np.zeros((0, 5), np.float32))
+    assert w0.shape == (5,) and not w0.any() and not r0.any()
+    with pytest.raises(ValueError, match="identical 2D shapes"):
+        cb.cbackgroundWeightedStats(np.zeros((2, 3), np.float32), np.zeros((3, 3), np.float32))
+
+
+def test_solve_matches_reference_golden_vectors(cb):
+    for name, c in golden_cases("solve").items():
+        got = cb.csolveZeroCenteredBackground(c["weight"], c["rhs"], float(c["lam"]), bool(c["zeroCenter"]),
+                                              lamFirst=float(c["lamFirst"]))
+        want = c["out"]
+        tol = SOLVE_ATOL_REL * max(np.abs(want).max(), 1e-30)
+        np.testing.assert_allclose(got, want, rtol=0, atol=tol, err_msg=name)
+
+
+@pytest.mark.parametrize("zero_center", [True, False])
+def test_solve_matches_oracle_on_fresh_seeds(cb, oracle, zero_center):
+    from golden.make_background_golden import background_inputs
+    rng = np.random.default_rng(2026)
+    for n in (1, 2, 3, 4, 5, 8, 9, 127, 128, 129, 4095, 4097, 70001, 300_000):
+        for lam, lam1 in ((128.0, 0.0), (16.0, 2.0), (0.0, 8.0)):
+            w, rhs = background_inputs(rng, n)
+            want = oracle.csolveZeroCenteredBackground(w, rhs, lam, zero_center, lamFirst=lam1)
+            got = cb.csolveZeroCenteredBackground(w, rhs, lam, zero_center, lamFirst=lam1)
+            tol = SOLVE_ATOL_REL * max(np.abs(want).max(), 1e-30)
+            np.testing.assert_allclose(got, want, rtol=0, atol=tol, err_msg=f"n={n} lam={lam} lamFirst={lam1}")
+            if zero_center and n > 1:
+                assert abs(got.sum()) <= 1e-9 * np.abs(got).sum()
+
+
+def test_solve_at_chromosome_lengths_satisfies_the_system(cb):
+    """hg38 chr19 @ 25 bp and chr1 @ 10 bp: size-independent check through the system's own residual
+    (A x = rhs - mu 1 with sum x = 0), plus the oracle on the shorter one."""
+    from golden.make_background_golden import background_inputs
+    rng = np.random.default_rng(19)
+    for n in (2_344_705, 24_895_643):
+        w, rhs = background_inputs(rng, n)
+        lam, lam1 = 128.0, 0.0
+        x = cb.csolveZeroCenteredBackground(w, rhs, lam, True, lamFirst=lam1)
+        r = rhs - penalised_matvec(w, lam, lam1, x)  # = mu * 1
+        mu = r.mean()
+        scale = np.abs(w * x).max() + lam * 16.0 * np.abs(x).max()
+        assert np.abs(r - mu).max() <= 1e-10 * scale
+        assert abs(x.sum()) <= 1e-9 * np.abs(x).sum()
+        y = cb.csolveZeroCenteredBackground(w, rhs, lam, False, lamFirst=lam1)
+        assert np.abs(rhs - penalised_matvec(w, lam, lam1, y)).max() <= 1e-10 * scale
+
+
+def test_solve_errors_and_edge_cases_follow_the_reference(cb, oracle):
+    w = np.ones(4)
+    with pytest.raises(ValueError, match="weightTrack and rhsTrack must have the same length"):
+        cb.csolveZeroCenteredBackground(w, np.ones(3), 1.0)
+    with pytest.raises(ValueError, match="lam must be finite and nonnegative"):
+        cb.csolveZeroCenteredBackground(w, w, float("inf"))
+    with pytest.raises(ValueError, match="lamFirst must be finite and nonnegative"):
+        cb.csolveZeroCenteredBackground(w, w, 1.0, True, lamFirst=-2.0)
+    assert cb.csolveZeroCenteredBackground(np.zeros(0), np.zeros(0), 1.0).shape == (0,)
+    np.testing.assert_array_equal(cb.csolveZeroCenteredBackground(np.array([2.0]), np.array([3.0]), 1.0, False),
+                                  np.array([1.5]))
+    np.testing.assert_array_equal(cb.csolveZeroCenteredBackground(np.array([2.0]), np.array([3.0]), 1.0, True),
+                                  np.array([0.0]))
+    # a system the reference refuses (zero weights, no penalty: every pivot is floored)
+    for mod in (oracle, cb):
+        with pytest.raises(RuntimeError, match="required pivot modification at index 0"):
+            mod.csolveZeroCenteredBackground(np.zeros(6), np.ones(6), 0.0, False)
+        with pytest.raises(RuntimeError, match="required pivot modification at index 0"):
+            mod.csolveZeroCenteredBackground(np.array([0.0]), np.array([1.0]), 0.0, False)
+
+
+def test_installed_background_functions_run_under_the_reference_driver(cb):
+    """install() swaps the three background functions too; the reference's own solver wrappers
+    (core.py:7530-7590) then run on the device."""
+    import os
+    import sys
+    drv = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "driver")
+    if not os.path.isdir(os.path.join(drv, "consenrich")):
+        pytest.skip("oracle/_ref/driver not built")
+    sys.path.insert(0, drv)
+    try:
+        import consenrich.core as core
+        import consenrich.cconsenrich as cc
+        rng = np.random.default_rng(5)
+        n = 5000
+        w = rng.uniform(1, 50, n)
+        rhs = rng.normal(size=n) * w
+        want = core.solveZeroCenteredBackgroundLinearSystem(w, rhs, 1.0, 64.0)
+        cb.install(cc)
+        try:
+            assert cc.csolveZeroCenteredBackground is cb.csolveZeroCenteredBackground
+            got = core.solveZeroCenteredBackgroundLinearSystem(w, rhs, 1.0, 64.0)
+        finally:
+            cb.uninstall(cc)
+        np.testing.assert_allclose(got, want, rtol=0, atol=SOLVE_ATOL_REL * np.abs(want).max())
+    finally:
+        sys.path.remove(drv)
