@@ -266,6 +266,81 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def background_block(torch, dev, stream, ctx, rep, host, m, n, ld, no_cpu):
+    """Times the background-track row: cbackgroundWeightedStatsWithSupport and
+    csolveZeroCenteredBackground (zero-centred, lam = 128: constants.py's ECM_backgroundSmoothness) at the
+    workload's size, device-resident, through the host API, and the reference's own functions on one core."""
+    import ctypes as C
+    import consenrich_b200 as cb
+    from consenrich_b200 import _lib
+    from consenrich_b200.device import _p
+    L = ctx._lib
+    d, v, _ = rep  # count / variance matrices stand in for residuals / inverse variances
+    w = torch.empty(n, dtype=torch.float64, device=dev)
+    rhs = torch.empty(n, dtype=torch.float64, device=dev)
+    out = torch.empty(n, dtype=torch.float64, device=dev)
+    lam, lam1 = 128.0, 0.0
+
+    def stats():
+        _lib.check(L.cb200_background_stats(ctx.handle, _p(d), _p(v), m, n, ld, _p(w), _p(rhs), None))
+
+    def solve():
+        _lib.check(L.cb200_background_solve(ctx.handle, _p(w), _p(rhs), n, lam, lam1, 1, _p(out), None, None))
+
+    def timed(fn, k=20):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record(stream)
+        for _ in range(k):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / k
+
+    ms_stats = timed(stats)
+    w.add_(1.0)  # positive weights everywhere: a system the reference accepts
+    l0 = ctx.launch_count
+    ms_solve = timed(solve, 10)
+    launches = (ctx.launch_count - l0) // 13
+    hw, hr = w.cpu().numpy(), rhs.cpu().numpy()
+    for _ in range(2):
+        x = cb.csolveZeroCenteredBackground(hw, hr, lam, True, lamFirst=lam1)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        x = cb.csolveZeroCenteredBackground(hw, hr, lam, True, lamFirst=lam1)
+    host_solve = (time.perf_counter() - t0) / 3
+    cb.cbackgroundWeightedStatsWithSupport(host["data"], host["munc"])
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cb.cbackgroundWeightedStatsWithSupport(host["data"], host["munc"])
+    host_stats = (time.perf_counter() - t0) / 3
+    peak = 6458.1
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    stats_bytes, solve_bytes = 8.0 * m * n + 16.0 * n, 24.0 * n  # in: resid + inv; w, rhs out | in: w, rhs; x out
+    blk = {"what": "cbackgroundWeightedStatsWithSupport + csolveZeroCenteredBackground(zeroCenter, lam=128) at the "
+                   "workload's size",
+           "stats_ms_device": ms_stats, "stats_frac_of_peak": stats_bytes / (ms_stats * 1e-3) / 1e9 / peak,
+           "solve_ms_device": ms_solve, "solve_frac_of_peak": solve_bytes / (ms_solve * 1e-3) / 1e9 / peak,
+           "solve_kernel_launches": int(launches), "stats_ms_host_api": 1e3 * host_stats,
+           "solve_ms_host_api": 1e3 * host_solve, "cpu_reference": None}
+    if not no_cpu:
+        mod, kind = _cpu_module()
+        t0 = time.perf_counter()
+        y = mod.csolveZeroCenteredBackground(hw, hr, lam, True, lamFirst=lam1)
+        cpu_solve = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        mod.cbackgroundWeightedStatsWithSupport(host["data"], host["munc"])
+        cpu_stats = time.perf_counter() - t0
+        blk["cpu_reference"] = {"kind": kind, "cores": 1, "solve_ms": 1e3 * cpu_solve, "stats_ms": 1e3 * cpu_stats,
+                                "max_abs_diff_over_max_abs": float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))}
+    return blk
+
+
 def run_b200_arm(args):
     import ctypes as C
 
@@ -385,7 +460,7 @@ def run_b200_arm(args):
     e2e_s = time.perf_counter() - t0
     barrier()
     e2e_launches = hctx.launch_count - hl0
-    h2d = host["data"].nbytes + host["munc"].nbytes + 4 * n            # tracks + the kappa warm start
+    h2d = host["data"].nbytes + host["munc"].nbytes                    # tracks (kappa starts at 1 on the device)
     d2h = n * (8 + 16) + (n - 1) * 16 + n * m * 4 + 4 * n + 16          # xs, Ps, lag, residuals, kappa, scalars
     nll_e2e = float(r[1])
     # single sweep through the host API (cforwardPass + cbackwardPass on one upload)
@@ -400,6 +475,11 @@ def run_b200_arm(args):
         cb.sweep(host["data"], host["munc"], F, Q0, 0.0, 1000.0, processPrecExp=host["kap"],
                  procPrecisionMultiplierMin=KAP_BOUNDS[0], procPrecisionMultiplierMax=KAP_BOUNDS[1], out=out)
     sweep_e2e_s = (time.perf_counter() - t0) / 3
+
+    # ---- background track: statistics + penalised solve, rank 0 at N=1 only ----
+    background = None
+    if world == 1:
+        background = background_block(torch, dev, stream, ctx, reps[0], host, m, n, ld, args.no_cpu_baseline)
 
     # ---- reduce over ranks: max time ----
     t = torch.tensor([ms_total, e2e_s, ms_sweep], dtype=torch.float64, device=dev)
@@ -485,6 +565,7 @@ def run_b200_arm(args):
                         "algorithmic_bytes": sweep_alg, "GBps": sweep_alg / (ms_sweep * 1e-3) / 1e9,
                         "frac_of_peak": sweep_alg / (ms_sweep * 1e-3) / 1e9 / peak,
                         "ms_per_sweep_host_api": 1e3 * sweep_e2e_s, "value_host_api": cells / sweep_e2e_s},
+            "background": background,
             "check": {"final_nll_device": nll, "final_nll_e2e": nll_e2e,
                       "ms_per_step_without_kernel_events": ms_plain / args.steps},
         }

@@ -101,11 +101,16 @@ __device__ __forceinline__ double mat_off2(int64_t n, int64_t k, double lam) {  
     return (k + 2 < n) ? lam : 0.0;
 }
 
-__global__ void build_rows_kernel(const double *__restrict__ w, const double *__restrict__ rhs, int64_t n, double lam,
-                                  double lam1, int64_t rows, double *__restrict__ out, BackgroundStatus *st) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= rows) return;
-    const int64_t k = 2 * i;
+// block row i of level 0, straight from the weight / rhs tracks
+struct Level0 {
+    const double *w, *rhs;
+    int64_t n;
+    double lam, lam1;
+};
+__device__ __forceinline__ Row build_row(const Level0 &a, int64_t i, BackgroundStatus *st) {
+    const double *w = a.w, *rhs = a.rhs;
+    const int64_t n = a.n, k = 2 * i;
+    const double lam = a.lam, lam1 = a.lam1;
     Row r;
     r.d00 = mat_diag(w, n, k, lam, lam1, st);
     r.d11 = mat_diag(w, n, k + 1, lam, lam1, st);
@@ -119,18 +124,27 @@ __global__ void build_rows_kernel(const double *__restrict__ w, const double *__
     r.b01 = 1.0;
     r.b10 = (k + 1 < n) ? rhs[k + 1] : 0.0;
     r.b11 = (k + 1 < n) ? 1.0 : 0.0;
-    store_row(out + i * ROW, r);
+    return r;
+}
+
+// rows of a level: stored (12 doubles each) or, for level 0, formed on the fly
+struct Rows {
+    const double *stored;  // nullptr: level 0
+    Level0 l0;
+};
+__device__ __forceinline__ Row get_row(const Rows &rw, int64_t i, BackgroundStatus *st) {
+    return rw.stored ? load_row(rw.stored + i * ROW) : build_row(rw.l0, i, st);
 }
 
 // new row j of the next level from rows 2j-1, 2j, 2j+1 of this one
-__device__ __forceinline__ void reduce_row(const double *__restrict__ in, int64_t rows_in, int64_t j, int64_t stride_unknowns,
+__device__ __forceinline__ void reduce_row(const Rows &in, int64_t rows_in, int64_t j, int64_t stride_unknowns,
                                            double *__restrict__ out, BackgroundStatus *st) {
     const int64_t i = 2 * j;
-    Row c = load_row(in + i * ROW);
+    Row c = get_row(in, i, st);
     Row o = c;
     o.u00 = o.u01 = o.u10 = o.u11 = 0.0;
     if (i - 1 >= 0) {
-        const Row p = load_row(in + (i - 1) * ROW);
+        const Row p = get_row(in, i - 1, st);
         const Inv2 v = inv_spd2(p, (i - 1) * stride_unknowns, st);
         // L_i = U_p'.  alpha = L_i inv(D_p) = U_p' V
         const double a00 = p.u00 * v.i00 + p.u10 * v.i01, a01 = p.u00 * v.i01 + p.u10 * v.i11;
@@ -146,7 +160,7 @@ __device__ __forceinline__ void reduce_row(const double *__restrict__ in, int64_
         // (the new coupling to the previous kept row is that row's new U transposed)
     }
     if (i + 1 < rows_in) {
-        const Row q = load_row(in + (i + 1) * ROW);
+        const Row q = get_row(in, i + 1, st);
         const Inv2 v = inv_spd2(q, (i + 1) * stride_unknowns, st);
         // gamma = U_i inv(D_q)
         const double g00 = c.u00 * v.i00 + c.u01 * v.i01, g01 = c.u00 * v.i01 + c.u01 * v.i11;
@@ -170,7 +184,7 @@ __device__ __forceinline__ void reduce_row(const double *__restrict__ in, int64_
 
 // X: [rows][4] doubles = x[r][c] of each block row.  Odd rows of this level from their even neighbours
 // (already solved: they are the rows of the next level), even rows copied from the next level.
-__device__ __forceinline__ void backsub_row(const double *__restrict__ lvl, int64_t rows, const double *__restrict__ x_next,
+__device__ __forceinline__ void backsub_row(const Rows &lvl, int64_t rows, const double *__restrict__ x_next,
                                             int64_t i, double *__restrict__ x_out, BackgroundStatus *st,
                                             int64_t stride_unknowns) {
     double2 *o = reinterpret_cast<double2 *>(x_out + i * 4);
@@ -180,8 +194,8 @@ __device__ __forceinline__ void backsub_row(const double *__restrict__ lvl, int6
         o[1] = s[1];
         return;
     }
-    const Row r = load_row(lvl + i * ROW);
-    const Row p = load_row(lvl + (i - 1) * ROW);  // for L_i = U_p'
+    const Row r = get_row(lvl, i, st);
+    const Row p = get_row(lvl, i - 1, st);  // for L_i = U_p'
     const double2 *xp = reinterpret_cast<const double2 *>(x_next + ((i - 1) >> 1) * 4);
     const double2 xp0 = xp[0], xp1 = xp[1];  // x[0][0], x[0][1]; x[1][0], x[1][1]
     double t00 = r.b00 - (p.u00 * xp0.x + p.u10 * xp1.x);
@@ -196,7 +210,6 @@ __device__ __forceinline__ void backsub_row(const double *__restrict__ lvl, int6
         t10 -= r.u10 * xq0.x + r.u11 * xq1.x;
         t11 -= r.u10 * xq0.y + r.u11 * xq1.y;
     }
-    (void)st;
     (void)stride_unknowns;
     const double rdet = 1.0 / (r.d00 * r.d11 - r.d01 * r.d01);
     const double i00 = r.d11 * rdet, i01 = -r.d01 * rdet, i11 = r.d00 * rdet;
@@ -204,49 +217,154 @@ __device__ __forceinline__ void backsub_row(const double *__restrict__ lvl, int6
     o[1] = make_double2(i01 * t00 + i11 * t10, i01 * t01 + i11 * t11);
 }
 
-__global__ void reduce_kernel(const double *__restrict__ in, int64_t rows_in, int64_t rows_out, int64_t stride_unknowns,
+__global__ void reduce_kernel(const Rows in, int64_t rows_in, int64_t rows_out, int64_t stride_unknowns,
                               double *__restrict__ out, BackgroundStatus *st) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < rows_out) reduce_row(in, rows_in, j, stride_unknowns, out, st);
 }
 
-__global__ void backsub_kernel(const double *__restrict__ lvl, int64_t rows, const double *__restrict__ x_next,
+__global__ void backsub_kernel(const Rows lvl, int64_t rows, const double *__restrict__ x_next,
                                double *__restrict__ x_out, BackgroundStatus *st, int64_t stride_unknowns) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows) backsub_row(lvl, rows, x_next, i, x_out, st, stride_unknowns);
 }
 
-// The small end of the recursion in one CTA: levels first..last-1 reduced, the single remaining row
-// solved, and the levels substituted back, with CTA barriers between levels.
-struct SmallArgs {
-    const double *lvl[BG_MAX_LEVELS];
-    double *lvl_out[BG_MAX_LEVELS];
-    double *x[BG_MAX_LEVELS];
-    int64_t rows[BG_MAX_LEVELS];
-    int64_t stride[BG_MAX_LEVELS];
-    int first, last;  // levels [first, last]; rows[last] == 1
+// The small end of the recursion (<= BG_SMALL_ROWS block rows) in ONE CTA, in place in shared memory.
+// At the level with stride s the active rows sit at positions 0, s, 2s, ...; those at even multiples
+// of s are replaced by the next level's rows, the odd ones stay for the substitution back, which
+// needs their coupling to the LEFT too -- so here a row carries its L explicitly (16 doubles).  The
+// solution overwrites B.
+constexpr int SROW = 16;
+struct RowS {
+    double l00, l01, l10, l11, d00, d01, d11, u00, u01, u10, u11, b00, b01, b10, b11;
 };
+__device__ __forceinline__ RowS load_rows(const double *p) {
+    const double2 *q = reinterpret_cast<const double2 *>(p);
+    const double2 a = q[0], b = q[1], c = q[2], d = q[3], e = q[4], f = q[5], g = q[6], h = q[7];
+    return RowS{a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, e.x, e.y, f.x, f.y, g.x, g.y, h.x};
+}
+__device__ __forceinline__ void store_rows(double *p, const RowS &r) {
+    double2 *q = reinterpret_cast<double2 *>(p);
+    q[0] = make_double2(r.l00, r.l01);
+    q[1] = make_double2(r.l10, r.l11);
+    q[2] = make_double2(r.d00, r.d01);
+    q[3] = make_double2(r.d11, r.u00);
+    q[4] = make_double2(r.u01, r.u10);
+    q[5] = make_double2(r.u11, r.b00);
+    q[6] = make_double2(r.b01, r.b10);
+    q[7] = make_double2(r.b11, 0.0);
+}
+__device__ __forceinline__ Inv2 inv_spd2s(const RowS &r, int64_t unknown0, BackgroundStatus *st) {
+    Row t{};
+    t.d00 = r.d00; t.d01 = r.d01; t.d11 = r.d11;
+    return inv_spd2(t, unknown0, st);
+}
 
-__global__ void __launch_bounds__(1024) small_system_kernel(const SmallArgs a, BackgroundStatus *st) {
-    for (int l = a.first; l < a.last; ++l) {
-        for (int64_t j = threadIdx.x; j < a.rows[l + 1]; j += blockDim.x)
-            reduce_row(a.lvl[l], a.rows[l], j, a.stride[l], a.lvl_out[l + 1], st);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        const Row r = load_row(a.lvl[a.last]);
-        const Inv2 v = inv_spd2(r, 0, st);
-        double *x = a.x[a.last];
-        x[0] = v.i00 * r.b00 + v.i01 * r.b10;
-        x[1] = v.i00 * r.b01 + v.i01 * r.b11;
-        x[2] = v.i01 * r.b00 + v.i11 * r.b10;
-        x[3] = v.i01 * r.b01 + v.i11 * r.b11;
+__global__ void __launch_bounds__(1024) small_system_kernel(const Rows in, int64_t rows, int64_t stride_unknowns,
+                                                            double *__restrict__ x_out, BackgroundStatus *st) {
+    extern __shared__ __align__(16) double sm[];
+    const int R = (int)rows;
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        const Row r = get_row(in, i, st);
+        RowS t{};
+        if (i > 0) {  // L_i = U_{i-1}'
+            const Row p = get_row(in, i - 1, st);
+            t.l00 = p.u00; t.l01 = p.u10; t.l10 = p.u01; t.l11 = p.u11;
+        }
+        t.d00 = r.d00; t.d01 = r.d01; t.d11 = r.d11;
+        t.u00 = r.u00; t.u01 = r.u01; t.u10 = r.u10; t.u11 = r.u11;
+        t.b00 = r.b00; t.b01 = r.b01; t.b10 = r.b10; t.b11 = r.b11;
+        store_rows(sm + i * SROW, t);
     }
     __syncthreads();
-    for (int l = a.last - 1; l >= a.first; --l) {
-        for (int64_t i = threadIdx.x; i < a.rows[l]; i += blockDim.x)
-            backsub_row(a.lvl[l], a.rows[l], a.x[l + 1], i, a.x[l], st, a.stride[l]);
+    int s = 1;
+    for (; s < R; s <<= 1) {  // reduce: rows at multiples of 2s from their neighbours at +-s
+        for (int pos = threadIdx.x * 2 * s; pos < R; pos += blockDim.x * 2 * s) {
+            const RowS c = load_rows(sm + pos * SROW);
+            RowS o = c;
+            o.l00 = o.l01 = o.l10 = o.l11 = 0.0;
+            o.u00 = o.u01 = o.u10 = o.u11 = 0.0;
+            if (pos - s >= 0) {
+                const RowS p = load_rows(sm + (pos - s) * SROW);
+                const Inv2 v = inv_spd2s(p, (int64_t)(pos - s) * stride_unknowns, st);
+                const double a00 = c.l00 * v.i00 + c.l01 * v.i01, a01 = c.l00 * v.i01 + c.l01 * v.i11;
+                const double a10 = c.l10 * v.i00 + c.l11 * v.i01, a11 = c.l10 * v.i01 + c.l11 * v.i11;
+                o.d00 -= a00 * p.u00 + a01 * p.u10;
+                o.d01 -= a00 * p.u01 + a01 * p.u11;
+                o.d11 -= a10 * p.u01 + a11 * p.u11;
+                o.b00 -= a00 * p.b00 + a01 * p.b10;
+                o.b01 -= a00 * p.b01 + a01 * p.b11;
+                o.b10 -= a10 * p.b00 + a11 * p.b10;
+                o.b11 -= a10 * p.b01 + a11 * p.b11;
+                o.l00 = -(a00 * p.l00 + a01 * p.l10);
+                o.l01 = -(a00 * p.l01 + a01 * p.l11);
+                o.l10 = -(a10 * p.l00 + a11 * p.l10);
+                o.l11 = -(a10 * p.l01 + a11 * p.l11);
+            }
+            if (pos + s < R) {
+                const RowS q = load_rows(sm + (pos + s) * SROW);
+                const Inv2 v = inv_spd2s(q, (int64_t)(pos + s) * stride_unknowns, st);
+                const double g00 = c.u00 * v.i00 + c.u01 * v.i01, g01 = c.u00 * v.i01 + c.u01 * v.i11;
+                const double g10 = c.u10 * v.i00 + c.u11 * v.i01, g11 = c.u10 * v.i01 + c.u11 * v.i11;
+                o.d00 -= g00 * q.l00 + g01 * q.l10;
+                o.d01 -= g00 * q.l01 + g01 * q.l11;
+                o.d11 -= g10 * q.l01 + g11 * q.l11;
+                o.b00 -= g00 * q.b00 + g01 * q.b10;
+                o.b01 -= g00 * q.b01 + g01 * q.b11;
+                o.b10 -= g10 * q.b00 + g11 * q.b10;
+                o.b11 -= g10 * q.b01 + g11 * q.b11;
+                o.u00 = -(g00 * q.u00 + g01 * q.u10);
+                o.u01 = -(g00 * q.u01 + g01 * q.u11);
+                o.u10 = -(g10 * q.u00 + g11 * q.u10);
+                o.u11 = -(g10 * q.u01 + g11 * q.u11);
+            }
+            store_rows(sm + pos * SROW, o);
+        }
         __syncthreads();
+    }
+    // row 0 now stands alone
+    if (threadIdx.x == 0) {
+        RowS r = load_rows(sm);
+        const Inv2 v = inv_spd2s(r, 0, st);
+        const double t00 = r.b00, t01 = r.b01, t10 = r.b10, t11 = r.b11;
+        r.b00 = v.i00 * t00 + v.i01 * t10;
+        r.b01 = v.i00 * t01 + v.i01 * t11;
+        r.b10 = v.i01 * t00 + v.i11 * t10;
+        r.b11 = v.i01 * t01 + v.i11 * t11;
+        store_rows(sm, r);
+    }
+    __syncthreads();
+    // back up: rows at odd multiples of h from the solved rows at +-h
+    for (int h = s >> 1; h >= 1; h >>= 1) {
+        for (int pos = h + (int)threadIdx.x * 2 * h; pos < R; pos += blockDim.x * 2 * h) {
+            RowS r = load_rows(sm + pos * SROW);
+            const RowS xl = load_rows(sm + (pos - h) * SROW);
+            double t00 = r.b00 - (r.l00 * xl.b00 + r.l01 * xl.b10);
+            double t01 = r.b01 - (r.l00 * xl.b01 + r.l01 * xl.b11);
+            double t10 = r.b10 - (r.l10 * xl.b00 + r.l11 * xl.b10);
+            double t11 = r.b11 - (r.l10 * xl.b01 + r.l11 * xl.b11);
+            if (pos + h < R) {
+                const RowS xr = load_rows(sm + (pos + h) * SROW);
+                t00 -= r.u00 * xr.b00 + r.u01 * xr.b10;
+                t01 -= r.u00 * xr.b01 + r.u01 * xr.b11;
+                t10 -= r.u10 * xr.b00 + r.u11 * xr.b10;
+                t11 -= r.u10 * xr.b01 + r.u11 * xr.b11;
+            }
+            const double rdet = 1.0 / (r.d00 * r.d11 - r.d01 * r.d01);
+            const double i00 = r.d11 * rdet, i01 = -r.d01 * rdet, i11 = r.d00 * rdet;
+            r.b00 = i00 * t00 + i01 * t10;
+            r.b01 = i00 * t01 + i01 * t11;
+            r.b10 = i01 * t00 + i11 * t10;
+            r.b11 = i01 * t01 + i11 * t11;
+            store_rows(sm + pos * SROW, r);
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < R; i += blockDim.x) {
+        const RowS r = load_rows(sm + i * SROW);
+        double2 *o = reinterpret_cast<double2 *>(x_out + (int64_t)i * 4);
+        o[0] = make_double2(r.b00, r.b01);
+        o[1] = make_double2(r.b10, r.b11);
     }
 }
 
@@ -340,14 +458,17 @@ __global__ void __launch_bounds__(STAT_THREADS) weighted_stats_kernel(const floa
 int64_t background_rows(int64_t n) { return (n + 1) / 2; }
 
 size_t background_workspace_bytes(int64_t n) {
-    // rows of all levels (<= 2 x level 0) + solutions of all levels + partial sums
-    int64_t rows = background_rows(n), total = 0;
+    // stored rows of levels 1.. (level 0 is formed on the fly) + solutions of all levels + partial sums
+    int64_t rows = background_rows(n), total_rows = 0, total_x = 0;
+    bool first = true;
     while (true) {
-        total += rows;
+        if (!first) total_rows += rows;
+        total_x += rows;
+        first = false;
         if (rows <= 1) break;
         rows = (rows + 1) / 2;
     }
-    return (size_t)total * (ROW + 4) * 8 + (size_t)(BG_SUM_BLOCKS * 2 + 2) * 8 + 256;
+    return (size_t)total_rows * ROW * 8 + (size_t)total_x * 4 * 8 + (size_t)(BG_SUM_BLOCKS * 2 + 2) * 8 + 256;
 }
 
 cudaError_t launch_background_stats(const float *resid, const float *inv, int64_t m, int64_t n, int64_t ld,
@@ -366,7 +487,7 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
                                     int zero_center, double *out, void *workspace, BackgroundStatus *status,
                                     cudaStream_t st, int *launches) {
     if (n <= 0) return cudaSuccess;
-    // carve the workspace
+    // levels: rows[0] = ceil(n / 2) block rows formed on the fly from w / rhs, each following level half of it
     int64_t rows[BG_MAX_LEVELS], stride[BG_MAX_LEVELS];
     double *lvl[BG_MAX_LEVELS], *x[BG_MAX_LEVELS];
     int nl = 0;
@@ -381,45 +502,45 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
             s *= 2;
         }
     }
+    // the large levels get one launch each way; from the first level with <= BG_SMALL_ROWS rows on,
+    // one CTA finishes the recursion in shared memory
+    int first_small = 0;
+    while (rows[first_small] > BG_SMALL_ROWS) ++first_small;
     double *p = static_cast<double *>(workspace);
-    for (int l = 0; l < nl; ++l) {
+    lvl[0] = nullptr;  // never stored
+    for (int l = 1; l <= first_small; ++l) {
         lvl[l] = p;
         p += rows[l] * ROW;
     }
-    for (int l = 0; l < nl; ++l) {
+    for (int l = 0; l <= first_small; ++l) {
         x[l] = p;
         p += rows[l] * 4;
     }
     double *partial = p;
+    auto level = [&](int l) {
+        Rows r{};
+        r.stored = lvl[l];
+        r.l0 = Level0{w, rhs, n, lam, lam_first};
+        return r;
+    };
     const BackgroundStatus init{INT64_MAX, 0.0};
     cudaError_t e = cudaMemcpyAsync(status, &init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
+    // per device, so set on every call (a few hundred nanoseconds)
+    e = cudaFuncSetAttribute(small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMALL_ROWS * SROW * 8);
+    if (e != cudaSuccess) return e;
     int count = 0;
     const int T = 256;
-    build_rows_kernel<<<(unsigned)((rows[0] + T - 1) / T), T, 0, st>>>(w, rhs, n, lam, lam_first, rows[0], lvl[0], status);
-    ++count;
-    // large levels: one launch each; from the first level with <= BG_SMALL_ROWS rows on, one CTA does the rest
-    int first_small = 0;
-    while (first_small < nl - 1 && rows[first_small] > BG_SMALL_ROWS) ++first_small;
     for (int l = 0; l < first_small; ++l) {
-        reduce_kernel<<<(unsigned)((rows[l + 1] + T - 1) / T), T, 0, st>>>(lvl[l], rows[l], rows[l + 1], stride[l], lvl[l + 1],
-                                                                         status);
+        reduce_kernel<<<(unsigned)((rows[l + 1] + T - 1) / T), T, 0, st>>>(level(l), rows[l], rows[l + 1], stride[l],
+                                                                         lvl[l + 1], status);
         ++count;
     }
-    SmallArgs sa{};
-    for (int l = 0; l < nl; ++l) {
-        sa.lvl[l] = lvl[l];
-        sa.lvl_out[l] = lvl[l];
-        sa.x[l] = x[l];
-        sa.rows[l] = rows[l];
-        sa.stride[l] = stride[l];
-    }
-    sa.first = first_small;
-    sa.last = nl - 1;
-    small_system_kernel<<<1, 1024, 0, st>>>(sa, status);
+    small_system_kernel<<<1, 1024, (size_t)rows[first_small] * SROW * 8, st>>>(level(first_small), rows[first_small],
+                                                                             stride[first_small], x[first_small], status);
     ++count;
     for (int l = first_small - 1; l >= 0; --l) {
-        backsub_kernel<<<(unsigned)((rows[l] + T - 1) / T), T, 0, st>>>(lvl[l], rows[l], x[l + 1], x[l], status, stride[l]);
+        backsub_kernel<<<(unsigned)((rows[l] + T - 1) / T), T, 0, st>>>(level(l), rows[l], x[l + 1], x[l], status, stride[l]);
         ++count;
     }
     double *mu = nullptr;

@@ -7,7 +7,7 @@
 namespace cb200 {
 
 constexpr int BG_MAX_LEVELS = 32;
-constexpr int BG_SMALL_ROWS = 2048;  // from this many block rows on, one CTA finishes the recursion
+constexpr int BG_SMALL_ROWS = 1024;  // from this many block rows on, one CTA finishes the recursion in shared memory
 constexpr int BG_SUM_BLOCKS = 1024;
 
 // outcome of a solve: first unknown whose pivot fell below the reference's floor (1e-12), or
