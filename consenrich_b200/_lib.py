@@ -16,7 +16,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 ABI_VERSION = 2
 
 FAM_FOLD, FAM_FORWARD, FAM_BACKWARD, FAM_RESIDUALS, FAM_PRECISION = range(5)
-FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates", "background")
+FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates", "background", "munc")
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -108,6 +108,10 @@ SIGNATURES = {
     "cb200_host_background_stats": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, C.POINTER(_i64)]),
     "cb200_host_background_solve": (C.c_int, [_vp, _vp, _vp, _i64, _dbl, _dbl, _i32, _vp, C.POINTER(_i64),
                                               C.POINTER(_dbl)]),
+    "cb200_munc_smooth_local_evidence": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _i64, _i64, _dbl, _vp, _i64,
+                                                   _vp]),
+    "cb200_host_munc_smooth_local_evidence": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _dbl, _vp,
+                                                        C.POINTER(_i32)]),
 }
 
 _lib = None

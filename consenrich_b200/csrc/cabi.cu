@@ -18,6 +18,7 @@
 #include "../../include/consenrich_b200.h"
 #include "ssm_kernels.cuh"
 #include "background_kernels.cuh"
+#include "munc_kernels.cuh"
 
 using namespace cb200;
 
@@ -68,7 +69,7 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_BG = 5, FAM_COUNT = 6 };
+enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_BG = 5, FAM_MUNC = 6, FAM_COUNT = 7 };
 
 struct TimedSpan {
     cudaEvent_t a, b;
@@ -91,13 +92,14 @@ struct cb200_ctx {
     // arena (device)
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, smo, smo2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     DevBuf bg_ws, bg_w, bg_rhs, bg_out, bg_status;  // background solve: workspace, operands, outcome
+    DevBuf mask;  // MUNC stage: exclusion mask
     double *sums_host = nullptr;  // pinned double[2]
     // timing
     bool timing = false;
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> pool;
-    double fam_ms[FAM_COUNT] = {0, 0, 0, 0, 0, 0};
-    int64_t fam_n[FAM_COUNT] = {0, 0, 0, 0, 0, 0};
+    double fam_ms[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    int64_t fam_n[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 namespace {
@@ -476,7 +478,7 @@ void cb200_ctx_destroy(cb200_ctx *c) {
     DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->xf2, &c->Pf2,
                       &c->Qf2, &c->smo, &c->smo2, &c->D,
                       &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard,
-                      &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status};
+                      &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status, &c->mask};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->sums_host) cudaFreeHost(c->sums_host);
@@ -1241,6 +1243,67 @@ int cb200_host_background_solve(cb200_ctx *c, const double *weight, const double
     if (bad_index) *bad_index = bi;
     if (bad_value) *bad_value = bv;
     CB_TRY(d2h(c, out, c->bg_out.p, (size_t)n * 8));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
+// ---- observation-noise (MUNC) stage -----------------------------------------------------
+static int check_munc_smooth_args(int32_t mask_mode, int64_t window, double eps) {
+    // messages of cconsenrich.pyx:5665-5668
+    if (window < 1) return fail(CB200_ERR_INVALID, "windowIntervals must be positive");
+    if (!(eps > 0.0) || !std::isfinite(eps)) return fail(CB200_ERR_INVALID, "eps must be positive and finite");
+    if (mask_mode < 0 || mask_mode > 2) return fail(CB200_ERR_INVALID, "excludeMask must be one- or two-dimensional");
+    if (window > MUNC_MAX_WINDOW)
+        return fail(CB200_ERR_UNSUPPORTED, "windowIntervals above %lld is not supported on the device",
+                    (long long)MUNC_MAX_WINDOW);
+    return CB200_OK;
+}
+
+int cb200_munc_smooth_local_evidence(cb200_ctx *c, const float *local, const unsigned char *mask, int32_t mask_mode,
+                                     int64_t m, int64_t n, int64_t ld, int64_t mask_ld, int64_t window, double eps,
+                                     float *out, int64_t out_ld, int32_t *invalid) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !invalid) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_munc_smooth_args(mask_mode, window, eps));
+    if (m < 0 || n < 0 || ld < n || out_ld < n) return fail(CB200_ERR_INVALID, "bad matrix shape");
+    if (mask_mode != 0 && !mask) return fail(CB200_ERR_INVALID, "excludeMask is NULL");
+    if (m == 0 || n == 0) {
+        CU_TRY(cudaMemsetAsync(invalid, 0, sizeof(int32_t), c->stream));
+        return CB200_OK;
+    }
+    if (!local || !out) return fail(CB200_ERR_INVALID, "NULL argument");
+    Span sp(c, FAM_MUNC);
+    CU_TRY(launch_munc_rolling_mean(local, mask, mask_mode, m, n, ld, mask_ld, window, eps, out, out_ld,
+                                    reinterpret_cast<int *>(invalid), c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_host_munc_smooth_local_evidence(cb200_ctx *c, const float *local, const unsigned char *mask,
+                                          int32_t mask_mode, int64_t m, int64_t n, int64_t window, double eps,
+                                          float *out, int32_t *invalid) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !invalid) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_munc_smooth_args(mask_mode, window, eps));
+    *invalid = 0;
+    if (m <= 0 || n <= 0) return CB200_OK;
+    if (!local || !out || (mask_mode != 0 && !mask)) return fail(CB200_ERR_INVALID, "NULL argument");
+    int64_t ld = 0;
+    CB_TRY(upload_tracks(c, c->data, local, m, n, &ld));
+    CB_TRY(ensure(c, c->munc, (size_t)m * (size_t)ld * 4));  // output, same pitch
+    const size_t mask_bytes = mask_mode == 1 ? (size_t)n : (mask_mode == 2 ? (size_t)m * (size_t)n : 0);
+    if (mask_bytes) {
+        CB_TRY(ensure(c, c->mask, mask_bytes));
+        CB_TRY(h2d(c, c->mask.p, mask, mask_bytes));
+    }
+    CB_TRY(ensure(c, c->bg_status, sizeof(BackgroundStatus)));
+    int32_t *dflag = reinterpret_cast<int32_t *>(c->bg_status.p);
+    CB_TRY(cb200_munc_smooth_local_evidence(c, static_cast<const float *>(c->data.p),
+                                            static_cast<const unsigned char *>(c->mask.p), mask_mode, m, n, ld, n, window,
+                                            eps, static_cast<float *>(c->munc.p), ld, dflag));
+    CB_TRY(d2h(c, invalid, dflag, sizeof(int32_t)));
+    CU_TRY(cudaMemcpy2DAsync(out, (size_t)n * 4, c->munc.p, (size_t)ld * 4, (size_t)n * 4, (size_t)m,
+                             cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return CB200_OK;
 }

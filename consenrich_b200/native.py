@@ -34,6 +34,8 @@ _HOT_PATH = ("cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPas
              "cfixedBackgroundECM", "cfixedBackgroundECMLevel")
 # the callers on the other side of the ECM inside an outer pass
 _BACKGROUND = ("cbackgroundWeightedStats", "cbackgroundWeightedStatsWithSupport", "csolveZeroCenteredBackground")
+# dense kernels of the observation-noise stage that produces matrixMunc
+_MUNC = ("cMuncSmoothDenseLocalEvidence",)
 
 
 def _f32(x) -> float:
@@ -539,20 +541,63 @@ def csolveZeroCenteredBackground(weightTrack, rhsTrack, lam, zeroCenter=True, la
     return out
 
 
+# ------------------------------------------------------------------------------------------
+# observation-noise (MUNC) stage: dense kernels (consenrich.py:7546)
+# ------------------------------------------------------------------------------------------
+def cMuncSmoothDenseLocalEvidence(localEvidence, windowIntervals, excludeMask=None, eps=1.0e-12):
+    """Centred rolling mean of per-cell local evidence with an exclusion mask; signature, checks and
+    error texts of cconsenrich.pyx:5642-5740."""
+    local = np.asarray(localEvidence)
+    if local.dtype != np.float32 or local.ndim != 2:
+        raise ValueError("localEvidence must be a two-dimensional float32 array")
+    local = np.ascontiguousarray(local)
+    m, n = local.shape
+    window = int(windowIntervals)
+    eps_d = _f32(eps)  # the reference takes eps as a C float (pyx:5646)
+    if window < 1:
+        raise ValueError("windowIntervals must be positive")
+    if eps_d <= 0.0 or not np.isfinite(eps_d):
+        raise ValueError("eps must be positive and finite")
+    mask, mode = None, 0
+    if excludeMask is not None:
+        mask = np.ascontiguousarray(excludeMask, dtype=np.uint8)
+        if mask.ndim == 1:
+            if mask.shape[0] != n:
+                raise ValueError("excludeMask length must match interval count")
+            mode = 1
+        elif mask.ndim == 2:
+            if mask.shape[0] != m or mask.shape[1] != n:
+                raise ValueError("excludeMask shape must match localEvidence shape")
+            mode = 2
+        else:
+            raise ValueError("excludeMask must be one- or two-dimensional")
+    out = np.empty((m, n), np.float32)
+    if m == 0 or n == 0:
+        return out
+    invalid = C.c_int32(0)
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_munc_smooth_local_evidence(ctx.handle, _ptr(local), _ptr(mask), mode, m, n, window,
+                                                              eps_d, _ptr(out), C.byref(invalid)))
+    if invalid.value:
+        raise ValueError("active local evidence cells must be positive and finite")
+    return out
+
+
 _saved: dict = {}
 
 
-def install(module=None, background=True):
+def install(module=None, background=True, munc=True):
     """Replace the six hot-path attributes of ``consenrich.cconsenrich`` (or ``module``) with the
     B200 implementations.  ``core.py`` looks them up by attribute at call time (core.py:4274,
     4309, 3286), so ``runConsenrich`` picks them up without modification.  ``background``: also the
-    three background-track functions (core.py:7543, 8145)."""
+    three background-track functions (core.py:7543, 8145); ``munc``: also the dense kernels of the
+    observation-noise stage (consenrich.py:7546)."""
     if module is None:
         import importlib
         module = importlib.import_module("consenrich.cconsenrich")
     _lib.load()  # fail now, loudly, if the native library is missing
     saved = _saved.setdefault(id(module), {})
-    for name in _HOT_PATH + (_BACKGROUND if background else ()):
+    for name in _HOT_PATH + (_BACKGROUND if background else ()) + (_MUNC if munc else ()):
         if name not in saved:
             saved[name] = getattr(module, name, None)
         setattr(module, name, globals()[name])

@@ -17,6 +17,7 @@
  *   _accumulateObservationValue :259-283                cb200_fold_tracks (device fold kernel)
  *   cbackgroundWeightedStats[WithSupport] :9675-9724    cb200_host_background_stats
  *   csolveZeroCenteredBackground :944-1096              cb200_host_background_solve
+ *   cMuncSmoothDenseLocalEvidence :5547-5740            cb200_host_munc_smooth_local_evidence
  *
  * Conventions
  *   - plain C: pointers, sizes, POD structs; no torch / numpy types.
@@ -266,6 +267,22 @@ CB200_API int cb200_host_background_stats(cb200_ctx *ctx, const float *resid, co
 CB200_API int cb200_host_background_solve(cb200_ctx *ctx, const double *weight, const double *rhs, int64_t n,
                                 double lam, double lam_first, int32_t zero_center, double *out,
                                 int64_t *bad_index, double *bad_value);
+
+/* ---- observation-noise (MUNC) stage: dense [tracks x intervals] kernels --------------------- */
+#define CB200_MUNC_MAX_WINDOW 8192
+/* cMuncSmoothDenseLocalEvidence (cconsenrich.pyx:5547-5740): out[j][i] = max(eps, mean of the unmasked
+ * local[j][k] over the window of `window` intervals centred on i (clipped at the ends)), the cell itself
+ * where the whole window is masked; float32 in and out, float64 sums.  mask_mode 0: no mask; 1: mask is
+ * uint8 [n]; 2: mask is uint8 [m][mask_ld]; nonzero excludes a cell.  *invalid (device int32) is set to 1
+ * when an unmasked cell is not positive and finite (the reference raises ValueError).
+ * 1 <= window <= CB200_MUNC_MAX_WINDOW, otherwise CB200_ERR_UNSUPPORTED. */
+CB200_API int cb200_munc_smooth_local_evidence(cb200_ctx *ctx, const float *local, const unsigned char *mask,
+                                     int32_t mask_mode, int64_t m, int64_t n, int64_t ld, int64_t mask_ld,
+                                     int64_t window, double eps, float *out, int64_t out_ld, int32_t *invalid);
+/* The same with HOST arrays (local, out: [m][n] contiguous; mask: [n] or [m][n]); *invalid is a host int32. */
+CB200_API int cb200_host_munc_smooth_local_evidence(cb200_ctx *ctx, const float *local, const unsigned char *mask,
+                                          int32_t mask_mode, int64_t m, int64_t n, int64_t window, double eps,
+                                          float *out, int32_t *invalid);
 
 #ifdef __cplusplus
 }

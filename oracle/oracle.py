@@ -17,6 +17,10 @@ and (``oracle/background_oracle.c``) the background-track functions on the other
 * ``cbackgroundWeightedStats[WithSupport]`` <- cconsenrich.pyx:9675-9724
 * ``csolveZeroCenteredBackground``          <- cconsenrich.pyx:944-1096
 
+and (``oracle/munc_oracle.c``) the dense kernels of the observation-noise stage:
+
+* ``cMuncSmoothDenseLocalEvidence``         <- cconsenrich.pyx:5547-5740
+
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this module.  The product (``consenrich_b200``) never does.
 
@@ -42,7 +46,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libssm_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the C restatement (gcc, reference flags).  Returns the library path."""
-    srcs = [os.path.join(_HERE, f) for f in ("ssm_oracle.c", "background_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("ssm_oracle.c", "background_oracle.c", "munc_oracle.c")]
     if force or (not os.path.exists(_LIB_PATH)) or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
     return _LIB_PATH
@@ -586,4 +590,47 @@ def csolveZeroCenteredBackground(weightTrack, rhsTrack, lam, zeroCenter=True, la
     if bad >= 0:
         raise RuntimeError("roughness-penalized LDL factorization required pivot "
                            f"modification at index {bad} (pivot={val:.6g}, floor={min_pivot:.6g}).")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# observation-noise (MUNC) stage (oracle/munc_oracle.c)
+# ------------------------------------------------------------------------------------------
+def cMuncSmoothDenseLocalEvidence(localEvidence, windowIntervals, excludeMask=None, eps=1.0e-12):
+    """cconsenrich.pyx:5642-5740 (checks and error texts included)."""
+    local = np.asarray(localEvidence)
+    if local.dtype != np.float32 or local.ndim != 2:
+        raise ValueError("localEvidence must be a two-dimensional float32 array")
+    local = np.ascontiguousarray(local)
+    m, n = local.shape
+    window = int(windowIntervals)
+    eps_d = float(np.float32(eps))
+    if window < 1:
+        raise ValueError("windowIntervals must be positive")
+    if eps_d <= 0.0 or not np.isfinite(eps_d):
+        raise ValueError("eps must be positive and finite")
+    mask, mode = None, 0
+    if excludeMask is not None:
+        mask = np.ascontiguousarray(excludeMask, dtype=np.uint8)
+        if mask.ndim == 1:
+            if mask.shape[0] != n:
+                raise ValueError("excludeMask length must match interval count")
+            mode = 1
+        elif mask.ndim == 2:
+            if mask.shape[0] != m or mask.shape[1] != n:
+                raise ValueError("excludeMask shape must match localEvidence shape")
+            mode = 2
+        else:
+            raise ValueError("excludeMask must be one- or two-dimensional")
+    lib = _L()
+    lib.munc_smooth_invalid_index.restype = C.c_int64
+    lib.munc_smooth_invalid_index.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64]
+    lib.munc_smooth_rows.restype = None
+    lib.munc_smooth_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_double,
+                                     C.c_void_p]
+    mp = mask.ctypes.data if mask is not None else None
+    if lib.munc_smooth_invalid_index(local.ctypes.data, mp, mode, m, n) >= 0:
+        raise ValueError("active local evidence cells must be positive and finite")
+    out = np.empty((m, n), np.float32)
+    lib.munc_smooth_rows(local.ctypes.data, mp, mode, m, n, window, eps_d, out.ctypes.data)
     return out

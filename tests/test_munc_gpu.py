@@ -1,0 +1,90 @@
+"""GPU parity of cMuncSmoothDenseLocalEvidence through the C ABI.
+
+The reference slides a float64 running sum along each row; the kernel reads each window as a
+difference of tile-local float64 prefix sums.  The two sums differ by ~1e-13 relative, so the float32
+outputs are identical except where that lands on a rounding boundary: stated tolerance 1 float32 ulp
+(1.2e-7 relative), and all but a vanishing fraction of cells must be bit-equal."""
+import numpy as np
+import pytest
+
+from golden.make_munc_golden import exclude_mask, local_evidence
+from test_munc_oracle import golden_cases, run_case
+
+pytestmark = pytest.mark.gpu
+ULP = float(np.finfo(np.float32).eps)
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import consenrich_b200 as cb
+    return cb
+
+
+def assert_one_ulp(got, want, what):
+    assert got.shape == want.shape and got.dtype == np.float32, what
+    g, w = got.astype(np.float64), want.astype(np.float64)
+    assert np.all(np.abs(g - w) <= ULP * np.abs(w)), f"{what}: beyond one float32 ulp"
+    differing = np.count_nonzero(got != want)
+    assert differing <= max(2, 1e-5 * got.size), f"{what}: {differing} of {got.size} cells differ"
+
+
+def test_matches_reference_golden_vectors(cb):
+    for name, c in golden_cases().items():
+        assert_one_ulp(run_case(cb, c), c["out"], name)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_matches_oracle_on_fresh_seeds(cb, oracle, mode):
+    rng = np.random.default_rng(100 + mode)
+    shapes = [(1, 1, 1), (2, 5, 3), (3, 2047, 4), (3, 2048, 5), (2, 2049, 64), (10, 70001, 41), (4, 9000, 2048),
+              (2, 30000, 8192), (1, 100, 1000), (130, 3000, 16)]
+    for m, n, w in shapes:
+        le, mk = local_evidence(rng, m, n), exclude_mask(rng, m, n, mode)
+        want = oracle.cMuncSmoothDenseLocalEvidence(le, w, excludeMask=mk, eps=1e-6)
+        got = cb.cMuncSmoothDenseLocalEvidence(le, w, excludeMask=mk, eps=1e-6)
+        assert_one_ulp(got, want, f"{m}x{n} window {w} mask mode {mode}")
+
+
+def test_full_size_properties(cb):
+    """hg38 chr19 @ 25 bp x 10 tracks: constant rows come back unchanged; a fully masked stretch returns
+    the cells themselves; outputs are bounded by the window's extremes."""
+    m, n, w = 10, 2_344_705, 41
+    rng = np.random.default_rng(1)
+    const = np.full((m, n), np.float32(0.375))
+    np.testing.assert_array_equal(cb.cMuncSmoothDenseLocalEvidence(const, w), const)
+    le = local_evidence(rng, m, n)
+    mk = np.zeros(n, np.uint8)
+    mk[1000:1200] = 1
+    out = cb.cMuncSmoothDenseLocalEvidence(le, w, excludeMask=mk, eps=1e-12)
+    np.testing.assert_array_equal(out[:, 1030:1170], le[:, 1030:1170])  # windows with no unmasked cell
+    assert out.min() >= le.min() * (1 - 1e-6) and out.max() <= le.max() * (1 + 1e-6)
+    j, i = 3, 1_500_000
+    want = np.float32(le[j, i - w // 2: i - w // 2 + w].astype(np.float64).mean())
+    assert abs(float(out[j, i]) - float(want)) <= ULP * float(want)
+
+
+def test_errors_follow_the_reference(cb):
+    le = np.ones((2, 40), np.float32)
+    with pytest.raises(ValueError, match="windowIntervals must be positive"):
+        cb.cMuncSmoothDenseLocalEvidence(le, 0)
+    with pytest.raises(ValueError, match="eps must be positive and finite"):
+        cb.cMuncSmoothDenseLocalEvidence(le, 3, eps=-1.0)
+    with pytest.raises(ValueError, match="excludeMask length must match interval count"):
+        cb.cMuncSmoothDenseLocalEvidence(le, 3, excludeMask=np.zeros(41, np.uint8))
+    with pytest.raises(ValueError, match="excludeMask shape must match localEvidence shape"):
+        cb.cMuncSmoothDenseLocalEvidence(le, 3, excludeMask=np.zeros((2, 41), np.uint8))
+    with pytest.raises(ValueError, match="excludeMask must be one- or two-dimensional"):
+        cb.cMuncSmoothDenseLocalEvidence(le, 3, excludeMask=np.zeros((1, 2, 40), np.uint8))
+    bad = le.copy()
+    bad[1, 7] = np.nan
+    with pytest.raises(ValueError, match="active local evidence cells must be positive and finite"):
+        cb.cMuncSmoothDenseLocalEvidence(bad, 5)
+    mk = np.zeros(40, np.uint8)
+    mk[7] = 1
+    assert cb.cMuncSmoothDenseLocalEvidence(bad, 5, excludeMask=mk).shape == (2, 40)
+    with pytest.raises(NotImplementedError, match="not supported on the device"):
+        cb.cMuncSmoothDenseLocalEvidence(le, 8193)
+    assert cb.cMuncSmoothDenseLocalEvidence(np.zeros((0, 5), np.float32), 3).shape == (0, 5)

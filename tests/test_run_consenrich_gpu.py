@@ -75,12 +75,17 @@ def test_run_consenrich_with_b200_kernels_matches_the_reference(ref_core, case):
     mod = cb.install()
     try:
         assert mod.cforwardPass is cb.cforwardPass  # the driver now calls into libconsenrich_b200.so
+        assert mod.csolveZeroCenteredBackground is cb.csolveZeroCenteredBackground
+        solves = []
+        mod.csolveZeroCenteredBackground = lambda *a, **k: (solves.append(1), cb.csolveZeroCenteredBackground(*a, **k))[1]
         launches0 = cb._lib.default_context().launch_count
         got = ref_core.runConsenrich(data, munc, **kw)
         launches = cb._lib.default_context().launch_count - launches0
     finally:
         cb.uninstall()
     assert launches > 10, "runConsenrich did not reach the GPU kernels"
+    if kw.get("fitBackground", True):
+        assert solves, "the background update did not reach the device solve"
     state_w, P_w, res_w, nis_w, bm_w, diag_w = want
     state_g, P_g, res_g, nis_g, bm_g, diag_g = got
     np.testing.assert_array_equal(bm_g, bm_w)
