@@ -266,7 +266,7 @@ def run_reference_arm(args):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
-def background_block(torch, dev, stream, ctx, rep, host, m, n, ld, no_cpu):
+def background_block(torch, dev, stream, ctx, reps, host, m, n, ld, no_cpu):
     """Times the background-track row: cbackgroundWeightedStatsWithSupport and
     csolveZeroCenteredBackground (zero-centred, lam = 128: constants.py's ECM_backgroundSmoothness) at the
     workload's size, device-resident, through the host API, and the reference's own functions on one core."""
@@ -275,14 +275,20 @@ def background_block(torch, dev, stream, ctx, rep, host, m, n, ld, no_cpu):
     from consenrich_b200 import _lib
     from consenrich_b200.device import _p
     L = ctx._lib
-    d, v, _ = rep  # count / variance matrices stand in for residuals / inverse variances
+    d, v, _ = reps[0]  # count / variance matrices stand in for residuals / inverse variances
+    turn = [0]
+
+    def rotate():  # inputs larger than L2: a different replica every call
+        turn[0] += 1
+        return reps[turn[0] % len(reps)]
     w = torch.empty(n, dtype=torch.float64, device=dev)
     rhs = torch.empty(n, dtype=torch.float64, device=dev)
     out = torch.empty(n, dtype=torch.float64, device=dev)
     lam, lam1 = 128.0, 0.0
 
     def stats():
-        _lib.check(L.cb200_background_stats(ctx.handle, _p(d), _p(v), m, n, ld, _p(w), _p(rhs), None))
+        dd, vv, _ = rotate()
+        _lib.check(L.cb200_background_stats(ctx.handle, _p(dd), _p(vv), m, n, ld, _p(w), _p(rhs), None))
 
     def solve():
         _lib.check(L.cb200_background_solve(ctx.handle, _p(w), _p(rhs), n, lam, lam1, 1, _p(out), None, None))
@@ -328,6 +334,23 @@ def background_block(torch, dev, stream, ctx, rep, host, m, n, ld, no_cpu):
            "solve_ms_device": ms_solve, "solve_frac_of_peak": solve_bytes / (ms_solve * 1e-3) / 1e9 / peak,
            "solve_kernel_launches": int(launches), "stats_ms_host_api": 1e3 * host_stats,
            "solve_ms_host_api": 1e3 * host_solve, "cpu_reference": None}
+    # the rolling local-variance track of the observation-noise stage (cMuncSmoothDenseLocalEvidence), window
+    # 41 intervals (~1 kb at 25 bp), per-interval exclusion mask
+    window = 41
+    mask = (torch.rand(n, device=dev) < 0.02).to(torch.uint8)
+    smooth_out = torch.empty((m, ld), dtype=torch.float32, device=dev)
+    flag = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def smooth():
+        _, vv, _ = rotate()
+        _lib.check(L.cb200_munc_smooth_local_evidence(ctx.handle, _p(vv), _p(mask), 1, m, n, ld, n, window, 1e-12,
+                                                      _p(smooth_out), ld, _p(flag)))
+
+    ms_smooth = timed(smooth)
+    smooth_bytes = 8.0 * m * n + 1.0 * n
+    blk["munc_smooth_ms_device"] = ms_smooth
+    blk["munc_smooth_frac_of_peak"] = smooth_bytes / (ms_smooth * 1e-3) / 1e9 / peak
+    blk["munc_smooth_window"] = window
     if not no_cpu:
         mod, kind = _cpu_module()
         t0 = time.perf_counter()
@@ -336,7 +359,12 @@ def background_block(torch, dev, stream, ctx, rep, host, m, n, ld, no_cpu):
         t0 = time.perf_counter()
         mod.cbackgroundWeightedStatsWithSupport(host["data"], host["munc"])
         cpu_stats = time.perf_counter() - t0
+        hmask = mask.cpu().numpy()
+        t0 = time.perf_counter()
+        mod.cMuncSmoothDenseLocalEvidence(host["munc"], window, excludeMask=hmask, eps=1e-12)
+        cpu_smooth = time.perf_counter() - t0
         blk["cpu_reference"] = {"kind": kind, "cores": 1, "solve_ms": 1e3 * cpu_solve, "stats_ms": 1e3 * cpu_stats,
+                                "munc_smooth_ms": 1e3 * cpu_smooth,
                                 "max_abs_diff_over_max_abs": float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))}
     return blk
 
@@ -479,7 +507,7 @@ def run_b200_arm(args):
     # ---- background track: statistics + penalised solve, rank 0 at N=1 only ----
     background = None
     if world == 1:
-        background = background_block(torch, dev, stream, ctx, reps[0], host, m, n, ld, args.no_cpu_baseline)
+        background = background_block(torch, dev, stream, ctx, reps, host, m, n, ld, args.no_cpu_baseline)
 
     # ---- reduce over ranks: max time ----
     t = torch.tensor([ms_total, e2e_s, ms_sweep], dtype=torch.float64, device=dev)

@@ -397,19 +397,26 @@ __global__ void __launch_bounds__(SUM_THREADS) column_sums_kernel(const double *
     }
 }
 
-// mu of the zero-sum constraint from the per-block partial sums (one warp, fixed order)
-__global__ void mu_kernel(const double *__restrict__ partial, int nparts, int64_t n, double *__restrict__ mu) {
+// mu of the zero-sum constraint from the per-block partial sums (one CTA, fixed reduction tree)
+__global__ void __launch_bounds__(SUM_THREADS) mu_kernel(const double *__restrict__ partial, int nparts, int64_t n,
+                                                         double *__restrict__ mu) {
+    __shared__ double s0[SUM_THREADS], s1[SUM_THREADS];
     double t0 = 0.0, t1 = 0.0;
-    for (int p = threadIdx.x; p < nparts; p += 32) {
+    for (int p = threadIdx.x; p < nparts; p += SUM_THREADS) {
         t0 += partial[2 * p];
         t1 += partial[2 * p + 1];
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-        t0 += __shfl_xor_sync(0xffffffffu, t0, d);
-        t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+    s0[threadIdx.x] = t0;
+    s1[threadIdx.x] = t1;
+    __syncthreads();
+    for (int d = SUM_THREADS / 2; d > 0; d >>= 1) {
+        if ((int)threadIdx.x < d) {
+            s0[threadIdx.x] += s0[threadIdx.x + d];
+            s1[threadIdx.x] += s1[threadIdx.x + d];
+        }
+        __syncthreads();
     }
-    if (threadIdx.x == 0) *mu = (fabs(t1) > MIN_PIVOT) ? t0 / t1 : t0 / (double)n;  // pyx:1078-1081
+    if (threadIdx.x == 0) *mu = (fabs(s1[0]) > MIN_PIVOT) ? s0[0] / s1[0] : s0[0] / (double)n;  // pyx:1078-1081
 }
 
 __global__ void finish_kernel(const double *__restrict__ x, int64_t n, const double *__restrict__ mu_ptr,
@@ -549,7 +556,7 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
         if (nparts > BG_SUM_BLOCKS) nparts = BG_SUM_BLOCKS;
         mu = partial + 2 * BG_SUM_BLOCKS;
         column_sums_kernel<<<nparts, SUM_THREADS, 0, st>>>(x[0], n, partial);
-        mu_kernel<<<1, 32, 0, st>>>(partial, nparts, n, mu);
+        mu_kernel<<<1, SUM_THREADS, 0, st>>>(partial, nparts, n, mu);
         count += 2;
     }
     finish_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x[0], n, mu, out);

@@ -14,6 +14,7 @@
 #include <stdint.h>
 
 #include "munc_kernels.cuh"
+#include "ssm_math.cuh"  // cb_div: the correctly rounded quotient without the special-case path
 
 namespace cb200 {
 namespace {
@@ -57,19 +58,29 @@ rolling_mean_kernel(const float *__restrict__ local, const uint8_t *__restrict__
     __shared__ int seg_cnt[RM_THREADS];
     const float *row = local + j * ld;
 
-    // coalesced load: masked cells contribute 0 to the sums and to the counts
+    // coalesced load, four cells per thread in flight (values are fetched whether masked or not, so that
+    // nothing waits for the mask); masked cells contribute 0 to the sums and to the counts
     int bad = 0;
-    for (int c = threadIdx.x; c < cells; c += RM_THREADS) {
-        const int64_t k = lo + c;
-        double v = 0.0;
-        int a = 0;
-        if (mask_allows(mask, mask_mode, mask_ld, j, k)) {
-            v = (double)row[k];
-            if (!(isfinite(v)) || v <= 0.0) bad = 1;  // pyx:5569-5571
-            a = 1;
+    constexpr int LD_UNROLL = 4;
+    for (int c0 = threadIdx.x; c0 < cells; c0 += RM_THREADS * LD_UNROLL) {
+        float f[LD_UNROLL];
+        bool on[LD_UNROLL];
+#pragma unroll
+        for (int u = 0; u < LD_UNROLL; ++u) {
+            const int c = c0 + u * RM_THREADS;
+            const int64_t k = lo + (c < cells ? c : 0);
+            f[u] = row[k];
+            on[u] = c < cells && mask_allows(mask, mask_mode, mask_ld, j, k);
         }
-        ps[c + 1] = v;
-        pc[c + 1] = a;
+#pragma unroll
+        for (int u = 0; u < LD_UNROLL; ++u) {
+            const int c = c0 + u * RM_THREADS;
+            if (c < cells) {
+                if (on[u] && (!(f[u] > 0.0f) || f[u] == INFINITY)) bad = 1;  // not positive and finite (pyx:5569-5571)
+                ps[c + 1] = on[u] ? (double)f[u] : 0.0;
+                pc[c + 1] = on[u] ? 1 : 0;
+            }
+        }
     }
     __syncthreads();
     // each thread owns a contiguous segment: local inclusive scan
@@ -134,11 +145,22 @@ rolling_mean_kernel(const float *__restrict__ local, const uint8_t *__restrict__
     __syncthreads();
 
     float *orow = out + j * out_ld;
+    const int64_t half = W / 2;
+    // away from the ends of the row every window is [i - half, i - half + W): 32-bit tile-relative indices
+    const bool interior = i0 >= half && (i1 - 1 - half) + W <= n;
     for (int64_t i = i0 + threadIdx.x; i < i1; i += RM_THREADS) {
-        int64_t l, r;
-        window_of(i, n, W, l, r);
-        const int count = pc[r - lo] - pc[l - lo];
-        double v = count > 0 ? (ps[r - lo] - ps[l - lo]) / (double)count : (double)row[i];
+        int bl, br;
+        if (interior) {
+            bl = (int)(i - i0);
+            br = bl + (int)W;
+        } else {
+            int64_t l, r;
+            window_of(i, n, W, l, r);
+            bl = (int)(l - lo);
+            br = (int)(r - lo);
+        }
+        const int count = pc[br] - pc[bl];
+        double v = count > 0 ? cb_div(ps[br] - ps[bl], (double)count) : (double)row[i];
         if (v < eps) v = eps;
         orow[i] = (float)v;
     }
