@@ -610,6 +610,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that write there on their own (NCCL prints its
+    # version line to stdout under torchrun) are sent to stderr for the length of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(json_fd, "w", buffering=1)
     if args.impl == "reference":
         args.steps = 3 if args.steps is None else args.steps
         args.warmup = 1 if args.warmup is None else args.warmup
