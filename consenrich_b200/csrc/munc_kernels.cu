@@ -4,10 +4,10 @@
 // (cconsenrich.pyx:5547-5740).
 //
 // The reference slides one running sum along each row (add the entering cell, subtract the leaving
-// one).  Here a CTA takes a tile of TILE consecutive outputs of one row, loads the TILE + window cells
-// its windows cover into shared memory as float64 (0 for masked cells) next to their 0/1 counts, forms
-// tile-local prefix sums (thread-sequential segments + one block scan of the segment totals) and
-// reads every window as a difference of two prefixes.  The float64 window sums agree with the
+// one).  Here a CTA takes a tile of consecutive outputs of one row, loads the tile + window cells its
+// windows cover (two aligned float4 per thread and group), forms tile-local float64 prefix sums of the
+// unmasked values next to int32 prefix counts (registers, warp shuffles, one pass through shared
+// memory) and reads every window as a difference of two prefixes.  The float64 window sums agree with the
 // reference's running sum to ~1e-13 relative, far below the float32 rounding of the output.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -21,12 +21,7 @@ namespace {
 
 constexpr int RM_THREADS = 256;
 
-__device__ __forceinline__ bool mask_allows(const uint8_t *mask, int mode, int64_t mask_ld, int64_t j, int64_t k) {
-    // _muncSeedMaskAllowsCell with nonzeroMeansActive = False (pyx:4746-4766): nonzero excludes
-    if (mode == 0) return true;
-    const uint8_t v = mode == 1 ? mask[k] : mask[j * mask_ld + k];
-    return v == 0;
-}
+// mask semantics: _muncSeedMaskAllowsCell with nonzeroMeansActive = False (pyx:4746-4766), nonzero excludes
 
 // window [left, right) of output i (pyx:5601-5609)
 __device__ __forceinline__ void window_of(int64_t i, int64_t n, int64_t W, int64_t &left, int64_t &right) {
@@ -39,10 +34,14 @@ __device__ __forceinline__ void window_of(int64_t i, int64_t n, int64_t W, int64
     }
 }
 
+// A CTA covers RM_THREADS * 8 * groups cells of one row, starting at a multiple of 4 so that a thread's
+// 8 cells of a round are two aligned float4.  A thread scans its 8 cells in registers, the warp scans
+// the thread totals by shuffle, the eight warp totals go through shared memory, and only the finished
+// exclusive prefixes (float64 sums, int32 counts) are written to shared memory, once.
 __global__ void __launch_bounds__(RM_THREADS)
 rolling_mean_kernel(const float *__restrict__ local, const uint8_t *__restrict__ mask, int mask_mode, int64_t n,
-                    int64_t ld, int64_t mask_ld, int64_t W, double eps, int tile, float *__restrict__ out, int64_t out_ld,
-                    int *__restrict__ invalid) {
+                    int64_t ld, int64_t mask_ld, int64_t W, double eps, int tile, int groups, int vec_ok,
+                    float *__restrict__ out, int64_t out_ld, int *__restrict__ invalid) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int64_t j = blockIdx.y;
     const int64_t i0 = (int64_t)blockIdx.x * tile;
@@ -51,148 +50,183 @@ rolling_mean_kernel(const float *__restrict__ local, const uint8_t *__restrict__
     int64_t lo, hi, t;
     window_of(i0, n, W, lo, t);
     window_of(i1 - 1, n, W, t, hi);  // cells [lo, hi) cover every window of the tile
-    const int cells = (int)(hi - lo);
-    double *ps = reinterpret_cast<double *>(smem_raw);             // [cells + 1] exclusive prefix of the values
-    int *pc = reinterpret_cast<int *>(ps + (cells + 1 + 1) / 2 * 2);  // [cells + 1] exclusive prefix of the counts
-    __shared__ double seg_sum[RM_THREADS];
-    __shared__ int seg_cnt[RM_THREADS];
+    lo &= ~(int64_t)3;               // aligned start; the extra cells in front are simply part of the prefix
+    const int cells = RM_THREADS * 8 * groups, slots = cells + cells / 8 + 2;
+    double *ps = reinterpret_cast<double *>(smem_raw);  // exclusive prefixes of the values (padded slots)
+    int *pc = reinterpret_cast<int *>(ps + slots);      // ... of the counts
+    __shared__ double warp_sum[RM_THREADS / 32];
+    __shared__ int warp_cnt[RM_THREADS / 32];
     const float *row = local + j * ld;
+    const uint8_t *mrow = mask_mode == 2 ? mask + j * mask_ld : mask;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    // coalesced load, four cells per thread in flight (values are fetched whether masked or not, so that
-    // nothing waits for the mask); masked cells contribute 0 to the sums and to the counts
-    int bad = 0;
-    constexpr int LD_UNROLL = 4;
-    for (int c0 = threadIdx.x; c0 < cells; c0 += RM_THREADS * LD_UNROLL) {
-        float f[LD_UNROLL];
-        bool on[LD_UNROLL];
+    // ---- rounds of RM_THREADS * 8 cells: thread t owns cells [8 t, 8 t + 8) of the round ----
+    // slot of boundary b (prefix over the first b cells): one pad slot after every 8 cells keeps the
+    // per-thread runs of 8 on different banks
+    auto slot = [](int b) { return b == 0 ? 0 : b + ((b - 1) >> 3); };
+    double carry_s = 0.0;  // totals of the rounds before this one
+    int carry_c = 0, bad = 0;
+    for (int g = 0; g < groups; ++g) {
+        const int c0 = (g * RM_THREADS + tid) * 8;
+        const int64_t k = lo + c0;
+        float f[8];
+        uint8_t ex[8];
+        if (vec_ok && k + 8 <= n) {
+            const float4 a = *reinterpret_cast<const float4 *>(row + k), b = *reinterpret_cast<const float4 *>(row + k + 4);
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            if (!mask_mode) {
 #pragma unroll
-        for (int u = 0; u < LD_UNROLL; ++u) {
-            const int c = c0 + u * RM_THREADS;
-            const int64_t k = lo + (c < cells ? c : 0);
-            f[u] = row[k];
-            on[u] = c < cells && mask_allows(mask, mask_mode, mask_ld, j, k);
-        }
+                for (int u = 0; u < 8; ++u) ex[u] = 0;
+            } else if ((reinterpret_cast<uintptr_t>(mrow + k) & 3) == 0) {
+                const uint32_t m0 = *reinterpret_cast<const uint32_t *>(mrow + k);
+                const uint32_t m1 = *reinterpret_cast<const uint32_t *>(mrow + k + 4);
 #pragma unroll
-        for (int u = 0; u < LD_UNROLL; ++u) {
-            const int c = c0 + u * RM_THREADS;
-            if (c < cells) {
-                if (on[u] && (!(f[u] > 0.0f) || f[u] == INFINITY)) bad = 1;  // not positive and finite (pyx:5569-5571)
-                ps[c + 1] = on[u] ? (double)f[u] : 0.0;
-                pc[c + 1] = on[u] ? 1 : 0;
+                for (int u = 0; u < 4; ++u) {
+                    ex[u] = (uint8_t)(m0 >> (8 * u));
+                    ex[4 + u] = (uint8_t)(m1 >> (8 * u));
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) ex[u] = mrow[k + u];
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool in = k + u < n;
+                f[u] = in ? row[k + u] : 1.0f;
+                ex[u] = in ? (mask_mode ? mrow[k + u] : 0) : 1;  // cells past the row end count as excluded
             }
         }
-    }
-    __syncthreads();
-    // each thread owns a contiguous segment: local inclusive scan
-    const int per = (cells + RM_THREADS - 1) / RM_THREADS;
-    const int s0 = min((int)threadIdx.x * per, cells), s1 = min(s0 + per, cells);
-    double run = 0.0;
-    int cnt = 0;
-    for (int c = s0; c < s1; ++c) {
-        run += ps[c + 1];
-        cnt += pc[c + 1];
-        ps[c + 1] = run;
-        pc[c + 1] = cnt;
-    }
-    seg_sum[threadIdx.x] = run;
-    seg_cnt[threadIdx.x] = cnt;
-    if (bad) atomicOr(invalid, 1);
-    __syncthreads();
-    // exclusive scan of the segment totals (256 values: one warp-strided pass is plenty)
-    if (threadIdx.x < 32) {
-        double a = 0.0;
-        int b = 0;
-        // lane l scans segments [8 l, 8 l + 8)
-        double loc_s[8];
-        int loc_c[8];
+        // inclusive scan of the own 8 cells in registers
+        double ls[8];
+        int lc[8];
+        double run = 0.0;
+        int cnt = 0;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            loc_s[u] = a;
-            loc_c[u] = b;
-            a += seg_sum[threadIdx.x * 8 + u];
-            b += seg_cnt[threadIdx.x * 8 + u];
+            const bool on = ex[u] == 0;
+            if (on && (!(f[u] > 0.0f) || f[u] == INFINITY)) bad = 1;  // not positive and finite (pyx:5569-5571)
+            run += on ? (double)f[u] : 0.0;
+            cnt += on ? 1 : 0;
+            ls[u] = run;
+            lc[u] = cnt;
         }
-        double ex_s = a;
-        int ex_c = b;
+        // exclusive prefix of the thread totals: across the warp by shuffle, across warps through shared memory
+        double inc_s = run;
+        int inc_c = cnt;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            const double os = __shfl_up_sync(0xffffffffu, ex_s, d);
-            const int oc = __shfl_up_sync(0xffffffffu, ex_c, d);
-            if ((int)threadIdx.x >= d) {
-                ex_s += os;
-                ex_c += oc;
+            const double os = __shfl_up_sync(0xffffffffu, inc_s, d);
+            const int oc = __shfl_up_sync(0xffffffffu, inc_c, d);
+            if (lane >= d) {
+                inc_s += os;
+                inc_c += oc;
             }
         }
-        ex_s -= a;  // exclusive over lanes
-        ex_c -= b;
+        if (g) __syncthreads();  // the warp totals of the previous round have been read
+        if (lane == 31) {
+            warp_sum[warp] = inc_s;
+            warp_cnt[warp] = inc_c;
+        }
+        __syncthreads();
+        double off_s = carry_s + (inc_s - run);
+        int off_c = carry_c + (inc_c - cnt);
+#pragma unroll
+        for (int w = 0; w < RM_THREADS / 32; ++w) {
+            if (w < warp) {
+                off_s += warp_sum[w];
+                off_c += warp_cnt[w];
+            }
+            carry_s += warp_sum[w];
+            carry_c += warp_cnt[w];
+        }
+        double *pd = ps + slot(c0 + 1);
+        int *pi = pc + slot(c0 + 1);
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            seg_sum[threadIdx.x * 8 + u] = ex_s + loc_s[u];
-            seg_cnt[threadIdx.x * 8 + u] = ex_c + loc_c[u];
+            pd[u] = off_s + ls[u];
+            pi[u] = off_c + lc[u];
         }
     }
-    __syncthreads();
-    const double off_s = seg_sum[threadIdx.x];
-    const int off_c = seg_cnt[threadIdx.x];
-    for (int c = s0; c < s1; ++c) {
-        ps[c + 1] += off_s;
-        pc[c + 1] += off_c;
-    }
-    if (threadIdx.x == 0) {
+    if (bad) atomicOr(invalid, 1);
+    if (tid == 0) {
         ps[0] = 0.0;
         pc[0] = 0;
     }
     __syncthreads();
 
+    // ---- outputs: every window is a difference of two prefixes ----
     float *orow = out + j * out_ld;
     const int64_t half = W / 2;
-    // away from the ends of the row every window is [i - half, i - half + W): 32-bit tile-relative indices
-    const bool interior = i0 >= half && (i1 - 1 - half) + W <= n;
-    for (int64_t i = i0 + threadIdx.x; i < i1; i += RM_THREADS) {
+    const bool interior = i0 >= half && (i1 - 1 - half) + W <= n;  // all windows are [i - half, i - half + W)
+    const int base = interior ? (int)((i0 - half) - lo) : 0;
+    const int nout = (int)(i1 - i0), iw = (int)W;
+    if (interior && vec_ok && (out_ld & 3) == 0 && (nout & 3) == 0 && ((i0 & 3) == 0) &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        // four consecutive outputs per thread: their boundaries are consecutive too
+        for (int o = 4 * tid; o < nout; o += 4 * RM_THREADS) {
+            float r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int ql = slot(base + o + u), qr = slot(base + o + u + iw);
+                const int count = pc[qr] - pc[ql];
+                double v = count > 0 ? cb_div(ps[qr] - ps[ql], (double)count) : (double)row[i0 + o + u];
+                if (v < eps) v = eps;
+                r[u] = (float)v;
+            }
+            *reinterpret_cast<float4 *>(orow + i0 + o) = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        return;
+    }
+    for (int o = tid; o < nout; o += RM_THREADS) {
         int bl, br;
         if (interior) {
-            bl = (int)(i - i0);
-            br = bl + (int)W;
+            bl = base + o;
+            br = bl + iw;
         } else {
             int64_t l, r;
-            window_of(i, n, W, l, r);
+            window_of(i0 + o, n, W, l, r);
             bl = (int)(l - lo);
             br = (int)(r - lo);
         }
-        const int count = pc[br] - pc[bl];
-        double v = count > 0 ? cb_div(ps[br] - ps[bl], (double)count) : (double)row[i];
+        const int ql = slot(bl), qr = slot(br);
+        const int count = pc[qr] - pc[ql];
+        double v = count > 0 ? cb_div(ps[qr] - ps[ql], (double)count) : (double)row[i0 + o];
         if (v < eps) v = eps;
-        orow[i] = (float)v;
+        orow[i0 + o] = (float)v;
     }
 }
 
 }  // namespace
 
-int munc_rolling_tile(int64_t window) {
-    // outputs per CTA: at least as many as the window so that a cell is loaded at most ~twice
-    int tile = 2048;
-    while (tile < window) tile *= 2;
-    return tile;
+// rounds of 8 cells per thread: a CTA covers RM_THREADS * 8 * groups cells, at least 1.5 windows
+// (+ alignment slack), so that a cell is loaded at most about three times even for the widest window
+// shared memory admits
+int munc_rolling_groups(int64_t window) {
+    return (int)((window + window / 2 + 8 + RM_THREADS * 8 - 1) / (RM_THREADS * 8));
 }
 
-size_t munc_rolling_smem(int tile, int64_t window) {
-    const size_t cells = (size_t)tile + (size_t)window + 2;
-    return cells * 8 + cells * 4 + 16;
+size_t munc_rolling_smem(int groups) {
+    const size_t cells = (size_t)RM_THREADS * 8 * groups, slots = cells + cells / 8 + 2;
+    return slots * 8 + slots * 4;
 }
 
 cudaError_t launch_munc_rolling_mean(const float *local, const uint8_t *mask, int mask_mode, int64_t m, int64_t n,
                                      int64_t ld, int64_t mask_ld, int64_t window, double eps, float *out, int64_t out_ld,
                                      int *invalid, cudaStream_t st) {
     if (m <= 0 || n <= 0) return cudaSuccess;
-    const int tile = munc_rolling_tile(window);
-    const size_t smem = munc_rolling_smem(tile, window);
+    const int groups = munc_rolling_groups(window);
+    // outputs per CTA (3: alignment slack of the first cell), a multiple of 4 for the vector stores
+    const int tile = (int)(((int64_t)RM_THREADS * 8 * groups - window - 3) & ~(int64_t)3);
+    const size_t smem = munc_rolling_smem(groups);
+    const int vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(local) & 15) == 0);
     cudaError_t e = cudaFuncSetAttribute(rolling_mean_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaMemsetAsync(invalid, 0, sizeof(int), st);
     if (e != cudaSuccess) return e;
     const dim3 grid((unsigned)((n + tile - 1) / tile), (unsigned)m);
-    rolling_mean_kernel<<<grid, RM_THREADS, smem, st>>>(local, mask, mask_mode, n, ld, mask_ld, window, eps, tile, out, out_ld,
-                                                        invalid);
+    rolling_mean_kernel<<<grid, RM_THREADS, smem, st>>>(local, mask, mask_mode, n, ld, mask_ld, window, eps, tile, groups,
+                                                        vec_ok, out, out_ld, invalid);
     return cudaGetLastError();
 }
 

@@ -8,8 +8,8 @@ namespace cb200 {
 
 constexpr int64_t MUNC_MAX_WINDOW = 8192;  // tile + window cells must fit one CTA's shared memory
 
-int munc_rolling_tile(int64_t window);
-size_t munc_rolling_smem(int tile, int64_t window);
+int munc_rolling_groups(int64_t window);
+size_t munc_rolling_smem(int groups);
 
 // out[j][i] = max(eps, mean of the unmasked local[j][k] over the centred window of i) (float32),
 // the cell itself where the whole window is masked.  mask_mode: 0 none, 1 per interval [n],
