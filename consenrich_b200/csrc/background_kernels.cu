@@ -13,8 +13,10 @@
 //
 // A block row is 12 doubles: D (symmetric: d00 d01 d11), U (coupling to the NEXT row; the coupling to
 // the previous row is the previous row's U transposed), B (2 unknowns x 2 right-hand sides), pad.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "background_kernels.cuh"
 
@@ -138,7 +140,7 @@ __device__ __forceinline__ Row get_row(const Rows &rw, int64_t i, BackgroundStat
 
 // new row j of the next level from rows 2j-1, 2j, 2j+1 of this one
 __device__ __forceinline__ void reduce_row(const Rows &in, int64_t rows_in, int64_t j, int64_t stride_unknowns,
-                                           double *__restrict__ out, BackgroundStatus *st) {
+                                           double *out, BackgroundStatus *st) {
     const int64_t i = 2 * j;
     Row c = get_row(in, i, st);
     Row o = c;
@@ -184,9 +186,8 @@ __device__ __forceinline__ void reduce_row(const Rows &in, int64_t rows_in, int6
 
 // X: [rows][4] doubles = x[r][c] of each block row.  Odd rows of this level from their even neighbours
 // (already solved: they are the rows of the next level), even rows copied from the next level.
-__device__ __forceinline__ void backsub_row(const Rows &lvl, int64_t rows, const double *__restrict__ x_next,
-                                            int64_t i, double *__restrict__ x_out, BackgroundStatus *st,
-                                            int64_t stride_unknowns) {
+__device__ __forceinline__ void backsub_row(const Rows &lvl, int64_t rows, const double *x_next, int64_t i,
+                                            double *x_out, BackgroundStatus *st, int64_t stride_unknowns) {
     double2 *o = reinterpret_cast<double2 *>(x_out + i * 4);
     if ((i & 1) == 0) {
         const double2 *s = reinterpret_cast<const double2 *>(x_next + (i >> 1) * 4);
@@ -260,9 +261,8 @@ __device__ __forceinline__ Inv2 inv_spd2s(const RowS &r, int64_t unknown0, Backg
     return inv_spd2(t, unknown0, st);
 }
 
-__global__ void __launch_bounds__(1024) small_system_kernel(const Rows in, int64_t rows, int64_t stride_unknowns,
-                                                            double *__restrict__ x_out, BackgroundStatus *st) {
-    extern __shared__ __align__(16) double sm[];
+__device__ __forceinline__ void small_system(const Rows &in, int64_t rows, int64_t stride_unknowns, double *x_out,
+                                             BackgroundStatus *st, double *sm) {
     const int R = (int)rows;
     for (int i = threadIdx.x; i < R; i += blockDim.x) {
         const Row r = get_row(in, i, st);
@@ -365,6 +365,49 @@ __global__ void __launch_bounds__(1024) small_system_kernel(const Rows in, int64
         double2 *o = reinterpret_cast<double2 *>(x_out + (int64_t)i * 4);
         o[0] = make_double2(r.b00, r.b01);
         o[1] = make_double2(r.b10, r.b11);
+    }
+}
+
+__global__ void __launch_bounds__(1024) small_system_kernel(const Rows in, int64_t rows, int64_t stride_unknowns,
+                                                            double *x_out, BackgroundStatus *st) {
+    extern __shared__ __align__(16) double sm_small[];
+    small_system(in, rows, stride_unknowns, x_out, st, sm_small);
+}
+
+// The middle of the recursion (levels with at most BG_MID_ROWS block rows) in ONE cooperative launch:
+// every level is a grid-stride loop followed by a grid barrier, CTA 0 runs the shared-memory tail in
+// between.  Replaces a dozen launches of a few CTAs each, which cost latency, not traffic.
+struct MidArgs {
+    const double *lvl[BG_MAX_LEVELS];  // stored rows of a level (nullptr: level 0, formed on the fly)
+    double *x[BG_MAX_LEVELS];
+    int64_t rows[BG_MAX_LEVELS], stride[BG_MAX_LEVELS];
+    Level0 l0;
+    int first, small;  // levels [first, small): reduced / substituted here; level `small`: the tail
+};
+
+__global__ void __launch_bounds__(BG_MID_THREADS) mid_system_kernel(const MidArgs a, BackgroundStatus *st) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) double sm_mid[];
+    cg::grid_group grid = cg::this_grid();
+    const int64_t me = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, all = (int64_t)gridDim.x * blockDim.x;
+    auto level = [&](int l) {
+        Rows r{};
+        r.stored = a.lvl[l];
+        r.l0 = a.l0;
+        return r;
+    };
+    for (int l = a.first; l < a.small; ++l) {
+        const Rows in = level(l);
+        for (int64_t j = me; j < a.rows[l + 1]; j += all)
+            reduce_row(in, a.rows[l], j, a.stride[l], const_cast<double *>(a.lvl[l + 1]), st);
+        grid.sync();
+    }
+    if (blockIdx.x == 0) small_system(level(a.small), a.rows[a.small], a.stride[a.small], a.x[a.small], st, sm_mid);
+    grid.sync();
+    for (int l = a.small - 1; l >= a.first; --l) {
+        const Rows in = level(l);
+        for (int64_t i = me; i < a.rows[l]; i += all) backsub_row(in, a.rows[l], a.x[l + 1], i, a.x[l], st, a.stride[l]);
+        grid.sync();
     }
 }
 
@@ -533,20 +576,60 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
     const BackgroundStatus init{INT64_MAX, 0.0};
     cudaError_t e = cudaMemcpyAsync(status, &init, sizeof(init), cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) return e;
-    // per device, so set on every call (a few hundred nanoseconds)
-    e = cudaFuncSetAttribute(small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMALL_ROWS * SROW * 8);
-    if (e != cudaSuccess) return e;
+    // the levels: [0, first_mid) one launch each way; [first_mid, first_small) + the shared-memory tail in
+    // one cooperative launch when the device takes it (co-resident CTAs), else launch by launch
+    int first_mid = 0;
+    while (first_mid < first_small && rows[first_mid] > BG_MID_ROWS) ++first_mid;
+    const size_t tail_smem = (size_t)rows[first_small] * SROW * 8;
     int count = 0;
     const int T = 256;
-    for (int l = 0; l < first_small; ++l) {
+    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    if (first_mid < first_small && !getenv("CB200_BG_NO_COOP") && cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
+        cudaFuncSetAttribute(mid_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tail_smem) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mid_system_kernel, BG_MID_THREADS, tail_smem) == cudaSuccess &&
+        per_sm > 0) {
+        coop = 1;
+    } else {
+        coop = 0;
+        first_mid = first_small;
+    }
+    for (int l = 0; l < first_mid; ++l) {
         reduce_kernel<<<(unsigned)((rows[l + 1] + T - 1) / T), T, 0, st>>>(level(l), rows[l], rows[l + 1], stride[l],
                                                                          lvl[l + 1], status);
         ++count;
     }
-    small_system_kernel<<<1, 1024, (size_t)rows[first_small] * SROW * 8, st>>>(level(first_small), rows[first_small],
-                                                                             stride[first_small], x[first_small], status);
-    ++count;
-    for (int l = first_small - 1; l >= 0; --l) {
+    if (coop) {
+        MidArgs ma{};
+        for (int l = 0; l <= first_small; ++l) {
+            ma.lvl[l] = lvl[l];
+            ma.x[l] = x[l];
+            ma.rows[l] = rows[l];
+            ma.stride[l] = stride[l];
+        }
+        ma.l0 = Level0{w, rhs, n, lam, lam_first};
+        ma.first = first_mid;
+        ma.small = first_small;
+        int64_t want = (rows[first_mid] + BG_MID_THREADS - 1) / BG_MID_THREADS;
+        const int64_t cap = (int64_t)sms * per_sm;
+        if (want > cap) want = cap;
+        if (want < 1) want = 1;
+        BackgroundStatus *stp = status;
+        void *kargs[] = {&ma, &stp};
+        e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(mid_system_kernel), dim3((unsigned)want), dim3(BG_MID_THREADS),
+                                        kargs, tail_smem, st);
+        if (e != cudaSuccess) return e;
+        ++count;
+    } else {
+        // per device, so set on every call (a few hundred nanoseconds)
+        e = cudaFuncSetAttribute(small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMALL_ROWS * SROW * 8);
+        if (e != cudaSuccess) return e;
+        small_system_kernel<<<1, 1024, tail_smem, st>>>(level(first_small), rows[first_small], stride[first_small],
+                                                       x[first_small], status);
+        ++count;
+    }
+    for (int l = first_mid - 1; l >= 0; --l) {
         backsub_kernel<<<(unsigned)((rows[l] + T - 1) / T), T, 0, st>>>(level(l), rows[l], x[l + 1], x[l], status, stride[l]);
         ++count;
     }

@@ -9,6 +9,8 @@ namespace cb200 {
 constexpr int BG_MAX_LEVELS = 32;
 constexpr int BG_SMALL_ROWS = 1024;  // from this many block rows on, one CTA finishes the recursion in shared memory
 constexpr int BG_SUM_BLOCKS = 1024;
+constexpr int BG_MID_ROWS = 65536;    // levels up to this many block rows share one cooperative launch
+constexpr int BG_MID_THREADS = 256;
 
 // outcome of a solve: first unknown whose pivot fell below the reference's floor (1e-12), or
 // INT64_MAX; the reference fails such a solve (cconsenrich.pyx:1090-1095)
