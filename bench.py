@@ -347,6 +347,17 @@ def background_block(torch, dev, stream, ctx, reps, host, m, n, ld, no_cpu):
                                                       _p(smooth_out), ld, _p(flag)))
 
     ms_smooth = timed(smooth)
+    # cFinalizeMuncEBTrack over one track: local, prior, count floor in, posterior variance out
+    fl, fp, fc, fo = (torch.rand(n, device=dev) + 0.01 for _ in range(4))
+    fres = _lib.MuncFinalizeResult()
+
+    def finalize():
+        _lib.check(L.cb200_munc_finalize_eb(ctx.handle, _p(fl), _p(fp), _p(fc), n, 37.0, 12.0, 1e-3, 5.0, 1, _p(fo),
+                                            C.byref(fres)))
+
+    ms_finalize = timed(finalize)  # includes the status read-back (one stream synchronisation per call)
+    blk["munc_finalize_ms_device"] = ms_finalize
+    blk["munc_finalize_frac_of_peak"] = 16.0 * n / (ms_finalize * 1e-3) / 1e9 / peak
     smooth_bytes = 8.0 * m * n + 1.0 * n
     blk["munc_smooth_ms_device"] = ms_smooth
     blk["munc_smooth_frac_of_peak"] = smooth_bytes / (ms_smooth * 1e-3) / 1e9 / peak

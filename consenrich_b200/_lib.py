@@ -57,6 +57,13 @@ class EcmResult(C.Structure):
     ]
 
 
+class MuncFinalizeResult(C.Structure):
+    """cb200_munc_finalize_result"""
+    _fields_ = [(k, C.c_int64) for k in ("support_count", "count_floor_finite", "count_floor_added",
+                                         "count_floor_missing", "invalid_local", "invalid_prior",
+                                         "invalid_count_floor")]
+
+
 _vp, _i64, _i32, _dbl, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t
 _pm, _po, _pr = C.POINTER(Model), C.POINTER(EcmOpts), C.POINTER(EcmResult)
 
@@ -112,6 +119,10 @@ SIGNATURES = {
                                                    _vp]),
     "cb200_host_munc_smooth_local_evidence": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i64, _i64, _dbl, _vp,
                                                         C.POINTER(_i32)]),
+    "cb200_munc_finalize_eb": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _vp,
+                                         C.POINTER(MuncFinalizeResult)]),
+    "cb200_host_munc_finalize_eb": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _vp,
+                                              C.POINTER(MuncFinalizeResult)]),
 }
 
 _lib = None

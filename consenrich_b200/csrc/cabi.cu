@@ -1308,4 +1308,74 @@ int cb200_host_munc_smooth_local_evidence(cb200_ctx *c, const float *local, cons
     return CB200_OK;
 }
 
+int cb200_munc_finalize_eb(cb200_ctx *c, const float *local, const float *prior, const float *count_floor, int64_t n,
+                           double nu_local, double nu_prior, double variance_floor, double variance_cap, int32_t use_eb,
+                           float *out, cb200_munc_finalize_result *result) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !result) return fail(CB200_ERR_INVALID, "NULL argument");
+    // messages of cconsenrich.pyx:5468-5482
+    if (!(variance_floor > 0.0) || !std::isfinite(variance_floor))
+        return fail(CB200_ERR_INVALID, "varianceFloor must be positive and finite");
+    if (variance_cap < variance_floor || !std::isfinite(variance_cap))
+        return fail(CB200_ERR_INVALID, "varianceCap must be finite and at least varianceFloor");
+    if (use_eb) {
+        if (!prior && n > 0) return fail(CB200_ERR_INVALID, "priorVarianceTrack is required for MUNC EB finalization");
+        if (!std::isfinite(nu_local) || nu_local <= 0.0) return fail(CB200_ERR_INVALID, "nuLocal must be positive and finite");
+        if (!std::isfinite(nu_prior) || nu_prior <= 0.0) return fail(CB200_ERR_INVALID, "nuPrior must be positive and finite");
+        if (!std::isfinite(nu_local + nu_prior) || nu_local + nu_prior <= 0.0)
+            return fail(CB200_ERR_INVALID, "posterior sample size must be positive and finite");
+    }
+    if (n < 0) return fail(CB200_ERR_INVALID, "n must be nonnegative");
+    memset(result, 0, sizeof(*result));
+    result->invalid_local = result->invalid_prior = result->invalid_count_floor = -1;
+    if (n == 0) return CB200_OK;
+    if (!local || !out) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(ensure(c, c->bg_status, sizeof(MuncFinalizeStatus) > sizeof(BackgroundStatus) ? sizeof(MuncFinalizeStatus)
+                                                                                       : sizeof(BackgroundStatus)));
+    MuncFinalizeStatus *dst = static_cast<MuncFinalizeStatus *>(c->bg_status.p);
+    {
+        Span sp(c, FAM_MUNC);
+        CU_TRY(launch_munc_finalize_eb(local, use_eb ? prior : nullptr, count_floor, n, nu_local, nu_prior, variance_floor,
+                                       variance_cap, use_eb ? 1 : 0, out, dst, c->stream));
+    }
+    c->launches += 1;
+    MuncFinalizeStatus h;
+    CU_TRY(cudaMemcpyAsync(&h, dst, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    result->support_count = h.support;
+    result->count_floor_finite = h.cfloor_finite;
+    result->count_floor_added = h.cfloor_added;
+    result->count_floor_missing = h.cfloor_missing;
+    // the reference stops at the first offending interval; at equal index local is tested before prior
+    // before the count floor
+    const int64_t il = h.invalid_local, ip = h.invalid_prior, ic = h.invalid_cfloor;
+    if (il != INT64_MAX && il <= ip && il <= ic) result->invalid_local = il;
+    else if (ip != INT64_MAX && ip <= ic) result->invalid_prior = ip;
+    else if (ic != INT64_MAX) result->invalid_count_floor = ic;
+    return CB200_OK;
+}
+
+int cb200_host_munc_finalize_eb(cb200_ctx *c, const float *local, const float *prior, const float *count_floor, int64_t n,
+                                double nu_local, double nu_prior, double variance_floor, double variance_cap,
+                                int32_t use_eb, float *out, cb200_munc_finalize_result *result) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !result) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (n > 0 && (!local || !out)) return fail(CB200_ERR_INVALID, "NULL argument");
+    const float *dl = nullptr, *dp = nullptr, *dc = nullptr;
+    if (n > 0) {
+        CB_TRY(upload_vec(c, c->lam, local, n, true, &dl));
+        CB_TRY(upload_vec(c, c->kap, prior, n, use_eb && prior != nullptr, &dp));
+        CB_TRY(upload_vec(c, c->qs, count_floor, n, count_floor != nullptr, &dc));
+        CB_TRY(ensure(c, c->D, (size_t)n * 4));
+    }
+    if (use_eb && !prior && n > 0) return fail(CB200_ERR_INVALID, "priorVarianceTrack is required for MUNC EB finalization");
+    CB_TRY(cb200_munc_finalize_eb(c, dl, dp, dc, n, nu_local, nu_prior, variance_floor, variance_cap, use_eb,
+                                  static_cast<float *>(c->D.p), result));
+    if (n > 0) {
+        CB_TRY(d2h(c, out, c->D.p, (size_t)n * 4));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return CB200_OK;
+}
+
 }  // extern "C"

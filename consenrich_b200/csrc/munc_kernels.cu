@@ -197,7 +197,86 @@ rolling_mean_kernel(const float *__restrict__ local, const uint8_t *__restrict__
     }
 }
 
+// ---- cFinalizeMuncEBTrack (cconsenrich.pyx:5372-5440): per-interval shrinkage of the local variance
+// towards the prior, clipping, count floor.  Elementwise; separately rounded float64 products, sums and
+// quotient, so the float32 output is bit-identical to the reference's loop.
+constexpr int FIN_THREADS = 256;
+
+__device__ __forceinline__ double clip_var(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_eb_kernel(const float *__restrict__ local, const float *__restrict__ prior, const float *__restrict__ cfloor,
+                   int64_t n, double nu_local, double nu_prior, double post, double vfloor, double vcap, int use_eb,
+                   float *__restrict__ out, MuncFinalizeStatus *st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int support = 0, cf_finite = 0, cf_added = 0, cf_missing = 0;
+    if (i < n) {
+        double lv = (double)local[i];
+        bool ok = true;
+        if (!isfinite(lv) || lv <= 0.0) {
+            atomicMin(reinterpret_cast<long long *>(&st->invalid_local), (long long)i);
+            ok = false;
+        }
+        if (ok) {
+            support = lv > vfloor;
+            lv = clip_var(lv, vfloor, vcap);
+            double ov = lv;
+            if (use_eb) {
+                double pv = (double)prior[i];
+                if (!isfinite(pv) || pv <= 0.0) {
+                    atomicMin(reinterpret_cast<long long *>(&st->invalid_prior), (long long)i);
+                    ok = false;
+                } else {
+                    pv = clip_var(pv, vfloor, vcap);
+                    ov = __ddiv_rn(__dadd_rn(__dmul_rn(nu_local, lv), __dmul_rn(nu_prior, pv)), post);
+                }
+            }
+            if (ok) {
+                ov = clip_var(ov, vfloor, vcap);
+                if (cfloor) {
+                    const double cv = (double)cfloor[i];
+                    if (cv == cv) {  // NaN = no count floor for this interval
+                        if (!isfinite(cv) || cv < 0.0) {
+                            atomicMin(reinterpret_cast<long long *>(&st->invalid_cfloor), (long long)i);
+                            ok = false;
+                        } else {
+                            cf_finite = 1;
+                            ov = __dadd_rn(ov, cv);
+                            cf_added = cv > 0.0;
+                            ov = clip_var(ov, vfloor, vcap);
+                        }
+                    } else {
+                        cf_missing = 1;
+                    }
+                }
+                if (ok) out[i] = (float)ov;
+            }
+            if (!ok) support = cf_finite = cf_added = cf_missing = 0;
+        }
+    }
+    // counters: warp ballots, one atomic per warp and counter that has anything to add
+    const unsigned b0 = __ballot_sync(0xffffffffu, support), b1 = __ballot_sync(0xffffffffu, cf_finite);
+    const unsigned b2 = __ballot_sync(0xffffffffu, cf_added), b3 = __ballot_sync(0xffffffffu, cf_missing);
+    if ((threadIdx.x & 31) == 0) {
+        if (b0) atomicAdd(reinterpret_cast<unsigned long long *>(&st->support), (unsigned long long)__popc(b0));
+        if (b1) atomicAdd(reinterpret_cast<unsigned long long *>(&st->cfloor_finite), (unsigned long long)__popc(b1));
+        if (b2) atomicAdd(reinterpret_cast<unsigned long long *>(&st->cfloor_added), (unsigned long long)__popc(b2));
+        if (b3) atomicAdd(reinterpret_cast<unsigned long long *>(&st->cfloor_missing), (unsigned long long)__popc(b3));
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_munc_finalize_eb(const float *local, const float *prior, const float *cfloor, int64_t n,
+                                    double nu_local, double nu_prior, double vfloor, double vcap, int use_eb, float *out,
+                                    MuncFinalizeStatus *status, cudaStream_t st) {
+    const MuncFinalizeStatus init{0, 0, 0, 0, INT64_MAX, INT64_MAX, INT64_MAX};
+    cudaError_t e = cudaMemcpyAsync(status, &init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess || n <= 0) return e;
+    finalize_eb_kernel<<<(unsigned)((n + FIN_THREADS - 1) / FIN_THREADS), FIN_THREADS, 0, st>>>(
+        local, prior, cfloor, n, nu_local, nu_prior, nu_local + nu_prior, vfloor, vcap, use_eb, out, status);
+    return cudaGetLastError();
+}
 
 // rounds of 8 cells per thread: a CTA covers RM_THREADS * 8 * groups cells, at least 1.5 windows
 // (+ alignment slack), so that a cell is loaded at most about three times even for the widest window

@@ -19,4 +19,18 @@ cudaError_t launch_munc_rolling_mean(const float *local, const uint8_t *mask, in
                                      int64_t ld, int64_t mask_ld, int64_t window, double eps, float *out, int64_t out_ld,
                                      int *invalid, cudaStream_t st);
 
+// outcome of launch_munc_finalize_eb (device memory): counters of cconsenrich.pyx:5355-5362; the invalid_*
+// fields hold the first offending interval of each kind or INT64_MAX
+struct MuncFinalizeStatus {
+    int64_t support, cfloor_finite, cfloor_added, cfloor_missing;
+    int64_t invalid_local, invalid_prior, invalid_cfloor;
+};
+
+// out[i] = clip(clip((nu_local clip(local[i]) + nu_prior clip(prior[i])) / (nu_local + nu_prior)) + cfloor[i])
+// (prior == nullptr / use_eb == 0: no shrinkage; cfloor == nullptr: no count floor; NaN in cfloor: none for
+// that interval).  Counters are valid only when no invalid_* index was reported.
+cudaError_t launch_munc_finalize_eb(const float *local, const float *prior, const float *cfloor, int64_t n,
+                                    double nu_local, double nu_prior, double vfloor, double vcap, int use_eb, float *out,
+                                    MuncFinalizeStatus *status, cudaStream_t st);
+
 }  // namespace cb200

@@ -35,7 +35,7 @@ _HOT_PATH = ("cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPas
 # the callers on the other side of the ECM inside an outer pass
 _BACKGROUND = ("cbackgroundWeightedStats", "cbackgroundWeightedStatsWithSupport", "csolveZeroCenteredBackground")
 # dense kernels of the observation-noise stage that produces matrixMunc
-_MUNC = ("cMuncSmoothDenseLocalEvidence",)
+_MUNC = ("cMuncSmoothDenseLocalEvidence", "cFinalizeMuncEBTrack")
 
 
 def _f32(x) -> float:
@@ -581,6 +581,60 @@ def cMuncSmoothDenseLocalEvidence(localEvidence, windowIntervals, excludeMask=No
     if invalid.value:
         raise ValueError("active local evidence cells must be positive and finite")
     return out
+
+
+def cFinalizeMuncEBTrack(localVarianceTrack, priorVarianceTrack=None, countFloor=None, nuLocal=0.0, nuPrior=0.0,
+                         varianceFloor=1.0e-12, varianceCap=3.4028234663852886e38, useEB=True):
+    """Shrinkage of the local variance track towards its prior, clipping and count floor; signature,
+    checks, error texts and diagnostics of cconsenrich.pyx:5445-5545."""
+    local = np.ascontiguousarray(localVarianceTrack, dtype=np.float32).reshape(-1)
+    n = local.shape[0]
+    nu_l, nu_p = _f32(nuLocal), _f32(nuPrior)            # C float arguments (pyx:5449-5452)
+    vfloor, vcap = _f32(varianceFloor), _f32(varianceCap)
+    use_eb = bool(useEB)
+    if vfloor <= 0.0 or not np.isfinite(vfloor):
+        raise ValueError("varianceFloor must be positive and finite")
+    if vcap < vfloor or not np.isfinite(vcap):
+        raise ValueError("varianceCap must be finite and at least varianceFloor")
+    prior = cfloor = None
+    if use_eb:
+        if priorVarianceTrack is None:
+            raise ValueError("priorVarianceTrack is required for MUNC EB finalization")
+        if not np.isfinite(nu_l) or nu_l <= 0.0:
+            raise ValueError("nuLocal must be positive and finite")
+        if not np.isfinite(nu_p) or nu_p <= 0.0:
+            raise ValueError("nuPrior must be positive and finite")
+        if not np.isfinite(nu_l + nu_p) or nu_l + nu_p <= 0.0:
+            raise ValueError("posterior sample size must be positive and finite")
+        prior = np.ascontiguousarray(priorVarianceTrack, dtype=np.float32).reshape(-1)
+        if prior.shape[0] != n:
+            raise ValueError("priorVarianceTrack length must match localVarianceTrack length")
+    if countFloor is not None:
+        cfloor = np.ascontiguousarray(countFloor, dtype=np.float32).reshape(-1)
+        if cfloor.shape[0] != n:
+            raise ValueError("countFloor length must match localVarianceTrack length")
+    out = np.empty(n, np.float32)
+    res = _lib.MuncFinalizeResult()
+    res.invalid_local = res.invalid_prior = res.invalid_count_floor = -1
+    if n > 0:
+        ctx = _ctx()
+        _lib.check(ctx._lib.cb200_host_munc_finalize_eb(ctx.handle, _ptr(local), _ptr(prior), _ptr(cfloor), n, nu_l, nu_p,
+                                                        vfloor, vcap, int(use_eb), _ptr(out), C.byref(res)))
+    if res.invalid_local >= 0:
+        raise ValueError(f"localVarianceTrack must contain finite positive values at index {res.invalid_local}")
+    if res.invalid_prior >= 0:
+        raise ValueError(f"priorVarianceTrack must contain finite positive values at index {res.invalid_prior}")
+    if res.invalid_count_floor >= 0:
+        raise ValueError(f"countFloor must be nonnegative where finite at index {res.invalid_count_floor}")
+    return out, {
+        "supportCount": int(res.support_count),
+        "supportFraction": (float(res.support_count) / float(n)) if n > 0 else 0.0,
+        "countFloorFiniteCount": int(res.count_floor_finite),
+        "countFloorAddedCount": int(res.count_floor_added),
+        "countFloorMissingCount": int(res.count_floor_missing),
+        "finalShrinkagePairCount": n if use_eb else 0,
+        "finalShrinkagePairFraction": 1.0 if use_eb and n > 0 else 0.0,
+    }
 
 
 _saved: dict = {}

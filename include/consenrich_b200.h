@@ -18,6 +18,7 @@
  *   cbackgroundWeightedStats[WithSupport] :9675-9724    cb200_host_background_stats
  *   csolveZeroCenteredBackground :944-1096              cb200_host_background_solve
  *   cMuncSmoothDenseLocalEvidence :5547-5740            cb200_host_munc_smooth_local_evidence
+ *   cFinalizeMuncEBTrack :5372-5545                     cb200_host_munc_finalize_eb
  *
  * Conventions
  *   - plain C: pointers, sizes, POD structs; no torch / numpy types.
@@ -283,6 +284,33 @@ CB200_API int cb200_munc_smooth_local_evidence(cb200_ctx *ctx, const float *loca
 CB200_API int cb200_host_munc_smooth_local_evidence(cb200_ctx *ctx, const float *local, const unsigned char *mask,
                                           int32_t mask_mode, int64_t m, int64_t n, int64_t window, double eps,
                                           float *out, int32_t *invalid);
+
+/* cFinalizeMuncEBTrack (cconsenrich.pyx:5372-5545): per interval, the local variance clipped to
+ * [variance_floor, variance_cap], shrunk towards the clipped prior with weights nu_local : nu_prior when
+ * use_eb is set, clipped, plus the count floor where that is not NaN, clipped again; float32 in and out,
+ * float64 arithmetic with the reference's rounding sequence (bit-identical).  prior / count_floor may be
+ * NULL (no shrinkage / no count floor).  The outcome mirrors the reference's diagnostics; an invalid_*
+ * field >= 0 names the first interval for which the reference raises ValueError (the one with the
+ * smallest index wins; local before prior before count floor at equal index), and the counters and `out`
+ * are then meaningless. */
+typedef struct cb200_munc_finalize_result {
+    int64_t support_count;        /* intervals with local variance above the floor */
+    int64_t count_floor_finite;
+    int64_t count_floor_added;
+    int64_t count_floor_missing;
+    int64_t invalid_local;        /* -1 or the first interval whose local variance is not positive and finite */
+    int64_t invalid_prior;
+    int64_t invalid_count_floor;  /* finite-or-inf but negative / infinite */
+} cb200_munc_finalize_result;
+/* device arrays; `result` is HOST memory (the call synchronises the stream to fill it) */
+CB200_API int cb200_munc_finalize_eb(cb200_ctx *ctx, const float *local, const float *prior, const float *count_floor,
+                           int64_t n, double nu_local, double nu_prior, double variance_floor, double variance_cap,
+                           int32_t use_eb, float *out, cb200_munc_finalize_result *result);
+/* host arrays */
+CB200_API int cb200_host_munc_finalize_eb(cb200_ctx *ctx, const float *local, const float *prior,
+                                const float *count_floor, int64_t n, double nu_local, double nu_prior,
+                                double variance_floor, double variance_cap, int32_t use_eb, float *out,
+                                cb200_munc_finalize_result *result);
 
 #ifdef __cplusplus
 }

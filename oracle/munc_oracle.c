@@ -68,3 +68,44 @@ void munc_smooth_rows(const float *local, const uint8_t *mask, int mode, int64_t
         }
     }
 }
+
+/* _finalizeMuncEBTrackLoop, cconsenrich.pyx:5365-5440.  counters: [support, cfFinite, cfAdded, cfMissing];
+ * invalid: [local, prior, countFloor] (first offending index of the kind that stopped the loop, others -1) */
+void munc_finalize_eb(const float *local, const float *prior, const float *cfloor, float *out, int64_t n,
+                      double nu_local, double nu_prior, double post, double vfloor, double vcap, int use_eb,
+                      int64_t *counters, int64_t *invalid) {
+    counters[0] = counters[1] = counters[2] = counters[3] = 0;
+    invalid[0] = invalid[1] = invalid[2] = -1;
+    for (int64_t i = 0; i < n; ++i) {
+        double lv = (double)local[i], ov;
+        if (!isfinite(lv) || lv <= 0.0) { invalid[0] = i; return; }
+        if (lv > vfloor) counters[0] += 1;
+        if (lv < vfloor) lv = vfloor;
+        else if (lv > vcap) lv = vcap;
+        if (use_eb) {
+            double pv = (double)prior[i];
+            if (!isfinite(pv) || pv <= 0.0) { invalid[1] = i; return; }
+            if (pv < vfloor) pv = vfloor;
+            else if (pv > vcap) pv = vcap;
+            ov = ((nu_local * lv) + (nu_prior * pv)) / post;
+        } else {
+            ov = lv;
+        }
+        if (ov < vfloor) ov = vfloor;
+        else if (ov > vcap) ov = vcap;
+        if (cfloor) {
+            const double cv = (double)cfloor[i];
+            if (cv == cv) {
+                if (!isfinite(cv) || cv < 0.0) { invalid[2] = i; return; }
+                counters[1] += 1;
+                ov += cv;
+                if (cv > 0.0) counters[2] += 1;
+                if (ov < vfloor) ov = vfloor;
+                else if (ov > vcap) ov = vcap;
+            } else {
+                counters[3] += 1;
+            }
+        }
+        out[i] = (float)ov;
+    }
+}

@@ -20,6 +20,7 @@ and (``oracle/background_oracle.c``) the background-track functions on the other
 and (``oracle/munc_oracle.c``) the dense kernels of the observation-noise stage:
 
 * ``cMuncSmoothDenseLocalEvidence``         <- cconsenrich.pyx:5547-5740
+* ``cFinalizeMuncEBTrack``                  <- cconsenrich.pyx:5365-5545
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this module.  The product (``consenrich_b200``) never does.
@@ -634,3 +635,58 @@ def cMuncSmoothDenseLocalEvidence(localEvidence, windowIntervals, excludeMask=No
     out = np.empty((m, n), np.float32)
     lib.munc_smooth_rows(local.ctypes.data, mp, mode, m, n, window, eps_d, out.ctypes.data)
     return out
+
+
+def cFinalizeMuncEBTrack(localVarianceTrack, priorVarianceTrack=None, countFloor=None, nuLocal=0.0, nuPrior=0.0,
+                         varianceFloor=1.0e-12, varianceCap=3.4028234663852886e38, useEB=True):
+    """cconsenrich.pyx:5445-5545 (checks, error texts and diagnostics included)."""
+    f32 = lambda v: float(np.float32(v))
+    local = np.ascontiguousarray(localVarianceTrack, dtype=np.float32).reshape(-1)
+    n = local.shape[0]
+    nu_l, nu_p, vfloor, vcap = f32(nuLocal), f32(nuPrior), f32(varianceFloor), f32(varianceCap)
+    post = nu_l + nu_p
+    use_eb = bool(useEB)
+    if vfloor <= 0.0 or not np.isfinite(vfloor):
+        raise ValueError("varianceFloor must be positive and finite")
+    if vcap < vfloor or not np.isfinite(vcap):
+        raise ValueError("varianceCap must be finite and at least varianceFloor")
+    prior = cfloor = None
+    if use_eb:
+        if priorVarianceTrack is None:
+            raise ValueError("priorVarianceTrack is required for MUNC EB finalization")
+        if not np.isfinite(nu_l) or nu_l <= 0.0:
+            raise ValueError("nuLocal must be positive and finite")
+        if not np.isfinite(nu_p) or nu_p <= 0.0:
+            raise ValueError("nuPrior must be positive and finite")
+        if not np.isfinite(post) or post <= 0.0:
+            raise ValueError("posterior sample size must be positive and finite")
+        prior = np.ascontiguousarray(priorVarianceTrack, dtype=np.float32).reshape(-1)
+        if prior.shape[0] != n:
+            raise ValueError("priorVarianceTrack length must match localVarianceTrack length")
+    if countFloor is not None:
+        cfloor = np.ascontiguousarray(countFloor, dtype=np.float32).reshape(-1)
+        if cfloor.shape[0] != n:
+            raise ValueError("countFloor length must match localVarianceTrack length")
+    out = np.empty(n, np.float32)
+    counters, invalid = np.zeros(4, np.int64), np.full(3, -1, np.int64)
+    lib = _L()
+    lib.munc_finalize_eb.restype = None
+    lib.munc_finalize_eb.argtypes = [C.c_void_p] * 4 + [C.c_int64] + [C.c_double] * 5 + [C.c_int, C.c_void_p, C.c_void_p]
+    lib.munc_finalize_eb(local.ctypes.data, prior.ctypes.data if prior is not None else None,
+                         cfloor.ctypes.data if cfloor is not None else None, out.ctypes.data, n, nu_l, nu_p, post,
+                         vfloor, vcap, int(use_eb), counters.ctypes.data, invalid.ctypes.data)
+    if invalid[0] >= 0:
+        raise ValueError(f"localVarianceTrack must contain finite positive values at index {int(invalid[0])}")
+    if invalid[1] >= 0:
+        raise ValueError(f"priorVarianceTrack must contain finite positive values at index {int(invalid[1])}")
+    if invalid[2] >= 0:
+        raise ValueError(f"countFloor must be nonnegative where finite at index {int(invalid[2])}")
+    return out, {
+        "supportCount": int(counters[0]),
+        "supportFraction": (float(counters[0]) / float(n)) if n > 0 else 0.0,
+        "countFloorFiniteCount": int(counters[1]),
+        "countFloorAddedCount": int(counters[2]),
+        "countFloorMissingCount": int(counters[3]),
+        "finalShrinkagePairCount": n if use_eb else 0,
+        "finalShrinkagePairFraction": 1.0 if use_eb and n > 0 else 0.0,
+    }

@@ -58,6 +58,36 @@ def main():
             out[f"smooth/{name}/mask"] = mk
         out[f"smooth/{name}/window"], out[f"smooth/{name}/eps"] = np.int64(w), np.float64(eps)
         out[f"smooth/{name}/out"] = res
+    # cFinalizeMuncEBTrack: the reference's own known-answer case (tests/test_core.py:1481-1522) + seeded ones
+    fin = [("ref_case", np.asarray([0.05, 0.20, 4.00, 0.001], np.float32), np.asarray([0.35, 0.60, 10.00, 0.02], np.float32),
+            np.asarray([np.nan, 0.25, 2.00, 0.00], np.float32), dict(nuLocal=2.0, nuPrior=3.0, useEB=True,
+                                                                       varianceFloor=0.01, varianceCap=5.0)),
+           ("ref_case_no_eb", np.asarray([0.05, 0.20, 4.00, 0.001], np.float32), None,
+            np.asarray([np.nan, 0.25, 2.00, 0.00], np.float32), dict(useEB=False, varianceFloor=0.01, varianceCap=5.0))]
+    for name, n, with_cf, opts in (("n1", 1, True, dict(nuLocal=4.0, nuPrior=9.5, varianceFloor=1e-4, varianceCap=50.0)),
+                                   ("n5000", 5000, True, dict(nuLocal=37.0, nuPrior=12.25, varianceFloor=1e-3,
+                                                              varianceCap=3.0)),
+                                   ("n3001_defaults", 3001, False, dict(nuLocal=6.0, nuPrior=2.0))):
+        loc = local_evidence(rng, 1, n)[0]
+        pri = (loc * rng.uniform(0.3, 3.0, n)).astype(np.float32)
+        cf = None
+        if with_cf:
+            cf = rng.uniform(0.0, 0.5, n).astype(np.float32)
+            cf[rng.random(n) < 0.2] = np.nan
+            cf[rng.random(n) < 0.2] = 0.0
+        fin.append((name, loc, pri, cf, opts))
+    for name, loc, pri, cf, opts in fin:
+        res, diag = ref.cFinalizeMuncEBTrack(loc, priorVarianceTrack=pri, countFloor=cf, **opts)
+        out[f"finalize/{name}/local"] = loc
+        if pri is not None:
+            out[f"finalize/{name}/prior"] = pri
+        if cf is not None:
+            out[f"finalize/{name}/countFloor"] = cf
+        for k_, v_ in opts.items():
+            out[f"finalize/{name}/opt_{k_}"] = np.asarray(v_)
+        out[f"finalize/{name}/out"] = res
+        for k_, v_ in diag.items():
+            out[f"finalize/{name}/diag_{k_}"] = np.asarray(v_)
     path = os.path.join(HERE, "munc_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

@@ -88,3 +88,63 @@ def test_errors_follow_the_reference(cb):
     with pytest.raises(NotImplementedError, match="not supported on the device"):
         cb.cMuncSmoothDenseLocalEvidence(le, 8193)
     assert cb.cMuncSmoothDenseLocalEvidence(np.zeros((0, 5), np.float32), 3).shape == (0, 5)
+
+
+# ---- cFinalizeMuncEBTrack: elementwise, float64 arithmetic with the reference's rounding sequence ----
+def test_finalize_matches_golden_vectors_bitwise(cb):
+    from test_munc_oracle import check_finalize, run_finalize
+    for name, c in golden_cases("finalize").items():
+        check_finalize(run_finalize(cb, c), c)
+
+
+def test_finalize_matches_oracle_bitwise_on_fresh_seeds(cb, oracle):
+    rng = np.random.default_rng(31)
+    for n in (1, 31, 257, 70001, 2_344_705):
+        loc = np.exp(rng.normal(-2.0, 2.0, n)).astype(np.float32)
+        pri = np.exp(rng.normal(-2.0, 1.0, n)).astype(np.float32)
+        cf = rng.uniform(0.0, 0.3, n).astype(np.float32)
+        cf[rng.random(n) < 0.3] = np.nan
+        cf[rng.random(n) < 0.2] = 0.0
+        for kw in (dict(nuLocal=37.0, nuPrior=12.25, varianceFloor=1e-3, varianceCap=3.0),
+                   dict(nuLocal=5.0, nuPrior=1e-3), dict(useEB=False, varianceFloor=0.02, varianceCap=0.5)):
+            for use_cf in (True, False):
+                args = (loc, None if kw.get("useEB") is False else pri, cf if use_cf else None)
+                want = oracle.cFinalizeMuncEBTrack(*args, **kw)
+                got = cb.cFinalizeMuncEBTrack(*args, **kw)
+                np.testing.assert_array_equal(got[0], want[0])
+                assert got[1] == want[1]
+    out, diag = cb.cFinalizeMuncEBTrack(np.zeros(0, np.float32), np.zeros(0, np.float32), nuLocal=1.0, nuPrior=1.0)
+    assert out.shape == (0,) and diag["supportFraction"] == 0.0 and diag["finalShrinkagePairFraction"] == 0.0
+
+
+def test_finalize_errors_follow_the_reference(cb, oracle):
+    rng = np.random.default_rng(4)
+    n = 100_000
+    loc = rng.uniform(1e-3, 2.0, n).astype(np.float32)
+    pri = rng.uniform(1e-3, 2.0, n).astype(np.float32)
+    cf = rng.uniform(0, 1, n).astype(np.float32)
+    kw = dict(nuLocal=3.0, nuPrior=2.0, varianceFloor=1e-3, varianceCap=5.0)
+    bad_l, bad_p, bad_c = loc.copy(), pri.copy(), cf.copy()
+    bad_l[[90_000, 77_777]] = [np.nan, -1.0]
+    bad_p[[300, 50_000]] = np.inf
+    bad_c[[300, 301]] = [-1.0, np.inf]
+    cases = [(bad_l, pri, cf), (loc, bad_p, cf), (loc, pri, bad_c), (bad_l, bad_p, bad_c), (loc, bad_p, bad_c)]
+    for args in cases:
+        msgs = []
+        for mod in (oracle, cb):
+            with pytest.raises(ValueError) as e:
+                mod.cFinalizeMuncEBTrack(*args, **kw)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1], msgs
+    for bad_kw, text in ((dict(varianceFloor=0.0), "varianceFloor must be positive and finite"),
+                         (dict(varianceCap=1e-4), "varianceCap must be finite and at least varianceFloor"),
+                         (dict(nuLocal=0.0), "nuLocal must be positive and finite"),
+                         (dict(nuPrior=float("inf")), "nuPrior must be positive and finite")):
+        with pytest.raises(ValueError, match=text):
+            cb.cFinalizeMuncEBTrack(loc, pri, cf, **{**kw, **bad_kw})
+    with pytest.raises(ValueError, match="priorVarianceTrack is required"):
+        cb.cFinalizeMuncEBTrack(loc, None, cf, **kw)
+    with pytest.raises(ValueError, match="priorVarianceTrack length must match"):
+        cb.cFinalizeMuncEBTrack(loc, pri[:-1], cf, **kw)
+    with pytest.raises(ValueError, match="countFloor length must match"):
+        cb.cFinalizeMuncEBTrack(loc, pri, cf[:-1], **kw)

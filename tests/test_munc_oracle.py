@@ -9,13 +9,27 @@ import pytest
 from conftest import GOLDEN_DIR
 
 
-def golden_cases():
+def golden_cases(kind="smooth"):
     z = np.load(os.path.join(GOLDEN_DIR, "munc_golden.npz"), allow_pickle=False)
     cases = {}
     for key in z.files:
-        _, name, field = key.split("/")
-        cases.setdefault(name, {})[field] = z[key]
+        k, name, field = key.split("/")
+        if k == kind:
+            cases.setdefault(name, {})[field] = z[key]
     return cases
+
+
+def run_finalize(mod, c):
+    opts = {k[4:]: (v.item() if v.ndim == 0 else v) for k, v in c.items() if k.startswith("opt_")}
+    return mod.cFinalizeMuncEBTrack(c["local"], priorVarianceTrack=c.get("prior"), countFloor=c.get("countFloor"), **opts)
+
+
+def check_finalize(got, c, exact=True):
+    out, diag = got
+    np.testing.assert_array_equal(out, c["out"])
+    for k, v in c.items():
+        if k.startswith("diag_"):
+            assert diag[k[5:]] == v.item(), k
 
 
 def run_case(mod, c):
@@ -60,3 +74,48 @@ def test_oracle_matches_reference_build_on_fresh_seeds(oracle):
             mod.cMuncSmoothDenseLocalEvidence(le, 3, excludeMask=np.zeros(39, np.uint8))
         with pytest.raises(ValueError, match="excludeMask shape must match localEvidence shape"):
             mod.cMuncSmoothDenseLocalEvidence(le, 3, excludeMask=np.zeros((3, 40), np.uint8))
+
+
+def test_oracle_matches_golden_finalize_vectors_bitwise(oracle):
+    cases = golden_cases("finalize")
+    assert len(cases) >= 5
+    for name, c in cases.items():
+        check_finalize(run_finalize(oracle, c), c)
+    out, diag = run_finalize(oracle, cases["ref_case"])  # the reference's own expectation
+    np.testing.assert_allclose(out, np.asarray([0.23, 0.69, 5.0, 0.016], np.float32), rtol=1e-6, atol=1e-6)
+    assert (diag["supportCount"], diag["countFloorFiniteCount"], diag["countFloorAddedCount"],
+            diag["countFloorMissingCount"], diag["finalShrinkagePairCount"]) == (3, 3, 2, 1, 4)
+
+
+def test_oracle_finalize_matches_reference_build_errors_included(oracle):
+    ref = oracle.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    rng = np.random.default_rng(12)
+    n = 4000
+    loc = rng.uniform(1e-4, 3.0, n).astype(np.float32)
+    pri = rng.uniform(1e-4, 3.0, n).astype(np.float32)
+    cf = rng.uniform(0, 1, n).astype(np.float32)
+    cf[::7] = np.nan
+    kw = dict(nuLocal=11.0, nuPrior=5.5, varianceFloor=1e-3, varianceCap=2.5)
+    a, b = ref.cFinalizeMuncEBTrack(loc, pri, cf, **kw), oracle.cFinalizeMuncEBTrack(loc, pri, cf, **kw)
+    np.testing.assert_array_equal(a[0], b[0])
+    assert a[1] == b[1]
+    bad_l, bad_p, bad_c = loc.copy(), pri.copy(), cf.copy()
+    bad_l[900] = 0.0
+    bad_p[300] = np.inf
+    bad_c[300] = -1.0
+    for args in ((bad_l, pri, cf), (loc, bad_p, cf), (loc, pri, bad_c), (bad_l, bad_p, bad_c), (loc, bad_p, bad_c)):
+        msgs = []
+        for mod in (ref, oracle):
+            with pytest.raises(ValueError) as e:
+                mod.cFinalizeMuncEBTrack(*args, **kw)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1], msgs
+    for bad_kw in (dict(varianceFloor=0.0), dict(varianceCap=1e-4), dict(nuLocal=0.0), dict(nuPrior=float("nan"))):
+        msgs = []
+        for mod in (ref, oracle):
+            with pytest.raises(ValueError) as e:
+                mod.cFinalizeMuncEBTrack(loc, pri, cf, **{**kw, **bad_kw})
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1]
