@@ -269,7 +269,7 @@ def pinned_empty(shape, dtype):
     return np.frombuffer(buf, dtype=dt, count=count).reshape(shape)
 
 
-_default_ctx: dict = {}
+_default_ctx = threading.local()  # per thread: a context (stream + device arena) serves one call at a time
 
 
 def current_device() -> int:
@@ -279,12 +279,16 @@ def current_device() -> int:
 
 
 def default_context(device: int | None = None) -> Context:
-    """Process-wide context per device, used by the drop-in functions; the device defaults to the one
-    the calling thread has selected (cudaGetDevice), i.e. the rank's GPU under torchrun."""
+    """The calling thread's context for a device, used by the drop-in functions; the device defaults to
+    the one the thread has selected (cudaGetDevice), i.e. the rank's GPU under torchrun.  Contexts are per
+    thread because the reference's functions are re-entrant and its MUNC stage calls them from a thread
+    pool (consenrich.py:9055): each thread gets its own stream and device buffers."""
     if device is None:
         device = current_device()
-    ctx = _default_ctx.get(device)
+    table = getattr(_default_ctx, "by_device", None)
+    if table is None:
+        table = _default_ctx.by_device = {}
+    ctx = table.get(device)
     if ctx is None:
-        ctx = Context(device)
-        _default_ctx[device] = ctx
+        ctx = table[device] = Context(device)
     return ctx

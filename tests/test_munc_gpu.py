@@ -148,3 +148,24 @@ def test_finalize_errors_follow_the_reference(cb, oracle):
         cb.cFinalizeMuncEBTrack(loc, pri[:-1], cf, **kw)
     with pytest.raises(ValueError, match="countFloor length must match"):
         cb.cFinalizeMuncEBTrack(loc, pri, cf[:-1], **kw)
+
+
+def test_concurrent_calls_from_a_thread_pool(cb, oracle):
+    """The reference's MUNC stage calls these functions from a ThreadPool (consenrich.py:9055); every
+    thread gets its own context, so concurrent calls of different shapes do not disturb one another."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(9)
+    jobs = []
+    for t in range(8):
+        m, n, w = 2 + t % 3, 20_000 + 7_001 * t, 5 + 3 * t
+        le = local_evidence(rng, m, n)
+        jobs.append((le, w, oracle.cMuncSmoothDenseLocalEvidence(le, w)))
+
+    def work(job):
+        le, w, want = job
+        for _ in range(5):
+            assert_one_ulp(cb.cMuncSmoothDenseLocalEvidence(le, w), want, f"thread job window {w}")
+        return True
+
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        assert all(pool.map(work, jobs))
