@@ -13,7 +13,8 @@ There is no CPU implementation: importing works anywhere, calling requires the b
 and a CUDA device, and fails loudly otherwise.
 """
 from . import _lib  # noqa: F401
-from .native import (cFinalizeMuncEBTrack, cMuncSmoothDenseLocalEvidence, cbackgroundWeightedStats,  # noqa: F401
+from .native import (cFinalizeMuncEBTrack, cMuncObservationMomentSeedPass,  # noqa: F401
+                     cMuncSmoothDenseLocalEvidence, cbackgroundWeightedStats,
                      cbackgroundWeightedStatsWithSupport,
                      cbackwardPass, cbackwardPassLevel, cfixedBackgroundECM, cfixedBackgroundECMLevel,
                      cforwardPass, cforwardPassLevel, csolveZeroCenteredBackground, install, sweep, uninstall)

@@ -64,6 +64,17 @@ class MuncFinalizeResult(C.Structure):
                                          "invalid_count_floor")]
 
 
+class MuncSeedArgs(C.Structure):
+    """cb200_munc_seed_args"""
+    _fields_ = ([(k, C.c_void_p) for k in ("data", "munc", "state_mean", "state_var", "background", "g_var",
+                                           "count_floor", "omega_in", "rho_in", "active", "moment", "rho_out",
+                                           "omega_raw", "omega_out", "local", "variance")]
+                + [(k, C.c_int64) for k in ("m", "n", "ld", "active_ld")]
+                + [(k, C.c_int32) for k in ("active_mode", "use_weights", "student_t", "update_weights")]
+                + [(k, C.c_double) for k in ("pad", "student_t_df", "d_omega", "omega_min", "omega_max",
+                                             "variance_floor", "variance_cap")])
+
+
 _vp, _i64, _i32, _dbl, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_size_t
 _pm, _po, _pr = C.POINTER(Model), C.POINTER(EcmOpts), C.POINTER(EcmResult)
 
@@ -123,6 +134,8 @@ SIGNATURES = {
                                          C.POINTER(MuncFinalizeResult)]),
     "cb200_host_munc_finalize_eb": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _dbl, _dbl, _dbl, _dbl, _i32, _vp,
                                               C.POINTER(MuncFinalizeResult)]),
+    "cb200_munc_seed_pass": (C.c_int, [_vp, C.POINTER(MuncSeedArgs), _vp]),
+    "cb200_host_munc_seed_pass": (C.c_int, [_vp, C.POINTER(MuncSeedArgs), C.POINTER(_i32)]),
 }
 
 _lib = None

@@ -93,6 +93,7 @@ struct cb200_ctx {
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, smo, smo2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     DevBuf bg_ws, bg_w, bg_rhs, bg_out, bg_status;  // background solve: workspace, operands, outcome
     DevBuf mask;  // MUNC stage: exclusion mask
+    DevBuf seed_mat[6], seed_vec[7];  // MUNC seed pass: count floor, rho in, 4 outputs; 5 input + 2 output vectors
     double *sums_host = nullptr;  // pinned double[2]
     // timing
     bool timing = false;
@@ -478,7 +479,10 @@ void cb200_ctx_destroy(cb200_ctx *c) {
     DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->xf2, &c->Pf2,
                       &c->Qf2, &c->smo, &c->smo2, &c->D,
                       &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard,
-                      &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status, &c->mask};
+                      &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status, &c->mask,
+                      &c->seed_mat[0], &c->seed_mat[1], &c->seed_mat[2], &c->seed_mat[3], &c->seed_mat[4], &c->seed_mat[5],
+                      &c->seed_vec[0], &c->seed_vec[1], &c->seed_vec[2], &c->seed_vec[3], &c->seed_vec[4], &c->seed_vec[5],
+                      &c->seed_vec[6]};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->sums_host) cudaFreeHost(c->sums_host);
@@ -1374,6 +1378,130 @@ int cb200_host_munc_finalize_eb(cb200_ctx *c, const float *local, const float *p
     if (n > 0) {
         CB_TRY(d2h(c, out, c->D.p, (size_t)n * 4));
         CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    return CB200_OK;
+}
+
+static int check_munc_seed_args(const cb200_munc_seed_args *a) {
+    // messages of cconsenrich.pyx:5112-5132
+    if (a->m < 0 || a->n < 0) return fail(CB200_ERR_INVALID, "bad matrix shape");
+    if (a->pad < 0.0 || !std::isfinite(a->pad)) return fail(CB200_ERR_INVALID, "pad must be finite and nonnegative");
+    if (!(a->variance_floor > 0.0) || !std::isfinite(a->variance_floor))
+        return fail(CB200_ERR_INVALID, "varianceFloor must be positive and finite");
+    if (!std::isfinite(a->variance_cap) || a->variance_cap < a->variance_floor)
+        return fail(CB200_ERR_INVALID, "varianceCap must be greater than or equal to varianceFloor");
+    if (a->use_weights && a->student_t &&
+        (a->student_t_df <= 0.0 || a->d_omega <= 0.0 || !std::isfinite(a->student_t_df) || !std::isfinite(a->d_omega) ||
+         a->omega_min <= 0.0 || a->omega_max < a->omega_min || !std::isfinite(a->omega_min) ||
+         !std::isfinite(a->omega_max)))
+        return fail(CB200_ERR_INVALID, "seed weight parameters are invalid");
+    if (a->active_mode < 0 || a->active_mode > 2) return fail(CB200_ERR_INVALID, "activeMask must be one- or two-dimensional");
+    return CB200_OK;
+}
+
+static MuncSeedArgs to_seed_args(const cb200_munc_seed_args *a) {
+    MuncSeedArgs k{};
+    k.data = a->data; k.munc = a->munc; k.state_mean = a->state_mean; k.state_var = a->state_var;
+    k.background = a->background; k.g_var = a->g_var; k.count_floor = a->count_floor; k.omega_in = a->omega_in;
+    k.rho_in = a->rho_in; k.active = a->active_mode ? a->active : nullptr;
+    k.moment = a->moment; k.rho_out = a->rho_out; k.local = a->local; k.variance = a->variance;
+    k.omega_raw = a->omega_raw; k.omega_out = a->omega_out;
+    k.m = a->m; k.n = a->n; k.ld = a->ld; k.active_ld = a->active_ld;
+    k.active_mode = a->active_mode; k.use_weights = a->use_weights; k.student_t = a->student_t;
+    k.update_weights = a->update_weights;
+    k.pad = a->pad; k.d_s = a->student_t_df; k.d_omega = a->d_omega; k.omega_min = a->omega_min;
+    k.omega_max = a->omega_max; k.var_floor = a->variance_floor; k.var_cap = a->variance_cap;
+    return k;
+}
+
+int cb200_munc_seed_pass(cb200_ctx *c, const cb200_munc_seed_args *a, int32_t *invalid) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !a || !invalid) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_munc_seed_args(a));
+    if (a->m > 0 && a->n > 0) {
+        if (!a->data || !a->munc || !a->state_mean || !a->state_var || !a->moment || !a->rho_out || !a->omega_raw ||
+            !a->omega_out || !a->local || !a->variance || (a->active_mode && !a->active))
+            return fail(CB200_ERR_INVALID, "NULL argument");
+        if (a->ld < a->n) return fail(CB200_ERR_INVALID, "bad matrix shape");
+    }
+    Span sp(c, FAM_MUNC);
+    CU_TRY(launch_munc_seed_pass(to_seed_args(a), reinterpret_cast<int *>(invalid), c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_host_munc_seed_pass(cb200_ctx *c, const cb200_munc_seed_args *a, int32_t *invalid) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !a || !invalid) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_munc_seed_args(a));
+    *invalid = 0;
+    const int64_t m = a->m, n = a->n;
+    if (n <= 0) return CB200_OK;
+    if (!a->state_mean || !a->state_var || !a->omega_raw || !a->omega_out) return fail(CB200_ERR_INVALID, "NULL argument");
+    if (m > 0 && (!a->data || !a->munc || !a->moment || !a->rho_out || !a->local || !a->variance ||
+                  (a->active_mode && !a->active)))
+        return fail(CB200_ERR_INVALID, "NULL argument");
+    cb200_munc_seed_args d = *a;
+    int64_t ld = round_up(n, 32), t = 0;
+    d.ld = ld;
+    if (m > 0) {
+        CB_TRY(upload_tracks(c, c->data, a->data, m, n, &t));
+        CB_TRY(upload_tracks(c, c->munc, a->munc, m, n, &t));
+        d.data = static_cast<const float *>(c->data.p);
+        d.munc = static_cast<const float *>(c->munc.p);
+        if (a->count_floor) {
+            CB_TRY(upload_tracks(c, c->seed_mat[0], a->count_floor, m, n, &t));
+            d.count_floor = static_cast<const float *>(c->seed_mat[0].p);
+        }
+        if (a->rho_in) {
+            CB_TRY(upload_tracks(c, c->seed_mat[1], a->rho_in, m, n, &t));
+            d.rho_in = static_cast<const float *>(c->seed_mat[1].p);
+        }
+        float **outs[4] = {&d.moment, &d.rho_out, &d.local, &d.variance};
+        for (int i = 0; i < 4; ++i) {
+            CB_TRY(ensure(c, c->seed_mat[2 + i], (size_t)m * (size_t)ld * 4));
+            *outs[i] = static_cast<float *>(c->seed_mat[2 + i].p);
+        }
+        if (a->active_mode) {
+            const size_t bytes = a->active_mode == 1 ? (size_t)n : (size_t)m * (size_t)n;
+            CB_TRY(ensure(c, c->mask, bytes));
+            CB_TRY(h2d(c, c->mask.p, a->active, bytes));
+            d.active = static_cast<const unsigned char *>(c->mask.p);
+            d.active_ld = n;
+        }
+    }
+    const float *vin[5] = {a->state_mean, a->state_var, a->background, a->g_var, a->omega_in};
+    const float **vdst[5] = {&d.state_mean, &d.state_var, &d.background, &d.g_var, &d.omega_in};
+    for (int i = 0; i < 5; ++i) CB_TRY(upload_vec(c, c->seed_vec[i], vin[i], n, vin[i] != nullptr, vdst[i]));
+    CB_TRY(ensure(c, c->seed_vec[5], (size_t)n * 4));
+    CB_TRY(ensure(c, c->seed_vec[6], (size_t)n * 4));
+    d.omega_raw = static_cast<float *>(c->seed_vec[5].p);
+    d.omega_out = static_cast<float *>(c->seed_vec[6].p);
+    CB_TRY(ensure(c, c->bg_status, sizeof(MuncFinalizeStatus)));
+    int32_t *dflag = reinterpret_cast<int32_t *>(c->bg_status.p);
+    if (m > 0) {
+        CB_TRY(cb200_munc_seed_pass(c, &d, dflag));
+        CB_TRY(d2h(c, invalid, dflag, sizeof(int32_t)));
+        float *houts[4] = {a->moment, a->rho_out, a->local, a->variance};
+        float *douts[4] = {d.moment, d.rho_out, d.local, d.variance};
+        for (int i = 0; i < 4; ++i)
+            CU_TRY(cudaMemcpy2DAsync(houts[i], (size_t)n * 4, douts[i], (size_t)ld * 4, (size_t)n * 4, (size_t)m,
+                                     cudaMemcpyDeviceToHost, c->stream));
+        CB_TRY(d2h(c, a->omega_raw, d.omega_raw, (size_t)n * 4));
+        CB_TRY(d2h(c, a->omega_out, d.omega_out, (size_t)n * 4));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    } else {
+        // no tracks: the reference still writes the per-interval weights (1 without an active cell)
+        for (int64_t k = 0; k < n; ++k) {
+            const bool weighted = a->use_weights && a->student_t;
+            double raw = 1.0, om = 1.0;
+            if (weighted && !a->update_weights) {
+                raw = a->omega_in ? (double)a->omega_in[k] : 1.0;
+                om = raw < a->omega_min ? a->omega_min : (raw > a->omega_max ? a->omega_max : raw);
+            }
+            a->omega_raw[k] = (float)raw;
+            a->omega_out[k] = (float)om;
+        }
     }
     return CB200_OK;
 }

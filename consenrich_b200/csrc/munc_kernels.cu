@@ -265,7 +265,158 @@ finalize_eb_kernel(const float *__restrict__ local, const float *__restrict__ pr
     }
 }
 
+// ---- cMuncObservationMomentSeedPass (cconsenrich.pyx:4843-5040) ----------------------------------
+// One thread per interval, the tracks in order (the Student-t weight of an interval averages over its
+// active tracks in that order); every product, sum and quotient rounded separately, as the reference's
+// C does, so all six outputs are bit-identical.
+constexpr int SEED_THREADS = 256;
+
+__device__ __forceinline__ bool seed_active(const MuncSeedArgs &a, int64_t j, int64_t k) {
+    if (a.active_mode == 0) return true;
+    return (a.active_mode == 1 ? a.active[k] : a.active[j * a.active_ld + k]) != 0;
+}
+
+// clip the local variance and the total (local + count floor) the way pyx:5003-5015 does
+__device__ __forceinline__ void seed_clip(double &lv, double &tv, double cv, double vfloor, double vcap) {
+    if (lv < vfloor) {
+        lv = vfloor;
+        tv = __dadd_rn(lv, cv);
+    }
+    if (tv > vcap) {
+        tv = vcap;
+        lv = __dsub_rn(tv, cv);
+        if (lv < vfloor) {
+            lv = vfloor;
+            tv = __dadd_rn(lv, cv);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SEED_THREADS) seed_pass_kernel(const MuncSeedArgs a, int *__restrict__ invalid) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    const bool weighted = a.use_weights && a.student_t;
+    const double state = (double)a.state_mean[k];
+    double mvb = (double)a.state_var[k];
+    const double bg = a.background ? (double)a.background[k] : 0.0;
+    const double gv = a.g_var ? (double)a.g_var[k] : 0.0;
+    bool bad_k = !isfinite(state) || !isfinite(mvb) || !isfinite(bg) || !isfinite(gv);
+    if (a.g_var) mvb = __dadd_rn(mvb, gv);
+    if (mvb < 0.0) mvb = 0.0;
+    double omega_in = 1.0;
+    if (weighted && a.omega_in) {
+        omega_in = (double)a.omega_in[k];
+        if (!isfinite(omega_in) || omega_in <= 0.0) bad_k = true;
+    }
+    bool bad = false;
+    double omega_raw = 1.0, omega = 1.0;
+    if (weighted) {
+        if (a.update_weights) {
+            double dbar = 0.0;
+            int64_t active = 0;
+            for (int64_t j = 0; j < a.m; ++j) {
+                const int64_t idx = j * a.ld + k;
+                if (!seed_active(a, j, k)) {
+                    a.moment[idx] = 0.0f;
+                    a.rho_out[idx] = 1.0f;
+                    continue;
+                }
+                const double d = (double)a.data[idx];
+                const double mu = __dadd_rn((double)a.munc[idx], a.pad);
+                if (bad_k || !isfinite(d) || !isfinite(mu) || mu <= 0.0) bad = true;
+                double base = mu;
+                if (base < a.var_floor) base = a.var_floor;
+                const double res = __dsub_rn(__dsub_rn(d, bg), state);
+                const double mom = __dadd_rn(__dmul_rn(res, res), mvb);
+                const double rho = __ddiv_rn(__dadd_rn(a.d_s, 1.0),
+                                             __dadd_rn(a.d_s, __ddiv_rn(__dmul_rn(omega_in, mom), base)));
+                a.moment[idx] = (float)mom;
+                a.rho_out[idx] = (float)rho;
+                dbar = __dadd_rn(dbar, __ddiv_rn(mom, base));
+                active += 1;
+            }
+            if (active > 0) {
+                dbar = __ddiv_rn(dbar, (double)active);
+                omega_raw = __ddiv_rn(__dadd_rn(a.d_omega, 1.0), __dadd_rn(a.d_omega, dbar));
+                omega = omega_raw < a.omega_min ? a.omega_min : (omega_raw > a.omega_max ? a.omega_max : omega_raw);
+            }
+        } else {
+            omega_raw = omega_in;
+            omega = omega_raw < a.omega_min ? a.omega_min : (omega_raw > a.omega_max ? a.omega_max : omega_raw);
+            for (int64_t j = 0; j < a.m; ++j) {
+                const int64_t idx = j * a.ld + k;
+                if (!seed_active(a, j, k)) {
+                    a.moment[idx] = 0.0f;
+                    a.rho_out[idx] = 1.0f;
+                    continue;
+                }
+                const double d = (double)a.data[idx];
+                const double mu = __dadd_rn((double)a.munc[idx], a.pad);
+                const double rho = a.rho_in ? (double)a.rho_in[idx] : 1.0;
+                if (bad_k || !isfinite(d) || !isfinite(mu) || mu <= 0.0 || !isfinite(rho) || rho <= 0.0) bad = true;
+                const double res = __dsub_rn(__dsub_rn(d, bg), state);
+                a.moment[idx] = (float)__dadd_rn(__dmul_rn(res, res), mvb);
+                a.rho_out[idx] = (float)rho;
+            }
+        }
+        a.omega_raw[k] = (float)omega_raw;
+        a.omega_out[k] = (float)omega;
+    } else {
+        a.omega_raw[k] = 1.0f;
+        a.omega_out[k] = 1.0f;
+    }
+    for (int64_t j = 0; j < a.m; ++j) {
+        const int64_t idx = j * a.ld + k;
+        const double cv = a.count_floor ? (double)a.count_floor[idx] : 0.0;
+        double lv, tv;
+        if (seed_active(a, j, k)) {
+            if (a.count_floor && (!isfinite(cv) || cv < 0.0)) bad = true;
+            double mom, rho = 1.0;
+            if (!weighted) {
+                const double d = (double)a.data[idx];
+                const double mu = __dadd_rn((double)a.munc[idx], a.pad);
+                if (bad_k || !isfinite(d) || !isfinite(mu) || mu <= 0.0) bad = true;
+                const double res = __dsub_rn(__dsub_rn(d, bg), state);
+                mom = __dadd_rn(__dmul_rn(res, res), mvb);
+                a.moment[idx] = (float)mom;
+                a.rho_out[idx] = 1.0f;
+                lv = __dsub_rn(__dsub_rn(mom, a.pad), cv);
+            } else {
+                mom = (double)a.moment[idx];  // the float32 values just stored, as the reference re-reads them
+                rho = (double)a.rho_out[idx];
+                lv = __dsub_rn(__dsub_rn(__dmul_rn(__dmul_rn(omega, rho), mom), a.pad), cv);
+            }
+            tv = __dadd_rn(lv, cv);
+            seed_clip(lv, tv, cv, a.var_floor, a.var_cap);
+        } else {
+            lv = __dsub_rn((double)a.munc[idx], cv);
+            if (lv < a.var_floor) lv = a.var_floor;
+            tv = __dadd_rn(lv, cv);
+            if (tv > a.var_cap) {
+                tv = a.var_cap;
+                lv = __dsub_rn(tv, cv);
+                if (lv < a.var_floor) {
+                    lv = a.var_floor;
+                    tv = __dadd_rn(lv, cv);
+                }
+            }
+            a.moment[idx] = 0.0f;
+            a.rho_out[idx] = 1.0f;
+        }
+        a.local[idx] = (float)lv;
+        a.variance[idx] = (float)tv;
+    }
+    if (bad) atomicOr(invalid, 1);
+}
+
 }  // namespace
+
+cudaError_t launch_munc_seed_pass(const MuncSeedArgs &a, int *invalid, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(invalid, 0, sizeof(int), st);
+    if (e != cudaSuccess || a.n <= 0 || a.m <= 0) return e;
+    seed_pass_kernel<<<(unsigned)((a.n + SEED_THREADS - 1) / SEED_THREADS), SEED_THREADS, 0, st>>>(a, invalid);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_munc_finalize_eb(const float *local, const float *prior, const float *cfloor, int64_t n,
                                     double nu_local, double nu_prior, double vfloor, double vcap, int use_eb, float *out,

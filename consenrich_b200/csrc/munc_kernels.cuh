@@ -33,4 +33,24 @@ cudaError_t launch_munc_finalize_eb(const float *local, const float *prior, cons
                                     double nu_local, double nu_prior, double vfloor, double vcap, int use_eb, float *out,
                                     MuncFinalizeStatus *status, cudaStream_t st);
 
+// cMuncObservationMomentSeedPass (cconsenrich.pyx:4843-5040): arguments of one launch.  Matrices are
+// float32 [m][ld]; per-interval vectors float32 [n]; nullptr = absent.
+struct MuncSeedArgs {
+    const float *data, *munc;          // [m][ld]
+    const float *state_mean, *state_var;  // [n]
+    const float *background, *g_var;   // [n] or nullptr
+    const float *count_floor;          // [m][ld] or nullptr
+    const float *omega_in;             // [n] or nullptr
+    const float *rho_in;               // [m][ld] or nullptr (all ones)
+    const uint8_t *active;             // nullptr, [n] (active_mode 1) or [m][active_ld] (2); nonzero = active
+    float *moment, *rho_out, *local, *variance;  // [m][ld]
+    float *omega_raw, *omega_out;      // [n]
+    int64_t m, n, ld, active_ld;
+    int32_t active_mode, use_weights, student_t, update_weights;
+    double pad, d_s, d_omega, omega_min, omega_max, var_floor, var_cap;
+};
+
+// *invalid (device int) is set when an active cell fails the reference's input check (pyx:4767-4840)
+cudaError_t launch_munc_seed_pass(const MuncSeedArgs &a, int *invalid, cudaStream_t st);
+
 }  // namespace cb200

@@ -35,7 +35,7 @@ _HOT_PATH = ("cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPas
 # the callers on the other side of the ECM inside an outer pass
 _BACKGROUND = ("cbackgroundWeightedStats", "cbackgroundWeightedStatsWithSupport", "csolveZeroCenteredBackground")
 # dense kernels of the observation-noise stage that produces matrixMunc
-_MUNC = ("cMuncSmoothDenseLocalEvidence", "cFinalizeMuncEBTrack")
+_MUNC = ("cMuncSmoothDenseLocalEvidence", "cFinalizeMuncEBTrack", "cMuncObservationMomentSeedPass")
 
 
 def _f32(x) -> float:
@@ -581,6 +581,116 @@ def cMuncSmoothDenseLocalEvidence(localEvidence, windowIntervals, excludeMask=No
     if invalid.value:
         raise ValueError("active local evidence cells must be positive and finite")
     return out
+
+
+def _seed_pass_arguments(matrixData, matrixMunc, stateMean, stateVariance, background, gVariance, countFloor, omegaIn,
+                         rhoIn, pad, studentTdf, useSeedWeights, updateWeights, omegaMin, omegaMax, varianceFloor,
+                         varianceCap, enabled, studentT, dOmega, activeMask):
+    """Argument handling of cMuncObservationMomentSeedPass (cconsenrich.pyx:5042-5198): coercions, checks in
+    the reference's order with its error texts.  Returns the arrays (kept alive by the caller) and scalars."""
+    data = np.asarray(matrixData)
+    munc = np.asarray(matrixMunc)
+    if data.dtype != np.float32 or data.ndim != 2 or munc.dtype != np.float32 or munc.ndim != 2:
+        raise ValueError("matrixData and matrixMunc must be two-dimensional float32 arrays")
+    data, munc = np.ascontiguousarray(data), np.ascontiguousarray(munc)
+    mean, var = np.asarray(stateMean), np.asarray(stateVariance)
+    if mean.dtype != np.float32 or mean.ndim != 1 or var.dtype != np.float32 or var.ndim != 1:
+        raise ValueError("stateMean and stateVariance must be one-dimensional float32 arrays")
+    mean, var = np.ascontiguousarray(mean), np.ascontiguousarray(var)
+    m, n = data.shape
+    use_weights = bool(enabled) and bool(useSeedWeights)
+    student_t, update = bool(studentT), bool(updateWeights)
+    pad_d, df, d_om = _f32(pad), _f32(studentTdf), _f32(dOmega)
+    om_lo, om_hi, vfloor, vcap = _f32(omegaMin), _f32(omegaMax), _f32(varianceFloor), _f32(varianceCap)
+    if munc.shape[0] != m or munc.shape[1] != n:
+        raise ValueError("matrixMunc shape must match matrixData shape")
+    if mean.shape[0] != n:
+        raise ValueError("stateMean length must match interval count")
+    if var.shape[0] != n:
+        raise ValueError("stateVariance length must match interval count")
+    if pad_d < 0.0 or not np.isfinite(pad_d):
+        raise ValueError("pad must be finite and nonnegative")
+    if vfloor <= 0.0 or not np.isfinite(vfloor):
+        raise ValueError("varianceFloor must be positive and finite")
+    if not np.isfinite(vcap) or vcap < vfloor:
+        raise ValueError("varianceCap must be greater than or equal to varianceFloor")
+    if use_weights and student_t and (df <= 0.0 or d_om <= 0.0 or not np.isfinite(df) or not np.isfinite(d_om)
+                                      or om_lo <= 0.0 or om_hi < om_lo or not np.isfinite(om_lo)
+                                      or not np.isfinite(om_hi)):
+        raise ValueError("seed weight parameters are invalid")
+    arrays = dict(data=data, munc=munc, state_mean=mean, state_var=var)
+    if background is not None:
+        arrays["background"] = np.ascontiguousarray(background, dtype=np.float32).reshape(-1)
+        if arrays["background"].shape[0] != n:
+            raise ValueError("background length must match interval count")
+    if gVariance is not None:
+        arrays["g_var"] = np.ascontiguousarray(gVariance, dtype=np.float32).reshape(-1)
+        if arrays["g_var"].shape[0] != n:
+            raise ValueError("gVariance length must match interval count")
+    if countFloor is not None:
+        cf = np.ascontiguousarray(countFloor, dtype=np.float32)
+        if cf.ndim != 2 or cf.shape[0] != m or cf.shape[1] != n:
+            raise ValueError("countFloor shape must match matrixData shape")
+        arrays["count_floor"] = cf
+    if omegaIn is not None:
+        om = np.ascontiguousarray(omegaIn, dtype=np.float32)
+        if om.ndim != 1:
+            raise ValueError("omegaIn must be one-dimensional")
+        if om.shape[0] != n:
+            raise ValueError("omegaIn length must match interval count")
+        arrays["omega_in"] = om
+    if rhoIn is not None:
+        rho = np.ascontiguousarray(rhoIn, dtype=np.float32)
+        if rho.ndim != 2 or rho.shape[0] != m or rho.shape[1] != n:
+            raise ValueError("rhoIn shape must match matrixData shape")
+        arrays["rho_in"] = rho
+    mode = 0
+    if activeMask is not None:
+        act = np.ascontiguousarray(activeMask, dtype=np.uint8)
+        if act.ndim == 1:
+            if act.shape[0] != n:
+                raise ValueError("activeMask length must match interval count")
+            mode = 1
+        elif act.ndim == 2:
+            if act.shape[0] != m or act.shape[1] != n:
+                raise ValueError("activeMask shape must match matrixData shape")
+            mode = 2
+        else:
+            raise ValueError("activeMask must be one- or two-dimensional")
+        arrays["active"] = act
+    scalars = dict(m=m, n=n, ld=n, active_ld=n, active_mode=mode, use_weights=int(use_weights), student_t=int(student_t),
+                   update_weights=int(update), pad=pad_d, student_t_df=df, d_omega=d_om, omega_min=om_lo,
+                   omega_max=om_hi, variance_floor=vfloor, variance_cap=vcap)
+    return arrays, scalars
+
+
+def cMuncObservationMomentSeedPass(matrixData, matrixMunc, stateMean, stateVariance, background=None, gVariance=None,
+                                   countFloor=None, omegaIn=None, rhoIn=None, pad=1.0e-4, studentTdf=8.0,
+                                   useSeedWeights=True, updateWeights=True, omegaMin=0.01, omegaMax=100.0,
+                                   varianceFloor=1.0e-12, varianceCap=3.4028234663852886e38, enabled=True,
+                                   studentT=True, dOmega=8.0, activeMask=None):
+    """Moment / Student-t weight / local-variance pass of the MUNC seed smoother; signature, checks, error
+    texts and the six returned arrays of cconsenrich.pyx:5042-5345."""
+    arrays, scalars = _seed_pass_arguments(matrixData, matrixMunc, stateMean, stateVariance, background, gVariance,
+                                           countFloor, omegaIn, rhoIn, pad, studentTdf, useSeedWeights, updateWeights,
+                                           omegaMin, omegaMax, varianceFloor, varianceCap, enabled, studentT, dOmega,
+                                           activeMask)
+    m, n = scalars["m"], scalars["n"]
+    big = _lib.pinned_empty if m * n * 4 >= (1 << 20) else np.empty
+    outs = dict(moment=big((m, n), np.float32), rho_out=big((m, n), np.float32), omega_raw=np.empty(n, np.float32),
+                omega_out=np.empty(n, np.float32), local=big((m, n), np.float32), variance=big((m, n), np.float32))
+    if n > 0:
+        args = _lib.MuncSeedArgs()
+        for k, v in {**arrays, **outs}.items():
+            setattr(args, k, v.ctypes.data if v.size else None)
+        for k, v in scalars.items():
+            setattr(args, k, v)
+        invalid = C.c_int32(0)
+        ctx = _ctx()
+        _lib.check(ctx._lib.cb200_host_munc_seed_pass(ctx.handle, C.byref(args), C.byref(invalid)))
+        if invalid.value:
+            raise ValueError("active MUNC seed cells must be finite with positive denominators")
+    return (outs["moment"], outs["rho_out"], outs["omega_raw"], outs["omega_out"], outs["local"], outs["variance"])
 
 
 def cFinalizeMuncEBTrack(localVarianceTrack, priorVarianceTrack=None, countFloor=None, nuLocal=0.0, nuPrior=0.0,

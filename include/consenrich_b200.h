@@ -19,6 +19,7 @@
  *   csolveZeroCenteredBackground :944-1096              cb200_host_background_solve
  *   cMuncSmoothDenseLocalEvidence :5547-5740            cb200_host_munc_smooth_local_evidence
  *   cFinalizeMuncEBTrack :5372-5545                     cb200_host_munc_finalize_eb
+ *   cMuncObservationMomentSeedPass :4843-5345           cb200_host_munc_seed_pass
  *
  * Conventions
  *   - plain C: pointers, sizes, POD structs; no torch / numpy types.
@@ -311,6 +312,32 @@ CB200_API int cb200_host_munc_finalize_eb(cb200_ctx *ctx, const float *local, co
                                 const float *count_floor, int64_t n, double nu_local, double nu_prior,
                                 double variance_floor, double variance_cap, int32_t use_eb, float *out,
                                 cb200_munc_finalize_result *result);
+
+/* cMuncObservationMomentSeedPass (cconsenrich.pyx:4843-5345): per cell, the squared residual against the
+ * seed smoother's state plus its variance (`moment`), the Student-t cell weight (`rho_out`), per interval
+ * the track-averaged weight (`omega_raw`, clamped: `omega_out`), and from them the local variance and the
+ * total variance (local + count floor), both clipped to [variance_floor, variance_cap].  float32 in and
+ * out, float64 arithmetic in the reference's order with separately rounded operations: bit-identical.
+ * Matrices are [m][ld] (cb200_munc_seed_pass: device, pitch ld; cb200_host_munc_seed_pass: host,
+ * contiguous, ld ignored); vectors are [n]; NULL = absent (background, g_var, count_floor, omega_in,
+ * rho_in (treated as ones), active).  active_mode 0: every cell active; 1: active is uint8 [n];
+ * 2: uint8 [m][active_ld]; nonzero = active.  *invalid is set to 1 when an active cell fails the
+ * reference's input check (pyx:4767-4840; it raises ValueError). */
+typedef struct cb200_munc_seed_args {
+    const float *data, *munc, *state_mean, *state_var, *background, *g_var, *count_floor, *omega_in, *rho_in;
+    const unsigned char *active;
+    float *moment, *rho_out, *omega_raw, *omega_out, *local, *variance;
+    int64_t m, n, ld, active_ld;
+    int32_t active_mode;
+    int32_t use_weights;     /* enabled and useSeedWeights */
+    int32_t student_t;
+    int32_t update_weights;
+    double pad, student_t_df, d_omega, omega_min, omega_max, variance_floor, variance_cap;
+} cb200_munc_seed_args;
+/* device arrays; *invalid is a device int32 */
+CB200_API int cb200_munc_seed_pass(cb200_ctx *ctx, const cb200_munc_seed_args *args, int32_t *invalid);
+/* host arrays; *invalid is a host int32 */
+CB200_API int cb200_host_munc_seed_pass(cb200_ctx *ctx, const cb200_munc_seed_args *args, int32_t *invalid);
 
 #ifdef __cplusplus
 }

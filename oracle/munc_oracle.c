@@ -109,3 +109,169 @@ void munc_finalize_eb(const float *local, const float *prior, const float *cfloo
         out[i] = (float)ov;
     }
 }
+
+/* ---- cMuncObservationMomentSeedPass, cconsenrich.pyx:4767-5040 ---- */
+typedef struct {
+    const float *data, *munc, *state_mean, *state_var, *background, *g_var, *count_floor, *omega_in, *rho_in;
+    const uint8_t *active;
+    float *moment, *rho_out, *omega_raw, *omega_out, *local, *variance;
+    int64_t m, n;
+    int32_t active_mode, use_weights, student_t, update_weights;
+    double pad, d_s, d_omega, omega_min, omega_max, var_floor, var_cap;
+} seed_args;
+
+static int seed_active(const seed_args *a, int64_t j, int64_t k) {
+    /* _muncSeedMaskAllowsCell with nonzeroMeansActive = True */
+    if (a->active_mode == 0) return 1;
+    return (a->active_mode == 1 ? a->active[k] : a->active[j * a->n + k]) != 0;
+}
+
+static double clamp_mult(double v, double lo, double hi) { /* :135-140 */
+    if (v < lo) return lo;
+    if (v > hi) return hi;
+    return v;
+}
+
+/* _muncObservationMomentSeedInvalidIndex, :4767-4840 */
+int64_t munc_seed_invalid_index(const seed_args *a) {
+    const int weighted = a->use_weights && a->student_t;
+    for (int64_t j = 0; j < a->m; ++j)
+        for (int64_t k = 0; k < a->n; ++k) {
+            int64_t idx = j * a->n + k;
+            double v;
+            if (!seed_active(a, j, k)) continue;
+            if (!isfinite((double)a->state_mean[k])) return idx;
+            if (!isfinite((double)a->state_var[k])) return idx;
+            if (a->background && !isfinite((double)a->background[k])) return idx;
+            if (a->g_var && !isfinite((double)a->g_var[k])) return idx;
+            if (!isfinite((double)a->data[idx])) return idx;
+            v = (double)a->munc[idx] + a->pad;
+            if (!isfinite(v) || v <= 0.0) return idx;
+            if (a->count_floor) {
+                v = (double)a->count_floor[idx];
+                if (!isfinite(v) || v < 0.0) return idx;
+            }
+            if (weighted) {
+                if (a->omega_in) {
+                    v = (double)a->omega_in[k];
+                    if (!isfinite(v) || v <= 0.0) return idx;
+                }
+                if (!a->update_weights) {
+                    v = (double)a->rho_in[idx];
+                    if (!isfinite(v) || v <= 0.0) return idx;
+                }
+            }
+        }
+    return -1;
+}
+
+/* _muncObservationMomentSeedPassInterval for every interval, :4843-5040 */
+void munc_seed_pass(const seed_args *a) {
+    const int weighted = a->use_weights && a->student_t;
+    for (int64_t k = 0; k < a->n; ++k) {
+        int64_t active_count = 0;
+        double state = (double)a->state_mean[k], mvb = (double)a->state_var[k];
+        double bg = 0.0, cv, base, res, mom, rho = 1.0, omega_in = 1.0, omega_raw, omega = 1.0, dbar, lv, tv;
+        if (a->background) bg = (double)a->background[k];
+        if (a->g_var) mvb += (double)a->g_var[k];
+        if (mvb < 0.0) mvb = 0.0;
+        if (weighted) {
+            omega_in = a->omega_in ? (double)a->omega_in[k] : 1.0;
+            if (a->update_weights) {
+                dbar = 0.0;
+                for (int64_t j = 0; j < a->m; ++j) {
+                    int64_t idx = j * a->n + k;
+                    if (!seed_active(a, j, k)) {
+                        a->moment[idx] = 0.0f;
+                        a->rho_out[idx] = 1.0f;
+                        continue;
+                    }
+                    base = (double)a->munc[idx] + a->pad;
+                    if (base < a->var_floor) base = a->var_floor;
+                    res = (double)a->data[idx] - bg - state;
+                    mom = res * res + mvb;
+                    rho = (a->d_s + 1.0) / (a->d_s + omega_in * mom / base);
+                    a->moment[idx] = (float)mom;
+                    a->rho_out[idx] = (float)rho;
+                    dbar += mom / base;
+                    active_count += 1;
+                }
+                if (active_count > 0) {
+                    dbar = dbar / (double)active_count;
+                    omega_raw = (a->d_omega + 1.0) / (a->d_omega + dbar);
+                    omega = clamp_mult(omega_raw, a->omega_min, a->omega_max);
+                } else {
+                    omega_raw = 1.0;
+                    omega = 1.0;
+                }
+            } else {
+                omega_raw = omega_in;
+                omega = clamp_mult(omega_raw, a->omega_min, a->omega_max);
+                for (int64_t j = 0; j < a->m; ++j) {
+                    int64_t idx = j * a->n + k;
+                    if (!seed_active(a, j, k)) {
+                        a->moment[idx] = 0.0f;
+                        a->rho_out[idx] = 1.0f;
+                        continue;
+                    }
+                    res = (double)a->data[idx] - bg - state;
+                    mom = res * res + mvb;
+                    rho = (double)a->rho_in[idx];
+                    a->moment[idx] = (float)mom;
+                    a->rho_out[idx] = (float)rho;
+                }
+            }
+            a->omega_raw[k] = (float)omega_raw;
+            a->omega_out[k] = (float)omega;
+        } else {
+            a->omega_raw[k] = 1.0f;
+            a->omega_out[k] = 1.0f;
+        }
+        for (int64_t j = 0; j < a->m; ++j) {
+            int64_t idx = j * a->n + k;
+            cv = a->count_floor ? (double)a->count_floor[idx] : 0.0;
+            if (seed_active(a, j, k)) {
+                if (!weighted) {
+                    res = (double)a->data[idx] - bg - state;
+                    mom = res * res + mvb;
+                    a->moment[idx] = (float)mom;
+                    a->rho_out[idx] = 1.0f;
+                    lv = mom - a->pad - cv;
+                } else {
+                    mom = (double)a->moment[idx];
+                    rho = (double)a->rho_out[idx];
+                    lv = omega * rho * mom - a->pad - cv;
+                }
+                tv = lv + cv;
+                if (lv < a->var_floor) {
+                    lv = a->var_floor;
+                    tv = lv + cv;
+                }
+                if (tv > a->var_cap) {
+                    tv = a->var_cap;
+                    lv = tv - cv;
+                    if (lv < a->var_floor) {
+                        lv = a->var_floor;
+                        tv = lv + cv;
+                    }
+                }
+            } else {
+                lv = (double)a->munc[idx] - cv;
+                if (lv < a->var_floor) lv = a->var_floor;
+                tv = lv + cv;
+                if (tv > a->var_cap) {
+                    tv = a->var_cap;
+                    lv = tv - cv;
+                    if (lv < a->var_floor) {
+                        lv = a->var_floor;
+                        tv = lv + cv;
+                    }
+                }
+                a->moment[idx] = 0.0f;
+                a->rho_out[idx] = 1.0f;
+            }
+            a->local[idx] = (float)lv;
+            a->variance[idx] = (float)tv;
+        }
+    }
+}

@@ -21,6 +21,7 @@ and (``oracle/munc_oracle.c``) the dense kernels of the observation-noise stage:
 
 * ``cMuncSmoothDenseLocalEvidence``         <- cconsenrich.pyx:5547-5740
 * ``cFinalizeMuncEBTrack``                  <- cconsenrich.pyx:5365-5545
+* ``cMuncObservationMomentSeedPass``        <- cconsenrich.pyx:4767-5345
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this module.  The product (``consenrich_b200``) never does.
@@ -690,3 +691,105 @@ def cFinalizeMuncEBTrack(localVarianceTrack, priorVarianceTrack=None, countFloor
         "finalShrinkagePairCount": n if use_eb else 0,
         "finalShrinkagePairFraction": 1.0 if use_eb and n > 0 else 0.0,
     }
+
+
+class _SeedArgs(C.Structure):
+    _fields_ = ([(k, C.c_void_p) for k in ("data", "munc", "state_mean", "state_var", "background", "g_var",
+                                           "count_floor", "omega_in", "rho_in", "active", "moment", "rho_out",
+                                           "omega_raw", "omega_out", "local", "variance")]
+                + [("m", C.c_int64), ("n", C.c_int64)]
+                + [(k, C.c_int32) for k in ("active_mode", "use_weights", "student_t", "update_weights")]
+                + [(k, C.c_double) for k in ("pad", "d_s", "d_omega", "omega_min", "omega_max", "var_floor", "var_cap")])
+
+
+def cMuncObservationMomentSeedPass(matrixData, matrixMunc, stateMean, stateVariance, background=None, gVariance=None,
+                                   countFloor=None, omegaIn=None, rhoIn=None, pad=1.0e-4, studentTdf=8.0,
+                                   useSeedWeights=True, updateWeights=True, omegaMin=0.01, omegaMax=100.0,
+                                   varianceFloor=1.0e-12, varianceCap=3.4028234663852886e38, enabled=True,
+                                   studentT=True, dOmega=8.0, activeMask=None):
+    """cconsenrich.pyx:5042-5345 (checks and error texts included)."""
+    f32 = lambda v: float(np.float32(v))
+    data = np.ascontiguousarray(matrixData, dtype=np.float32)
+    munc = np.ascontiguousarray(matrixMunc, dtype=np.float32)
+    mean = np.ascontiguousarray(stateMean, dtype=np.float32)
+    var = np.ascontiguousarray(stateVariance, dtype=np.float32)
+    m, n = data.shape
+    use_weights, student_t, update = bool(enabled) and bool(useSeedWeights), bool(studentT), bool(updateWeights)
+    pad_d, df, d_om = f32(pad), f32(studentTdf), f32(dOmega)
+    om_lo, om_hi, vfloor, vcap = f32(omegaMin), f32(omegaMax), f32(varianceFloor), f32(varianceCap)
+    if munc.shape[0] != m or munc.shape[1] != n:
+        raise ValueError("matrixMunc shape must match matrixData shape")
+    if mean.shape[0] != n:
+        raise ValueError("stateMean length must match interval count")
+    if var.shape[0] != n:
+        raise ValueError("stateVariance length must match interval count")
+    if pad_d < 0.0 or not np.isfinite(pad_d):
+        raise ValueError("pad must be finite and nonnegative")
+    if vfloor <= 0.0 or not np.isfinite(vfloor):
+        raise ValueError("varianceFloor must be positive and finite")
+    if not np.isfinite(vcap) or vcap < vfloor:
+        raise ValueError("varianceCap must be greater than or equal to varianceFloor")
+    if use_weights and student_t and (df <= 0.0 or d_om <= 0.0 or not np.isfinite(df) or not np.isfinite(d_om)
+                                      or om_lo <= 0.0 or om_hi < om_lo or not np.isfinite(om_lo)
+                                      or not np.isfinite(om_hi)):
+        raise ValueError("seed weight parameters are invalid")
+    keep = dict(data=data, munc=munc, state_mean=mean, state_var=var)
+    if background is not None:
+        keep["background"] = np.ascontiguousarray(background, dtype=np.float32).reshape(-1)
+        if keep["background"].shape[0] != n:
+            raise ValueError("background length must match interval count")
+    if gVariance is not None:
+        keep["g_var"] = np.ascontiguousarray(gVariance, dtype=np.float32).reshape(-1)
+        if keep["g_var"].shape[0] != n:
+            raise ValueError("gVariance length must match interval count")
+    if countFloor is not None:
+        cf = np.ascontiguousarray(countFloor, dtype=np.float32)
+        if cf.ndim != 2 or cf.shape[0] != m or cf.shape[1] != n:
+            raise ValueError("countFloor shape must match matrixData shape")
+        keep["count_floor"] = cf
+    if omegaIn is not None:
+        om = np.ascontiguousarray(omegaIn, dtype=np.float32)
+        if om.ndim != 1:
+            raise ValueError("omegaIn must be one-dimensional")
+        if om.shape[0] != n:
+            raise ValueError("omegaIn length must match interval count")
+        keep["omega_in"] = om
+    if rhoIn is None and use_weights and student_t and not update:
+        keep["rho_in"] = np.ones((m, n), np.float32)
+    elif rhoIn is not None:
+        rho = np.ascontiguousarray(rhoIn, dtype=np.float32)
+        if rho.ndim != 2 or rho.shape[0] != m or rho.shape[1] != n:
+            raise ValueError("rhoIn shape must match matrixData shape")
+        keep["rho_in"] = rho
+    mode = 0
+    if activeMask is not None:
+        act = np.ascontiguousarray(activeMask, dtype=np.uint8)
+        if act.ndim == 1:
+            if act.shape[0] != n:
+                raise ValueError("activeMask length must match interval count")
+            mode = 1
+        elif act.ndim == 2:
+            if act.shape[0] != m or act.shape[1] != n:
+                raise ValueError("activeMask shape must match matrixData shape")
+            mode = 2
+        else:
+            raise ValueError("activeMask must be one- or two-dimensional")
+        keep["active"] = act
+    outs = dict(moment=np.empty((m, n), np.float32), rho_out=np.empty((m, n), np.float32),
+                omega_raw=np.empty(n, np.float32), omega_out=np.empty(n, np.float32),
+                local=np.empty((m, n), np.float32), variance=np.empty((m, n), np.float32))
+    a = _SeedArgs()
+    for k, v in {**keep, **outs}.items():
+        setattr(a, k, v.ctypes.data)
+    a.m, a.n, a.active_mode = m, n, mode
+    a.use_weights, a.student_t, a.update_weights = int(use_weights), int(student_t), int(update)
+    a.pad, a.d_s, a.d_omega, a.omega_min, a.omega_max, a.var_floor, a.var_cap = pad_d, df, d_om, om_lo, om_hi, vfloor, vcap
+    lib = _L()
+    lib.munc_seed_invalid_index.restype = C.c_int64
+    lib.munc_seed_invalid_index.argtypes = [C.POINTER(_SeedArgs)]
+    lib.munc_seed_pass.restype = None
+    lib.munc_seed_pass.argtypes = [C.POINTER(_SeedArgs)]
+    if lib.munc_seed_invalid_index(C.byref(a)) >= 0:
+        raise ValueError("active MUNC seed cells must be finite with positive denominators")
+    lib.munc_seed_pass(C.byref(a))
+    return (outs["moment"], outs["rho_out"], outs["omega_raw"], outs["omega_out"], outs["local"], outs["variance"])

@@ -34,6 +34,38 @@ def exclude_mask(rng, m, n, mode):
     return mask
 
 
+SEED_POSITIONAL = ("matrixData", "matrixMunc", "stateMean", "stateVariance")
+SEED_OUTPUTS = ("moment", "rhoOut", "omegaRaw", "omegaOut", "local", "variance")
+
+
+def seed_case(rng, m, n, variant):
+    """Inputs of one cMuncObservationMomentSeedPass call; `variant` picks the branch of pyx:4843-5040."""
+    c = dict(matrixData=rng.normal(0, 1, (m, n)).astype(np.float32),
+             matrixMunc=rng.uniform(0.05, 1.0, (m, n)).astype(np.float32),
+             stateMean=rng.normal(0, 0.3, n).astype(np.float32), stateVariance=rng.uniform(0, 0.2, n).astype(np.float32))
+    if variant in ("update", "fixed", "gaussian"):
+        c["background"] = rng.normal(0, 0.1, n).astype(np.float32)
+        c["gVariance"] = rng.uniform(-0.01, 0.05, n).astype(np.float32)
+        c["countFloor"] = rng.uniform(0, 0.3, (m, n)).astype(np.float32)
+    if variant == "update":
+        c["omegaIn"] = rng.uniform(0.2, 3.0, n).astype(np.float32)
+        c["activeMask"] = (rng.random(n) < 0.9).astype(np.uint8)
+        c.update(pad=0.01, studentTdf=4.0, dOmega=6.0, omegaMin=0.5, omegaMax=1.5, varianceFloor=1e-3, varianceCap=1.5)
+    elif variant == "fixed":
+        c["omegaIn"] = rng.uniform(0.2, 3.0, n).astype(np.float32)
+        c["rhoIn"] = rng.uniform(0.2, 2.0, (m, n)).astype(np.float32)
+        c["activeMask"] = (rng.random((m, n)) < 0.85).astype(np.uint8)
+        c["updateWeights"] = False
+    elif variant == "unweighted":
+        c["useSeedWeights"] = False
+        c["activeMask"] = (rng.random((m, n)) < 0.7).astype(np.uint8)
+        c["countFloor"] = rng.uniform(0, 0.3, (m, n)).astype(np.float32)
+        c["varianceCap"] = 0.8
+    elif variant == "gaussian":
+        c.update(studentT=False, varianceFloor=0.05, varianceCap=0.6)
+    return c
+
+
 def main():
     ref = O.load_reference()
     if ref is None:
@@ -88,6 +120,17 @@ def main():
         out[f"finalize/{name}/out"] = res
         for k_, v_ in diag.items():
             out[f"finalize/{name}/diag_{k_}"] = np.asarray(v_)
+    # cMuncObservationMomentSeedPass: every branch of pyx:4843-5040
+    for name, m, n, variant in (("weighted_update", 4, 600, "update"), ("weighted_fixed", 3, 501, "fixed"),
+                                ("unweighted_masked", 5, 400, "unweighted"), ("gaussian_clipped", 2, 300, "gaussian"),
+                                ("single_cell", 1, 1, "update")):
+        c = seed_case(rng, m, n, variant)
+        res = ref.cMuncObservationMomentSeedPass(c["matrixData"], c["matrixMunc"], c["stateMean"], c["stateVariance"],
+                                                 **{k: v for k, v in c.items() if k not in SEED_POSITIONAL})
+        for k, v in c.items():
+            out[f"seed/{name}/in_{k}"] = np.asarray(v)
+        for k, v in zip(SEED_OUTPUTS, res):
+            out[f"seed/{name}/out_{k}"] = v
     path = os.path.join(HERE, "munc_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

@@ -169,3 +169,78 @@ def test_concurrent_calls_from_a_thread_pool(cb, oracle):
 
     with ThreadPoolExecutor(max_workers=4) as pool:
         assert all(pool.map(work, jobs))
+
+
+# ---- cMuncObservationMomentSeedPass: per-interval loops over the tracks, bit-identical ----
+SEED_NAMES = ("moment", "rhoOut", "omegaRaw", "omegaOut", "local", "variance")
+
+
+def test_seed_pass_matches_golden_vectors_bitwise(cb):
+    from test_munc_oracle import check_seed, run_seed
+    for name, c in golden_cases("seed").items():
+        check_seed(run_seed(cb, c), c, name)
+
+
+@pytest.mark.parametrize("variant", ["update", "fixed", "unweighted", "gaussian"])
+def test_seed_pass_matches_oracle_bitwise_on_fresh_seeds(cb, oracle, variant):
+    from golden.make_munc_golden import SEED_POSITIONAL, seed_case
+    rng = np.random.default_rng(400 + len(variant))
+    for m, n in ((1, 1), (2, 33), (10, 70001), (130, 4000), (3, 600_001)):
+        c = seed_case(rng, m, n, variant)
+        pos = [c[k] for k in SEED_POSITIONAL]
+        kw = {k: v for k, v in c.items() if k not in SEED_POSITIONAL}
+        want = oracle.cMuncObservationMomentSeedPass(*pos, **kw)
+        got = cb.cMuncObservationMomentSeedPass(*pos, **kw)
+        for name, g, w in zip(SEED_NAMES, got, want):
+            assert g.shape == w.shape and g.dtype == np.float32
+            np.testing.assert_array_equal(g, w, err_msg=f"{variant} {m}x{n} {name}")
+
+
+def test_seed_pass_at_the_bench_size(cb, oracle):
+    """hg38 chr19 @ 25 bp x 10 tracks: the oracle on the first 200 000 intervals (columns are independent),
+    and the definitions themselves on the rest (variance = local + count floor inside the clip range)."""
+    from golden.make_munc_golden import SEED_POSITIONAL, seed_case
+    rng = np.random.default_rng(5)
+    m, n, h = 10, 2_344_705, 200_000
+    c = seed_case(rng, m, n, "update")
+    pos = [c[k] for k in SEED_POSITIONAL]
+    kw = {k: v for k, v in c.items() if k not in SEED_POSITIONAL}
+    got = cb.cMuncObservationMomentSeedPass(*pos, **kw)
+    head = lambda v: np.ascontiguousarray(v[..., :h]) if isinstance(v, np.ndarray) else v
+    want = oracle.cMuncObservationMomentSeedPass(*[head(p) for p in pos], **{k: head(v) for k, v in kw.items()})
+    for name, g, w in zip(SEED_NAMES, got, want):
+        np.testing.assert_array_equal(g[..., :h], w, err_msg=name)
+    local, variance = got[4].astype(np.float64), got[5].astype(np.float64)
+    assert local.min() >= np.float32(1e-3) and variance.max() <= np.float32(1.5)
+    inside = variance < 1.5 - 1e-6
+    np.testing.assert_allclose(variance[inside], (local + c["countFloor"])[inside], rtol=2e-7)
+    assert np.all((got[3] >= np.float32(0.5)) & (got[3] <= np.float32(1.5)))
+
+
+def test_seed_pass_errors_follow_the_reference(cb, oracle):
+    from golden.make_munc_golden import SEED_POSITIONAL, seed_case
+    rng = np.random.default_rng(6)
+    c = seed_case(rng, 3, 5000, "update")
+    pos = [c[k] for k in SEED_POSITIONAL]
+    kw = {k: v for k, v in c.items() if k not in SEED_POSITIONAL}
+    k_act, k_off = int(np.flatnonzero(c["activeMask"])[-1]), int(np.flatnonzero(c["activeMask"] == 0)[0])
+    bad_data, ok_data = pos[0].copy(), pos[0].copy()
+    bad_data[1, k_act] = np.inf
+    ok_data[1, k_off] = np.nan  # an inactive cell may hold anything
+    bad_mean = pos[2].copy()
+    bad_mean[k_act] = np.nan
+    cases = [((bad_data, *pos[1:]), kw), ((pos[0], pos[1], bad_mean, pos[3]), kw), (pos, {**kw, "pad": -1.0}),
+             (pos, {**kw, "varianceFloor": 0.0}), (pos, {**kw, "varianceCap": 1e-9}), (pos, {**kw, "omegaMin": 0.0}),
+             (pos, {**kw, "omegaIn": c["omegaIn"][:-1]}), (pos, {**kw, "countFloor": c["countFloor"][:, :-1]}),
+             (pos, {**kw, "activeMask": np.zeros((1, 2, 3), np.uint8)}), ((pos[0], pos[1][:, :-1], pos[2], pos[3]), kw)]
+    for args, kwargs in cases:
+        msgs = []
+        for mod in (oracle, cb):
+            with pytest.raises(ValueError) as e:
+                mod.cMuncObservationMomentSeedPass(*args, **kwargs)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1], msgs
+    a = oracle.cMuncObservationMomentSeedPass(ok_data, *pos[1:], **kw)
+    b = cb.cMuncObservationMomentSeedPass(ok_data, *pos[1:], **kw)
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)

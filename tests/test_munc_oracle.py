@@ -119,3 +119,53 @@ def test_oracle_finalize_matches_reference_build_errors_included(oracle):
                 mod.cFinalizeMuncEBTrack(loc, pri, cf, **{**kw, **bad_kw})
             msgs.append(str(e.value))
         assert msgs[0] == msgs[1]
+
+
+def run_seed(mod, c):
+    ins = {k[3:]: (v.item() if v.ndim == 0 else v) for k, v in c.items() if k.startswith("in_")}
+    pos = [ins.pop(k) for k in ("matrixData", "matrixMunc", "stateMean", "stateVariance")]
+    return mod.cMuncObservationMomentSeedPass(*pos, **ins)
+
+
+def check_seed(got, c, what=""):
+    for k, v in zip(("moment", "rhoOut", "omegaRaw", "omegaOut", "local", "variance"), got):
+        np.testing.assert_array_equal(v, c["out_" + k], err_msg=f"{what} {k}")
+
+
+def test_oracle_matches_golden_seed_pass_vectors_bitwise(oracle):
+    cases = golden_cases("seed")
+    assert len(cases) >= 5
+    for name, c in cases.items():
+        check_seed(run_seed(oracle, c), c, name)
+
+
+def test_oracle_seed_pass_matches_reference_build_errors_included(oracle):
+    ref = oracle.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    from golden.make_munc_golden import SEED_POSITIONAL, seed_case
+    rng = np.random.default_rng(21)
+    for variant in ("update", "fixed", "unweighted", "gaussian"):
+        for m, n in ((1, 3), (7, 2500)):
+            c = seed_case(rng, m, n, variant)
+            pos = [c[k] for k in SEED_POSITIONAL]
+            kw = {k: v for k, v in c.items() if k not in SEED_POSITIONAL}
+            for x, y in zip(ref.cMuncObservationMomentSeedPass(*pos, **kw), oracle.cMuncObservationMomentSeedPass(*pos, **kw)):
+                np.testing.assert_array_equal(x, y)
+    c = seed_case(rng, 3, 50, "update")
+    pos = [c[k] for k in SEED_POSITIONAL]
+    kw = {k: v for k, v in c.items() if k not in SEED_POSITIONAL}
+    k_act = int(np.flatnonzero(c["activeMask"])[0])
+    bad_data = pos[0].copy()
+    bad_data[1, k_act] = np.nan
+    bad_munc = pos[1].copy()
+    bad_munc[2, k_act] = -1.0
+    for args, kwargs in (((bad_data, *pos[1:]), kw), ((pos[0], bad_munc, *pos[2:]), kw), (pos, {**kw, "pad": -1.0}),
+                         (pos, {**kw, "varianceFloor": 0.0}), (pos, {**kw, "omegaMin": 0.0}),
+                         (pos, {**kw, "omegaIn": c["omegaIn"][:-1]}), (pos, {**kw, "countFloor": c["countFloor"][:, :-1]})):
+        msgs = []
+        for mod in (ref, oracle):
+            with pytest.raises(ValueError) as e:
+                mod.cMuncObservationMomentSeedPass(*args, **kwargs)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1], msgs
