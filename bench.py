@@ -356,6 +356,28 @@ def background_block(torch, dev, stream, ctx, reps, host, m, n, ld, no_cpu):
                                             C.byref(fres)))
 
     ms_finalize = timed(finalize)  # includes the status read-back (one stream synchronisation per call)
+    # cMuncObservationMomentSeedPass, Student-t weights updated, count floor given: 3 matrices in, 4 out
+    seed_out = [torch.empty((m, ld), dtype=torch.float32, device=dev) for _ in range(4)]
+    seed_cf = torch.rand((m, ld), dtype=torch.float32, device=dev) * 0.1
+    seed_vec = [torch.rand(n, dtype=torch.float32, device=dev) * 0.1 for _ in range(2)]
+    seed_om = [torch.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+    sargs = _lib.MuncSeedArgs()
+    sargs.count_floor, sargs.state_mean, sargs.state_var = seed_cf.data_ptr(), seed_vec[0].data_ptr(), seed_vec[1].data_ptr()
+    sargs.moment, sargs.rho_out, sargs.local, sargs.variance = (t_.data_ptr() for t_ in seed_out)
+    sargs.omega_raw, sargs.omega_out = seed_om[0].data_ptr(), seed_om[1].data_ptr()
+    sargs.m, sargs.n, sargs.ld, sargs.active_ld = m, n, ld, n
+    sargs.active_mode, sargs.use_weights, sargs.student_t, sargs.update_weights = 0, 1, 1, 1
+    sargs.pad, sargs.student_t_df, sargs.d_omega, sargs.omega_min, sargs.omega_max = 1e-4, 8.0, 8.0, 0.01, 100.0
+    sargs.variance_floor, sargs.variance_cap = 1e-12, 3.0e38
+
+    def seed():
+        dd, vv, _ = rotate()
+        sargs.data, sargs.munc = dd.data_ptr(), vv.data_ptr()
+        _lib.check(L.cb200_munc_seed_pass(ctx.handle, C.byref(sargs), _p(flag)))
+
+    ms_seed = timed(seed)
+    blk["munc_seed_pass_ms_device"] = ms_seed
+    blk["munc_seed_pass_frac_of_peak"] = (28.0 * m * n + 16.0 * n) / (ms_seed * 1e-3) / 1e9 / peak
     blk["munc_finalize_ms_device"] = ms_finalize
     blk["munc_finalize_frac_of_peak"] = 16.0 * n / (ms_finalize * 1e-3) / 1e9 / peak
     smooth_bytes = 8.0 * m * n + 1.0 * n
@@ -374,7 +396,12 @@ def background_block(torch, dev, stream, ctx, reps, host, m, n, ld, no_cpu):
         t0 = time.perf_counter()
         mod.cMuncSmoothDenseLocalEvidence(host["munc"], window, excludeMask=hmask, eps=1e-12)
         cpu_smooth = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        mod.cMuncObservationMomentSeedPass(host["data"], host["munc"], seed_vec[0].cpu().numpy(), seed_vec[1].cpu().numpy(),
+                                           countFloor=np.ascontiguousarray(seed_cf[:, :n].cpu().numpy()))
+        cpu_seed = time.perf_counter() - t0
         blk["cpu_reference"] = {"kind": kind, "cores": 1, "solve_ms": 1e3 * cpu_solve, "stats_ms": 1e3 * cpu_stats,
+                                "munc_seed_pass_ms": 1e3 * cpu_seed,
                                 "munc_smooth_ms": 1e3 * cpu_smooth,
                                 "max_abs_diff_over_max_abs": float(np.abs(x - y).max() / max(np.abs(y).max(), 1e-300))}
     return blk

@@ -573,8 +573,7 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
         r.l0 = Level0{w, rhs, n, lam, lam_first};
         return r;
     };
-    const BackgroundStatus init{INT64_MAX, 0.0};
-    cudaError_t e = cudaMemcpyAsync(status, &init, sizeof(init), cudaMemcpyHostToDevice, st);
+    cudaError_t e = cudaMemsetAsync(status, 0x7f, sizeof(BackgroundStatus), st);  // bad_index = STATUS_NONE
     if (e != cudaSuccess) return e;
     // the levels: [0, first_mid) one launch each way; [first_mid, first_small) + the shared-memory tail in
     // one cooperative launch when the device takes it (co-resident CTAs), else launch by launch

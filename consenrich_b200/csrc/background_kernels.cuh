@@ -12,8 +12,12 @@ constexpr int BG_SUM_BLOCKS = 1024;
 constexpr int BG_MID_ROWS = 65536;    // levels up to this many block rows share one cooperative launch
 constexpr int BG_MID_THREADS = 256;
 
+// "no index" in the status records the kernels fill by atomicMin: the value cudaMemsetAsync(0x7f) leaves,
+// so that arming a record needs no host-to-device copy
+constexpr int64_t STATUS_NONE = 0x7f7f7f7f7f7f7f7fLL;
+
 // outcome of a solve: first unknown whose pivot fell below the reference's floor (1e-12), or
-// INT64_MAX; the reference fails such a solve (cconsenrich.pyx:1090-1095)
+// STATUS_NONE; the reference fails such a solve (cconsenrich.pyx:1090-1095)
 struct BackgroundStatus {
     int64_t bad_index;
     double bad_value;

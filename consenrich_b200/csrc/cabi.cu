@@ -1175,7 +1175,7 @@ int cb200_background_solve(cb200_ctx *c, const double *weight, const double *rhs
         BackgroundStatus st;
         CU_TRY(cudaMemcpyAsync(&st, c->bg_status.p, sizeof(st), cudaMemcpyDeviceToHost, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream));
-        if (st.bad_index != INT64_MAX) {
+        if (st.bad_index != STATUS_NONE) {
             if (bad_index) *bad_index = st.bad_index;
             if (bad_value) *bad_value = st.bad_value;
         }
@@ -1353,9 +1353,9 @@ int cb200_munc_finalize_eb(cb200_ctx *c, const float *local, const float *prior,
     // the reference stops at the first offending interval; at equal index local is tested before prior
     // before the count floor
     const int64_t il = h.invalid_local, ip = h.invalid_prior, ic = h.invalid_cfloor;
-    if (il != INT64_MAX && il <= ip && il <= ic) result->invalid_local = il;
-    else if (ip != INT64_MAX && ip <= ic) result->invalid_prior = ip;
-    else if (ic != INT64_MAX) result->invalid_count_floor = ic;
+    if (il != STATUS_NONE && il <= ip && il <= ic) result->invalid_local = il;
+    else if (ip != STATUS_NONE && ip <= ic) result->invalid_prior = ip;
+    else if (ic != STATUS_NONE) result->invalid_count_floor = ic;
     return CB200_OK;
 }
 

@@ -421,8 +421,10 @@ cudaError_t launch_munc_seed_pass(const MuncSeedArgs &a, int *invalid, cudaStrea
 cudaError_t launch_munc_finalize_eb(const float *local, const float *prior, const float *cfloor, int64_t n,
                                     double nu_local, double nu_prior, double vfloor, double vcap, int use_eb, float *out,
                                     MuncFinalizeStatus *status, cudaStream_t st) {
-    const MuncFinalizeStatus init{0, 0, 0, 0, INT64_MAX, INT64_MAX, INT64_MAX};
-    cudaError_t e = cudaMemcpyAsync(status, &init, sizeof(init), cudaMemcpyHostToDevice, st);
+    // counters 0, invalid_* = STATUS_NONE: two memsets, no host-to-device copy
+    cudaError_t e = cudaMemsetAsync(status, 0, 4 * sizeof(int64_t), st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(&status->invalid_local, 0x7f, 3 * sizeof(int64_t), st);
     if (e != cudaSuccess || n <= 0) return e;
     finalize_eb_kernel<<<(unsigned)((n + FIN_THREADS - 1) / FIN_THREADS), FIN_THREADS, 0, st>>>(
         local, prior, cfloor, n, nu_local, nu_prior, nu_local + nu_prior, vfloor, vcap, use_eb, out, status);

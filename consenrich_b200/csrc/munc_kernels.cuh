@@ -4,6 +4,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "background_kernels.cuh"
+
 namespace cb200 {
 
 constexpr int64_t MUNC_MAX_WINDOW = 8192;  // tile + window cells must fit one CTA's shared memory
@@ -20,7 +22,7 @@ cudaError_t launch_munc_rolling_mean(const float *local, const uint8_t *mask, in
                                      int *invalid, cudaStream_t st);
 
 // outcome of launch_munc_finalize_eb (device memory): counters of cconsenrich.pyx:5355-5362; the invalid_*
-// fields hold the first offending interval of each kind or INT64_MAX
+// fields hold the first offending interval of each kind or STATUS_NONE (background_kernels.cuh)
 struct MuncFinalizeStatus {
     int64_t support, cfloor_finite, cfloor_added, cfloor_missing;
     int64_t invalid_local, invalid_prior, invalid_cfloor;
