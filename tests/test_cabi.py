@@ -64,12 +64,14 @@ def test_ctypes_table_matches_header(built_lib):
     os.makedirs(os.path.dirname(probe), exist_ok=True)
     src = probe + ".c"
     with open(src, "w") as f:
-        f.write('#include <stdio.h>\n#include "consenrich_b200.h"\nint main(void){printf("%zu %zu %zu\\n",'
-                "sizeof(cb200_model),sizeof(cb200_ecm_opts),sizeof(cb200_ecm_result));return 0;}\n")
+        f.write('#include <stdio.h>\n#include "consenrich_b200.h"\nint main(void){printf("%zu %zu %zu %zu %zu\\n",'
+                "sizeof(cb200_model),sizeof(cb200_ecm_opts),sizeof(cb200_ecm_result),"
+                "sizeof(cb200_munc_finalize_result),sizeof(cb200_munc_seed_args));return 0;}\n")
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", probe])
     sizes = [int(x) for x in subprocess.check_output([probe], text=True).split()]
     import ctypes as C
-    assert sizes == [C.sizeof(_lib.Model), C.sizeof(_lib.EcmOpts), C.sizeof(_lib.EcmResult)]
+    assert sizes == [C.sizeof(_lib.Model), C.sizeof(_lib.EcmOpts), C.sizeof(_lib.EcmResult),
+                     C.sizeof(_lib.MuncFinalizeResult), C.sizeof(_lib.MuncSeedArgs)]
 
 
 def test_no_device_means_loud_failure_not_a_cpu_path(built_lib):
