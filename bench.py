@@ -587,9 +587,9 @@ def run_b200_arm(args):
         # DRAM bytes of the same kernel from the committed `ncu --set full` capture (per launch)
         traffic, traffic_src = None, None
         try:
-            prof = json.load(open(os.path.join(ROOT, "profiles", "r1m_ncu_full_summary.json")))
+            prof = json.load(open(os.path.join(ROOT, "profiles", "r1q_ncu_full_summary.json")))
             traffic = float(prof["kernels"][dom]["dram_bytes_per_launch"])
-            traffic_src = "profiles/r1m_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
+            traffic_src = "profiles/r1q_ncu_full_summary.json (dram__bytes_read.sum + dram__bytes_write.sum)"
         except Exception:
             pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
