@@ -13,7 +13,7 @@ There is no CPU implementation: importing works anywhere, calling requires the b
 and a CUDA device, and fails loudly otherwise.
 """
 from . import _lib  # noqa: F401
-from .native import (cFinalizeMuncEBTrack, cMuncObservationMomentSeedPass,  # noqa: F401
+from .native import (cEMA, cFinalizeMuncEBTrack, cMuncObservationMomentSeedPass,  # noqa: F401
                      cMuncSmoothDenseLocalEvidence, cbackgroundWeightedStats,
                      cbackgroundWeightedStatsWithSupport,
                      cbackwardPass, cbackwardPassLevel, cfixedBackgroundECM, cfixedBackgroundECMLevel,

@@ -1506,4 +1506,35 @@ int cb200_host_munc_seed_pass(cb200_ctx *c, const cb200_munc_seed_args *a, int32
     return CB200_OK;
 }
 
+int cb200_ema(cb200_ctx *c, const void *x, int64_t n, int32_t is_double, double alpha, void *out) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (!(alpha >= 0.0 && alpha <= 1.0)) return fail(CB200_ERR_INVALID, "alpha must lie in [0, 1]");
+    if (n < 0) return fail(CB200_ERR_INVALID, "n must be nonnegative");
+    if (n == 0) return CB200_OK;
+    if (!x || !out) return fail(CB200_ERR_INVALID, "NULL argument");
+    const size_t esz = is_double ? 8 : 4;
+    CB_TRY(ensure(c, c->seed_mat[0], (size_t)n * esz));  // scratch: the forward pass
+    CB_TRY(ensure(c, c->bg_ws, munc_ema_workspace_bytes(n)));
+    Span sp(c, FAM_MUNC);
+    CU_TRY(launch_munc_ema(x, c->seed_mat[0].p, out, n, is_double ? 1 : 0, alpha, c->bg_ws.p, c->stream));
+    c->launches += 6;
+    return CB200_OK;
+}
+
+int cb200_host_ema(cb200_ctx *c, const void *x, int64_t n, int32_t is_double, double alpha, void *out) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (n <= 0) return n < 0 ? fail(CB200_ERR_INVALID, "n must be nonnegative") : CB200_OK;
+    if (!x || !out) return fail(CB200_ERR_INVALID, "NULL argument");
+    const size_t bytes = (size_t)n * (is_double ? 8 : 4);
+    CB_TRY(ensure(c, c->seed_mat[1], bytes));
+    CB_TRY(ensure(c, c->seed_mat[2], bytes));
+    CB_TRY(h2d(c, c->seed_mat[1].p, x, bytes));
+    CB_TRY(cb200_ema(c, c->seed_mat[1].p, n, is_double, alpha, c->seed_mat[2].p));
+    CB_TRY(d2h(c, out, c->seed_mat[2].p, bytes));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
 }  // extern "C"

@@ -409,7 +409,140 @@ __global__ void __launch_bounds__(SEED_THREADS) seed_pass_kernel(const MuncSeedA
     if (bad) atomicOr(invalid, 1);
 }
 
+// ---- cEMA (cconsenrich.pyx:5744-5759, 5897-5915): forward then backward exponential filter of a track ----
+// y_p = alpha x_p + (1 - alpha) y_{p-1} is an affine recurrence: each thread composes the map of its run
+// of EMA_RUN elements in float64, one CTA scans the run maps, and each thread then REPLAYS the
+// reference's own arithmetic (its rounding sequence in the track's type) over the run before its own --
+// a warm-up that lets the replay forget the scan's un-rounded start value -- and over its own run.
+constexpr int EMA_RUN = 256;
+constexpr int EMA_THREADS = 128;
+constexpr int EMA_SCAN_THREADS = 1024;
+
+template <class T>
+__device__ __forceinline__ T ema_step(T alpha, double c, T x, T y_prev);
+template <>
+__device__ __forceinline__ float ema_step<float>(float alpha, double c, float x, float y_prev) {
+    // alpha * x in float; (1.0 - alpha) * y in double; sum in double; stored as float (the C semantics of
+    // pyx:5752 for real_t = float)
+    return (float)__dadd_rn((double)__fmul_rn(alpha, x), __dmul_rn(c, (double)y_prev));
+}
+template <>
+__device__ __forceinline__ double ema_step<double>(double alpha, double c, double x, double y_prev) {
+    return __dadd_rn(__dmul_rn(alpha, x), __dmul_rn(c, y_prev));
+}
+
+// element p of the pass in processing order: index p forward, n - 1 - p backward
+__device__ __forceinline__ int64_t ema_index(int64_t p, int64_t n, int reversed) { return reversed ? n - 1 - p : p; }
+
+template <class T>
+__global__ void __launch_bounds__(EMA_THREADS) ema_run_maps_kernel(const T *__restrict__ src, int64_t n, int reversed,
+                                                                   T alpha, double c, int64_t runs,
+                                                                   double2 *__restrict__ maps) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= runs) return;
+    double A = 1.0, B = 0.0;
+    const int64_t p1 = min((r + 1) * EMA_RUN, n);
+    for (int64_t p = r * EMA_RUN; p < p1; ++p) {
+        const T x = src[ema_index(p, n, reversed)];
+        if (p == 0) {  // the pass starts from the first element itself
+            A = 0.0;
+            B = (double)x;
+        } else {
+            B = c * B + (double)ema_step<T>(alpha, 0.0, x, (T)0);  // alpha x in the track's arithmetic
+            A = c * A;
+        }
+    }
+    maps[r] = make_double2(A, B);
+}
+
+// exclusive scan of the run maps: state[r] = value of the pass just before run r (state[0] unused)
+__global__ void __launch_bounds__(EMA_SCAN_THREADS) ema_scan_kernel(const double2 *__restrict__ maps, int64_t runs,
+                                                                    double *__restrict__ state) {
+    __shared__ double sA[EMA_SCAN_THREADS], sB[EMA_SCAN_THREADS];
+    const int t = threadIdx.x;
+    const int64_t per = (runs + EMA_SCAN_THREADS - 1) / EMA_SCAN_THREADS;
+    const int64_t r0 = min((int64_t)t * per, runs), r1 = min(r0 + per, runs);
+    double A = 1.0, B = 0.0;  // composition of this thread's runs
+    for (int64_t r = r0; r < r1; ++r) {
+        const double2 m = maps[r];
+        B = m.x * B + m.y;
+        A = m.x * A;
+    }
+    sA[t] = A;
+    sB[t] = B;
+    __syncthreads();
+    for (int d = 1; d < EMA_SCAN_THREADS; d <<= 1) {  // inclusive scan of the thread maps (later after earlier)
+        double a = sA[t], b = sB[t];
+        if (t >= d) {
+            b = a * sB[t - d] + b;
+            a = a * sA[t - d];
+        }
+        __syncthreads();
+        sA[t] = a;
+        sB[t] = b;
+        __syncthreads();
+    }
+    double y = t > 0 ? sB[t - 1] : 0.0;  // value before this thread's first run (the chain starts with A = 0)
+    for (int64_t r = r0; r < r1; ++r) {
+        state[r] = y;
+        const double2 m = maps[r];
+        y = m.x * y + m.y;
+    }
+}
+
+template <class T>
+__global__ void __launch_bounds__(EMA_THREADS) ema_replay_kernel(const T *__restrict__ src, T *__restrict__ dst, int64_t n,
+                                                                 int reversed, T alpha, double c, int64_t runs,
+                                                                 const double *__restrict__ state) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= runs) return;
+    const int64_t own0 = r * EMA_RUN, p1 = min((r + 1) * EMA_RUN, n);
+    const int64_t p0 = r > 0 ? own0 - EMA_RUN : 0;  // warm-up: the run before
+    T y = r > 1 ? (T)state[r - 1] : (T)0;           // value before the warm-up run (run 0 starts the pass itself)
+    for (int64_t p = p0; p < p1; ++p) {
+        const int64_t i = ema_index(p, n, reversed);
+        const T x = src[i];
+        y = p == 0 ? x : ema_step<T>(alpha, c, x, y);
+        if (p >= own0) dst[i] = y;
+    }
+}
+
+template <class T>
+cudaError_t ema_launch(const T *x, T *tmp, T *out, int64_t n, double alpha, double2 *maps, double *state,
+                       cudaStream_t st) {
+    const int64_t runs = (n + EMA_RUN - 1) / EMA_RUN;
+    const unsigned grid = (unsigned)((runs + EMA_THREADS - 1) / EMA_THREADS);
+    const T a = (T)alpha;
+    const double c = 1.0 - (double)a;  // (1.0 - alpha) with alpha in the track's type (pyx:5752)
+    for (int pass = 0; pass < 2; ++pass) {
+        const T *src = pass == 0 ? x : tmp;
+        T *dst = pass == 0 ? tmp : out;
+        ema_run_maps_kernel<T><<<grid, EMA_THREADS, 0, st>>>(src, n, pass, a, c, runs, maps);
+        ema_scan_kernel<<<1, EMA_SCAN_THREADS, 0, st>>>(maps, runs, state);
+        ema_replay_kernel<T><<<grid, EMA_THREADS, 0, st>>>(src, dst, n, pass, a, c, runs, state);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace
+
+size_t munc_ema_workspace_bytes(int64_t n) {
+    const size_t runs = (size_t)((n + EMA_RUN - 1) / EMA_RUN) + 1;
+    return runs * 16 + runs * 8 + 64;
+}
+
+cudaError_t launch_munc_ema(const void *x, void *tmp, void *out, int64_t n, int is_double, double alpha, void *workspace,
+                            cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    const size_t runs = (size_t)((n + EMA_RUN - 1) / EMA_RUN) + 1;
+    double2 *maps = static_cast<double2 *>(workspace);
+    double *state = reinterpret_cast<double *>(maps + runs);
+    if (is_double)
+        return ema_launch<double>(static_cast<const double *>(x), static_cast<double *>(tmp), static_cast<double *>(out), n,
+                                  alpha, maps, state, st);
+    return ema_launch<float>(static_cast<const float *>(x), static_cast<float *>(tmp), static_cast<float *>(out), n, alpha,
+                             maps, state, st);
+}
 
 cudaError_t launch_munc_seed_pass(const MuncSeedArgs &a, int *invalid, cudaStream_t st) {
     cudaError_t e = cudaMemsetAsync(invalid, 0, sizeof(int), st);

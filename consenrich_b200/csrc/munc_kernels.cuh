@@ -35,6 +35,12 @@ cudaError_t launch_munc_finalize_eb(const float *local, const float *prior, cons
                                     double nu_local, double nu_prior, double vfloor, double vcap, int use_eb, float *out,
                                     MuncFinalizeStatus *status, cudaStream_t st);
 
+// cEMA (cconsenrich.pyx:5744-5759): out = the forward-then-backward exponential filter of x (float32 or
+// float64 track, n elements); tmp: n elements of scratch; workspace: munc_ema_workspace_bytes(n).
+size_t munc_ema_workspace_bytes(int64_t n);
+cudaError_t launch_munc_ema(const void *x, void *tmp, void *out, int64_t n, int is_double, double alpha, void *workspace,
+                            cudaStream_t st);
+
 // cMuncObservationMomentSeedPass (cconsenrich.pyx:4843-5040): arguments of one launch.  Matrices are
 // float32 [m][ld]; per-interval vectors float32 [n]; nullptr = absent.
 struct MuncSeedArgs {

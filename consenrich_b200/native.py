@@ -35,7 +35,7 @@ _HOT_PATH = ("cforwardPass", "cbackwardPass", "cforwardPassLevel", "cbackwardPas
 # the callers on the other side of the ECM inside an outer pass
 _BACKGROUND = ("cbackgroundWeightedStats", "cbackgroundWeightedStatsWithSupport", "csolveZeroCenteredBackground")
 # dense kernels of the observation-noise stage that produces matrixMunc
-_MUNC = ("cMuncSmoothDenseLocalEvidence", "cFinalizeMuncEBTrack", "cMuncObservationMomentSeedPass")
+_MUNC = ("cMuncSmoothDenseLocalEvidence", "cFinalizeMuncEBTrack", "cMuncObservationMomentSeedPass", "cEMA")
 
 
 def _f32(x) -> float:
@@ -691,6 +691,25 @@ def cMuncObservationMomentSeedPass(matrixData, matrixMunc, stateMean, stateVaria
         if invalid.value:
             raise ValueError("active MUNC seed cells must be finite with positive denominators")
     return (outs["moment"], outs["rho_out"], outs["omega_raw"], outs["omega_out"], outs["local"], outs["variance"])
+
+
+def cEMA(x, alpha):
+    """Forward-then-backward exponential filter of a track; signature and dtype rule of
+    cconsenrich.pyx:5897-5915 (a float32 ndarray stays float32, everything else is filtered as float64)."""
+    is_f32 = isinstance(x, np.ndarray) and x.dtype == np.float32
+    arr = np.ascontiguousarray(x, dtype=np.float32 if is_f32 else np.float64).reshape(-1)
+    n = arr.shape[0]
+    out = np.empty(n, arr.dtype)
+    if n == 0:
+        return out
+    a = _f32(alpha) if is_f32 else float(alpha)
+    if not (0.0 <= a <= 1.0):
+        # the reference's kernel refuses such an alpha and its wrapper hands back the unwritten array
+        # (pyx:5747-5748, 5908): there is no value to agree with, so say so instead
+        raise ValueError("alpha must lie in [0, 1]")
+    ctx = _ctx()
+    _lib.check(ctx._lib.cb200_host_ema(ctx.handle, _ptr(arr), n, int(not is_f32), float(alpha), _ptr(out)))
+    return out
 
 
 def cFinalizeMuncEBTrack(localVarianceTrack, priorVarianceTrack=None, countFloor=None, nuLocal=0.0, nuPrior=0.0,

@@ -20,6 +20,7 @@
  *   cMuncSmoothDenseLocalEvidence :5547-5740            cb200_host_munc_smooth_local_evidence
  *   cFinalizeMuncEBTrack :5372-5545                     cb200_host_munc_finalize_eb
  *   cMuncObservationMomentSeedPass :4843-5345           cb200_host_munc_seed_pass
+ *   cEMA :5744-5759, 5897-5915                          cb200_host_ema
  *
  * Conventions
  *   - plain C: pointers, sizes, POD structs; no torch / numpy types.
@@ -338,6 +339,16 @@ typedef struct cb200_munc_seed_args {
 CB200_API int cb200_munc_seed_pass(cb200_ctx *ctx, const cb200_munc_seed_args *args, int32_t *invalid);
 /* host arrays; *invalid is a host int32 */
 CB200_API int cb200_host_munc_seed_pass(cb200_ctx *ctx, const cb200_munc_seed_args *args, int32_t *invalid);
+
+/* cEMA (cconsenrich.pyx:5744-5759, 5897-5915): y[0] = x[0], y[i] = alpha x[i] + (1 - alpha) y[i-1] forward,
+ * then the same recurrence backward over y, for a float32 (is_double = 0; alpha rounded to float, products
+ * and sums in the reference's mixed float/double sequence) or float64 track.  The recurrence is scanned in
+ * parallel and replayed with a warm-up, so the result equals the reference's sequential loop to the
+ * tolerance its own test states (1e-6 relative for float32, 1e-14 for float64) and in practice to the last
+ * bit once (1 - alpha)^256 is below the type's resolution.  0 <= alpha <= 1 (the reference leaves `out`
+ * unwritten otherwise; here that is CB200_ERR_INVALID).  x, out: device arrays of n elements. */
+CB200_API int cb200_ema(cb200_ctx *ctx, const void *x, int64_t n, int32_t is_double, double alpha, void *out);
+CB200_API int cb200_host_ema(cb200_ctx *ctx, const void *x, int64_t n, int32_t is_double, double alpha, void *out);
 
 #ifdef __cplusplus
 }

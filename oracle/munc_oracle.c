@@ -275,3 +275,20 @@ void munc_seed_pass(const seed_args *a) {
         }
     }
 }
+
+/* _cEMA, cconsenrich.pyx:5744-5759, for real_t = float and real_t = double (the C Cython emits: alpha * x
+ * in the track's type, (1.0 - alpha) in double).  Returns 1 without writing when alpha is outside [0, 1]. */
+int munc_ema_f32(const float *x, float *out, int64_t n, float alpha) {
+    if (alpha > 1.0f || alpha < 0.0f) return 1;
+    out[0] = x[0];
+    for (int64_t i = 1; i < n; ++i) out[i] = alpha * x[i] + (1.0 - alpha) * out[i - 1];
+    for (int64_t i = n - 2; i >= 0; --i) out[i] = alpha * out[i] + (1.0 - alpha) * out[i + 1];
+    return 0;
+}
+int munc_ema_f64(const double *x, double *out, int64_t n, double alpha) {
+    if (alpha > 1.0 || alpha < 0.0) return 1;
+    out[0] = x[0];
+    for (int64_t i = 1; i < n; ++i) out[i] = alpha * x[i] + (1.0 - alpha) * out[i - 1];
+    for (int64_t i = n - 2; i >= 0; --i) out[i] = alpha * out[i] + (1.0 - alpha) * out[i + 1];
+    return 0;
+}

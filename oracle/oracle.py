@@ -22,6 +22,7 @@ and (``oracle/munc_oracle.c``) the dense kernels of the observation-noise stage:
 * ``cMuncSmoothDenseLocalEvidence``         <- cconsenrich.pyx:5547-5740
 * ``cFinalizeMuncEBTrack``                  <- cconsenrich.pyx:5365-5545
 * ``cMuncObservationMomentSeedPass``        <- cconsenrich.pyx:4767-5345
+* ``cEMA``                                  <- cconsenrich.pyx:5744-5759, 5897-5915
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may import
 this module.  The product (``consenrich_b200``) never does.
@@ -793,3 +794,22 @@ def cMuncObservationMomentSeedPass(matrixData, matrixMunc, stateMean, stateVaria
         raise ValueError("active MUNC seed cells must be finite with positive denominators")
     lib.munc_seed_pass(C.byref(a))
     return (outs["moment"], outs["rho_out"], outs["omega_raw"], outs["omega_out"], outs["local"], outs["variance"])
+
+
+def cEMA(x, alpha):
+    """cconsenrich.pyx:5897-5915; n >= 1 and 0 <= alpha <= 1 (outside that the reference is undefined)."""
+    is_f32 = isinstance(x, np.ndarray) and x.dtype == np.float32
+    arr = np.ascontiguousarray(x, dtype=np.float32 if is_f32 else np.float64).reshape(-1)
+    out = np.empty(arr.shape[0], arr.dtype)
+    lib = _L()
+    if is_f32:
+        lib.munc_ema_f32.restype = C.c_int
+        lib.munc_ema_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_float]
+        rc = lib.munc_ema_f32(arr.ctypes.data, out.ctypes.data, arr.shape[0], float(alpha))
+    else:
+        lib.munc_ema_f64.restype = C.c_int
+        lib.munc_ema_f64.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double]
+        rc = lib.munc_ema_f64(arr.ctypes.data, out.ctypes.data, arr.shape[0], float(alpha))
+    if rc:
+        raise ValueError("alpha must lie in [0, 1]")
+    return out

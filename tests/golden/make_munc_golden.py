@@ -131,6 +131,16 @@ def main():
             out[f"seed/{name}/in_{k}"] = np.asarray(v)
         for k, v in zip(SEED_OUTPUTS, res):
             out[f"seed/{name}/out_{k}"] = v
+    # cEMA: the reference's own known-answer input (tests/test_core.py:1357-1369) in both types + seeded tracks
+    ema = [("ref_case_f32", np.array([0.0, 2.0, -1.0, 5.0, 4.0, 7.0], np.float32), 0.35),
+           ("ref_case_f64", np.array([0.0, 2.0, -1.0, 5.0, 4.0, 7.0], np.float64), 0.35)]
+    for name, n, dt, alpha in (("n1_f32", 1, np.float32, 0.5), ("n3000_f32", 3000, np.float32, 2.0 / 42.0),
+                               ("n3001_f64", 3001, np.float64, 0.1), ("n1025_f32_tiny", 1025, np.float32, 1e-3),
+                               ("n700_f64_one", 700, np.float64, 1.0)):
+        ema.append((name, (0.3 + np.abs(rng.normal(size=n))).astype(dt), alpha))
+    for name, x, alpha in ema:
+        out[f"ema/{name}/x"], out[f"ema/{name}/alpha"] = x, np.float64(alpha)
+        out[f"ema/{name}/out"] = ref.cEMA(x, alpha)
     path = os.path.join(HERE, "munc_golden.npz")
     np.savez_compressed(path, **out)
     print(path, os.path.getsize(path), "bytes")

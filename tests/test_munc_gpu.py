@@ -244,3 +244,39 @@ def test_seed_pass_errors_follow_the_reference(cb, oracle):
     b = cb.cMuncObservationMomentSeedPass(ok_data, *pos[1:], **kw)
     for x, y in zip(a, b):
         np.testing.assert_array_equal(x, y)
+
+
+# ---- cEMA: affine scan + warm-up replay of the reference's own arithmetic ----
+def assert_ema_close(got, want, what):
+    """The reference's own tolerance for this function (tests/test_core.py:1364-1368): 1e-6 relative for
+    float32, 1e-14 for float64 (scaled by the track's magnitude)."""
+    assert got.dtype == want.dtype and got.shape == want.shape, what
+    scale = max(float(np.abs(want).max()), 1e-30)
+    if want.dtype == np.float32:
+        np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7 * scale, err_msg=what)
+    else:
+        np.testing.assert_allclose(got, want, rtol=1e-13, atol=1e-14 * scale, err_msg=what)
+
+
+def test_ema_matches_golden_vectors(cb):
+    for name, c in golden_cases("ema").items():
+        assert_ema_close(cb.cEMA(c["x"], float(c["alpha"])), c["out"], name)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_ema_matches_oracle_on_fresh_seeds(cb, oracle, dtype):
+    rng = np.random.default_rng(77)
+    exact = total = 0
+    for n in (1, 2, 255, 256, 257, 513, 70_001, 2_344_705):
+        for alpha in (0.35, 2.0 / 42.0, 2.0 / 2001.0, 1.0, 0.0):
+            x = (0.5 * np.sin(np.arange(n) / 50.0) + rng.normal(size=n)).astype(dtype)
+            want, got = oracle.cEMA(x, alpha), cb.cEMA(x, alpha)
+            assert_ema_close(got, want, f"n={n} alpha={alpha}")
+            if alpha >= 2.0 / 42.0:  # (1 - alpha)^256 < 4e-6: the warm-up forgets the scan's start value
+                exact += int(np.count_nonzero(got == want))
+                total += n
+    assert exact >= (1 - 1e-4) * total  # ... and then the replay is the reference's loop, bit for bit
+    assert cb.cEMA(np.arange(5), 0.5).dtype == np.float64
+    assert cb.cEMA(np.zeros(0, dtype), 0.5).shape == (0,)
+    with pytest.raises(ValueError, match="alpha must lie in"):
+        cb.cEMA(np.ones(4, dtype), 1.5)

@@ -169,3 +169,24 @@ def test_oracle_seed_pass_matches_reference_build_errors_included(oracle):
                 mod.cMuncObservationMomentSeedPass(*args, **kwargs)
             msgs.append(str(e.value))
         assert msgs[0] == msgs[1], msgs
+
+
+def test_oracle_matches_golden_ema_vectors_bitwise(oracle):
+    cases = golden_cases("ema")
+    assert len(cases) >= 7
+    for name, c in cases.items():
+        got = oracle.cEMA(c["x"], float(c["alpha"]))
+        assert got.dtype == c["out"].dtype
+        np.testing.assert_array_equal(got, c["out"], err_msg=name)
+
+
+def test_oracle_ema_matches_reference_build(oracle):
+    ref = oracle.load_reference()
+    if ref is None:
+        pytest.skip("oracle/_ref not built here")
+    rng = np.random.default_rng(2)
+    for dt in (np.float32, np.float64):
+        for n, alpha in ((1, 0.3), (2, 0.9), (257, 0.05), (50_001, 2.0 / 300.0), (4000, 0.0), (4000, 1.0)):
+            x = rng.normal(size=n).astype(dt)
+            np.testing.assert_array_equal(ref.cEMA(x, alpha), oracle.cEMA(x, alpha))
+    assert oracle.cEMA(np.arange(5), 0.5).dtype == np.float64  # everything but float32 is filtered as float64
