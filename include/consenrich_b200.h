@@ -264,7 +264,9 @@ CB200_API int cb200_background_stats(cb200_ctx *ctx, const float *resid, const f
 CB200_API int cb200_background_solve(cb200_ctx *ctx, const double *weight, const double *rhs, int64_t n, double lam,
                            double lam_first, int32_t zero_center, double *out, int64_t *bad_index,
                            double *bad_value);
-/* The same two with HOST arrays (uploads, kernels, downloads; return when the results are in place). */
+/* The same two with HOST arrays (uploads, kernels, downloads; return when the results are in place).  The
+ * degenerate shapes the reference special-cases are answered without a launch: a single interval is one
+ * division (cconsenrich.pyx:995-1006), no tracks give zero sums. */
 CB200_API int cb200_host_background_stats(cb200_ctx *ctx, const float *resid, const float *inv, int64_t m, int64_t n,
                                 double *weight, double *rhs, int64_t *support);
 CB200_API int cb200_host_background_solve(cb200_ctx *ctx, const double *weight, const double *rhs, int64_t n,
