@@ -6,6 +6,7 @@ Only what the path needs lives here:
 * ``_lib``       ctypes binding of ``lib/libconsenrich_b200.so``
 * ``native``     drop-in replacements for the six hot-path functions of ``consenrich.cconsenrich`` (and the
                  three background-track functions that call them from the other side)
+* ``driver``     device versions of the driver-side ``[tracks x intervals]`` reductions of ``consenrich.core``
 * ``device``     device-resident sweeps on torch tensors (torch is only a tensor carrier)
 * ``sharding``   chromosome / bin-range sharding across ranks (torch.distributed plumbing)
 
@@ -18,5 +19,7 @@ from .native import (cEMA, cFinalizeMuncEBTrack, cMuncObservationMomentSeedPass,
                      cbackgroundWeightedStatsWithSupport,
                      cbackwardPass, cbackwardPassLevel, cfixedBackgroundECM, cfixedBackgroundECMLevel,
                      cforwardPass, cforwardPassLevel, csolveZeroCenteredBackground, install, sweep, uninstall)
+
+from .driver import install_driver, uninstall_driver  # noqa: E402,F401
 
 __version__ = "0.1.0"

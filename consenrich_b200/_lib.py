@@ -136,6 +136,8 @@ SIGNATURES = {
                                               C.POINTER(MuncFinalizeResult)]),
     "cb200_munc_seed_pass": (C.c_int, [_vp, C.POINTER(MuncSeedArgs), _vp]),
     "cb200_host_munc_seed_pass": (C.c_int, [_vp, C.POINTER(MuncSeedArgs), C.POINTER(_i32)]),
+    "cb200_weighted_mean_residual": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _dbl, _vp]),
+    "cb200_host_weighted_mean_residual": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _dbl, _vp]),
     "cb200_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
     "cb200_host_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
 }

@@ -500,6 +500,30 @@ __global__ void __launch_bounds__(STAT_THREADS) weighted_stats_kernel(const floa
     }
 }
 
+// ---- core._relativeSignChangePerKB (core.py:2647-2700), the [m x n] part: per interval the state minus
+// the inverse-variance weighted mean of (data - background) over the tracks whose cell is valid.  numpy's
+// float64 arithmetic in its order (quotient, product, sums rounded separately): bit-identical.
+__global__ void __launch_bounds__(STAT_THREADS) weighted_mean_residual_kernel(
+    const float *__restrict__ data, const float *__restrict__ munc, int64_t m, int64_t n, int64_t ld,
+    const double *__restrict__ state, const double *__restrict__ background, double pad, double *__restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double sv = state[k], bg = background ? background[k] : 0.0;
+    const bool state_ok = isfinite(sv);
+    double total = 0.0, wsum = 0.0;
+    for (int64_t j = 0; j < m; ++j) {
+        const double d = (double)__ldcs(data + j * ld + k);
+        const double den = __dadd_rn((double)__ldcs(munc + j * ld + k), pad);
+        if (state_ok && isfinite(d) && isfinite(den) && den > 0.0) {
+            const double w = __ddiv_rn(1.0, den > 1.0e-12 ? den : 1.0e-12);
+            total = __dadd_rn(total, __dmul_rn(__dsub_rn(d, bg), w));
+            wsum = __dadd_rn(wsum, w);
+        }
+    }
+    const double mean = wsum > 0.0 ? __ddiv_rn(total, wsum) : nan("");
+    out[k] = __dsub_rn(sv, mean);
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -530,6 +554,15 @@ cudaError_t launch_background_stats(const float *resid, const float *inv, int64_
     }
     weighted_stats_kernel<<<(unsigned)((n + STAT_THREADS - 1) / STAT_THREADS), STAT_THREADS, 0, st>>>(
         resid, inv, m, n, ld, weight, rhs, support);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_weighted_mean_residual(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld,
+                                          const double *state, const double *background, double pad, double *out,
+                                          cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    weighted_mean_residual_kernel<<<(unsigned)((n + STAT_THREADS - 1) / STAT_THREADS), STAT_THREADS, 0, st>>>(
+        data, munc, m, n, ld, state, background, pad, out);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,12 @@ size_t background_workspace_bytes(int64_t n);
 cudaError_t launch_background_stats(const float *resid, const float *inv, int64_t m, int64_t n, int64_t ld,
                                     double *weight, double *rhs, unsigned long long *support, cudaStream_t st);
 
+// out[k] = state[k] - sum_j w_jk (data[j][k] - background[k]) / sum_j w_jk, w_jk = 1 / max(munc[j][k] + pad, 1e-12)
+// over the valid cells of interval k (core.py:2670-2696); NaN where no cell is valid.  background may be null.
+cudaError_t launch_weighted_mean_residual(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld,
+                                          const double *state, const double *background, double pad, double *out,
+                                          cudaStream_t st);
+
 // (diag(w) + lam_first D1'D1 + lam D2'D2) x = rhs, optionally with sum(x) = 0; n >= 2.
 // workspace: background_workspace_bytes(n) bytes of device memory; status: device BackgroundStatus.
 cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t n, double lam, double lam_first,

@@ -1251,6 +1251,45 @@ int cb200_host_background_solve(cb200_ctx *c, const double *weight, const double
     return CB200_OK;
 }
 
+// ---- driver-side reductions -------------------------------------------------------------
+int cb200_weighted_mean_residual(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n, int64_t ld,
+                                 const double *state, const double *background, double pad, double *out) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (m < 0 || n < 0 || ld < n) return fail(CB200_ERR_INVALID, "bad matrix shape");
+    if (n == 0) return CB200_OK;
+    if (!state || !out || (m > 0 && (!data || !munc))) return fail(CB200_ERR_INVALID, "NULL argument");
+    Span sp(c, FAM_BG);
+    CU_TRY(launch_weighted_mean_residual(data, munc, m, n, ld, state, background, pad, out, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_host_weighted_mean_residual(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64_t n,
+                                      const double *state, const double *background, double pad, double *out) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (n <= 0) return n < 0 ? fail(CB200_ERR_INVALID, "bad matrix shape") : CB200_OK;
+    if (!state || !out || (m > 0 && (!data || !munc))) return fail(CB200_ERR_INVALID, "NULL argument");
+    int64_t ld = round_up(n, 32), t = 0;
+    if (m > 0) {
+        CB_TRY(upload_tracks(c, c->data, data, m, n, &t));
+        CB_TRY(upload_tracks(c, c->munc, munc, m, n, &t));
+    }
+    CB_TRY(ensure(c, c->bg_w, (size_t)n * 8));
+    CB_TRY(ensure(c, c->bg_rhs, (size_t)n * 8));
+    CB_TRY(ensure(c, c->bg_out, (size_t)n * 8));
+    CB_TRY(h2d(c, c->bg_w.p, state, (size_t)n * 8));
+    if (background) CB_TRY(h2d(c, c->bg_rhs.p, background, (size_t)n * 8));
+    CB_TRY(cb200_weighted_mean_residual(c, static_cast<const float *>(c->data.p), static_cast<const float *>(c->munc.p), m, n,
+                                        ld, static_cast<const double *>(c->bg_w.p),
+                                        background ? static_cast<const double *>(c->bg_rhs.p) : nullptr, pad,
+                                        static_cast<double *>(c->bg_out.p)));
+    CB_TRY(d2h(c, out, c->bg_out.p, (size_t)n * 8));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
 // ---- observation-noise (MUNC) stage -----------------------------------------------------
 static int check_munc_smooth_args(int32_t mask_mode, int64_t window, double eps) {
     // messages of cconsenrich.pyx:5665-5668

@@ -273,6 +273,20 @@ CB200_API int cb200_host_background_solve(cb200_ctx *ctx, const double *weight, 
                                 double lam, double lam_first, int32_t zero_center, double *out,
                                 int64_t *bad_index, double *bad_value);
 
+/* ---- driver-side [tracks x intervals] reductions --------------------------- */
+/* The matrix half of core._relativeSignChangePerKB (core.py:2647-2700): out[k] = state[k] minus the
+ * inverse-variance weighted mean over the tracks of data[j][k] - background[k], weights
+ * 1 / max(munc[j][k] + pad, 1e-12), over the cells that are finite with a positive denominator; NaN where an
+ * interval has none.  float32 matrices, float64 vectors; numpy's float64 arithmetic in its order
+ * (bit-identical).  The sign-change density the reference derives from `out` is a per-interval vector
+ * operation and stays the reference's own function (core.py:2614-2644). */
+CB200_API int cb200_weighted_mean_residual(cb200_ctx *ctx, const float *data, const float *munc, int64_t m, int64_t n,
+                                 int64_t ld, const double *state, const double *background, double pad,
+                                 double *out);
+CB200_API int cb200_host_weighted_mean_residual(cb200_ctx *ctx, const float *data, const float *munc, int64_t m,
+                                      int64_t n, const double *state, const double *background, double pad,
+                                      double *out);
+
 /* ---- observation-noise (MUNC) stage: dense [tracks x intervals] kernels --------------------- */
 #define CB200_MUNC_MAX_WINDOW 8192
 /* cMuncSmoothDenseLocalEvidence (cconsenrich.pyx:5547-5740): out[j][i] = max(eps, mean of the unmasked

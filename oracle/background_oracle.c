@@ -121,3 +121,23 @@ int64_t bg_solve(double *diag, double *rhs, double *cons, double *lower, double 
     }
     return bad;
 }
+
+/* The matrix half of core._relativeSignChangePerKB, core.py:2670-2696 (numpy float64 operations, one row
+ * of the matrices at a time): out[k] = state[k] - weighted mean over the valid cells of interval k. */
+void bg_weighted_mean_residual(const float *data, const float *munc, int64_t m, int64_t n, const double *state,
+                               const double *background, double pad, double *out) {
+    for (int64_t k = 0; k < n; ++k) {
+        const double sv = state[k], bg = background ? background[k] : 0.0;
+        double total = 0.0, wsum = 0.0, mean;
+        for (int64_t j = 0; j < m; ++j) {
+            const double d = (double)data[j * n + k], den = (double)munc[j * n + k] + pad;
+            if (isfinite(sv) && isfinite(d) && isfinite(den) && den > 0.0) {
+                const double w = 1.0 / (den > 1.0e-12 ? den : 1.0e-12);
+                total += (d - bg) * w;
+                wsum += w;
+            }
+        }
+        mean = wsum > 0.0 ? total / wsum : NAN;
+        out[k] = sv - mean;
+    }
+}

@@ -813,3 +813,50 @@ def cEMA(x, alpha):
     if rc:
         raise ValueError("alpha must lie in [0, 1]")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# driver-side reductions (oracle/background_oracle.c)
+# ------------------------------------------------------------------------------------------
+def weighted_mean_residual(stateValues, matrixData, matrixMunc, background=None, pad=0.0):
+    """Matrix half of core._relativeSignChangePerKB (core.py:2670-2696): state minus the weighted mean."""
+    data = np.ascontiguousarray(matrixData, dtype=np.float32)
+    munc = np.ascontiguousarray(matrixMunc, dtype=np.float32)
+    state = np.ascontiguousarray(stateValues, dtype=np.float64).reshape(-1)
+    bg = None if background is None else np.ascontiguousarray(background, dtype=np.float64).reshape(-1)
+    m, n = data.shape
+    out = np.empty(n, np.float64)
+    lib = _L()
+    lib.bg_weighted_mean_residual.restype = None
+    lib.bg_weighted_mean_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                              C.c_double, C.c_void_p]
+    lib.bg_weighted_mean_residual(data.ctypes.data, munc.ctypes.data, m, n, state.ctypes.data,
+                                  bg.ctypes.data if bg is not None else None, float(pad), out.ctypes.data)
+    return out
+
+
+def sign_change_per_kb(values, intervalSizeBP):
+    """core._signChangePerKB (core.py:2614-2644): sign changes per kilobase among the entries that are finite and
+    at least 1 % of the mean magnitude."""
+    arr = np.asarray(values, dtype=np.float64).reshape(-1)
+    if arr.size == 0 or int(intervalSizeBP) <= 0:
+        return None
+    kept = arr[np.isfinite(arr)]
+    if kept.size == 0:
+        return None
+    floor = 0.01 * float(np.mean(np.abs(kept), dtype=np.float64))
+    if not np.isfinite(floor):
+        return None
+    if floor > 0.0:
+        kept = kept[np.abs(kept) >= floor]
+    sg = np.sign(kept)
+    sg = sg[sg != 0.0]
+    flips = int(np.count_nonzero(sg[1:] * sg[:-1] < 0.0)) if sg.size >= 2 else 0
+    span_kb = float(arr.size) * float(int(intervalSizeBP)) / 1000.0
+    value = float(flips) / span_kb
+    return value if np.isfinite(value) else None
+
+
+def relativeSignChangePerKB(stateValues, matrixData, matrixMunc, *, intervalSizeBP, background=None, pad=0.0):
+    """core._relativeSignChangePerKB (core.py:2647-2700) for float32 matrices."""
+    return sign_change_per_kb(weighted_mean_residual(stateValues, matrixData, matrixMunc, background, pad), intervalSizeBP)
