@@ -44,10 +44,16 @@ try:
     l0 = ctx.launch_count
     t_gpu, got = run()
     launches = ctx.launch_count - l0
-    pr = cProfile.Profile()
-    pr.enable()
-    run()
-    pr.disable()
+    cb.install_driver(core)
+    try:
+        run()
+        t_gpu_driver, got_driver = run()
+        pr = cProfile.Profile()
+        pr.enable()
+        run()
+        pr.disable()
+    finally:
+        cb.uninstall_driver(core)
 finally:
     cb.uninstall()
 err = float(np.abs(got[0].astype(np.float64) - want[0]).max() / np.abs(want[0]).max())
@@ -55,6 +61,8 @@ buf = io.StringIO()
 pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(14)
 print(json.dumps({"what": "core.runConsenrich, CLI defaults (fitBackground on), synthetic tracks", "tracks": m, "intervals": n,
                   "seconds_reference_kernels": t_ref, "seconds_b200_kernels": t_gpu, "speedup": t_ref / t_gpu,
+                  "seconds_b200_kernels_and_driver_hooks": t_gpu_driver, "speedup_with_driver_hooks": t_ref / t_gpu_driver,
+                  "driver_hooks_change_the_result": bool(not np.array_equal(got_driver[0], got[0])),
                   "kernel_launches": int(launches), "max_state_err_over_scale": err,
                   "final_nll": [float(want[-1]["final_nll"]), float(got[-1]["final_nll"])]}))
 print(buf.getvalue())
