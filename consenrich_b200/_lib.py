@@ -64,6 +64,14 @@ class MuncFinalizeResult(C.Structure):
                                          "invalid_count_floor")]
 
 
+class DiagGainArgs(C.Structure):
+    """cb200_diag_gain_args"""
+    _fields_ = ([(k, C.c_void_p) for k in ("covar", "p_noise", "q_scale", "proc_prec", "sum_inv_r", "sum_gain0",
+                                           "sum_gain1")]
+                + [("n", C.c_int64), ("dim", C.c_int32), ("cov_dim", C.c_int32), ("base_q", C.c_double * 4),
+                   ("f", C.c_double * 4), ("cov_init", C.c_double)])
+
+
 class MuncSeedArgs(C.Structure):
     """cb200_munc_seed_args"""
     _fields_ = ([(k, C.c_void_p) for k in ("data", "munc", "state_mean", "state_var", "background", "g_var",
@@ -138,6 +146,9 @@ SIGNATURES = {
     "cb200_host_munc_seed_pass": (C.c_int, [_vp, C.POINTER(MuncSeedArgs), C.POINTER(_i32)]),
     "cb200_weighted_mean_residual": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _dbl, _vp]),
     "cb200_host_weighted_mean_residual": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _vp, _dbl, _vp]),
+    "cb200_diag_obs_sums": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _dbl, _vp, _vp]),
+    "cb200_diag_gain": (C.c_int, [_vp, C.POINTER(DiagGainArgs)]),
+    "cb200_host_interval_diagnostics": (C.c_int, [_vp, _vp, _i64, _vp, _dbl, C.POINTER(DiagGainArgs), _vp, _vp]),
     "cb200_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
     "cb200_host_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
 }

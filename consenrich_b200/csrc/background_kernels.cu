@@ -524,6 +524,115 @@ __global__ void __launch_bounds__(STAT_THREADS) weighted_mean_residual_kernel(
     out[k] = __dsub_rn(sv, mean);
 }
 
+// ---- core._perIntervalOutputDiagnosticTracks (core.py:7734-7880): the two parts that cost time ----
+// (1) muncTrace / sumInvR: per interval, sums over the tracks of the effective observation variance and of
+//     its inverse, finite terms only (core.py:7786-7800);
+// (2) the per-interval loop over the one-step predicted covariance and the summed Kalman gain
+//     (core.py:7840-7866) -- interval k needs only the filtered covariance of interval k - 1, so the
+//     reference's Python loop of n iterations with 2x2 matrix products is one thread per interval here.
+__global__ void __launch_bounds__(STAT_THREADS) diag_obs_sums_kernel(const float *__restrict__ munc, int64_t m, int64_t n,
+                                                                     int64_t ld, const double *__restrict__ obs_prec,
+                                                                     double pad, double *__restrict__ munc_trace,
+                                                                     double *__restrict__ sum_inv_r) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double lam = obs_prec[k];
+    double tr = 0.0, si = 0.0;
+    for (int64_t j = 0; j < m; ++j) {
+        double v = __dadd_rn((double)__ldcs(munc + j * ld + k), pad);
+        if (!(v >= 1.0e-12)) v = v != v ? v : 1.0e-12;  // np.maximum propagates NaN
+        const double eff = __ddiv_rn(v, lam), inv = __ddiv_rn(lam, v);
+        if (isfinite(eff)) tr = __dadd_rn(tr, eff);
+        if (isfinite(inv)) si = __dadd_rn(si, inv);
+    }
+    munc_trace[k] = tr;
+    sum_inv_r[k] = si;
+}
+
+__global__ void __launch_bounds__(STAT_THREADS) diag_gain_kernel(const DiagGainArgs a) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    const int d = a.dim, dd = a.cov_dim * a.cov_dim;
+    // process noise of interval k (core.py:7841-7851)
+    double q00, q01 = 0.0, q10 = 0.0, q11 = 0.0;
+    bool from_track = false;
+    if (a.p_noise && k > 0) {
+        const float *pn = a.p_noise + (k - 1) * dd;
+        const double p00 = (double)pn[0];
+        bool fin = isfinite(p00);
+        if (d == 2) {
+            fin = fin && isfinite((double)pn[1]) && isfinite((double)pn[a.cov_dim]) && isfinite((double)pn[a.cov_dim + 1]);
+        }
+        if (fin) {
+            from_track = true;
+            q00 = p00;
+            if (d == 2) {
+                q01 = (double)pn[1];
+                q10 = (double)pn[a.cov_dim];
+                q11 = (double)pn[a.cov_dim + 1];
+            }
+        }
+    }
+    if (!from_track) {
+        const double s = a.q_scale[k];
+        q00 = __dmul_rn(a.base_q[0], s);
+        if (d == 2) {
+            q01 = __dmul_rn(a.base_q[1], s);
+            q10 = __dmul_rn(a.base_q[2], s);
+            q11 = __dmul_rn(a.base_q[3], s);
+        }
+        if (!(a.p_noise && k > 0) && a.proc_prec) {  // the division sits in the `else` branch of core.py:7847
+            const double kp = a.proc_prec[k];
+            q00 = __ddiv_rn(q00, kp);
+            if (d == 2) {
+                q01 = __ddiv_rn(q01, kp);
+                q10 = __ddiv_rn(q10, kp);
+                q11 = __ddiv_rn(q11, kp);
+            }
+        }
+    }
+    // filtered covariance of the interval before (the prior for k = 0)
+    double p00, p01 = 0.0, p10 = 0.0, p11 = 0.0;
+    if (k == 0) {
+        p00 = a.cov_init;
+        p11 = a.cov_init;
+    } else {
+        const float *pc = a.covar + (k - 1) * dd;
+        p00 = (double)pc[0];
+        if (d == 2) {
+            p01 = (double)pc[1];
+            p10 = (double)pc[a.cov_dim];
+            p11 = (double)pc[a.cov_dim + 1];
+        }
+    }
+    double pred00, pred10 = 0.0;
+    if (d == 2) {
+        // (F P) F' + Q, products and sums rounded separately (numpy matmul without fused multiply-add)
+        const double f00 = a.f[0], f01 = a.f[1], f10 = a.f[2], f11 = a.f[3];
+        const double t00 = __dadd_rn(__dmul_rn(f00, p00), __dmul_rn(f01, p10));
+        const double t01 = __dadd_rn(__dmul_rn(f00, p01), __dmul_rn(f01, p11));
+        const double t10 = __dadd_rn(__dmul_rn(f10, p00), __dmul_rn(f11, p10));
+        const double t11 = __dadd_rn(__dmul_rn(f10, p01), __dmul_rn(f11, p11));
+        pred00 = __dadd_rn(__dadd_rn(__dmul_rn(t00, f00), __dmul_rn(t01, f01)), q00);
+        pred10 = __dadd_rn(__dadd_rn(__dmul_rn(t10, f00), __dmul_rn(t11, f01)), q10);
+        (void)q01;
+        (void)q11;
+    } else {
+        pred00 = __dadd_rn(p00, q00);
+    }
+    if (!(pred00 > 0.0)) pred00 = pred00 != pred00 ? pred00 : 0.0;  // max(float(x), 0.0) keeps a NaN first argument
+    const double sir = a.sum_inv_r[k];
+    const double denom = __dadd_rn(1.0, __dmul_rn(pred00, sir));
+    double g0 = 0.0, g1 = 0.0;
+    if (isfinite(denom) && denom > 0.0) {
+        const double gs = __ddiv_rn(sir, denom);
+        g0 = __dmul_rn(pred00, gs);
+        g1 = __dmul_rn(pred10, gs);
+    }
+    a.sum_gain0[k] = g0;
+    a.sum_gain1[k] = g1;
+}
+
 }  // namespace
 
 // =====================================================================================
@@ -554,6 +663,20 @@ cudaError_t launch_background_stats(const float *resid, const float *inv, int64_
     }
     weighted_stats_kernel<<<(unsigned)((n + STAT_THREADS - 1) / STAT_THREADS), STAT_THREADS, 0, st>>>(
         resid, inv, m, n, ld, weight, rhs, support);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diag_obs_sums(const float *munc, int64_t m, int64_t n, int64_t ld, const double *obs_prec, double pad,
+                                 double *munc_trace, double *sum_inv_r, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    diag_obs_sums_kernel<<<(unsigned)((n + STAT_THREADS - 1) / STAT_THREADS), STAT_THREADS, 0, st>>>(munc, m, n, ld, obs_prec,
+                                                                                                  pad, munc_trace, sum_inv_r);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_diag_gain(const DiagGainArgs &a, cudaStream_t st) {
+    if (a.n <= 0) return cudaSuccess;
+    diag_gain_kernel<<<(unsigned)((a.n + STAT_THREADS - 1) / STAT_THREADS), STAT_THREADS, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -36,6 +36,25 @@ cudaError_t launch_weighted_mean_residual(const float *data, const float *munc, 
                                           const double *state, const double *background, double pad, double *out,
                                           cudaStream_t st);
 
+// core._perIntervalOutputDiagnosticTracks (core.py:7734-7880), device parts.
+// munc_trace[k] = sum_j max(munc[j][k] + pad, 1e-12) / obs_prec[k], sum_inv_r[k] = sum_j obs_prec[k] / max(...),
+// finite terms only.
+cudaError_t launch_diag_obs_sums(const float *munc, int64_t m, int64_t n, int64_t ld, const double *obs_prec, double pad,
+                                 double *munc_trace, double *sum_inv_r, cudaStream_t st);
+// summed Kalman gain of every interval from the filtered covariance of the one before it
+struct DiagGainArgs {
+    const float *covar;      // [n][cov_dim][cov_dim] filtered covariances (float32)
+    const float *p_noise;    // [n][cov_dim][cov_dim] stored process noise (Q_k at row k - 1) or nullptr
+    const double *q_scale;   // [n]
+    const double *proc_prec; // [n] clipped kappa, or nullptr
+    const double *sum_inv_r; // [n]
+    double *sum_gain0, *sum_gain1;  // [n]
+    int64_t n;
+    int32_t dim, cov_dim;    // state dimension used (1 or 2) and the stored matrices' dimension
+    double base_q[4], f[4], cov_init;
+};
+cudaError_t launch_diag_gain(const DiagGainArgs &a, cudaStream_t st);
+
 // (diag(w) + lam_first D1'D1 + lam D2'D2) x = rhs, optionally with sum(x) = 0; n >= 2.
 // workspace: background_workspace_bytes(n) bytes of device memory; status: device BackgroundStatus.
 cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t n, double lam, double lam_first,

@@ -1290,6 +1290,97 @@ int cb200_host_weighted_mean_residual(cb200_ctx *c, const float *data, const flo
     return CB200_OK;
 }
 
+int cb200_diag_obs_sums(cb200_ctx *c, const float *munc, int64_t m, int64_t n, int64_t ld, const double *obs_prec,
+                        double pad, double *munc_trace, double *sum_inv_r) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
+    if (m < 0 || n < 0 || ld < n) return fail(CB200_ERR_INVALID, "bad matrix shape");
+    if (n == 0) return CB200_OK;
+    if (!obs_prec || !munc_trace || !sum_inv_r || (m > 0 && !munc)) return fail(CB200_ERR_INVALID, "NULL argument");
+    Span sp(c, FAM_BG);
+    CU_TRY(launch_diag_obs_sums(munc, m, n, ld, obs_prec, pad, munc_trace, sum_inv_r, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+static int to_diag_args(const cb200_diag_gain_args *a, DiagGainArgs *k) {
+    if (a->n < 0 || (a->dim != 1 && a->dim != 2) || a->cov_dim < a->dim)
+        return fail(CB200_ERR_INVALID, "stateCovarForward shape does not match stateModel");
+    k->covar = a->covar; k->p_noise = a->p_noise; k->q_scale = a->q_scale; k->proc_prec = a->proc_prec;
+    k->sum_inv_r = a->sum_inv_r; k->sum_gain0 = a->sum_gain0; k->sum_gain1 = a->sum_gain1;
+    k->n = a->n; k->dim = a->dim; k->cov_dim = a->cov_dim; k->cov_init = a->cov_init;
+    for (int i = 0; i < 4; ++i) {
+        k->base_q[i] = a->base_q[i];
+        k->f[i] = a->f[i];
+    }
+    return CB200_OK;
+}
+
+int cb200_diag_gain(cb200_ctx *c, const cb200_diag_gain_args *a) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !a) return fail(CB200_ERR_INVALID, "NULL argument");
+    DiagGainArgs k{};
+    CB_TRY(to_diag_args(a, &k));
+    if (a->n == 0) return CB200_OK;
+    if (!a->covar || !a->q_scale || !a->sum_inv_r || !a->sum_gain0 || !a->sum_gain1)
+        return fail(CB200_ERR_INVALID, "NULL argument");
+    Span sp(c, FAM_BG);
+    CU_TRY(launch_diag_gain(k, c->stream));
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_host_interval_diagnostics(cb200_ctx *c, const float *munc, int64_t m, const double *obs_prec, double pad,
+                                    const cb200_diag_gain_args *a, double *munc_trace, double *sum_inv_r) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !a) return fail(CB200_ERR_INVALID, "NULL argument");
+    DiagGainArgs k{};
+    CB_TRY(to_diag_args(a, &k));
+    const int64_t n = a->n;
+    if (n == 0) return CB200_OK;
+    if (!obs_prec || !munc_trace || !sum_inv_r || (m > 0 && !munc) || !a->covar || !a->q_scale || !a->sum_gain0 ||
+        !a->sum_gain1)
+        return fail(CB200_ERR_INVALID, "NULL argument");
+    int64_t ld = round_up(n, 32);
+    if (m > 0) CB_TRY(upload_tracks(c, c->munc, munc, m, n, &ld));
+    const size_t cov_bytes = (size_t)n * a->cov_dim * a->cov_dim * 4;
+    CB_TRY(ensure(c, c->Pf, cov_bytes));
+    CB_TRY(h2d(c, c->Pf.p, a->covar, cov_bytes));
+    k.covar = static_cast<const float *>(c->Pf.p);
+    if (a->p_noise) {
+        CB_TRY(ensure(c, c->Qf, cov_bytes));
+        CB_TRY(h2d(c, c->Qf.p, a->p_noise, cov_bytes));
+        k.p_noise = static_cast<const float *>(c->Qf.p);
+    }
+    // double vectors: obs_prec, q_scale, proc_prec in; munc_trace, sum_inv_r, gains out
+    DevBuf *vec[7] = {&c->bg_w, &c->bg_rhs, &c->bg_out, &c->seed_vec[0], &c->seed_vec[1], &c->seed_vec[2], &c->seed_vec[3]};
+    for (DevBuf *b : vec) CB_TRY(ensure(c, *b, (size_t)n * 8));
+    double *d_obs = static_cast<double *>(vec[0]->p), *d_qs = static_cast<double *>(vec[1]->p);
+    double *d_pp = static_cast<double *>(vec[2]->p), *d_tr = static_cast<double *>(vec[3]->p);
+    double *d_si = static_cast<double *>(vec[4]->p), *d_g0 = static_cast<double *>(vec[5]->p);
+    double *d_g1 = static_cast<double *>(vec[6]->p);
+    CB_TRY(h2d(c, d_obs, obs_prec, (size_t)n * 8));
+    CB_TRY(h2d(c, d_qs, a->q_scale, (size_t)n * 8));
+    if (a->proc_prec) CB_TRY(h2d(c, d_pp, a->proc_prec, (size_t)n * 8));
+    CB_TRY(cb200_diag_obs_sums(c, static_cast<const float *>(c->munc.p), m, n, ld, d_obs, pad, d_tr, d_si));
+    k.q_scale = d_qs;
+    k.proc_prec = a->proc_prec ? d_pp : nullptr;
+    k.sum_inv_r = d_si;
+    k.sum_gain0 = d_g0;
+    k.sum_gain1 = d_g1;
+    {
+        Span sp(c, FAM_BG);
+        CU_TRY(launch_diag_gain(k, c->stream));
+    }
+    c->launches += 1;
+    CB_TRY(d2h(c, munc_trace, d_tr, (size_t)n * 8));
+    CB_TRY(d2h(c, sum_inv_r, d_si, (size_t)n * 8));
+    CB_TRY(d2h(c, a->sum_gain0, d_g0, (size_t)n * 8));
+    CB_TRY(d2h(c, a->sum_gain1, d_g1, (size_t)n * 8));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
 // ---- observation-noise (MUNC) stage -----------------------------------------------------
 static int check_munc_smooth_args(int32_t mask_mode, int64_t window, double eps) {
     // messages of cconsenrich.pyx:5665-5668

@@ -287,6 +287,33 @@ CB200_API int cb200_host_weighted_mean_residual(cb200_ctx *ctx, const float *dat
                                       int64_t n, const double *state, const double *background, double pad,
                                       double *out);
 
+/* The two costly parts of core._perIntervalOutputDiagnosticTracks (core.py:7734-7880; run once per fit when
+ * precision diagnostics are requested):
+ *   munc_trace[k] = sum_j v_jk / obs_prec[k],  sum_inv_r[k] = sum_j obs_prec[k] / v_jk,  v_jk = max(munc[j][k] + pad,
+ *   1e-12), finite terms only (core.py:7786-7800);
+ *   sum_gain0/1[k]: the level / trend entries of the summed Kalman gain from the one-step prediction of the
+ *   filtered covariance of interval k - 1 (the prior cov_init I for k = 0), core.py:7840-7866 -- the reference's
+ *   Python loop over all intervals, here one thread per interval.
+ * float32 matrices, float64 vectors in and out; float64 arithmetic, separately rounded operations. */
+typedef struct cb200_diag_gain_args {
+    const float *covar;       /* [n][cov_dim][cov_dim] stateCovarForward */
+    const float *p_noise;     /* [n][cov_dim][cov_dim] pNoiseForward (Q_k at row k-1) or NULL */
+    const double *q_scale;    /* [n] processQScale (ones when absent) */
+    const double *proc_prec;  /* [n] clipped processPrecExp or NULL (then p_noise, when given, is used) */
+    const double *sum_inv_r;  /* [n] */
+    double *sum_gain0, *sum_gain1; /* [n] */
+    int64_t n;
+    int32_t dim, cov_dim;     /* state dimension (1 or 2), dimension of the stored matrices (>= dim) */
+    double base_q[4], f[4], cov_init;
+} cb200_diag_gain_args;
+CB200_API int cb200_diag_obs_sums(cb200_ctx *ctx, const float *munc, int64_t m, int64_t n, int64_t ld,
+                        const double *obs_prec, double pad, double *munc_trace, double *sum_inv_r);
+CB200_API int cb200_diag_gain(cb200_ctx *ctx, const cb200_diag_gain_args *args);
+/* both, with HOST arrays (munc contiguous [m][n]); args->sum_inv_r is ignored (it is computed here) */
+CB200_API int cb200_host_interval_diagnostics(cb200_ctx *ctx, const float *munc, int64_t m, const double *obs_prec,
+                                    double pad, const cb200_diag_gain_args *args, double *munc_trace,
+                                    double *sum_inv_r);
+
 /* ---- observation-noise (MUNC) stage: dense [tracks x intervals] kernels --------------------- */
 #define CB200_MUNC_MAX_WINDOW 8192
 /* cMuncSmoothDenseLocalEvidence (cconsenrich.pyx:5547-5740): out[j][i] = max(eps, mean of the unmasked

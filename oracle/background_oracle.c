@@ -141,3 +141,70 @@ void bg_weighted_mean_residual(const float *data, const float *munc, int64_t m, 
         out[k] = sv - mean;
     }
 }
+
+/* core._perIntervalOutputDiagnosticTracks, core.py:7786-7800: per-interval sums over the tracks of the effective
+ * observation variance and of its inverse, finite terms only. */
+void bg_diag_obs_sums(const float *munc, int64_t m, int64_t n, const double *obs_prec, double pad, double *munc_trace,
+                      double *sum_inv_r) {
+    for (int64_t k = 0; k < n; ++k) {
+        double tr = 0.0, si = 0.0;
+        for (int64_t j = 0; j < m; ++j) {
+            double v = (double)munc[j * n + k] + pad, eff, inv;
+            if (!(v >= 1.0e-12)) v = v != v ? v : 1.0e-12; /* np.maximum keeps NaN */
+            eff = v / obs_prec[k];
+            inv = obs_prec[k] / v;
+            if (isfinite(eff)) tr += eff;
+            if (isfinite(inv)) si += inv;
+        }
+        munc_trace[k] = tr;
+        sum_inv_r[k] = si;
+    }
+}
+
+/* the per-interval loop of core.py:7840-7866.  covar, p_noise: float32 [n][c][c]; p_noise / proc_prec may be NULL */
+void bg_diag_gain(const float *covar, const float *p_noise, const double *q_scale, const double *proc_prec,
+                  const double *sum_inv_r, int64_t n, int dim, int c, const double *base_q, const double *f,
+                  double cov_init, double *gain0, double *gain1) {
+    double prev[4] = {cov_init, 0.0, 0.0, cov_init};
+    for (int64_t k = 0; k < n; ++k) {
+        double q[4] = {0, 0, 0, 0}, pred00, pred10 = 0.0, denom;
+        int from_track = 0;
+        if (p_noise && k > 0) {
+            const float *pn = p_noise + (k - 1) * c * c;
+            int fin = isfinite((double)pn[0]);
+            if (dim == 2) fin = fin && isfinite((double)pn[1]) && isfinite((double)pn[c]) && isfinite((double)pn[c + 1]);
+            if (fin) {
+                from_track = 1;
+                q[0] = (double)pn[0];
+                if (dim == 2) { q[1] = (double)pn[1]; q[2] = (double)pn[c]; q[3] = (double)pn[c + 1]; }
+            }
+        }
+        if (!from_track) {
+            for (int i = 0; i < dim * dim; ++i) q[i] = base_q[i] * q_scale[k];
+            if (!(p_noise && k > 0) && proc_prec)
+                for (int i = 0; i < dim * dim; ++i) q[i] /= proc_prec[k];
+        }
+        if (dim == 2) {
+            const double t00 = f[0] * prev[0] + f[1] * prev[2], t01 = f[0] * prev[1] + f[1] * prev[3];
+            const double t10 = f[2] * prev[0] + f[3] * prev[2], t11 = f[2] * prev[1] + f[3] * prev[3];
+            pred00 = (t00 * f[0] + t01 * f[1]) + q[0];
+            pred10 = (t10 * f[0] + t11 * f[1]) + q[2];
+        } else {
+            pred00 = prev[0] + q[0];
+        }
+        if (!(pred00 > 0.0)) pred00 = pred00 != pred00 ? pred00 : 0.0;
+        denom = 1.0 + pred00 * sum_inv_r[k];
+        gain0[k] = gain1[k] = 0.0;
+        if (isfinite(denom) && denom > 0.0) {
+            const double gs = sum_inv_r[k] / denom;
+            gain0[k] = pred00 * gs;
+            gain1[k] = pred10 * gs;
+        }
+        prev[0] = (double)covar[k * c * c];
+        if (dim == 2) {
+            prev[1] = (double)covar[k * c * c + 1];
+            prev[2] = (double)covar[k * c * c + c];
+            prev[3] = (double)covar[k * c * c + c + 1];
+        }
+    }
+}

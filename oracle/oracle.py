@@ -860,3 +860,28 @@ def sign_change_per_kb(values, intervalSizeBP):
 def relativeSignChangePerKB(stateValues, matrixData, matrixMunc, *, intervalSizeBP, background=None, pad=0.0):
     """core._relativeSignChangePerKB (core.py:2647-2700) for float32 matrices."""
     return sign_change_per_kb(weighted_mean_residual(stateValues, matrixData, matrixMunc, background, pad), intervalSizeBP)
+
+
+def interval_diagnostics(covar, munc, obs_prec, q_scale, proc_prec, p_noise, base_q, f, state_dim, cov_init, pad):
+    """muncTrace, sumInvR, sumGain0, sumGain1 (float64 [n]) of core._perIntervalOutputDiagnosticTracks
+    (core.py:7786-7866); arguments as consenrich_b200.driver.interval_diagnostics."""
+    covar = np.ascontiguousarray(covar, dtype=np.float32)
+    munc = np.ascontiguousarray(munc, dtype=np.float32)
+    n, c = covar.shape[0], covar.shape[1]
+    vec = lambda v: None if v is None else np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+    obs_prec, q_scale, proc_prec = vec(obs_prec), vec(q_scale), vec(proc_prec)
+    p_noise = None if p_noise is None else np.ascontiguousarray(p_noise, dtype=np.float32)
+    bq = np.ascontiguousarray(np.asarray(base_q, dtype=np.float64)[:state_dim, :state_dim]).reshape(-1)
+    ff = np.ascontiguousarray(np.asarray(f, dtype=np.float64)).reshape(-1) if state_dim == 2 else np.zeros(4)
+    outs = [np.empty(n, np.float64) for _ in range(4)]
+    lib = _L()
+    vp = C.c_void_p
+    lib.bg_diag_obs_sums.restype = None
+    lib.bg_diag_obs_sums.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_double, vp, vp]
+    lib.bg_diag_gain.restype = None
+    lib.bg_diag_gain.argtypes = [vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp, C.c_double, vp, vp]
+    ptr = lambda a: None if a is None else a.ctypes.data
+    lib.bg_diag_obs_sums(ptr(munc), munc.shape[0], n, ptr(obs_prec), float(pad), ptr(outs[0]), ptr(outs[1]))
+    lib.bg_diag_gain(ptr(covar), ptr(p_noise), ptr(q_scale), ptr(proc_prec), ptr(outs[1]), n, int(state_dim), int(c),
+                     ptr(bq), ptr(ff), float(cov_init), ptr(outs[2]), ptr(outs[3]))
+    return outs

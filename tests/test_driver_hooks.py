@@ -93,3 +93,110 @@ def test_hook_installed_into_the_reference_driver():
         driver.uninstall_driver(core)
     assert core._relativeSignChangePerKB is original
     assert got == want and got64 == want64
+
+
+# ---- core._perIntervalOutputDiagnosticTracks (core.py:7734-7880) ----
+def diag_inputs(rng, m, n, dim, variant):
+    covar = np.zeros((n, 2, 2), np.float32)
+    covar[:, 0, 0] = rng.uniform(0.01, 1.0, n)
+    covar[:, 1, 1] = rng.uniform(0.001, 0.1, n)
+    covar[:, 0, 1] = covar[:, 1, 0] = rng.uniform(-0.005, 0.005, n)
+    if dim == 1:
+        covar = np.ascontiguousarray(covar[:, :1, :1])
+    munc = rng.uniform(0.05, 1.0, (m, n)).astype(np.float32)
+    munc[rng.random((m, n)) < 0.02] = np.float32(1e30)
+    kw = dict(stateCovarForward=covar, matrixMunc=munc, matrixQ0=np.diag([2e-3, 4e-4]).astype(np.float32),
+              matrixF=np.array([[1, 1], [0, 1]], np.float32), stateCovarInit=1000.0,
+              stateModel="level" if dim == 1 else "level_trend", lambdaExp=None, processPrecExp=None, processQScale=None,
+              pNoiseForward=None, pad=1e-4, obsPrecisionMultiplierMin=0.1, obsPrecisionMultiplierMax=10.0,
+              procPrecisionMultiplierMin=5e-3, procPrecisionMultiplierMax=5e3)
+    if variant in ("kappa", "all"):
+        kw["processPrecExp"] = np.exp(rng.normal(0, 1.5, n)).astype(np.float32)
+    if variant in ("lambda", "all"):
+        kw["lambdaExp"] = rng.uniform(0.05, 20.0, n).astype(np.float32)
+    if variant in ("qscale", "all"):
+        qs = rng.uniform(0.5, 2.0, n).astype(np.float32)
+        qs[0] = 1.0
+        kw["processQScale"] = qs
+    if variant == "pnoise":
+        pn = (covar * 0.01).astype(np.float32)
+        if n > 20:
+            pn[7] = np.nan  # falls back to Q0 * qScale for interval 8
+        kw["pNoiseForward"] = pn
+    return kw
+
+
+def diag_state_model(core, dim):
+    return core.STATE_MODEL_LEVEL if dim == 1 else [getattr(core, k) for k in dir(core)
+                                                    if k.startswith("STATE_MODEL_") and k != "STATE_MODEL_LEVEL"
+                                                    and isinstance(getattr(core, k), str)][0]
+
+
+def test_oracle_interval_diagnostics_match_the_reference_function(oracle):
+    core = ref_core()
+    rng = np.random.default_rng(5)
+    for dim in (2, 1):
+        for variant in ("plain", "kappa", "lambda", "qscale", "pnoise", "all"):
+            kw = diag_inputs(rng, 3, 400, dim, variant)
+            kw["stateModel"] = diag_state_model(core, dim)
+            want = core._perIntervalOutputDiagnosticTracks(**kw)
+            n = kw["stateCovarForward"].shape[0]
+            obs = np.ones(n) if kw["lambdaExp"] is None else np.clip(np.asarray(kw["lambdaExp"], np.float64), 0.1, 10.0)
+            pp = None if kw["processPrecExp"] is None else np.clip(np.asarray(kw["processPrecExp"], np.float64), 5e-3, 5e3)
+            pn = None if (kw["pNoiseForward"] is None or pp is not None) else kw["pNoiseForward"]
+            tr, _, g0, g1 = oracle.interval_diagnostics(kw["stateCovarForward"], kw["matrixMunc"], obs,
+                                                        np.asarray(want["processQScale"], np.float64), pp, pn,
+                                                        np.asarray(kw["matrixQ0"], np.float64), kw["matrixF"], dim, 1000.0, 1e-4)
+            for name, got in (("muncTrace", tr), ("sumGain0", g0), ("sumGain1", g1)):
+                np.testing.assert_allclose(got.astype(np.float32), want[name], rtol=3e-7, atol=0, err_msg=f"{dim} {variant} {name}")
+
+
+@pytest.mark.gpu
+def test_device_interval_diagnostics_match_oracle_bitwise(oracle):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from consenrich_b200 import driver
+    rng = np.random.default_rng(6)
+    for dim in (2, 1):
+        for m, n in ((1, 1), (3, 33), (10, 70_001), (6, 600_001)):
+            for variant in ("plain", "kappa", "pnoise", "all"):
+                kw = diag_inputs(rng, m, n, dim, variant)
+                obs = np.ones(n) if kw["lambdaExp"] is None else np.clip(np.asarray(kw["lambdaExp"], np.float64), 0.1, 10.0)
+                qs = np.ones(n) if kw["processQScale"] is None else np.asarray(kw["processQScale"], np.float64)
+                pp = None if kw["processPrecExp"] is None else np.clip(np.asarray(kw["processPrecExp"], np.float64), 5e-3, 5e3)
+                pn = None if (kw["pNoiseForward"] is None or pp is not None) else kw["pNoiseForward"]
+                args = (kw["stateCovarForward"], kw["matrixMunc"], obs, qs, pp, pn, np.asarray(kw["matrixQ0"], np.float64),
+                        kw["matrixF"], dim, 1000.0, 1e-4)
+                for got, want in zip(driver.interval_diagnostics(*args), oracle.interval_diagnostics(*args)):
+                    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.gpu
+def test_interval_diagnostics_hook_in_the_reference_driver():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    core = ref_core()
+    from consenrich_b200 import driver
+    rng = np.random.default_rng(7)
+    cases = []
+    for dim in (2, 1):
+        for variant in ("plain", "kappa", "lambda", "qscale", "pnoise", "all"):
+            kw = diag_inputs(rng, 5, 20_000, dim, variant)
+            kw["stateModel"] = diag_state_model(core, dim)
+            cases.append((kw, core._perIntervalOutputDiagnosticTracks(**kw)))
+    driver.install_driver(core)
+    try:
+        for kw, want in cases:
+            got = core._perIntervalOutputDiagnosticTracks(**kw)
+            assert list(got) == list(want)
+            for name in want:
+                assert got[name].dtype == np.float32 and got[name].shape == want[name].shape
+                # float32 outputs of float64 arithmetic: equal up to the last float32 bit (numpy's 2x2 matrix
+                # product may fuse multiply-adds; the kernel rounds every operation)
+                np.testing.assert_allclose(got[name], want[name], rtol=3e-7, atol=0, err_msg=name)
+        with pytest.raises(ValueError, match="matrixMunc must have shape"):
+            core._perIntervalOutputDiagnosticTracks(**{**cases[0][0], "matrixMunc": cases[0][0]["matrixMunc"][:, :-1]})
+    finally:
+        driver.uninstall_driver(core)
