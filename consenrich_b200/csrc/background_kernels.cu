@@ -108,9 +108,10 @@ struct Level0 {
     const double *w, *rhs;
     int64_t n;
     double lam, lam1;
+    const double *rhs2;  // second right-hand side; nullptr: the vector of ones
 };
 __device__ __forceinline__ Row build_row(const Level0 &a, int64_t i, BackgroundStatus *st) {
-    const double *w = a.w, *rhs = a.rhs;
+    const double *w = a.w, *rhs = a.rhs, *rhs2 = a.rhs2;
     const int64_t n = a.n, k = 2 * i;
     const double lam = a.lam, lam1 = a.lam1;
     Row r;
@@ -123,9 +124,9 @@ __device__ __forceinline__ Row build_row(const Level0 &a, int64_t i, BackgroundS
     r.u10 = mat_off1(n, k + 1, lam, lam1);
     r.u11 = mat_off2(n, k + 1, lam);
     r.b00 = rhs[k];
-    r.b01 = 1.0;
+    r.b01 = rhs2 ? rhs2[k] : 1.0;
     r.b10 = (k + 1 < n) ? rhs[k + 1] : 0.0;
-    r.b11 = (k + 1 < n) ? 1.0 : 0.0;
+    r.b11 = (k + 1 < n) ? (rhs2 ? rhs2[k + 1] : 1.0) : 0.0;
     return r;
 }
 
@@ -411,6 +412,55 @@ __global__ void __launch_bounds__(BG_MID_THREADS) mid_system_kernel(const MidArg
     }
 }
 
+// ---- one step of iterative refinement ----
+// Block cyclic reduction is backward stable, but on systems with long stretches of zero weight (masked
+// regions: only the roughness penalty holds the solution there) its error constant is ~50x that of the
+// reference's sequential LDL'.  One refinement step -- residual of both right-hand sides in float64, a
+// second solve for the correction -- brings it to the LDL' level (measured with an extended-precision
+// yardstick; further steps gain nothing, the residual itself is the limit).
+__global__ void __launch_bounds__(256) penta_residual_kernel(const double *__restrict__ w, const double *__restrict__ rhs,
+                                                             int64_t n, double lam, double lam1,
+                                                             const double *__restrict__ x, double *__restrict__ r0,
+                                                             double *__restrict__ r1, BackgroundStatus *st) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    auto col = [&](int64_t u) { return *reinterpret_cast<const double2 *>(x + (u >> 1) * 4 + (u & 1) * 2); };
+    const double2 xk = col(k);
+    const double ad = mat_diag(w, n, k, lam, lam1, st);
+    double a0 = ad * xk.x, a1 = ad * xk.y;
+    if (k >= 1) {
+        const double b = mat_off1(n, k - 1, lam, lam1);
+        const double2 v = col(k - 1);
+        a0 = fma(b, v.x, a0);
+        a1 = fma(b, v.y, a1);
+    }
+    if (k + 1 < n) {
+        const double b = mat_off1(n, k, lam, lam1);
+        const double2 v = col(k + 1);
+        a0 = fma(b, v.x, a0);
+        a1 = fma(b, v.y, a1);
+    }
+    if (k >= 2) {
+        const double c = mat_off2(n, k - 2, lam);
+        const double2 v = col(k - 2);
+        a0 = fma(c, v.x, a0);
+        a1 = fma(c, v.y, a1);
+    }
+    if (k + 2 < n) {
+        const double c = mat_off2(n, k, lam);
+        const double2 v = col(k + 2);
+        a0 = fma(c, v.x, a0);
+        a1 = fma(c, v.y, a1);
+    }
+    r0[k] = rhs[k] - a0;
+    r1[k] = 1.0 - a1;
+}
+
+__global__ void __launch_bounds__(256) accumulate_kernel(double *__restrict__ acc, const double *__restrict__ add, int64_t count) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) acc[i] += add[i];
+}
+
 // ---- zero-sum constraint: column sums of X, then out = x0 - mu x1 ----
 constexpr int SUM_THREADS = 256;
 
@@ -651,7 +701,9 @@ size_t background_workspace_bytes(int64_t n) {
         if (rows <= 1) break;
         rows = (rows + 1) / 2;
     }
-    return (size_t)total_rows * ROW * 8 + (size_t)total_x * 4 * 8 + (size_t)(BG_SUM_BLOCKS * 2 + 2) * 8 + 256;
+    // + the accumulated solution and the two residual vectors of the refinement step
+    const size_t refine = (size_t)background_rows(n) * 4 * 8 + 2 * (size_t)(n + 2) * 8;
+    return (size_t)total_rows * ROW * 8 + (size_t)total_x * 4 * 8 + refine + (size_t)(BG_SUM_BLOCKS * 2 + 2) * 8 + 256;
 }
 
 cudaError_t launch_background_stats(const float *resid, const float *inv, int64_t m, int64_t n, int64_t ld,
@@ -722,11 +774,18 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
         x[l] = p;
         p += rows[l] * 4;
     }
+    double *x_acc = p;  // refinement: the accumulated solution, then the two residual vectors
+    p += rows[0] * 4;
+    double *res0 = p;
+    p += n + 2;
+    double *res1 = p;
+    p += n + 2;
     double *partial = p;
+    Level0 l0{w, rhs, n, lam, lam_first, nullptr};
     auto level = [&](int l) {
         Rows r{};
         r.stored = lvl[l];
-        r.l0 = Level0{w, rhs, n, lam, lam_first};
+        r.l0 = l0;
         return r;
     };
     cudaError_t e = cudaMemsetAsync(status, 0x7f, sizeof(BackgroundStatus), st);  // bad_index = STATUS_NONE
@@ -750,54 +809,78 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
         coop = 0;
         first_mid = first_small;
     }
-    for (int l = 0; l < first_mid; ++l) {
-        reduce_kernel<<<(unsigned)((rows[l + 1] + T - 1) / T), T, 0, st>>>(level(l), rows[l], rows[l + 1], stride[l],
-                                                                         lvl[l + 1], status);
-        ++count;
-    }
-    if (coop) {
-        MidArgs ma{};
-        for (int l = 0; l <= first_small; ++l) {
-            ma.lvl[l] = lvl[l];
-            ma.x[l] = x[l];
-            ma.rows[l] = rows[l];
-            ma.stride[l] = stride[l];
+    // one pass down and up the levels for the right-hand sides in l0; the solution lands in x[0]
+    auto run_levels = [&]() -> cudaError_t {
+        for (int l = 0; l < first_mid; ++l) {
+            reduce_kernel<<<(unsigned)((rows[l + 1] + T - 1) / T), T, 0, st>>>(level(l), rows[l], rows[l + 1], stride[l],
+                                                                             lvl[l + 1], status);
+            ++count;
         }
-        ma.l0 = Level0{w, rhs, n, lam, lam_first};
-        ma.first = first_mid;
-        ma.small = first_small;
-        int64_t want = (rows[first_mid] + BG_MID_THREADS - 1) / BG_MID_THREADS;
-        const int64_t cap = (int64_t)sms * per_sm;
-        if (want > cap) want = cap;
-        if (want < 1) want = 1;
-        BackgroundStatus *stp = status;
-        void *kargs[] = {&ma, &stp};
-        e = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(mid_system_kernel), dim3((unsigned)want), dim3(BG_MID_THREADS),
-                                        kargs, tail_smem, st);
+        if (coop) {
+            MidArgs ma{};
+            for (int l = 0; l <= first_small; ++l) {
+                ma.lvl[l] = lvl[l];
+                ma.x[l] = x[l];
+                ma.rows[l] = rows[l];
+                ma.stride[l] = stride[l];
+            }
+            ma.l0 = l0;
+            ma.first = first_mid;
+            ma.small = first_small;
+            int64_t want = (rows[first_mid] + BG_MID_THREADS - 1) / BG_MID_THREADS;
+            const int64_t cap = (int64_t)sms * per_sm;
+            if (want > cap) want = cap;
+            if (want < 1) want = 1;
+            BackgroundStatus *stp = status;
+            void *kargs[] = {&ma, &stp};
+            cudaError_t ec = cudaLaunchCooperativeKernel(reinterpret_cast<void *>(mid_system_kernel), dim3((unsigned)want),
+                                                         dim3(BG_MID_THREADS), kargs, tail_smem, st);
+            if (ec != cudaSuccess) return ec;
+            ++count;
+        } else {
+            // per device, so set on every call (a few hundred nanoseconds)
+            cudaError_t ec = cudaFuncSetAttribute(small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  BG_SMALL_ROWS * SROW * 8);
+            if (ec != cudaSuccess) return ec;
+            small_system_kernel<<<1, 1024, tail_smem, st>>>(level(first_small), rows[first_small], stride[first_small],
+                                                           x[first_small], status);
+            ++count;
+        }
+        for (int l = first_mid - 1; l >= 0; --l) {
+            backsub_kernel<<<(unsigned)((rows[l] + T - 1) / T), T, 0, st>>>(level(l), rows[l], x[l + 1], x[l], status,
+                                                                          stride[l]);
+            ++count;
+        }
+        return cudaGetLastError();
+    };
+    e = run_levels();
+    if (e != cudaSuccess) return e;
+    const double *solution = x[0];
+    if (!getenv("CB200_BG_NO_REFINE")) {
+        // one refinement step: X += A^-1 (B - A X) for both right-hand sides
+        const int64_t xcount = rows[0] * 4;
+        e = cudaMemcpyAsync(x_acc, x[0], (size_t)xcount * 8, cudaMemcpyDeviceToDevice, st);
         if (e != cudaSuccess) return e;
+        penta_residual_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(w, rhs, n, lam, lam_first, x_acc, res0, res1, status);
         ++count;
-    } else {
-        // per device, so set on every call (a few hundred nanoseconds)
-        e = cudaFuncSetAttribute(small_system_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BG_SMALL_ROWS * SROW * 8);
+        l0.rhs = res0;
+        l0.rhs2 = res1;
+        e = run_levels();
         if (e != cudaSuccess) return e;
-        small_system_kernel<<<1, 1024, tail_smem, st>>>(level(first_small), rows[first_small], stride[first_small],
-                                                       x[first_small], status);
+        accumulate_kernel<<<(unsigned)((xcount + T - 1) / T), T, 0, st>>>(x_acc, x[0], xcount);
         ++count;
-    }
-    for (int l = first_mid - 1; l >= 0; --l) {
-        backsub_kernel<<<(unsigned)((rows[l] + T - 1) / T), T, 0, st>>>(level(l), rows[l], x[l + 1], x[l], status, stride[l]);
-        ++count;
+        solution = x_acc;
     }
     double *mu = nullptr;
     if (zero_center) {
         int nparts = (int)((n + SUM_THREADS - 1) / SUM_THREADS);
         if (nparts > BG_SUM_BLOCKS) nparts = BG_SUM_BLOCKS;
         mu = partial + 2 * BG_SUM_BLOCKS;
-        column_sums_kernel<<<nparts, SUM_THREADS, 0, st>>>(x[0], n, partial);
+        column_sums_kernel<<<nparts, SUM_THREADS, 0, st>>>(solution, n, partial);
         mu_kernel<<<1, SUM_THREADS, 0, st>>>(partial, nparts, n, mu);
         count += 2;
     }
-    finish_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(x[0], n, mu, out);
+    finish_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(solution, n, mu, out);
     ++count;
     if (launches) *launches += count;
     return cudaGetLastError();

@@ -107,6 +107,24 @@ def test_solve_at_chromosome_lengths_satisfies_the_system(cb):
         assert np.abs(rhs - penalised_matvec(w, lam, lam1, y)).max() <= 1e-10 * scale
 
 
+def test_solve_with_long_masked_stretches_stays_at_the_reference_accuracy(cb, oracle):
+    """Thousands of consecutive intervals without weight (masked regions): only the roughness penalty holds the
+    solution there and the system's conditioning grows with the fourth power of the stretch.  The reference's
+    own LDL' is then accurate to ~1e-8 (1 000 intervals) / ~1e-5 (5 000) of scale against an extended-precision
+    solve; plain block cyclic reduction is ~50x worse, which is why the solve ends with one refinement step.
+    Stated tolerance: ten times the reference's own error at each length."""
+    from golden.make_background_golden import background_inputs
+    rng = np.random.default_rng(44)
+    for gap, tol in ((1000, 1e-7), (5000, 1e-4)):
+        n = 30_001
+        w, rhs = background_inputs(rng, n)
+        w[n // 2: n // 2 + gap] = 0.0
+        for zc in (False, True):
+            want = oracle.csolveZeroCenteredBackground(w, rhs, 128.0, zc)
+            got = cb.csolveZeroCenteredBackground(w, rhs, 128.0, zc)
+            assert np.abs(got - want).max() <= tol * np.abs(want).max(), (gap, zc)
+
+
 def test_solve_errors_and_edge_cases_follow_the_reference(cb, oracle):
     w = np.ones(4)
     with pytest.raises(ValueError, match="weightTrack and rhsTrack must have the same length"):
