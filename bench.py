@@ -27,6 +27,9 @@ collective on the data path), so scaling is weak and `value` is the sum over ran
              single-threaded).
 `l_sweep`  : the single forward + backward sweep (fold + filter + smoother + residuals), device-resident
              and through the host API, for reference.
+`background` : (N = 1) the rows next to the path at the same size, device-resident and through the host API, with
+             the reference's functions timed on one core beside them: background statistics + penalised solve,
+             and the variance-stage kernels (seed pass, rolling mean, finalisation).
 """
 from __future__ import annotations
 
