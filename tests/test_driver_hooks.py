@@ -200,3 +200,33 @@ def test_interval_diagnostics_hook_in_the_reference_driver():
             core._perIntervalOutputDiagnosticTracks(**{**cases[0][0], "matrixMunc": cases[0][0]["matrixMunc"][:, :-1]})
     finally:
         driver.uninstall_driver(core)
+
+
+def test_hooks_pass_uncovered_inputs_to_the_functions_they_replace():
+    """No GPU needed: float64 matrices are not covered on the device, so the installed hooks hand them to the
+    reference's own functions; uninstall restores the originals."""
+    core = ref_core()
+    from consenrich_b200 import driver
+    rng = np.random.default_rng(10)
+    state, data, munc, bg = sign_change_inputs(rng, 3, 500)
+    kw = diag_inputs(rng, 3, 300, 2, "all")
+    kw["stateModel"] = diag_state_model(core, 2)
+    kw64 = {**kw, "stateCovarForward": kw["stateCovarForward"].astype(np.float64)}
+    originals = (core._relativeSignChangePerKB, core._perIntervalOutputDiagnosticTracks)
+    want_sign = core._relativeSignChangePerKB(state, data.astype(np.float64), munc.astype(np.float64), intervalSizeBP=25,
+                                              background=bg, pad=1e-4)
+    want_diag = core._perIntervalOutputDiagnosticTracks(**kw64)
+    driver.install_driver(core)
+    try:
+        assert core._relativeSignChangePerKB is not originals[0]
+        assert core._perIntervalOutputDiagnosticTracks is not originals[1]
+        got_sign = core._relativeSignChangePerKB(state, data.astype(np.float64), munc.astype(np.float64), intervalSizeBP=25,
+                                                 background=bg, pad=1e-4)
+        got_diag = core._perIntervalOutputDiagnosticTracks(**kw64)
+        assert core._relativeSignChangePerKB(state, None, munc, intervalSizeBP=25) is None
+    finally:
+        driver.uninstall_driver(core)
+    assert (core._relativeSignChangePerKB, core._perIntervalOutputDiagnosticTracks) == originals
+    assert got_sign == want_sign
+    for k in want_diag:
+        np.testing.assert_array_equal(got_diag[k], want_diag[k])
