@@ -16,7 +16,8 @@ OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
 ABI_VERSION = 2
 
 FAM_FOLD, FAM_FORWARD, FAM_BACKWARD, FAM_RESIDUALS, FAM_PRECISION = range(5)
-FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates", "background", "munc")
+FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates", "background", "munc",
+                "forward_compose", "segment_scan", "backward_publish")
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -100,6 +101,7 @@ SIGNATURES = {
     "cb200_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cb200_ctx_reset_timing": (C.c_int, [_vp]),
     "cb200_set_scan_substeps": (C.c_int, [C.c_int]),
+    "cb200_set_lean_sweeps": (C.c_int, [C.c_int, C.c_int]),
     "cb200_debug_scan_times": (C.c_int, [_vp, _i64, _vp]),
     "cb200_device_alloc": (C.c_int, [_vp, _sz, C.POINTER(_vp)]),
     "cb200_device_free": (C.c_int, [_vp, _vp]),

@@ -17,6 +17,7 @@
 
 #include "../../include/consenrich_b200.h"
 #include "ssm_kernels.cuh"
+#include "lean_kernels.cuh"
 #include "background_kernels.cuh"
 #include "munc_kernels.cuh"
 
@@ -69,7 +70,8 @@ struct DevBuf {
     size_t cap = 0;
 };
 
-enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_BG = 5, FAM_MUNC = 6, FAM_COUNT = 7 };
+enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_BG = 5, FAM_MUNC = 6,
+              FAM_COMPOSE = 7, FAM_SEGSCAN = 8, FAM_PUBLISH = 9, FAM_COUNT = 10 };
 
 struct TimedSpan {
     cudaEvent_t a, b;
@@ -92,6 +94,8 @@ struct cb200_ctx {
     // arena (device)
     DevBuf scan_ws, stats, sums, data, munc, xf, Pf, Qf, xf2, Pf2, Qf2, smo, smo2, D, xs, Ps, lag, resid, lam, kap, qs, shard;
     DevBuf bg_ws, bg_w, bg_rhs, bg_out, bg_status;  // background solve: workspace, operands, outcome
+    // lean sweeps (lean_kernels.cuh): run-major statistics, multipliers, two sets of forward tracks, scratch
+    DevBuf ln_SA, ln_SB, ln_kap, ln_qs, ln_A[2], ln_B[2], ln_sagg[2], ln_sex[2], ln_fagg, ln_fex, ln_fpref, ln_ssuf, ln_part;
     DevBuf mask;  // MUNC stage: exclusion mask
     DevBuf seed_mat[6], seed_vec[7];  // MUNC seed pass: count floor, rho in, 4 outputs; 5 input + 2 output vectors
     double *sums_host = nullptr;  // pinned double[2]
@@ -99,8 +103,8 @@ struct cb200_ctx {
     bool timing = false;
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> pool;
-    double fam_ms[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0};
-    int64_t fam_n[FAM_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+    double fam_ms[FAM_COUNT] = {};
+    int64_t fam_n[FAM_COUNT] = {};
 };
 
 namespace {
@@ -223,6 +227,22 @@ Model2 to_model2(const cb200_model *mo) {
 }
 
 bool aligned(const void *p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int g_lean_off = -1;   // CB200_NO_LEAN / cb200_set_lean_sweeps: always the look-back kernels
+int g_lean_logL = 0;   // CB200_LEAN_LOGL / cb200_set_lean_sweeps: run length override (5 or 6)
+
+void lean_read_env() {
+    if (g_lean_off >= 0) return;
+    const char *e = getenv("CB200_NO_LEAN");
+    g_lean_off = (e && *e && *e != '0') ? 1 : 0;
+    const char *l = getenv("CB200_LEAN_LOGL");
+    g_lean_logL = (l && *l) ? atoi(l) : 0;
+}
+
+void lean_set_mode(int mode, int log2_run) {
+    g_lean_off = mode ? 0 : 1;
+    g_lean_logL = log2_run;
+}
 
 int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
@@ -480,6 +500,9 @@ void cb200_ctx_destroy(cb200_ctx *c) {
                       &c->Qf2, &c->smo, &c->smo2, &c->D,
                       &c->xs, &c->Ps, &c->lag, &c->resid, &c->lam, &c->kap, &c->qs, &c->shard,
                       &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status, &c->mask,
+                      &c->ln_SA, &c->ln_SB, &c->ln_kap, &c->ln_qs, &c->ln_A[0], &c->ln_A[1], &c->ln_B[0], &c->ln_B[1],
+                      &c->ln_sagg[0], &c->ln_sagg[1], &c->ln_sex[0], &c->ln_sex[1], &c->ln_fagg, &c->ln_fex, &c->ln_fpref,
+                      &c->ln_ssuf, &c->ln_part,
                       &c->seed_mat[0], &c->seed_mat[1], &c->seed_mat[2], &c->seed_mat[3], &c->seed_mat[4], &c->seed_mat[5],
                       &c->seed_vec[0], &c->seed_vec[1], &c->seed_vec[2], &c->seed_vec[3], &c->seed_vec[4], &c->seed_vec[5],
                       &c->seed_vec[6]};
@@ -566,6 +589,13 @@ int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
 int cb200_set_scan_substeps(int nsub) {
     if (nsub < 0 || nsub > MAX_NSUB) return fail(CB200_ERR_INVALID, "scan sub-steps must be in [0, %d]", MAX_NSUB);
     scan_set_nsub_override(nsub);
+    return CB200_OK;
+}
+
+int cb200_set_lean_sweeps(int mode, int log2_run) {
+    if (mode != 0 && mode != 1) return fail(CB200_ERR_INVALID, "lean sweep mode must be 0 or 1");
+    if (log2_run != 0 && log2_run != 5 && log2_run != 6) return fail(CB200_ERR_INVALID, "log2_run must be 0, 5 or 6");
+    lean_set_mode(mode, log2_run);
     return CB200_OK;
 }
 
@@ -769,9 +799,232 @@ int cb200_update_kappa(cb200_ctx *c, const cb200_model *mo, int64_t n, const flo
     return CB200_OK;
 }
 
+}  // extern "C"
+
+// =====================================================================================
+// ECM on run-major private tracks (lean_kernels.cuh)
+// =====================================================================================
+namespace {
+
+bool lean_eligible(const cb200_model *mo, const cb200_ecm_opts *op, int64_t n, const float *lam, const float *kap) {
+    lean_read_env();
+    if (g_lean_off || op->max_iters <= 0 || op->inner_iters <= 0) return false;
+    return mo->state_dim == 2 && lam == nullptr && kap != nullptr && n >= LEAN_MIN_BINS && mo->F[0] == 1.0 &&
+           mo->F[2] == 0.0 && mo->F[3] == 1.0;
+}
+
+struct EcmLoopState {
+    double prev = 1.0e16, cur = 0.0, init_nll = 0.0, rel_impr = 0.0, abs_rel = 0.0;
+    bool has_init = false, converged = false;
+    int iters_done = 0, stable = 0, inc = 0;
+};
+
+// convergence bookkeeping of one ECM iteration (cconsenrich.pyx:8337-8407); true = stop
+bool ecm_iteration_done(EcmLoopState &L, double rtol, int patience) {
+    const bool has_prev = L.has_init;
+    if (!has_prev) {
+        L.init_nll = L.cur;
+        L.has_init = true;
+    } else if (L.cur > L.prev + (1.0e-12 * fmax(fabs(L.prev), 1.0))) {
+        L.inc += 1;
+    }
+    double delta, scale;
+    if (has_prev) {
+        delta = fabs(L.cur - L.prev);
+        scale = fabs(L.prev);
+    } else {
+        delta = 0.0;
+        scale = fabs(L.cur);
+    }
+    scale = fmax(scale, fabs(L.cur));
+    scale = fmax(scale, 1.0);
+    if (has_prev) {
+        L.rel_impr = (L.prev - L.cur) / scale;
+        L.abs_rel = delta / scale;
+    } else {
+        L.rel_impr = L.abs_rel = 0.0;
+    }
+    const double tol = rtol * scale;
+    L.prev = L.cur;
+    L.stable = (has_prev && delta <= tol) ? L.stable + 1 : 0;
+    if (L.stable >= patience) {
+        L.converged = true;
+        return true;
+    }
+    return false;
+}
+
+int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op, const float *data,
+                    const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *kap, float *xs,
+                    float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
+    // run length: 32 bins, 64 once the chromosome gives every SM more than a few rounds of segments
+    int logL = g_lean_logL >= 5 && g_lean_logL <= 6 ? g_lean_logL : (n >= (int64_t)6 << 20 ? 6 : 5);
+    const LeanGeom g = lean_geom(n, logL);
+    const size_t np = (size_t)g.npad(), W = (size_t)g.W;
+    CB_TRY(ensure(c, c->ln_SA, np * 16));
+    CB_TRY(ensure(c, c->ln_SB, np * 16));
+    CB_TRY(ensure(c, c->ln_kap, np * 4));
+    if (qscale) CB_TRY(ensure(c, c->ln_qs, np * 4));
+    for (int s = 0; s < 2; ++s) {
+        CB_TRY(ensure(c, c->ln_A[s], np * 16));
+        CB_TRY(ensure(c, c->ln_B[s], np * 16));
+        CB_TRY(ensure(c, c->ln_sagg[s], W * 16 * 8));
+        CB_TRY(ensure(c, c->ln_sex[s], W * 9 * 32 * 8));
+    }
+    CB_TRY(ensure(c, c->ln_fagg, W * 16 * 8));
+    CB_TRY(ensure(c, c->ln_fex, W * 14 * 32 * 8));
+    CB_TRY(ensure(c, c->ln_fpref, W * 8 * 8));
+    CB_TRY(ensure(c, c->ln_ssuf, W * 8 * 8));
+    if (!c->ln_part.p || c->ln_part.cap < (W + 32) * 8) {
+        CB_TRY(ensure(c, c->ln_part, (W + 32) * 8 + W * 2));  // headroom: the counter must start at zero only once
+        CU_TRY(cudaMemsetAsync(c->ln_part.p, 0, 256, c->stream));
+    }
+    // layout of ln_part: [0] counter (int32, left at zero by every launch), partial sums from byte 256
+    double *sums = static_cast<double *>(c->sums.p);
+    {
+        Span sp(c, FAM_FOLD);
+        CU_TRY(launch_fold(data, munc, m, n, ld, mo->pad, static_cast<double2 *>(c->ln_SA.p),
+                           static_cast<double2 *>(c->ln_SB.p), c->stream, logL));
+        c->launches += 1;
+    }
+    float *kap_rm = static_cast<float *>(c->ln_kap.p);
+    float *qs_rm = nullptr;
+    {
+        Span sp(c, FAM_PREC);
+        CU_TRY(lean_gather_f32(kap, kap_rm, g, 1.0f, c->stream));
+        c->launches += 1;
+        if (qscale) {
+            qs_rm = static_cast<float *>(c->ln_qs.p);
+            CU_TRY(lean_gather_f32(qscale, qs_rm, g, 1.0f, c->stream));
+            c->launches += 1;
+        }
+    }
+    LeanTrack trk[2];
+    for (int s = 0; s < 2; ++s) {
+        trk[s].A = static_cast<float4 *>(c->ln_A[s].p);
+        trk[s].B = static_cast<float4 *>(c->ln_B[s].p);
+        trk[s].sagg = static_cast<double *>(c->ln_sagg[s].p);
+        trk[s].sex = static_cast<double *>(c->ln_sex[s].p);
+    }
+    LeanFwdArgs fa{};
+    fa.g = g;
+    fa.SA = static_cast<const double2 *>(c->ln_SA.p);
+    fa.SB = static_cast<const double2 *>(c->ln_SB.p);
+    fa.kap = kap_rm;
+    fa.qs = qs_rm;
+    fa.sc.fagg = static_cast<double *>(c->ln_fagg.p);
+    fa.sc.fex = static_cast<double *>(c->ln_fex.p);
+    fa.sc.fpref = static_cast<double *>(c->ln_fpref.p);
+    fa.sc.counter = static_cast<int32_t *>(c->ln_part.p);
+    fa.sc.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(c->ln_part.p) + 256);
+    fa.sums = sums;
+    fa.m = (double)m;
+    fa.inv_m = 1.0 / (double)m;
+    fa.mlog2pi = (double)m * log(6.2831853071795864769);
+    fa.M = to_model2(mo);
+    fa.state_init = mo->state_init;
+    fa.cov_init = mo->cov_init;
+    fa.kap_min = mo->kap_min;
+    fa.kap_max = mo->kap_max;
+    LeanBwdArgs ba{};
+    ba.g = g;
+    ba.ssuf = static_cast<double *>(c->ln_ssuf.p);
+    ba.qs = qs_rm;
+    ba.kap_out = kap_rm;
+    ba.xs = xs; ba.Ps = Ps; ba.lag = lag;
+    ba.lag_rows = n > 1 ? n - 1 : 1;
+    ba.M = fa.M;
+    ba.nu = op->nu;
+    ba.kap_lo = mo->kap_min;
+    ba.kap_hi = mo->kap_max;
+    {
+        const double det = mo->Q0[0] * mo->Q0[3] - mo->Q0[1] * mo->Q0[2];
+        ba.qi00 = mo->Q0[3] / det; ba.qi01 = -mo->Q0[1] / det; ba.qi10 = -mo->Q0[2] / det; ba.qi11 = mo->Q0[0] / det;
+    }
+    int cur_set = 0;
+    auto forward = [&](int set, bool with_nll, bool store) -> int {
+        fa.trk = trk[set];
+        fa.want_nll = with_nll ? 1 : 0;
+        fa.do_store = store ? 1 : 0;
+        {
+            Span sp(c, FAM_COMPOSE);
+            CU_TRY(lean_fwd_compose(fa, c->stream));
+        }
+        {
+            Span sp(c, FAM_SEGSCAN);
+            CU_TRY(lean_fwd_prefix(fa, c->stream));
+        }
+        {
+            Span sp(c, FAM_FWD);
+            CU_TRY(lean_fwd_replay(fa, c->stream));
+        }
+        c->launches += 3;
+        return CB200_OK;
+    };
+    auto backward = [&](bool publish) -> int {
+        ba.trk = trk[cur_set];
+        if (!publish) {
+            Span sp(c, FAM_SEGSCAN);
+            CU_TRY(lean_bwd_suffix(ba, c->stream));
+            c->launches += 1;
+        }
+        {
+            Span sp(c, publish ? FAM_PUBLISH : FAM_BWD);
+            CU_TRY(lean_bwd_replay(ba, publish, c->stream));
+        }
+        c->launches += 1;
+        return CB200_OK;
+    };
+    EcmLoopState L;
+    bool opened = false;  // the forward pass of the next sweep has already run (into the current set)
+    for (int i = 0; i < op->max_iters; ++i) {
+        L.iters_done = i + 1;
+        for (int t = 0; t < op->inner_iters; ++t) {
+            if (!opened) CB_TRY(forward(cur_set, false, true));
+            opened = false;
+            CB_TRY(backward(false));  // kappa is rewritten in place: only the forward pass reads it
+        }
+        const bool ahead = i + 1 < op->max_iters && op->inner_iters > 0;
+        // NLL of this iteration; with another iteration to come it is the by-product of that iteration's
+        // opening forward pass, run ahead into the spare set
+        CB_TRY(forward(ahead ? 1 - cur_set : cur_set, true, ahead));
+        double s2[2];
+        CB_TRY(read_sums(c, s2));
+        L.cur = s2[1];
+        if (nll_path) nll_path[i] = L.cur;
+        if (ecm_iteration_done(L, op->rtol, 2)) break;  // tracks run ahead into the spare set are dropped
+        if (ahead) {
+            cur_set = 1 - cur_set;
+            opened = true;
+        }
+    }
+    {
+        Span sp(c, FAM_PREC);
+        CU_TRY(lean_scatter_f32(kap_rm, kap, g, c->stream));
+        c->launches += 1;
+    }
+    CB_TRY(backward(true));  // the smoothed tracks the call returns: the last sweep's, in the reference's layouts
+    if (resid) CB_TRY(do_residuals(c, data, m, n, ld, xs, 2, resid));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    res->iters_done = L.iters_done;
+    res->converged = L.converged ? 1 : 0;
+    res->skipped = 0;
+    res->stable_iters = L.stable;
+    res->nll_increase_count = L.inc;
+    res->has_initial = L.has_init ? 1 : 0;
+    res->initial_nll = L.init_nll;
+    res->final_nll = L.prev;
+    res->final_abs_rel_change = L.abs_rel;
+    res->final_rel_improvement = L.rel_impr;
+    return CB200_OK;
+}
+
+}  // namespace
+
 // =====================================================================================
 // ECM (cconsenrich.pyx:7877-8442, 7188-7657)
 // =====================================================================================
+extern "C" {
 int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opts *op, const float *data,
                      const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *lam, float *kap,
                      float *xs, float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
@@ -802,6 +1055,10 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     CB_TRY(ensure(c, c->Pf2, (size_t)n * d * d * 4));
     CB_TRY(ensure(c, c->Qf2, (size_t)n * d * d * 4));
     double *stats = static_cast<double *>(c->stats.p);
+    // The inner sweeps of the CLI-default configuration (2-state model, F = [[1, f], [0, 1]], kappa the
+    // only multiplier being fitted) run on run-major private tracks: lean_kernels.cuh.
+    if (lean_eligible(&mo, op, n, lam, kap))
+        return ecm_device_lean(c, &mo, op, data, munc, m, n, ld, qscale, kap, xs, Ps, lag, resid, res, nll_path);
     // two sets of forward tracks: the NLL pass that closes an iteration is, when another iteration
     // follows, the storing forward pass that iteration would open with (same multipliers, same
     // arithmetic), run ahead of time into the spare set

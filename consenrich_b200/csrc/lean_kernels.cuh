@@ -1,0 +1,123 @@
+// consenrich_b200/csrc/lean_kernels.cuh -- the ECM's inner sweeps on run-major private tracks.
+//
+// Inside cfixedBackgroundECM (cconsenrich.pyx:8151-8335) the forward filter's tracks are read by
+// nothing but the backward pass of the same sweep, and -- when the process precision kappa is the
+// only multiplier being fitted, the CLI default -- the smoothed tracks by nothing but the kappa
+// update.  None of them has to exist in the reference's public layouts.  These kernels keep every
+// per-bin track of the inner sweeps in a RUN-MAJOR layout instead: a warp owns a segment of
+// 32 runs x L consecutive bins (one run per lane), and element i of all 32 runs is one contiguous
+// row, so every load and store of the sequential per-run recursions is a fully coalesced warp
+// access straight from / to registers -- no shared-memory staging, no bank conflicts, no barriers.
+//
+//   position of bin k:   seg = k / (32 L),  lane = (k mod 32 L) / L,  i = k mod L
+//                        index = seg * 32 L + i * 32 + lane
+//
+// A forward pass is three launches (no spinning between CTAs):
+//   lean_fwd_compose   every run composes its filtering element (Sarkka & Garcia-Fernandez), a warp
+//                      scan leaves per-run exclusive elements and one aggregate per segment
+//   lean_fwd_prefix    one CTA scans the segment aggregates into per-segment start states
+//   lean_fwd_replay    every run replays the reference's own recursion (float32 rounding points
+//                      included, ssm_math.cuh: kf2_step) from its exact start state, writes the
+//                      compact forward track (x, P upper triangle, Q upper triangle: 32 B per bin),
+//                      and composes the smoother's run elements on the way
+// and a backward pass two:
+//   lean_bwd_suffix    one CTA scans the segments' smoothing aggregates from the far end
+//   lean_bwd_replay    every run replays the reference's RTS recursion and forms kappa_{k+1} the
+//                      moment smoothed bins k, k+1 and their lag-one covariance are in registers
+//                      (LEAN_PUBLIC: writes stateSmoothed / stateCovarSmoothed / lagCovSmoothed in
+//                      the reference's layouts instead -- the one pass whose result the call returns)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ssm_math.cuh"
+
+namespace cb200 {
+
+constexpr int LEAN_THREADS = 128;
+constexpr int LEAN_WARPS = LEAN_THREADS / 32;
+constexpr int LEAN_SCAN_THREADS = 512;  // the single-CTA segment scans
+constexpr int LEAN_MIN_BINS = 4096;     // below this the look-back kernels serve the call
+
+struct LeanGeom {
+    int64_t n;     // bins
+    int32_t logL;  // run length L = 1 << logL (32 or 64)
+    int32_t W;     // segments (warps): ceil(n / (32 L))
+    __host__ __device__ int64_t L() const { return (int64_t)1 << logL; }
+    __host__ __device__ int64_t seg_bins() const { return (int64_t)32 << logL; }
+    __host__ __device__ int64_t npad() const { return (int64_t)W * seg_bins(); }
+    // run-major position of bin k
+    __host__ __device__ int64_t index(int64_t k) const {
+        const int64_t sb = seg_bins();
+        const int64_t r = k & (sb - 1);
+        return (k - r) + ((r & (L() - 1)) << 5) + (r >> logL);
+    }
+};
+
+inline LeanGeom lean_geom(int64_t n, int logL) {
+    LeanGeom g;
+    g.n = n;
+    g.logL = logL;
+    const int64_t sb = (int64_t)32 << logL;
+    g.W = (int32_t)((n + sb - 1) / sb);
+    return g;
+}
+
+// per-segment scratch of a forward pass
+struct LeanFwdScratch {
+    double *fagg;   // [W][16]     filtering aggregate of the segment (14 used)
+    double *fex;    // [W][14][32] per-run exclusive element within the segment
+    double *fpref;  // [W][8]      Gaussian at the start of the segment (5 used)
+    double *partials;  // [W][2]
+    int32_t *counter;  // zero between launches
+};
+
+// one set of forward tracks (the ECM keeps two: the pass that closes an iteration runs ahead into
+// the spare set)
+struct LeanTrack {
+    float4 *A;     // [npad] x0 x1 P00 P01
+    float4 *B;     // [npad] P11 Q00 Q01 Q11   (Q of the same bin, float32 as the reference stores it)
+    double *sagg;  // [W][16]    smoothing aggregate of the segment (9 used)
+    double *sex;   // [W][9][32] per-run exclusive (from the far end) smoothing element
+};
+
+struct LeanFwdArgs {
+    LeanGeom g;
+    const double2 *SA, *SB;  // run-major fold statistics {S0,S1}, {S2,SL}
+    const float *kap, *qs;   // run-major multipliers (qs may be nullptr)
+    LeanFwdScratch sc;
+    LeanTrack trk;
+    double *sums;            // device double[2] or nullptr: {0, sum NLL}
+    double m, inv_m, mlog2pi;
+    Model2 M;                // F = [[1, F01], [0, 1]] only
+    double state_init, cov_init, kap_min, kap_max;
+    int32_t want_nll, do_store;
+};
+
+struct LeanBwdArgs {
+    LeanGeom g;
+    LeanTrack trk;
+    double *ssuf;            // [W][8] smoothed Gaussian just beyond the segment (5 used)
+    const float *qs;         // run-major processQScale or nullptr
+    float *kap_out;          // run-major, written at the position of bin k+1
+    float *xs, *Ps, *lag;    // LEAN_PUBLIC: the reference's layouts
+    int64_t lag_rows;
+    Model2 M;
+    double nu, kap_lo, kap_hi;
+    double qi00, qi01, qi10, qi11;  // Q0^-1
+};
+
+// all return the cudaError_t of the launch; a forward pass = compose, prefix, replay in this order, a
+// backward pass = suffix, replay (a publishing replay re-uses the suffix states of the sweep before it)
+cudaError_t lean_fwd_compose(const LeanFwdArgs &a, cudaStream_t st);
+cudaError_t lean_fwd_prefix(const LeanFwdArgs &a, cudaStream_t st);
+cudaError_t lean_fwd_replay(const LeanFwdArgs &a, cudaStream_t st);
+cudaError_t lean_bwd_suffix(const LeanBwdArgs &a, cudaStream_t st);
+cudaError_t lean_bwd_replay(const LeanBwdArgs &a, bool publish, cudaStream_t st);
+// run-major <-> linear copies of per-bin float vectors (fill: value of the padding positions)
+cudaError_t lean_gather_f32(const float *linear, float *run_major, const LeanGeom &g, float fill, cudaStream_t st);
+cudaError_t lean_scatter_f32(const float *run_major, float *linear, const LeanGeom &g, cudaStream_t st);
+cudaError_t lean_fill_f32(float *run_major, const LeanGeom &g, float value, cudaStream_t st);
+cudaError_t lean_configure();
+
+}  // namespace cb200

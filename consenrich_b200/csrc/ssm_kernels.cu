@@ -143,7 +143,7 @@ constexpr int FOLD_UNROLL = 4;
 template <int VEC>
 __global__ void __launch_bounds__(FOLD_THREADS, FOLD_MIN_CTAS)
 fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int64_t m, int64_t n, int64_t ld,
-            double pad, double2 *__restrict__ SA, double2 *__restrict__ SB) {
+            double pad, double2 *__restrict__ SA, double2 *__restrict__ SB, int rm_logL) {
     const int64_t k0 = ((int64_t)blockIdx.x * FOLD_THREADS + threadIdx.x) * VEC;
     if (k0 >= n) return;
     FoldAcc acc[VEC];
@@ -209,8 +209,15 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
     for (int c = 0; c < VEC; ++c) {
         const int64_t k = k0 + c;
         if (k < n) {
-            SA[k] = make_double2(acc[c].s0, acc[c].s1);
-            SB[k] = make_double2(acc[c].s2, fold_logsum(acc[c]));
+            // rm_logL >= 0: run-major output for the lean sweeps (lean_kernels.cuh), runs of 1 << rm_logL bins
+            int64_t pos = k;
+            if (rm_logL >= 0) {
+                const int64_t sb = (int64_t)32 << rm_logL;
+                const int64_t r = k & (sb - 1);
+                pos = (k - r) + ((r & (((int64_t)1 << rm_logL) - 1)) << 5) + (r >> rm_logL);
+            }
+            SA[pos] = make_double2(acc[c].s0, acc[c].s1);
+            SB[pos] = make_double2(acc[c].s2, fold_logsum(acc[c]));
         }
     }
 }
@@ -1348,66 +1355,59 @@ __global__ void backward_shard_prefix_kernel(const double *aggs, int rank, int n
 // difference of two floats is exact, so rounding it to float is the correctly rounded float
 // difference: a single FSUB gives the same bits.
 //
-// A CTA transposes RES_BINS bins x up to RES_TRACKS tracks per step through shared memory:
-// float4 loads along the bins (coalesced rows of data), scalar stores along the tracks (the
-// [bins x tracks] block of the output is contiguous when the tile spans all m tracks, and rows
-// of >= 32 floats otherwise).  Output indices advance incrementally: no per-element division.
-constexpr int RES_BINS = 128;
-constexpr int RES_TRACKS = 32;
+// A CTA transposes `bins` consecutive bins x ALL m tracks through shared memory, so that what it
+// writes -- rows k0 .. k0 + bins of the [n x m] output -- is ONE contiguous stretch of memory
+// whatever m is (m = 50: a 32-track tile would end every output row inside a sector).  `bins` is a
+// multiple of 32 chosen by the launcher from the shared-memory budget.  Loads: 4-byte cp.async, a warp
+// copies 32 consecutive bins of one track (one 128-byte line) per instruction, the whole tile in
+// flight at once; the tile row pitch is odd, so both the writes (lanes along the bins) and the reads
+// (lanes along the tracks) are free of bank conflicts.  Stores walk the output in memory order, one coalesced 128-byte line per warp
+// instruction; (bin, track) advance incrementally, no per-element division.
 constexpr int RES_THREADS = 256;
-constexpr int RES_PITCH = RES_BINS + 4;  // floats; keeps float4 rows 16-byte aligned, row stride = 4 banks
+constexpr int RES_SMEM_BUDGET = 96 * 1024;  // two CTAs per SM
 
 __global__ void __launch_bounds__(RES_THREADS)
-residual_kernel(const float *__restrict__ data, int64_t m, int64_t n, int64_t ld, const float *__restrict__ xs,
-                int dim, float *__restrict__ resid, int steps_per_cta, int vec_ok) {
-    __shared__ __align__(16) float tile[RES_TRACKS * RES_PITCH];
-    const int tid = threadIdx.x;
-    const int64_t j0 = (int64_t)blockIdx.y * RES_TRACKS;
-    const int nt = (int)min((int64_t)RES_TRACKS, m - j0);
-    const int c = tid & 31, r0 = tid >> 5;  // column group (4 bins) and first row of this thread
-    // (dkk, djj) = RES_THREADS divmod nt: how the output position moves per store iteration
-    const int dkk = RES_THREADS / nt, djj = RES_THREADS - dkk * nt;
-    const int kk0 = tid / nt, jj0 = tid - kk0 * nt;
-    for (int st = 0; st < steps_per_cta; ++st) {
-        const int64_t k0 = ((int64_t)blockIdx.x * steps_per_cta + st) * RES_BINS;
-        if (k0 >= n) break;
-        const int nb = (int)min((int64_t)RES_BINS, n - k0);
-        // ---- load: rows of data, minus the level of each bin ----
-        float lv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t k = k0 + 4 * c + i;
-            lv[i] = k < n ? __ldg(xs + k * dim) : 0.0f;
+residual_kernel(const float *__restrict__ data, int64_t m_all, int64_t n, int64_t ld, const float *__restrict__ xs,
+                int dim, float *__restrict__ resid, int bins, int m_chunk) {
+    extern __shared__ float res_tile[];  // [m][bins + 1] then level[bins]
+    // tracks [j0, j0 + m) of the m_all (one chunk unless m_all exceeds what shared memory holds)
+    const int64_t j0 = (int64_t)blockIdx.y * m_chunk;
+    const int m = (int)min((int64_t)m_chunk, m_all - j0);
+    data += j0 * ld;
+    const int pitch = bins + 1;
+    float *level = res_tile + (size_t)m_chunk * pitch;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t k0 = (int64_t)blockIdx.x * bins;
+    const int nb = (int)min((int64_t)bins, n - k0);
+    // ---- load: the whole tile by 4-byte cp.async (no registers, every copy in flight at once); a warp
+    //      copies 32 consecutive bins of one track per instruction: one 128-byte line, conflict-free ----
+    const int nseg = (nb + 31) >> 5;
+    for (int j = warp; j < m; j += RES_THREADS / 32) {
+        const float *row = data + (int64_t)j * ld + k0;
+        float *trow = res_tile + j * pitch;
+        for (int sgm = 0; sgm < nseg; ++sgm) {
+            const int kk = (sgm << 5) + lane;
+            if (kk < nb) cp_async_full<4>(trow + kk, row + kk);
         }
-        if (vec_ok && nb == RES_BINS) {
-            for (int jj = r0; jj < nt; jj += RES_THREADS / 32) {
-                const float4 z = __ldcs(reinterpret_cast<const float4 *>(data + (j0 + jj) * ld + k0) + c);
-                *reinterpret_cast<float4 *>(tile + jj * RES_PITCH + 4 * c) =
-                    make_float4(z.x - lv[0], z.y - lv[1], z.z - lv[2], z.w - lv[3]);
-            }
-        } else {
-            for (int jj = r0; jj < nt; jj += RES_THREADS / 32) {
-                const float *row = data + (j0 + jj) * ld + k0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (4 * c + i < nb) tile[jj * RES_PITCH + 4 * c + i] = __ldcs(row + 4 * c + i) - lv[i];
-            }
+    }
+    cp_async_commit();
+    for (int kk = tid; kk < nb; kk += RES_THREADS) level[kk] = __ldg(xs + (k0 + kk) * dim);
+    cp_async_wait_all();
+    __syncthreads();
+    // ---- store: the [nb][m] block in memory order ----
+    const int total = nb * m;
+    const int dkk = RES_THREADS / m, djj = RES_THREADS - dkk * m;
+    int kk = tid / m, jj = tid - kk * m;
+    float *out = resid + k0 * m_all + j0;
+    const bool whole = m == m_all;  // the block of output rows is one contiguous stretch
+    for (int idx = tid; idx < total; idx += RES_THREADS) {
+        __stcs(whole ? out + idx : out + (int64_t)kk * m_all + jj, res_tile[jj * pitch + kk] - level[kk]);
+        kk += dkk;
+        jj += djj;
+        if (jj >= m) {
+            jj -= m;
+            kk += 1;
         }
-        __syncthreads();
-        // ---- store: walk the [nb][nt] output block in memory order ----
-        const int total = nb * nt;
-        int kk = kk0, jj = jj0;
-        float *out = resid + k0 * m + j0;
-        for (int idx = tid; idx < total; idx += RES_THREADS) {
-            __stcs(out + (int64_t)kk * m + jj, tile[jj * RES_PITCH + kk]);
-            kk += dkk;
-            jj += djj;
-            if (jj >= nt) {
-                jj -= nt;
-                kk += 1;
-            }
-        }
-        __syncthreads();
     }
 }
 
@@ -1582,17 +1582,17 @@ cudaError_t launch_fill(float *v, int64_t n, float value, cudaStream_t st) {
 }
 
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
-                        double2 *SA, double2 *SB, cudaStream_t st) {
+                        double2 *SA, double2 *SB, cudaStream_t st, int rm_logL) {
     if (n <= 0) return cudaSuccess;
     const bool vec = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(munc) & 15) == 0);
     if (vec) {
         const int64_t threads = (n + 3) / 4;
         const unsigned grid = (unsigned)((threads + FOLD_THREADS - 1) / FOLD_THREADS);
-        fold_kernel<4><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, SA, SB);
+        fold_kernel<4><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, SA, SB, rm_logL);
     } else {
         const unsigned grid = (unsigned)((n + FOLD_THREADS - 1) / FOLD_THREADS);
-        fold_kernel<1><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, SA, SB);
+        fold_kernel<1><<<grid, FOLD_THREADS, 0, st>>>(data, munc, m, n, ld, pad, SA, SB, rm_logL);
     }
     return cudaGetLastError();
 }
@@ -1635,14 +1635,28 @@ cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, 
 cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld, const float *xs, int dim,
                              float *resid, cudaStream_t st) {
     if (n <= 0 || m <= 0) return cudaSuccess;
-    const int64_t gy = (m + RES_TRACKS - 1) / RES_TRACKS;
-    if (gy > 65535) return cudaErrorInvalidValue;
-    // few tracks: a CTA walks several bin blocks so that it has enough work per launch slot
-    const int steps = m <= 8 ? 8 : (m <= 16 ? 4 : (m <= 32 ? 2 : 1));
-    const int64_t blocks = (n + RES_BINS - 1) / RES_BINS;
-    const int vec_ok = (ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(data) & 15) == 0);
-    dim3 grid((unsigned)((blocks + steps - 1) / steps), (unsigned)gy);
-    residual_kernel<<<grid, RES_THREADS, 0, st>>>(data, m, n, ld, xs, dim, resid, steps, vec_ok);
+    // bins per CTA: as many 32-bin groups as the shared-memory budget holds for m tracks (at least
+    // one; m beyond ~1700 tracks would need more than a CTA's shared memory for a single group)
+    const int64_t max_bytes = 200 * 1024;
+    const int64_t m_chunk = m <= 1024 ? m : 1024;
+    const int64_t chunks = (m + m_chunk - 1) / m_chunk;
+    if (chunks > 65535) return cudaErrorInvalidValue;
+    int64_t bins = (RES_SMEM_BUDGET / 4 - 1) / (m_chunk + 1) / 32 * 32;
+    if (bins < 32) bins = 32;
+    if (bins > 512) bins = 512;
+    // short tracks: enough CTAs to cover the machine
+    while (bins > 32 && (n + bins - 1) / bins < 296) bins -= 32;
+    const int64_t smem = (m_chunk * (bins + 1) + bins) * 4;
+    if (smem > max_bytes) return cudaErrorInvalidValue;
+    static int64_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes);
+        if (e != cudaSuccess) return e;
+        configured = max_bytes;
+    }
+    const int64_t blocks = (n + bins - 1) / bins;
+    residual_kernel<<<dim3((unsigned)blocks, (unsigned)chunks), RES_THREADS, (size_t)smem, st>>>(data, m, n, ld, xs, dim, resid,
+                                                                                                (int)bins, (int)m_chunk);
     return cudaGetLastError();
 }
 

@@ -89,8 +89,9 @@ int scan_pick_nsub(int64_t positions, int which);
 void scan_set_nsub_override(int nsub);
 
 // every launcher returns the cudaError_t of the launch (cudaGetLastError)
+// rm_logL >= 0: the statistics are written run-major for the lean sweeps (lean_kernels.cuh)
 cudaError_t launch_fold(const float *data, const float *munc, int64_t m, int64_t n, int64_t ld, double pad,
-                        double2 *SA, double2 *SB, cudaStream_t st);
+                        double2 *SA, double2 *SB, cudaStream_t st, int rm_logL = -1);
 cudaError_t launch_forward(int dim, const FwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,
                            cudaStream_t st, int *launches);
 cudaError_t launch_backward(int dim, const BwdArgs &a, const ScanWorkspace &ws, bool aggregate_only,

@@ -117,8 +117,10 @@ CB200_API const char *cb200_last_error(void); /* thread-local; valid until the n
 /* number of kernel launches this context has enqueued (bench.py's gpu_launches). */
 CB200_API int64_t cb200_ctx_launch_count(const cb200_ctx *ctx);
 /* cumulative device time (ms) of the named kernel family since the last reset, measured
- * with CUDA events on the context's stream when timing is enabled: 0 fold, 1 forward scan,
- * 2 backward scan, 3 residuals, 4 precision updates. */
+ * with CUDA events on the context's stream when timing is enabled: 0 fold, 1 forward scan (lean
+ * sweeps: the replay kernel), 2 backward scan (lean: the kappa-carrying replay), 3 residuals,
+ * 4 precision updates and run-major copies, 5 background, 6 variance stage, 7 lean run-element
+ * composition, 8 lean segment scans, 9 lean publishing backward replay. */
 CB200_API int cb200_ctx_enable_timing(cb200_ctx *ctx, int on);
 CB200_API int cb200_ctx_kernel_ms(cb200_ctx *ctx, int family, double *ms, int64_t *launches);
 CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
@@ -126,6 +128,14 @@ CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
  * (1..16), 0 = choose per launch from the track length and the resident tile slots.  Results do not
  * depend on it beyond float64 re-association.  Also settable with CB200_SCAN_NSUB. */
 CB200_API int cb200_set_scan_substeps(int nsub);
+/* Tuning / diagnostics knob (process-wide).  The inner sweeps of cb200_ecm_device -- 2-state model,
+ * F = [[1, f], [0, 1]], process precision the only multiplier fitted (the CLI default of
+ * cfixedBackgroundECM, cconsenrich.pyx:7660) -- run on run-major private tracks (csrc/lean_kernels.cuh)
+ * when the track has at least 4096 intervals.  mode 0: always the look-back scan kernels; 1: lean sweeps
+ * where eligible (default).  log2_run: 5 or 6 fixes the run length at 32 / 64 intervals, 0 chooses per
+ * call.  Results agree between the two paths to float64 re-association of each run's start state.
+ * Also settable with CB200_NO_LEAN / CB200_LEAN_LOGL. */
+CB200_API int cb200_set_lean_sweeps(int mode, int log2_run);
 /* Diagnostics.  (tiles > 0, host_out NULL) arms phase stamping: every tile of the following scan
  * launches writes eight %globaltimer values (0 start, 1 run elements composed, 2 prefix known, 3 end,
  * 4 look-back flags ready, 5 window loaded, 6 look-back entered, 7 aggregate published).

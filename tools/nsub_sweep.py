@@ -10,9 +10,9 @@ from consenrich_b200.device import TrackSweep, make_model, _p
 
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(dev); torch.cuda.set_stream(stream)
-m, n = bench.M_TRACKS, int(os.environ.get("SWEEP_N", bench.N_BINS))
+m, n = int(os.environ.get("SWEEP_M", bench.M_TRACKS)), int(os.environ.get("SWEEP_N", bench.N_BINS))
 ld = (n + 31) // 32 * 32
-reps = [bench.synth_device(torch, dev, 1729 + i, m, n, ld) for i in range(4)]
+reps = [bench.synth_device(torch, dev, 1729 + i, m, n, ld) for i in range(int(os.environ.get("SWEEP_REPS", 4)))]
 model = make_model(2, bench.F_MAT, bench.Q0_MAT, 0.0, 1000.0, 1e-4, kap_bounds=bench.KAP_BOUNDS, return_nll=True,
                    use_kappa=True)
 ts = TrackSweep(m, n, 2, 0, residuals=True)
@@ -48,10 +48,11 @@ def fam():
         ecm(i)
     torch.cuda.synchronize()
     out = {}
-    for name, f in (("fold", 0), ("fwd", 1), ("bwd", 2), ("res", 3)):
+    for name, f in (("fold", 0), ("fwd", 1), ("bwd", 2), ("res", 3), ("prec", 4), ("compose", 7), ("segscan", 8), ("publish", 9)):
         ms, cnt = C.c_double(), C.c_int64()
         _lib.check(L.cb200_ctx_kernel_ms(ctx.handle, f, C.byref(ms), C.byref(cnt)))
-        out[name] = round(ms.value / max(cnt.value, 1) * 1e3, 1)
+        if cnt.value:
+            out[name] = (round(ms.value / max(cnt.value, 1) * 1e3, 1), cnt.value // 6)
     ctx.enable_timing(False)
     return out
 
