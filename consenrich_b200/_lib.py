@@ -5,6 +5,7 @@ fall back to.  Creating a context fails loudly when no CUDA device is present.
 """
 from __future__ import annotations
 
+import bisect
 import ctypes as C
 import os
 import threading
@@ -253,10 +254,10 @@ class Context:
 # through a bounce buffer by the driver at a fraction of that).  Blocks are recycled through a
 # small pool when the numpy array that wraps them is garbage collected: cudaHostAlloc is far too
 # slow to call per result.
-_pin_pool: dict = {}
+_pin_pool: list = []      # free blocks, (nbytes, ptr), sorted by size
 _pin_lock = threading.Lock()
 _PIN_MIN = 1 << 16        # smaller results stay ordinary numpy arrays
-_PIN_POOL_CAP = 8 << 30   # bytes kept for reuse
+_PIN_POOL_CAP = int(os.environ.get("CB200_PINNED_POOL_BYTES", 24 << 30))   # bytes kept for reuse
 
 
 class _PinnedBlock:
@@ -268,9 +269,9 @@ class _PinnedBlock:
     def __del__(self):
         try:
             with _pin_lock:
-                held = sum(k * len(v) for k, v in _pin_pool.items())
+                held = sum(k for k, _ in _pin_pool)
                 if held + self.nbytes <= _PIN_POOL_CAP:
-                    _pin_pool.setdefault(self.nbytes, []).append(self.ptr)
+                    bisect.insort(_pin_pool, (self.nbytes, self.ptr))
                     return
             load().cb200_pinned_free(_vp(self.ptr))
         except Exception:
@@ -278,7 +279,9 @@ class _PinnedBlock:
 
 
 def pinned_empty(shape, dtype):
-    """numpy array in page-locked memory (falls back to numpy.empty for small results)."""
+    """numpy array in page-locked memory (falls back to numpy.empty for small results).  A freed block
+    serves any later request it is large enough for (best fit, at most 4x the request): a genome's
+    chromosomes come in decreasing sizes, and cudaHostAlloc costs ~0.3 s per GB."""
     import numpy as np
     dt = np.dtype(dtype)
     count = int(np.prod(shape)) if len(shape) else 1
@@ -286,9 +289,11 @@ def pinned_empty(shape, dtype):
     if nbytes < _PIN_MIN:
         return np.empty(shape, dt)
     size = 1 << (nbytes - 1).bit_length() if nbytes < (1 << 24) else (nbytes + (1 << 22) - 1) >> 22 << 22
+    ptr = None
     with _pin_lock:
-        free = _pin_pool.get(size)
-        ptr = free.pop() if free else None
+        i = bisect.bisect_left(_pin_pool, (size, 0))
+        if i < len(_pin_pool) and _pin_pool[i][0] <= 4 * size:
+            size, ptr = _pin_pool.pop(i)
     if ptr is None:
         p = _vp()
         check(load().cb200_pinned_alloc(size, C.byref(p)))

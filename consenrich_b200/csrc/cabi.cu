@@ -144,7 +144,11 @@ int next_scan_ws(cb200_ctx *c, int64_t n, ScanWorkspace *ws) {
     *ws = scan_workspace_carve(c->scan_ws.p, c->scan_ws_n);
     ws->epoch4 = c->scan_epoch * 4;
     ws->dbg = nullptr;
-    if (c->scan_dbg && (c->scan_dbg_pick < 0 || c->scan_dbg_seen == c->scan_dbg_pick)) ws->dbg = c->scan_dbg;
+    ws->dbg_tiles = 0;
+    if (c->scan_dbg && (c->scan_dbg_pick < 0 || c->scan_dbg_seen == c->scan_dbg_pick)) {
+        ws->dbg = c->scan_dbg;
+        ws->dbg_tiles = (int32_t)(c->scan_dbg_tiles > 0x7fffffff ? 0x7fffffff : c->scan_dbg_tiles);
+    }
     if (c->scan_dbg) c->scan_dbg_seen += 1;
     return CB200_OK;
 }
@@ -857,10 +861,10 @@ bool ecm_iteration_done(EcmLoopState &L, double rtol, int patience) {
 int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op, const float *data,
                     const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *kap, float *xs,
                     float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
-    // run length: 32 bins, 64 once the chromosome gives every SM more than a few rounds of segments
-    int logL = g_lean_logL >= 5 && g_lean_logL <= 6 ? g_lean_logL : (n >= (int64_t)6 << 20 ? 6 : 5);
+    // run length: 32 bins (measured on B200: faster than 64 at chr19 and at chr1 @ 25 bp alike)
+    int logL = g_lean_logL >= 5 && g_lean_logL <= 6 ? g_lean_logL : 5;
     const LeanGeom g = lean_geom(n, logL);
-    const size_t np = (size_t)g.npad(), W = (size_t)g.W;
+    const size_t np = (size_t)g.npad(), G = (size_t)g.G, Gp = (size_t)g.Gp, segs = G * LEAN_WARPS;
     CB_TRY(ensure(c, c->ln_SA, np * 16));
     CB_TRY(ensure(c, c->ln_SB, np * 16));
     CB_TRY(ensure(c, c->ln_kap, np * 4));
@@ -868,15 +872,15 @@ int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *o
     for (int s = 0; s < 2; ++s) {
         CB_TRY(ensure(c, c->ln_A[s], np * 16));
         CB_TRY(ensure(c, c->ln_B[s], np * 16));
-        CB_TRY(ensure(c, c->ln_sagg[s], W * 16 * 8));
-        CB_TRY(ensure(c, c->ln_sex[s], W * 9 * 32 * 8));
+        CB_TRY(ensure(c, c->ln_sagg[s], Gp * 9 * 8));
+        CB_TRY(ensure(c, c->ln_sex[s], segs * 9 * 32 * 8));
     }
-    CB_TRY(ensure(c, c->ln_fagg, W * 16 * 8));
-    CB_TRY(ensure(c, c->ln_fex, W * 14 * 32 * 8));
-    CB_TRY(ensure(c, c->ln_fpref, W * 8 * 8));
-    CB_TRY(ensure(c, c->ln_ssuf, W * 8 * 8));
-    if (!c->ln_part.p || c->ln_part.cap < (W + 32) * 8) {
-        CB_TRY(ensure(c, c->ln_part, (W + 32) * 8 + W * 2));  // headroom: the counter must start at zero only once
+    CB_TRY(ensure(c, c->ln_fagg, Gp * 14 * 8));
+    CB_TRY(ensure(c, c->ln_fex, segs * 14 * 32 * 8));
+    CB_TRY(ensure(c, c->ln_fpref, Gp * 5 * 8));
+    CB_TRY(ensure(c, c->ln_ssuf, Gp * 5 * 8));
+    if (!c->ln_part.p || c->ln_part.cap < 256 + G * 8) {
+        CB_TRY(ensure(c, c->ln_part, 256 + G * 8 + G * 2));  // headroom: the counter must start at zero only once
         CU_TRY(cudaMemsetAsync(c->ln_part.p, 0, 256, c->stream));
     }
     // layout of ln_part: [0] counter (int32, left at zero by every launch), partial sums from byte 256

@@ -14,13 +14,13 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 #ifndef LEAN_COMPOSE_CTAS
-#define LEAN_COMPOSE_CTAS 6
+#define LEAN_COMPOSE_CTAS 2
 #endif
 #ifndef LEAN_FWD_CTAS
-#define LEAN_FWD_CTAS 4
+#define LEAN_FWD_CTAS 2
 #endif
 #ifndef LEAN_BWD_CTAS
-#define LEAN_BWD_CTAS 4
+#define LEAN_BWD_CTAS 2
 #endif
 
 template <class E>
@@ -88,8 +88,8 @@ struct ComposeIn {
 };
 
 __global__ void __launch_bounds__(LEAN_THREADS, LEAN_COMPOSE_CTAS) lean_fwd_compose_kernel(const LeanFwdArgs a) {
-    const Seg sg = seg_of(a.g);
-    if (sg.w >= a.g.W) return;
+    __shared__ double sh[LEAN_WARPS * Filt2::N], sh_ex[LEAN_WARPS * Filt2::N];
+    const Seg sg = seg_of(a.g);  // segments past the end of the track (last group) hold no valid bin: identity
     const double2 *SA = a.SA + sg.base + sg.lane;
     const float *kap = a.kap + sg.base + sg.lane;
     const bool has_qs = a.qs != nullptr;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_COMPOSE_CTAS) lean_fwd_comp
         if (i0 + 8 < sg.L) load(c0, i0 + 8);
         step(c1, i0 + 4);
     }
-    // inclusive Kogge-Stone scan over the warp's 32 runs
+    // inclusive Kogge-Stone scan over the warp's 32 runs, then over the CTA's warps
     Filt2 inc = g;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -132,8 +132,27 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_COMPOSE_CTAS) lean_fwd_comp
     }
     Filt2 ex = shfl_up_elem(inc, 1);
     if (sg.lane == 0) ex = filt2_identity();
+    const int warp = threadIdx.x >> 5;
+    if (sg.lane == 31) store_strided(sh + warp * Filt2::N, 1, inc);
+    __syncthreads();
+    if (warp == 0) {
+        Filt2 v = sg.lane < LEAN_WARPS ? load_strided<Filt2>(sh + sg.lane * Filt2::N, 1) : filt2_identity();
+#pragma unroll
+        for (int d = 1; d < LEAN_WARPS; d <<= 1) {
+            const Filt2 o = shfl_up_elem(v, d);
+            if (sg.lane >= d) v = filt2_combine(o, v);
+        }
+        if (sg.lane == LEAN_WARPS - 1) store_strided(a.sc.fagg + blockIdx.x, a.g.Gp, v);  // the group's aggregate
+        Filt2 x = shfl_up_elem(v, 1);
+        if (sg.lane == 0) x = filt2_identity();
+        if (sg.lane < LEAN_WARPS) store_strided(sh_ex + sg.lane * Filt2::N, 1, x);
+    }
+    __syncthreads();
+    if (warp > 0) {
+        const Filt2 wex = load_strided<Filt2>(sh_ex + warp * Filt2::N, 1);
+        ex = sg.lane > 0 ? filt2_combine(wex, ex) : wex;
+    }
     store_strided(a.sc.fex + (int64_t)sg.w * (Filt2::N * 32) + sg.lane, 32, ex);
-    if (sg.lane == 31) store_strided(a.sc.fagg + (int64_t)sg.w * 16, 1, inc);
 }
 
 // =====================================================================================
@@ -152,38 +171,43 @@ struct SmoOps {
     __device__ static __forceinline__ State2 apply(const Elem &e, const State2 &s) { return smo2_apply(e, s); }
 };
 
-// Scan position j is segment j (REVERSE = false) or segment W - 1 - j (REVERSE = true); out[seg]
-// receives the Gaussian the segment starts from: `first` pushed through the aggregates of all
-// scan positions before it.
+// Scan position j is group j (REVERSE = false) or group G - 1 - j (REVERSE = true); out[.][grp]
+// receives the Gaussian the group starts from: `first` pushed through the aggregates of all scan
+// positions before it.  agg: [N][pitch], out: [5][pitch].
 template <class Ops, bool REVERSE>
-__global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_segment_scan_kernel(const double *agg, int W, State2 first,
-                                                                             double *out) {
+__global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_group_scan_kernel(const double *agg, int G, int pitch,
+                                                                           State2 first, double *out) {
     using Elem = typename Ops::Elem;
     constexpr int N = Elem::N;
     constexpr int NW = LEAN_SCAN_THREADS / 32;
     __shared__ double sh[NW * N];
     __shared__ double sh_ex[NW * N];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = (W + LEAN_SCAN_THREADS - 1) / LEAN_SCAN_THREADS;
+    const int c = (G + LEAN_SCAN_THREADS - 1) / LEAN_SCAN_THREADS;
     const int j0 = tid * c;
-    auto seg = [&](int j) { return REVERSE ? W - 1 - j : j; };
+    auto grp = [&](int j) { return REVERSE ? G - 1 - j : j; };
     Elem e = Ops::identity();
     for (int u = 0; u < c; ++u) {
         const int j = j0 + u;
-        if (j < W) e = Ops::combine(e, load_strided<Elem>(agg + (int64_t)seg(j) * 16, 1));
+        if (j < G) {
+            const Elem x = load_strided<Elem>(agg + grp(j), pitch);
+            e = u == 0 ? x : Ops::combine(e, x);
+        }
     }
+    const int warps_live = min(NW, (G + 32 * c - 1) / (32 * c));  // warps that hold any group
     Elem inc = e;
+    if (warp < warps_live) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const Elem o = shfl_up_elem(inc, d);
-        if (lane >= d) inc = Ops::combine(o, inc);
+        for (int d = 1; d < 32; d <<= 1) {
+            const Elem o = shfl_up_elem(inc, d);
+            if (lane >= d) inc = Ops::combine(o, inc);
+        }
+        if (lane == 31) store_strided(sh + warp * N, 1, inc);
     }
-    if (lane == 31) store_strided(sh + warp * N, 1, inc);
     __syncthreads();
-    if (warp == 0) {
-        Elem v = lane < NW ? load_strided<Elem>(sh + lane * N, 1) : Ops::identity();
-#pragma unroll
-        for (int d = 1; d < NW; d <<= 1) {
+    if (warp == 0 && warps_live > 1) {
+        Elem v = lane < warps_live ? load_strided<Elem>(sh + lane * N, 1) : Ops::identity();
+        for (int d = 1; d < warps_live; d <<= 1) {
             const Elem o = shfl_up_elem(v, d);
             if (lane >= d) v = Ops::combine(o, v);
         }
@@ -192,19 +216,22 @@ __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_segment_scan_kernel(co
         if (lane < NW) store_strided(sh_ex + lane * N, 1, x);
     }
     __syncthreads();
+    if (warp >= warps_live) return;
     Elem tex = shfl_up_elem(inc, 1);
     State2 st = first;
     if (tid > 0) {
-        Elem full = load_strided<Elem>(sh_ex + warp * N, 1);
-        if (lane > 0) full = warp > 0 ? Ops::combine(full, tex) : tex;
-        st = Ops::apply(full, first);
+        if (warp > 0) {
+            const Elem wex = load_strided<Elem>(sh_ex + warp * N, 1);
+            tex = lane > 0 ? Ops::combine(wex, tex) : wex;
+        }
+        st = Ops::apply(tex, first);
     }
     for (int u = 0; u < c; ++u) {
         const int j = j0 + u;
-        if (j < W) {
-            const int s = seg(j);
-            store_strided(out + (int64_t)s * 8, 1, st);
-            st = Ops::apply(load_strided<Elem>(agg + (int64_t)s * 16, 1), st);
+        if (j < G) {
+            const int s = grp(j);
+            store_strided(out + s, pitch, st);
+            if (u + 1 < c) st = Ops::apply(load_strided<Elem>(agg + s, pitch), st);
         }
     }
 }
@@ -230,20 +257,21 @@ __device__ __forceinline__ void compose_smo(const Model2 &M, Smo2 &brun, const K
 template <bool NLL>
 __global__ void __launch_bounds__(LEAN_THREADS, LEAN_FWD_CTAS) lean_fwd_replay_kernel(const LeanFwdArgs a) {
     __shared__ double sh_part[LEAN_WARPS];
+    __shared__ double sh[LEAN_WARPS * Smo2::N], sh_ex[LEAN_WARPS * Smo2::N];
     __shared__ int sh_last;
     const Seg sg = seg_of(a.g);
-    const bool live = sg.w < a.g.W;
+    const int warp = threadIdx.x >> 5;
     double nll = 0.0;
-    if (live) {
+    Smo2 brun = smo2_identity();
+    {
         const bool has_qs = a.qs != nullptr;
-        // start state of the run: the segment's Gaussian pushed through the runs in front of this one
-        State2 start = load_strided<State2>(a.sc.fpref + (int64_t)sg.w * 8, 1);
-        if (sg.lane > 0)
+        // start state of the run: the group's Gaussian pushed through the runs of the group in front of it
+        State2 start = load_strided<State2>(a.sc.fpref + blockIdx.x, a.g.Gp);
+        if (threadIdx.x > 0)
             start = filt2_apply(load_strided<Filt2>(a.sc.fex + (int64_t)sg.w * (Filt2::N * 32) + sg.lane, 32), start);
         Kf2 s{r32(start.x0), r32(start.x1), r32(start.P00), r32(start.P01), r32(start.P01), r32(start.P11)};
         NllAcc acc;
         nll_acc_init(acc);
-        Smo2 brun = smo2_identity();
         const double2 *SA = a.SA + sg.base + sg.lane;
         const double2 *SB = a.SB + sg.base + sg.lane;
         const float *kap = a.kap + sg.base + sg.lane;
@@ -303,29 +331,53 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_FWD_CTAS) lean_fwd_replay_k
                     compose_smo(a.M, brun, s, qk * a.M.q00, qk * a.M.q01, qk * a.M.q10, qk * a.M.q11);
                 }
             }
-            // reverse inclusive scan: lane l ends up with the composition of runs 31 .. l
-            Smo2 inc = brun;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const Smo2 o = shfl_down_elem(inc, d);
-                if (sg.lane + d < 32) inc = smo2_combine(o, inc);
-            }
-            Smo2 ex = shfl_down_elem(inc, 1);
-            if (sg.lane == 31) ex = smo2_identity();
-            store_strided(a.trk.sex + (int64_t)sg.w * (Smo2::N * 32) + sg.lane, 32, ex);
-            if (sg.lane == 0) store_strided(a.trk.sagg + (int64_t)sg.w * 16, 1, inc);
         }
+    }
+    if (a.do_store) {
+        // reverse inclusive scan: lane l ends up with the composition of runs 31 .. l, then the same over
+        // the CTA's warps (warp 7 first)
+        Smo2 inc = brun;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const Smo2 o = shfl_down_elem(inc, d);
+            if (sg.lane + d < 32) inc = smo2_combine(o, inc);
+        }
+        Smo2 ex = shfl_down_elem(inc, 1);
+        if (sg.lane == 31) ex = smo2_identity();
+        if (sg.lane == 0) store_strided(sh + warp * Smo2::N, 1, inc);
+        __syncthreads();
+        if (warp == 0) {
+            // lane l holds warp LEAN_WARPS - 1 - l: scan position l of the reverse order
+            Smo2 v = sg.lane < LEAN_WARPS ? load_strided<Smo2>(sh + (LEAN_WARPS - 1 - sg.lane) * Smo2::N, 1) : smo2_identity();
+#pragma unroll
+            for (int d = 1; d < LEAN_WARPS; d <<= 1) {
+                const Smo2 o = shfl_up_elem(v, d);
+                if (sg.lane >= d) v = smo2_combine(o, v);
+            }
+            if (sg.lane == LEAN_WARPS - 1) store_strided(a.trk.sagg + blockIdx.x, a.g.Gp, v);  // the group's aggregate
+            Smo2 x = shfl_up_elem(v, 1);
+            if (sg.lane == 0) x = smo2_identity();
+            if (sg.lane < LEAN_WARPS) store_strided(sh_ex + (LEAN_WARPS - 1 - sg.lane) * Smo2::N, 1, x);
+        }
+        __syncthreads();
+        if (warp < LEAN_WARPS - 1) {
+            const Smo2 wex = load_strided<Smo2>(sh_ex + warp * Smo2::N, 1);
+            ex = sg.lane < 31 ? smo2_combine(wex, ex) : wex;
+        }
+        store_strided(a.trk.sex + (int64_t)sg.w * (Smo2::N * 32) + sg.lane, 32, ex);
     }
     if (!NLL) return;
     // ---- sum of the NLL pieces: per segment, then (last CTA to finish) over the segments in order ----
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) nll += __shfl_xor_sync(FULL, nll, d);
-    if (live && sg.lane == 0) {
-        a.sc.partials[sg.w] = nll;
-        __threadfence();
-    }
+    if (sg.lane == 0) sh_part[warp] = nll;
     __syncthreads();
     if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < LEAN_WARPS; ++i) t += sh_part[i];
+        a.sc.partials[blockIdx.x] = t;
+        __threadfence();
         const int done = atomicAdd(a.sc.counter, 1);
         sh_last = done == (int)gridDim.x - 1;
     }
@@ -333,10 +385,11 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_FWD_CTAS) lean_fwd_replay_k
     if (!sh_last) return;
     __threadfence();
     double t = 0.0;
-    for (int i = threadIdx.x; i < a.g.W; i += LEAN_THREADS) t += __ldcg(a.sc.partials + i);
+    for (int i = threadIdx.x; i < a.g.G; i += LEAN_THREADS) t += __ldcg(a.sc.partials + i);
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(FULL, t, d);
-    if (sg.lane == 0) sh_part[threadIdx.x >> 5] = t;
+    __syncthreads();  // sh_part is re-used
+    if (sg.lane == 0) sh_part[warp] = t;
     __syncthreads();
     if (threadIdx.x == 0) {
         double tot = 0.0;
@@ -361,11 +414,13 @@ struct BwdIn {
 template <bool KAPPA, bool PUBLIC>
 __global__ void __launch_bounds__(LEAN_THREADS, LEAN_BWD_CTAS) lean_bwd_replay_kernel(const LeanBwdArgs a) {
     const Seg sg = seg_of(a.g);
-    if (sg.w >= a.g.W || sg.valid == 0) return;
+    if (sg.valid == 0) return;
     const bool has_qs = a.qs != nullptr;
-    // smoothed Gaussian of the first bin of the next run
-    State2 st = load_strided<State2>(a.ssuf + (int64_t)sg.w * 8, 1);
-    if (sg.lane < 31) st = smo2_apply(load_strided<Smo2>(a.trk.sex + (int64_t)sg.w * (Smo2::N * 32) + sg.lane, 32), st);
+    // smoothed Gaussian of the first bin of the next run: the one just beyond the group pushed through the
+    // runs of the group behind this one
+    State2 st = load_strided<State2>(a.ssuf + blockIdx.x, a.g.Gp);
+    if (threadIdx.x < LEAN_THREADS - 1)
+        st = smo2_apply(load_strided<Smo2>(a.trk.sex + (int64_t)sg.w * (Smo2::N * 32) + sg.lane, 32), st);
     Rs2 c{r32(st.x0), r32(st.x1), r32(st.P00), r32(st.P01), r32(st.P01), r32(st.P11)};
     const float4 *tA = a.trk.A + sg.base + sg.lane;
     const float4 *tB = a.trk.B + sg.base + sg.lane;
@@ -474,7 +529,7 @@ __global__ void lean_fill_kernel(float *rm, int64_t count, float value) {
 // =====================================================================================
 cudaError_t lean_configure() { return cudaSuccess; }
 
-static unsigned lean_grid(const LeanGeom &g) { return (unsigned)((g.W + LEAN_WARPS - 1) / LEAN_WARPS); }
+static unsigned lean_grid(const LeanGeom &g) { return (unsigned)g.G; }
 
 cudaError_t lean_fwd_compose(const LeanFwdArgs &a, cudaStream_t st) {
     lean_fwd_compose_kernel<<<lean_grid(a.g), LEAN_THREADS, 0, st>>>(a);
@@ -483,7 +538,7 @@ cudaError_t lean_fwd_compose(const LeanFwdArgs &a, cudaStream_t st) {
 
 cudaError_t lean_fwd_prefix(const LeanFwdArgs &a, cudaStream_t st) {
     const State2 prior{a.state_init, 0.0, a.cov_init, 0.0, a.cov_init};
-    lean_segment_scan_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.W, prior, a.sc.fpref);
+    lean_group_scan_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.G, a.g.Gp, prior, a.sc.fpref);
     return cudaGetLastError();
 }
 
@@ -497,7 +552,7 @@ cudaError_t lean_fwd_replay(const LeanFwdArgs &a, cudaStream_t st) {
 
 cudaError_t lean_bwd_suffix(const LeanBwdArgs &a, cudaStream_t st) {
     const State2 beyond{0.0, 0.0, 0.0, 0.0, 0.0};
-    lean_segment_scan_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.trk.sagg, a.g.W, beyond, a.ssuf);
+    lean_group_scan_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.trk.sagg, a.g.G, a.g.Gp, beyond, a.ssuf);
     return cudaGetLastError();
 }
 

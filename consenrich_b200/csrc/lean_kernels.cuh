@@ -13,15 +13,16 @@
 //                        index = seg * 32 L + i * 32 + lane
 //
 // A forward pass is three launches (no spinning between CTAs):
-//   lean_fwd_compose   every run composes its filtering element (Sarkka & Garcia-Fernandez), a warp
-//                      scan leaves per-run exclusive elements and one aggregate per segment
-//   lean_fwd_prefix    one CTA scans the segment aggregates into per-segment start states
+//   lean_fwd_compose   every run composes its filtering element (Sarkka & Garcia-Fernandez); a warp scan
+//                      and a scan over the CTA's 8 warps leave per-run exclusive elements and one
+//                      aggregate per GROUP (CTA: 8 segments = 256 runs)
+//   lean_fwd_prefix    one CTA scans the group aggregates into per-group start states
 //   lean_fwd_replay    every run replays the reference's own recursion (float32 rounding points
 //                      included, ssm_math.cuh: kf2_step) from its exact start state, writes the
 //                      compact forward track (x, P upper triangle, Q upper triangle: 32 B per bin),
 //                      and composes the smoother's run elements on the way
 // and a backward pass two:
-//   lean_bwd_suffix    one CTA scans the segments' smoothing aggregates from the far end
+//   lean_bwd_suffix    one CTA scans the groups' smoothing aggregates from the far end
 //   lean_bwd_replay    every run replays the reference's RTS recursion and forms kappa_{k+1} the
 //                      moment smoothed bins k, k+1 and their lag-one covariance are in registers
 //                      (LEAN_PUBLIC: writes stateSmoothed / stateCovarSmoothed / lagCovSmoothed in
@@ -34,18 +35,21 @@
 
 namespace cb200 {
 
-constexpr int LEAN_THREADS = 128;
-constexpr int LEAN_WARPS = LEAN_THREADS / 32;
-constexpr int LEAN_SCAN_THREADS = 512;  // the single-CTA segment scans
+constexpr int LEAN_THREADS = 256;
+constexpr int LEAN_WARPS = LEAN_THREADS / 32;  // segments per CTA = one GROUP: the unit of the cross-CTA scan
+constexpr int LEAN_SCAN_THREADS = 512;  // the single-CTA group scans
 constexpr int LEAN_MIN_BINS = 4096;     // below this the look-back kernels serve the call
 
 struct LeanGeom {
     int64_t n;     // bins
     int32_t logL;  // run length L = 1 << logL (32 or 64)
     int32_t W;     // segments (warps): ceil(n / (32 L))
+    int32_t G;     // groups (CTAs of LEAN_WARPS segments): ceil(W / LEAN_WARPS)
+    int32_t Gp;    // pitch of the per-group arrays (G rounded up to 32)
     __host__ __device__ int64_t L() const { return (int64_t)1 << logL; }
     __host__ __device__ int64_t seg_bins() const { return (int64_t)32 << logL; }
-    __host__ __device__ int64_t npad() const { return (int64_t)W * seg_bins(); }
+    // positions of the run-major arrays: whole groups (the last group's empty segments are addressable)
+    __host__ __device__ int64_t npad() const { return (int64_t)G * LEAN_WARPS * seg_bins(); }
     // run-major position of bin k
     __host__ __device__ int64_t index(int64_t k) const {
         const int64_t sb = seg_bins();
@@ -60,15 +64,18 @@ inline LeanGeom lean_geom(int64_t n, int logL) {
     g.logL = logL;
     const int64_t sb = (int64_t)32 << logL;
     g.W = (int32_t)((n + sb - 1) / sb);
+    g.G = (g.W + LEAN_WARPS - 1) / LEAN_WARPS;
+    g.Gp = (g.G + 31) / 32 * 32;
     return g;
 }
 
-// per-segment scratch of a forward pass
+// scratch of a forward pass.  Per-group arrays are structures of arrays (component j of group g at
+// [j * Gp + g]): the group scan reads them coalesced.
 struct LeanFwdScratch {
-    double *fagg;   // [W][16]     filtering aggregate of the segment (14 used)
-    double *fex;    // [W][14][32] per-run exclusive element within the segment
-    double *fpref;  // [W][8]      Gaussian at the start of the segment (5 used)
-    double *partials;  // [W][2]
+    double *fagg;   // [14][Gp]          filtering aggregate of the group
+    double *fex;    // [G * 8][14][32]   per-run exclusive element within the group
+    double *fpref;  // [5][Gp]           Gaussian at the start of the group
+    double *partials;  // [G]
     int32_t *counter;  // zero between launches
 };
 
@@ -77,8 +84,8 @@ struct LeanFwdScratch {
 struct LeanTrack {
     float4 *A;     // [npad] x0 x1 P00 P01
     float4 *B;     // [npad] P11 Q00 Q01 Q11   (Q of the same bin, float32 as the reference stores it)
-    double *sagg;  // [W][16]    smoothing aggregate of the segment (9 used)
-    double *sex;   // [W][9][32] per-run exclusive (from the far end) smoothing element
+    double *sagg;  // [9][Gp]         smoothing aggregate of the group
+    double *sex;   // [G * 8][9][32]  per-run exclusive (from the far end of the group) smoothing element
 };
 
 struct LeanFwdArgs {
@@ -97,7 +104,7 @@ struct LeanFwdArgs {
 struct LeanBwdArgs {
     LeanGeom g;
     LeanTrack trk;
-    double *ssuf;            // [W][8] smoothed Gaussian just beyond the segment (5 used)
+    double *ssuf;            // [5][Gp] smoothed Gaussian just beyond the group
     const float *qs;         // run-major processQScale or nullptr
     float *kap_out;          // run-major, written at the position of bin k+1
     float *xs, *Ps, *lag;    // LEAN_PUBLIC: the reference's layouts

@@ -1467,7 +1467,9 @@ cudaError_t launch_scan(const typename Tr::Args &a, const ScanWorkspace &ws, int
     // aggregate-only: one CTA per tile; full scan: as many CTAs as are resident, each working through
     // the tiles it claims
     const int grid = AGG_ONLY ? ntiles : (slots > 0 && slots < ntiles ? slots : ntiles);
-    scan_kernel<Tr, AGG_ONLY><<<grid, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, ws, ntiles, nsub, ntiles);
+    ScanWorkspace w = ws;
+    if (w.dbg && ntiles > w.dbg_tiles) w.dbg = nullptr;  // the stamps of this launch would not fit the armed buffer
+    scan_kernel<Tr, AGG_ONLY><<<grid, SCAN_THREADS, ScanSmem<Tr>::BYTES, st>>>(a, w, ntiles, nsub, ntiles);
     if (launches) *launches += 1;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;

@@ -30,7 +30,8 @@ struct ScanWorkspace {    // sized by scan_workspace_bytes(n); zeroed once when 
     int32_t *flags;       // [ntiles]  epoch4 + 1 = aggregate published, epoch4 + 2 = inclusive prefix published
     int32_t *counters;    // [0] dynamic tile ticket, [1] tiles finished (reset by the last tile)
     int32_t epoch4;       // 4 * launch epoch: flags of earlier launches read as "nothing"
-    long long *dbg;       // diagnostics: [ntiles][4] globaltimer stamps (start, pass 1 done, prefix known, end) or nullptr
+    long long *dbg;       // diagnostics: [dbg_tiles][8] globaltimer stamps (cb200_debug_scan_times) or nullptr
+    int32_t dbg_tiles;    // tiles the diagnostics buffer holds: launches with more tiles do not stamp
 };
 
 struct FwdArgs {

@@ -51,7 +51,7 @@ class TrackSweep:
         self.m, self.n, self.d = int(m), int(n), int(state_dim)
         self.dev = torch.device("cuda", device)
         # kernels are enqueued on torch's CURRENT stream; the legacy default stream has handle 0, which
-        # the C ABI reads as "make your own stream", so it is passed as the per-thread alias instead
+        # the C ABI reads as "make your own stream", so it is passed as cudaStreamLegacy (handle 0x1) instead
         self.ctx = ctx or _lib.Context(device, self._stream_handle(torch.cuda.current_stream(self.dev)))
         self.stride = (self.n + 31) // 32 * 32
         f32, f64 = torch.float32, torch.float64

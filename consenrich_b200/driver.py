@@ -13,6 +13,7 @@ Built: ``_relativeSignChangePerKB`` (core.py:2647-2700) and ``_perIntervalOutput
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 
 import numpy as np
 
@@ -21,6 +22,17 @@ from .native import _ctx, _ptr
 
 _HOOKS = ("_relativeSignChangePerKB", "_perIntervalOutputDiagnosticTracks")
 _saved: dict = {}
+
+
+class HostPathWarning(RuntimeWarning):
+    """A hooked driver function was handed inputs its device version does not cover and ran the
+    reference's own host function instead.  Never silent: runConsenrich itself passes float32 matrices,
+    which are covered, so this only fires for callers that deviate from it."""
+
+
+def _host_path(name, why):
+    warnings.warn(f"consenrich_b200.driver: {name} ran the reference's host implementation ({why})", HostPathWarning,
+                  stacklevel=3)
 
 
 def weighted_mean_residual(stateValues, matrixData, matrixMunc, background=None, pad=0.0):
@@ -49,14 +61,17 @@ def weighted_mean_residual(stateValues, matrixData, matrixMunc, background=None,
 
 def _make_relative_sign_change(module, original):
     def _relativeSignChangePerKB(stateValues, matrixData, matrixMunc, *, intervalSizeBP, background=None, pad=0.0):
-        # argument handling of core.py:2656-2669: anything the device version does not cover goes to the
-        # function it replaced
+        # argument handling of core.py:2656-2669.  Malformed shapes go to the function that was replaced, which
+        # raises the reference's own errors for them; matrices that are not float32 (runConsenrich always
+        # passes float32) are computed by it in their own precision, with a HostPathWarning
         if stateValues is None or matrixData is None or matrixMunc is None:
             return None
         data, munc = np.asarray(matrixData), np.asarray(matrixMunc)
-        if (data.dtype != np.float32 or munc.dtype != np.float32 or data.ndim != 2 or munc.shape != data.shape
-                or data.shape[1] != np.asarray(stateValues).size
-                or (background is not None and np.asarray(background).size != data.shape[1])):
+        malformed = (data.ndim != 2 or munc.shape != data.shape or data.shape[1] != np.asarray(stateValues).size
+                     or (background is not None and np.asarray(background).size != data.shape[1]))
+        if malformed or data.dtype != np.float32 or munc.dtype != np.float32:
+            if not malformed:
+                _host_path("_relativeSignChangePerKB", f"matrices are {data.dtype}/{munc.dtype}, not float32")
             return original(stateValues, matrixData, matrixMunc, intervalSizeBP=intervalSizeBP, background=background,
                             pad=pad)
         residual = weighted_mean_residual(stateValues, data, munc, background, pad)
@@ -112,7 +127,9 @@ def _make_interval_diagnostics(module, original):
         covar_in, munc = np.asarray(stateCovarForward), np.asarray(matrixMunc)
         if covar_in.dtype != np.float32 or munc.dtype != np.float32 or (
                 pNoiseForward is not None and np.asarray(pNoiseForward).dtype != np.float32):
-            return original(**kwargs)  # the device version reads float32 tracks, as runConsenrich passes them
+            # the device version reads float32 tracks, as runConsenrich passes them
+            _host_path("_perIntervalOutputDiagnosticTracks", "tracks are not float32")
+            return original(**kwargs)
         # shape checks and vector preparation of core.py:7756-7785, 7802-7838 (same texts)
         q0 = np.asarray(matrixQ0, dtype=np.float64)
         f = np.asarray(matrixF, dtype=np.float64)
@@ -121,6 +138,7 @@ def _make_interval_diagnostics(module, original):
         if covar_in.ndim != 3 or covar_in.shape[1] < dim or covar_in.shape[2] < dim:
             raise ValueError("stateCovarForward shape does not match stateModel")
         if covar_in.shape[1] != covar_in.shape[2]:
+            _host_path("_perIntervalOutputDiagnosticTracks", "stateCovarForward is not square")
             return original(**kwargs)
         n = int(covar_in.shape[0])
         if munc.ndim != 2 or int(munc.shape[1]) != n:

@@ -53,6 +53,16 @@ def _c32(a, name, ndim):
     return a
 
 
+def _buf32(a, name, shape_min):
+    """A caller-supplied in/out buffer: C-contiguous float32 of at least ``shape_min`` rows and exactly the
+    trailing dimensions (the reference's typed memoryviews raise on anything else; a raw pointer would
+    read or write out of bounds)."""
+    a = _c32(a, name, len(shape_min))
+    if a.shape[0] < shape_min[0] or tuple(a.shape[1:]) != tuple(shape_min[1:]):
+        raise ValueError(f"{name}: shape {tuple(a.shape)} does not hold {tuple(shape_min)}")
+    return a
+
+
 def _vec32(a, name, n):
     if a is None:
         return None
@@ -162,10 +172,11 @@ def _forward(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalT
         raise ValueError("vectorD length must match intervalCount")
     if _apn_live(useAPN, use_qscale, Q0, dim):
         raise NotImplementedError(_APN_MSG)
+    _buf32(vectorD, "vectorD", (n,))
     if do_store:
-        _c32(stateForward, "stateForward", 2)
-        _c32(stateCovarForward, "stateCovarForward", 3)
-        _c32(pNoiseForward, "pNoiseForward", 3)
+        _buf32(stateForward, "stateForward", (n, dim))
+        _buf32(stateCovarForward, "stateCovarForward", (n, dim, dim))
+        _buf32(pNoiseForward, "pNoiseForward", (max(n - 1, 1), dim, dim))
     mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kapMin, kapMax, use_lambda,
                 use_kappa, use_qscale, returnNLL, storeNLLInD)
     sum_d, sum_nll = C.c_double(0.0), C.c_double(0.0)
@@ -226,9 +237,13 @@ def _backward(dim, matrixData, matrixF, stateForward, stateCovarForward, pNoiseF
     res = postFitResiduals if postFitResiduals is not None else alloc((n, m), np.float32)
     if n <= 0:
         return (xs, Ps, lag, res)
-    xf = _c32(stateForward, "stateForward", 2)
-    Pf = _c32(stateCovarForward, "stateCovarForward", 3)
-    Qf = _c32(pNoiseForward, "pNoiseForward", 3)
+    xf = _buf32(stateForward, "stateForward", (n, dim))
+    Pf = _buf32(stateCovarForward, "stateCovarForward", (n, dim, dim))
+    Qf = _buf32(pNoiseForward, "pNoiseForward", (max(n - 1, 1), dim, dim))
+    _buf32(xs, "stateSmoothed", (n, dim))
+    _buf32(Ps, "stateCovarSmoothed", (n, dim, dim))
+    _buf32(lag, "lagCovSmoothed", (1, dim, dim))
+    _buf32(res, "postFitResiduals", (n, m))
     mo = _model(dim, matrixF, np.eye(2), 0.0, 1.0, 0.0, 1.0, 1.0, 1.0, 1.0, False, False, False, False, False)
     ctx = _ctx()
     _lib.check(ctx._lib.cb200_host_backward_pass(

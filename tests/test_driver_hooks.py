@@ -86,8 +86,9 @@ def test_hook_installed_into_the_reference_driver():
     try:
         assert core._relativeSignChangePerKB is not original
         got = [core._relativeSignChangePerKB(state, data, munc, intervalSizeBP=25, background=b, pad=1e-4) for b in (None, bg)]
-        # float64 matrices are not covered on the device: they go to the function that was replaced
-        got64 = core._relativeSignChangePerKB(state, data.astype(np.float64), munc.astype(np.float64), intervalSizeBP=25)
+        # float64 matrices are not covered on the device: they go to the function that was replaced, loudly
+        with pytest.warns(driver.HostPathWarning):
+            got64 = core._relativeSignChangePerKB(state, data.astype(np.float64), munc.astype(np.float64), intervalSizeBP=25)
         assert core._relativeSignChangePerKB(None, data, munc, intervalSizeBP=25) is None
     finally:
         driver.uninstall_driver(core)
@@ -204,7 +205,7 @@ def test_interval_diagnostics_hook_in_the_reference_driver():
 
 def test_hooks_pass_uncovered_inputs_to_the_functions_they_replace():
     """No GPU needed: float64 matrices are not covered on the device, so the installed hooks hand them to the
-    reference's own functions; uninstall restores the originals."""
+    reference's own functions -- with a HostPathWarning, never silently; uninstall restores the originals."""
     core = ref_core()
     from consenrich_b200 import driver
     rng = np.random.default_rng(10)
@@ -220,9 +221,11 @@ def test_hooks_pass_uncovered_inputs_to_the_functions_they_replace():
     try:
         assert core._relativeSignChangePerKB is not originals[0]
         assert core._perIntervalOutputDiagnosticTracks is not originals[1]
-        got_sign = core._relativeSignChangePerKB(state, data.astype(np.float64), munc.astype(np.float64), intervalSizeBP=25,
-                                                 background=bg, pad=1e-4)
-        got_diag = core._perIntervalOutputDiagnosticTracks(**kw64)
+        with pytest.warns(driver.HostPathWarning, match="_relativeSignChangePerKB"):
+            got_sign = core._relativeSignChangePerKB(state, data.astype(np.float64), munc.astype(np.float64),
+                                                     intervalSizeBP=25, background=bg, pad=1e-4)
+        with pytest.warns(driver.HostPathWarning, match="_perIntervalOutputDiagnosticTracks"):
+            got_diag = core._perIntervalOutputDiagnosticTracks(**kw64)
         assert core._relativeSignChangePerKB(state, None, munc, intervalSizeBP=25) is None
     finally:
         driver.uninstall_driver(core)
