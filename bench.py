@@ -468,24 +468,28 @@ def run_b200_arm(args):
         from concurrent.futures import ThreadPoolExecutor
         pool = ThreadPoolExecutor(max(1, args.e2e_threads), initializer=lambda: torch.cuda.set_device(local))
 
+        e2e_ctxs, e2e_lock = {}, threading.Lock()
+
         def one(c):
             hd, hv = host_mats(bins_all[c])
-            return float(cb.cfixedBackgroundECM(**ecm_kwargs(hd, hv))[1])
+            nll = float(cb.cfixedBackgroundECM(**ecm_kwargs(hd, hv))[1])
+            x = _lib.default_context(local)  # this worker thread's context (launch accounting)
+            with e2e_lock:
+                e2e_ctxs[id(x)] = x
+            return nll
 
         def e2e_step():
             return sum(pool.map(one, mine))
 
         e2e_step()  # warm-up: device arenas, page-locked result pool
-        e2e_ctxs = list(pool.map(lambda _: _lib.default_context(local), range(4 * max(1, args.e2e_threads))))
-        e2e_ctxs = list({id(x): x for x in e2e_ctxs}.values())
-        hl0 = sum(x.launch_count for x in e2e_ctxs)
+        hl0 = sum(x.launch_count for x in e2e_ctxs.values())
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             nll_e2e = e2e_step()
         torch.cuda.synchronize(dev)
         e2e_s = time.perf_counter() - t0
-        e2e_launches = sum(x.launch_count for x in e2e_ctxs) - hl0
+        e2e_launches = sum(x.launch_count for x in e2e_ctxs.values()) - hl0
         pool.shutdown()
         h2d = sum(2 * 4 * m * n for n in my_bins)                                       # tracks (kappa starts at 1 on the device)
         d2h = sum(n * (8 + 16) + (n - 1) * 16 + n * m * 4 + 4 * n + 16 for n in my_bins)  # xs, Ps, lag, residuals, kappa, scalars
@@ -636,7 +640,7 @@ def main():
     ap.add_argument("--cpu-bins", type=int, default=None, help="bins of the cpu_baseline / check slice")
     args = ap.parse_args()
     if args.cpu_bins is None:
-        args.cpu_bins = max(50_000, int(2.0e7 / CONFIGS[args.config]["m"]))  # ~15-25 s on one core
+        args.cpu_bins = max(50_000, int(2.0e8 / CONFIGS[args.config]["m"]))  # ~15-25 s on one core
     # stdout carries exactly ONE line, the JSON: libraries that write there on their own (NCCL prints its
     # version line to stdout under torchrun) are sent to stderr for the length of the run
     sys.stdout.flush()

@@ -9,6 +9,7 @@ Only what the path needs lives here:
 * ``driver``     device versions of the driver-side ``[tracks x intervals]`` reductions of ``consenrich.core``
 * ``device``     device-resident sweeps on torch tensors (torch is only a tensor carrier)
 * ``sharding``   chromosome / bin-range sharding across ranks (torch.distributed plumbing)
+* ``writers``    bedGraph chunks formatted on the device, byte-identical to the reference's pandas writer
 
 There is no CPU implementation: importing works anywhere, calling requires the built library
 and a CUDA device, and fails loudly otherwise.
@@ -21,5 +22,6 @@ from .native import (cEMA, cFinalizeMuncEBTrack, cMuncObservationMomentSeedPass,
                      cforwardPass, cforwardPassLevel, csolveZeroCenteredBackground, install, sweep, uninstall)
 
 from .driver import install_driver, uninstall_driver  # noqa: E402,F401
+from . import writers  # noqa: E402,F401
 
 __version__ = "0.1.0"

@@ -14,11 +14,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libconsenrich_b200.so")
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 FAM_FOLD, FAM_FORWARD, FAM_BACKWARD, FAM_RESIDUALS, FAM_PRECISION = range(5)
 FAMILY_NAMES = ("fold", "forward_scan", "backward_scan", "residuals", "precision_updates", "background", "munc",
-                "forward_compose", "segment_scan", "backward_publish")
+                "forward_compose", "segment_scan", "backward_publish", "writer")
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -33,10 +33,12 @@ class Model(C.Structure):
     """cb200_model"""
     _fields_ = [
         ("state_dim", C.c_int32), ("use_lambda", C.c_int32), ("use_kappa", C.c_int32), ("use_qscale", C.c_int32),
-        ("return_nll", C.c_int32), ("store_nll_in_d", C.c_int32), ("reserved0", C.c_int32), ("reserved1", C.c_int32),
+        ("return_nll", C.c_int32), ("store_nll_in_d", C.c_int32), ("use_apn", C.c_int32), ("reserved1", C.c_int32),
         ("F", C.c_double * 4), ("Q0", C.c_double * 4),
         ("state_init", C.c_double), ("cov_init", C.c_double), ("pad", C.c_double),
         ("lam_min", C.c_double), ("lam_max", C.c_double), ("kap_min", C.c_double), ("kap_max", C.c_double),
+        ("apn_min_q", C.c_double), ("apn_max_q", C.c_double), ("apn_thresh", C.c_double), ("apn_scale", C.c_double),
+        ("apn_pc", C.c_double),
     ]
 
 
@@ -154,6 +156,10 @@ SIGNATURES = {
     "cb200_host_interval_diagnostics": (C.c_int, [_vp, _vp, _i64, _vp, _dbl, C.POINTER(DiagGainArgs), _vp, _vp]),
     "cb200_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
     "cb200_host_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
+    "cb200_bedgraph_chunk": (C.c_int, [_vp, C.c_char_p, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, C.POINTER(_vp),
+                                       C.POINTER(_i64)]),
+    "cb200_host_bedgraph_chunk": (C.c_int, [_vp, C.c_char_p, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64,
+                                            C.POINTER(_vp), C.POINTER(_i64)]),
 }
 
 _lib = None

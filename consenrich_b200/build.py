@@ -16,8 +16,8 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libconsenrich_b200.so")
-SOURCES = ["ssm_kernels.cu", "lean_kernels.cu", "background_kernels.cu", "munc_kernels.cu", "cabi.cu"]
-HEADERS = ["ssm_math.cuh", "ssm_kernels.cuh", "lean_kernels.cuh", "background_kernels.cuh", "munc_kernels.cuh", os.path.join(ROOT, "include", "consenrich_b200.h")]
+SOURCES = ["ssm_kernels.cu", "lean_kernels.cu", "apn_kernels.cu", "writer_kernels.cu", "background_kernels.cu", "munc_kernels.cu", "cabi.cu"]
+HEADERS = ["ssm_math.cuh", "ssm_kernels.cuh", "lean_kernels.cuh", "writer_kernels.cuh", "background_kernels.cuh", "munc_kernels.cuh", os.path.join(ROOT, "include", "consenrich_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared", "-cudart", "static",

@@ -20,6 +20,7 @@
 #include "lean_kernels.cuh"
 #include "background_kernels.cuh"
 #include "munc_kernels.cuh"
+#include "writer_kernels.cuh"
 
 using namespace cb200;
 
@@ -71,7 +72,7 @@ struct DevBuf {
 };
 
 enum Family { FAM_FOLD = 0, FAM_FWD = 1, FAM_BWD = 2, FAM_RESID = 3, FAM_PREC = 4, FAM_BG = 5, FAM_MUNC = 6,
-              FAM_COMPOSE = 7, FAM_SEGSCAN = 8, FAM_PUBLISH = 9, FAM_COUNT = 10 };
+              FAM_COMPOSE = 7, FAM_SEGSCAN = 8, FAM_PUBLISH = 9, FAM_WRITER = 10, FAM_COUNT = 11 };
 
 struct TimedSpan {
     cudaEvent_t a, b;
@@ -96,6 +97,9 @@ struct cb200_ctx {
     DevBuf bg_ws, bg_w, bg_rhs, bg_out, bg_status;  // background solve: workspace, operands, outcome
     // lean sweeps (lean_kernels.cuh): run-major statistics, multipliers, two sets of forward tracks, scratch
     DevBuf ln_SA, ln_SB, ln_kap, ln_qs, ln_A[2], ln_B[2], ln_sagg[2], ln_sex[2], ln_fagg, ln_fex, ln_fpref, ln_ssuf, ln_part;
+    DevBuf wr_text, wr_tiles, wr_vals, wr_starts, wr_ends;  // bedGraph writer
+    char *wr_host = nullptr;  // pinned text buffer
+    size_t wr_host_cap = 0;
     DevBuf mask;  // MUNC stage: exclusion mask
     DevBuf seed_mat[6], seed_vec[7];  // MUNC seed pass: count floor, rho in, 4 outputs; 5 input + 2 output vectors
     double *sums_host = nullptr;  // pinned double[2]
@@ -267,6 +271,14 @@ int do_fold(cb200_ctx *c, const float *data, const float *munc, int64_t m, int64
     return CB200_OK;
 }
 
+// ECM_useAPN is live exactly when the reference's loop would feed D_k back into the process noise
+// (cconsenrich.pyx:510, 6574-6576, 6997-6998)
+bool apn_live(const cb200_model *mo) {
+    if (!mo->use_apn || mo->use_qscale) return false;
+    const double q_diag = mo->state_dim == 2 ? 0.5 * (mo->Q0[0] + mo->Q0[3]) : mo->Q0[0];
+    return q_diag > 1.0e-12;
+}
+
 int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t stride, int64_t m, int64_t n,
                const float *lam, const float *kap, const float *qs, const double *init_state, float *xf, float *Pf,
                float *Qf, float *D, double *sums, double *agg_out, bool aggregate_only, float *q_head = nullptr,
@@ -279,6 +291,38 @@ int do_forward(cb200_ctx *c, const cb200_model *mo, const double *stats, int64_t
     if (mo->use_lambda && !lam) return fail(CB200_ERR_INVALID, "lambdaExp is required when use_lambda is set");
     if (mo->use_kappa && !kap) return fail(CB200_ERR_INVALID, "processPrecExp is required when use_kappa is set");
     if (mo->use_qscale && !qs) return fail(CB200_ERR_INVALID, "processQScale is required when use_qscale is set");
+    if (apn_live(mo)) {
+        // adaptive process noise: a sequential recursion over the fold statistics (apn_kernels.cu)
+        if (aggregate_only || init_state)
+            return fail(CB200_ERR_UNSUPPORTED, "adaptive process noise cannot run on a shard of a split chromosome: the "
+                                               "feedback is sequential over the whole chromosome");
+        if (mo->use_kappa) return fail(CB200_ERR_INVALID, "process precision multipliers are not live under adaptive process noise");
+        ApnArgs p{};
+        p.SA = reinterpret_cast<const double2 *>(stats);
+        p.SB = reinterpret_cast<const double2 *>(stats + 2 * stride);
+        p.lam = lam;
+        p.xf = xf; p.Pf = Pf; p.Qf = Qf; p.D = D;
+        p.sums = sums;
+        p.n = n;
+        p.m = (double)m;
+        p.inv_m = 1.0 / (double)m;
+        p.mlog2pi = (double)m * log(6.2831853071795864769);
+        p.M = to_model2(mo);
+        p.state_init = mo->state_init;
+        p.cov_init = mo->cov_init;
+        p.lam_min = mo->lam_min; p.lam_max = mo->lam_max;
+        p.apn_min_q = mo->apn_min_q; p.apn_max_q = mo->apn_max_q; p.apn_thresh = mo->apn_thresh;
+        p.apn_scale = mo->apn_scale; p.apn_pc = mo->apn_pc;
+        p.q_diag = d == 2 ? 0.5 * (mo->Q0[0] + mo->Q0[3]) : mo->Q0[0];
+        p.use_lambda = mo->use_lambda; p.want_nll = mo->return_nll; p.nll_in_d = mo->store_nll_in_d;
+        p.do_store = store ? 1 : 0;
+        {
+            Span sp(c, FAM_FWD);
+            CU_TRY(launch_apn_forward(d, p, c->stream));
+        }
+        c->launches += 1;
+        return CB200_OK;
+    }
     ScanWorkspace ws;
     CB_TRY(next_scan_ws(c, n, &ws));
     FwdArgs a{};
@@ -506,13 +550,14 @@ void cb200_ctx_destroy(cb200_ctx *c) {
                       &c->bg_ws, &c->bg_w, &c->bg_rhs, &c->bg_out, &c->bg_status, &c->mask,
                       &c->ln_SA, &c->ln_SB, &c->ln_kap, &c->ln_qs, &c->ln_A[0], &c->ln_A[1], &c->ln_B[0], &c->ln_B[1],
                       &c->ln_sagg[0], &c->ln_sagg[1], &c->ln_sex[0], &c->ln_sex[1], &c->ln_fagg, &c->ln_fex, &c->ln_fpref,
-                      &c->ln_ssuf, &c->ln_part,
+                      &c->ln_ssuf, &c->ln_part, &c->wr_text, &c->wr_tiles, &c->wr_vals, &c->wr_starts, &c->wr_ends,
                       &c->seed_mat[0], &c->seed_mat[1], &c->seed_mat[2], &c->seed_mat[3], &c->seed_mat[4], &c->seed_mat[5],
                       &c->seed_vec[0], &c->seed_vec[1], &c->seed_vec[2], &c->seed_vec[3], &c->seed_vec[4], &c->seed_vec[5],
                       &c->seed_vec[6]};
     for (DevBuf *b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->sums_host) cudaFreeHost(c->sums_host);
+    if (c->wr_host) cudaFreeHost(c->wr_host);
     for (auto &s : c->spans) {
         cudaEventDestroy(s.a);
         cudaEventDestroy(s.b);
@@ -1077,7 +1122,7 @@ int cb200_ecm_device(cb200_ctx *c, const cb200_model *mo_in, const cb200_ecm_opt
     SmoFuse sfa, sfb;  // current / spare set, like the forward tracks
     {
         const int ns = scan_pick_nsub(n, 0);
-        if (d == 2 && CHUNK * ns >= HEAD_BINS) {
+        if (d == 2 && CHUNK * ns >= HEAD_BINS && !apn_live(&mo)) {
             const int64_t tiles = scan_num_tiles(n, ns);
             const int64_t runs = tiles * SCAN_THREADS;
             const int64_t pitch = round_up(runs, 32);
@@ -1925,6 +1970,100 @@ int cb200_host_ema(cb200_ctx *c, const void *x, int64_t n, int32_t is_double, do
     CB_TRY(cb200_ema(c, c->seed_mat[1].p, n, is_double, alpha, c->seed_mat[2].p));
     CB_TRY(d2h(c, out, c->seed_mat[2].p, bytes));
     CU_TRY(cudaStreamSynchronize(c->stream));
+    return CB200_OK;
+}
+
+// ---- bedGraph text ---------------------------------------------------------------------
+static int bedgraph_core(cb200_ctx *c, const char *chrom, int64_t n, const int64_t *starts, const int64_t *ends,
+                         int64_t start0, int64_t step, int64_t end_clip, const float *values, int64_t value_stride,
+                         int64_t *bytes) {
+    if (!chrom) return fail(CB200_ERR_INVALID, "chrom is NULL");
+    const size_t cl = strlen(chrom);
+    if (cl == 0 || cl > (size_t)BG_MAX_CHROM) return fail(CB200_ERR_INVALID, "chromosome name must be 1..%d bytes", BG_MAX_CHROM);
+    if (n < 0 || value_stride <= 0) return fail(CB200_ERR_INVALID, "bad row count or value stride");
+    if ((starts == nullptr) != (ends == nullptr)) return fail(CB200_ERR_INVALID, "starts and ends are given together or not at all");
+    *bytes = 0;
+    if (n == 0) return CB200_OK;
+    if (!values) return fail(CB200_ERR_INVALID, "values is NULL");
+    BedGraphArgs a{};
+    memcpy(a.chrom, chrom, cl);
+    a.chrom_len = (int32_t)cl;
+    a.n = n;
+    a.starts = reinterpret_cast<const long long *>(starts);
+    a.ends = reinterpret_cast<const long long *>(ends);
+    a.start0 = start0; a.step = step; a.end_clip = end_clip;
+    a.values = values;
+    a.value_stride = value_stride;
+    const int64_t tiles = bedgraph_tiles(n);
+    CB_TRY(ensure(c, c->wr_tiles, (size_t)(tiles + 1) * 8));
+    long long *tile_bytes = static_cast<long long *>(c->wr_tiles.p);
+    {
+        Span sp(c, FAM_WRITER);
+        CU_TRY(launch_bedgraph_lengths(a, tile_bytes, c->stream));
+    }
+    c->launches += 2;
+    long long total = 0;
+    CU_TRY(cudaMemcpyAsync(&total, tile_bytes + tiles, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    CB_TRY(ensure(c, c->wr_text, (size_t)total + 16));
+    {
+        Span sp(c, FAM_WRITER);
+        CU_TRY(launch_bedgraph_write(a, tile_bytes, static_cast<char *>(c->wr_text.p), total, c->stream));
+    }
+    c->launches += 1;
+    *bytes = total;
+    return CB200_OK;
+}
+
+int cb200_bedgraph_chunk(cb200_ctx *c, const char *chrom, int64_t n, const int64_t *starts, const int64_t *ends,
+                         int64_t start0, int64_t step, int64_t end_clip, const float *values, int64_t value_stride,
+                         const char **text, int64_t *bytes) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !text || !bytes) return fail(CB200_ERR_INVALID, "NULL argument");
+    *text = nullptr;
+    CB_TRY(bedgraph_core(c, chrom, n, starts, ends, start0, step, end_clip, values, value_stride, bytes));
+    *text = static_cast<const char *>(c->wr_text.p);
+    return CB200_OK;
+}
+
+int cb200_host_bedgraph_chunk(cb200_ctx *c, const char *chrom, int64_t n, const int64_t *starts, const int64_t *ends,
+                              int64_t start0, int64_t step, int64_t end_clip, const float *values,
+                              int64_t value_stride, const char **text, int64_t *bytes) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !text || !bytes) return fail(CB200_ERR_INVALID, "NULL argument");
+    *text = nullptr;
+    *bytes = 0;
+    if (n < 0 || value_stride <= 0) return fail(CB200_ERR_INVALID, "bad row count or value stride");
+    if (n == 0) return CB200_OK;
+    if (!values) return fail(CB200_ERR_INVALID, "values is NULL");
+    if ((starts == nullptr) != (ends == nullptr)) return fail(CB200_ERR_INVALID, "starts and ends are given together or not at all");
+    // only the strided values travel (the level column of a [n][2] state is gathered on the host side of the copy)
+    CB_TRY(ensure(c, c->wr_vals, (size_t)n * 4));
+    CU_TRY(cudaMemcpy2DAsync(c->wr_vals.p, 4, values, (size_t)value_stride * 4, 4, (size_t)n, cudaMemcpyHostToDevice,
+                             c->stream));
+    const int64_t *ds = nullptr, *de = nullptr;
+    if (starts) {
+        CB_TRY(ensure(c, c->wr_starts, (size_t)n * 8));
+        CB_TRY(ensure(c, c->wr_ends, (size_t)n * 8));
+        CB_TRY(h2d(c, c->wr_starts.p, starts, (size_t)n * 8));
+        CB_TRY(h2d(c, c->wr_ends.p, ends, (size_t)n * 8));
+        ds = static_cast<const int64_t *>(c->wr_starts.p);
+        de = static_cast<const int64_t *>(c->wr_ends.p);
+    }
+    int64_t total = 0;
+    CB_TRY(bedgraph_core(c, chrom, n, ds, de, start0, step, end_clip, static_cast<const float *>(c->wr_vals.p), 1, &total));
+    if ((size_t)total + 16 > c->wr_host_cap) {
+        if (c->wr_host) CU_TRY(cudaFreeHost(c->wr_host));
+        c->wr_host = nullptr;
+        c->wr_host_cap = 0;
+        const size_t want = (size_t)total + (size_t)total / 4 + 4096;
+        CU_TRY(cudaMallocHost(reinterpret_cast<void **>(&c->wr_host), want));
+        c->wr_host_cap = want;
+    }
+    CB_TRY(d2h(c, c->wr_host, c->wr_text.p, (size_t)total));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *text = c->wr_host;
+    *bytes = total;
     return CB200_OK;
 }
 

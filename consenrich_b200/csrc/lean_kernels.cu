@@ -250,8 +250,9 @@ struct ReplayIn {
 // reverse scan meets first)
 __device__ __forceinline__ void compose_smo(const Model2 &M, Smo2 &brun, const Kf2 &f, double Q00, double Q01,
                                             double Q10, double Q11) {
-    const Rts2 r = rts2_gain<true>(M, f.x0, f.x1, f.P00, f.P01, f.P10, f.P11, r32(Q00), r32(Q01), r32(Q10), r32(Q11));
-    brun = smo2_combine(smo2_from_rts(r, f.x0, f.x1, f.P00, f.P01, f.P11), brun);
+    (void)Q10;  // the scan requires a symmetric Q0 (cb200: check_model)
+    brun = smo2_combine(smo2_from_filtered_canon(M.F01, f.x0, f.x1, f.P00, f.P01, f.P11, r32(Q00), r32(Q01), r32(Q11)),
+                        brun);
 }
 
 template <bool NLL>

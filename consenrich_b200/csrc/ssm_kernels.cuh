@@ -83,6 +83,23 @@ struct BwdArgs {
     double qi00, qi01, qi10, qi11;  // Q0^-1 (state_dim 1: qi00 = 1 / Q0[0])
 };
 
+// forward filter with adaptive process noise (apn_kernels.cu): a sequential recursion over the linear
+// fold statistics
+struct ApnArgs {
+    const double2 *SA, *SB;
+    const float *lam;
+    float *xf, *Pf, *Qf, *D;   // xf/Pf/Qf may be nullptr (do_store == 0); D may be nullptr
+    double *sums;              // device double[2] or nullptr: {sum D, sum NLL}
+    int64_t n;
+    double m, inv_m, mlog2pi;
+    Model2 M;
+    double state_init, cov_init, lam_min, lam_max;
+    double apn_min_q, apn_max_q, apn_thresh, apn_scale, apn_pc;
+    double q_diag;             // 0.5 (Q0[0,0] + Q0[1,1]), or Q0[0,0] for the level model
+    int32_t use_lambda, want_nll, nll_in_d, do_store;
+};
+cudaError_t launch_apn_forward(int dim, const ApnArgs &a, cudaStream_t st);
+
 size_t scan_workspace_bytes(int64_t n);
 ScanWorkspace scan_workspace_carve(void *base, int64_t n);
 int64_t scan_num_tiles(int64_t positions, int nsub);

@@ -14,7 +14,7 @@ unchanged.  Arguments the reference accepts but never forwards to its loops (``c
 ``projectStateDuringFiltering``, ``stateLowerBound``/``stateUpperBound``; pyx:6403-6406) are
 accepted and ignored here too.  Adaptive process noise (``ECM_useAPN`` without a
 ``processQScale``; pyx:510-527) is a per-bin nonlinear feedback that no associative scan can
-express: it raises NotImplementedError instead of silently running something else.
+express: that forward pass runs as a sequential recursion on the device (csrc/apn_kernels.cu).
 
 There is no CPU fallback: without the built library or without a CUDA device every function
 raises.
@@ -101,14 +101,15 @@ def _apn_live(useAPN, use_qscale, Q0, dim) -> bool:
     return q_diag > 1.0e-12
 
 
-_APN_MSG = ("ECM_useAPN without processQScale is a sequential nonlinear feedback (cconsenrich.pyx:510-527) that the "
-            "parallel-in-time scan cannot express; consenrich_b200 has no CPU fallback. Pass processQScale or "
-            "disable APN.")
+_APN_DEFAULTS = (1.0e-4, 1000.0, 5.0, 10.0, 2.0)  # APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC
 
 
 def _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kapMin, kapMax, use_lambda, use_kappa,
-           use_qscale, returnNLL, storeNLLInD):
+           use_qscale, returnNLL, storeNLLInD, useAPN=False, apn=_APN_DEFAULTS):
     mo = _lib.Model()
+    # adaptive process noise (pyx:510-527): the scalars arrive as C float in the reference (pyx:6422-6426)
+    mo.use_apn = int(bool(useAPN))
+    mo.apn_min_q, mo.apn_max_q, mo.apn_thresh, mo.apn_scale, mo.apn_pc = map(_f32, apn)
     mo.state_dim = dim
     mo.use_lambda, mo.use_kappa, mo.use_qscale = int(use_lambda), int(use_kappa), int(use_qscale)
     mo.return_nll, mo.store_nll_in_d = int(bool(returnNLL)), int(bool(storeNLLInD))
@@ -130,7 +131,8 @@ def _ctx(device=None):
 
 def _forward(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount, stateInit,
              stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD, returnNLL, storeNLLInD,
-             lambdaExp, processPrecExp, useObs, useProc, useAPN, lamMin, lamMax, kapMin, kapMax, processQScale):
+             lambdaExp, processPrecExp, useObs, useProc, useAPN, lamMin, lamMax, kapMin, kapMax, processQScale,
+             apn=_APN_DEFAULTS):
     data = _c32(matrixData, "matrixData", 2)
     munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
     m, n = data.shape
@@ -170,15 +172,13 @@ def _forward(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalT
         vectorD = np.empty(n, dtype=np.float32)
     elif vectorD.shape[0] < n:
         raise ValueError("vectorD length must match intervalCount")
-    if _apn_live(useAPN, use_qscale, Q0, dim):
-        raise NotImplementedError(_APN_MSG)
     _buf32(vectorD, "vectorD", (n,))
     if do_store:
         _buf32(stateForward, "stateForward", (n, dim))
         _buf32(stateCovarForward, "stateCovarForward", (n, dim, dim))
         _buf32(pNoiseForward, "pNoiseForward", (max(n - 1, 1), dim, dim))
     mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin, lamMax, kapMin, kapMax, use_lambda,
-                use_kappa, use_qscale, returnNLL, storeNLLInD)
+                use_kappa, use_qscale, returnNLL, storeNLLInD, useAPN, apn)
     sum_d, sum_nll = C.c_double(0.0), C.c_double(0.0)
     ctx = _ctx()
     _lib.check(ctx._lib.cb200_host_forward_pass(
@@ -206,7 +206,8 @@ def cforwardPass(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalTo
                     stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
                     returnNLL, storeNLLInD, lambdaExp, processPrecExp, ECM_useObsPrecisionReweighting,
                     ECM_useProcessPrecisionReweighting, ECM_useAPN, obsPrecisionMultiplierMin,
-                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax, processQScale)
+                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax, processQScale,
+                    (APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC))
 
 
 def cforwardPassLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBlockMap, blockCount,
@@ -223,7 +224,8 @@ def cforwardPassLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBloc
                     stateInit, stateCovarInit, pad, stateForward, stateCovarForward, pNoiseForward, vectorD,
                     returnNLL, storeNLLInD, lambdaExp, processPrecExp, ECM_useObsPrecisionReweighting,
                     ECM_useProcessPrecisionReweighting, ECM_useAPN, obsPrecisionMultiplierMin,
-                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax, processQScale)
+                    obsPrecisionMultiplierMax, procPrecisionMultiplierMin, procPrecisionMultiplierMax, processQScale,
+                    (APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC))
 
 
 def _backward(dim, matrixData, matrixF, stateForward, stateCovarForward, pNoiseForward, stateSmoothed,
@@ -341,7 +343,7 @@ def _init_multiplier(src, n, lo, hi, pinned, fill=True):
 def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlockMap, blockCount, stateInit,
          stateCovarInit, iters, rtol, pad, nu, lamMin, lamMax, kapMin, kapMax, useObs, useProc, useAPN,
          t_innerIters, returnIntermediates, returnDiagnostics, lambdaExpInit, processPrecExpInit,
-         trackOptimizationPath, processQScale):
+         trackOptimizationPath, processQScale, apn=_APN_DEFAULTS):
     """ECM driver with the packing rules of cconsenrich.pyx:8409-8442."""
     data = _c32(matrixData, "matrixData", 2)
     munc = _c32(matrixPluginMuncInit, "matrixPluginMuncInit", 2)
@@ -395,16 +397,13 @@ def _ecm(dim, matrixData, matrixPluginMuncInit, matrixF, matrixQ0, intervalToBlo
         det = float(Q0[0, 0]) * float(Q0[1, 1]) - float(Q0[0, 1]) * float(Q0[1, 0])
         if det == 0.0:
             raise ValueError("matrixQ0 is singular")
-    if _apn_live(useAPN, use_qscale, Q0, dim):
-        raise NotImplementedError(_APN_MSG)
-
     lam = _init_multiplier(lam_src, n, lamMin, lamMax, True, fill=False) if use_lam else None
     kap = _init_multiplier(kap_src, n, kapMin, kapMax, True, fill=False) if use_kap else None
     alloc = _lib.pinned_empty if want else np.empty
     xs, Ps = alloc((n, dim), np.float32), alloc((n, dim, dim), np.float32)
     lag, res = alloc((max(n - 1, 1), dim, dim), np.float32), alloc((n, m), np.float32)
     mo = _model(dim, matrixF, Q0, stateInit, stateCovarInit, pad, lamMin_d, lamMax_d, kapMin_d, kapMax_d,
-                lam is not None, kap is not None, use_qscale, True, False)
+                lam is not None, kap is not None, use_qscale, True, False, useAPN, apn)
     op = _lib.EcmOpts()
     op.max_iters, op.inner_iters = int(iters), int(t_innerIters)
     op.update_lambda, op.update_kappa = int(lam is not None), int(kap is not None)
@@ -480,7 +479,8 @@ def cfixedBackgroundECM(matrixData, matrixPluginMuncInit, matrixF, matrixQ0, int
                 obsPrecisionMultiplierMin, obsPrecisionMultiplierMax, procPrecisionMultiplierMin,
                 procPrecisionMultiplierMax, ECM_useObsPrecisionReweighting, ECM_useProcessPrecisionReweighting,
                 ECM_useAPN, t_innerIters, returnIntermediates, returnDiagnostics, lambdaExpInit,
-                processPrecExpInit, trackOptimizationPath, processQScale)
+                processPrecExpInit, trackOptimizationPath, processQScale,
+                (APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC))
 
 
 def cfixedBackgroundECMLevel(matrixData, matrixPluginMuncInit, matrixQ0, intervalToBlockMap, blockCount,
@@ -499,7 +499,8 @@ def cfixedBackgroundECMLevel(matrixData, matrixPluginMuncInit, matrixQ0, interva
                 obsPrecisionMultiplierMin, obsPrecisionMultiplierMax, procPrecisionMultiplierMin,
                 procPrecisionMultiplierMax, ECM_useObsPrecisionReweighting, ECM_useProcessPrecisionReweighting,
                 ECM_useAPN, t_innerIters, returnIntermediates, returnDiagnostics, lambdaExpInit,
-                processPrecExpInit, trackOptimizationPath, processQScale)
+                processPrecExpInit, trackOptimizationPath, processQScale,
+                (APN_minQ, APN_maxQ, APN_dStatThresh, APN_dStatScale, APN_dStatPC))
 
 
 # ------------------------------------------------------------------------------------------

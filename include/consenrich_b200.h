@@ -51,7 +51,7 @@ extern "C" {
 #define CB200_ERR_CUDA 2        /* CUDA runtime / driver failure */
 #define CB200_ERR_UNSUPPORTED 3 /* valid in the reference, not expressible as a scan (APN) */
 
-#define CB200_ABI_VERSION 2
+#define CB200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define CB200_API __attribute__((visibility("default")))
@@ -71,12 +71,17 @@ typedef struct cb200_model {
     int32_t use_qscale;     /* per-interval processQScale is live */
     int32_t return_nll;     /* accumulate the Gaussian negative log-likelihood */
     int32_t store_nll_in_d; /* vectorD holds the per-interval NLL instead of NIS */
-    int32_t reserved0, reserved1;
+    int32_t use_apn;        /* ECM_useAPN: adaptive process noise (cconsenrich.pyx:510-527, 688-703).  Live only
+                             * without processQScale and with 0.5 (Q0[0,0] + Q0[1,1]) > 1e-12 (pyx:6574-6576), as in
+                             * the reference; the forward pass is then a sequential device recursion, not a scan */
+    int32_t reserved1;
     double F[4];            /* row-major transition matrix (ignored when state_dim == 1) */
     double Q0[4];           /* row-major base process noise; state_dim 1 uses Q0[0] */
     double state_init, cov_init, pad;
     double lam_min, lam_max; /* observation precision multiplier clamp */
     double kap_min, kap_max; /* process precision multiplier clamp */
+    double apn_min_q, apn_max_q, apn_thresh, apn_scale, apn_pc; /* APN_minQ, APN_maxQ, APN_dStatThresh,
+                             * APN_dStatScale, APN_dStatPC (rounded to float by the caller) */
 } cb200_model;
 
 /* ECM controls (cconsenrich.pyx:7660-7693). */
@@ -402,6 +407,23 @@ CB200_API int cb200_host_munc_seed_pass(cb200_ctx *ctx, const cb200_munc_seed_ar
  * unwritten otherwise; here that is CB200_ERR_INVALID).  x, out: device arrays of n elements. */
 CB200_API int cb200_ema(cb200_ctx *ctx, const void *x, int64_t n, int32_t is_double, double alpha, void *out);
 CB200_API int cb200_host_ema(cb200_ctx *ctx, const void *x, int64_t n, int32_t is_double, double alpha, void *out);
+
+/* ---- output: bedGraph text ----------------------------------------------
+ * The rows the reference appends per chromosome and track with pandas (consenrich.py:9797-9805:
+ * to_csv(sep="\t", header=False, index=False, float_format="%.4f", lineterminator="\n")):
+ * "chrom\tstart\tend\tvalue\n", value = C's "%.4f" of the float32 track value (NaN -> empty, +-inf ->
+ * "inf" / "-inf"), formatted on the device, byte-identical to the reference writer.
+ * starts / ends: [n] int64 or NULL (NULL: start = start0 + k step, end = start + step, clipped to end_clip
+ * when end_clip > 0).  values: row k at values[k * value_stride].  chrom: at most 32 bytes.
+ * cb200_bedgraph_chunk: device arrays; *text receives a DEVICE pointer owned by the context.
+ * cb200_host_bedgraph_chunk: host arrays; *text receives a page-locked HOST pointer owned by the context.
+ * Either pointer stays valid until the next bedGraph call on the context; *bytes is the text length. */
+CB200_API int cb200_bedgraph_chunk(cb200_ctx *ctx, const char *chrom, int64_t n, const int64_t *starts,
+                                   const int64_t *ends, int64_t start0, int64_t step, int64_t end_clip,
+                                   const float *values, int64_t value_stride, const char **text, int64_t *bytes);
+CB200_API int cb200_host_bedgraph_chunk(cb200_ctx *ctx, const char *chrom, int64_t n, const int64_t *starts,
+                                        const int64_t *ends, int64_t start0, int64_t step, int64_t end_clip,
+                                        const float *values, int64_t value_stride, const char **text, int64_t *bytes);
 
 #ifdef __cplusplus
 }

@@ -489,4 +489,19 @@ void emul_fold(const float *data, const float *munc, int64_t m, int64_t n, int64
     }
 }
 
+// Smoothing element of one bin two ways: the general route (rts2_gain + smo2_from_rts) and the
+// canonical-F shortcut the lean forward replay uses (smo2_from_filtered_canon).  out: 2 x 9 doubles.
+void emul_smoothing_element(double dF, const double *xP, const double *Q, double *out) {
+    Model2 M{};
+    M.F00 = 1.0; M.F01 = dF; M.F10 = 0.0; M.F11 = 1.0;
+    const Rts2 r = rts2_gain<true>(M, xP[0], xP[1], xP[2], xP[3], xP[3], xP[4], Q[0], Q[1], Q[1], Q[2]);
+    const Smo2 a = smo2_from_rts(r, xP[0], xP[1], xP[2], xP[3], xP[4]);
+    const Smo2 b = smo2_from_filtered_canon(dF, xP[0], xP[1], xP[2], xP[3], xP[4], Q[0], Q[1], Q[2]);
+    const double *pa = reinterpret_cast<const double *>(&a), *pb = reinterpret_cast<const double *>(&b);
+    for (int i = 0; i < 9; ++i) {
+        out[i] = pa[i];
+        out[9 + i] = pb[i];
+    }
+}
+
 }  // extern "C"

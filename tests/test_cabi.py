@@ -110,8 +110,13 @@ def test_argument_validation_precedes_device_work(built_lib):
         cb.cforwardPassLevel(**{k: v for k, v in base.items() if k != "matrixF"} | {"matrixQ0": np.zeros((1, 1), np.float32)})
     with pytest.raises(ValueError, match="matrixQ0 is singular"):
         cb.cfixedBackgroundECM(**{**base, "matrixQ0": np.ones((2, 2), np.float32)})
-    with pytest.raises(NotImplementedError, match="APN"):
-        cb.cforwardPass(**base, ECM_useAPN=True)
+    # adaptive process noise is a device path like any other (csrc/apn_kernels.cu): without a device it fails
+    # loudly, it does not fall back
+    import torch
+    from consenrich_b200 import _lib
+    if not torch.cuda.is_available():
+        with pytest.raises((_lib.CudaError, _lib.NativeLibraryMissing)):
+            cb.cforwardPass(**base, ECM_useAPN=True)
     # empty input: zeros, no device needed (pyx:6494-6501)
     e = np.empty((2, 0), np.float32)
     r = cb.cforwardPass(**{**base, "matrixData": e, "matrixPluginMuncInit": e, "intervalToBlockMap": np.zeros(0, np.int32)})

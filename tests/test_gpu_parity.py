@@ -176,10 +176,7 @@ def test_sweep_matches_reference_golden_vectors(cb, dim):
                   pad=1.0e-4, returnNLL=True, **extra)
         st = dict(stateForward=np.empty((n, dim), np.float32), stateCovarForward=np.empty((n, dim, dim), np.float32),
                   pNoiseForward=np.zeros((n, dim, dim), np.float32), vectorD=np.empty(n, np.float32))
-        if extra.get("ECM_useAPN"):
-            with pytest.raises(NotImplementedError):
-                (cb.cforwardPass(matrixF=F, **kw, **st) if dim == 2 else cb.cforwardPassLevel(**kw, **st))
-            continue
+        apn = bool(extra.get("ECM_useAPN"))
         if dim == 2:
             r = cb.cforwardPass(matrixF=F, **kw, **st)
             b = cb.cbackwardPass(matrixData=data, matrixF=F, stateForward=st["stateForward"],
@@ -192,7 +189,10 @@ def test_sweep_matches_reference_golden_vectors(cb, dim):
         close = assert_sweep_tracks_close
         close(st["stateForward"], case[pre + "stateForward"], name)
         close(st["stateCovarForward"], case[pre + "stateCovarForward"], name, scale="component")
-        np.testing.assert_array_equal(st["pNoiseForward"][: n - 1], case[pre + "pNoiseForward"][: n - 1])
+        if apn:  # the process noise follows the innovation statistic through the APN feedback (pyx:510-527)
+            close(st["pNoiseForward"][: n - 1], case[pre + "pNoiseForward"][: n - 1], name, scale="component")
+        else:
+            np.testing.assert_array_equal(st["pNoiseForward"][: n - 1], case[pre + "pNoiseForward"][: n - 1])
         close(st["vectorD"], case[pre + "vectorD"], name)
         assert abs(r[3] - float(case[pre + "sumNLL"])) <= 2e-6 * max(abs(float(case[pre + "sumNLL"])), 1.0)
         close(b[0], case[pre + "stateSmoothed"], name)
@@ -210,17 +210,35 @@ def _ecm(mod, dim, data, munc, **opts):
     return mod.cfixedBackgroundECM(matrixF=F, **kw) if dim == 2 else mod.cfixedBackgroundECMLevel(**kw)
 
 
-def _compare_ecm(a, b, label, exact_iters=True):
+# Stated ECM tolerance, set from the measured GPU-vs-oracle error over every case of this file and of
+# test_lean_sweeps.py (tools/ecm_error_probe.py on B200: state <= 3.2e-7, residuals <= 4.2e-7, covariances
+# <= 1.8e-5, lambda <= 7.7e-7, kappa <= 1.9e-6 of the track's scale; final NLL <= 3.8e-9 relative): about ten
+# times those.  The ECM compounds the sweeps' re-association error through the multiplier updates, so it
+# sits above the single-sweep figure (tests/parity_util.py) but far below the 1e-4 the stopping rule could
+# introduce if iteration counts diverged -- and those are compared exactly.
+ECM_TOL = dict(state=dict(rtol=2e-5, atol_rel=4e-6), cov=dict(rtol=2e-4, atol_rel=1e-4),
+               mult=dict(rtol=5e-5, atol_rel=1e-5), nll=5e-8)
+# Where the two sides may legitimately take different discrete decisions -- a free-running stopping rule that
+# ends on different iterations, or the adaptive-process-noise feedback, which branches on D_k against a
+# threshold (pyx:510-527) -- the comparison is at the level such a decision moves the result.
+ECM_TOL_DISCRETE = dict(state=dict(rtol=2e-4, atol_rel=1e-4), cov=dict(rtol=2e-3, atol_rel=1e-4),
+                        mult=dict(rtol=2e-3, atol_rel=1e-4), nll=1e-6)
+
+
+def _compare_ecm(a, b, label, exact_iters=True, tol=None):
     if exact_iters:
         assert a[0] == b[0], label
-    assert abs(a[1] - b[1]) <= 1e-6 * max(abs(b[1]), 1.0), f"{label}: nll {a[1]} vs {b[1]}"
-    assert_tracks_close(a[2], b[2], f"{label} stateSmoothed", rtol=2e-4, atol_rel=1e-4)
-    assert_tracks_close(a[3], b[3], f"{label} stateCovarSmoothed", scale="component", rtol=2e-3, atol_rel=1e-4)
-    assert_tracks_close(a[5], b[5], f"{label} residuals", rtol=2e-4, atol_rel=1e-4)
+    if tol is None:
+        tol = ECM_TOL if a[0] == b[0] else ECM_TOL_DISCRETE
+    assert abs(a[1] - b[1]) <= tol["nll"] * max(abs(b[1]), 1.0), f"{label}: nll {a[1]} vs {b[1]}"
+    assert_tracks_close(a[2], b[2], f"{label} stateSmoothed", **tol["state"])
+    assert_tracks_close(a[3], b[3], f"{label} stateCovarSmoothed", scale="component", **tol["cov"])
+    assert_tracks_close(a[4], b[4], f"{label} lagCovSmoothed", scale="component", **tol["cov"])
+    assert_tracks_close(a[5], b[5], f"{label} residuals", **tol["state"])
     for x, y, nm in ((a[6], b[6], "lambda"), (a[7], b[7], "kappa")):
         assert (x is None) == (y is None), f"{label} {nm}"
         if x is not None:
-            assert_tracks_close(x, y, f"{label} {nm}", rtol=2e-3, atol_rel=1e-4)
+            assert_tracks_close(x, y, f"{label} {nm}", **tol["mult"])
     da, db = a[8], b[8]
     assert set(da) == set(db)
     for key in ("max_iters", "skipped", "skip_reason", "fallback", "patience_target"):
@@ -308,8 +326,6 @@ def test_error_behaviour_matches_reference(cb, oracle):
     with pytest.raises(ValueError, match="matrixQ0 is singular"):
         cb.cfixedBackgroundECM(**{**base, "intervalToBlockMap": np.zeros(50, np.int32),
                                   "matrixQ0": np.ones((2, 2), np.float32)})
-    with pytest.raises(NotImplementedError):
-        cb.cforwardPass(**base, intervalToBlockMap=np.zeros(50, np.int32), ECM_useAPN=True)
     # empty input returns zeros without touching the device (pyx:6494-6501)
     e = np.empty((3, 0), np.float32)
     r = cb.cforwardPass(**{**base, "matrixData": e, "matrixPluginMuncInit": e}, intervalToBlockMap=np.zeros(0, np.int32),
@@ -423,3 +439,48 @@ def test_ecm_with_run_elements_composed_by_the_forward_replay(cb, oracle, nsub, 
         o = dict(ECM_fixedBackgroundIters=2, ECM_fixedBackgroundRtol=0.0, t_innerIters=2,
                  ECM_useObsPrecisionReweighting=False)
         _compare_ecm(_ecm(cb, 2, data, munc, **o), _ecm(oracle, 2, data, munc, **o), "fused long track")
+
+
+# ---------------------------------------------------------------------------------------------
+# adaptive process noise (cconsenrich.pyx:510-527, 688-703): the forward pass as a sequential device
+# recursion (csrc/apn_kernels.cu)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 1])
+@pytest.mark.parametrize("m,n", [(3, 1), (4, 33), (6, 1000), (5, 20_011)])
+def test_adaptive_process_noise_forward_matches_oracle(cb, oracle, dim, m, n):
+    data, munc = synth_tracks(600 + n, m, n, masked_frac=0.02 if n > 100 else 0.0)
+    data[:, n // 2: n // 2 + 7] += 6.0  # a stretch the model does not explain: D above the threshold, Q scaled up
+    lam = (0.3 + 3 * np.random.default_rng(n).random(n)).astype(np.float32)
+    for extra in (dict(), dict(lambdaExp=lam, APN_dStatThresh=1.5, APN_dStatScale=4.0, APN_dStatPC=1.5, APN_minQ=1e-5,
+                               APN_maxQ=10.0, storeNLLInD=False)):
+        kw = dict(matrixData=data, matrixPluginMuncInit=munc, matrixQ0=Q0, intervalToBlockMap=np.zeros(n, np.int32),
+                  blockCount=1, stateInit=0.25, stateCovarInit=1000.0, pad=1e-4, returnNLL=True, ECM_useAPN=True, **extra)
+        outs = []
+        for mod in (cb, oracle):
+            st = dict(stateForward=np.empty((n, dim), np.float32), stateCovarForward=np.empty((n, dim, dim), np.float32),
+                      pNoiseForward=np.zeros((n, dim, dim), np.float32), vectorD=np.empty(n, np.float32))
+            r = mod.cforwardPass(matrixF=F, **kw, **st) if dim == 2 else mod.cforwardPassLevel(**kw, **st)
+            outs.append((r, st))
+        (rg, sg), (ro, so) = outs
+        label = f"apn d{dim} {m}x{n} {sorted(extra)}"
+        assert_sweep_tracks_close(sg["stateForward"], so["stateForward"], label + " stateForward")
+        assert_sweep_tracks_close(sg["stateCovarForward"], so["stateCovarForward"], label + " stateCovarForward",
+                                  scale="component")
+        if n > 1:
+            assert_sweep_tracks_close(sg["pNoiseForward"][: n - 1], so["pNoiseForward"][: n - 1], label + " pNoiseForward",
+                                      scale="component")
+            assert len(np.unique(so["pNoiseForward"][: n - 1, 0, 0])) > 1 or n < 30  # the feedback did act
+        assert_sweep_tracks_close(sg["vectorD"], so["vectorD"], label + " vectorD")
+        assert abs(rg[3] - ro[3]) <= 2e-6 * max(abs(ro[3]), 1.0), (label, rg[3], ro[3])
+        assert abs(rg[0] - ro[0]) <= 1e-4 * max(abs(ro[0]), 1e-3), label
+
+
+@pytest.mark.parametrize("dim", [2, 1])
+def test_adaptive_process_noise_ecm_matches_oracle(cb, oracle, dim):
+    """cfixedBackgroundECM with ECM_useAPN: kappa is not fitted (pyx:7268, 8244), lambda is; the reference's
+    collected case _caseRunConsenrichAPNSmoke (tests/test_core.py:6051) goes through this path."""
+    data, munc = synth_tracks(77, 6, 5_003, masked_frac=0.02)
+    opts = dict(ECM_fixedBackgroundIters=3, ECM_fixedBackgroundRtol=0.0, t_innerIters=2, ECM_useAPN=True)
+    a, b = _ecm(cb, dim, data, munc, **opts), _ecm(oracle, dim, data, munc, **opts)
+    _compare_ecm(a, b, f"ecm apn d{dim}", tol=ECM_TOL_DISCRETE)
+    assert a[7] is None and b[7] is None and a[6] is not None

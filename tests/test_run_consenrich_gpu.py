@@ -62,15 +62,23 @@ CASES = {
     "fixed_budget": dict(ECM_fixedBackgroundRtol=0.0, ECM_fixedBackgroundIters=3, fitBackground=False, ECM_outerIters=1),
     # level-only state model
     "level_model": dict(stateModel="level", ECM_fixedBackgroundRtol=1e-5),
+    # adaptive process noise (core.py:3974-3976; the reference's collected _caseRunConsenrichAPNSmoke)
+    "apn": dict(ECM_useAPN=True, ECM_fixedBackgroundIters=3, ECM_outerIters=1,
+                processNoiseCalibration="fixedDiagonal"),
 }
+# BASELINE.json configs[0] ("cfg1"): the reference's two-sample run at the default bin size.  The BAM decoding of
+# that configuration is htslib work outside this path (and tests/smallTest.bam is absent from the reference
+# tree, .MISSING_LARGE_BLOBS:5; pysam is not installed), so the case enters where the path does: a two-track
+# count / variance matrix at the default 50 bp interval size over a smallTest-sized region, CLI defaults.
+CFG1 = dict(m=2, n=40_000, kw=CASES["cli_defaults"])
 
 
-@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("case", list(CASES) + ["cfg1_two_sample"])
 def test_run_consenrich_with_b200_kernels_matches_the_reference(ref_core, case):
     import consenrich_b200 as cb
-    m, n = 6, 60_000
+    m, n = (CFG1["m"], CFG1["n"]) if case == "cfg1_two_sample" else (6, 60_000)
     data, munc = _tracks(11 + len(case), m, n)
-    kw = {**BASE, **CASES[case]}
+    kw = {**BASE, **(CFG1["kw"] if case == "cfg1_two_sample" else CASES[case])}
     want = ref_core.runConsenrich(data, munc, **kw)
     mod = cb.install()
     try:

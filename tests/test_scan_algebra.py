@@ -143,3 +143,40 @@ def test_emulated_scan_matches_oracle(oracle, emul, dim, case):
     assert_tracks_close(Ps, b[1], "stateCovarSmoothed", scale="component")
     if n > 1:
         assert_tracks_close(lag, b[2], "lagCovSmoothed", scale="component")
+
+
+def test_canonical_smoothing_element_shortcut(emul):
+    """smo2_from_filtered_canon (what the lean forward replay composes per bin) is the same element as
+    rts2_gain + smo2_from_rts for F = [[1, f], [0, 1]] and symmetric P, Q.  The element is ill-conditioned
+    when P^- is (J = P F^T (P^-)^-1, L = P - J P^- J^T cancels), so the two routes are both measured against
+    an extended-precision evaluation: the shortcut must not be less accurate than the route it replaces."""
+    rng = np.random.default_rng(12)
+    ld = np.longdouble
+    worse = []
+    for _ in range(2000):
+        dF = float(rng.choice([1.0, 0.5, 2.0]))
+        a = rng.normal(size=(2, 2))
+        P = a @ a.T * float(10.0 ** rng.uniform(-6, 3)) + np.eye(2) * 1e-9
+        q = rng.normal(size=(2, 2))
+        Q = q @ q.T * float(10.0 ** rng.uniform(-8, 0)) + np.eye(2) * 1e-12
+        xP = np.array([rng.normal(), rng.normal(), P[0, 0], P[0, 1], P[1, 1]])
+        xP[2:] = xP[2:].astype(np.float32)  # the replay feeds float32 values
+        Qv = np.array([Q[0, 0], Q[0, 1], Q[1, 1]]).astype(np.float32).astype(np.float64)
+        out = np.empty(18)
+        emul.emul_smoothing_element(C.c_double(dF), _ptr(xP), _ptr(Qv), _ptr(out))
+        Fm = np.array([[1, dF], [0, 1]], ld)
+        Pm = np.array([[xP[2], xP[3]], [xP[3], xP[4]]], ld)
+        Qm = np.array([[Qv[0], Qv[1]], [Qv[1], Qv[2]]], ld)
+        x = np.array([xP[0], xP[1]], ld)
+        PP = Fm @ Pm @ Fm.T + Qm
+        det = PP[0, 0] * PP[1, 1] - PP[0, 1] * PP[1, 0]
+        inv = np.array([[PP[1, 1], -PP[0, 1]], [-PP[1, 0], PP[0, 0]]], ld) / det
+        J = Pm @ Fm.T @ inv
+        g = x - J @ (Fm @ x)
+        Lm = Pm - J @ PP @ J.T
+        want = np.array([J[0, 0], J[0, 1], J[1, 0], J[1, 1], g[0], g[1], Lm[0, 0], Lm[0, 1], Lm[1, 1]], ld)
+        sc = np.array([1.0] * 4 + [1.0 + abs(xP[0]) + abs(xP[1])] * 2 + [xP[2], max(abs(xP[3]), xP[2] * 1e-3), xP[4]])
+        e_general = float(np.max(np.abs(out[:9] - want) / sc))
+        e_canon = float(np.max(np.abs(out[9:] - want) / sc))
+        worse.append(e_canon - 4.0 * e_general)
+        assert e_canon <= 4.0 * e_general + 1e-13, (e_canon, e_general)
