@@ -256,7 +256,7 @@ def run_reference_arm(args):
     cores = max(1, min(os.cpu_count() or 1, 64))
     probe = synth_host(1, m, 4_000, cfg["bin_bp"])
     secs_per_bin = min(cpu_ecm(mod, probe[0], probe[1])[0] for _ in range(2)) / 4_000
-    budget = 150.0 / max(args.steps + min(args.warmup, 1), 1)  # seconds per step
+    budget = float(os.environ.get("CB200_REF_BUDGET_S", 150.0)) / max(args.steps + min(args.warmup, 1), 1)  # seconds per step
     longest = max(chrom_bins(cfg).values())
     n_sample = int(max(2_000, min(longest, budget / (3.0 * secs_per_bin))))  # 3.0: the threads share memory bandwidth
     data, munc, _ = synth_host(1729, m, n_sample, cfg["bin_bp"])
@@ -481,7 +481,8 @@ def run_b200_arm(args):
         def e2e_step():
             return sum(pool.map(one, mine))
 
-        e2e_step()  # warm-up: device arenas, page-locked result pool
+        for _ in range(2):  # warm-up: device arenas and the page-locked result pool of every worker thread
+            e2e_step()
         hl0 = sum(x.launch_count for x in e2e_ctxs.values())
         barrier()
         t0 = time.perf_counter()

@@ -156,6 +156,12 @@ SIGNATURES = {
     "cb200_host_interval_diagnostics": (C.c_int, [_vp, _vp, _i64, _vp, _dbl, C.POINTER(DiagGainArgs), _vp, _vp]),
     "cb200_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
     "cb200_host_ema": (C.c_int, [_vp, _vp, _i64, _i32, _dbl, _vp]),
+    "cb200_split_begin": (C.c_int, [_vp, _pm, _dbl, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _i32, _i32]),
+    "cb200_split_forward_compose": (C.c_int, [_vp, _vp]),
+    "cb200_split_forward_replay": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "cb200_split_backward_compose": (C.c_int, [_vp, _i32, _vp]),
+    "cb200_split_backward_replay": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "cb200_split_end": (C.c_int, [_vp, _vp]),
     "cb200_bedgraph_chunk": (C.c_int, [_vp, C.c_char_p, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64, C.POINTER(_vp),
                                        C.POINTER(_i64)]),
     "cb200_host_bedgraph_chunk": (C.c_int, [_vp, C.c_char_p, _i64, _vp, _vp, _i64, _i64, _i64, _vp, _i64,

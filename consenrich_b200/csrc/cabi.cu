@@ -81,6 +81,8 @@ struct TimedSpan {
 
 }  // namespace
 
+static void split_free(void *p);
+
 struct cb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -97,6 +99,7 @@ struct cb200_ctx {
     DevBuf bg_ws, bg_w, bg_rhs, bg_out, bg_status;  // background solve: workspace, operands, outcome
     // lean sweeps (lean_kernels.cuh): run-major statistics, multipliers, two sets of forward tracks, scratch
     DevBuf ln_SA, ln_SB, ln_kap, ln_qs, ln_A[2], ln_B[2], ln_sagg[2], ln_sex[2], ln_fagg, ln_fex, ln_fpref, ln_ssuf, ln_part;
+    void *split = nullptr;  // SplitState of a chromosome shard between cb200_split_begin and cb200_split_end
     DevBuf wr_text, wr_tiles, wr_vals, wr_starts, wr_ends;  // bedGraph writer
     char *wr_host = nullptr;  // pinned text buffer
     size_t wr_host_cap = 0;
@@ -543,6 +546,8 @@ int cb200_ctx_create(int device, void *stream, cb200_ctx **out) {
 void cb200_ctx_destroy(cb200_ctx *c) {
     DeviceGuard _dg(c ? c->device : 0);
     if (!c) return;
+    split_free(c->split);
+    c->split = nullptr;
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->scan_ws, &c->stats, &c->sums, &c->data, &c->munc, &c->xf, &c->Pf, &c->Qf, &c->xf2, &c->Pf2,
                       &c->Qf2, &c->smo, &c->smo2, &c->D,
@@ -903,9 +908,19 @@ bool ecm_iteration_done(EcmLoopState &L, double rtol, int patience) {
     return false;
 }
 
-int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op, const float *data,
-                    const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *kap, float *xs,
-                    float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
+// Everything one lean ECM needs on the device: geometry, the two pass argument blocks, the two sets of
+// forward tracks.  lean_setup allocates (context arena), folds the tracks into run-major statistics and
+// brings kappa / qScale into run-major order.
+struct LeanRun {
+    LeanGeom g;
+    LeanFwdArgs fa;
+    LeanBwdArgs ba;
+    LeanTrack trk[2];
+    float *kap_rm = nullptr, *qs_rm = nullptr;
+};
+
+int lean_setup(cb200_ctx *c, const cb200_model *mo, double nu, const float *data, const float *munc, int64_t m,
+               int64_t n, int64_t ld, const float *qscale, const float *kap, LeanRun *R) {
     // run length: 32 bins (measured on B200: faster than 64 at chr19 and at chr1 @ 25 bp alike)
     int logL = g_lean_logL >= 5 && g_lean_logL <= 6 ? g_lean_logL : 5;
     const LeanGeom g = lean_geom(n, logL);
@@ -924,12 +939,12 @@ int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *o
     CB_TRY(ensure(c, c->ln_fex, segs * 14 * 32 * 8));
     CB_TRY(ensure(c, c->ln_fpref, Gp * 5 * 8));
     CB_TRY(ensure(c, c->ln_ssuf, Gp * 5 * 8));
-    if (!c->ln_part.p || c->ln_part.cap < 256 + G * 8) {
-        CB_TRY(ensure(c, c->ln_part, 256 + G * 8 + G * 2));  // headroom: the counter must start at zero only once
-        CU_TRY(cudaMemsetAsync(c->ln_part.p, 0, 256, c->stream));
+    if (!c->ln_part.p || c->ln_part.cap < 512 + G * 8) {
+        CB_TRY(ensure(c, c->ln_part, 512 + G * 8 + G * 2));  // headroom: the counter must start at zero only once
+        CU_TRY(cudaMemsetAsync(c->ln_part.p, 0, 512, c->stream));
     }
-    // layout of ln_part: [0] counter (int32, left at zero by every launch), partial sums from byte 256
-    double *sums = static_cast<double *>(c->sums.p);
+    // layout of ln_part: [0] counter (int32, left at zero by every launch); [128] the float a non-last shard
+    // drops its boundary kappa into; [256] two 5-double shard start states; partial sums from byte 512
     {
         Span sp(c, FAM_FOLD);
         CU_TRY(launch_fold(data, munc, m, n, ld, mo->pad, static_cast<double2 *>(c->ln_SA.p),
@@ -948,13 +963,16 @@ int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *o
             c->launches += 1;
         }
     }
-    LeanTrack trk[2];
+    R->g = g;
+    R->kap_rm = kap_rm;
+    R->qs_rm = qs_rm;
     for (int s = 0; s < 2; ++s) {
-        trk[s].A = static_cast<float4 *>(c->ln_A[s].p);
-        trk[s].B = static_cast<float4 *>(c->ln_B[s].p);
-        trk[s].sagg = static_cast<double *>(c->ln_sagg[s].p);
-        trk[s].sex = static_cast<double *>(c->ln_sex[s].p);
+        R->trk[s].A = static_cast<float4 *>(c->ln_A[s].p);
+        R->trk[s].B = static_cast<float4 *>(c->ln_B[s].p);
+        R->trk[s].sagg = static_cast<double *>(c->ln_sagg[s].p);
+        R->trk[s].sex = static_cast<double *>(c->ln_sex[s].p);
     }
+    unsigned char *part = static_cast<unsigned char *>(c->ln_part.p);
     LeanFwdArgs fa{};
     fa.g = g;
     fa.SA = static_cast<const double2 *>(c->ln_SA.p);
@@ -964,9 +982,9 @@ int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *o
     fa.sc.fagg = static_cast<double *>(c->ln_fagg.p);
     fa.sc.fex = static_cast<double *>(c->ln_fex.p);
     fa.sc.fpref = static_cast<double *>(c->ln_fpref.p);
-    fa.sc.counter = static_cast<int32_t *>(c->ln_part.p);
-    fa.sc.partials = reinterpret_cast<double *>(static_cast<unsigned char *>(c->ln_part.p) + 256);
-    fa.sums = sums;
+    fa.sc.counter = reinterpret_cast<int32_t *>(part);
+    fa.sc.partials = reinterpret_cast<double *>(part + 512);
+    fa.sums = static_cast<double *>(c->sums.p);
     fa.m = (double)m;
     fa.inv_m = 1.0 / (double)m;
     fa.mlog2pi = (double)m * log(6.2831853071795864769);
@@ -975,21 +993,39 @@ int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *o
     fa.cov_init = mo->cov_init;
     fa.kap_min = mo->kap_min;
     fa.kap_max = mo->kap_max;
+    fa.sh.is_first = fa.sh.is_last = 1;
     LeanBwdArgs ba{};
     ba.g = g;
     ba.ssuf = static_cast<double *>(c->ln_ssuf.p);
     ba.qs = qs_rm;
     ba.kap_out = kap_rm;
-    ba.xs = xs; ba.Ps = Ps; ba.lag = lag;
     ba.lag_rows = n > 1 ? n - 1 : 1;
     ba.M = fa.M;
-    ba.nu = op->nu;
+    ba.nu = nu;
     ba.kap_lo = mo->kap_min;
     ba.kap_hi = mo->kap_max;
+    ba.sh.is_first = ba.sh.is_last = 1;
+    ba.kap_discard = reinterpret_cast<float *>(part + 128);
     {
         const double det = mo->Q0[0] * mo->Q0[3] - mo->Q0[1] * mo->Q0[2];
         ba.qi00 = mo->Q0[3] / det; ba.qi01 = -mo->Q0[1] / det; ba.qi10 = -mo->Q0[2] / det; ba.qi11 = mo->Q0[0] / det;
     }
+    R->fa = fa;
+    R->ba = ba;
+    return CB200_OK;
+}
+
+int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *op, const float *data,
+                    const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale, float *kap, float *xs,
+                    float *Ps, float *lag, float *resid, cb200_ecm_result *res, double *nll_path) {
+    LeanRun R;
+    CB_TRY(lean_setup(c, mo, op->nu, data, munc, m, n, ld, qscale, kap, &R));
+    LeanFwdArgs &fa = R.fa;
+    LeanBwdArgs &ba = R.ba;
+    LeanTrack *trk = R.trk;
+    const LeanGeom g = R.g;
+    float *kap_rm = R.kap_rm;
+    ba.xs = xs; ba.Ps = Ps; ba.lag = lag;
     int cur_set = 0;
     auto forward = [&](int set, bool with_nll, bool store) -> int {
         fa.trk = trk[set];
@@ -1068,6 +1104,168 @@ int ecm_device_lean(cb200_ctx *c, const cb200_model *mo, const cb200_ecm_opts *o
     return CB200_OK;
 }
 
+struct SplitState {
+    LeanRun R;
+    cb200_model mo;
+    int64_t m = 0, n = 0;
+    int is_first = 1, is_last = 1;
+};
+
+}  // namespace
+
+static void split_free(void *p) { delete static_cast<SplitState *>(p); }
+
+// =====================================================================================
+// a chromosome split over several GPUs: one shard per context
+// =====================================================================================
+extern "C" {
+
+int cb200_split_begin(cb200_ctx *c, const cb200_model *mo_in, double nu, const float *data, const float *munc, int64_t m,
+                      int64_t n, int64_t ld, const float *qscale, const float *kap, int32_t is_first, int32_t is_last) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || !data || !munc || !kap) return fail(CB200_ERR_INVALID, "NULL argument");
+    CB_TRY(check_model(mo_in));
+    cb200_model mo = *mo_in;
+    mo.use_lambda = 0;
+    mo.use_kappa = 1;
+    mo.use_qscale = qscale != nullptr;
+    if (mo.state_dim != 2 || mo.F[0] != 1.0 || mo.F[2] != 0.0 || mo.F[3] != 1.0)
+        return fail(CB200_ERR_UNSUPPORTED, "split chromosomes run the 2-state model with F = [[1, f], [0, 1]]");
+    if (apn_live(&mo)) return fail(CB200_ERR_UNSUPPORTED, "adaptive process noise cannot run on a split chromosome");
+    if (n < 64 || m <= 0) return fail(CB200_ERR_INVALID, "a shard needs at least 64 intervals");
+    {
+        const double det = mo.Q0[0] * mo.Q0[3] - mo.Q0[1] * mo.Q0[2];
+        if (det == 0.0) return fail(CB200_ERR_INVALID, "matrixQ0 is singular");
+    }
+    lean_read_env();
+    split_free(c->split);
+    c->split = nullptr;
+    SplitState *S = new SplitState();
+    S->mo = mo;
+    S->m = m;
+    S->n = n;
+    S->is_first = is_first != 0;
+    S->is_last = is_last != 0;
+    const int rc = lean_setup(c, &mo, nu, data, munc, m, n, ld, qscale, kap, &S->R);
+    if (rc != CB200_OK) {
+        delete S;
+        return rc;
+    }
+    S->R.fa.sh.is_first = S->R.ba.sh.is_first = S->is_first;
+    S->R.fa.sh.is_last = S->R.ba.sh.is_last = S->is_last;
+    S->R.ba.lag_rows = S->is_last ? (n > 1 ? n - 1 : 1) : n;
+    c->split = S;
+    return CB200_OK;
+}
+
+static SplitState *split_of(cb200_ctx *c) { return c ? static_cast<SplitState *>(c->split) : nullptr; }
+
+int cb200_split_forward_compose(cb200_ctx *c, double *payload) {
+    DeviceGuard _dg(c ? c->device : 0);
+    SplitState *S = split_of(c);
+    if (!S || !payload) return fail(CB200_ERR_INVALID, "no split in progress (cb200_split_begin) or NULL payload");
+    {
+        Span sp(c, FAM_COMPOSE);
+        CU_TRY(lean_fwd_compose(S->R.fa, c->stream));
+    }
+    {
+        Span sp(c, FAM_SEGSCAN);
+        CU_TRY(lean_reduce_groups(S->R.fa.sc.fagg, S->R.g, false, payload, c->stream));
+        CU_TRY(lean_payload_tail(S->R.fa, S->R.trk[0], false, payload, c->stream));
+    }
+    c->launches += 3;
+    return CB200_OK;
+}
+
+int cb200_split_forward_replay(cb200_ctx *c, const double *gathered, int32_t rank, int32_t world, int32_t with_nll,
+                               int32_t store, int32_t set, double *sums) {
+    DeviceGuard _dg(c ? c->device : 0);
+    SplitState *S = split_of(c);
+    if (!S || !gathered) return fail(CB200_ERR_INVALID, "no split in progress (cb200_split_begin) or NULL payloads");
+    if (rank < 0 || rank >= world || set < 0 || set > 1) return fail(CB200_ERR_INVALID, "bad rank / track set");
+    if ((rank == 0) != (S->is_first != 0) || (rank == world - 1) != (S->is_last != 0))
+        return fail(CB200_ERR_INVALID, "rank does not match the shard's position given to cb200_split_begin");
+    LeanFwdArgs fa = S->R.fa;
+    double *first = reinterpret_cast<double *>(static_cast<unsigned char *>(c->ln_part.p) + 256);
+    fa.trk = S->R.trk[set];
+    fa.want_nll = with_nll ? 1 : 0;
+    fa.do_store = store ? 1 : 0;
+    fa.sums = sums ? sums : static_cast<double *>(c->sums.p);
+    fa.sh.first = first;
+    fa.sh.fwd_next = S->is_last ? nullptr : gathered + (int64_t)(rank + 1) * LEAN_PAYLOAD;
+    {
+        Span sp(c, FAM_SEGSCAN);
+        CU_TRY(lean_shard_state(gathered, LEAN_PAYLOAD, rank, world, false, S->mo.state_init, S->mo.cov_init, first, c->stream));
+        CU_TRY(lean_fwd_prefix(fa, c->stream));
+    }
+    {
+        Span sp(c, FAM_FWD);
+        CU_TRY(lean_fwd_replay(fa, c->stream));
+    }
+    c->launches += 3;
+    return CB200_OK;
+}
+
+int cb200_split_backward_compose(cb200_ctx *c, int32_t set, double *payload) {
+    DeviceGuard _dg(c ? c->device : 0);
+    SplitState *S = split_of(c);
+    if (!S || !payload || set < 0 || set > 1) return fail(CB200_ERR_INVALID, "no split in progress, NULL payload or bad track set");
+    {
+        Span sp(c, FAM_SEGSCAN);
+        CU_TRY(lean_reduce_groups(S->R.trk[set].sagg, S->R.g, true, payload, c->stream));
+        CU_TRY(lean_payload_tail(S->R.fa, S->R.trk[set], true, payload, c->stream));
+    }
+    c->launches += 2;
+    return CB200_OK;
+}
+
+int cb200_split_backward_replay(cb200_ctx *c, const double *gathered_bwd, const double *gathered_fwd, int32_t rank,
+                                int32_t world, int32_t set, int32_t publish, float *xs, float *Ps, float *lag) {
+    DeviceGuard _dg(c ? c->device : 0);
+    SplitState *S = split_of(c);
+    if (!S || !gathered_bwd || !gathered_fwd) return fail(CB200_ERR_INVALID, "no split in progress or NULL payloads");
+    if (rank < 0 || rank >= world || set < 0 || set > 1) return fail(CB200_ERR_INVALID, "bad rank / track set");
+    if (publish && (!xs || !Ps || !lag)) return fail(CB200_ERR_INVALID, "a publishing pass needs xs, Ps and lag");
+    LeanBwdArgs ba = S->R.ba;
+    double *beyond = reinterpret_cast<double *>(static_cast<unsigned char *>(c->ln_part.p) + 256 + 64);
+    ba.trk = S->R.trk[set];
+    ba.xs = xs; ba.Ps = Ps; ba.lag = lag;
+    ba.sh.first = beyond;
+    ba.sh.fwd_next = S->is_last ? nullptr : gathered_fwd + (int64_t)(rank + 1) * LEAN_PAYLOAD;
+    ba.sh.bwd_prev = S->is_first ? nullptr : gathered_bwd + (int64_t)(rank - 1) * LEAN_PAYLOAD;
+    if (!publish) {
+        // a publishing pass re-uses the suffix states of the kappa-carrying pass before it (same tracks)
+        Span sp(c, FAM_SEGSCAN);
+        CU_TRY(lean_shard_state(gathered_bwd, LEAN_PAYLOAD, rank, world, true, 0.0, 0.0, beyond, c->stream));
+        CU_TRY(lean_bwd_suffix(ba, c->stream));
+        c->launches += 2;
+    }
+    {
+        Span sp(c, publish ? FAM_PUBLISH : FAM_BWD);
+        CU_TRY(lean_bwd_replay(ba, publish != 0, c->stream));
+    }
+    c->launches += 1;
+    return CB200_OK;
+}
+
+int cb200_split_end(cb200_ctx *c, float *kap) {
+    DeviceGuard _dg(c ? c->device : 0);
+    SplitState *S = split_of(c);
+    if (!S) return fail(CB200_ERR_INVALID, "no split in progress (cb200_split_begin)");
+    if (kap) {
+        Span sp(c, FAM_PREC);
+        CU_TRY(lean_scatter_f32(S->R.kap_rm, kap, S->R.g, c->stream));
+        c->launches += 1;
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    split_free(c->split);
+    c->split = nullptr;
+    return CB200_OK;
+}
+
+}  // extern "C"
+
+namespace {
 }  // namespace
 
 // =====================================================================================

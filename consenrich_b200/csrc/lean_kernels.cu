@@ -176,8 +176,10 @@ struct SmoOps {
 // positions before it.  agg: [N][pitch], out: [5][pitch].
 template <class Ops, bool REVERSE>
 __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_group_scan_kernel(const double *agg, int G, int pitch,
-                                                                           State2 first, double *out) {
+                                                                           State2 first, const double *first_dev,
+                                                                           double *out) {
     using Elem = typename Ops::Elem;
+    if (first_dev) first = load_strided<State2>(first_dev, 1);  // a shard of a split chromosome
     constexpr int N = Elem::N;
     constexpr int NW = LEAN_SCAN_THREADS / 32;
     __shared__ double sh[NW * N];
@@ -234,6 +236,58 @@ __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_group_scan_kernel(cons
             if (u + 1 < c) st = Ops::apply(load_strided<Elem>(agg + s, pitch), st);
         }
     }
+}
+
+// The whole aggregate of a shard (split chromosomes): ordered reduction of the group aggregates.
+template <class Ops, bool REVERSE>
+__global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_reduce_groups_kernel(const double *agg, int G, int pitch,
+                                                                              double *out) {
+    using Elem = typename Ops::Elem;
+    constexpr int N = Elem::N;
+    constexpr int NW = LEAN_SCAN_THREADS / 32;
+    __shared__ double sh[NW * N];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c = (G + LEAN_SCAN_THREADS - 1) / LEAN_SCAN_THREADS;
+    const int j0 = tid * c;
+    Elem e = Ops::identity();
+    for (int u = 0; u < c; ++u) {
+        const int j = j0 + u;
+        if (j < G) {
+            const Elem x = load_strided<Elem>(agg + (REVERSE ? G - 1 - j : j), pitch);
+            e = u == 0 ? x : Ops::combine(e, x);
+        }
+    }
+    // ordered tree: lane l covers scan positions before lane l + d
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const Elem o = shfl_down_elem(e, d);
+        if ((lane & (2 * d - 1)) == 0) e = Ops::combine(e, o);
+    }
+    if (lane == 0) store_strided(sh + warp * N, 1, e);
+    __syncthreads();
+    if (warp == 0) {
+        Elem v = lane < NW ? load_strided<Elem>(sh + lane * N, 1) : Ops::identity();
+#pragma unroll
+        for (int d = 1; d < NW; d <<= 1) {
+            const Elem o = shfl_down_elem(v, d);
+            if ((lane & (2 * d - 1)) == 0) v = Ops::combine(v, o);
+        }
+        if (lane == 0) store_strided(out, 1, v);
+    }
+}
+
+// Start state of a shard's scan from the gathered payloads (element first in every payload).
+template <class Ops, bool REVERSE>
+__global__ void lean_shard_state_kernel(const double *gathered, int pitch, int rank, int world, State2 first,
+                                        double *out5) {
+    if (threadIdx.x != 0) return;
+    State2 s = first;
+    if (!REVERSE) {
+        for (int r = 0; r < rank; ++r) s = Ops::apply(load_strided<typename Ops::Elem>(gathered + (int64_t)r * pitch, 1), s);
+    } else {
+        for (int r = world - 1; r > rank; --r) s = Ops::apply(load_strided<typename Ops::Elem>(gathered + (int64_t)r * pitch, 1), s);
+    }
+    store_strided(out5, 1, s);
 }
 
 // =====================================================================================
@@ -324,8 +378,12 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_FWD_CTAS) lean_fwd_replay_k
             // terminal element of the chromosome (x_s = x_f, P_s = P_f there)
             if (sg.valid > 0) {
                 const int64_t next = sg.k0 + sg.L;
-                if (next >= a.g.n) {
+                if (next >= a.g.n && a.sh.is_last) {
                     brun = smo2_combine(smo2_from_state(State2{s.x0, s.x1, s.P00, s.P01, s.P11}), brun);
+                } else if (next >= a.g.n) {
+                    // the shard's last bin: the next bin is the following shard's first one
+                    const double qk = lean_qk(has_qs, (float)a.sh.fwd_next[14], (float)a.sh.fwd_next[15], a.kap_min, a.kap_max);
+                    compose_smo(a.M, brun, s, qk * a.M.q00, qk * a.M.q01, qk * a.M.q10, qk * a.M.q11);
                 } else {
                     const int64_t pn = a.g.index(next);
                     const double qk = lean_qk(has_qs, a.kap[pn], has_qs ? a.qs[pn] : 1.0f, a.kap_min, a.kap_max);
@@ -437,6 +495,14 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_BWD_CTAS) lean_bwd_replay_k
         qn0 = b.y; qn1 = b.z; qn2 = b.w;
         if (has_qs) qsn = a.qs[pn];
         if (KAPPA) knext = a.kap_out + pn;
+    } else if (!a.sh.is_last) {
+        // the bin after the shard's last one is the next shard's first: its process noise as that shard's
+        // forward pass stored it (float32 of qk Q0); its kappa is that shard's to compute
+        const float nk = (float)a.sh.fwd_next[14], nq = (float)a.sh.fwd_next[15];
+        const double qk = lean_qk(has_qs, nk, nq, a.kap_lo, a.kap_hi);
+        qn0 = (float)(qk * a.M.q00); qn1 = (float)(qk * a.M.q01); qn2 = (float)(qk * a.M.q11);
+        qsn = has_qs ? nq : 1.0f;
+        if (KAPPA) knext = a.kap_discard;
     }
     auto load = [&](BwdIn &r, int i0) {
 #pragma unroll
@@ -454,7 +520,7 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_BWD_CTAS) lean_bwd_replay_k
             if (i < sg.valid) {
                 const float4 fa = r.a[u], fb = r.b[u];
                 const int64_t k = sg.k0 + i;
-                if (k == a.g.n - 1) {
+                if (k == a.g.n - 1 && a.sh.is_last) {
                     // the chromosome's last bin: x_s = x_f, P_s = P_f
                     c = Rs2{(double)fa.x, (double)fa.y, (double)fa.z, (double)fa.w, (double)fa.w, (double)fb.x};
                     if (PUBLIC) {
@@ -497,7 +563,24 @@ __global__ void __launch_bounds__(LEAN_THREADS, LEAN_BWD_CTAS) lean_bwd_replay_k
         if (i0 - 8 >= 0) load(c0, i0 - 8);
         step(c1, i0 - 4);
     }
-    if (KAPPA && sg.k0 == 0) kout[0] = 1.0f;  // kappa_0 is not estimated (cconsenrich.pyx:8252)
+    if (KAPPA && sg.k0 == 0) {
+        if (a.sh.is_first) {
+            kout[0] = 1.0f;  // kappa_0 is not estimated (cconsenrich.pyx:8252)
+        } else {
+            // the multiplier of this shard's first bin: one more RTS step into the previous shard's last bin
+            // (its filtered Gaussian came with the backward payload); c holds the smoothed first bin
+            const double px0 = a.sh.bwd_prev[9], px1 = a.sh.bwd_prev[10], pP00 = a.sh.bwd_prev[11],
+                         pP01 = a.sh.bwd_prev[12], pP11 = a.sh.bwd_prev[13];
+            const Rts2 g = rts2_gain<true>(a.M, px0, px1, pP00, pP01, pP01, pP11, qn0, qn1, qn1, qn2);
+            const Rs2 nxt = c;
+            Smo2Out o;
+            rts2_step(c, g, px0, px1, pP00, pP01, pP11, o);
+            kout[0] = (float)kappa2_update<true>(a.M, a.qi00, a.qi01, a.qi10, a.qi11, c.x0, c.x1, c.P00, c.P01, c.P10,
+                                                 c.P11, nxt.x0, nxt.x1, nxt.P00, nxt.P01, nxt.P10, nxt.P11, r32(o.C00),
+                                                 r32(o.C01), r32(o.C10), r32(o.C11), (double)qsn, has_qs, a.nu, a.kap_lo,
+                                                 a.kap_hi);
+        }
+    }
 }
 
 // =====================================================================================
@@ -539,7 +622,7 @@ cudaError_t lean_fwd_compose(const LeanFwdArgs &a, cudaStream_t st) {
 
 cudaError_t lean_fwd_prefix(const LeanFwdArgs &a, cudaStream_t st) {
     const State2 prior{a.state_init, 0.0, a.cov_init, 0.0, a.cov_init};
-    lean_group_scan_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.G, a.g.Gp, prior, a.sc.fpref);
+    lean_group_scan_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.G, a.g.Gp, prior, a.sh.first, a.sc.fpref);
     return cudaGetLastError();
 }
 
@@ -553,7 +636,7 @@ cudaError_t lean_fwd_replay(const LeanFwdArgs &a, cudaStream_t st) {
 
 cudaError_t lean_bwd_suffix(const LeanBwdArgs &a, cudaStream_t st) {
     const State2 beyond{0.0, 0.0, 0.0, 0.0, 0.0};
-    lean_group_scan_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.trk.sagg, a.g.G, a.g.Gp, beyond, a.ssuf);
+    lean_group_scan_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.trk.sagg, a.g.G, a.g.Gp, beyond, a.sh.first, a.ssuf);
     return cudaGetLastError();
 }
 
@@ -562,6 +645,45 @@ cudaError_t lean_bwd_replay(const LeanBwdArgs &a, bool publish, cudaStream_t st)
         lean_bwd_replay_kernel<false, true><<<lean_grid(a.g), LEAN_THREADS, 0, st>>>(a);
     else
         lean_bwd_replay_kernel<true, false><<<lean_grid(a.g), LEAN_THREADS, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+namespace {
+__global__ void lean_payload_tail_kernel(const float *kap, const float *qs, const float4 *A, const float4 *B,
+                                         int64_t last_pos, int backward, double *payload) {
+    if (threadIdx.x != 0) return;
+    if (!backward) {
+        payload[14] = (double)kap[0];
+        payload[15] = qs ? (double)qs[0] : 1.0;
+    } else {
+        const float4 a = A[last_pos], b = B[last_pos];
+        payload[9] = (double)a.x; payload[10] = (double)a.y; payload[11] = (double)a.z; payload[12] = (double)a.w;
+        payload[13] = (double)b.x;
+    }
+}
+}  // namespace
+
+cudaError_t lean_payload_tail(const LeanFwdArgs &a, const LeanTrack &trk, bool backward, double *payload, cudaStream_t st) {
+    lean_payload_tail_kernel<<<1, 32, 0, st>>>(a.kap, a.qs, trk.A, trk.B, a.g.index(a.g.n - 1), backward ? 1 : 0, payload);
+    return cudaGetLastError();
+}
+
+cudaError_t lean_reduce_groups(const double *agg, const LeanGeom &g, bool backward, double *out, cudaStream_t st) {
+    if (backward)
+        lean_reduce_groups_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(agg, g.G, g.Gp, out);
+    else
+        lean_reduce_groups_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(agg, g.G, g.Gp, out);
+    return cudaGetLastError();
+}
+
+cudaError_t lean_shard_state(const double *gathered, int pitch, int rank, int world, bool backward, double state_init,
+                             double cov_init, double *out5, cudaStream_t st) {
+    if (backward)
+        lean_shard_state_kernel<SmoOps, true><<<1, 32, 0, st>>>(gathered, pitch, rank, world,
+                                                               State2{0.0, 0.0, 0.0, 0.0, 0.0}, out5);
+    else
+        lean_shard_state_kernel<FiltOps, false><<<1, 32, 0, st>>>(gathered, pitch, rank, world,
+                                                                 State2{state_init, 0.0, cov_init, 0.0, cov_init}, out5);
     return cudaGetLastError();
 }
 

@@ -88,6 +88,21 @@ struct LeanTrack {
     double *sex;   // [G * 8][9][32]  per-run exclusive (from the far end of the group) smoothing element
 };
 
+// A chromosome split over several GPUs (contiguous bin ranges, one shard per rank): what a shard knows
+// about its neighbours.  The shards exchange ONE payload per pass (cabi.cu: cb200_split_*):
+//   forward : the shard's filtering aggregate (14 f64) + kappa and qScale of its first bin
+//   backward: the shard's smoothing aggregate (9 f64) + the filtered Gaussian of its last bin (5 f64)
+struct LeanShard {
+    int32_t is_first, is_last;  // of the chromosome (an unsplit chromosome: both 1)
+    const double *fwd_next;     // device: forward payload of the NEXT shard ([14] kappa, [15] qScale of its first
+                                // bin, as that shard's forward pass of this sweep saw them); is_last == 0
+    const double *bwd_prev;     // device: backward payload of the PREVIOUS shard ([9..13] filtered Gaussian of its
+                                // last bin, float32 values); is_first == 0, kappa-carrying backward replay only
+    const double *first;        // device double[5] or nullptr: Gaussian the shard's scan starts from
+                                // (forward: at the shard's first bin; backward: just beyond its last)
+};
+constexpr int LEAN_PAYLOAD = 16;  // doubles per shard per pass
+
 struct LeanFwdArgs {
     LeanGeom g;
     const double2 *SA, *SB;  // run-major fold statistics {S0,S1}, {S2,SL}
@@ -99,6 +114,7 @@ struct LeanFwdArgs {
     Model2 M;                // F = [[1, F01], [0, 1]] only
     double state_init, cov_init, kap_min, kap_max;
     int32_t want_nll, do_store;
+    LeanShard sh;
 };
 
 struct LeanBwdArgs {
@@ -112,6 +128,9 @@ struct LeanBwdArgs {
     Model2 M;
     double nu, kap_lo, kap_hi;
     double qi00, qi01, qi10, qi11;  // Q0^-1
+    LeanShard sh;
+    float *kap_discard;             // device float: where a non-last shard drops the kappa of the bin after its
+                                    // last one (the next shard computes that multiplier itself)
 };
 
 // all return the cudaError_t of the launch; a forward pass = compose, prefix, replay in this order, a
@@ -121,6 +140,16 @@ cudaError_t lean_fwd_prefix(const LeanFwdArgs &a, cudaStream_t st);
 cudaError_t lean_fwd_replay(const LeanFwdArgs &a, cudaStream_t st);
 cudaError_t lean_bwd_suffix(const LeanBwdArgs &a, cudaStream_t st);
 cudaError_t lean_bwd_replay(const LeanBwdArgs &a, bool publish, cudaStream_t st);
+// Split chromosomes.  lean_reduce_groups: the shard's whole aggregate (forward: filtering element, 14 f64;
+// backward: smoothing element, 9 f64) into out[0..N).  lean_shard_state: the Gaussian this shard's scan starts
+// from, out of the gathered payloads ([world][pitch] doubles, element first): forward = the prior pushed through
+// the shards before `rank`, backward = "nothing beyond" pushed through the shards after it.
+cudaError_t lean_reduce_groups(const double *agg, const LeanGeom &g, bool backward, double *out, cudaStream_t st);
+// the non-aggregate part of a payload: forward [14], [15] = kappa, qScale of the shard's first bin; backward
+// [9..13] = filtered Gaussian of its last bin
+cudaError_t lean_payload_tail(const LeanFwdArgs &a, const LeanTrack &trk, bool backward, double *payload, cudaStream_t st);
+cudaError_t lean_shard_state(const double *gathered, int pitch, int rank, int world, bool backward, double state_init,
+                             double cov_init, double *out5, cudaStream_t st);
 // run-major <-> linear copies of per-bin float vectors (fill: value of the padding positions)
 cudaError_t lean_gather_f32(const float *linear, float *run_major, const LeanGeom &g, float fill, cudaStream_t st);
 cudaError_t lean_scatter_f32(const float *run_major, float *linear, const LeanGeom &g, cudaStream_t st);

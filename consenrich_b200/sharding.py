@@ -215,3 +215,178 @@ class DeviceShard:
 
     def sums(self):
         return self.ts.sums.clone()
+
+
+# ------------------------------------------------------------------------------------------
+# cfixedBackgroundECM on a chromosome split into contiguous ranges (lean sweeps, csrc/lean_kernels.cuh)
+# ------------------------------------------------------------------------------------------
+PAYLOAD = 16  # doubles per shard per pass (include/consenrich_b200.h: CB200_SPLIT_PAYLOAD)
+
+
+class EcmShard:
+    """One shard of a split chromosome on one GPU: the device-side half of ``split_ecm`` (C ABI
+    ``cb200_split_*``).  ``data`` / ``munc``: float32 [m, ld] device tensors of the shard's intervals;
+    ``kap``: float32 [n] (warm start in, fitted multipliers out); ``qscale``: float32 [n] or None."""
+
+    def __init__(self, ctx, model, nu, data, munc, ld, n, kap, qscale, rank, world, residuals=True):
+        import torch
+        from . import _lib
+        self.torch, self._lib = torch, _lib
+        self.ctx, self.model, self.nu = ctx, model, float(nu)
+        self.data, self.munc, self.ld, self.n, self.m = data, munc, int(ld), int(n), int(data.shape[0])
+        self.kap, self.qs, self.rank, self.world = kap, qscale, int(rank), int(world)
+        dev = data.device
+        f32, f64 = torch.float32, torch.float64
+        self.payload = torch.zeros(PAYLOAD, dtype=f64, device=dev)
+        self.sums = torch.zeros(2, dtype=f64, device=dev)
+        self.xs = torch.empty((n, 2), dtype=f32, device=dev)
+        self.Ps = torch.empty((n, 2, 2), dtype=f32, device=dev)
+        self.lag = torch.empty((n, 2, 2), dtype=f32, device=dev)  # row n-1 belongs to a non-final shard only
+        self.resid = torch.empty((n, self.m), dtype=f32, device=dev) if residuals else None
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else C.c_void_p(t.data_ptr())
+
+    def _call(self, name, *args):
+        self._lib.check(getattr(self.ctx._lib, name)(self.ctx.handle, *args))
+
+    def begin(self):
+        self._call("cb200_split_begin", C.byref(self.model), self.nu, self._p(self.data), self._p(self.munc), self.m,
+                   self.n, self.ld, self._p(self.qs), self._p(self.kap), int(self.rank == 0),
+                   int(self.rank == self.world - 1))
+
+    def forward_compose(self):
+        self._call("cb200_split_forward_compose", self._p(self.payload))
+        return self.payload
+
+    def forward_replay(self, gathered, with_nll, store, track_set):
+        self._call("cb200_split_forward_replay", self._p(gathered), self.rank, self.world, int(with_nll), int(store),
+                   int(track_set), self._p(self.sums))
+
+    def backward_compose(self, track_set):
+        self._call("cb200_split_backward_compose", int(track_set), self._p(self.payload))
+        return self.payload
+
+    def backward_replay(self, gathered_bwd, gathered_fwd, track_set, publish):
+        self._call("cb200_split_backward_replay", self._p(gathered_bwd), self._p(gathered_fwd), self.rank, self.world,
+                   int(track_set), int(publish), self._p(self.xs), self._p(self.Ps), self._p(self.lag))
+
+    def end(self):
+        if self.resid is not None:
+            self._call("cb200_residuals", self._p(self.data), self.m, self.n, self.ld, self._p(self.xs), 2, self._p(self.resid))
+        self._call("cb200_split_end", self._p(self.kap))
+
+
+class LocalGather:
+    """The collectives of ``split_ecm`` when every shard lives in this process (one GPU emulating several):
+    payloads are stacked, sums added.  ``TorchGather`` is the same interface over NCCL."""
+
+    def gather(self, payloads, out):
+        for r, p in enumerate(payloads):
+            out[r].copy_(p)
+        return out
+
+    def total(self, sums):
+        t = sums[0].clone()
+        for s in sums[1:]:
+            t += s
+        return float(t[1].item())
+
+
+class TorchGather:
+    """One shard per rank: ONE all-gather of 128 bytes per rank per pass (NCCL on the GPUs), one all-reduce of
+    the NLL per ECM iteration."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist, self.group = dist, group
+
+    def gather(self, payloads, out):
+        self.dist.all_gather_into_tensor(out.view(-1), payloads[0], group=self.group)
+        return out
+
+    def total(self, sums):
+        t = sums[0].clone()
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+        return float(t[1].item())
+
+
+def split_ecm(shards, comm, max_iters, inner_iters, rtol, patience=2):
+    """cfixedBackgroundECM (cconsenrich.pyx:7660-8442; 2-state, kappa the only multiplier fitted) on ONE
+    chromosome held as ``shards`` -- the ``EcmShard`` objects of THIS process, in interval order: one per rank
+    under torchrun (``comm = TorchGather()``), all of them in a single-process emulation (``LocalGather()``).
+
+    The iteration structure is that of ``cb200_ecm_device`` (csrc/cabi.cu: ecm_device_lean): per iteration
+    ``inner_iters`` forward + kappa-carrying backward sweeps, then the NLL forward pass, which -- when another
+    iteration follows -- is that iteration's opening pass run ahead into the spare track set; the stopping rule
+    is evaluated on the all-reduced NLL, so every rank takes the same decision.  Per pass the shards exchange one
+    payload (forward: filtering aggregate + first interval's kappa / qScale; backward: smoothing aggregate + last
+    interval's filtered Gaussian).  Returns the diagnostics of the reference's dict (pyx:8409-8425)."""
+    torch = shards[0].torch
+    world = shards[0].world
+    dev = shards[0].data.device
+    new = lambda: torch.zeros((world, PAYLOAD), dtype=torch.float64, device=dev)
+    g_fwd = [[new(), new()] for _ in shards]   # per local shard, per track set: the forward payloads that set was built from
+    g_scr = [new() for _ in shards]            # forward passes that store nothing
+    g_bwd = [new() for _ in shards]
+
+    def exchange(payloads, outs):
+        if len(shards) == 1:
+            comm.gather(payloads, outs[0])
+        else:  # emulation: every shard sees the same stack
+            comm.gather(payloads, outs[0])
+            for o in outs[1:]:
+                o.copy_(outs[0])
+
+    def forward(track_set, with_nll, store):
+        pay = [s.forward_compose() for s in shards]
+        outs = [g[track_set] for g in g_fwd] if store else g_scr
+        exchange(pay, outs)
+        for s, g in zip(shards, outs):
+            s.forward_replay(g, with_nll, store, track_set)
+
+    def backward(track_set, publish):
+        if not publish:
+            pay = [s.backward_compose(track_set) for s in shards]
+            exchange(pay, g_bwd)
+        for s, gb, gf in zip(shards, g_bwd, g_fwd):
+            s.backward_replay(gb, gf[track_set], track_set, publish)
+
+    for s in shards:
+        s.begin()
+    prev, init_nll, has_init, stable, inc, converged = 1.0e16, 0.0, False, 0, 0, False
+    rel_impr = abs_rel = 0.0
+    cur_set, opened, iters_done = 0, False, 0
+    for i in range(int(max_iters)):
+        iters_done = i + 1
+        for _ in range(int(inner_iters)):
+            if not opened:
+                forward(cur_set, False, True)
+            opened = False
+            backward(cur_set, False)
+        ahead = i + 1 < max_iters and inner_iters > 0
+        forward(1 - cur_set if ahead else cur_set, True, ahead)
+        cur = comm.total([s.sums for s in shards])
+        # convergence bookkeeping of cconsenrich.pyx:8337-8407
+        has_prev = has_init
+        if not has_prev:
+            init_nll, has_init = cur, True
+        elif cur > prev + 1.0e-12 * max(abs(prev), 1.0):
+            inc += 1
+        delta = abs(cur - prev) if has_prev else 0.0
+        scale = max(abs(prev) if has_prev else abs(cur), abs(cur), 1.0)
+        rel_impr, abs_rel = ((prev - cur) / scale, delta / scale) if has_prev else (0.0, 0.0)
+        prev = cur
+        stable = stable + 1 if (has_prev and delta <= rtol * scale) else 0
+        if stable >= patience:
+            converged = True
+            break
+        if ahead:
+            cur_set, opened = 1 - cur_set, True
+    backward(cur_set, True)
+    for s in shards:
+        s.end()
+    return {"iters_done": iters_done, "converged": converged, "stable_iters": stable, "nll_increase_count": inc,
+            "initial_nll": init_nll, "final_nll": prev, "final_abs_rel_change": abs_rel,
+            "final_rel_improvement": rel_impr}

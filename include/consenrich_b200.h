@@ -408,6 +408,35 @@ CB200_API int cb200_host_munc_seed_pass(cb200_ctx *ctx, const cb200_munc_seed_ar
 CB200_API int cb200_ema(cb200_ctx *ctx, const void *x, int64_t n, int32_t is_double, double alpha, void *out);
 CB200_API int cb200_host_ema(cb200_ctx *ctx, const void *x, int64_t n, int32_t is_double, double alpha, void *out);
 
+/* ---- a chromosome split over several GPUs ---------------------------------------
+ * cfixedBackgroundECM (2-state, kappa the only multiplier fitted) on ONE chromosome whose bins are split into
+ * contiguous ranges, one shard per rank / context.  The shards run the same lean sweeps as a whole chromosome
+ * (csrc/lean_kernels.cuh) and exchange one payload of CB200_SPLIT_PAYLOAD doubles per pass, which the caller
+ * all-gathers (NCCL; consenrich_b200/sharding.py: SplitECM) -- nothing else crosses the GPUs:
+ *   forward : [0..13] the shard's filtering aggregate, [14] kappa and [15] qScale of its first interval
+ *   backward: [0..8] the shard's smoothing aggregate, [9..13] the filtered Gaussian of its last interval
+ * A pass = compose (local, fills the payload) -> all-gather -> replay (local).  The kappa of a shard's first
+ * interval (cconsenrich.pyx:8244-8298 needs smoothed intervals k and k+1 on either side of the boundary) is
+ * formed by that shard from the previous shard's last filtered interval, which rides in the backward payload.
+ * All pointers are device pointers; every call is asynchronous on the context's stream except cb200_split_end.
+ *   sums (forward_replay, with_nll): device double[2], [1] receives the shard's part of the NLL.
+ *   set: which of the two forward-track sets the pass writes / reads (the ECM runs the pass that closes an
+ *        iteration ahead into the spare set).  gathered_fwd of backward_replay: the forward payloads gathered
+ *        for the forward pass that wrote `set`. */
+#define CB200_SPLIT_PAYLOAD 16
+CB200_API int cb200_split_begin(cb200_ctx *ctx, const cb200_model *model, double nu, const float *data,
+                                const float *munc, int64_t m, int64_t n, int64_t ld, const float *qscale,
+                                const float *kap, int32_t is_first, int32_t is_last);
+CB200_API int cb200_split_forward_compose(cb200_ctx *ctx, double *payload);
+CB200_API int cb200_split_forward_replay(cb200_ctx *ctx, const double *gathered, int32_t rank, int32_t world,
+                                         int32_t with_nll, int32_t store, int32_t set, double *sums);
+CB200_API int cb200_split_backward_compose(cb200_ctx *ctx, int32_t set, double *payload);
+CB200_API int cb200_split_backward_replay(cb200_ctx *ctx, const double *gathered_bwd, const double *gathered_fwd,
+                                          int32_t rank, int32_t world, int32_t set, int32_t publish, float *xs,
+                                          float *Ps, float *lag);
+/* writes the shard's kappa back in interval order (kap may be NULL), waits for the stream, ends the split */
+CB200_API int cb200_split_end(cb200_ctx *ctx, float *kap);
+
 /* ---- output: bedGraph text ----------------------------------------------
  * The rows the reference appends per chromosome and track with pandas (consenrich.py:9797-9805:
  * to_csv(sep="\t", header=False, index=False, float_format="%.4f", lineterminator="\n")):

@@ -212,3 +212,106 @@ def test_split_sweep_over_gloo_matches_the_unsharded_oracle(tmp_path, oracle):
     for p in parts:  # the all-reduce handed every rank the chromosome's totals
         assert abs(p["sums"][1] - want["nll"]) <= 2e-6 * abs(want["nll"])
         assert abs(np.float32(p["sums"][0] / n) - want["phi"]) <= 1e-4 * abs(want["phi"])
+
+
+# ------------------------------------------------------------------------------------------
+# split_ecm over gloo: the exchange protocol and the (replicated) stopping rule, with a recording stand-in
+# for the device shard
+# ------------------------------------------------------------------------------------------
+class RecordingShard:
+    """Stands in for sharding.EcmShard: payloads carry (rank, pass counter), the NLL part of each shard is a
+    fixed sequence that converges, and every call is logged with what it was handed."""
+
+    def __init__(self, rank, world):
+        import torch
+        self.torch, self.rank, self.world = torch, rank, world
+        self.data = torch.zeros(1)  # split_ecm reads .device from it
+        self.sums = torch.zeros(2, dtype=torch.float64)
+        self.payload = torch.zeros(16, dtype=torch.float64)
+        self.log, self.passes, self.nll_calls = [], 0, 0
+
+    def begin(self):
+        self.log.append(("begin",))
+
+    def forward_compose(self):
+        self.passes += 1
+        self.payload[:] = 0
+        self.payload[0], self.payload[1], self.payload[14] = self.rank, self.passes, 100 + self.rank
+        return self.payload
+
+    def forward_replay(self, gathered, with_nll, store, track_set):
+        self.log.append(("fwd", int(track_set), bool(with_nll), bool(store), gathered.clone()))
+        if with_nll:
+            self.nll_calls += 1
+            self.sums[1] = (1000.0 + 100.0 * 0.1 ** self.nll_calls) * (self.rank + 1)  # converges geometrically
+
+    def backward_compose(self, track_set):
+        self.passes += 1
+        self.payload[:] = 0
+        self.payload[0], self.payload[1], self.payload[9] = self.rank, self.passes, 200 + self.rank
+        return self.payload
+
+    def backward_replay(self, gathered_bwd, gathered_fwd, track_set, publish):
+        self.log.append(("bwd", int(track_set), bool(publish), gathered_bwd.clone(), gathered_fwd.clone()))
+
+    def end(self):
+        self.log.append(("end",))
+
+
+def _ecm_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import pickle
+
+    import torch.distributed as dist
+
+    from consenrich_b200 import sharding
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shard = RecordingShard(rank, world)
+        diag = sharding.split_ecm([shard], sharding.TorchGather(), max_iters=12, inner_iters=2, rtol=1e-4)
+        log = [tuple(x.numpy() if hasattr(x, "numpy") else x for x in e) for e in shard.log]
+        with open(os.path.join(out_dir, f"ecm{rank}.pkl"), "wb") as f:
+            pickle.dump((diag, log), f)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_split_ecm_protocol_over_gloo(tmp_path):
+    import pickle
+    import socket
+
+    import torch.multiprocessing as mp
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    world = 2
+    mp.spawn(_ecm_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    runs = [pickle.load(open(tmp_path / f"ecm{r}.pkl", "rb")) for r in range(world)]
+    (d0, l0), (d1, l1) = runs
+    # every rank saw the same all-reduced NLL, hence took the same decisions
+    assert d0 == d1 and d0["converged"] and 2 < d0["iters_done"] < 12
+    assert [e[:3] if e[0] == "fwd" else e[:3] for e in l0] == [e[:3] if e[0] == "fwd" else e[:3] for e in l1]
+    assert l0[0] == ("begin",) and l0[-1] == ("end",) and l0[-2][0] == "bwd" and l0[-2][2] is True  # publish last
+    for log in (l0, l1):
+        stored = {}  # track set -> forward payloads it was built from
+        for e in log[1:-1]:
+            if e[0] == "fwd":
+                _, s, with_nll, store, g = e
+                assert g.shape == (world, 16) and list(g[:, 0]) == [0.0, 1.0]      # rank order
+                assert g[0, 1] == g[1, 1] and list(g[:, 14]) == [100.0, 101.0]     # same pass on both ranks
+                if store:
+                    stored[s] = g
+            else:
+                _, s, publish, gb, gf = e
+                # the backward pass of a track set is handed the forward payloads of the pass that stored it,
+                # even when a later, non-storing NLL pass has run in between
+                assert np.array_equal(gf, stored[s])
+                if not publish:
+                    assert list(gb[:, 0]) == [0.0, 1.0] and list(gb[:, 9]) == [200.0, 201.0]
+    # iteration structure: 2 sweeps per iteration, the closing NLL pass opens the next iteration
+    kinds = [(e[0],) + tuple(e[1:4] if e[0] == "fwd" else e[1:3]) for e in l0[1:-1]]
+    assert kinds[:5] == [("fwd", 0, False, True), ("bwd", 0, False), ("fwd", 0, False, True), ("bwd", 0, False),
+                         ("fwd", 1, True, True)]
+    assert kinds[5:8] == [("bwd", 1, False), ("fwd", 1, False, True), ("bwd", 1, False)]
