@@ -421,7 +421,7 @@ def run_b200_arm(args):
 
     # ---- timed region: exactly K steps, CUDA events on the launching stream ----
     ctx.reset_timing()
-    ctx.enable_timing(True)
+    ctx.enable_timing(True, stride=args.timing_stride)
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
@@ -434,6 +434,7 @@ def run_b200_arm(args):
     ms_total = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
     kern = ctx.kernel_ms()
+    kern_all = ctx.kernel_launches()
     ctx.enable_timing(False)
     nll_device = nll_sum[0]
     # diagnostic: the same K steps without the per-kernel event pairs (how much the bracketing costs)
@@ -450,7 +451,7 @@ def run_b200_arm(args):
     e2e_s, h2d, d2h, e2e_launches, nll_e2e = 0.0, 0, 0, 0, 0.0
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     host_d = host_v = None
-    if my_bins:
+    if my_bins and args.e2e_steps > 0:
         c0 = max(mine, key=lambda c: bins_all[c])
         host_d = torch.empty((m, n_max), dtype=f32, pin_memory=True)
         host_v = torch.empty((m, n_max), dtype=f32, pin_memory=True)
@@ -516,8 +517,8 @@ def run_b200_arm(args):
         forced = int(os.environ.get("CB200_LEAN_LOGL", "0") or 0)
         log_run_of = (lambda n: forced) if forced in (5, 6) else (lambda n: 5)
         alg = algorithmic_bytes(m, my_bins, lean, log_run_of)
-        per = {k_: (v[0] / v[1]) for k_, v in kern.items() if v[1] > 0}          # ms per launch
-        tot = {k_: v[0] for k_, v in kern.items() if v[1] > 0}                   # ms inside the timed region
+        per = {k_: (v[0] / v[1]) for k_, v in kern.items() if v[1] > 0}          # ms per (sampled) launch
+        tot = {k_: per[k_] * kern_all[k_] for k_ in per}                         # ms inside the timed region
         dom = max(tot, key=lambda k_: tot[k_])
         by_kernel = {}
         for k_ in per:
@@ -543,7 +544,11 @@ def run_b200_arm(args):
                     "algorithmic_bytes_per_launch": alg_dom,
                     "frac_by_kernel": by_kernel,
                     "kernel_ms_per_launch": per,
-                    "kernel_launches_per_step": {k_: kern[k_][1] / args.steps for k_ in per},
+                    "kernel_launches_per_step": {k_: kern_all[k_] / args.steps for k_ in per},
+                    "kernel_launches_timed": {k_: kern[k_][1] for k_ in per},
+                    "timing": f"CUDA events on the launching stream around every {args.timing_stride}-th launch of each "
+                              "kernel family inside the timed region (an event pair costs the bracketed kernel's "
+                              "neighbours their overlap, about 5 us per launch)",
                     "kernel_share_of_step": {k_: tot[k_] / ms_total for k_ in per},
                     "rank0_step": {"algorithmic_bytes": sum(v[0] for v in alg.values()),
                                    "algorithmic_GBps": sum(v[0] for v in alg.values()) / (ms_total / args.steps * 1e-3) / 1e9,
@@ -556,7 +561,7 @@ def run_b200_arm(args):
         cpu = {"value": None, "unit": UNIT, "cores": 1, "kind": None, "sample": None}
         check = {"final_nll_sum_device": nll_device, "final_nll_sum_e2e": nll_e2e,
                  "note": "device and e2e legs run different synthetic bytes; parity is the block below"}
-        if world == 1 and not args.no_cpu_baseline and my_bins:
+        if world == 1 and not args.no_cpu_baseline and my_bins and host_d is not None:
             cpu, chk = cpu_baseline_and_check(cb, m, host_d.numpy(), host_v.numpy(), args.cpu_bins)
             check.update(chk)
         line = {
@@ -636,8 +641,10 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=2, help="0 skips the e2e leg (profiling runs)")
     ap.add_argument("--e2e-threads", type=int, default=3, help="host threads that drive chromosomes concurrently in the e2e leg")
+    ap.add_argument("--timing-stride", type=int, default=7,
+                    help="every n-th launch of a kernel family is event-timed (7 is coprime to the 24 chromosomes and the 16 / 31 passes of a call, so the samples cover every position)")
     ap.add_argument("--cpu-bins", type=int, default=None, help="bins of the cpu_baseline / check slice")
     args = ap.parse_args()
     if args.cpu_bins is None:

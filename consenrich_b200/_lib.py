@@ -103,6 +103,8 @@ SIGNATURES = {
     "cb200_ctx_enable_timing": (C.c_int, [_vp, C.c_int]),
     "cb200_ctx_kernel_ms": (C.c_int, [_vp, C.c_int, C.POINTER(_dbl), C.POINTER(_i64)]),
     "cb200_ctx_reset_timing": (C.c_int, [_vp]),
+    "cb200_ctx_set_timing_stride": (C.c_int, [_vp, C.c_int]),
+    "cb200_ctx_kernel_launches": (C.c_int, [_vp, C.c_int, C.POINTER(_i64)]),
     "cb200_set_scan_substeps": (C.c_int, [C.c_int]),
     "cb200_set_lean_sweeps": (C.c_int, [C.c_int, C.c_int]),
     "cb200_debug_scan_times": (C.c_int, [_vp, _i64, _vp]),
@@ -243,7 +245,9 @@ class Context:
     def launch_count(self) -> int:
         return int(self._lib.cb200_ctx_launch_count(self.handle))
 
-    def enable_timing(self, on: bool = True):
+    def enable_timing(self, on: bool = True, stride: int = 1):
+        """Bracket every ``stride``-th launch of each kernel family with CUDA events."""
+        check(self._lib.cb200_ctx_set_timing_stride(self.handle, int(stride)))
         check(self._lib.cb200_ctx_enable_timing(self.handle, int(on)))
 
     def reset_timing(self):
@@ -255,6 +259,15 @@ class Context:
             ms, cnt = _dbl(), _i64()
             check(self._lib.cb200_ctx_kernel_ms(self.handle, fam, C.byref(ms), C.byref(cnt)))
             out[name] = (ms.value, cnt.value)
+        return out
+
+    def kernel_launches(self) -> dict:
+        """Launches of each family made while timing was enabled (all of them, not only the sampled ones)."""
+        out = {}
+        for fam, name in enumerate(FAMILY_NAMES):
+            cnt = _i64()
+            check(self._lib.cb200_ctx_kernel_launches(self.handle, fam, C.byref(cnt)))
+            out[name] = cnt.value
         return out
 
 

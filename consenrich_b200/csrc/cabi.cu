@@ -108,10 +108,12 @@ struct cb200_ctx {
     double *sums_host = nullptr;  // pinned double[2]
     // timing
     bool timing = false;
+    int timing_stride = 1;   // every timing_stride-th launch of a family is bracketed by events (1: all)
     std::vector<TimedSpan> spans;
     std::vector<cudaEvent_t> pool;
     double fam_ms[FAM_COUNT] = {};
-    int64_t fam_n[FAM_COUNT] = {};
+    int64_t fam_n[FAM_COUNT] = {};      // launches bracketed by events
+    int64_t fam_all[FAM_COUNT] = {};    // launches made while timing was enabled
 };
 
 namespace {
@@ -166,6 +168,7 @@ struct Span {
     bool on = false;
     Span(cb200_ctx *ctx, int fam) : c(ctx) {
         if (!c->timing) return;
+        if ((c->fam_all[fam]++ % c->timing_stride) != 0) return;
         auto get = [&](cudaEvent_t &e) {
             if (!c->pool.empty()) {
                 e = c->pool.back();
@@ -616,6 +619,20 @@ int cb200_ctx_kernel_ms(cb200_ctx *c, int family, double *ms, int64_t *launches)
     return CB200_OK;
 }
 
+int cb200_ctx_kernel_launches(cb200_ctx *c, int family, int64_t *launches) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || family < 0 || family >= FAM_COUNT || !launches) return fail(CB200_ERR_INVALID, "bad kernel family");
+    *launches = c->fam_all[family];
+    return CB200_OK;
+}
+
+int cb200_ctx_set_timing_stride(cb200_ctx *c, int stride) {
+    DeviceGuard _dg(c ? c->device : 0);
+    if (!c || stride < 1) return fail(CB200_ERR_INVALID, "timing stride must be >= 1");
+    c->timing_stride = stride;
+    return CB200_OK;
+}
+
 int cb200_debug_scan_times(cb200_ctx *c, int64_t tiles, long long *host_out) {
     DeviceGuard _dg(c ? c->device : 0);
     if (!c) return fail(CB200_ERR_INVALID, "ctx is NULL");
@@ -660,6 +677,7 @@ int cb200_ctx_reset_timing(cb200_ctx *c) {
     for (int i = 0; i < FAM_COUNT; ++i) {
         c->fam_ms[i] = 0.0;
         c->fam_n[i] = 0;
+        c->fam_all[i] = 0;
     }
     return CB200_OK;
 }

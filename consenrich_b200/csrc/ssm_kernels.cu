@@ -116,10 +116,9 @@ __device__ __forceinline__ void fold_cell(FoldAcc &a, float zf, float vf, double
     a.s0 += w;
     a.s1 += wz;
     a.s2 = fma(wz, z, a.s2);
-    // sum of logs as the log of a product: split r = mant * 2^e, mant in [1, 2)
-    const long long bits = __double_as_longlong(r);
-    a.esum += (int)((bits >> 52) & 0x7ff) - 1023;
-    a.prod *= __longlong_as_double((bits & 0x000fffffffffffffLL) | 0x3ff0000000000000LL);
+    // sum of logs as the log of a running product; fold_renorm moves its exponent into an integer
+    // counter every FOLD_RENORM cells, before it can leave the double range (1e-12 <= r <= ~1e30 per cell)
+    a.prod *= r;
 }
 
 __device__ __forceinline__ void fold_renorm(FoldAcc &a) {
@@ -137,6 +136,7 @@ constexpr int FOLD_THREADS = 256;
 #define FOLD_MIN_CTAS 4
 #endif
 constexpr int FOLD_UNROLL = 4;
+constexpr int FOLD_RENORM = 4;  // cells between renormalisations of the running product: at most 7 with the tail rows, and (3.4e38)^7, (1e-12)^7 fit a double
 
 // VEC = 4: each thread owns 4 consecutive bins and streams float4 (needs 16-byte aligned rows);
 // VEC = 1: scalar loads, any alignment.
@@ -173,7 +173,7 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
                 fold_cell(acc[3 % VEC], z[u].w, v[u].w, pad);
             }
             since += FOLD_UNROLL;
-            if (since >= 512) {
+            if (since >= FOLD_RENORM) {
 #pragma unroll
                 for (int c = 0; c < VEC; ++c) fold_renorm(acc[c]);
                 since = 0;
@@ -198,7 +198,7 @@ fold_kernel(const float *__restrict__ data, const float *__restrict__ munc, int6
 #pragma unroll
             for (int u = 0; u < FOLD_UNROLL; ++u) fold_cell(acc[0], z[u], v[u], pad);
             since += FOLD_UNROLL;
-            if (since >= 512) {
+            if (since >= FOLD_RENORM) {
                 fold_renorm(acc[0]);
                 since = 0;
             }
@@ -1366,29 +1366,51 @@ __global__ void backward_shard_prefix_kernel(const double *aggs, int rank, int n
 constexpr int RES_THREADS = 256;
 constexpr int RES_SMEM_BUDGET = 96 * 1024;  // two CTAs per SM
 
+__device__ __forceinline__ void cp_async4(unsigned dst_shared, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_shared), "l"(src) : "memory");
+}
+
+// WHOLE: the tile spans all m tracks (its output rows are one contiguous stretch).  VEC: 16-byte stores
+// (the launcher checks the alignment they need).  Index arithmetic is 32-bit and incremental throughout: the
+// first version of this kernel spent 37 instructions per element and was issue-bound (profiles/README.md).
+template <bool WHOLE, bool VEC>
 __global__ void __launch_bounds__(RES_THREADS)
 residual_kernel(const float *__restrict__ data, int64_t m_all, int64_t n, int64_t ld, const float *__restrict__ xs,
                 int dim, float *__restrict__ resid, int bins, int m_chunk) {
     extern __shared__ float res_tile[];  // [m][bins + 1] then level[bins]
-    // tracks [j0, j0 + m) of the m_all (one chunk unless m_all exceeds what shared memory holds)
-    const int64_t j0 = (int64_t)blockIdx.y * m_chunk;
+    // tracks [j0, j0 + m) of the m_all; the chunks of one bin range are neighbours in launch order, so the
+    // pieces of an output row are written close together in time
+    const int chunks = (int)((m_all + m_chunk - 1) / m_chunk);
+    const int64_t bid = blockIdx.x;
+    const int64_t j0 = (bid % chunks) * m_chunk;
     const int m = (int)min((int64_t)m_chunk, m_all - j0);
     data += j0 * ld;
     const int pitch = bins + 1;
     float *level = res_tile + (size_t)m_chunk * pitch;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t k0 = (int64_t)blockIdx.x * bins;
+    const int64_t k0 = (bid / chunks) * bins;
     const int nb = (int)min((int64_t)bins, n - k0);
     // ---- load: the whole tile by 4-byte cp.async (no registers, every copy in flight at once); a warp
     //      copies 32 consecutive bins of one track per instruction: one 128-byte line, conflict-free ----
-    const int nseg = (nb + 31) >> 5;
+    const int nfull = nb >> 5, tail = nb & 31;
     for (int j = warp; j < m; j += RES_THREADS / 32) {
-        const float *row = data + (int64_t)j * ld + k0;
-        float *trow = res_tile + j * pitch;
-        for (int sgm = 0; sgm < nseg; ++sgm) {
-            const int kk = (sgm << 5) + lane;
-            if (kk < nb) cp_async_full<4>(trow + kk, row + kk);
+        const float *g = data + (int64_t)j * ld + k0 + lane;
+        unsigned sa = (unsigned)__cvta_generic_to_shared(res_tile + j * pitch + lane);
+        int sgm = 0;
+        for (; sgm + 4 <= nfull; sgm += 4) {
+            cp_async4(sa, g);
+            cp_async4(sa + 128, g + 32);
+            cp_async4(sa + 256, g + 64);
+            cp_async4(sa + 384, g + 96);
+            sa += 512;
+            g += 128;
         }
+        for (; sgm < nfull; ++sgm) {
+            cp_async4(sa, g);
+            sa += 128;
+            g += 32;
+        }
+        if (lane < tail) cp_async4(sa, g);
     }
     cp_async_commit();
     for (int kk = tid; kk < nb; kk += RES_THREADS) level[kk] = __ldg(xs + (k0 + kk) * dim);
@@ -1396,17 +1418,63 @@ residual_kernel(const float *__restrict__ data, int64_t m_all, int64_t n, int64_
     __syncthreads();
     // ---- store: the [nb][m] block in memory order ----
     const int total = nb * m;
-    const int dkk = RES_THREADS / m, djj = RES_THREADS - dkk * m;
-    int kk = tid / m, jj = tid - kk * m;
     float *out = resid + k0 * m_all + j0;
-    const bool whole = m == m_all;  // the block of output rows is one contiguous stretch
-    for (int idx = tid; idx < total; idx += RES_THREADS) {
-        __stcs(whole ? out + idx : out + (int64_t)kk * m_all + jj, res_tile[jj * pitch + kk] - level[kk]);
-        kk += dkk;
-        jj += djj;
-        if (jj >= m) {
-            jj -= m;
-            kk += 1;
+    if (VEC) {
+        // four consecutive outputs per thread and store: tracks jj .. jj + 3 of one bin (or the wrap into the next)
+        const int quads = total >> 2;
+        const int dkk = (4 * RES_THREADS) / m, djj = 4 * RES_THREADS - dkk * m;
+        int kk = (4 * tid) / m, jj = 4 * tid - kk * m;
+        const int m_all32 = (int)m_all;
+        for (int q = tid; q < quads; q += RES_THREADS) {
+            float4 v;
+            if (jj + 3 < m) {
+                const float *t = res_tile + jj * pitch + kk;
+                const float lv = level[kk];
+                v = make_float4(t[0] - lv, t[pitch] - lv, t[2 * pitch] - lv, t[3 * pitch] - lv);
+            } else {  // the quad runs over the end of a bin's tracks (WHOLE only: chunks are multiples of 4)
+                float w[4];
+                int k2 = kk, j2 = jj;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    w[u] = res_tile[j2 * pitch + k2] - level[k2];
+                    if (++j2 == m) {
+                        j2 = 0;
+                        ++k2;
+                    }
+                }
+                v = make_float4(w[0], w[1], w[2], w[3]);
+            }
+            float *dst = WHOLE ? out + 4 * q : out + (int64_t)kk * m_all32 + jj;
+            __stcs(reinterpret_cast<float4 *>(dst), v);
+            kk += dkk;
+            jj += djj;
+            if (jj >= m) {
+                jj -= m;
+                kk += 1;
+            }
+        }
+        if (WHOLE) {  // at most three elements left over (last, ragged tile)
+            const int idx = 4 * quads + tid;
+            if (idx < total) {
+                const int k2 = idx / m, j2 = idx - k2 * m;
+                __stcs(out + idx, res_tile[j2 * pitch + k2] - level[k2]);
+            }
+        }
+    } else {
+        const int dkk = RES_THREADS / m, djj = RES_THREADS - dkk * m;
+        int kk = tid / m, jj = tid - kk * m;
+        for (int idx = tid; idx < total; idx += RES_THREADS) {
+            const float v = res_tile[jj * pitch + kk] - level[kk];
+            if (WHOLE)
+                __stcs(out + idx, v);
+            else
+                __stcs(out + (int64_t)kk * m_all + jj, v);
+            kk += dkk;
+            jj += djj;
+            if (jj >= m) {
+                jj -= m;
+                kk += 1;
+            }
         }
     }
 }
@@ -1640,9 +1708,11 @@ cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld
     // bins per CTA: as many 32-bin groups as the shared-memory budget holds for m tracks (at least
     // one; m beyond ~1700 tracks would need more than a CTA's shared memory for a single group)
     const int64_t max_bytes = 200 * 1024;
-    const int64_t m_chunk = m <= 1024 ? m : 1024;
+    // Few tracks: a tile spans all of them, so the output rows it writes are one contiguous stretch whatever m
+    // is.  Many tracks: chunks of 128 (output pieces of 512 aligned bytes, input rows visited for 640 bytes):
+    // a tile of all 1000 tracks would visit every input row for 128 bytes only.
+    const int64_t m_chunk = m <= 96 ? m : 128;
     const int64_t chunks = (m + m_chunk - 1) / m_chunk;
-    if (chunks > 65535) return cudaErrorInvalidValue;
     int64_t bins = (RES_SMEM_BUDGET / 4 - 1) / (m_chunk + 1) / 32 * 32;
     if (bins < 32) bins = 32;
     if (bins > 512) bins = 512;
@@ -1650,15 +1720,23 @@ cudaError_t launch_residuals(const float *data, int64_t m, int64_t n, int64_t ld
     while (bins > 32 && (n + bins - 1) / bins < 296) bins -= 32;
     const int64_t smem = (m_chunk * (bins + 1) + bins) * 4;
     if (smem > max_bytes) return cudaErrorInvalidValue;
-    static int64_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(residual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes);
+    const bool whole = chunks == 1;
+    // 16-byte stores: the output block of a tile starts on a 16-byte boundary (k0 is a multiple of 32) when the
+    // array does; a chunked tile also needs every output row piece aligned (m and the chunk multiples of 4)
+    const bool vec = (reinterpret_cast<uintptr_t>(resid) & 15) == 0 && (whole || (m % 4 == 0 && m_chunk % 4 == 0)) &&
+                     m * 4 * (int64_t)RES_THREADS < (int64_t)1 << 30;
+    auto kern = whole ? (vec ? residual_kernel<true, true> : residual_kernel<true, false>)
+                      : (vec ? residual_kernel<false, true> : residual_kernel<false, false>);
+    static bool configured[4] = {false, false, false, false};
+    const int which = (whole ? 2 : 0) + (vec ? 1 : 0);
+    if (!configured[which]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_bytes);
         if (e != cudaSuccess) return e;
-        configured = max_bytes;
+        configured[which] = true;
     }
     const int64_t blocks = (n + bins - 1) / bins;
-    residual_kernel<<<dim3((unsigned)blocks, (unsigned)chunks), RES_THREADS, (size_t)smem, st>>>(data, m, n, ld, xs, dim, resid,
-                                                                                                (int)bins, (int)m_chunk);
+    if (blocks * chunks > 0x7fffffffLL) return cudaErrorInvalidValue;
+    kern<<<(unsigned)(blocks * chunks), RES_THREADS, (size_t)smem, st>>>(data, m, n, ld, xs, dim, resid, (int)bins, (int)m_chunk);
     return cudaGetLastError();
 }
 

@@ -18,16 +18,10 @@ import warnings
 import numpy as np
 
 from . import _lib
-from .native import _ctx, _ptr
+from .native import HostPathWarning, _ctx, _ptr
 
 _HOOKS = ("_relativeSignChangePerKB", "_perIntervalOutputDiagnosticTracks")
 _saved: dict = {}
-
-
-class HostPathWarning(RuntimeWarning):
-    """A hooked driver function was handed inputs its device version does not cover and ran the
-    reference's own host function instead.  Never silent: runConsenrich itself passes float32 matrices,
-    which are covered, so this only fires for callers that deviate from it."""
 
 
 def _host_path(name, why):

@@ -785,6 +785,32 @@ def cFinalizeMuncEBTrack(localVarianceTrack, priorVarianceTrack=None, countFloor
 _saved: dict = {}
 
 
+class HostPathWarning(RuntimeWarning):
+    """An installed function was handed an input its device version does not cover and the reference's own
+    host function (the one ``install`` replaced) ran instead.  Never silent."""
+
+
+_MUNC_WINDOW_MAX = 8192  # csrc/munc_kernels.cu: tile + window must fit a CTA's shared memory
+
+
+def _make_smooth_with_host_path(original):
+    """cMuncSmoothDenseLocalEvidence for ``install``: windows beyond the device kernel's limit (a user-settable
+    muncLocalWindowSizeBP far above the dependence spans the reference sizes it from) go to the function that
+    was replaced, with a HostPathWarning, instead of failing a configuration the reference accepts."""
+    import functools
+    import warnings
+
+    @functools.wraps(cMuncSmoothDenseLocalEvidence)
+    def smooth(localEvidence, windowIntervals, excludeMask=None, eps=1.0e-12):
+        if original is not None and int(windowIntervals) > _MUNC_WINDOW_MAX:
+            warnings.warn(f"consenrich_b200: cMuncSmoothDenseLocalEvidence ran the reference's host implementation "
+                          f"(windowIntervals {int(windowIntervals)} > {_MUNC_WINDOW_MAX})", HostPathWarning, stacklevel=2)
+            return original(localEvidence, windowIntervals, excludeMask=excludeMask, eps=eps)
+        return cMuncSmoothDenseLocalEvidence(localEvidence, windowIntervals, excludeMask=excludeMask, eps=eps)
+
+    return smooth
+
+
 def install(module=None, background=True, munc=True):
     """Replace the six hot-path attributes of ``consenrich.cconsenrich`` (or ``module``) with the
     B200 implementations.  ``core.py`` looks them up by attribute at call time (core.py:4274,
@@ -799,7 +825,10 @@ def install(module=None, background=True, munc=True):
     for name in _HOT_PATH + (_BACKGROUND if background else ()) + (_MUNC if munc else ()):
         if name not in saved:
             saved[name] = getattr(module, name, None)
-        setattr(module, name, globals()[name])
+        fn = globals()[name]
+        if name == "cMuncSmoothDenseLocalEvidence":
+            fn = _make_smooth_with_host_path(saved[name])
+        setattr(module, name, fn)
     return module
 
 

@@ -129,6 +129,11 @@ CB200_API int64_t cb200_ctx_launch_count(const cb200_ctx *ctx);
 CB200_API int cb200_ctx_enable_timing(cb200_ctx *ctx, int on);
 CB200_API int cb200_ctx_kernel_ms(cb200_ctx *ctx, int family, double *ms, int64_t *launches);
 CB200_API int cb200_ctx_reset_timing(cb200_ctx *ctx);
+/* Event pairs keep neighbouring kernels from overlapping their ramps (about 5 us per launch): with a stride s
+ * only every s-th launch of each family is bracketed (cb200_ctx_kernel_ms then reports the sampled launches),
+ * while cb200_ctx_kernel_launches counts every launch of the family made with timing enabled. */
+CB200_API int cb200_ctx_set_timing_stride(cb200_ctx *ctx, int stride);
+CB200_API int cb200_ctx_kernel_launches(cb200_ctx *ctx, int family, int64_t *launches);
 /* Tuning knob (process-wide): sub-steps of 4 bins each thread of the scan kernels runs through
  * (1..16), 0 = choose per launch from the track length and the resident tile slots.  Results do not
  * depend on it beyond float64 re-association.  Also settable with CB200_SCAN_NSUB. */

@@ -190,3 +190,24 @@ def test_oracle_ema_matches_reference_build(oracle):
             x = rng.normal(size=n).astype(dt)
             np.testing.assert_array_equal(ref.cEMA(x, alpha), oracle.cEMA(x, alpha))
     assert oracle.cEMA(np.arange(5), 0.5).dtype == np.float64  # everything but float32 is filtered as float64
+
+
+def test_installed_smoother_hands_oversized_windows_to_the_function_it_replaced():
+    """No GPU needed: a window beyond the device kernel's limit (a configuration the reference accepts) goes to
+    the replaced host function under install(), with a HostPathWarning -- never a failure, never silent."""
+    import types
+
+    import consenrich_b200 as cb
+    from consenrich_b200 import native
+    calls = []
+    fake = types.ModuleType("cconsenrich")
+    fake.cMuncSmoothDenseLocalEvidence = lambda le, w, excludeMask=None, eps=1e-12: calls.append(int(w)) or "reference"
+    cb.install(fake, background=False, munc=True)
+    try:
+        ev = np.ones((2, 64), np.float32)
+        with pytest.warns(native.HostPathWarning, match="windowIntervals 9000"):
+            assert fake.cMuncSmoothDenseLocalEvidence(ev, 9000) == "reference"
+        assert calls == [9000]
+    finally:
+        cb.uninstall(fake)
+    assert fake.cMuncSmoothDenseLocalEvidence(np.ones((2, 4), np.float32), 3) == "reference"

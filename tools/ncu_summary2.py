@@ -1,7 +1,7 @@
 """Condenses an `ncu --set full` report of one cb200_ecm_device call (tools/ecm_once.py) into the JSON kept
 under profiles/ and read by bench.py for `roofline.traffic` (run where ncu is installed; launches nothing).
 
-usage: python tools/ncu_summary2.py REPORT.ncu-rep OUT.json M N "how the report was captured"
+usage: python tools/ncu_summary2.py OUT.json M N "how the reports were captured" REPORT.ncu-rep [REPORT.ncu-rep ...]
 
 Per kernel family (the names bench.py / cb200_ctx_kernel_ms use): launches seen, mean duration, DRAM bytes per
 launch, registers, occupancy, pipe / issue utilisation, stall reasons per issued instruction, and the
@@ -42,14 +42,19 @@ STALL = re.compile(r"smsp__average_warps_issue_stalled_(\w+)_per_issue_active\.r
 
 
 def main():
-    report, out_path, m, n = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
-    how = sys.argv[5] if len(sys.argv) > 5 else ""
-    out = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
-    rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, rows = rows[0], rows[1], rows[2:]
-    col = {h: i for i, h in enumerate(hdr)}
+    out_path, m, n, how, reports = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5:]
     alg = bench.algorithmic_bytes(m, [n], True, lambda _n: 5)
     fams = {}
+    for report in reports:
+        out = subprocess.run(["ncu", "-i", report, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units, rows = rows[0], rows[1], rows[2:]
+        col = {h: i for i, h in enumerate(hdr)}
+        accumulate(fams, hdr, units, rows, col)
+    finish(fams, alg, m, n, how, out_path)
+
+
+def accumulate(fams, hdr, units, rows, col):
     for r in rows:
         name = r[col["Kernel Name"]]
         fam = next((f for tag, f in FAMILY if tag in name), None)
@@ -66,6 +71,9 @@ def main():
             mt = STALL.match(h)
             if mt and r[i] not in ("", "0"):
                 k["stall"][mt.group(1)] = k["stall"].get(mt.group(1), 0.0) + float(r[i])
+
+
+def finish(fams, alg, m, n, how, out_path):
     kernels = {}
     for fam, k in fams.items():
         e = {short: v / k["n"] for short, v in k["acc"].items()}
