@@ -576,7 +576,10 @@ def run_b200_arm(args):
                            "page-locked results out), chromosomes spread over "
                            f"{args.e2e_threads} host threads (one library context each) so that copies and sweeps of different "
                            "chromosomes overlap; host matrices: one pinned pair of the rank's longest chromosome, re-shaped per "
-                           "chromosome"},
+                           "chromosome",
+                    "limiter": "the bus: every step moves h2d + d2h bytes between host memory and the GPUs (68 GB/s with one "
+                               "GPU, both directions overlapped); with N ranks the same bytes share the host's memory and "
+                               "PCIe complex, so this number scales far below the device-resident one"},
             "roofline": roofline, "cpu_baseline": cpu,
             "placement": {"sharding": "chromosomes bin-packed onto ranks, longest first; no collective on the data path",
                           "chromosomes_per_rank": [len(p) for p in plan],

@@ -686,6 +686,97 @@ __global__ void __launch_bounds__(STAT_THREADS) diag_gain_kernel(const DiagGainA
 }  // namespace
 
 // =====================================================================================
+// pivot parity with the reference on degenerate systems
+// =====================================================================================
+// The reference fails a solve when a pivot of its SEQUENTIAL pentadiagonal LDL' falls below 1e-12
+// (cconsenrich.pyx:1016-1055, 1090-1095).  Block cyclic reduction meets different pivots, so on a singular
+// system it may sail through (one positive weight under a second-difference penalty: the null space is
+// not pinned down, the reference raises, the parallel solve returns ~1e14) or flag a different index.  The
+// sequential recurrence is two divisions per unknown and cannot be parallelised, but it only has to run
+// when the outcome is in doubt: the parallel solve flagged a pivot, or the weights cannot pin the penalty's
+// null space (fewer than three positive weights).  Then one warp replays the reference's recurrence -- lanes
+// stream the weights in, lane 0 runs it -- and ITS verdict (first bad index and value, or none) replaces
+// the parallel one.
+__global__ void __launch_bounds__(256) positive_weight_count_kernel(const double *__restrict__ w, int64_t n,
+                                                                    unsigned long long *count) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += w[i] > 0.0 ? 1ull : 0ull;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+
+__global__ void __launch_bounds__(32) ldl_pivot_check_kernel(const double *__restrict__ w, int64_t n, double lam,
+                                                             double lam1, const unsigned long long *positive,
+                                                             BackgroundStatus *st) {
+    if (st->bad_index == STATUS_NONE && *positive >= 3ull) return;  // not in doubt
+    __shared__ double sw[32];
+    const int lane = threadIdx.x;
+    long long bad = -1;
+    double bad_value = 0.0;
+    // ---- the reference's first loop (pyx:1016-1031): entries of the assembled diagonal below the floor; the
+    //      first of them is its verdict whatever the factorisation meets afterwards ----
+    {
+        long long first = 0x7fffffffffffffffLL;
+        for (int64_t i = lane; i < n; i += 32) {
+            const double d = w[i] + first_diag(n, i, lam1) + second_diag(n, i, lam);
+            if (d < MIN_PIVOT) {
+                first = i;
+                break;
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, d));
+        if (first != 0x7fffffffffffffffLL) {
+            if (lane == 0) {
+                st->bad_index = first;
+                st->bad_value = w[first] + first_diag(n, first, lam1) + second_diag(n, first, lam);
+            }
+            return;
+        }
+    }
+    // ---- the factorisation's pivots (pyx:1033-1055) ----
+    double d1 = 0.0, d2 = 0.0, l1 = 0.0;  // pivots i-1, i-2; first lower diagonal at i-1
+    double r = lane < n ? w[lane] : 0.0;
+    for (int64_t c0 = 0; c0 < n; c0 += 32) {
+        sw[lane] = r;
+        __syncwarp();
+        if (c0 + 32 + lane < n) r = w[c0 + 32 + lane];
+        if (lane == 0) {
+            const int cnt = (int)min((int64_t)32, n - c0);
+            for (int u = 0; u < cnt; ++u) {
+                const int64_t i = c0 + u;
+                double d = __dadd_rn(__dadd_rn(sw[u], first_diag(n, i, lam1)), second_diag(n, i, lam));
+                // every operation rounded on its own, in the reference's order (no fused multiply-add: a pivot that
+                // is zero in exact arithmetic is pure rounding, and the message quotes it)
+                if (i == 1) {
+                    l1 = __ddiv_rn(__dadd_rn(first_off1(n, lam1), second_off1(n, 0, lam)), d1);
+                    d = __dadd_rn(d, -__dmul_rn(__dmul_rn(l1, l1), d1));
+                } else if (i >= 2) {
+                    l1 = __ddiv_rn(__dadd_rn(__dadd_rn(first_off1(n, lam1), second_off1(n, i - 1, lam)), -__dmul_rn(lam, l1)), d1);
+                    d = __dadd_rn(__dadd_rn(d, -__dmul_rn(__dmul_rn(l1, l1), d1)), -__ddiv_rn(__dmul_rn(lam, lam), d2));
+                }
+                if (i >= 1 && d < MIN_PIVOT) {
+                    if (bad < 0) {
+                        bad = i;
+                        bad_value = d;
+                    }
+                    d = MIN_PIVOT;
+                }
+                d2 = d1;
+                d1 = d;
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        st->bad_index = bad >= 0 ? bad : STATUS_NONE;
+        st->bad_value = bad_value;
+    }
+}
+
+// =====================================================================================
 // host side
 // =====================================================================================
 int64_t background_rows(int64_t n) { return (n + 1) / 2; }
@@ -781,6 +872,7 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
     double *res1 = p;
     p += n + 2;
     double *partial = p;
+    double *mu_slot = partial + 2 * BG_SUM_BLOCKS + 2;  // one word of scratch after the zero-sum multiplier
     Level0 l0{w, rhs, n, lam, lam_first, nullptr};
     auto level = [&](int l) {
         Rows r{};
@@ -882,6 +974,17 @@ cudaError_t launch_background_solve(const double *w, const double *rhs, int64_t 
     }
     finish_kernel<<<(unsigned)((n + T - 1) / T), T, 0, st>>>(solution, n, mu, out);
     ++count;
+    if (n >= 2) {
+        // the reference's own pivot verdict where the parallel one is in doubt (see ldl_pivot_check_kernel)
+        unsigned long long *positive = reinterpret_cast<unsigned long long *>(mu_slot);
+        e = cudaMemsetAsync(positive, 0, sizeof(unsigned long long), st);
+        if (e != cudaSuccess) return e;
+        int blocks = (int)((n + 255) / 256);
+        if (blocks > 592) blocks = 592;
+        positive_weight_count_kernel<<<blocks, 256, 0, st>>>(w, n, positive);
+        ldl_pivot_check_kernel<<<1, 32, 0, st>>>(w, n, lam, lam_first, positive, status);
+        count += 2;
+    }
     if (launches) *launches += count;
     return cudaGetLastError();
 }

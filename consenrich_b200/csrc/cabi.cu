@@ -962,7 +962,7 @@ int lean_setup(cb200_ctx *c, const cb200_model *mo, double nu, const float *data
         CU_TRY(cudaMemsetAsync(c->ln_part.p, 0, 512, c->stream));
     }
     // layout of ln_part: [0] counter (int32, left at zero by every launch); [128] the float a non-last shard
-    // drops its boundary kappa into; [256] two 5-double shard start states; partial sums from byte 512
+    // drops its boundary kappa into; partial sums from byte 512
     {
         Span sp(c, FAM_FOLD);
         CU_TRY(launch_fold(data, munc, m, n, ld, mo->pad, static_cast<double2 *>(c->ln_SA.p),
@@ -1188,10 +1188,9 @@ int cb200_split_forward_compose(cb200_ctx *c, double *payload) {
     }
     {
         Span sp(c, FAM_SEGSCAN);
-        CU_TRY(lean_reduce_groups(S->R.fa.sc.fagg, S->R.g, false, payload, c->stream));
-        CU_TRY(lean_payload_tail(S->R.fa, S->R.trk[0], false, payload, c->stream));
+        CU_TRY(lean_shard_payload(S->R.fa, S->R.trk[0], false, payload, c->stream));
     }
-    c->launches += 3;
+    c->launches += 2;
     return CB200_OK;
 }
 
@@ -1204,23 +1203,23 @@ int cb200_split_forward_replay(cb200_ctx *c, const double *gathered, int32_t ran
     if ((rank == 0) != (S->is_first != 0) || (rank == world - 1) != (S->is_last != 0))
         return fail(CB200_ERR_INVALID, "rank does not match the shard's position given to cb200_split_begin");
     LeanFwdArgs fa = S->R.fa;
-    double *first = reinterpret_cast<double *>(static_cast<unsigned char *>(c->ln_part.p) + 256);
     fa.trk = S->R.trk[set];
     fa.want_nll = with_nll ? 1 : 0;
     fa.do_store = store ? 1 : 0;
     fa.sums = sums ? sums : static_cast<double *>(c->sums.p);
-    fa.sh.first = first;
+    fa.sh.gathered = gathered;
+    fa.sh.rank = rank;
+    fa.sh.world = world;
     fa.sh.fwd_next = S->is_last ? nullptr : gathered + (int64_t)(rank + 1) * LEAN_PAYLOAD;
     {
         Span sp(c, FAM_SEGSCAN);
-        CU_TRY(lean_shard_state(gathered, LEAN_PAYLOAD, rank, world, false, S->mo.state_init, S->mo.cov_init, first, c->stream));
         CU_TRY(lean_fwd_prefix(fa, c->stream));
     }
     {
         Span sp(c, FAM_FWD);
         CU_TRY(lean_fwd_replay(fa, c->stream));
     }
-    c->launches += 3;
+    c->launches += 2;
     return CB200_OK;
 }
 
@@ -1230,10 +1229,9 @@ int cb200_split_backward_compose(cb200_ctx *c, int32_t set, double *payload) {
     if (!S || !payload || set < 0 || set > 1) return fail(CB200_ERR_INVALID, "no split in progress, NULL payload or bad track set");
     {
         Span sp(c, FAM_SEGSCAN);
-        CU_TRY(lean_reduce_groups(S->R.trk[set].sagg, S->R.g, true, payload, c->stream));
-        CU_TRY(lean_payload_tail(S->R.fa, S->R.trk[set], true, payload, c->stream));
+        CU_TRY(lean_shard_payload(S->R.fa, S->R.trk[set], true, payload, c->stream));
     }
-    c->launches += 2;
+    c->launches += 1;
     return CB200_OK;
 }
 
@@ -1245,18 +1243,18 @@ int cb200_split_backward_replay(cb200_ctx *c, const double *gathered_bwd, const 
     if (rank < 0 || rank >= world || set < 0 || set > 1) return fail(CB200_ERR_INVALID, "bad rank / track set");
     if (publish && (!xs || !Ps || !lag)) return fail(CB200_ERR_INVALID, "a publishing pass needs xs, Ps and lag");
     LeanBwdArgs ba = S->R.ba;
-    double *beyond = reinterpret_cast<double *>(static_cast<unsigned char *>(c->ln_part.p) + 256 + 64);
     ba.trk = S->R.trk[set];
     ba.xs = xs; ba.Ps = Ps; ba.lag = lag;
-    ba.sh.first = beyond;
+    ba.sh.gathered = gathered_bwd;
+    ba.sh.rank = rank;
+    ba.sh.world = world;
     ba.sh.fwd_next = S->is_last ? nullptr : gathered_fwd + (int64_t)(rank + 1) * LEAN_PAYLOAD;
     ba.sh.bwd_prev = S->is_first ? nullptr : gathered_bwd + (int64_t)(rank - 1) * LEAN_PAYLOAD;
     if (!publish) {
         // a publishing pass re-uses the suffix states of the kappa-carrying pass before it (same tracks)
         Span sp(c, FAM_SEGSCAN);
-        CU_TRY(lean_shard_state(gathered_bwd, LEAN_PAYLOAD, rank, world, true, 0.0, 0.0, beyond, c->stream));
         CU_TRY(lean_bwd_suffix(ba, c->stream));
-        c->launches += 2;
+        c->launches += 1;
     }
     {
         Span sp(c, publish ? FAM_PUBLISH : FAM_BWD);

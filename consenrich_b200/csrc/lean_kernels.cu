@@ -176,10 +176,18 @@ struct SmoOps {
 // positions before it.  agg: [N][pitch], out: [5][pitch].
 template <class Ops, bool REVERSE>
 __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_group_scan_kernel(const double *agg, int G, int pitch,
-                                                                           State2 first, const double *first_dev,
-                                                                           double *out) {
+                                                                           State2 first, const double *gathered,
+                                                                           int rank, int world, double *out) {
     using Elem = typename Ops::Elem;
-    if (first_dev) first = load_strided<State2>(first_dev, 1);  // a shard of a split chromosome
+    if (gathered) {
+        // a shard of a split chromosome: `first` pushed through the aggregates of the shards before it in
+        // scan order (every thread does the same few applies: no barrier, no extra launch)
+        if (!REVERSE) {
+            for (int r = 0; r < rank; ++r) first = Ops::apply(load_strided<Elem>(gathered + (int64_t)r * LEAN_PAYLOAD, 1), first);
+        } else {
+            for (int r = world - 1; r > rank; --r) first = Ops::apply(load_strided<Elem>(gathered + (int64_t)r * LEAN_PAYLOAD, 1), first);
+        }
+    }
     constexpr int N = Elem::N;
     constexpr int NW = LEAN_SCAN_THREADS / 32;
     __shared__ double sh[NW * N];
@@ -241,7 +249,9 @@ __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_group_scan_kernel(cons
 // The whole aggregate of a shard (split chromosomes): ordered reduction of the group aggregates.
 template <class Ops, bool REVERSE>
 __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_reduce_groups_kernel(const double *agg, int G, int pitch,
-                                                                              double *out) {
+                                                                              double *out, const float *kap, const float *qs,
+                                                                              const float4 *A, const float4 *B,
+                                                                              int64_t last_pos) {
     using Elem = typename Ops::Elem;
     constexpr int N = Elem::N;
     constexpr int NW = LEAN_SCAN_THREADS / 32;
@@ -272,22 +282,20 @@ __global__ void __launch_bounds__(LEAN_SCAN_THREADS) lean_reduce_groups_kernel(c
             const Elem o = shfl_down_elem(v, d);
             if ((lane & (2 * d - 1)) == 0) v = Ops::combine(v, o);
         }
-        if (lane == 0) store_strided(out, 1, v);
+        if (lane == 0) {
+            store_strided(out, 1, v);
+            // the rest of the payload: forward [14], [15] = kappa, qScale of the shard's first bin; backward
+            // [9..13] = filtered Gaussian of its last bin
+            if (!REVERSE) {
+                out[14] = (double)kap[0];
+                out[15] = qs ? (double)qs[0] : 1.0;
+            } else {
+                const float4 a = A[last_pos], b = B[last_pos];
+                out[9] = (double)a.x; out[10] = (double)a.y; out[11] = (double)a.z; out[12] = (double)a.w;
+                out[13] = (double)b.x;
+            }
+        }
     }
-}
-
-// Start state of a shard's scan from the gathered payloads (element first in every payload).
-template <class Ops, bool REVERSE>
-__global__ void lean_shard_state_kernel(const double *gathered, int pitch, int rank, int world, State2 first,
-                                        double *out5) {
-    if (threadIdx.x != 0) return;
-    State2 s = first;
-    if (!REVERSE) {
-        for (int r = 0; r < rank; ++r) s = Ops::apply(load_strided<typename Ops::Elem>(gathered + (int64_t)r * pitch, 1), s);
-    } else {
-        for (int r = world - 1; r > rank; --r) s = Ops::apply(load_strided<typename Ops::Elem>(gathered + (int64_t)r * pitch, 1), s);
-    }
-    store_strided(out5, 1, s);
 }
 
 // =====================================================================================
@@ -622,7 +630,8 @@ cudaError_t lean_fwd_compose(const LeanFwdArgs &a, cudaStream_t st) {
 
 cudaError_t lean_fwd_prefix(const LeanFwdArgs &a, cudaStream_t st) {
     const State2 prior{a.state_init, 0.0, a.cov_init, 0.0, a.cov_init};
-    lean_group_scan_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.G, a.g.Gp, prior, a.sh.first, a.sc.fpref);
+    lean_group_scan_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.G, a.g.Gp, prior, a.sh.gathered,
+                                                                      a.sh.rank, a.sh.world, a.sc.fpref);
     return cudaGetLastError();
 }
 
@@ -636,7 +645,8 @@ cudaError_t lean_fwd_replay(const LeanFwdArgs &a, cudaStream_t st) {
 
 cudaError_t lean_bwd_suffix(const LeanBwdArgs &a, cudaStream_t st) {
     const State2 beyond{0.0, 0.0, 0.0, 0.0, 0.0};
-    lean_group_scan_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.trk.sagg, a.g.G, a.g.Gp, beyond, a.sh.first, a.ssuf);
+    lean_group_scan_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.trk.sagg, a.g.G, a.g.Gp, beyond, a.sh.gathered,
+                                                                    a.sh.rank, a.sh.world, a.ssuf);
     return cudaGetLastError();
 }
 
@@ -648,42 +658,14 @@ cudaError_t lean_bwd_replay(const LeanBwdArgs &a, bool publish, cudaStream_t st)
     return cudaGetLastError();
 }
 
-namespace {
-__global__ void lean_payload_tail_kernel(const float *kap, const float *qs, const float4 *A, const float4 *B,
-                                         int64_t last_pos, int backward, double *payload) {
-    if (threadIdx.x != 0) return;
-    if (!backward) {
-        payload[14] = (double)kap[0];
-        payload[15] = qs ? (double)qs[0] : 1.0;
-    } else {
-        const float4 a = A[last_pos], b = B[last_pos];
-        payload[9] = (double)a.x; payload[10] = (double)a.y; payload[11] = (double)a.z; payload[12] = (double)a.w;
-        payload[13] = (double)b.x;
-    }
-}
-}  // namespace
-
-cudaError_t lean_payload_tail(const LeanFwdArgs &a, const LeanTrack &trk, bool backward, double *payload, cudaStream_t st) {
-    lean_payload_tail_kernel<<<1, 32, 0, st>>>(a.kap, a.qs, trk.A, trk.B, a.g.index(a.g.n - 1), backward ? 1 : 0, payload);
-    return cudaGetLastError();
-}
-
-cudaError_t lean_reduce_groups(const double *agg, const LeanGeom &g, bool backward, double *out, cudaStream_t st) {
+cudaError_t lean_shard_payload(const LeanFwdArgs &a, const LeanTrack &trk, bool backward, double *payload, cudaStream_t st) {
+    const int64_t last = a.g.index(a.g.n - 1);
     if (backward)
-        lean_reduce_groups_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(agg, g.G, g.Gp, out);
+        lean_reduce_groups_kernel<SmoOps, true><<<1, LEAN_SCAN_THREADS, 0, st>>>(trk.sagg, a.g.G, a.g.Gp, payload, a.kap, a.qs,
+                                                                               trk.A, trk.B, last);
     else
-        lean_reduce_groups_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(agg, g.G, g.Gp, out);
-    return cudaGetLastError();
-}
-
-cudaError_t lean_shard_state(const double *gathered, int pitch, int rank, int world, bool backward, double state_init,
-                             double cov_init, double *out5, cudaStream_t st) {
-    if (backward)
-        lean_shard_state_kernel<SmoOps, true><<<1, 32, 0, st>>>(gathered, pitch, rank, world,
-                                                               State2{0.0, 0.0, 0.0, 0.0, 0.0}, out5);
-    else
-        lean_shard_state_kernel<FiltOps, false><<<1, 32, 0, st>>>(gathered, pitch, rank, world,
-                                                                 State2{state_init, 0.0, cov_init, 0.0, cov_init}, out5);
+        lean_reduce_groups_kernel<FiltOps, false><<<1, LEAN_SCAN_THREADS, 0, st>>>(a.sc.fagg, a.g.G, a.g.Gp, payload, a.kap,
+                                                                                 a.qs, trk.A, trk.B, last);
     return cudaGetLastError();
 }
 

@@ -98,8 +98,8 @@ struct LeanShard {
                                 // bin, as that shard's forward pass of this sweep saw them); is_last == 0
     const double *bwd_prev;     // device: backward payload of the PREVIOUS shard ([9..13] filtered Gaussian of its
                                 // last bin, float32 values); is_first == 0, kappa-carrying backward replay only
-    const double *first;        // device double[5] or nullptr: Gaussian the shard's scan starts from
-                                // (forward: at the shard's first bin; backward: just beyond its last)
+    const double *gathered;     // device [world][LEAN_PAYLOAD] or nullptr: the payloads of this pass; the group scan
+    int32_t rank, world;        // pushes its start state through the aggregates of the shards before it
 };
 constexpr int LEAN_PAYLOAD = 16;  // doubles per shard per pass
 
@@ -140,16 +140,10 @@ cudaError_t lean_fwd_prefix(const LeanFwdArgs &a, cudaStream_t st);
 cudaError_t lean_fwd_replay(const LeanFwdArgs &a, cudaStream_t st);
 cudaError_t lean_bwd_suffix(const LeanBwdArgs &a, cudaStream_t st);
 cudaError_t lean_bwd_replay(const LeanBwdArgs &a, bool publish, cudaStream_t st);
-// Split chromosomes.  lean_reduce_groups: the shard's whole aggregate (forward: filtering element, 14 f64;
-// backward: smoothing element, 9 f64) into out[0..N).  lean_shard_state: the Gaussian this shard's scan starts
-// from, out of the gathered payloads ([world][pitch] doubles, element first): forward = the prior pushed through
-// the shards before `rank`, backward = "nothing beyond" pushed through the shards after it.
-cudaError_t lean_reduce_groups(const double *agg, const LeanGeom &g, bool backward, double *out, cudaStream_t st);
-// the non-aggregate part of a payload: forward [14], [15] = kappa, qScale of the shard's first bin; backward
-// [9..13] = filtered Gaussian of its last bin
-cudaError_t lean_payload_tail(const LeanFwdArgs &a, const LeanTrack &trk, bool backward, double *payload, cudaStream_t st);
-cudaError_t lean_shard_state(const double *gathered, int pitch, int rank, int world, bool backward, double state_init,
-                             double cov_init, double *out5, cudaStream_t st);
+// Split chromosomes: the shard's payload of a pass -- its whole aggregate (ordered reduction of the group
+// aggregates; forward: filtering element, 14 f64; backward: smoothing element, 9 f64) and, forward, [14], [15] =
+// kappa, qScale of its first bin, backward, [9..13] = the filtered Gaussian of its last bin.
+cudaError_t lean_shard_payload(const LeanFwdArgs &a, const LeanTrack &trk, bool backward, double *payload, cudaStream_t st);
 // run-major <-> linear copies of per-bin float vectors (fill: value of the padding positions)
 cudaError_t lean_gather_f32(const float *linear, float *run_major, const LeanGeom &g, float fill, cudaStream_t st);
 cudaError_t lean_scatter_f32(const float *run_major, float *linear, const LeanGeom &g, cudaStream_t st);

@@ -255,22 +255,46 @@ class EcmShard:
         self._call("cb200_split_begin", C.byref(self.model), self.nu, self._p(self.data), self._p(self.munc), self.m,
                    self.n, self.ld, self._p(self.qs), self._p(self.kap), int(self.rank == 0),
                    int(self.rank == self.world - 1))
+        # the per-pass calls are on the critical path of a sweep at 8 shards (the host issues ~6 calls per
+        # sweep): bound once, with their constant arguments already converted
+        L, h, vp = self.ctx._lib, self.ctx.handle, C.c_void_p
+        self._f = (L.cb200_split_forward_compose, L.cb200_split_forward_replay, L.cb200_split_backward_compose,
+                   L.cb200_split_backward_replay)
+        self._h = h
+        self._pay, self._sums = vp(self.payload.data_ptr()), vp(self.sums.data_ptr())
+        self._out = (vp(self.xs.data_ptr()), vp(self.Ps.data_ptr()), vp(self.lag.data_ptr()))
+        self._ptr_cache = {}
+
+    def _ptr_of(self, t):
+        k = t.data_ptr()
+        p = self._ptr_cache.get(k)
+        if p is None:
+            p = self._ptr_cache[k] = C.c_void_p(k)
+        return p
 
     def forward_compose(self):
-        self._call("cb200_split_forward_compose", self._p(self.payload))
+        rc = self._f[0](self._h, self._pay)
+        if rc:
+            self._lib.check(rc)
         return self.payload
 
     def forward_replay(self, gathered, with_nll, store, track_set):
-        self._call("cb200_split_forward_replay", self._p(gathered), self.rank, self.world, int(with_nll), int(store),
-                   int(track_set), self._p(self.sums))
+        rc = self._f[1](self._h, self._ptr_of(gathered), self.rank, self.world, int(with_nll), int(store), int(track_set),
+                        self._sums)
+        if rc:
+            self._lib.check(rc)
 
     def backward_compose(self, track_set):
-        self._call("cb200_split_backward_compose", int(track_set), self._p(self.payload))
+        rc = self._f[2](self._h, int(track_set), self._pay)
+        if rc:
+            self._lib.check(rc)
         return self.payload
 
     def backward_replay(self, gathered_bwd, gathered_fwd, track_set, publish):
-        self._call("cb200_split_backward_replay", self._p(gathered_bwd), self._p(gathered_fwd), self.rank, self.world,
-                   int(track_set), int(publish), self._p(self.xs), self._p(self.Ps), self._p(self.lag))
+        rc = self._f[3](self._h, self._ptr_of(gathered_bwd), self._ptr_of(gathered_fwd), self.rank, self.world,
+                        int(track_set), int(publish), *self._out)
+        if rc:
+            self._lib.check(rc)
 
     def end(self):
         if self.resid is not None:
@@ -312,7 +336,7 @@ class TorchGather:
         return float(t[1].item())
 
 
-def split_ecm(shards, comm, max_iters, inner_iters, rtol, patience=2):
+def split_ecm(shards, comm, max_iters, inner_iters, rtol, patience=2, graphs=None):
     """cfixedBackgroundECM (cconsenrich.pyx:7660-8442; 2-state, kappa the only multiplier fitted) on ONE
     chromosome held as ``shards`` -- the ``EcmShard`` objects of THIS process, in interval order: one per rank
     under torchrun (``comm = TorchGather()``), all of them in a single-process emulation (``LocalGather()``).
@@ -322,14 +346,24 @@ def split_ecm(shards, comm, max_iters, inner_iters, rtol, patience=2):
     iteration follows -- is that iteration's opening pass run ahead into the spare track set; the stopping rule
     is evaluated on the all-reduced NLL, so every rank takes the same decision.  Per pass the shards exchange one
     payload (forward: filtering aggregate + first interval's kappa / qScale; backward: smoothing aggregate + last
-    interval's filtered Gaussian).  Returns the diagnostics of the reference's dict (pyx:8409-8425)."""
+    interval's filtered Gaussian).  Returns the diagnostics of the reference's dict (pyx:8409-8425).
+
+    ``graphs``: a dict that lives across calls (or None).  A pass is a fixed sequence of launches -- the shard's
+    kernels, the all-gather, the shard's kernels -- with fixed arguments, so with ``graphs`` given every kind of
+    pass is captured ONCE into a CUDA graph (stream capture on the shards' stream, NCCL included) and replayed
+    afterwards: at 8 shards of chr1 @ 10 bp a sweep is 0.12 ms of kernels per GPU, and ~6 Python-issued calls
+    per sweep would otherwise bound it.  The dict must be dropped when the shards (or their sizes) change."""
     torch = shards[0].torch
     world = shards[0].world
     dev = shards[0].data.device
-    new = lambda: torch.zeros((world, PAYLOAD), dtype=torch.float64, device=dev)
-    g_fwd = [[new(), new()] for _ in shards]   # per local shard, per track set: the forward payloads that set was built from
-    g_scr = [new() for _ in shards]            # forward passes that store nothing
-    g_bwd = [new() for _ in shards]
+    cache = getattr(shards[0], "_gather_buffers", None)
+    if cache is None or len(cache[0]) != len(shards):
+        new = lambda: torch.zeros((world, PAYLOAD), dtype=torch.float64, device=dev)
+        cache = ([[new(), new()] for _ in shards], [new() for _ in shards], [new() for _ in shards])
+        shards[0]._gather_buffers = cache
+    # per local shard: the forward payloads each track set was built from; a scratch for forward passes that
+    # store nothing; the backward payloads
+    g_fwd, g_scr, g_bwd = cache
 
     def exchange(payloads, outs):
         if len(shards) == 1:
@@ -339,19 +373,39 @@ def split_ecm(shards, comm, max_iters, inner_iters, rtol, patience=2):
             for o in outs[1:]:
                 o.copy_(outs[0])
 
-    def forward(track_set, with_nll, store):
+    def forward_eager(track_set, with_nll, store):
         pay = [s.forward_compose() for s in shards]
         outs = [g[track_set] for g in g_fwd] if store else g_scr
         exchange(pay, outs)
         for s, g in zip(shards, outs):
             s.forward_replay(g, with_nll, store, track_set)
 
-    def backward(track_set, publish):
+    def backward_eager(track_set, publish):
         if not publish:
             pay = [s.backward_compose(track_set) for s in shards]
             exchange(pay, g_bwd)
         for s, gb, gf in zip(shards, g_bwd, g_fwd):
             s.backward_replay(gb, gf[track_set], track_set, publish)
+
+    def replayed(key, fn, *args):
+        """Run ``fn(*args)``; with ``graphs`` given, through the CUDA graph of that pass (captured on first use)."""
+        if graphs is None:
+            return fn(*args)
+        g = graphs.get(key)
+        if g is None:
+            stream = torch.cuda.current_stream(dev)
+            stream.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=stream):
+                fn(*args)
+            graphs[key] = g
+        g.replay()
+
+    def forward(track_set, with_nll, store):
+        replayed(("fwd", track_set, bool(with_nll), bool(store)), forward_eager, track_set, with_nll, store)
+
+    def backward(track_set, publish):
+        replayed(("bwd", track_set, bool(publish)), backward_eager, track_set, publish)
 
     for s in shards:
         s.begin()

@@ -114,3 +114,47 @@ def test_split_chromosome_ecm_matches_unsharded_oracle(oracle, shards, n, qscale
     assert_tracks_close(cat("resid"), want[5], "split residuals", **ECM_TOL["state"])
     assert_tracks_close(cat("kap"), want[7], "split kappa", **ECM_TOL["mult"])
     assert cat("kap")[0] == 1.0
+
+
+def test_split_chromosome_ecm_replayed_from_cuda_graphs(oracle):
+    """The passes of split_ecm captured once into CUDA graphs (stream capture on the shards' stream) and replayed:
+    the first call captures while it runs, the second only replays -- both must give the unsharded reference."""
+    import torch
+
+    from consenrich_b200 import _lib, sharding
+    from consenrich_b200.device import make_model
+    from parity_util import assert_tracks_close
+    from test_gpu_parity import ECM_TOL, _ecm
+
+    m, n, shards = 4, 120_011, 3
+    data, munc = synth_tracks(4321, m, n, masked_frac=0.02)
+    opts = dict(ECM_fixedBackgroundIters=3, ECM_fixedBackgroundRtol=0.0, t_innerIters=2, ECM_robustTNu=8.0,
+                ECM_useObsPrecisionReweighting=False, procPrecisionMultiplierMin=5e-3, procPrecisionMultiplierMax=5e3)
+    want = _ecm(oracle, 2, data, munc, **opts)
+    dev = torch.device("cuda", 0)
+    side = torch.cuda.Stream(dev)  # capture needs a non-default stream, and the library must launch on the same one
+    with torch.cuda.stream(side):
+        model = make_model(2, F, Q0, 0.0, 1000.0, 1e-4, kap_bounds=(5e-3, 5e3), return_nll=True, use_kappa=True)
+        parts = []
+        for r, (a, b) in enumerate(sharding.split_ranges(n, shards, align=512)):
+            nb = b - a
+            ld = (nb + 31) // 32 * 32
+            d_dev = torch.zeros((m, ld), dtype=torch.float32, device=dev)
+            v_dev = torch.ones((m, ld), dtype=torch.float32, device=dev)
+            d_dev[:, :nb] = torch.from_numpy(data[:, a:b]).to(dev)
+            v_dev[:, :nb] = torch.from_numpy(munc[:, a:b]).to(dev)
+            kap = torch.ones(nb, dtype=torch.float32, device=dev)
+            parts.append(sharding.EcmShard(_lib.Context(0, int(side.cuda_stream)), model, 8.0, d_dev, v_dev, ld, nb, kap,
+                                           None, r, shards))
+        graphs = {}
+        for attempt in ("captured", "replayed"):
+            for p in parts:
+                p.kap.fill_(1.0)
+            diag = sharding.split_ecm(parts, sharding.LocalGather(), max_iters=3, inner_iters=2, rtol=0.0, graphs=graphs)
+            side.synchronize()
+            cat = lambda name: np.concatenate([getattr(p, name).cpu().numpy() for p in parts])
+            assert diag["iters_done"] == want[0] and abs(diag["final_nll"] - want[1]) <= ECM_TOL["nll"] * abs(want[1]), attempt
+            assert_tracks_close(cat("xs"), want[2], f"{attempt} stateSmoothed", **ECM_TOL["state"])
+            assert_tracks_close(cat("Ps"), want[3], f"{attempt} stateCovarSmoothed", scale="component", **ECM_TOL["cov"])
+            assert_tracks_close(cat("kap"), want[7], f"{attempt} kappa", **ECM_TOL["mult"])
+        assert len(graphs) >= 4  # forward (plain, NLL + store, NLL only), backward (kappa, publish)
