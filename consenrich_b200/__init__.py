@@ -10,6 +10,7 @@ Only what the path needs lives here:
 * ``device``     device-resident sweeps on torch tensors (torch is only a tensor carrier)
 * ``sharding``   chromosome / bin-range sharding across ranks (torch.distributed plumbing)
 * ``writers``    bedGraph chunks formatted on the device, byte-identical to the reference's pandas writer
+* ``bigwig``     host-side bigWig container for the finished bedGraph files (what the reference asks pyBigWig for)
 
 There is no CPU implementation: importing works anywhere, calling requires the built library
 and a CUDA device, and fails loudly otherwise.
@@ -23,5 +24,6 @@ from .native import (cEMA, cFinalizeMuncEBTrack, cMuncObservationMomentSeedPass,
 
 from .driver import install_driver, uninstall_driver  # noqa: E402,F401
 from . import writers  # noqa: E402,F401
+from . import bigwig  # noqa: E402,F401
 
 __version__ = "0.1.0"
