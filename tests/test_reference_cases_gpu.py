@@ -27,7 +27,7 @@ pytestmark = pytest.mark.gpu
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "driver")
 SOURCE = os.path.join(DRIVER, "ref_tests", "test_core_source.py")
 
-# name -> needs the monkeypatch fixture
+# name -> False: called without arguments; True: called with a MonkeyPatch; a list of tuples: called once per tuple
 CASES = {
     # collected by test_core_em_loop_contracts (tests/test_core.py:7585-7607)
     "_caseRunConsenrichOuterPassSmoke": False,
@@ -49,6 +49,21 @@ CASES = {
     "_caseFinalForwardNISUsesMeanFinalForwardDiagnostic": False,
     "_caseFinalForwardGainSummaryUsesReplicateContigRows": False,
     "_casePerIntervalOutputDiagnosticsUseEffectiveNoiseAndGainComponents": False,
+}
+
+# the observation-noise stage: the reference's cases of its four compiled functions, alone and under its own
+# `core.getMuncTrack` (core.py:8390), which reaches them by attribute (core.py:8526-8830)
+MUNC_FUNCTIONS = ("cMuncSmoothDenseLocalEvidence", "cFinalizeMuncEBTrack", "cMuncObservationMomentSeedPass", "cEMA")
+MUNC_CASES = {
+    "_caseCEMAUsesSameBidirectionalKernelForFloat32AndFloat64": [(np.float32,), (np.float64,)],
+    "_caseMuncObservationMomentSeedPassUsesOmegaMomentsAndFloors": False,
+    "_caseFinalizeMuncEBTrackPreservesCountFloorSentinel": False,
+    "_caseMuncSmoothDenseLocalEvidenceUsesCenteredWindows": False,
+    "_caseGetMuncTrackAppliesAdditiveCovariatesBeforeEBShrinkage": False,
+    "_caseGetMuncTrackRejectsSparseLocalVariancePaths": False,
+    "_caseGetMuncTrackCapsPriorStrengthAtFiftyTimesLocalDf": True,
+    "_caseGetMuncTrackSmoothsPriorMeanWithEMA": True,
+    "_caseGetMuncTrackAppliesReplicateVarianceFactor": False,
 }
 
 
@@ -100,16 +115,38 @@ def ref_ns():
     sys.path.remove(DRIVER)
 
 
-def _call(ns, name, needs_monkeypatch):
+def _call(ns, name, how):
     fn = ns[name]
-    if needs_monkeypatch:
+    if how is True:
         mp = pytest.MonkeyPatch()
         try:
             fn(mp)
         finally:
             mp.undo()
-    else:
+    elif how is False:
         fn()
+    else:
+        for args in how:
+            fn(*args)
+
+
+def count_calls(module, names):
+    """Wrap ``module``'s attributes ``names`` with counters; returns (counts, undo)."""
+    counts = {k: 0 for k in names}
+    before = {k: getattr(module, k) for k in names}
+
+    def wrap(k, fn):
+        def counted(*args, **kwargs):
+            counts[k] += 1
+            return fn(*args, **kwargs)
+        return counted
+    for k in names:
+        setattr(module, k, wrap(k, before[k]))
+
+    def undo():
+        for k in names:
+            setattr(module, k, before[k])
+    return counts, undo
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -131,4 +168,26 @@ def test_reference_case_passes_on_the_installed_kernels(ref_ns, name):
             assert cb._lib.default_context().launch_count > launches0, "the case did not reach the device"
     finally:
         cb.uninstall_driver(ref_ns["core"])
+        cb.uninstall(ref_ns["cconsenrich"])
+
+
+@pytest.mark.parametrize("name", list(MUNC_CASES))
+def test_reference_munc_case_passes_on_the_installed_kernels(ref_ns, name):
+    import consenrich_b200 as cb
+    if name not in ref_ns:
+        pytest.skip(f"{name} is not defined in this reference checkout")
+    try:
+        _call(ref_ns, name, MUNC_CASES[name])
+    except Exception as e:  # noqa: BLE001
+        pytest.skip(f"{name} fails on the reference build itself ({type(e).__name__}): drifted, not a parity statement")
+    mod = cb.install(ref_ns["cconsenrich"], munc=True)
+    try:
+        assert mod.cEMA is cb.cEMA and mod.cFinalizeMuncEBTrack is cb.cFinalizeMuncEBTrack
+        counts, undo = count_calls(mod, MUNC_FUNCTIONS)
+        try:
+            _call(ref_ns, name, MUNC_CASES[name])
+        finally:
+            undo()
+        assert sum(counts.values()) > 0, "the case did not reach the installed functions"
+    finally:
         cb.uninstall(ref_ns["cconsenrich"])
