@@ -29,7 +29,8 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["write_bigwig", "convert_bedgraph_to_bigwig", "convert_outputs", "read_bigwig", "bigwig_path", "read_chrom_sizes"]
+__all__ = ["write_bigwig", "convert_bedgraph_to_bigwig", "convert_outputs", "read_bigwig", "bigwig_path", "read_chrom_sizes",
+           "values_as_printed", "fixed_step_track"]
 
 BIGWIG_MAGIC = 0x888FFC26
 BPT_MAGIC = 0x78CA8C91
@@ -330,6 +331,27 @@ def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
     finally:
         if os.path.exists(tmp):
             os.remove(tmp)
+
+
+def values_as_printed(values) -> np.ndarray:
+    """The float32 a bigWig holds for a value that went through the bedGraph text: ``"%.4f" % v`` parsed back
+    (io.py:728) and narrowed by pyBigWig.  For a float32 v the product v * 10^4 is exact in double, so its
+    half-even ``rint`` is printf's correctly rounded digit string and the quotient by 10^4 the double that string
+    parses to -- the track can skip the text without changing a bit of the file."""
+    v = np.asarray(values, dtype=np.float32).astype(np.float64)
+    return (np.rint(v * 1.0e4) / 1.0e4).astype(np.float32)
+
+
+def fixed_step_track(chromosome: str, values, *, start0: int = 0, step: int, chrom_size: Optional[int] = None):
+    """(chromosome, starts, ends, values) of a fixed-step track for ``write_bigwig``: interval i is
+    [start0 + i step, start0 + (i + 1) step), the last one cut at the chromosome end the way the bedGraph rows
+    are; values as the bedGraph would have printed them."""
+    v = values_as_printed(np.asarray(values).reshape(-1))
+    starts = int(start0) + np.arange(len(v), dtype=np.int64) * int(step)
+    ends = starts + int(step)
+    if chrom_size is not None:
+        ends = np.minimum(ends, int(chrom_size))
+    return chromosome, starts, ends, v
 
 
 def convert_bedgraph_to_bigwig(bedgraph_path: str, chrom_sizes, bigwig_path_: str, *, zoom_levels: int = MAX_ZOOM_LEVELS) -> None:

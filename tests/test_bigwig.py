@@ -240,3 +240,22 @@ def test_convert_outputs_loop(tmp_path):
     np.testing.assert_array_equal(bigwig.read_bigwig(written[0])["tracks"]["chr2"][2], np.array([2.0], np.float32))
     with pytest.warns(UserWarning, match="does not exist"):
         assert bigwig.convert_outputs("exp", str(tmp_path / "nope.sizes"), ["uncertainty"], version="1.2.3", directory=d) == []
+
+
+def test_values_as_printed_equal_the_text_round_trip(tmp_path):
+    rng = np.random.default_rng(7)
+    v = np.concatenate([rng.normal(size=20000) * 10.0 ** rng.integers(-6, 5, size=20000),
+                        (rng.integers(-10 ** 6, 10 ** 6, size=5000) * 2 + 1) / 2.0e4,  # decimal ties of the 4th digit
+                        [0.0, -0.0, 1e-5, -4.99999e-5, 5e-5, 16777216.0, 123456.789]]).astype(np.float32)
+    want = np.array([np.float32(float("%.4f" % x)) for x in v.tolist()], dtype=np.float32)
+    np.testing.assert_array_equal(bigwig.values_as_printed(v), want)
+    # and so the two ways into a bigWig give the same intervals and values
+    vals = v[:3000]
+    chrom, s, e, q = bigwig.fixed_step_track("chr1", vals, start0=100, step=25, chrom_size=75_090)
+    assert e[-1] == 75_090 and s[0] == 100 and e[-2] - s[-2] == 25
+    direct = str(tmp_path / "direct.bw")
+    bigwig.write_bigwig(direct, SIZES, [(chrom, s, e, q)])
+    text = "".join(f"chr1\t{a}\t{b}\t{x:.4f}\n" for a, b, x in zip(s.tolist(), e.tolist(), vals.tolist()))
+    via_text = str(tmp_path / "text.bw")
+    bigwig.convert_bedgraph_to_bigwig(_bedgraph(tmp_path, text), SIZES, via_text)
+    assert open(direct, "rb").read() == open(via_text, "rb").read()
