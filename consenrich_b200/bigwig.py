@@ -145,15 +145,18 @@ def _rtree_bytes(items: np.ndarray, file_offset: int, items_per_slot: int) -> by
 _ITEM_DT = np.dtype([("chrom", "<u4"), ("start", "<u4"), ("end_chrom", "<u4"), ("end", "<u4"), ("offset", "<u8"), ("size", "<u8")])
 
 
+_ZOOM_WORK_DT = np.dtype([("chrom", "<u4"), ("start", "<u4"), ("end", "<u4"), ("valid", "<u4"), ("min", "<f4"), ("max", "<f4"),
+                          ("sum", "<f8"), ("sumsq", "<f8")])  # sums in float64 until the records are written
+
+
 def _zoom_records(chrom_id: int, starts: np.ndarray, ends: np.ndarray, values: np.ndarray, reduction: int):
-    """Summary records of one chromosome at one zoom level: windows of ``reduction`` bases (aligned to
+    """Summary records of one chromosome at the first zoom level: windows of ``reduction`` bases (aligned to
     multiples of it), each with the bases covered, min, max, sum and sum of squares of the data in it."""
     if len(starts) == 0:
-        return np.zeros(0, dtype=_ZOOM_DT)
+        return np.zeros(0, dtype=_ZOOM_WORK_DT)
     v = values.astype(np.float64)
     first_w, last_w = starts // reduction, (ends - 1) // reduction
     span = int(np.max(last_w - first_w)) + 1
-    recs: Dict[int, list] = {}
     # an interval contributes to every window it overlaps, weighted by the overlap (intervals are short
     # against any zoom window, so `span` is 1 or 2 in practice)
     parts_w, parts_cov, parts_v = [], [], []
@@ -170,10 +173,12 @@ def _zoom_records(chrom_id: int, starts: np.ndarray, ends: np.ndarray, values: n
     w = np.concatenate(parts_w)
     cov = np.concatenate(parts_cov).astype(np.float64)
     vv = np.concatenate(parts_v)
-    order = np.argsort(w, kind="stable")
-    w, cov, vv = w[order], cov[order], vv[order]
-    uniq, idx = np.unique(w, return_index=True)
-    out = np.zeros(len(uniq), dtype=_ZOOM_DT)
+    if span > 1:
+        order = np.argsort(w, kind="stable")
+        w, cov, vv = w[order], cov[order], vv[order]
+    idx = np.flatnonzero(np.concatenate(([True], w[1:] != w[:-1])))
+    uniq = w[idx]
+    out = np.zeros(len(uniq), dtype=_ZOOM_WORK_DT)
     out["chrom"] = chrom_id
     out["start"] = uniq * reduction
     out["end"] = (uniq + 1) * reduction
@@ -185,8 +190,37 @@ def _zoom_records(chrom_id: int, starts: np.ndarray, ends: np.ndarray, values: n
     return out
 
 
+def _zoom_coarsen(recs: np.ndarray, reduction: int) -> np.ndarray:
+    """The next zoom level from the records of the one below: windows nest (reductions grow by whole factors and
+    are aligned to multiples of themselves), so a coarse window is the merge of the fine ones inside it."""
+    if len(recs) == 0:
+        return recs
+    key = recs["chrom"].astype(np.int64) * (1 << 32) + recs["start"] // reduction
+    idx = np.flatnonzero(np.concatenate(([True], key[1:] != key[:-1])))
+    out = np.zeros(len(idx), dtype=_ZOOM_WORK_DT)
+    out["chrom"] = recs["chrom"][idx]
+    out["start"] = (recs["start"][idx] // reduction) * reduction
+    out["end"] = out["start"] + reduction
+    out["valid"] = np.add.reduceat(recs["valid"].astype(np.int64), idx).astype(np.uint32)
+    out["min"] = np.minimum.reduceat(recs["min"], idx)
+    out["max"] = np.maximum.reduceat(recs["max"], idx)
+    out["sum"] = np.add.reduceat(recs["sum"], idx)
+    out["sumsq"] = np.add.reduceat(recs["sumsq"], idx)
+    return out
+
+
 _ZOOM_DT = np.dtype([("chrom", "<u4"), ("start", "<u4"), ("end", "<u4"), ("valid", "<u4"), ("min", "<f4"), ("max", "<f4"),
                      ("sum", "<f4"), ("sumsq", "<f4")])
+
+
+def _deflate_all(blocks: List[bytes]) -> List[bytes]:
+    """zlib-compress every block; the calls release the GIL, so a few threads share them."""
+    if len(blocks) < 64:
+        return [zlib.compress(b) for b in blocks]
+    from concurrent.futures import ThreadPoolExecutor
+    workers = max(1, min(8, (os.cpu_count() or 1)))
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(zlib.compress, blocks, chunksize=64))
 
 
 def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
@@ -235,14 +269,19 @@ def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
         vmin, vmax = min(vmin, float(v.min())), max(vmax, float(v.max()))
         vsum += float((v64 * width).sum())
         vsumsq += float((v64 * v64 * width).sum())
+        # whole chromosome packed at once: [start, end, value] triples, cut into sections of ITEMS_PER_SLOT
+        rec = np.zeros(len(s), dtype=[("s", "<u4"), ("e", "<u4"), ("v", "<f4")])
+        rec["s"], rec["e"], rec["v"] = s, e, v
+        body = rec.tobytes()
+        raws = []
         for a in range(0, len(s), ITEMS_PER_SLOT):
             b = min(a + ITEMS_PER_SLOT, len(s))
-            rec = np.zeros(b - a, dtype=[("s", "<u4"), ("e", "<u4"), ("v", "<f4")])
-            rec["s"], rec["e"], rec["v"] = s[a:b], e[a:b], v[a:b]
-            raw = struct.pack("<IIIIIBBH", rank, int(s[a]), int(e[b - 1]), 0, 0, 1, 0, b - a) + rec.tobytes()
-            max_raw = max(max_raw, len(raw))
-            sections.append(zlib.compress(raw) if compress else raw)
-            sec_items.append((rank, int(s[a]), int(e[b - 1]), len(sections[-1])))
+            raws.append(struct.pack("<IIIIIBBH", rank, int(s[a]), int(e[b - 1]), 0, 0, 1, 0, b - a) + body[12 * a:12 * b])
+            sec_items.append([rank, int(s[a]), int(e[b - 1]), 0])
+        max_raw = max(max_raw, max(len(r) for r in raws))
+        sections.extend(_deflate_all(raws) if compress else raws)
+    for item, sec in zip(sec_items, sections):
+        item[3] = len(sec)
     if not sections:
         raise ValueError("No intervals to write")
 
@@ -252,15 +291,22 @@ def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
     reduction = mean_width * 10
     n_items = sum(len(x[1]) for x in per_chrom)
     prev = n_items
+    work = None
     for _ in range(max(0, int(zoom_levels))):
         if reduction > 0xFFFFFFFF // 4:
             break
-        recs = np.concatenate([_zoom_records(rank, s, e, v, reduction) for rank, s, e, v in per_chrom])
-        if len(recs) >= prev or len(recs) == 0:
+        if work is None:
+            work = np.concatenate([_zoom_records(rank, s, e, v, reduction) for rank, s, e, v in per_chrom])
+        else:
+            work = _zoom_coarsen(work, reduction)
+        if len(work) >= prev or len(work) == 0:
             break
+        recs = np.zeros(len(work), dtype=_ZOOM_DT)
+        for field in _ZOOM_DT.names:
+            recs[field] = work[field]
         zooms.append((reduction, recs))
-        prev = len(recs)
-        if len(recs) <= 1:
+        prev = len(work)
+        if len(work) <= 1:
             break
         reduction *= 4
     for _red, recs in zooms:
@@ -293,10 +339,11 @@ def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
         blob = bytearray(struct.pack("<I", len(recs)))
         pos += 4
         zitems = []
-        for a in range(0, len(recs), ZOOM_RECORDS_PER_SLOT):
-            sl = recs[a:a + ZOOM_RECORDS_PER_SLOT]
-            raw = sl.tobytes()
-            comp = zlib.compress(raw) if compress else raw
+        slots = [recs[a:a + ZOOM_RECORDS_PER_SLOT] for a in range(0, len(recs), ZOOM_RECORDS_PER_SLOT)]
+        comps = [sl.tobytes() for sl in slots]
+        if compress:
+            comps = _deflate_all(comps)
+        for sl, comp in zip(slots, comps):
             # a slot may span chromosomes: its bounding box runs from its first to its last record
             zitems.append((int(sl[0]["chrom"]), int(sl[0]["start"]), int(sl[-1]["chrom"]), int(sl[-1]["end"]), pos, len(comp)))
             blob += comp
