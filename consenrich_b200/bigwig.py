@@ -30,7 +30,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 import numpy as np
 
 __all__ = ["write_bigwig", "convert_bedgraph_to_bigwig", "convert_outputs", "read_bigwig", "bigwig_path", "read_chrom_sizes",
-           "values_as_printed", "fixed_step_track"]
+           "values_as_printed", "fixed_step_track", "sort_bedgraph_in_place"]
 
 BIGWIG_MAGIC = 0x888FFC26
 BPT_MAGIC = 0x78CA8C91
@@ -418,8 +418,7 @@ def convert_bedgraph_to_bigwig(bedgraph_path: str, chrom_sizes, bigwig_path_: st
     with open(bedgraph_path, "r", encoding="utf-8") as handle:
         for line_number, line in enumerate(handle, start=1):
             stripped = line.strip()
-            if (not stripped or stripped.startswith("#") or stripped == "track" or stripped.startswith("track ")
-                    or stripped == "browser" or stripped.startswith("browser ")):
+            if _is_header_line(stripped):
                 continue
             parts = stripped.split()
             if len(parts) != 4:
@@ -463,16 +462,66 @@ def convert_bedgraph_to_bigwig(bedgraph_path: str, chrom_sizes, bigwig_path_: st
                  zoom_levels=zoom_levels)
 
 
+def _is_header_line(stripped: str) -> bool:
+    return (not stripped or stripped.startswith("#") or stripped == "track" or stripped.startswith("track ")
+            or stripped == "browser" or stripped.startswith("browser "))
+
+
+def sort_bedgraph_in_place(bedgraph_path: str, chrom_order: Sequence[str]) -> None:
+    """``_sortBedGraphInPlace`` with a chromosome order (io.py:879-990): header lines first, rows by chromosome
+    rank, start, end (stable), values re-printed as ``%.4f``.  The repair the reference applies to a bedGraph
+    that fails its sortedness check before conversion (io.py:562-579)."""
+    if not os.path.exists(bedgraph_path) or os.path.getsize(bedgraph_path) == 0:
+        return
+    headers: List[str] = []
+    chroms: List[str] = []
+    cols: List[Tuple[int, int, float]] = []
+    with open(bedgraph_path, "r", encoding="utf-8") as handle:
+        for line_number, line in enumerate(handle, start=1):
+            stripped = line.strip()
+            if _is_header_line(stripped):
+                headers.append(line.rstrip("\n"))
+                continue
+            parts = stripped.split()
+            if len(parts) != 4:
+                raise ValueError(f"Malformed bedGraph row {line_number} in {bedgraph_path}: expected 4 columns")
+            chroms.append(parts[0])
+            cols.append((int(parts[1]), int(parts[2]), float(parts[3])))
+    rank_of = {str(c): r for r, c in enumerate(chrom_order)}
+    unknown = sorted({c for c in chroms if c not in rank_of})
+    if unknown:
+        raise ValueError("bedGraph contains chromosomes not present in chromosome order: " + ", ".join(unknown[:5]))
+    out_dir = os.path.dirname(os.path.abspath(bedgraph_path)) or "."
+    fd, tmp = tempfile.mkstemp(prefix="consenrich_sort_", suffix=".bedGraph", dir=out_dir)
+    try:
+        with os.fdopen(fd, "w", encoding="utf-8") as out:
+            for h in headers:
+                out.write(f"{h}\n")
+            if cols:
+                arr = np.array(cols, dtype=np.float64)
+                ranks = np.array([rank_of[c] for c in chroms], dtype=np.int64)
+                starts, ends = arr[:, 0].astype(np.int64), arr[:, 1].astype(np.int64)
+                order = np.lexsort((ends, starts, ranks))  # stable: ties keep the file's order, as mergesort does
+                for i in order.tolist():
+                    out.write("%s\t%d\t%d\t%.4f\n" % (chroms[i], starts[i], ends[i], arr[i, 2]))
+        os.replace(tmp, bedgraph_path)
+    finally:
+        if os.path.exists(tmp):
+            os.remove(tmp)
+
+
 def convert_outputs(experiment_name: str, chrom_sizes_file: str, suffixes: Optional[Sequence[str]] = None, *, version: str,
-                    delete_bedgraphs: bool = False, directory: str = ".") -> List[str]:
+                    delete_bedgraphs: bool = False, directory: str = ".", validated: Sequence[str] = ()) -> List[str]:
     """The loop of ``convertBedGraphToBigWig`` (io.py:530-600) over a run's finished bedGraph files
     (``consenrichOutput_{experiment}_{suffix}.v{version}.bedGraph``): a missing bedGraph is skipped with a
-    warning, a missing chromosome-sizes file ends the conversion, a track that fails validation is reported
-    and skipped (the reference first tries to sort such a file in place; the device writer emits sorted,
-    non-overlapping chunks, so here it is an error to report, not to repair).  Returns the bigWig files written."""
+    warning, a missing chromosome-sizes file ends the conversion, a bedGraph not listed in ``validated`` that
+    fails the conversion's order / overlap checks is sorted in place first (the reference's fallback,
+    io.py:562-579) and converted then; a track that still fails is reported and skipped.  Returns the bigWig
+    files written."""
     import warnings
     written: List[str] = []
     sizes = None
+    validated_paths = {os.path.abspath(str(p)) for p in validated}
     for suffix in (["state"] if suffixes is None else list(suffixes)):
         bedgraph = os.path.join(directory, f"consenrichOutput_{experiment_name}_{suffix}.v{version}.bedGraph")
         if not os.path.exists(bedgraph):
@@ -485,7 +534,15 @@ def convert_outputs(experiment_name: str, chrom_sizes_file: str, suffixes: Optio
             sizes = read_chrom_sizes(chrom_sizes_file)
         out = os.path.join(directory, bigwig_path(experiment_name, suffix, version))
         try:
-            convert_bedgraph_to_bigwig(bedgraph, sizes, out)
+            try:
+                convert_bedgraph_to_bigwig(bedgraph, sizes, out)
+            except ValueError as first:
+                if os.path.abspath(bedgraph) in validated_paths or "not sorted" not in str(first):
+                    raise
+                warnings.warn(f"bedGraph {bedgraph} failed sorted validation before bigWig conversion; sorting as a "
+                              f"fallback:\n{first}")
+                sort_bedgraph_in_place(bedgraph, [c for c, _s in sizes])
+                convert_bedgraph_to_bigwig(bedgraph, sizes, out)
         except Exception as e:  # the reference logs and moves on to the next track (io.py:589-593)
             warnings.warn(f"bedGraph-->bigWig conversion for {bedgraph} raised:\n{e}\n")
             continue
@@ -530,7 +587,8 @@ def _read_rtree(buf: bytes, offset: int):
 
 def read_bigwig(path: str) -> dict:
     """Parse a bigWig file: chromosomes, total summary, every interval (through the R-index), zoom levels."""
-    buf = open(path, "rb").read()
+    with open(path, "rb") as handle:
+        buf = handle.read()
     (magic, version, n_zoom, chrom_off, data_off, index_off, field_count, defined, autosql, summary_off, uncompress,
      _ext) = struct.unpack_from("<IHHQQQHHQQIQ", buf, 0)
     if magic != BIGWIG_MAGIC:

@@ -228,18 +228,42 @@ def test_convert_outputs_loop(tmp_path):
     sizes.write_text("chr1 1000\nchr2 500\n")
     d = str(tmp_path)
     (tmp_path / "consenrichOutput_exp_state.v1.2.3.bedGraph").write_text("chr1\t0\t25\t1.0000\nchr2\t0\t25\t2.0000\n")
-    (tmp_path / "consenrichOutput_exp_uncertainty.v1.2.3.bedGraph").write_text("chr2\t0\t25\t1\nchr1\t0\t25\t1\n")  # unsorted
+    unsorted = tmp_path / "consenrichOutput_exp_uncertainty.v1.2.3.bedGraph"
+    unsorted.write_text("track type=bedGraph\nchr2\t0\t25\t1\nchr1\t50\t75\t0.12345\nchr1\t0\t25\t-3\n")
+    (tmp_path / "consenrichOutput_exp_bad.v1.2.3.bedGraph").write_text("chr1\t0\t50\t1\nchr1\t25\t75\t1\n")  # overlap
     with pytest.warns(UserWarning) as rec:
-        written = bigwig.convert_outputs("exp", str(sizes), ["state", "uncertainty", "missing"], version="1.2.3",
+        written = bigwig.convert_outputs("exp", str(sizes), ["state", "uncertainty", "bad", "missing"], version="1.2.3",
                                          delete_bedgraphs=True, directory=d)
     messages = " | ".join(str(w.message) for w in rec)
-    assert "not sorted at row 2" in messages and "missing.v1.2.3.bedGraph does not exist" in messages
-    assert written == [os.path.join(d, "exp_consenrich_state.v1.2.3.bw")]
-    assert not os.path.exists(tmp_path / "consenrichOutput_exp_state.v1.2.3.bedGraph")      # converted and deleted
-    assert os.path.exists(tmp_path / "consenrichOutput_exp_uncertainty.v1.2.3.bedGraph")    # failed: kept
+    assert "sorting as a fallback" in messages and "not sorted at row 3" in messages
+    assert "Overlapping bedGraph interval at row 2" in messages and "missing.v1.2.3.bedGraph does not exist" in messages
+    assert written == [os.path.join(d, "exp_consenrich_state.v1.2.3.bw"), os.path.join(d, "exp_consenrich_uncertainty.v1.2.3.bw")]
+    assert not os.path.exists(tmp_path / "consenrichOutput_exp_state.v1.2.3.bedGraph")   # converted and deleted
+    assert os.path.exists(tmp_path / "consenrichOutput_exp_bad.v1.2.3.bedGraph")          # failed: kept
     np.testing.assert_array_equal(bigwig.read_bigwig(written[0])["tracks"]["chr2"][2], np.array([2.0], np.float32))
+    got = bigwig.read_bigwig(written[1])["tracks"]  # the unsorted file was repaired the way the reference repairs it
+    np.testing.assert_array_equal(got["chr1"][0], [0, 50])
+    np.testing.assert_array_equal(got["chr1"][2], np.array([-3.0, 0.1235], np.float32))  # values re-printed as %.4f
     with pytest.warns(UserWarning, match="does not exist"):
-        assert bigwig.convert_outputs("exp", str(tmp_path / "nope.sizes"), ["uncertainty"], version="1.2.3", directory=d) == []
+        assert bigwig.convert_outputs("exp", str(tmp_path / "nope.sizes"), ["bad"], version="1.2.3", directory=d) == []
+
+
+def test_sort_bedgraph_in_place(tmp_path):
+    p = _bedgraph(tmp_path, "# c\nchr2\t10\t20\t1\nchr1\t30\t40\t2.00006\nchr1\t30\t35\t-0.00004\ntrack x\nchr1\t0\t5\t1e2\n")
+    bigwig.sort_bedgraph_in_place(p, ["chr1", "chr2"])
+    assert open(p).read() == ("# c\ntrack x\nchr1\t0\t5\t100.0000\nchr1\t30\t35\t-0.0000\nchr1\t30\t40\t2.0001\n"
+                              "chr2\t10\t20\t1.0000\n")
+    with pytest.raises(ValueError, match="not present in chromosome order: chr2"):
+        bigwig.sort_bedgraph_in_place(p, ["chr1"])
+    assert [f for f in os.listdir(tmp_path) if f.startswith("consenrich_sort_")] == []
+    # a validated file is never rewritten: the failure is reported instead
+    q = tmp_path / "consenrichOutput_e_state.v1.bedGraph"
+    q.write_text("chr2\t0\t25\t1\nchr1\t0\t25\t1\n")
+    before = q.read_text()
+    (tmp_path / "s.sizes").write_text("chr1 100\nchr2 100\n")
+    with pytest.warns(UserWarning, match="not sorted at row 2"):
+        assert bigwig.convert_outputs("e", str(tmp_path / "s.sizes"), version="1", directory=str(tmp_path), validated=[str(q)]) == []
+    assert q.read_text() == before
 
 
 def test_values_as_printed_equal_the_text_round_trip(tmp_path):
