@@ -11,7 +11,7 @@ validation with the reference's messages, and the published BBI / bigWig contain
 
     header (64 B) | zoom headers | total summary (40 B) | chromosome B+ tree | data count |
     zlib-compressed sections of <= 1024 bedGraph items (24 B section header + 12 B per item) |
-    cirTree R-index over the sections | zoom levels (summary records + their own R-index)
+    cirTree R-index over the sections | zoom levels (summary records + their own R-index) | end signature
 
 (Kent et al., "BigWig and BigBed: enabling browsing of large distributed datasets", Bioinformatics 2010, and
 the UCSC bbiFile.h / bwgInternal.h layouts).  It is host-side byte packing (numpy + zlib), not device work.
@@ -374,6 +374,7 @@ def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
                 f.write(blob)
                 f.write(zindex)
             assert f.tell() == pos, (f.tell(), pos)
+            f.write(struct.pack("<I", BIGWIG_MAGIC))  # the end signature UCSC's and libBigWig's writers leave
         os.replace(tmp, path)
     finally:
         if os.path.exists(tmp):
@@ -593,6 +594,7 @@ def read_bigwig(path: str) -> dict:
      _ext) = struct.unpack_from("<IHHQQQHHQQIQ", buf, 0)
     if magic != BIGWIG_MAGIC:
         raise ValueError("not a bigWig file")
+    end_signature = struct.unpack_from("<I", buf, len(buf) - 4)[0] == BIGWIG_MAGIC
     inflate = (lambda b: zlib.decompress(b)) if uncompress else (lambda b: b)
     zoom_headers = [struct.unpack_from("<IIQQ", buf, 64 + 24 * i) for i in range(n_zoom)]
     covered, vmin, vmax, vsum, vsumsq = struct.unpack_from("<Qdddd", buf, summary_off)
@@ -644,4 +646,4 @@ def read_bigwig(path: str) -> dict:
     return {"version": version, "chroms": [chroms[i] for i in sorted(chroms)], "sections": int(n_sections),
             "summary": {"bases_covered": covered, "min": vmin, "max": vmax, "sum": vsum, "sum_squares": vsumsq},
             "tracks": tracks, "index": index, "zooms": zooms, "uncompress_buf_size": uncompress,
-            "field_count": field_count, "defined_field_count": defined, "autosql_offset": autosql}
+            "end_signature": end_signature, "field_count": field_count, "defined_field_count": defined, "autosql_offset": autosql}

@@ -41,7 +41,7 @@ def test_round_trip_and_header(tmp_path):
     magic, version, n_zoom = struct.unpack_from("<IHH", raw, 0)
     assert magic == 0x888FFC26 and version == 4 and 1 <= n_zoom <= 10
     got = bigwig.read_bigwig(path)
-    assert got["chroms"] == SIZES
+    assert got["chroms"] == SIZES and got["end_signature"]
     assert (got["field_count"], got["defined_field_count"], got["autosql_offset"]) == (0, 0, 0)
     n_items = 0
     for c, s, e, v in tracks:
