@@ -213,6 +213,44 @@ _ZOOM_DT = np.dtype([("chrom", "<u4"), ("start", "<u4"), ("end", "<u4"), ("valid
                      ("sum", "<f4"), ("sumsq", "<f4")])
 
 
+BPT_BLOCK = 256  # children per node of the chromosome B+ tree
+
+
+def _chrom_tree_bytes(chrom_sizes, ids, key_size: int, file_offset: int) -> bytes:
+    """Chromosome B+ tree (name -> id, size), written at ``file_offset``: header (32 B), then the levels from the
+    root down; keys in byte order, an inner item is the first key of its child and the child's file offset."""
+    items = sorted(((c.encode().ljust(key_size, b"\0"), ids[c], size) for c, size in chrom_sizes), key=lambda t: t[0])
+    n = len(items)
+    block = min(BPT_BLOCK, max(n, 1))
+    counts = [n]  # items per level, leaves first
+    while counts[-1] > block:
+        counts.append((counts[-1] + block - 1) // block)
+    item_bytes = key_size + 8
+
+    def level_size(count):
+        return ((count + block - 1) // block) * 4 + count * item_bytes
+    offsets = {}
+    pos = file_offset + 32
+    for lv in range(len(counts) - 1, -1, -1):
+        offsets[lv] = pos
+        pos += level_size(counts[lv])
+    out = bytearray(struct.pack("<IIIIQQ", BPT_MAGIC, block, key_size, 8, n, 0))
+    for lv in range(len(counts) - 1, -1, -1):
+        stride = block ** lv  # leaf items under one item of this level
+        for j in range((counts[lv] + block - 1) // block):
+            lo, hi = j * block, min((j + 1) * block, counts[lv])
+            out += struct.pack("<BBH", 1 if lv == 0 else 0, 0, hi - lo)
+            for g in range(lo, hi):
+                if lv == 0:
+                    key, cid, size = items[g]
+                    out += key + struct.pack("<II", cid, size)
+                else:
+                    child = offsets[lv - 1] + g * (4 + block * item_bytes)  # node g of the level below (all full before it)
+                    out += items[g * stride][0] + struct.pack("<Q", child)
+    assert len(out) == pos - file_offset
+    return bytes(out)
+
+
 def _deflate_all(blocks: List[bytes]) -> List[bytes]:
     """zlib-compress every block; the calls release the GIL, so a few threads share them."""
     if len(blocks) < 64:
@@ -319,10 +357,7 @@ def write_bigwig(path: str, chrom_sizes: Sequence[Tuple[str, int]],
     total_summary_offset = pos
     pos += 40
     chrom_tree_offset = pos
-    chrom_tree = bytearray(struct.pack("<IIIIQQ", BPT_MAGIC, n_chrom, key_size, 8, n_chrom, 0))
-    chrom_tree += struct.pack("<BBH", 1, 0, n_chrom)  # one leaf holds every chromosome (block size = their number)
-    for c, size in sorted(chrom_sizes, key=lambda cs: cs[0].encode()):  # keys in byte order, as a B+ tree leaf requires
-        chrom_tree += c.encode().ljust(key_size, b"\0") + struct.pack("<II", ids[c], size)
+    chrom_tree = _chrom_tree_bytes(chrom_sizes, ids, key_size, chrom_tree_offset)
     pos += len(chrom_tree)
     full_data_offset = pos
     pos += 8  # section count

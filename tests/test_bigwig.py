@@ -283,3 +283,44 @@ def test_values_as_printed_equal_the_text_round_trip(tmp_path):
     via_text = str(tmp_path / "text.bw")
     bigwig.convert_bedgraph_to_bigwig(_bedgraph(tmp_path, text), SIZES, via_text)
     assert open(direct, "rb").read() == open(via_text, "rb").read()
+
+
+def test_chromosome_tree_with_many_contigs(tmp_path):
+    # 70 000 contigs: more than one node's 16-bit count could hold, three levels of 256-way nodes
+    rng = np.random.default_rng(11)
+    names = [f"ctg{i:06d}_{rng.integers(1 << 30):x}" for i in range(70_000)]
+    order = rng.permutation(len(names))
+    sizes = [(names[i], 1000 + int(i)) for i in order]
+    pick = [sizes[0], sizes[12345], sizes[-1]]
+    tracks = [(c, np.array([0]), np.array([s]), np.array([float(s)], np.float32)) for c, s in pick]
+    path = _write(tmp_path, tracks, sizes=sizes, zoom_levels=0)
+    raw = open(path, "rb").read()
+    chrom_off = struct.unpack_from("<Q", raw, 8)[0]
+    magic, block, key_size, val_size, count, _ = struct.unpack_from("<IIIIQQ", raw, chrom_off)
+    assert (magic, block, val_size, count) == (0x78CA8C91, 256, 8, 70_000)
+    assert raw[chrom_off + 32] == 0  # the root is an inner node
+
+    def lookup(name):  # the search a reader does: last key <= name on every inner level
+        key = name.encode().ljust(key_size, b"\0")
+        pos = chrom_off + 32
+        while True:
+            is_leaf, _r, n = struct.unpack_from("<BBH", raw, pos)
+            pos += 4
+            entries = [(raw[pos + i * (key_size + 8):pos + i * (key_size + 8) + key_size],
+                        raw[pos + i * (key_size + 8) + key_size:pos + (i + 1) * (key_size + 8)]) for i in range(n)]
+            assert [k for k, _ in entries] == sorted(k for k, _ in entries)
+            if is_leaf:
+                hit = [v for k, v in entries if k == key]
+                return struct.unpack("<II", hit[0]) if hit else None
+            below = [v for k, v in entries if k <= key]
+            if not below:
+                return None
+            pos = struct.unpack("<Q", below[-1])[0]
+    for probe in (0, 1, 255, 256, 65_535, 65_536, 69_999):
+        name, size = sizes[probe]
+        assert lookup(name) == (probe, size)
+    assert lookup("zzz") is None and lookup("a") is None
+    got = bigwig.read_bigwig(path)
+    assert got["chroms"] == sizes
+    for c, s in pick:
+        np.testing.assert_array_equal(got["tracks"][c][1], [s])
