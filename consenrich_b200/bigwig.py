@@ -29,7 +29,7 @@ from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-__all__ = ["write_bigwig", "convert_bedgraph_to_bigwig", "convert_outputs", "read_bigwig", "bigwig_path", "read_chrom_sizes",
+__all__ = ["write_bigwig", "convert_bedgraph_to_bigwig", "convert_outputs", "read_bigwig", "query_bigwig", "bigwig_path", "read_chrom_sizes",
            "values_as_printed", "fixed_step_track", "sort_bedgraph_in_place"]
 
 BIGWIG_MAGIC = 0x888FFC26
@@ -682,3 +682,67 @@ def read_bigwig(path: str) -> dict:
             "summary": {"bases_covered": covered, "min": vmin, "max": vmax, "sum": vsum, "sum_squares": vsumsq},
             "tracks": tracks, "index": index, "zooms": zooms, "uncompress_buf_size": uncompress,
             "end_signature": end_signature, "field_count": field_count, "defined_field_count": defined, "autosql_offset": autosql}
+
+
+def query_bigwig(path: str, chromosome: str, start: int, end: int):
+    """Intervals of ``chromosome`` overlapping [start, end), found the way a genome browser finds them: chromosome
+    id through the B+ tree, then a descent of the R-index that follows only the children whose bounding box
+    overlaps the query, then the matching sections.  Returns (starts, ends, values)."""
+    with open(path, "rb") as handle:
+        buf = handle.read()
+    (magic, _version, _n_zoom, chrom_off, _data_off, index_off, _fc, _dfc, _as, _summ, uncompress,
+     _ext) = struct.unpack_from("<IHHQQQHHQQIQ", buf, 0)
+    if magic != BIGWIG_MAGIC:
+        raise ValueError("not a bigWig file")
+    _bm, _block, key_size, _vs, _count, _res = struct.unpack_from("<IIIIQQ", buf, chrom_off)
+    key = chromosome.encode().ljust(key_size, b"\0")
+    pos, cid = chrom_off + 32, None
+    while cid is None:
+        is_leaf, _r, n = struct.unpack_from("<BBH", buf, pos)
+        pos += 4
+        nxt = None
+        for i in range(n):
+            k = buf[pos:pos + key_size]
+            if is_leaf:
+                if k == key:
+                    cid = struct.unpack_from("<I", buf, pos + key_size)[0]
+                    break
+            elif k <= key:
+                nxt = struct.unpack_from("<Q", buf, pos + key_size)[0]
+            pos += key_size + 8
+        if cid is None:
+            if is_leaf or nxt is None:
+                raise KeyError(chromosome)
+            pos = nxt
+    lo, hi = (cid, int(start)), (cid, int(end))
+    blocks = []
+
+    def descend(pos):
+        is_leaf, _r, n = struct.unpack_from("<BBH", buf, pos)
+        pos += 4
+        for _ in range(n):
+            a, b, c_, d = struct.unpack_from("<IIII", buf, pos)
+            overlaps = (a, b) < hi and (c_, d) > lo
+            if is_leaf:
+                if overlaps:
+                    blocks.append(struct.unpack_from("<QQ", buf, pos + 16))
+                pos += 32
+            else:
+                if overlaps:
+                    descend(struct.unpack_from("<Q", buf, pos + 16)[0])
+                pos += 24
+    descend(index_off + 48)
+    out_s, out_e, out_v = [], [], []
+    for off, size in blocks:
+        raw = zlib.decompress(buf[off:off + size]) if uncompress else buf[off:off + size]
+        sec_chrom, _s0, _e1, _step, _span, _typ, _r, cnt = struct.unpack_from("<IIIIIBBH", raw, 0)
+        if sec_chrom != cid:
+            continue
+        rec = np.frombuffer(raw, dtype=[("s", "<u4"), ("e", "<u4"), ("v", "<f4")], count=cnt, offset=24)
+        keep = (rec["s"] < end) & (rec["e"] > start)
+        out_s.append(rec["s"][keep].astype(np.int64))
+        out_e.append(rec["e"][keep].astype(np.int64))
+        out_v.append(rec["v"][keep])
+    if not out_s:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float32)
+    return np.concatenate(out_s), np.concatenate(out_e), np.concatenate(out_v)

@@ -324,3 +324,24 @@ def test_chromosome_tree_with_many_contigs(tmp_path):
     assert got["chroms"] == sizes
     for c, s in pick:
         np.testing.assert_array_equal(got["tracks"][c][1], [s])
+
+
+def test_region_queries_descend_the_index(tmp_path):
+    rng = np.random.default_rng(5)
+    sizes = [("chrA", 40_000_000), ("chrB", 10_000_000), ("chrC", 1_000_000)]
+    tracks = [(c, *_track(rng, s, 100, s // 100, gaps=True)) for c, s in sizes]
+    path = _write(tmp_path, tracks, sizes=sizes, zoom_levels=1)
+    by_name = {c: (s, e, v) for c, s, e, v in tracks}
+    for _ in range(60):
+        c, size = sizes[int(rng.integers(3))]
+        a = int(rng.integers(0, size - 1))
+        b = min(size, a + int(10 ** rng.uniform(0, 6)))
+        s, e, v = by_name[c]
+        keep = (s < b) & (e > a)
+        gs, ge, gv = bigwig.query_bigwig(path, c, a, b)
+        np.testing.assert_array_equal(gs, s[keep])
+        np.testing.assert_array_equal(ge, e[keep])
+        np.testing.assert_array_equal(gv, v[keep])
+    assert len(bigwig.query_bigwig(path, "chrC", 0, 1_000_000)[0]) == len(by_name["chrC"][0])
+    with pytest.raises(KeyError):
+        bigwig.query_bigwig(path, "chrD", 0, 10)
